@@ -1,0 +1,71 @@
+"""Seeded parity cases shared by oracle/gen_golden.py and tests/ (TEST INFRASTRUCTURE).
+
+Every case is fully determined by integers: weights come from ``arch.make_state_dict(specs, seed)``,
+graphs/inputs from ``echoscene_b200.synth``.  Fixtures under tests/golden/ hold only the *reference's
+outputs* for these cases.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from echoscene_b200 import arch, synth
+
+WEIGHT_SEED_GCN = 10
+WEIGHT_SEED_LAYOUT = 11
+WEIGHT_SEED_SHAPE = 12
+
+
+@dataclass
+class GraphCase:
+    name: str
+    n_nodes: int
+    n_triples: int
+    seed: int
+
+
+GCN_CASE = GraphCase("gcn_layout_n8", 8, 32, 1)
+LAYOUT_CASE = GraphCase("layout_step_n8", 8, 32, 1)          # BASELINE config 1 graph
+LAYOUT_CHAIN_STEPS = 10                                        # config 1: 10 DDPM steps
+SHAPE_CASE = GraphCase("shape_step_n4", 4, 8, 4)
+SHAPE_CHAIN_STEPS = 3                                          # first 3 iterations of the S=100 DDIM schedule
+SHAPE_CHAIN_CASE = GraphCase("shape_chain_n3", 3, 4, 5)
+
+
+def layout_cfg() -> arch.UNet1DConfig:
+    return arch.UNet1DConfig()
+
+
+def shape_cfg() -> arch.UNet3DConfig:
+    return arch.UNet3DConfig()
+
+
+def gcn_inputs(case: GraphCase, cfg: arch.GCNConfig):
+    g = synth.make_scene_graph(case.n_nodes, case.n_triples, case.seed)
+    gen = torch.Generator().manual_seed(case.seed + 100)
+    obj = torch.randn(case.n_nodes, cfg.input_dim_obj, generator=gen)
+    pred = torch.randn(case.n_triples, cfg.input_dim_pred, generator=gen)
+    return g, obj, pred
+
+
+def layout_step_inputs(case: GraphCase, cfg: arch.UNet1DConfig):
+    g = synth.make_scene_graph(case.n_nodes, case.n_triples, case.seed)
+    obj_embed, x = synth.layout_inputs(case.n_nodes, case.seed + 200, cfg.obj_embed_dim, cfg.in_channels)
+    t = torch.tensor([999, 500, 3, 0, 17, 250, 731, 64][: case.n_nodes], dtype=torch.int64)
+    return g, obj_embed, x, t
+
+
+def layout_chain_inputs(case: GraphCase, cfg: arch.UNet1DConfig, steps: int):
+    g = synth.make_scene_graph(case.n_nodes, case.n_triples, case.seed)
+    obj_embed, x_T = synth.layout_inputs(case.n_nodes, case.seed + 300, cfg.obj_embed_dim, cfg.in_channels)
+    gen = torch.Generator().manual_seed(case.seed + 301)
+    noises = [torch.randn(case.n_nodes, cfg.in_channels, generator=gen) for _ in range(steps)]
+    return g, obj_embed, x_T, noises
+
+
+def shape_step_inputs(case: GraphCase, cfg: arch.UNet3DConfig, same_noise: bool = False):
+    g = synth.make_scene_graph(case.n_nodes, case.n_triples, case.seed)
+    uc, x = synth.shape_inputs(case.n_nodes, case.seed + 400, cfg.context_dim, same_noise=same_noise)
+    t = torch.tensor([991, 501, 1, 251, 11, 741, 331, 91][: case.n_nodes], dtype=torch.int64)
+    return g, uc, x, t
