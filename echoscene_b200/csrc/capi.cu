@@ -1,0 +1,368 @@
+// extern "C" boundary of libechoscene_b200 (include/echoscene_b200.h).  Exceptions never cross it: every entry
+// point returns a code and leaves the message in thread-local storage.
+#include "unet.cuh"
+
+#include <functional>
+#include <algorithm>
+
+struct echo_layout;
+struct echo_shape;
+
+namespace echo {
+const char* last_error();
+echo_layout* layout_create(const echo_layout_desc_t*, const echo_weight_t*, int);
+void layout_destroy(echo_layout*);
+void layout_forward(echo_layout*, const echo_graph*, const float*, const float*, const int64_t*, float*, cudaStream_t);
+void layout_step(echo_layout*, const echo_graph*, const float*, const float*, int, const float*, float*, cudaStream_t);
+const std::vector<float>& layout_table(const echo_layout*);
+echo_shape* shape_create(const echo_shape_desc_t*, const echo_weight_t*, int);
+void shape_destroy(echo_shape*);
+void shape_forward(echo_shape*, const echo_graph*, const float*, const float*, const int64_t*, float*, cudaStream_t);
+void shape_step(echo_shape*, const echo_graph*, const float*, const float*, int, float*, cudaStream_t);
+void shape_embed(echo_shape*, const float*, int, float*, cudaStream_t);
+void shape_trunk(echo_shape*, const echo_graph*, const float*, int, int, const float*, const float*, const int64_t*, int, float*,
+                 cudaStream_t);
+const float* shape_latent(const echo_shape*);
+int shape_context_dim(const echo_shape*);
+void shape_tables(const echo_shape*, const std::vector<float>**, const std::vector<int32_t>**);
+bool conv3d_small_cout_supported(int cin, int cout, int taps);
+void conv3d_small_cout(const Act& x, const float* wt, const float* bias, int cout, float* out, cudaStream_t s);
+
+static int guard(const std::function<void()>& f) {
+  try {
+    f();
+    return ECHO_OK;
+  } catch (const Error& e) {
+    set_last_error(e.what());
+    return e.code;
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return ECHO_ERR_INVALID;
+  } catch (...) {
+    set_last_error("unknown error");
+    return ECHO_ERR_INVALID;
+  }
+}
+
+// scratch for the single-operator entry points (tests / profiling only): grown on demand, freed at exit
+struct Scratch {
+  void* p = nullptr;
+  size_t cap = 0;
+  void* get(size_t bytes) {
+    if (bytes > cap) {
+      if (p) { cudaDeviceSynchronize(); cudaFree(p); }
+      ECHO_CUDA(cudaMalloc(&p, bytes));
+      cap = bytes;
+    }
+    return p;
+  }
+};
+static Scratch g_scratch[4];
+
+}  // namespace echo
+
+using namespace echo;
+
+extern "C" {
+
+int echo_version(void) { return ECHO_ABI_VERSION; }
+const char* echo_last_error(void) { return echo::last_error(); }
+int echo_has_tcgen05(void) {
+  int r = 0;
+  guard([&] { r = tc_available() ? 1 : 0; });
+  return r;
+}
+int64_t echo_launch_count(void) { return g_launches; }
+void echo_launch_count_reset(void) { g_launches = 0; }
+
+int echo_graph_create(echo_graph_t** out, const int64_t* triples_dev, int32_t T, int32_t N, void* stream) {
+  return guard([&] {
+    ECHO_CHECK(out && N >= 0 && T >= 0 && (triples_dev || T == 0), "graph_create: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<int64_t> h((size_t)T * 3);
+    if (T) {
+      ECHO_CUDA(cudaMemcpyAsync(h.data(), triples_dev, sizeof(int64_t) * 3 * T, cudaMemcpyDeviceToHost, s));
+      ECHO_CUDA(cudaStreamSynchronize(s));
+    }
+    std::vector<int> si(T), oi(T), off(N + 1, 0), items((size_t)2 * T);
+    for (int t = 0; t < T; ++t) {
+      const int64_t a = h[3 * t], b = h[3 * t + 2];
+      // the reference would raise an index error (graph.py:146-147)
+      ECHO_CHECK(a >= 0 && a < N && b >= 0 && b < N, "graph_create: triple %d has node index out of range [0, %d)", t, N);
+      si[t] = (int)a;
+      oi[t] = (int)b;
+      off[a + 1]++;
+      off[b + 1]++;
+    }
+    for (int n = 0; n < N; ++n) off[n + 1] += off[n];
+    std::vector<int> fill(off.begin(), off.end() - 1);
+    // subject roles first (ascending t), then object roles: the order scatter_add visits them (graph.py:176-177)
+    for (int t = 0; t < T; ++t) items[fill[si[t]]++] = t * 2 + 0;
+    for (int t = 0; t < T; ++t) items[fill[oi[t]]++] = t * 2 + 1;
+    echo_graph* g = new echo_graph();
+    g->n_nodes = N;
+    g->n_triples = T;
+    auto up = [&](const void* src, size_t bytes) {
+      void* d = nullptr;
+      ECHO_CUDA(cudaMalloc(&d, bytes ? bytes : 16));
+      if (bytes) ECHO_CUDA(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+      return d;
+    };
+    g->triples = (int64_t*)up(h.data(), sizeof(int64_t) * 3 * T);
+    g->s_idx = (int*)up(si.data(), sizeof(int) * T);
+    g->o_idx = (int*)up(oi.data(), sizeof(int) * T);
+    g->node_off = (int*)up(off.data(), sizeof(int) * (N + 1));
+    g->node_items = (int*)up(items.data(), sizeof(int) * 2 * T);
+    *out = g;
+  });
+}
+
+void echo_graph_destroy(echo_graph_t* g) {
+  if (!g) return;
+  cudaFree(g->triples);
+  cudaFree(g->s_idx);
+  cudaFree(g->o_idx);
+  cudaFree(g->node_off);
+  cudaFree(g->node_items);
+  delete g;
+}
+
+int echo_gather_rows(const float* obj, const int64_t* idx, int64_t n_idx, int64_t n_rows, int64_t dim, float* out, void* stream) {
+  return guard([&] {
+    ECHO_CHECK(obj && out && (idx || n_idx == 0) && dim > 0 && n_rows >= 0, "gather_rows: bad arguments");
+    gather_rows(obj, idx, n_idx, dim, out, (cudaStream_t)stream);
+  });
+}
+
+int echo_gcn_create(echo_gcn_t** out, const echo_gcn_desc_t* desc, const echo_weight_t* weights, int32_t n_weights) {
+  return guard([&] {
+    ECHO_CHECK(out && desc, "gcn_create: null argument");
+    echo_gcn* h = new echo_gcn();
+    try {
+      WeightMap wm;
+      wm.load(weights, n_weights);
+      echo_gcn_desc_t d = *desc;
+      if (d.max_triples < 1) d.max_triples = 1;
+      h->net.create(wm, "", d, h->pool);
+    } catch (...) {
+      h->pool.destroy();
+      delete h;
+      throw;
+    }
+    *out = h;
+  });
+}
+
+int echo_gcn_forward(echo_gcn_t* h, const echo_graph_t* g, const float* obj, const float* pred, float* obj_out, float* pred_out,
+                     void* stream) {
+  return guard([&] {
+    ECHO_CHECK(h && g && obj && (pred || g->n_triples == 0) && obj_out, "gcn_forward: null argument");
+    h->net.forward(g, obj, pred, obj_out, pred_out, (cudaStream_t)stream);
+  });
+}
+
+void echo_gcn_destroy(echo_gcn_t* h) {
+  if (!h) return;
+  h->pool.destroy();
+  delete h;
+}
+
+int echo_layout_create(echo_layout_t** out, const echo_layout_desc_t* desc, const echo_weight_t* weights, int32_t n_weights) {
+  return guard([&] {
+    ECHO_CHECK(out, "layout_create: null out");
+    *out = layout_create(desc, weights, n_weights);
+  });
+}
+int echo_layout_forward(echo_layout_t* h, const echo_graph_t* g, const float* box_t, const float* obj_embed, const int64_t* t,
+                        float* eps_out, void* stream) {
+  return guard([&] {
+    ECHO_CHECK(h && g && box_t && obj_embed && t && eps_out, "layout_forward: null argument");
+    layout_forward(h, g, box_t, obj_embed, t, eps_out, (cudaStream_t)stream);
+  });
+}
+int echo_layout_step(echo_layout_t* h, const echo_graph_t* g, const float* x_t, const float* obj_embed, int32_t t, const float* noise,
+                     float* x_prev, void* stream) {
+  return guard([&] {
+    ECHO_CHECK(h && g && x_t && obj_embed && noise && x_prev, "layout_step: null argument");
+    layout_step(h, g, x_t, obj_embed, t, noise, x_prev, (cudaStream_t)stream);
+  });
+}
+void echo_layout_destroy(echo_layout_t* h) { layout_destroy(h); }
+int echo_layout_schedule(const echo_layout_t* h, float* host_out) {
+  return guard([&] {
+    ECHO_CHECK(h && host_out, "layout_schedule: null argument");
+    const std::vector<float>& t = layout_table(h);
+    std::copy(t.begin(), t.end(), host_out);
+  });
+}
+
+int echo_shape_create(echo_shape_t** out, const echo_shape_desc_t* desc, const echo_weight_t* weights, int32_t n_weights) {
+  return guard([&] {
+    ECHO_CHECK(out, "shape_create: null out");
+    *out = shape_create(desc, weights, n_weights);
+  });
+}
+int echo_shape_forward(echo_shape_t* h, const echo_graph_t* g, const float* x, const float* obj_embed, const int64_t* t, float* eps_out,
+                       void* stream) {
+  return guard([&] {
+    ECHO_CHECK(h && g && x && obj_embed && t && eps_out, "shape_forward: null argument");
+    shape_forward(h, g, x, obj_embed, t, eps_out, (cudaStream_t)stream);
+  });
+}
+int echo_shape_step(echo_shape_t* h, const echo_graph_t* g, const float* x_t, const float* obj_embed, int32_t ddim_index, float* x_prev,
+                    void* stream) {
+  return guard([&] {
+    ECHO_CHECK(h && g && x_t && obj_embed && x_prev, "shape_step: null argument");
+    shape_step(h, g, x_t, obj_embed, ddim_index, x_prev, (cudaStream_t)stream);
+  });
+}
+int echo_shape_embed(echo_shape_t* h, const float* x_local, int32_t n_local, float* codes_out, void* stream) {
+  return guard([&] {
+    ECHO_CHECK(h && (x_local || n_local == 0) && (codes_out || n_local == 0), "shape_embed: null argument");
+    shape_embed(h, x_local, n_local, codes_out, (cudaStream_t)stream);
+  });
+}
+int echo_shape_trunk(echo_shape_t* h, const echo_graph_t* g, const float* x_local, int32_t obj_begin, int32_t n_local,
+                     const float* codes_all, const float* obj_embed_all, const int64_t* t_all, int32_t ddim_index, float* out_local,
+                     void* stream) {
+  return guard([&] {
+    ECHO_CHECK(h && g && codes_all && obj_embed_all && (n_local == 0 || (x_local && out_local)), "shape_trunk: null argument");
+    shape_trunk(h, g, x_local, obj_begin, n_local, codes_all, obj_embed_all, t_all, ddim_index, out_local, (cudaStream_t)stream);
+  });
+}
+int echo_shape_latent(const echo_shape_t* h, int32_t n_nodes, float* out_dev, void* stream) {
+  return guard([&] {
+    ECHO_CHECK(h && out_dev && n_nodes >= 0, "shape_latent: bad arguments");
+    ECHO_CUDA(cudaMemcpyAsync(out_dev, shape_latent(h), sizeof(float) * (size_t)n_nodes * shape_context_dim(h), cudaMemcpyDeviceToDevice,
+                              (cudaStream_t)stream));
+  });
+}
+void echo_shape_destroy(echo_shape_t* h) { shape_destroy(h); }
+int echo_shape_schedule(const echo_shape_t* h, float* host_coef_out, int32_t* host_ts_out) {
+  return guard([&] {
+    ECHO_CHECK(h, "shape_schedule: null handle");
+    const std::vector<float>* c;
+    const std::vector<int32_t>* t;
+    shape_tables(h, &c, &t);
+    if (host_coef_out) std::copy(c->begin(), c->end(), host_coef_out);
+    if (host_ts_out) std::copy(t->begin(), t->end(), host_ts_out);
+  });
+}
+
+// ---- single operators ---------------------------------------------------------------------------------------------
+int echo_op_conv3d(const float* x, int32_t n, int32_t d, int32_t h, int32_t w, int32_t cin, const float* weight, const float* bias,
+                   int32_t cout, int32_t ksize, int32_t stride_d, int32_t stride_hw, float* out, int32_t precision, void* stream) {
+  return guard([&] {
+    ECHO_CHECK(x && weight && out && (ksize == 1 || ksize == 3) && stride_d == 1 && (stride_hw == 1 || stride_hw == 2),
+               "op_conv3d: unsupported arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int taps = ksize * ksize * ksize;
+    const size_t wn = (size_t)cout * cin * taps;
+    float* wr = (float*)g_scratch[0].get(wn * sizeof(float));
+    if (taps == 1) ECHO_CUDA(cudaMemcpyAsync(wr, weight, wn * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    else repack_conv_weight(weight, cout, cin, taps, wr, s);
+    const int pad = ksize / 2;
+    GemmArgs g;
+    g.n = n; g.d = d; g.h = h; g.w = w; g.cin = cin; g.lda = cin;
+    g.od = d; g.oh = (h + 2 * pad - ksize) / stride_hw + 1; g.ow = (w + 2 * pad - ksize) / stride_hw + 1;
+    g.kd = g.kh = g.kw = ksize; g.sh = g.sw = stride_hw; g.pd = g.ph = g.pw = pad;
+    g.w_stride_n = (int64_t)taps * cin; g.cout = cout; g.bias = bias; g.out = out; g.ldo = cout;
+    const int64_t rows_in = (int64_t)n * d * h * w, rows_out = g.rows_out();
+    if (precision == ECHO_PREC_BF16) {
+      ECHO_CHECK(tc_available(), "op_conv3d: bf16 precision needs the tcgen05 kernels");
+      __nv_bfloat16* xb = (__nv_bfloat16*)g_scratch[1].get((size_t)rows_in * cin * 2);
+      __nv_bfloat16* wb = (__nv_bfloat16*)g_scratch[2].get(wn * 2);
+      __nv_bfloat16* ob = (__nv_bfloat16*)g_scratch[3].get((size_t)rows_out * cout * 2);
+      convert(x, F32, xb, BF16, rows_in * cin, s);
+      convert(wr, F32, wb, BF16, (int64_t)wn, s);
+      g.A = xb; g.a_dt = BF16; g.W = wb; g.w_dt = BF16; g.out = ob; g.out_dt = BF16;
+      ECHO_CHECK(gemm_tc_supported(g), "op_conv3d: shape not supported by the tcgen05 kernel");
+      gemm_tc(g, s);
+      convert(ob, BF16, out, F32, rows_out * cout, s);
+    } else if (ksize == 3 && stride_hw == 1 && conv3d_small_cout_supported(cin, cout, taps)) {
+      Act xa;
+      xa.p = (void*)x; xa.dt = F32; xa.n = n; xa.d = d; xa.h = h; xa.w = w; xa.c = cin;
+      conv3d_small_cout(xa, wr, bias, cout, out, s);
+    } else {
+      g.A = x; g.W = wr;
+      gemm_simt(g, s);
+    }
+  });
+}
+
+int echo_op_linear(const float* x, int64_t rows, int32_t cin, const float* weight, const float* bias, int32_t cout, float* out,
+                   int32_t precision, void* stream) {
+  return guard([&] {
+    ECHO_CHECK(x && weight && out && rows >= 0, "op_linear: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (precision == ECHO_PREC_BF16) {
+      ECHO_CHECK(tc_available(), "op_linear: bf16 precision needs the tcgen05 kernels");
+      __nv_bfloat16* xb = (__nv_bfloat16*)g_scratch[1].get((size_t)rows * cin * 2);
+      __nv_bfloat16* wb = (__nv_bfloat16*)g_scratch[2].get((size_t)cout * cin * 2);
+      __nv_bfloat16* ob = (__nv_bfloat16*)g_scratch[3].get((size_t)rows * cout * 2);
+      convert(x, F32, xb, BF16, rows * cin, s);
+      convert(weight, F32, wb, BF16, (int64_t)cout * cin, s);
+      GemmArgs g;
+      g.A = xb; g.a_dt = BF16; g.n = 1; g.w = (int)rows; g.ow = (int)rows; g.cin = cin; g.lda = cin;
+      g.W = wb; g.w_dt = BF16; g.w_stride_n = cin; g.cout = cout; g.bias = bias; g.out = ob; g.out_dt = BF16; g.ldo = cout;
+      ECHO_CHECK(gemm_tc_supported(g), "op_linear: shape not supported by the tcgen05 kernel");
+      gemm_tc(g, s);
+      convert(ob, BF16, out, F32, rows * cout, s);
+      return;
+    }
+    LinArgs a;
+    a.X = x; a.ldx = cin; a.M = (int)rows; a.K = cin; a.nout = cout; a.W = weight; a.bias = bias; a.Y = out; a.ldy = cout;
+    linear_auto(a, s);
+  });
+}
+
+int echo_op_group_norm(const float* x, int32_t n, int64_t voxels, int32_t c, int32_t groups, const float* gamma, const float* beta,
+                       float eps, int32_t silu, float* out, void* stream) {
+  return guard([&] {
+    ECHO_CHECK(x && out && gamma && beta && groups == 32, "op_group_norm: bad arguments (groups must be 32)");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (voxels == 1) {
+      gn_rows(x, n, c, groups, gamma, beta, eps, silu != 0, out, s);
+      return;
+    }
+    Act xa, oa;
+    xa.p = (void*)x; xa.n = n; xa.d = 1; xa.h = 1; xa.w = (int)voxels; xa.c = c;
+    oa = xa;
+    oa.p = out;
+    float* ws = (float*)g_scratch[0].get((gn_partial_floats(xa, groups) + (size_t)n * groups * 2) * sizeof(float));
+    float* stats = ws + gn_partial_floats(xa, groups);
+    gn_stats(xa, groups, eps, stats, ws, s);
+    gn_apply(xa, stats, gamma, beta, groups, silu != 0, oa, s);
+  });
+}
+
+int echo_op_layer_norm(const float* x, int64_t rows, int32_t c, const float* gamma, const float* beta, float eps, float* out,
+                       void* stream) {
+  return guard([&] {
+    ECHO_CHECK(x && out && gamma && beta, "op_layer_norm: null argument");
+    layer_norm(x, F32, rows, c, gamma, beta, eps, out, F32, (cudaStream_t)stream);
+  });
+}
+
+int echo_op_attention(const float* qkv, int32_t n, int32_t tokens, int32_t heads, int32_t dh, float* out, int32_t precision,
+                      void* stream) {
+  return guard([&] {
+    ECHO_CHECK(qkv && out, "op_attention: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int C = heads * dh;
+    const int64_t rows = (int64_t)n * tokens;
+    if (precision == ECHO_PREC_BF16) {
+      ECHO_CHECK(tc_available(), "op_attention: bf16 precision needs sm_100a");
+      __nv_bfloat16* qb = (__nv_bfloat16*)g_scratch[1].get((size_t)rows * 3 * C * 2);
+      __nv_bfloat16* ob = (__nv_bfloat16*)g_scratch[3].get((size_t)rows * C * 2);
+      convert(qkv, F32, qb, BF16, rows * 3 * C, s);
+      attention_bf16(qb, n, tokens, heads, dh, ob, s);
+      convert(ob, BF16, out, F32, rows * C, s);
+      return;
+    }
+    float* ws = (float*)g_scratch[0].get(attention_f32_ws_floats(n, tokens, heads) * sizeof(float));
+    attention_f32(qkv, n, tokens, heads, dh, ws, out, s);
+  });
+}
+
+}  // extern "C"

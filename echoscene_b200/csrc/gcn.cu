@@ -1,0 +1,247 @@
+// GraphTripleConv "echo" message passing (model/graph.py:124-211) as B200 kernels.
+//
+// Reference per layer: gather obj[s], obj[o] (T x Din each) -> cat with pred -> net1 (Linear, BN, ReLU) x2 ->
+// split -> scatter_add into nodes -> /degree -> net2 -> + residual projections.
+//
+// Here (eval mode, BatchNorm folded into the Linear at create time):
+//   1. PROJECT NODES FIRST: [Ps | Po] = obj @ [W1_s ; W1_o]^T  (N rows instead of T; net1's first Linear is
+//      linear in the concat, so W1 [s|p|o] columns are applied before the gather),  Pp = pred @ W1_p^T.
+//   2. edge_combine: one WARP PER EDGE reads rows Ps[s[t]], Po[o[t]], Pp[t] (H = 256 floats = two coalesced
+//      16-byte loads per lane each), adds the folded bias, ReLU -> h1[t].  The gather is a pure row copy of
+//      projected features; indices come from the CSR built once per graph (edges are constant over the chain).
+//   3. t2 = ReLU(h1 @ W2'^T + b2')  (T x (2H+Dp)).
+//   4. node_pool: one warp-group per node walks its CSR item list in a FIXED order (all subject roles by
+//      ascending t, then object roles) and averages — deterministic, no float atomics, same summation order as
+//      the reference's CPU scatter_add.
+//   5. net2 (two few-row linears) + residual projections (graph.py:205-209).
+#include "model.cuh"
+
+#include <algorithm>
+
+namespace echo {
+namespace {
+
+__global__ void edge_combine_kernel(const float* __restrict__ pso, const float* __restrict__ pp, const float* __restrict__ b1,
+                                    const int* __restrict__ s_idx, const int* __restrict__ o_idx, int T, int H,
+                                    float* __restrict__ h1) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (t >= T) return;
+  const float4* ps = reinterpret_cast<const float4*>(pso + (int64_t)s_idx[t] * 2 * H);
+  const float4* po = reinterpret_cast<const float4*>(pso + (int64_t)o_idx[t] * 2 * H + H);
+  const float4* pq = reinterpret_cast<const float4*>(pp + (int64_t)t * H);
+  const float4* bb = reinterpret_cast<const float4*>(b1);
+  float4* out = reinterpret_cast<float4*>(h1 + (int64_t)t * H);
+  for (int q = lane; q < H / 4; q += 32) {
+    const float4 a = __ldg(ps + q), b = __ldg(pq + q), c = __ldg(po + q), d = __ldg(bb + q);
+    float4 r;
+    r.x = fmaxf(((a.x + b.x) + c.x) + d.x, 0.f);
+    r.y = fmaxf(((a.y + b.y) + c.y) + d.y, 0.f);
+    r.z = fmaxf(((a.z + b.z) + c.z) + d.z, 0.f);
+    r.w = fmaxf(((a.w + b.w) + c.w) + d.w, 0.f);
+    out[q] = r;
+  }
+}
+
+// pooled[n, :] = (sum over items of t2[t, role ? H+Dp : 0 ...]) / max(count, 1)     (graph.py:161-199)
+__global__ void node_pool_kernel(const float* __restrict__ t2, int ld, int H, int off_o, const int* __restrict__ node_off,
+                                 const int* __restrict__ node_items, int N, float* __restrict__ pooled) {
+  const int n = blockIdx.x;
+  if (n >= N) return;
+  const int beg = node_off[n], end = node_off[n + 1];
+  const float cnt = fmaxf((float)(end - beg), 1.f);
+  for (int q = threadIdx.x; q < H / 4; q += blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = beg; i < end; ++i) {
+      const int item = node_items[i], t = item >> 1, role = item & 1;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(t2 + (int64_t)t * ld + (role ? off_o : 0)) + q);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    acc.x /= cnt; acc.y /= cnt; acc.z /= cnt; acc.w /= cnt;
+    reinterpret_cast<float4*>(pooled + (int64_t)n * H)[q] = acc;
+  }
+}
+
+Mat folded_linear(const WeightMap& wm, const std::string& lin, const std::string& bn, int nout, int K, float eps, DevPool& pool,
+                  cudaStream_t s) {
+  const WView& w = wm.get(lin + ".weight", {nout, K});
+  const WView& b = wm.get(lin + ".bias", {nout});
+  Mat m;
+  m.nout = nout;
+  m.K = K;
+  float* wo = pool.alloc_n<float>((size_t)nout * K);
+  float* bo = pool.alloc_n<float>(nout);
+  if (wm.has(bn + ".running_mean")) {
+    fold_bn(w.p, b.p, wm.get(bn + ".weight", {nout}).p, wm.get(bn + ".bias", {nout}).p, wm.get(bn + ".running_mean", {nout}).p,
+            wm.get(bn + ".running_var", {nout}).p, eps, nout, K, wo, bo, s);
+  } else {
+    ECHO_CUDA(cudaMemcpyAsync(wo, w.p, sizeof(float) * nout * K, cudaMemcpyDeviceToDevice, s));
+    ECHO_CUDA(cudaMemcpyAsync(bo, b.p, sizeof(float) * nout, cudaMemcpyDeviceToDevice, s));
+  }
+  m.w = wo;
+  m.b = bo;
+  return m;
+}
+
+Mat plain_linear(const WeightMap& wm, const std::string& lin, int nout, int K, DevPool& pool, cudaStream_t s) {
+  const WView& w = wm.get(lin + ".weight", {nout, K});
+  const WView& b = wm.get(lin + ".bias", {nout});
+  Mat m;
+  m.nout = nout;
+  m.K = K;
+  float* wo = pool.alloc_n<float>((size_t)nout * K);
+  float* bo = pool.alloc_n<float>(nout);
+  ECHO_CUDA(cudaMemcpyAsync(wo, w.p, sizeof(float) * nout * K, cudaMemcpyDeviceToDevice, s));
+  ECHO_CUDA(cudaMemcpyAsync(bo, b.p, sizeof(float) * nout, cudaMemcpyDeviceToDevice, s));
+  m.w = wo;
+  m.b = bo;
+  return m;
+}
+
+}  // namespace
+
+// Few-row kernel up to 64 rows, tiled SIMT GEMM above (batched scene graphs: hundreds of nodes / thousands of edges).
+void linear_auto(const LinArgs& a, cudaStream_t s) {
+  if (a.M <= 64 || a.in_act != 0 || a.act == 2) {
+    linear_rows(a, s);
+    return;
+  }
+  GemmArgs g;
+  g.A = a.X; g.n = 1; g.w = a.M; g.ow = a.M; g.cin = a.K; g.lda = a.ldx;
+  g.W = a.W; g.w_dt = a.w_dt; g.w_stride_n = a.ldw ? a.ldw : a.K; g.cout = a.nout;
+  g.bias = a.bias; g.act = a.act;
+  g.out = a.Y; g.ldo = a.ldy;
+  if (a.res && a.act == 0) {
+    g.res = a.res; g.ld_res = a.ld_res;
+    gemm_simt(g, s);
+  } else {
+    gemm_simt(g, s);
+    // the residual is added AFTER the activation (graph.py:203-206): second pass
+    if (a.res) add_rowvec(a.Y, F32, a.M, a.nout, a.res, a.ld_res, 1, s);
+  }
+}
+
+void Gcn::create(const WeightMap& wm, const std::string& prefix, const echo_gcn_desc_t& d, DevPool& pool) {
+  ECHO_CHECK(d.num_layers > 0 && d.hidden_dim % 4 == 0 && d.input_dim_obj % 4 == 0 && d.input_dim_pred % 4 == 0,
+             "gcn: dims must be multiples of 4");
+  cudaStream_t s = 0;
+  max_nodes = d.max_nodes;
+  max_triples = d.max_triples;
+  dp = d.input_dim_pred;
+  H = d.hidden_dim;
+  const float eps = d.bn_eps > 0 ? d.bn_eps : 1e-5f;
+  max_d = d.input_dim_obj;
+  layers.clear();
+  for (int i = 0; i < d.num_layers; ++i) {
+    GcnLayer L;
+    L.din = d.input_dim_obj;
+    L.dp = dp;
+    L.H = H;
+    const bool last = d.output_dim > 0 && i >= d.num_layers - 1;   // graph.py:239-243
+    L.dout = last ? d.output_dim : d.input_dim_obj;
+    max_d = std::max(max_d, L.dout);
+    const std::string p = prefix + "gconvs." + std::to_string(i) + ".";
+    const int k1 = 2 * L.din + dp;
+    const bool bn = wm.has(p + "net1.1.running_mean");
+    const int st = bn ? 3 : 2;   // build_mlp index layout (layers.py:21-38)
+    Mat w1 = folded_linear(wm, p + "net1.0", p + "net1.1", H, k1, eps, pool, s);
+    // split net1.0 by input block: [subject | predicate | object]
+    float* wso = pool.alloc_n<float>((size_t)2 * H * L.din);
+    copy_cols(w1.w, k1, H, L.din, wso, L.din, s);
+    copy_cols(w1.w + L.din + dp, k1, H, L.din, wso + (size_t)H * L.din, L.din, s);
+    float* wp = pool.alloc_n<float>((size_t)H * dp);
+    copy_cols(w1.w + L.din, k1, H, dp, wp, dp, s);
+    L.w_so.w = wso; L.w_so.nout = 2 * H; L.w_so.K = L.din;
+    L.w_p.w = wp; L.w_p.nout = H; L.w_p.K = dp;
+    L.b1 = w1.b;
+    L.w2 = folded_linear(wm, p + "net1." + std::to_string(st), p + "net1." + std::to_string(st + 1), 2 * H + dp, H, eps, pool, s);
+    L.w3 = folded_linear(wm, p + "net2.0", p + "net2.1", H, H, eps, pool, s);
+    L.w4 = folded_linear(wm, p + "net2." + std::to_string(st), p + "net2." + std::to_string(st + 1), L.dout, H, eps, pool, s);
+    L.residual = wm.has(p + "linear_projection.weight");
+    if (L.residual) {
+      L.proj = plain_linear(wm, p + "linear_projection", L.dout, L.din, pool, s);
+      L.projp = plain_linear(wm, p + "linear_projection_pred", dp, dp, pool, s);
+    }
+    if (i + 1 < d.num_layers) ECHO_CHECK(L.dout == d.input_dim_obj, "gcn: inner layer width mismatch");
+    layers.push_back(L);
+  }
+  const size_t N = max_nodes, T = max_triples;
+  pso = pool.alloc_n<float>(N * 2 * H);
+  pp = pool.alloc_n<float>(T * H);
+  h1 = pool.alloc_n<float>(T * H);
+  t2 = pool.alloc_n<float>(T * (2 * H + dp));
+  pooled = pool.alloc_n<float>(N * H);
+  n1 = pool.alloc_n<float>(N * H);
+  proj = pool.alloc_n<float>(N * max_d);
+  for (int i = 0; i < 2; ++i) {
+    obj_pp[i] = pool.alloc_n<float>(N * max_d);
+    pred_pp[i] = pool.alloc_n<float>(T * dp);
+  }
+  ECHO_CUDA(cudaStreamSynchronize(s));
+}
+
+void Gcn::forward(const echo_graph* g, const float* obj, const float* pred, float* obj_out, float* pred_out, cudaStream_t s) {
+  ECHO_CHECK(g, "gcn: null graph");
+  const int N = g->n_nodes, T = g->n_triples;
+  ECHO_CHECK(N <= max_nodes && T <= max_triples, "gcn: graph (%d nodes, %d triples) exceeds handle capacity (%d, %d)", N, T,
+             max_nodes, max_triples);
+  const float* cur_obj = obj;
+  const float* cur_pred = pred;
+  for (size_t li = 0; li < layers.size(); ++li) {
+    const GcnLayer& L = layers[li];
+    const bool lastl = li + 1 == layers.size();
+    float* nobj = lastl && obj_out ? obj_out : obj_pp[li & 1];
+    float* npred = lastl && pred_out ? pred_out : pred_pp[li & 1];
+    LinArgs a;
+    // 1. node / predicate projections of net1.0
+    a.X = cur_obj; a.ldx = L.din; a.M = N; a.K = L.din; a.nout = 2 * H; a.W = L.w_so.w; a.Y = pso; a.ldy = 2 * H;
+    linear_auto(a, s);
+    if (T > 0) {
+      a = LinArgs();
+      a.X = cur_pred; a.ldx = dp; a.M = T; a.K = dp; a.nout = H; a.W = L.w_p.w; a.Y = pp; a.ldy = H;
+      linear_auto(a, s);
+      // 2. warp-per-edge gather + combine
+      edge_combine_kernel<<<cdiv((int64_t)T * 32, 256), 256, 0, s>>>(pso, pp, L.b1, g->s_idx, g->o_idx, T, H, h1);
+      ECHO_LAUNCH_CHECK();
+      // 3. second Linear of net1
+      a = LinArgs();
+      a.X = h1; a.ldx = H; a.M = T; a.K = H; a.nout = 2 * H + dp; a.W = L.w2.w; a.bias = L.w2.b; a.act = 1; a.Y = t2;
+      a.ldy = 2 * H + dp;
+      linear_auto(a, s);
+    }
+    // 4. deterministic segmented mean
+    node_pool_kernel<<<N, 64, 0, s>>>(t2, 2 * H + dp, H, H + dp, g->node_off, g->node_items, N, pooled);
+    ECHO_LAUNCH_CHECK();
+    // new_p = t2[:, H:H+dp] + linear_projection_pred(pred)
+    if (T > 0) {
+      if (L.residual) {
+        a = LinArgs();
+        a.X = cur_pred; a.ldx = dp; a.M = T; a.K = dp; a.nout = dp; a.W = L.projp.w; a.bias = L.projp.b;
+        a.res = t2 + H; a.ld_res = 2 * H + dp; a.Y = npred; a.ldy = dp;
+        linear_auto(a, s);
+      } else {
+        copy_cols(t2 + H, 2 * H + dp, T, dp, npred, dp, s);
+      }
+    }
+    // 5. net2 + residual
+    a = LinArgs();
+    a.X = pooled; a.ldx = H; a.M = N; a.K = H; a.nout = H; a.W = L.w3.w; a.bias = L.w3.b; a.act = 1; a.Y = n1; a.ldy = H;
+    linear_auto(a, s);
+    const float* resid = nullptr;
+    if (L.residual) {
+      a = LinArgs();
+      a.X = cur_obj; a.ldx = L.din; a.M = N; a.K = L.din; a.nout = L.dout; a.W = L.proj.w; a.bias = L.proj.b; a.Y = proj;
+      a.ldy = L.dout;
+      linear_auto(a, s);
+      resid = proj;
+    }
+    a = LinArgs();
+    a.X = n1; a.ldx = H; a.M = N; a.K = H; a.nout = L.dout; a.W = L.w4.w; a.bias = L.w4.b; a.act = 1; a.res = resid;
+    a.ld_res = L.dout; a.Y = nobj; a.ldy = L.dout;
+    linear_auto(a, s);
+    cur_obj = nobj;
+    cur_pred = npred;
+  }
+}
+
+}  // namespace echo
+

@@ -1,0 +1,339 @@
+// Layout-branch denoiser step: UNet1DModel.forward (denoise_net.py:773-806) + the DDPM ancestral update
+// (diffusion_ddpm.py:220-264, 296-309).
+//
+// The layout "1-D UNet" runs on signals of length 1 (box_t (N,8) -> (N,8,1), denoise_net.py:788,796): objects are
+// the batch dimension.  So every Conv1d(k=3, p=1[, stride 2]) is a matrix product with its centre tap, Up/Down
+// sampling keeps length 1, and self-/cross-attention over one token is to_out(to_v(.)) (softmax of one logit == 1).
+// What remains is a chain of ~150 few-row contractions (rows = nodes) bound by streaming ~115 M live weights from
+// HBM once per step, plus GroupNorm/LayerNorm/GEGLU over (N, C) rows; the only cross-object coupling is the echo
+// GCN.  Activations are fp32 row-major (N, C) throughout; ECHO_PREC_BF16 streams bf16 copies of the weights.
+#include "unet.cuh"
+
+#include <math.h>
+
+using namespace echo;
+
+struct echo_layout {
+  echo_layout_desc_t d;
+  DevPool pool;
+  UNetPlan plan;
+  Gcn gcn;
+  Arena arena;
+  int prec = ECHO_PREC_FP32;
+  ConvW box_emb, time_emb_lin;
+  const float* pred_table = nullptr;
+  const float* freqs = nullptr;
+  std::vector<float> h_tab;
+  float* d_tab = nullptr;
+  float *temb = nullptr, *e1 = nullptr, *emb = nullptr, *node = nullptr, *pred = nullptr, *latent = nullptr;
+  float *embout = nullptr, *v2 = nullptr, *a2vec = nullptr, *eps = nullptr;
+  int64_t* t_dev = nullptr;
+  std::vector<int> a2_off;
+  int a2_total = 0;
+  int N = 0;   // rows of the current call
+
+  float* buf(int C) { return arena.alloc_n<float>((size_t)N * C); }
+
+  void lin(const float* X, int64_t ldx, const ConvW& w, float* Y, int64_t ldy, const float* res, int64_t ld_res, int in_act, int act,
+           cudaStream_t s) {
+    LinArgs a;
+    a.X = X; a.ldx = ldx; a.M = N; a.K = w.cin; a.nout = w.cout; a.bias = w.b; a.Y = Y; a.ldy = ldy;
+    a.res = res; a.ld_res = ld_res; a.in_act = in_act; a.act = act;
+    if (prec == ECHO_PREC_BF16 && w.wb && N <= 64) { a.W = w.wb; a.w_dt = BF16; }
+    else { a.W = w.w; a.w_dt = F32; }
+    linear_auto(a, s);
+  }
+
+  // ResBlock._forward on length-1 signals (denoise_net.py:293-313)
+  float* res_block(const float* x, const ResW& r, cudaStream_t s) {
+    float* out = buf(r.cout);
+    const size_t m = arena.mark();
+    float* a1 = buf(r.cin);
+    gn_rows(x, N, r.cin, 32, r.n1.g, r.n1.b, 1e-5f, true, a1, s);
+    float* h1 = buf(r.cout);
+    lin(a1, r.cin, r.c1, h1, r.cout, embout + r.emb_off, plan.emb_total, 0, 0, s);
+    float* a2 = buf(r.cout);
+    gn_rows(h1, N, r.cout, 32, r.n2.g, r.n2.b, 1e-5f, true, a2, s);
+    const float* skip = x;
+    if (r.has_skip) {
+      float* sk = buf(r.cout);
+      lin(x, r.cin, r.skip, sk, r.cout, nullptr, 0, 0, 0, s);
+      skip = sk;
+    }
+    lin(a2, r.cout, r.c2, out, r.cout, skip, r.cout, 0, 0, s);
+    arena.release(m);
+    return out;
+  }
+
+  // SpatialTransformer1D with one token per object (attention.py:353-396, 222-245)
+  float* transformer(const float* x, const AttnW& a, int ai, cudaStream_t s) {
+    const int C = a.C;
+    float* out = buf(C);
+    const size_t m = arena.mark();
+    float* xn = buf(C);
+    gn_rows(x, N, C, 32, a.norm.g, a.norm.b, 1e-6f, false, xn, s);
+    float* t0 = buf(C);
+    lin(xn, C, a.proj_in, t0, C, nullptr, 0, 0, 0, s);
+    float* l1 = buf(C);
+    layer_norm(t0, F32, N, C, a.ln1.g, a.ln1.b, 1e-5f, l1, F32, s);
+    float* v = buf(C);
+    lin(l1, C, a.v_only, v, C, nullptr, 0, 0, 0, s);                 // attn1: softmax over one key == 1
+    float* t1 = buf(C);
+    lin(v, C, a.attn1_out, t1, C, t0, C, 0, 0, s);
+    add_rowvec(t1, F32, N, C, a2vec + a2_off[ai], a2_total, 1, s);   // attn2: to_out(to_v(context)) + x
+    float* l3 = buf(C);
+    layer_norm(t1, F32, N, C, a.ln3.g, a.ln3.b, 1e-5f, l3, F32, s);
+    float* f1 = buf(8 * C);
+    lin(l3, C, a.ff1, f1, 8 * C, nullptr, 0, 0, 0, s);
+    float* gg = buf(4 * C);
+    geglu(f1, F32, N, 4 * C, gg, F32, s);
+    float* t2 = buf(C);
+    lin(gg, 4 * C, a.ff2, t2, C, t1, C, 0, 0, s);
+    lin(t2, C, a.proj_out, out, C, x, C, 0, 0, s);
+    arena.release(m);
+    return out;
+  }
+
+  void forward(const echo_graph* g, const float* box_t, const float* obj_embed, const int64_t* t, float* eps_out, cudaStream_t s) {
+    ECHO_CHECK(g && g->n_nodes <= d.max_nodes && g->n_triples <= d.max_triples, "layout: graph exceeds handle capacity");
+    N = g->n_nodes;
+    if (N == 0) return;
+    const int T = g->n_triples, mc = d.model_channels, E = 4 * mc, gd = d.gconv_dim, od = d.obj_embed_dim;
+    const int nd = od + gd + (d.enable_t_emb ? gd : 0);
+    arena.release(0);
+    timestep_embedding_tab(t, freqs, N, mc, temb, s);
+    lin(temb, mc, plan.time0, e1, E, nullptr, 0, 0, 2, s);
+    lin(e1, E, plan.time2, emb, E, nullptr, 0, 0, 0, s);
+    // box_messsage_passing (denoise_net.py:758-771): node = [obj_embed | box_embeddings(box_t) | box_time_emb(emb)]
+    copy_cols(obj_embed, od, N, od, node, nd, s);
+    {
+      const int p = prec;
+      prec = ECHO_PREC_FP32;   // tiny layers stay fp32
+      lin(box_t, d.in_channels, box_emb, node + od, nd, nullptr, 0, 0, 0, s);
+      if (d.enable_t_emb) lin(emb, E, time_emb_lin, node + od + gd, nd, nullptr, 0, 0, 0, s);
+      prec = p;
+    }
+    if (T > 0) embedding_rows(pred_table, 2 * gd, g->triples, 3, 1, T, pred, 2 * gd, s);
+    gcn.forward(g, node, pred, latent, nullptr, s);
+    lin(emb, E, plan.emb_stack, embout, plan.emb_total, nullptr, 0, 1, 0, s);
+    lin(latent, d.context_dim, plan.v2_stack, v2, plan.v2_total, nullptr, 0, 0, 0, s);
+    {
+      int ai = 0;
+      auto a2 = [&](const AttnW& a) {
+        lin(v2 + a.v2_off, plan.v2_total, a.attn2_out, a2vec + a2_off[ai], a2_total, nullptr, 0, 0, 0, s);
+        ++ai;
+      };
+      for (auto& b : plan.in_blocks) if (b.attn) a2(b.at);
+      a2(plan.mid_at);
+      for (auto& b : plan.out_blocks) if (b.attn) a2(b.at);
+    }
+    std::vector<std::pair<const float*, int>> hs;
+    const float* h = nullptr;
+    int hc = 0, ai = 0;
+    for (auto& b : plan.in_blocks) {
+      if (b.kind == BlockW::CONV_IN) {
+        float* o = buf(b.conv.cout);
+        lin(box_t, d.in_channels, b.conv, o, b.conv.cout, nullptr, 0, 0, 0, s);
+        h = o; hc = b.conv.cout;
+      } else if (b.kind == BlockW::RES) {
+        h = res_block(h, b.res, s); hc = b.res.cout;
+        if (b.attn) h = transformer(h, b.at, ai++, s);
+      } else {   // Downsample: Conv1d k3 stride 2 pad 1 on length 1 -> centre tap (denoise_net.py:172-198)
+        float* o = buf(b.conv.cout);
+        lin(h, hc, b.conv, o, b.conv.cout, nullptr, 0, 0, 0, s);
+        h = o; hc = b.conv.cout;
+      }
+      hs.push_back({h, hc});
+    }
+    h = res_block(h, plan.mid0, s);
+    h = transformer(h, plan.mid_at, ai++, s);
+    h = res_block(h, plan.mid2, s);
+    hc = plan.mid2.cout;
+    for (auto& b : plan.out_blocks) {
+      auto sk = hs.back();
+      hs.pop_back();
+      float* cat = buf(hc + sk.second);
+      copy_cols(h, hc, N, hc, cat, hc + sk.second, s);
+      copy_cols(sk.first, sk.second, N, sk.second, cat + hc, hc + sk.second, s);
+      h = res_block(cat, b.res, s); hc = b.res.cout;
+      if (b.attn) h = transformer(h, b.at, ai++, s);
+      if (b.up) {   // Upsample: scale_factor 1 (denoise_net.py:154) then Conv1d k3 -> centre tap
+        float* o = buf(b.conv.cout);
+        lin(h, hc, b.conv, o, b.conv.cout, nullptr, 0, 0, 0, s);
+        h = o; hc = b.conv.cout;
+      }
+    }
+    float* hn = buf(hc);
+    gn_rows(h, N, hc, 32, plan.out_norm.g, plan.out_norm.b, 1e-5f, true, hn, s);
+    {
+      const int p = prec;
+      prec = ECHO_PREC_FP32;
+      lin(hn, hc, plan.out_conv, eps_out, d.out_channels, nullptr, 0, 0, 0, s);
+      prec = p;
+    }
+  }
+};
+
+namespace echo {
+
+static void make_ddpm_tables(echo_layout* h) {
+  // get_betas('linear') = np.linspace(b0, b1, T) float64 (diffusion_ddpm.py:38-40); tables as fp32 torch ops (:133-162)
+  const int T = h->d.time_num;
+  ECHO_CHECK(T >= 1, "layout: time_num must be >= 1");
+  std::vector<double> betas(T);
+  const double b0 = (double)h->d.beta_start, b1 = (double)h->d.beta_end;
+  const double step = T > 1 ? (b1 - b0) / (double)(T - 1) : 0.0;
+  for (int i = 0; i < T; ++i) betas[i] = (double)i * step + b0;
+  if (T > 1) betas[T - 1] = b1;
+  std::vector<float> ac(T), acp(T), b32(T), a32(T);
+  double cp = 1.0;
+  for (int i = 0; i < T; ++i) {
+    cp *= (1.0 - betas[i]);
+    ac[i] = (float)cp;
+    b32[i] = (float)betas[i];
+    a32[i] = (float)(1.0 - betas[i]);
+  }
+  for (int i = 0; i < T; ++i) acp[i] = i == 0 ? 1.0f : ac[i - 1];
+  h->h_tab.assign((size_t)5 * T, 0.f);
+  for (int i = 0; i < T; ++i) {
+    const float one_m = 1.0f - ac[i];
+    h->h_tab[0 * T + i] = sqrtf(1.0f / ac[i]);
+    h->h_tab[1 * T + i] = sqrtf(1.0f / ac[i] - 1.0f);
+    h->h_tab[2 * T + i] = b32[i] * sqrtf(acp[i]) / one_m;
+    h->h_tab[3 * T + i] = (1.0f - acp[i]) * sqrtf(a32[i]) / one_m;
+    const float pv = b32[i] * (1.0f - acp[i]) / one_m;
+    h->h_tab[4 * T + i] = logf(fmaxf(pv, 1e-20f));
+  }
+  h->d_tab = h->pool.upload(h->h_tab);
+}
+
+echo_layout* layout_create(const echo_layout_desc_t* desc, const echo_weight_t* weights, int n_weights) {
+  ECHO_CHECK(desc, "layout: null desc");
+  echo_layout* h = new echo_layout();
+  try {
+    h->d = *desc;
+    const echo_layout_desc_t& d = h->d;
+    ECHO_CHECK(d.max_nodes > 0 && d.model_channels % 32 == 0 && d.num_levels >= 1 && d.num_levels <= 8, "layout: bad config");
+    ECHO_CHECK(d.in_channels % 4 == 0 && d.obj_embed_dim % 4 == 0 && d.gconv_dim % 4 == 0, "layout: channel counts must be multiples of 4");
+    h->prec = d.precision;
+    ECHO_CHECK(h->prec == ECHO_PREC_FP32 || h->prec == ECHO_PREC_BF16, "layout: unknown precision %d", h->prec);
+    WeightMap wm;
+    wm.load(weights, n_weights);
+    cudaStream_t s = 0;
+    UNetCfg cfg;
+    cfg.dims = 1;
+    cfg.in_channels = d.in_channels; cfg.out_channels = d.out_channels; cfg.model_channels = d.model_channels;
+    cfg.channel_mult.assign(d.channel_mult, d.channel_mult + d.num_levels);
+    cfg.attention_resolutions.assign(d.attention_resolutions, d.attention_resolutions + d.num_attention_resolutions);
+    cfg.num_res_blocks = d.num_res_blocks; cfg.num_heads = d.num_heads; cfg.context_dim = d.context_dim;
+    cfg.want_bf16 = h->prec == ECHO_PREC_BF16;
+    build_unet_plan(wm, cfg, h->pool, h->plan, s);
+    const int mc = d.model_channels, E = 4 * mc, gd = d.gconv_dim;
+    auto linear = [&](const std::string& p, int cin, int cout) {
+      ConvW c;
+      c.cin = cin; c.cout = cout; c.taps = 1;
+      const WView& v = wm.get(p + ".weight", {cout, cin});
+      float* o = h->pool.alloc_n<float>((size_t)cout * cin);
+      ECHO_CUDA(cudaMemcpyAsync(o, v.p, sizeof(float) * cout * cin, cudaMemcpyDeviceToDevice, s));
+      c.w = o;
+      const WView& bv = wm.get(p + ".bias", {cout});
+      float* bo = h->pool.alloc_n<float>(cout);
+      ECHO_CUDA(cudaMemcpyAsync(bo, bv.p, sizeof(float) * cout, cudaMemcpyDeviceToDevice, s));
+      c.b = bo;
+      return c;
+    };
+    h->box_emb = linear("box_embeddings", d.in_channels, gd);
+    if (d.enable_t_emb) h->time_emb_lin = linear("box_time_emb", E, gd);
+    {
+      const WView& pt = wm.get("pred_embeddings.weight");
+      ECHO_CHECK(pt.shape.size() == 2 && pt.shape[1] == 2 * gd, "pred_embeddings: bad shape");
+      float* o = h->pool.alloc_n<float>(pt.numel());
+      ECHO_CUDA(cudaMemcpyAsync(o, pt.p, sizeof(float) * pt.numel(), cudaMemcpyDeviceToDevice, s));
+      h->pred_table = o;
+    }
+    {
+      const int half = mc / 2;
+      float* f = h->pool.alloc_n<float>(half);
+      if (wm.has("__timestep_freqs")) {
+        const WView& v = wm.get("__timestep_freqs", {half});
+        ECHO_CUDA(cudaMemcpyAsync(f, v.p, sizeof(float) * half, cudaMemcpyDeviceToDevice, s));
+      } else {
+        std::vector<float> hf(half);
+        for (int i = 0; i < half; ++i) hf[i] = expf(-logf(10000.f) * (float)i / (float)half);
+        ECHO_CUDA(cudaMemcpy(f, hf.data(), sizeof(float) * half, cudaMemcpyHostToDevice));
+      }
+      h->freqs = f;
+    }
+    echo_gcn_desc_t gdsc;
+    gdsc.input_dim_obj = d.obj_embed_dim + gd + (d.enable_t_emb ? gd : 0);   // denoise_net.py:725-727
+    gdsc.input_dim_pred = 2 * gd;
+    gdsc.num_layers = 5;
+    gdsc.hidden_dim = 4 * gd;
+    gdsc.output_dim = d.context_dim;
+    gdsc.max_nodes = d.max_nodes;
+    gdsc.max_triples = d.max_triples > 0 ? d.max_triples : 1;
+    gdsc.bn_eps = 1e-5f;
+    h->gcn.create(wm, "box_graph_cov.", gdsc, h->pool);
+    make_ddpm_tables(h);
+    const size_t N = d.max_nodes, T = gdsc.max_triples;
+    h->temb = h->pool.alloc_n<float>(N * mc);
+    h->e1 = h->pool.alloc_n<float>(N * E);
+    h->emb = h->pool.alloc_n<float>(N * E);
+    h->node = h->pool.alloc_n<float>(N * gdsc.input_dim_obj);
+    h->pred = h->pool.alloc_n<float>(T * 2 * gd);
+    h->latent = h->pool.alloc_n<float>(N * d.context_dim);
+    h->embout = h->pool.alloc_n<float>(N * h->plan.emb_total);
+    h->v2 = h->pool.alloc_n<float>(N * h->plan.v2_total);
+    h->a2_total = h->plan.v2_total;
+    h->a2vec = h->pool.alloc_n<float>(N * h->a2_total);
+    h->eps = h->pool.alloc_n<float>(N * d.out_channels);
+    h->t_dev = h->pool.alloc_n<int64_t>(N);
+    {
+      int off = 0;
+      auto add = [&](const AttnW& a) { h->a2_off.push_back(off); off += a.C; };
+      for (auto& b : h->plan.in_blocks) if (b.attn) add(b.at);
+      add(h->plan.mid_at);
+      for (auto& b : h->plan.out_blocks) if (b.attn) add(b.at);
+    }
+    // workspace: every block output is (N, <= 2*mc*max_mult) fp32; ~60 live buffers is a generous bound
+    int maxmult = 1;
+    for (int i = 0; i < d.num_levels; ++i) maxmult = d.channel_mult[i] > maxmult ? d.channel_mult[i] : maxmult;
+    const size_t per = (size_t)N * mc * maxmult * sizeof(float);
+    const size_t nblk = h->plan.in_blocks.size() + h->plan.out_blocks.size() + 4;
+    h->arena.init(per * (nblk * 5 + 64) + (size_t(1) << 20));
+    ECHO_CUDA(cudaStreamSynchronize(s));
+    return h;
+  } catch (...) {
+    h->arena.destroy();
+    h->pool.destroy();
+    delete h;
+    throw;
+  }
+}
+
+void layout_destroy(echo_layout* h) {
+  if (!h) return;
+  h->arena.destroy();
+  h->pool.destroy();
+  delete h;
+}
+
+void layout_forward(echo_layout* h, const echo_graph* g, const float* box_t, const float* obj_embed, const int64_t* t, float* eps_out,
+                    cudaStream_t s) {
+  h->forward(g, box_t, obj_embed, t, eps_out, s);
+}
+
+void layout_step(echo_layout* h, const echo_graph* g, const float* x_t, const float* obj_embed, int t, const float* noise, float* x_prev,
+                 cudaStream_t s) {
+  ECHO_CHECK(t >= 0 && t < h->d.time_num, "layout_step: t=%d outside [0, %d)", t, h->d.time_num);
+  ECHO_CHECK(g, "layout_step: null graph");
+  fill_i64(h->t_dev, g->n_nodes, t, s);
+  h->forward(g, x_t, obj_embed, h->t_dev, h->eps, s);
+  ddpm_update(x_t, h->eps, noise, h->d_tab, h->d.time_num, t, (int64_t)g->n_nodes * h->d.out_channels, x_prev, s);
+}
+
+}  // namespace echo
+
+namespace echo {
+const std::vector<float>& layout_table(const echo_layout* h) { return h->h_tab; }
+}  // namespace echo

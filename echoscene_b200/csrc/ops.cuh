@@ -1,0 +1,136 @@
+// Kernel launchers of the EchoScene denoiser hot path (declarations).  Every launcher is asynchronous on the
+// given stream, allocates nothing, and counts its launches (common.cuh).
+#pragma once
+#include "common.cuh"
+
+namespace echo {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Implicit-GEMM contraction:  out[m, n] = act( sum_{tap,c} A[vox(m,tap), c] * W[n, tap*cin + c]
+//                                               + bias[n] + rowvec[obj(m), n] + res[m, n] )
+// A is a channels-last activation; m enumerates OUTPUT voxels (obj, od, oh, ow).  Linear layers are the 1x1x1 case.
+// Strides are in ELEMENTS.  `batch` lets one launch run nb0*nb1 independent problems (attention heads).
+// ---------------------------------------------------------------------------------------------------------------
+struct GemmArgs {
+  const void* A = nullptr;
+  DT a_dt = F32;
+  int n = 1, d = 1, h = 1, w = 1;   // input grid per object
+  int cin = 0;                      // reduction channels per tap
+  int64_t lda = 0;                  // elements between consecutive input voxels (>= cin)
+  int od = 1, oh = 1, ow = 1;       // output grid per object
+  int kd = 1, kh = 1, kw = 1, sd = 1, sh = 1, sw = 1, pd = 0, ph = 0, pw = 0;
+  const void* W = nullptr;
+  DT w_dt = F32;
+  int64_t w_stride_n = 0, w_stride_k = 1;   // W[n, k] at n*w_stride_n + k*w_stride_k
+  int cout = 0;
+  const float* bias = nullptr;
+  const float* rowvec = nullptr;    // [n_obj, ld_rowvec]
+  int64_t ld_rowvec = 0;
+  const void* res = nullptr;        // [rows_out, ld_res]
+  DT res_dt = F32;
+  int64_t ld_res = 0;
+  void* out = nullptr;
+  DT out_dt = F32;
+  int64_t ldo = 0;
+  int act = 0;                      // 0 none, 1 relu
+  float alpha = 1.f;                // scales the accumulator before the epilogue adds
+  // batching: problem b = b0*nb1 + b1
+  int nb0 = 1, nb1 = 1;
+  int64_t a_bs0 = 0, a_bs1 = 0, w_bs0 = 0, w_bs1 = 0, o_bs0 = 0, o_bs1 = 0;
+  int64_t rows_out() const { return (int64_t)n * od * oh * ow; }
+  int ktot() const { return kd * kh * kw * cin; }
+};
+
+void gemm_simt(const GemmArgs& g, cudaStream_t s);
+// tcgen05 + TMA path (gemm_tc.cu).  Requirements are checked by gemm_tc_supported().
+bool gemm_tc_supported(const GemmArgs& g);
+void gemm_tc(const GemmArgs& g, cudaStream_t s);
+bool tc_available();
+// precision: ECHO_PREC_*; BF16 falls back to the SIMT kernel (bf16 operands, fp32 accumulate) for shapes the
+// tensor-core kernel does not take (tiny channel counts).
+void gemm(const GemmArgs& g, int precision, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------------------------
+// Few-row ("skinny") linear: Y[M, nout] = epi( f(X)[M, K] @ W[nout, K]^T ), M = nodes/edges.  HBM-bound on W.
+// ---------------------------------------------------------------------------------------------------------------
+struct LinArgs {
+  const float* X = nullptr;
+  int64_t ldx = 0;
+  int M = 0, K = 0, nout = 0;
+  const void* W = nullptr;     // [nout, K] row-major, row stride ldw (0 = K)
+  DT w_dt = F32;
+  int64_t ldw = 0;
+  const float* bias = nullptr;
+  const float* res = nullptr;  // [M, ld_res] added after activation
+  int64_t ld_res = 0;
+  float* Y = nullptr;
+  int64_t ldy = 0;
+  int in_act = 0;              // 0 none, 1 SiLU applied to X on load
+  int act = 0;                 // 0 none, 1 relu, 2 silu (before res)
+};
+void linear_rows(const LinArgs& a, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------------------------
+// normalisations / elementwise
+// ---------------------------------------------------------------------------------------------------------------
+// GroupNorm over (voxels x C/groups) per (object, group); fp32 statistics (GroupNorm32, ldm_diffusion_util.py:237).
+// `stats` gets (mean, rstd) per (object, group); `partial` is scratch of gn_partial_floats(x) floats.
+size_t gn_partial_floats(const Act& x, int groups);
+void gn_stats(const Act& x, int groups, float eps, float* stats, float* partial, cudaStream_t s);
+void gn_apply(const Act& x, const float* stats, const float* gamma, const float* beta, int groups, bool silu,
+              const Act& out, cudaStream_t s);
+// rows variant for the layout branch (length-1 signals): X [M, C] -> Y [M, C]
+void gn_rows(const float* x, int M, int C, int groups, const float* gamma, const float* beta, float eps, bool silu,
+             float* y, cudaStream_t s);
+void layer_norm(const void* x, DT xdt, int64_t rows, int C, const float* gamma, const float* beta, float eps,
+                void* y, DT ydt, cudaStream_t s);
+// GEGLU: x [rows, 2F] = [a | g] -> y [rows, F] = a * gelu_erf(g)   (attention.py:39-46)
+void geglu(const void* x, DT xdt, int64_t rows, int F, void* y, DT ydt, cudaStream_t s);
+void concat_channels(const Act& a, const Act& b, const Act& out, cudaStream_t s);
+void upsample_hw2(const Act& x, const Act& out, cudaStream_t s);              // nearest x(1,2,2)
+void maxpool3d(const Act& x, int k, int stride, const Act& out, cudaStream_t s);
+void ncdhw_to_cl(const float* x, int n, int c, int64_t voxels, void* out, DT odt, cudaStream_t s);
+void cl_to_ncdhw(const void* x, DT xdt, int n, int c, int64_t voxels, float* out, cudaStream_t s);
+void convert(const void* x, DT xdt, void* y, DT ydt, int64_t count, cudaStream_t s);
+// y[r, :] += v[r / rows_per_obj, :]
+void add_rowvec(void* y, DT ydt, int64_t rows, int C, const float* v, int64_t ldv, int64_t rows_per_obj, cudaStream_t s);
+// in-place row softmax of S [rows, cols] (fp32)
+void softmax_rows(float* S, int64_t rows, int cols, cudaStream_t s);
+// [cos(t f) | sin(t f)] (ldm_diffusion_util.py:174-194); t int64 device, freqs [dim/2] device
+void timestep_embedding_tab(const int64_t* t, const float* freqs, int n, int dim, float* out, cudaStream_t s);
+void fill_i64(int64_t* p, int n, int64_t v, cudaStream_t s);
+// out[r, col0 : col0+D] = table[idx[r*idx_stride + idx_off], :]
+void embedding_rows(const float* table, int D, const int64_t* idx, int64_t idx_stride, int64_t idx_off, int64_t rows,
+                    float* out, int64_t ldo, cudaStream_t s);
+// out[r, col0:col0+D] = src[r, :D]
+void copy_cols(const float* src, int64_t lds, int64_t rows, int D, float* out, int64_t ldo, cudaStream_t s);
+// flatten(1) of a channels-last (n, d,h,w, c) tensor in NCDHW order -> [n, c*voxels] f32
+void flatten_ncdhw(const Act& x, float* out, cudaStream_t s);
+
+// samplers
+// DDPM: x_prev = c1*(a*x - b*eps) + c2*x + [t>0] exp(0.5 lv) noise   (diffusion_ddpm.py:220-309); tab = 5 x T
+void ddpm_update(const float* x, const float* eps, const float* noise, const float* tab, int T, int t, int64_t count,
+                 float* out, cudaStream_t s);
+// DDIM eta=0 on an NCDHW latent, e_t given channels-last (or NCDHW when e_cl == false)
+void ddim_update(const float* x_ncdhw, const void* e, DT edt, bool e_cl, int n, int c, int64_t voxels,
+                 const float* coef4 /* device, 4 floats */, float* out_ncdhw, cudaStream_t s);
+
+// attention (fp32, materialised scores): qkv [n*tokens, 3*heads*dh] -> out [n*tokens, heads*dh]
+void attention_f32(const float* qkv, int n, int tokens, int heads, int dh, float* scores_ws, float* out, cudaStream_t s);
+size_t attention_f32_ws_floats(int n, int tokens, int heads);
+// attention (bf16 tensor-core flash kernel): qkv bf16, out bf16
+void attention_bf16(const __nv_bfloat16* qkv, int n, int tokens, int heads, int dh, __nv_bfloat16* out, cudaStream_t s);
+
+// weight preparation
+// conv weight (cout, cin, taps) -> (cout, taps, cin); taps = kd*kh*kw
+void repack_conv_weight(const float* w, int cout, int cin, int taps, float* out, cudaStream_t s);
+// centre tap of a Conv1d(k=3) weight (cout, cin, 3) -> (cout, cin)
+void conv1d_center_tap(const float* w, int cout, int cin, int k, float* out, cudaStream_t s);
+// fold eval BatchNorm1d into the preceding Linear: W' = W*g/sqrt(v+eps), b' = (b-m)*g/sqrt(v+eps)+beta
+void fold_bn(const float* w, const float* b, const float* gamma, const float* beta, const float* mean, const float* var,
+             float eps, int nout, int K, float* w_out, float* b_out, cudaStream_t s);
+
+// graph ops
+void gather_rows(const float* src, const int64_t* idx, int64_t n_idx, int64_t D, float* out, cudaStream_t s);
+
+}  // namespace echo

@@ -1,0 +1,470 @@
+"""Host-side mirror of the reference's operator surface for the denoiser hot path.
+
+Each class keeps the reference constructor signature, forward signature and ``state_dict`` key names (so the
+reference's checkpoints load with ``strict=True``), holds its parameters as ordinary ``nn.Parameter``s, and runs its
+forward as CUDA kernels of ``libechoscene_b200.so`` through the C ABI (``_lib``).  There is no PyTorch arithmetic
+and no CPU path in any forward: weights are repacked by the library when the handle is (re)built, which happens
+lazily on the first call and whenever a parameter was modified or the graph outgrew the handle's capacity.
+
+  GraphTripleConv / GraphTripleConvNet   model/graph.py:89-250
+  UNet1DModel                            model/networks/diffusion_layout/denoise_net.py:451-806
+  UNet3DModel, DiffusionUNet             model/networks/diffusion_shape/openai_model_3d.py:452-863, network.py:11-43
+
+Inference only (eval-mode BatchNorm, no autograd): the training backward is outside this round's scope.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib, arch
+from ._lib import EchoError
+
+
+def _next_pow2(n: int, lo: int) -> int:
+    c = lo
+    while c < n:
+        c *= 2
+    return c
+
+
+class _SpecModule(nn.Module):
+    """nn.Module whose (nested) parameters/buffers are created from an ``arch`` spec table, so state_dict keys and
+    shapes are the reference's."""
+
+    def _build_from_specs(self, specs: "arch.Specs"):
+        self._spec_keys = list(specs.keys())
+        for key, spec in specs.items():
+            parts = key.split(".")
+            mod: nn.Module = self
+            for p in parts[:-1]:
+                if p not in mod._modules:
+                    mod.add_module(p, nn.Module())
+                mod = mod._modules[p]
+            t = arch.init_tensor(spec, _SpecModule._gen)
+            if spec.buffer:
+                mod.register_buffer(parts[-1], t)
+            else:
+                mod.register_parameter(parts[-1], nn.Parameter(t, requires_grad=False))
+
+    _gen = torch.Generator().manual_seed(0)
+
+    # ---- handle management ----
+    _handle = None
+    _handle_key = None
+
+    _wlist = None
+    frozen = False   # samplers set this inside a chain: weights cannot change between two steps
+
+    def _weights_version(self):
+        if self.frozen and self._handle_key is not None:
+            return self._handle_key[0]
+        if self._wlist is None or len(self._wlist) != len(self._spec_keys):
+            self._wlist = list(self.state_dict(keep_vars=True).values())
+        return tuple((t.data_ptr(), t._version) for t in self._wlist)
+
+    def _apply(self, fn, *a, **k):   # .cuda()/.to() replace parameter storage
+        self._wlist = None
+        return super()._apply(fn, *a, **k)
+
+    def _check_eval(self):
+        if self.training:
+            raise EchoError(f"{type(self).__name__}: only eval() mode is implemented on the B200 path "
+                            "(the reference samples under model.eval(), scripts/eval_3dfront.py:395)")
+
+    def _destroy_handle(self):
+        raise NotImplementedError
+
+    def __del__(self):
+        try:
+            self._destroy_handle()
+        except Exception:
+            pass
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# graph.py
+# ----------------------------------------------------------------------------------------------------------------------
+class GraphTripleConvNet(_SpecModule):
+    """A sequence of scene graph convolution layers — model/graph.py:214-250 (same arguments)."""
+
+    def __init__(self, input_dim_obj, input_dim_pred, num_layers=2, hidden_dim=512, residual=False, pooling="avg",
+                 mlp_normalization="none", output_dim=None):
+        super().__init__()
+        if pooling != "avg":
+            raise EchoError(f"pooling='{pooling}' is not on the hot path (every denoiser construction passes 'avg', "
+                            "denoise_net.py:729, openai_model_3d.py:770)")
+        if mlp_normalization not in ("batch", "none"):
+            raise EchoError(f"unsupported mlp_normalization {mlp_normalization}")
+        self.num_layers = num_layers
+        self.cfg = arch.GCNConfig(input_dim_obj, input_dim_pred, num_layers, hidden_dim, output_dim, residual,
+                                  pooling, mlp_normalization)
+        self._build_from_specs(arch.gcn_specs(self.cfg))
+        self.eval()
+
+    def _ensure(self, n_nodes: int, n_triples: int):
+        ver = self._weights_version()
+        cap = self._handle_key[1] if self._handle_key else (0, 0)
+        if self._handle is not None and self._handle_key[0] == ver and n_nodes <= cap[0] and n_triples <= cap[1]:
+            return
+        self._destroy_handle()
+        cap = (_next_pow2(n_nodes, 32), _next_pow2(n_triples, 128))
+        d = _lib.GcnDesc(self.cfg.input_dim_obj, self.cfg.input_dim_pred, self.cfg.num_layers, self.cfg.hidden_dim,
+                         self.cfg.output_dim or 0, cap[0], cap[1], 1e-5)
+        arr, n, keep = _lib.weights_table(self.state_dict())
+        h = C.c_void_p()
+        _lib.check(_lib.lib().echo_gcn_create(C.byref(h), C.byref(d), arr, n))
+        self._handle, self._handle_key = h, (ver, cap)
+
+    def _destroy_handle(self):
+        if self._handle is not None:
+            _lib.lib().echo_gcn_destroy(self._handle)
+            self._handle = None
+
+    @torch.no_grad()
+    def forward(self, obj_vecs, pred_vecs, edges):
+        self._check_eval()
+        _lib.require_cuda(obj_vecs, pred_vecs, edges)
+        obj_vecs = obj_vecs.float().contiguous()
+        pred_vecs = pred_vecs.float().contiguous()
+        n, t = obj_vecs.shape[0], pred_vecs.shape[0]
+        assert obj_vecs.shape[1] == self.cfg.input_dim_obj and pred_vecs.shape[1] == self.cfg.input_dim_pred
+        assert edges.shape == (t, 2)
+        self._ensure(n, t)
+        g = _lib.graph_for(_lib.edges_to_triples(edges), n) if not hasattr(edges, "_echo_graph") else edges._echo_graph
+        dout = self.cfg.output_dim or self.cfg.input_dim_obj
+        obj_out = torch.empty(n, dout, device=obj_vecs.device)
+        pred_out = torch.empty(t, self.cfg.input_dim_pred, device=obj_vecs.device)
+        _lib.check(_lib.lib().echo_gcn_forward(self._handle, g.h, _lib.ptr(obj_vecs), _lib.ptr(pred_vecs),
+                                               _lib.ptr(obj_out), _lib.ptr(pred_out), _lib.stream_ptr()))
+        return obj_out, pred_out
+
+
+class GraphTripleConv(GraphTripleConvNet):
+    """A single layer of scene graph convolution — model/graph.py:89-211 (same arguments)."""
+
+    def __init__(self, input_dim_obj, input_dim_pred, output_dim=None, hidden_dim=512, pooling="avg",
+                 mlp_normalization="none", residual=True):
+        nn.Module.__init__(self)
+        if pooling != "avg":
+            raise EchoError(f"pooling='{pooling}' is not on the hot path")
+        self.num_layers = 1
+        self.input_dim_obj, self.input_dim_pred = input_dim_obj, input_dim_pred
+        self.output_dim = output_dim or input_dim_obj
+        self.hidden_dim, self.residual, self.pooling = hidden_dim, residual, pooling
+        self.cfg = arch.GCNConfig(input_dim_obj, input_dim_pred, 1, hidden_dim, self.output_dim, residual, pooling,
+                                  mlp_normalization)
+        specs = arch.OrderedDict()
+        arch.gcn_layer_specs(specs, "", input_dim_obj, input_dim_pred, hidden_dim, self.output_dim, residual,
+                             mlp_normalization == "batch")
+        self._build_from_specs(specs)
+        self.eval()
+
+    def state_dict_for_lib(self):
+        return {"gconvs.0." + k: v for k, v in self.state_dict().items()}
+
+    def _ensure(self, n_nodes, n_triples):
+        ver = self._weights_version()
+        cap = self._handle_key[1] if self._handle_key else (0, 0)
+        if self._handle is not None and self._handle_key[0] == ver and n_nodes <= cap[0] and n_triples <= cap[1]:
+            return
+        self._destroy_handle()
+        cap = (_next_pow2(n_nodes, 32), _next_pow2(n_triples, 128))
+        d = _lib.GcnDesc(self.cfg.input_dim_obj, self.cfg.input_dim_pred, 1, self.cfg.hidden_dim, self.output_dim,
+                         cap[0], cap[1], 1e-5)
+        arr, n, keep = _lib.weights_table(self.state_dict_for_lib())
+        h = C.c_void_p()
+        _lib.check(_lib.lib().echo_gcn_create(C.byref(h), C.byref(d), arr, n))
+        self._handle, self._handle_key = h, (ver, cap)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# layout denoiser
+# ----------------------------------------------------------------------------------------------------------------------
+def _fill_levels(desc, channel_mult, attention_resolutions):
+    desc.num_levels = len(channel_mult)
+    for i, m in enumerate(channel_mult):
+        desc.channel_mult[i] = int(m)
+    desc.num_attention_resolutions = len(attention_resolutions)
+    for i, a in enumerate(attention_resolutions):
+        desc.attention_resolutions[i] = int(a)
+
+
+class UNet1DModel(_SpecModule):
+    """The layout denoiser — denoise_net.py:451-806.  Same keyword arguments as the reference; the settings the
+    default ``*_mp`` configs use (crossattn + message passing + spatial transformer) are the implemented ones."""
+
+    def __init__(self, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions, dropout=0,
+                 channel_mult=(1, 2, 4, 8), conv_resample=True, dims=1, use_checkpoint=False, use_fp16=False,
+                 num_heads=-1, num_head_channels=-1, num_heads_upsample=-1, use_scale_shift_norm=False,
+                 resblock_updown=False, use_new_attention_order=False, use_spatial_transformer=False,
+                 transformer_depth=1, concat_dim=None, crossattn_dim=None, conditioning_key="crossattn",
+                 using_clip=True, enable_t_emb=False, precision: str = "fp32", time_num: int = 1000,
+                 beta_start: float = 1e-4, beta_end: float = 0.02):
+        super().__init__()
+        unsupported = dict(dims=(dims, 1), conditioning_key=(conditioning_key, "crossattn"),
+                           use_spatial_transformer=(use_spatial_transformer, True),
+                           transformer_depth=(transformer_depth, 1), use_scale_shift_norm=(use_scale_shift_norm, False),
+                           resblock_updown=(resblock_updown, False), conv_resample=(conv_resample, True),
+                           num_head_channels=(num_head_channels, -1), dropout=(dropout, 0))
+        for k, (got, want) in unsupported.items():
+            if got != want:
+                raise EchoError(f"UNet1DModel: {k}={got!r} is outside the hot path (implemented: {want!r})")
+        self.conditioning_key = conditioning_key
+        self.cfg = arch.UNet1DConfig(in_channels=in_channels, out_channels=out_channels, model_channels=model_channels,
+                                     channel_mult=tuple(channel_mult), num_res_blocks=num_res_blocks,
+                                     attention_resolutions=tuple(attention_resolutions), num_heads=num_heads,
+                                     concat_dim=concat_dim, crossattn_dim=crossattn_dim, using_clip=using_clip,
+                                     enable_t_emb=enable_t_emb)
+        self.precision = precision
+        self.time_num, self.beta_start, self.beta_end = time_num, beta_start, beta_end
+        self._build_from_specs(arch.unet1d_specs(self.cfg))
+        self.eval()
+
+    def set_schedule(self, time_num, beta_start=1e-4, beta_end=0.02):
+        if (time_num, beta_start, beta_end) != (self.time_num, self.beta_start, self.beta_end):
+            self.time_num, self.beta_start, self.beta_end = time_num, beta_start, beta_end
+            self._destroy_handle()
+
+    def _ensure(self, n_nodes, n_triples):
+        ver = self._weights_version()
+        cap = self._handle_key[1] if self._handle_key else (0, 0)
+        if self._handle is not None and self._handle_key[0] == ver and n_nodes <= cap[0] and n_triples <= cap[1]:
+            return
+        self._destroy_handle()
+        cap = (_next_pow2(n_nodes, 32), _next_pow2(n_triples, 128))
+        c = self.cfg
+        d = _lib.LayoutDesc()
+        d.in_channels, d.out_channels, d.model_channels = c.in_channels, c.out_channels, c.model_channels
+        _fill_levels(d, c.channel_mult, c.attention_resolutions)
+        d.num_res_blocks, d.num_heads, d.context_dim = c.num_res_blocks, c.num_heads, c.crossattn_dim
+        d.obj_embed_dim, d.gconv_dim, d.enable_t_emb = c.obj_embed_dim, c.gconv_dim, int(c.enable_t_emb)
+        d.max_nodes, d.max_triples = cap
+        d.precision = _lib.PREC_BF16 if self.precision == "bf16" else _lib.PREC_FP32
+        d.time_num, d.beta_start, d.beta_end = self.time_num, self.beta_start, self.beta_end
+        dev = next(self.parameters()).device
+        arr, n, keep = _lib.weights_table(self.state_dict(),
+                                          {"__timestep_freqs": _lib.timestep_freqs(c.model_channels, dev)})
+        h = C.c_void_p()
+        _lib.check(_lib.lib().echo_layout_create(C.byref(h), C.byref(d), arr, n))
+        self._handle, self._handle_key = h, (ver, cap)
+
+    def _destroy_handle(self):
+        if self._handle is not None:
+            _lib.lib().echo_layout_destroy(self._handle)
+            self._handle = None
+
+    @torch.no_grad()
+    def forward(self, box_t, obj_embed, triples, timesteps=None, context=None, y=None, **kwargs):
+        """box_t (N,8), obj_embed (N,640), triples (T,3) i64, timesteps (N,) i64 -> (N,8,1).  ``context`` is accepted
+        and ignored exactly as the reference ignores it in crossattn mode (denoise_net.py:791-792)."""
+        self._check_eval()
+        _lib.require_cuda(box_t, obj_embed, triples, timesteps)
+        n = box_t.shape[0]
+        box_t = box_t.float().contiguous()
+        obj_embed = obj_embed.float().contiguous()
+        timesteps = timesteps.to(torch.int64).contiguous()
+        assert box_t.shape == (n, self.cfg.in_channels) and obj_embed.shape == (n, self.cfg.obj_embed_dim)
+        assert timesteps.shape == (n,)
+        self._ensure(n, triples.shape[0])
+        g = _lib.graph_for(triples, n)
+        out = torch.empty(n, self.cfg.out_channels, device=box_t.device)
+        _lib.check(_lib.lib().echo_layout_forward(self._handle, g.h, _lib.ptr(box_t), _lib.ptr(obj_embed),
+                                                  _lib.ptr(timesteps), _lib.ptr(out), _lib.stream_ptr()))
+        return out.unsqueeze(-1)
+
+    @torch.no_grad()
+    def ddpm_step(self, x_t, obj_embed, triples, t: int, noise):
+        """One iteration of p_sample_loop_sg (forward + posterior update) — diffusion_ddpm.py:296-345."""
+        self._check_eval()
+        _lib.require_cuda(x_t, obj_embed, triples, noise)
+        n = x_t.shape[0]
+        self._ensure(n, triples.shape[0])
+        g = _lib.graph_for(triples, n)
+        x_t, obj_embed, noise = x_t.float().contiguous(), obj_embed.float().contiguous(), noise.float().contiguous()
+        out = torch.empty_like(x_t)
+        _lib.check(_lib.lib().echo_layout_step(self._handle, g.h, _lib.ptr(x_t), _lib.ptr(obj_embed), int(t),
+                                               _lib.ptr(noise), _lib.ptr(out), _lib.stream_ptr()))
+        return out
+
+    def schedule_tables(self) -> torch.Tensor:
+        self._ensure(1, 1)
+        out = torch.empty(5, self.time_num, dtype=torch.float32)
+        _lib.check(_lib.lib().echo_layout_schedule(self._handle, out.data_ptr()))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# shape denoiser
+# ----------------------------------------------------------------------------------------------------------------------
+class UNet3DModel(_SpecModule):
+    """The shape denoiser — openai_model_3d.py:452-863, same keyword arguments."""
+
+    def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
+                 dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None,
+                 use_checkpoint=False, use_fp16=False, num_heads=-1, num_head_channels=-1, num_heads_upsample=-1,
+                 use_scale_shift_norm=False, resblock_updown=False, use_new_attention_order=False,
+                 use_spatial_transformer=False, transformer_depth=1, context_dim=None, n_embed=None, legacy=True,
+                 messsage_passing=True, conditioning_key=None, enable_t_emb=False, precision: str = "fp32",
+                 ddim_steps: int = 100, timesteps: int = 1000, linear_start: float = 0.00085,
+                 linear_end: float = 0.012):
+        super().__init__()
+        unsupported = dict(dims=(dims, 3), conditioning_key=(conditioning_key, "crossattn"),
+                           use_spatial_transformer=(use_spatial_transformer, True), messsage_passing=(messsage_passing, True),
+                           transformer_depth=(transformer_depth, 1), use_scale_shift_norm=(use_scale_shift_norm, False),
+                           resblock_updown=(resblock_updown, False), conv_resample=(conv_resample, True),
+                           num_head_channels=(num_head_channels, -1), num_classes=(num_classes, None),
+                           n_embed=(n_embed, None), legacy=(legacy, False), dropout=(dropout, 0))
+        for k, (got, want) in unsupported.items():
+            if got != want:
+                raise EchoError(f"UNet3DModel: {k}={got!r} is outside the hot path (implemented: {want!r})")
+        self.conditioning_key = conditioning_key
+        self.messsage_passing = messsage_passing
+        self.cfg = arch.UNet3DConfig(in_channels=in_channels, out_channels=out_channels, model_channels=model_channels,
+                                     channel_mult=tuple(channel_mult), num_res_blocks=num_res_blocks,
+                                     attention_resolutions=tuple(attention_resolutions), num_heads=num_heads,
+                                     context_dim=context_dim, image_size=image_size, enable_t_emb=enable_t_emb)
+        self.precision = precision
+        self.ddim_steps, self.timesteps_total = ddim_steps, timesteps
+        self.linear_start, self.linear_end = linear_start, linear_end
+        self._build_from_specs(arch.unet3d_specs(self.cfg))
+        self.eval()
+
+    def set_schedule(self, ddim_steps, timesteps=1000, linear_start=0.00085, linear_end=0.012):
+        new = (ddim_steps, timesteps, linear_start, linear_end)
+        if new != (self.ddim_steps, self.timesteps_total, self.linear_start, self.linear_end):
+            self.ddim_steps, self.timesteps_total, self.linear_start, self.linear_end = new
+            self._destroy_handle()
+
+    def _ensure(self, n_nodes, n_triples, n_local=None):
+        n_local = n_nodes if n_local is None else n_local
+        ver = self._weights_version()
+        cap = self._handle_key[1] if self._handle_key else (0, 0, 0)
+        if (self._handle is not None and self._handle_key[0] == ver and n_nodes <= cap[0] and n_triples <= cap[1]
+                and n_local <= cap[2] and (cap[2] == cap[0]) == (n_local == n_nodes)):
+            return
+        self._destroy_handle()
+        cap = (max(n_nodes, 1), _next_pow2(n_triples, 128), max(n_local, 1))
+        c = self.cfg
+        d = _lib.ShapeDesc()
+        d.in_channels, d.out_channels, d.model_channels = c.in_channels, c.out_channels, c.model_channels
+        _fill_levels(d, c.channel_mult, c.attention_resolutions)
+        d.num_res_blocks, d.num_heads, d.context_dim = c.num_res_blocks, c.num_heads, c.context_dim
+        d.gconv_dim, d.enable_t_emb, d.latent_size = c.gconv_dim, int(c.enable_t_emb), c.image_size
+        d.max_nodes, d.max_triples, d.max_local_nodes = cap
+        d.precision = _lib.PREC_BF16 if self.precision == "bf16" else _lib.PREC_FP32
+        d.timesteps, d.ddim_steps = self.timesteps_total, self.ddim_steps
+        d.linear_start, d.linear_end = self.linear_start, self.linear_end
+        dev = next(self.parameters()).device
+        arr, n, keep = _lib.weights_table(self.state_dict(),
+                                          {"__timestep_freqs": _lib.timestep_freqs(c.model_channels, dev)})
+        h = C.c_void_p()
+        _lib.check(_lib.lib().echo_shape_create(C.byref(h), C.byref(d), arr, n))
+        self._handle, self._handle_key = h, (ver, cap)
+
+    def _destroy_handle(self):
+        if self._handle is not None:
+            _lib.lib().echo_shape_destroy(self._handle)
+            self._handle = None
+
+    def _prep(self, x, obj_embed, triples):
+        _lib.require_cuda(x, obj_embed, triples)
+        n = x.shape[0]
+        c = self.cfg
+        assert x.shape == (n, c.in_channels, c.image_size, c.image_size, c.image_size), tuple(x.shape)
+        obj_embed = obj_embed.reshape(obj_embed.shape[0], -1).float().contiguous()
+        assert obj_embed.shape[1] == c.context_dim
+        return n, x.float().contiguous(), obj_embed
+
+    @torch.no_grad()
+    def forward(self, x, obj_embed, triples, timesteps=None, context=None, y=None, **kwargs):
+        """x (N,3,16,16,16), obj_embed (N,1,1280), triples (T,3) i64, timesteps (N,) i64 -> e_t like x.  ``context``
+        is accepted and ignored as in the reference ("we dont use the previous context", openai_model_3d.py:843-844)."""
+        self._check_eval()
+        n, x, obj_embed = self._prep(x, obj_embed, triples)
+        timesteps = timesteps.to(torch.int64).contiguous()
+        self._ensure(n, triples.shape[0])
+        g = _lib.graph_for(triples, n)
+        out = torch.empty_like(x)
+        _lib.check(_lib.lib().echo_shape_forward(self._handle, g.h, _lib.ptr(x), _lib.ptr(obj_embed),
+                                                 _lib.ptr(timesteps), _lib.ptr(out), _lib.stream_ptr()))
+        return out
+
+    @torch.no_grad()
+    def ddim_step(self, x_t, obj_embed, triples, index: int, out: Optional[torch.Tensor] = None):
+        """One iteration of DDIMSampler.ddim_sampling: forward at ddim_timesteps[index] + x_prev update (eta = 0)."""
+        self._check_eval()
+        n, x_t, obj_embed = self._prep(x_t, obj_embed, triples)
+        self._ensure(n, triples.shape[0])
+        g = _lib.graph_for(triples, n)
+        out = torch.empty_like(x_t) if out is None else out
+        _lib.check(_lib.lib().echo_shape_step(self._handle, g.h, _lib.ptr(x_t), _lib.ptr(obj_embed), int(index),
+                                              _lib.ptr(out), _lib.stream_ptr()))
+        return out
+
+    # ---- per-object sharding: embed local objects, all-gather the 64-d codes, run the trunk locally ----
+    @torch.no_grad()
+    def embed_local(self, x_local, n_nodes, n_triples):
+        _lib.require_cuda(x_local)
+        nl = x_local.shape[0]
+        self._ensure(n_nodes, n_triples, nl)
+        codes = torch.empty(nl, self.cfg.gconv_dim, device=x_local.device)
+        x_local = x_local.float().contiguous()
+        _lib.check(_lib.lib().echo_shape_embed(self._handle, _lib.ptr(x_local), nl, _lib.ptr(codes), _lib.stream_ptr()))
+        return codes
+
+    @torch.no_grad()
+    def trunk_local(self, x_local, obj_begin, codes_all, obj_embed_all, triples, index: int = -1, timesteps_all=None,
+                    out: Optional[torch.Tensor] = None):
+        _lib.require_cuda(x_local, codes_all, obj_embed_all, triples)
+        n = codes_all.shape[0]
+        nl = x_local.shape[0]
+        self._ensure(n, triples.shape[0], nl)
+        g = _lib.graph_for(triples, n)
+        x_local = x_local.float().contiguous()
+        obj_embed_all = obj_embed_all.reshape(n, -1).float().contiguous()
+        codes_all = codes_all.float().contiguous()
+        out = torch.empty_like(x_local) if out is None else out
+        t = None if timesteps_all is None else timesteps_all.to(torch.int64).contiguous()
+        _lib.check(_lib.lib().echo_shape_trunk(self._handle, g.h, _lib.ptr(x_local), int(obj_begin), nl,
+                                               _lib.ptr(codes_all), _lib.ptr(obj_embed_all), _lib.ptr(t), int(index),
+                                               _lib.ptr(out), _lib.stream_ptr()))
+        return out
+
+    def last_latent(self, n_nodes) -> torch.Tensor:
+        """latent_shape_rel (N, context_dim) of the last call (a copy)."""
+        out = torch.empty(n_nodes, self.cfg.context_dim, device=next(self.parameters()).device)
+        _lib.check(_lib.lib().echo_shape_latent(self._handle, int(n_nodes), _lib.ptr(out), _lib.stream_ptr()))
+        return out
+
+    def schedule_tables(self):
+        self._ensure(1, 1)
+        coef = torch.empty(self.ddim_steps_effective(), 4, dtype=torch.float32)
+        ts = torch.empty(self.ddim_steps_effective(), dtype=torch.int32)
+        _lib.check(_lib.lib().echo_shape_schedule(self._handle, coef.data_ptr(), ts.data_ptr()))
+        return coef, ts
+
+    def ddim_steps_effective(self) -> int:
+        c = self.timesteps_total // self.ddim_steps
+        return len(range(0, self.timesteps_total, c))
+
+
+class DiffusionUNet(nn.Module):
+    """Conditioning router around UNet3DModel — diffusion_shape/network.py:11-43."""
+
+    def __init__(self, unet_params, vq_conf=None, conditioning_key=None, **extra):
+        super().__init__()
+        self.conditioning_key = conditioning_key
+        params = dict(unet_params)
+        params["conditioning_key"] = conditioning_key
+        params.update(extra)
+        self.diffusion_net = UNet3DModel(**params)
+
+    def forward(self, x, obj_embed, triples, t, c_concat: list = None, c_crossattn: list = None):
+        if self.conditioning_key != "crossattn":
+            raise EchoError("only conditioning_key='crossattn' is on the hot path")
+        cc = torch.cat(c_crossattn, 1)
+        return self.diffusion_net(x, obj_embed, triples, t, context=cc)

@@ -1,0 +1,193 @@
+/*
+ * echoscene_b200.h — C ABI of libechoscene_b200.so: the B200 (sm_100a) denoiser hot path of EchoScene.
+ *
+ * The reference (ymxlzgy/echoscene) has no FFI on this path: its seam is the Python class surface
+ * (GraphTripleConv / GraphTripleConvNet / UNet1DModel / UNet3DModel / DDIMSampler / DiffusionPoint).
+ * Each entry point below names the reference interface it replaces (file:line under the reference root).
+ * The only native precedent in the reference is extension/old_chamfer/chamfer_cuda.cpp:17-32 (returns int,
+ * printf on error, default stream); this ABI keeps "returns int" and fixes the rest:
+ *
+ *   - every call returns 0 on success and a negative code on failure; echo_last_error() gives the
+ *     thread-local message; nothing prints, aborts or synchronises the device;
+ *   - all tensor arguments are DEVICE pointers owned by the caller, dense row-major, fp32 / int64 exactly
+ *     as the reference's torch tensors are laid out (NCDHW for the latent);
+ *   - every compute call takes an explicit stream (a cudaStream_t passed as void*) and is asynchronous;
+ *   - handles own repacked weights and workspace; no allocation happens after *_create;
+ *   - a handle is re-entrant but not thread-safe; distinct handles may be used from distinct threads.
+ *
+ * No torch / libtorch types appear here: the library is loadable with ctypes, cgo, JNI, ...
+ */
+#ifndef ECHOSCENE_B200_H
+#define ECHOSCENE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECHO_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define ECHO_API __attribute__((visibility("default")))
+#else
+#define ECHO_API
+#endif
+
+/* error codes */
+#define ECHO_OK 0
+#define ECHO_ERR_INVALID (-1)   /* bad argument / shape / missing weight */
+#define ECHO_ERR_CUDA (-2)      /* CUDA runtime or driver error */
+#define ECHO_ERR_NOMEM (-3)     /* workspace exhausted */
+#define ECHO_ERR_UNSUPPORTED (-4)
+
+/* arithmetic of the dense contractions */
+#define ECHO_PREC_FP32 0        /* fp32 operands, fp32 FMA: the 1e-3 parity mode */
+#define ECHO_PREC_BF16 1        /* bf16 operands on tcgen05 tensor cores, fp32 accumulate, fp32 norms */
+
+typedef struct echo_graph echo_graph_t;     /* CSR of one (batched) scene graph; edges are constant over a chain */
+typedef struct echo_gcn echo_gcn_t;         /* GraphTripleConvNet */
+typedef struct echo_layout echo_layout_t;   /* UNet1DModel + DDPM schedule */
+typedef struct echo_shape echo_shape_t;     /* UNet3DModel + DDIM schedule */
+
+/* One named parameter / buffer of a reference state_dict (device pointer, fp32 or int64, reference layout). */
+typedef struct echo_weight {
+  const char* name;     /* state_dict key, e.g. "input_blocks.4.1.transformer_blocks.0.attn1.to_v.weight" */
+  const void* data;     /* device pointer */
+  int32_t ndim;
+  int32_t dtype;        /* 0 = float32, 1 = int64 (BatchNorm num_batches_tracked; ignored) */
+  int64_t shape[6];
+} echo_weight_t;
+
+/* GraphTripleConvNet(input_dim_obj, input_dim_pred, num_layers, hidden_dim, output_dim) — model/graph.py:214-244 */
+typedef struct echo_gcn_desc {
+  int32_t input_dim_obj, input_dim_pred, num_layers, hidden_dim;
+  int32_t output_dim;   /* <= 0: same as input_dim_obj for every layer */
+  int32_t max_nodes, max_triples;
+  float bn_eps;         /* 1e-5, model/layers.py:29-30 */
+} echo_gcn_desc_t;
+
+/* UNet1DModel(**denoiser_kwargs) — config/full_mp.yaml:24-39, denoise_net.py:451-756 */
+typedef struct echo_layout_desc {
+  int32_t in_channels, out_channels, model_channels;
+  int32_t num_levels;
+  int32_t channel_mult[8];
+  int32_t num_res_blocks;
+  int32_t num_attention_resolutions;
+  int32_t attention_resolutions[8];
+  int32_t num_heads;
+  int32_t context_dim;          /* crossattn_dim = concat_dim = 1280 */
+  int32_t obj_embed_dim;        /* 640 */
+  int32_t gconv_dim;            /* 64 */
+  int32_t enable_t_emb;
+  int32_t max_nodes, max_triples;
+  int32_t precision;            /* ECHO_PREC_* */
+  /* DDPM schedule — diffusion_ddpm.py:38-40,133-162 */
+  int32_t time_num;
+  float beta_start, beta_end;
+} echo_layout_desc_t;
+
+/* UNet3DModel(**unet.params) — config/sdfusion-txt2shape_mp.yaml:16-41, openai_model_3d.py:452-782 */
+typedef struct echo_shape_desc {
+  int32_t in_channels, out_channels, model_channels;
+  int32_t num_levels;
+  int32_t channel_mult[8];
+  int32_t num_res_blocks;
+  int32_t num_attention_resolutions;
+  int32_t attention_resolutions[8];
+  int32_t num_heads;
+  int32_t context_dim;          /* 1280 */
+  int32_t gconv_dim;            /* 64 */
+  int32_t enable_t_emb;
+  int32_t latent_size;          /* 16: latent is (C,16,16,16) */
+  int32_t max_nodes, max_triples;
+  int32_t max_local_nodes;      /* objects whose trunk runs on this GPU (== max_nodes on one GPU) */
+  int32_t precision;            /* ECHO_PREC_* */
+  /* DDIM schedule — ldm_diffusion_util.py:43-47,68-96; samplers/ddim.py:28-57 */
+  int32_t timesteps;            /* 1000 */
+  int32_t ddim_steps;           /* S */
+  float linear_start, linear_end;
+} echo_shape_desc_t;
+
+ECHO_API int echo_version(void);
+ECHO_API const char* echo_last_error(void);
+/* 1 if the library was built with the sm_100a tcgen05/TMA kernels AND the current device can run them. */
+ECHO_API int echo_has_tcgen05(void);
+/* kernels launched by this library on the calling thread since the last reset (bench.py's gpu_launches). */
+ECHO_API int64_t echo_launch_count(void);
+ECHO_API void echo_launch_count_reset(void);
+
+/* ---- graph: edges = stack([s, o]) of `triples` (T,3) int64 [s,p,o] — denoise_net.py:759-761, graph.py:142-143 */
+ECHO_API int echo_graph_create(echo_graph_t** out, const int64_t* triples_dev, int32_t n_triples, int32_t n_nodes, void* stream);
+ECHO_API void echo_graph_destroy(echo_graph_t* g);
+
+/* ---- obj_vecs[idx]: the bit-exact edge-index gather — model/graph.py:146-147 */
+ECHO_API int echo_gather_rows(const float* obj_vecs, const int64_t* idx, int64_t n_idx, int64_t n_rows, int64_t dim,
+                     float* out, void* stream);
+
+/* ---- GraphTripleConvNet.forward(obj_vecs, pred_vecs, edges) (eval mode) — model/graph.py:246-250, 124-211.
+ * Weight names are state_dict keys relative to the net ("gconvs.0.net1.0.weight", ...). */
+ECHO_API int echo_gcn_create(echo_gcn_t** out, const echo_gcn_desc_t* desc, const echo_weight_t* weights, int32_t n_weights);
+ECHO_API int echo_gcn_forward(echo_gcn_t* h, const echo_graph_t* g, const float* obj_vecs, const float* pred_vecs,
+                     float* obj_out, float* pred_out, void* stream);
+ECHO_API void echo_gcn_destroy(echo_gcn_t* h);
+
+/* ---- layout branch.
+ * echo_layout_forward == UNet1DModel.forward(box_t, obj_embed, triples, timesteps, context) — denoise_net.py:773-806;
+ *   box_t (N,8) f32, obj_embed (N,640) f32, timesteps (N,) i64 -> eps (N,8) f32 (the reference returns (N,8,1)).
+ * echo_layout_step == one iteration of GaussianDiffusion.p_sample_loop_sg — diffusion_ddpm.py:220-264,296-309,330-345:
+ *   forward at timestep t for all nodes, eps->x0, posterior mean, + [t>0] exp(0.5 logvar) * noise. */
+ECHO_API int echo_layout_create(echo_layout_t** out, const echo_layout_desc_t* desc, const echo_weight_t* weights, int32_t n_weights);
+ECHO_API int echo_layout_forward(echo_layout_t* h, const echo_graph_t* g, const float* box_t, const float* obj_embed,
+                        const int64_t* timesteps, float* eps_out, void* stream);
+ECHO_API int echo_layout_step(echo_layout_t* h, const echo_graph_t* g, const float* x_t, const float* obj_embed, int32_t t,
+                     const float* noise, float* x_prev, void* stream);
+ECHO_API void echo_layout_destroy(echo_layout_t* h);
+
+/* ---- shape branch.
+ * echo_shape_forward == UNet3DModel.forward(x, obj_embed, triples, timesteps, context) — openai_model_3d.py:816-863;
+ *   x (N,3,16,16,16) f32 NCDHW, obj_embed (N,1,1280) f32 (the `uc_s` conditioning), timesteps (N,) i64 -> e_t like x.
+ * echo_shape_step == one iteration of DDIMSampler.ddim_sampling / p_sample_ddim with eta = 0 —
+ *   samplers/ddim.py:156-181,184-262: forward at ddim_timesteps[index] and the x_prev update (:252-261).
+ * The two halves are exported separately so that a per-object shard can all-gather the 64-d shape codes between
+ * them: echo_shape_embed == the `shape_embeddings` stack (openai_model_3d.py:757-764, 805-806) on
+ * the local objects; echo_shape_trunk == everything else, with the codes of ALL nodes given and the trunk run on
+ * objects [obj_begin, obj_begin + n_local). */
+ECHO_API int echo_shape_create(echo_shape_t** out, const echo_shape_desc_t* desc, const echo_weight_t* weights, int32_t n_weights);
+ECHO_API int echo_shape_forward(echo_shape_t* h, const echo_graph_t* g, const float* x, const float* obj_embed,
+                       const int64_t* timesteps, float* eps_out, void* stream);
+ECHO_API int echo_shape_step(echo_shape_t* h, const echo_graph_t* g, const float* x_t, const float* obj_embed, int32_t ddim_index,
+                    float* x_prev, void* stream);
+ECHO_API int echo_shape_embed(echo_shape_t* h, const float* x_local, int32_t n_local, float* codes_out, void* stream);
+ECHO_API int echo_shape_trunk(echo_shape_t* h, const echo_graph_t* g, const float* x_local, int32_t obj_begin, int32_t n_local,
+                     const float* codes_all, const float* obj_embed_all, const int64_t* timesteps_all,
+                     int32_t ddim_index /* < 0: no sampler update, write e_t */, float* out_local, void* stream);
+/* copies latent_shape_rel of the last forward/trunk call, (n_nodes, context_dim) f32, into out_dev. */
+ECHO_API int echo_shape_latent(const echo_shape_t* h, int32_t n_nodes, float* out_dev, void* stream);
+ECHO_API void echo_shape_destroy(echo_shape_t* h);
+
+/* ---- schedule tables, for host-side checks against the reference's buffers.
+ * layout: 5 x time_num f32 [sqrt_recip_ac, sqrt_recipm1_ac, post_mean_coef1, post_mean_coef2, post_log_var_clipped]
+ * shape : ddim_steps x 4 f32 [sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev)] and the int32 DDIM timesteps. */
+ECHO_API int echo_layout_schedule(const echo_layout_t* h, float* host_out);
+ECHO_API int echo_shape_schedule(const echo_shape_t* h, float* host_coef_out, int32_t* host_timesteps_out);
+
+/* ---- single operators (each is one kernel family of the hot path), exported for per-kernel parity tests and
+ * profiling.  Layouts: activations channels-last (n, d, h, w, c) f32; conv weights in the reference layout
+ * (cout, cin, kd, kh, kw) f32.  precision selects the contraction arithmetic (ECHO_PREC_*). */
+ECHO_API int echo_op_conv3d(const float* x, int32_t n, int32_t d, int32_t h, int32_t w, int32_t cin,
+                   const float* weight, const float* bias, int32_t cout, int32_t ksize,
+                   int32_t stride_d, int32_t stride_hw, float* out, int32_t precision, void* stream);
+ECHO_API int echo_op_linear(const float* x, int64_t rows, int32_t cin, const float* weight, const float* bias, int32_t cout,
+                   float* out, int32_t precision, void* stream);
+ECHO_API int echo_op_group_norm(const float* x, int32_t n, int64_t voxels, int32_t c, int32_t groups, const float* gamma,
+                       const float* beta, float eps, int32_t silu, float* out, void* stream);
+ECHO_API int echo_op_layer_norm(const float* x, int64_t rows, int32_t c, const float* gamma, const float* beta, float eps,
+                       float* out, void* stream);
+ECHO_API int echo_op_attention(const float* qkv, int32_t n, int32_t tokens, int32_t heads, int32_t dim_head, float* out,
+                      int32_t precision, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECHOSCENE_B200_H */

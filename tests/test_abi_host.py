@@ -1,0 +1,84 @@
+"""CPU: the C-ABI library loads, exports every symbol include/echoscene_b200.h declares, rejects bad arguments with
+codes (never crashes), and the host-side mirror keeps the reference's state_dict keys."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from echoscene_b200 import _lib, arch, modules, synth
+from oracle import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "echoscene_b200.h")).read()
+    return sorted(set(re.findall(r"ECHO_API [^;()]*?\b(echo_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    names = _declared()
+    assert len(names) >= 29
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in the header but not exported"
+        assert n in _lib.PROTOTYPES, f"{n} has no ctypes prototype"
+    assert sorted(_lib.PROTOTYPES) == names
+    assert L.echo_version() == 1
+
+
+def test_bad_arguments_return_codes():
+    L = _lib.lib()
+    assert L.echo_gather_rows(None, None, 4, 4, 16, None, None) == -1
+    assert b"gather_rows" in L.echo_last_error()
+    h = C.c_void_p()
+    assert L.echo_layout_create(C.byref(h), None, None, 0) == -1
+    assert L.echo_shape_create(C.byref(h), None, None, 0) == -1
+    assert L.echo_gcn_create(C.byref(h), None, None, 0) == -1
+    assert L.echo_op_conv3d(None, 1, 1, 1, 1, 16, None, None, 16, 5, 1, 1, None, 0, None) == -1
+    with pytest.raises(_lib.EchoError):
+        _lib.check(-1)
+
+
+def test_state_dict_keys_match_reference_specs():
+    for cls, kw, specs in (
+        (modules.UNet1DModel, dict(in_channels=8, model_channels=512, out_channels=8, num_res_blocks=2,
+                                   attention_resolutions=[4, 2], channel_mult=[1, 1, 1, 1], num_heads=8,
+                                   use_spatial_transformer=True, concat_dim=1280, crossattn_dim=1280, enable_t_emb=True),
+         arch.unet1d_specs(cases.layout_cfg())),
+    ):
+        m = cls(**kw)
+        sd = m.state_dict()
+        assert list(sd.keys()) == list(specs.keys())
+        for k, s in specs.items():
+            assert tuple(sd[k].shape) == tuple(s.shape), k
+    g = modules.GraphTripleConvNet(768, 128, num_layers=5, hidden_dim=256, residual=True, pooling="avg",
+                                   mlp_normalization="batch", output_dim=1280)
+    assert list(g.state_dict().keys()) == list(arch.gcn_specs(cases.layout_cfg().gcn()).keys())
+    one = modules.GraphTripleConv(768, 128, output_dim=1280, hidden_dim=256, mlp_normalization="batch")
+    assert "net1.0.weight" in one.state_dict() and "linear_projection_pred.bias" in one.state_dict()
+
+
+def test_no_cpu_fallback():
+    g = modules.GraphTripleConvNet(64, 16, num_layers=1, hidden_dim=32, residual=True, mlp_normalization="batch")
+    with pytest.raises(_lib.EchoError):
+        g(torch.randn(4, 64), torch.randn(3, 16), torch.zeros(3, 2, dtype=torch.int64))
+    with pytest.raises(_lib.EchoError):
+        modules.GraphTripleConvNet(64, 16, pooling="wAvg")
+    g.train()
+    with pytest.raises(_lib.EchoError):
+        g(torch.randn(4, 64), torch.randn(3, 16), torch.zeros(3, 2, dtype=torch.int64))
+
+
+def test_synthetic_graph_contract():
+    g = synth.make_scene_graph(16, 64, 2)
+    t = g.triples
+    assert t.shape == (64, 3) and t.dtype == torch.int64
+    assert (t[:15, 1] == 0).all() and (t[:15, 2] == 15).all()          # "in" edges to the _scene_ node
+    assert (t[15:, 0] != t[15:, 2]).all() and t[15:, 1].min() >= 1 and t[:, 1].max() <= 15
+    b = synth.batch_scene_graphs([g, g])
+    assert b.n_nodes == 32 and (b.triples[64:, 0] == t[:, 0] + 16).all()
+    with pytest.raises(ValueError):
+        synth.make_scene_graph(2, 4, 0)

@@ -1,0 +1,74 @@
+"""CPU: the oracle restatement against the committed reference outputs (tests/golden/, made by oracle/gen_golden.py
+from the reference's own modules).  Bit-exact on the machine that generated them; 1e-6 elsewhere (BLAS blocking)."""
+import json
+import os
+
+import torch
+
+from echoscene_b200 import arch
+from oracle import cases, echoscene_oracle as orc
+from util import GOLD, gold, rel_err
+
+TOL = 1e-5
+
+
+def test_pinning_record():
+    pin = json.load(open(os.path.join(GOLD, "PINNING.json")))
+    for name, rec in pin["cases"].items():
+        if "rel_l2" in rec:
+            assert rec["rel_l2"] < 1e-6, name
+    assert pin["cases"]["ddim_tables_100"]["timesteps_equal"]
+    assert pin["param_counts"] == {"unet1d": arch.count_params(arch.unet1d_specs(cases.layout_cfg())),
+                                   "unet3d": arch.count_params(arch.unet3d_specs(cases.shape_cfg()))}
+
+
+def test_gcn_oracle_vs_reference():
+    cfg = cases.layout_cfg().gcn()
+    sd = arch.make_state_dict(arch.gcn_specs(cfg), cases.WEIGHT_SEED_GCN)
+    g, obj, pred = cases.gcn_inputs(cases.GCN_CASE, cfg)
+    edges, _ = orc.edges_of(g.triples)
+    G = gold("gcn_layout_n8.pt")
+    o_obj, o_pred = orc.graph_triple_conv_net(sd, "", obj, pred, edges)
+    assert max(rel_err(o_obj, G["obj"])) < TOL and max(rel_err(o_pred, G["pred"])) < TOL
+    l_obj, l_pred = orc.graph_triple_conv(sd, "gconvs.0.", obj, pred, edges)
+    assert max(rel_err(l_obj, G["layer0_obj"])) < TOL and max(rel_err(l_pred, G["layer0_pred"])) < TOL
+    assert torch.equal(orc.gather_rows(obj, edges[:, 0]), G["gather_s"])
+    assert torch.equal(orc.gather_rows(obj, edges[:, 1]), G["gather_o"])
+
+
+def test_layout_oracle_vs_reference():
+    cfg = cases.layout_cfg()
+    sd = arch.make_state_dict(arch.unet1d_specs(cfg), cases.WEIGHT_SEED_LAYOUT)
+    g, obj_embed, x, t = cases.layout_step_inputs(cases.LAYOUT_CASE, cfg)
+    G = gold("layout_n8.pt")
+    with torch.no_grad():
+        o = orc.unet1d_forward(sd, cfg, x, obj_embed, g.triples, t)
+    assert o.abs().max() > 0.1, "vacuous parity (zero-initialised output)"
+    assert max(rel_err(o, G["step"])) < TOL
+    g, obj_embed, x_T, noises = cases.layout_chain_inputs(cases.LAYOUT_CASE, cfg, cases.LAYOUT_CHAIN_STEPS)
+    with torch.no_grad():
+        c = orc.layout_chain(sd, cfg, obj_embed, g.triples, x_T, noises, cases.LAYOUT_CHAIN_STEPS)
+    assert max(rel_err(c, G["chain"])) < TOL
+
+
+def test_shape_oracle_vs_reference():
+    cfg = cases.shape_cfg()
+    sd = arch.make_state_dict(arch.unet3d_specs(cfg), cases.WEIGHT_SEED_SHAPE)
+    g, uc, x, t = cases.shape_step_inputs(cases.SHAPE_CASE, cfg)
+    G = gold("shape.pt")
+    with torch.no_grad():
+        o = orc.unet3d_forward(sd, cfg, x, uc, g.triples, t)
+    assert o.abs().max() > 0.1
+    assert max(rel_err(o, G["step"])) < TOL
+
+
+def test_schedules_closed_form():
+    s = orc.DDIMSchedule(100)
+    assert list(s.ddim_timesteps[:3]) == [1, 11, 21] and s.ddim_timesteps[-1] == 991 and len(s.ddim_timesteps) == 100
+    assert s.alphas_prev[0] == s.alphas[0] * 0 + s.alphas_prev[0] and (s.sigmas == 0).all()
+    d = orc.DDPMSchedule(time_num=1000)
+    assert d.tables().shape == (5, 1000) and torch.isfinite(d.tables()).all()
+    # x_{t-1} at t = 0 carries no noise (diffusion_ddpm.py:304-305)
+    x = torch.randn(4, 8)
+    e = torch.randn(4, 8)
+    assert torch.equal(orc.ddpm_update(d, x, e, 0, torch.randn(4, 8)), orc.ddpm_update(d, x, e, 0, torch.zeros(4, 8)))
