@@ -129,7 +129,7 @@ void echo_graph_destroy(echo_graph_t* g) {
 
 int echo_gather_rows(const float* obj, const int64_t* idx, int64_t n_idx, int64_t n_rows, int64_t dim, float* out, void* stream) {
   return guard([&] {
-    ECHO_CHECK(obj && out && (idx || n_idx == 0) && dim > 0 && n_rows >= 0, "gather_rows: bad arguments");
+    ECHO_CHECK(obj && (out || n_idx == 0) && (idx || n_idx == 0) && dim > 0 && n_rows >= 0, "gather_rows: bad arguments");
     gather_rows(obj, idx, n_idx, dim, out, (cudaStream_t)stream);
   });
 }
@@ -276,6 +276,8 @@ int echo_op_conv3d(const float* x, int32_t n, int32_t d, int32_t h, int32_t w, i
       convert(x, F32, xb, BF16, rows_in * cin, s);
       convert(wr, F32, wb, BF16, (int64_t)wn, s);
       g.A = xb; g.a_dt = BF16; g.W = wb; g.w_dt = BF16; g.out = ob; g.out_dt = BF16;
+      static Scratch s2d;
+      if (stride_hw == 2) g.scratch = s2d.get((size_t)rows_in * cin * 2);
       ECHO_CHECK(gemm_tc_supported(g), "op_conv3d: shape not supported by the tcgen05 kernel");
       gemm_tc(g, s);
       convert(ob, BF16, out, F32, rows_out * cout, s);
@@ -353,9 +355,11 @@ int echo_op_attention(const float* qkv, int32_t n, int32_t tokens, int32_t heads
     const int64_t rows = (int64_t)n * tokens;
     if (precision == ECHO_PREC_BF16) {
       ECHO_CHECK(tc_available(), "op_attention: bf16 precision needs sm_100a");
-      __nv_bfloat16* qb = (__nv_bfloat16*)g_scratch[1].get((size_t)rows * 3 * C * 2);
+      ECHO_CHECK(attention_bf16_supported(tokens, dh), "op_attention: tokens=%d dh=%d not supported by the flash kernel", tokens, dh);
+      const int dhp = attention_pad_dh(dh);
+      __nv_bfloat16* qb = (__nv_bfloat16*)g_scratch[1].get((size_t)rows * 3 * heads * dhp * 2);
       __nv_bfloat16* ob = (__nv_bfloat16*)g_scratch[3].get((size_t)rows * C * 2);
-      convert(qkv, F32, qb, BF16, rows * 3 * C, s);
+      pad_qkv(qkv, rows, heads, dh, dhp, qb, s);
       attention_bf16(qb, n, tokens, heads, dh, ob, s);
       convert(ob, BF16, out, F32, rows * C, s);
       return;

@@ -1,8 +1,513 @@
-// placeholder: replaced by the tcgen05 kernel
+// bf16 implicit-GEMM convolution / linear on the 5th-generation tensor cores (sm_100a): TMA -> shared memory ->
+// tcgen05.mma (accumulators in TMEM) -> tcgen05.ld epilogue.  This is the contraction kernel of ECHO_PREC_BF16:
+// every 3x3x3 / 1x1x1 Conv3d and every token-wise Linear of the shape UNet runs here.
+//
+//   out[m, n] = act( sum_{tap, c} A[vox(m) + off(tap), c] * W[n, tap*cin + c] + bias[n] + rowvec[obj(m), n] + res[m, n] )
+//
+// A is a channels-last bf16 activation (obj, d, h, w, c) described to TMA as a 5-D tensor (c, w, h, d, obj).  One CTA
+// tile is 128 output voxels forming a (bd, bh, bw) box inside one object; for every filter tap the SAME box shifted by
+// the tap offset is fetched with one TMA box copy (64 channels x 128 voxels, 128-byte swizzle), and the hardware's
+// out-of-bounds zero fill implements the convolution's zero padding, the channel tail (cin not a multiple of 64) and
+// partial tiles.  The box lands in shared memory exactly in the K-major SWIZZLE_128B layout tcgen05.mma consumes, so
+// there is no im2col buffer and no register staging.  W is a [cout, taps*cin] bf16 matrix (tap-major K), tiled
+// 64 x BLOCK_N by a 2-D TMA map.  Stride-(1,2,2) convolutions read a 4-phase space-to-depth copy of the input (one
+// cheap streaming pre-pass), which turns every tap into a unit-stride box of one phase.
+//
+// Warp roles (256 threads, 1 CTA / SM, persistent over tiles): warp 0 = TMA producer (one elected lane), warp 1 = MMA
+// issuer (one elected lane issues tcgen05.mma kind::f16, M=128, N=BLOCK_N, K=16), warp 2 = TMEM allocator,
+// warps 4-7 = epilogue (each owns 32 TMEM lanes = 32 output voxels).  Pipelines: STAGES-deep smem ring (full/empty
+// mbarriers, tcgen05.commit releases slots) and a 2-deep TMEM accumulator ring so the epilogue of tile i overlaps
+// the main loop of tile i+1.
 #include "ops.cuh"
+
+#include <cuda.h>
+#include <mutex>
+
 namespace echo {
-bool tc_available() { return false; }
-bool gemm_tc_supported(const GemmArgs&) { return false; }
-void gemm_tc(const GemmArgs&, cudaStream_t) { fail(ECHO_ERR_UNSUPPORTED, "gemm_tc: not built"); }
-void attention_bf16(const __nv_bfloat16*, int, int, int, int, __nv_bfloat16*, cudaStream_t) { fail(ECHO_ERR_UNSUPPORTED, "attention_bf16: not built"); }
+
+namespace {
+
+constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
+constexpr int MAX_BLOCK_N = 256;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;       // 16 KiB
+constexpr int B_STAGE_BYTES = MAX_BLOCK_N * BLOCK_K * 2;   // 32 KiB (BLOCK_N rows used)
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int MAX_TAPS = 27;
+
+struct TcParams {
+  // problem
+  int n_obj, od, oh, ow;        // output grid per object
+  int bd, bh, bw;               // tile box (bd*bh*bw == 128)
+  int tiles_d, tiles_h, tiles_w;
+  int num_m_tiles, num_n_tiles, block_n;
+  int cin, cout, taps, kblocks_per_tap;
+  int obj_mul;                  // 4 for the space-to-depth input (obj index = obj*4 + phase), else 1
+  int8_t tap_d[MAX_TAPS], tap_h[MAX_TAPS], tap_w[MAX_TAPS], tap_p[MAX_TAPS];
+  // epilogue
+  const float* bias;
+  const float* rowvec;
+  long long ld_rowvec;
+  const void* res;
+  int res_bf16;
+  long long ld_res;
+  void* out;
+  int out_bf16;
+  long long ldo;
+  int relu;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 %%rx;\n"
+      ".reg .pred %%px;\n"
+      "elect.sync %%rx|%%px, %1;\n"
+      "@%%px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate));
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (8-row atoms of 1024 bytes)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(1024 >> 4) << 32;   // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;             // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+  return d;
+}
+
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = (uint64_t*)(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint64_t* full_bar = bars;                   // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;         // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;     // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int kblocks = p.taps * p.kblocks_per_tap;
+  const uint32_t stage_bytes = (uint32_t)A_STAGE_BYTES + (uint32_t)p.block_n * BLOCK_K * 2;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_blk = tile / p.num_m_tiles, m_blk = tile - n_blk * p.num_m_tiles;
+        int r = m_blk;
+        const int tw = r % p.tiles_w; r /= p.tiles_w;
+        const int th = r % p.tiles_h; r /= p.tiles_h;
+        const int td = r % p.tiles_d; const int obj = r / p.tiles_d;
+        const int w0 = tw * p.bw, h0 = th * p.bh, d0 = td * p.bd;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int cw = w0 + p.tap_w[tap], chh = h0 + p.tap_h[tap], cd = d0 + p.tap_d[tap];
+          const int cn = obj * p.obj_mul + p.tap_p[tap];
+          for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+            tma_load_5d(&map_a, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, cw, chh, cd, cn);
+            tma_load_2d(&map_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, tap * p.cin + kb * BLOCK_K, n_blk * p.block_n);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    // instruction descriptor: D=f32, A=B=bf16, both K-major, N = block_n, M = 128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      mbar_wait(&tmem_empty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * MAX_BLOCK_N;
+      int kb_total = 0;
+      for (int tap = 0; tap < p.taps; ++tap) {
+        for (int kb = 0; kb < p.kblocks_per_tap; ++kb, ++kb_total) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
+            const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
+            int nk = (p.cin - kb * BLOCK_K + UMMA_K - 1) / UMMA_K;   // skip the zero-filled channel tail
+            nk = nk > BLOCK_K / UMMA_K ? BLOCK_K / UMMA_K : nk;
+            for (int k = 0; k < nk; ++k)
+              umma_bf16(tmem_d, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
+                        (kb_total | k) != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);                         // frees the smem slot when these MMAs retire
+            if (kb_total == kblocks - 1) umma_commit(&tmem_full[as]);   // accumulator complete -> epilogue
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue: TMEM -> registers -> global =================
+    const int ew = warp - 4;                       // TMEM lanes [32*ew, 32*ew+32)
+    const int row = ew * 32 + lane;                // tile row = box voxel index
+    const int ww = row % p.bw, hh = (row / p.bw) % p.bh, dd = row / (p.bw * p.bh);
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      const int n_blk = tile / p.num_m_tiles, m_blk = tile - n_blk * p.num_m_tiles;
+      int r = m_blk;
+      const int tw = r % p.tiles_w; r /= p.tiles_w;
+      const int th = r % p.tiles_h; r /= p.tiles_h;
+      const int td = r % p.tiles_d; const int obj = r / p.tiles_d;
+      const int ow_ = tw * p.bw + ww, oh_ = th * p.bh + hh, od_ = td * p.bd + dd;
+      const bool valid = ow_ < p.ow && oh_ < p.oh && od_ < p.od;
+      const long long orow = (((long long)obj * p.od + od_) * p.oh + oh_) * p.ow + ow_;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * MAX_BLOCK_N;
+      const int n_base = n_blk * p.block_n;
+      for (int c = 0; c < p.block_n; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c, v);
+        tmem_ld_wait();
+        const int n0 = n_base + c;
+        if (valid && n0 < p.cout) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+            }
+          }
+          if (p.rowvec) {
+            const float* rv = p.rowvec + (long long)obj * p.ld_rowvec + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(rv + j));
+              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+            }
+          }
+          if (p.res) {
+            if (p.res_bf16) {
+              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + orow * p.ld_res + n0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 u = __ldg(rp + q);
+                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[e]);
+                  f[q * 8 + e * 2] += __low2float(h2);
+                  f[q * 8 + e * 2 + 1] += __high2float(h2);
+                }
+              }
+            } else {
+              const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + orow * p.ld_res + n0);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 u = __ldg(rp + q);
+                f[q * 4] += u.x; f[q * 4 + 1] += u.y; f[q * 4 + 2] += u.z; f[q * 4 + 3] += u.w;
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (p.out_bf16) {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + n0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t w4[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[q * 8 + e * 2], f[q * 8 + e * 2 + 1]);
+                w4[e] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              op[q] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+          } else {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + n0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) op[q] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// 4-phase space-to-depth of a channels-last tensor: out[(obj*4 + ph*2 + pw), d, h/2, w/2, c] = x[obj, d, 2h'+ph, 2w'+pw, c]
+__global__ void s2d_kernel(const __nv_bfloat16* __restrict__ x, int n, int d, int h, int w, int C, long long nvec, __nv_bfloat16* __restrict__ out) {
+  const int cv = C / 8, h2 = h / 2, w2 = w / 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv); long long r = i / cv;
+    const int xw = (int)(r % w); r /= w;
+    const int xh = (int)(r % h); r /= h;
+    const int xd = (int)(r % d); const long long obj = r / d;
+    const int ph = xh & 1, pw = xw & 1;
+    const long long dst = ((((obj * 4 + ph * 2 + pw) * d + xd) * h2 + (xh >> 1)) * w2 + (xw >> 1)) * (long long)C + c8 * 8;
+    *reinterpret_cast<uint4*>(out + dst) = __ldg(reinterpret_cast<const uint4*>(x + i * 8));
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TcState {
+  bool checked = false, ok = false;
+  EncodeTiledFn encode = nullptr;
+  int sms = 148;
+};
+TcState g_tc;
+std::mutex g_tc_mu;
+
+void tc_init() {
+  std::lock_guard<std::mutex> lk(g_tc_mu);
+  if (g_tc.checked) return;
+  g_tc.checked = true;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { cudaGetLastError(); return; }
+  if (prop.major != 10) return;   // tcgen05 / TMEM: sm_100a family only
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+    cudaGetLastError();
+    return;
+  }
+  g_tc.encode = (EncodeTiledFn)fn;
+  g_tc.sms = prop.multiProcessorCount;
+  if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  g_tc.ok = true;
+}
+
+int pow2_floor(int v) {
+  int p = 1;
+  while (p * 2 <= v) p *= 2;
+  return p;
+}
+
+int pick_block_n(int cout) {
+  for (int bn = 256; bn >= 32; bn -= 32)
+    if (cout % bn == 0) return bn;
+  return 0;
+}
+
+}  // namespace
+
+bool tc_available() {
+  tc_init();
+  return g_tc.ok;
+}
+
+bool gemm_tc_supported(const GemmArgs& g) {
+  if (g.a_dt != BF16 || g.w_dt != BF16) return false;
+  if (g.nb0 * g.nb1 != 1 || g.alpha != 1.f || g.act > 1) return false;
+  if (g.cin % 16 != 0 || g.lda != g.cin || g.w_stride_k != 1 || g.w_stride_n != (int64_t)g.ktot()) return false;
+  if (g.cout % 32 != 0 || pick_block_n(g.cout) == 0) return false;
+  if (!((g.kd == 1 && g.kh == 1 && g.kw == 1) || (g.kd == 3 && g.kh == 3 && g.kw == 3))) return false;
+  if (g.pd != g.kd / 2 || g.ph != g.kh / 2 || g.pw != g.kw / 2 || g.sd != 1 || g.sh != g.sw) return false;
+  if (g.sh == 2) {
+    if (g.kd != 3 || (g.h & 1) || (g.w & 1) || !g.scratch) return false;
+    if (g.oh != g.h / 2 || g.ow != g.w / 2) return false;
+  } else if (g.sh == 1) {
+    if (g.od != g.d || g.oh != g.h || g.ow != g.w) return false;
+  } else {
+    return false;
+  }
+  if (((uintptr_t)g.A % 16) || ((uintptr_t)g.W % 16) || ((uintptr_t)g.out % 16)) return false;
+  if (g.res && (((uintptr_t)g.res % 16) || g.ld_res % 8)) return false;
+  if (g.ldo % 8) return false;
+  if (g.rowvec && (g.ld_rowvec % 4 || ((uintptr_t)g.rowvec % 16))) return false;
+  if (g.bias && ((uintptr_t)g.bias % 16)) return false;
+  return true;
+}
+
+void gemm_tc(const GemmArgs& g, cudaStream_t s) {
+  ECHO_CHECK(tc_available(), "gemm_tc: tcgen05 path unavailable on this device");
+  ECHO_CHECK(gemm_tc_supported(g), "gemm_tc: unsupported problem");
+  if (g.rows_out() == 0) return;
+  const bool s2 = g.sh == 2;
+  const __nv_bfloat16* a_ptr = (const __nv_bfloat16*)g.A;
+  int in_h = g.h, in_w = g.w, in_objs = g.n;
+  if (s2) {
+    const long long nvec = (long long)g.n * g.d * g.h * g.w * (g.cin / 8);
+    long long blocks = (nvec + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    s2d_kernel<<<(int)blocks, 256, 0, s>>>(a_ptr, g.n, g.d, g.h, g.w, g.cin, nvec, (__nv_bfloat16*)g.scratch);
+    ECHO_LAUNCH_CHECK();
+    a_ptr = (const __nv_bfloat16*)g.scratch;
+    in_h = g.h / 2;
+    in_w = g.w / 2;
+    in_objs = g.n * 4;
+  }
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_obj = g.n; p.od = g.od; p.oh = g.oh; p.ow = g.ow;
+  p.bw = pow2_floor(g.ow) > 128 ? 128 : pow2_floor(g.ow);
+  p.bh = pow2_floor(g.oh) > 128 / p.bw ? 128 / p.bw : pow2_floor(g.oh);
+  p.bd = 128 / (p.bw * p.bh);
+  p.tiles_w = cdiv(g.ow, p.bw); p.tiles_h = cdiv(g.oh, p.bh); p.tiles_d = cdiv(g.od, p.bd);
+  p.num_m_tiles = g.n * p.tiles_d * p.tiles_h * p.tiles_w;
+  p.block_n = pick_block_n(g.cout);
+  p.num_n_tiles = g.cout / p.block_n;
+  p.cin = g.cin; p.cout = g.cout; p.taps = g.kd * g.kh * g.kw;
+  p.kblocks_per_tap = cdiv(g.cin, BLOCK_K);
+  p.obj_mul = s2 ? 4 : 1;
+  for (int t = 0; t < p.taps; ++t) {
+    const int kd = t / (g.kh * g.kw), kh = (t / g.kw) % g.kh, kw = t % g.kw;
+    p.tap_d[t] = (int8_t)(kd - g.pd);
+    if (!s2) {
+      p.tap_h[t] = (int8_t)(kh - g.ph);
+      p.tap_w[t] = (int8_t)(kw - g.pw);
+      p.tap_p[t] = 0;
+    } else {   // input row 2*oh + kh - 1: kh=1 -> even phase, offset 0; kh=0 -> odd phase, offset -1; kh=2 -> odd phase, offset 0
+      const int ph = (kh == 1) ? 0 : 1, pw = (kw == 1) ? 0 : 1;
+      p.tap_h[t] = (int8_t)(kh == 0 ? -1 : 0);
+      p.tap_w[t] = (int8_t)(kw == 0 ? -1 : 0);
+      p.tap_p[t] = (int8_t)(ph * 2 + pw);
+    }
+  }
+  p.bias = g.bias; p.rowvec = g.rowvec; p.ld_rowvec = g.ld_rowvec;
+  p.res = g.res; p.res_bf16 = g.res_dt == BF16; p.ld_res = g.ld_res;
+  p.out = g.out; p.out_bf16 = g.out_dt == BF16; p.ldo = g.ldo; p.relu = g.act == 1;
+
+  CUtensorMap map_a, map_b;
+  {
+    const cuuint64_t dims[5] = {(cuuint64_t)g.cin, (cuuint64_t)in_w, (cuuint64_t)in_h, (cuuint64_t)g.d, (cuuint64_t)in_objs};
+    const cuuint64_t strides[4] = {(cuuint64_t)g.cin * 2, (cuuint64_t)g.cin * 2 * in_w, (cuuint64_t)g.cin * 2 * in_w * in_h,
+                                   (cuuint64_t)g.cin * 2 * in_w * in_h * g.d};
+    const cuuint32_t box[5] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bd, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_tc.encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)a_ptr, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ECHO_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed: %d", (int)r);
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)g.ktot(), (cuuint64_t)g.cout};
+    const cuuint64_t strides[1] = {(cuuint64_t)g.ktot() * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.block_n};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_tc.encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)g.W, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ECHO_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < g_tc.sms ? tiles : g_tc.sms;
+  gemm_tc_kernel<<<grid, 256, SMEM_BYTES, s>>>(map_a, map_b, p);
+  ECHO_LAUNCH_CHECK();
+}
+
+}  // namespace echo
+

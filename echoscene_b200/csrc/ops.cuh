@@ -37,6 +37,7 @@ struct GemmArgs {
   // batching: problem b = b0*nb1 + b1
   int nb0 = 1, nb1 = 1;
   int64_t a_bs0 = 0, a_bs1 = 0, w_bs0 = 0, w_bs1 = 0, o_bs0 = 0, o_bs1 = 0;
+  void* scratch = nullptr;          // tcgen05 path, stride-2 convs: room for a space-to-depth copy of A (same bytes)
   int64_t rows_out() const { return (int64_t)n * od * oh * ow; }
   int ktot() const { return kd * kh * kw * cin; }
 };
@@ -118,8 +119,11 @@ void ddim_update(const float* x_ncdhw, const void* e, DT edt, bool e_cl, int n, 
 // attention (fp32, materialised scores): qkv [n*tokens, 3*heads*dh] -> out [n*tokens, heads*dh]
 void attention_f32(const float* qkv, int n, int tokens, int heads, int dh, float* scores_ws, float* out, cudaStream_t s);
 size_t attention_f32_ws_floats(int n, int tokens, int heads);
-// attention (bf16 tensor-core flash kernel): qkv bf16, out bf16
+// attention (bf16 flash kernel): qkv bf16 [rows, 3*heads*attention_pad_dh(dh)] (heads zero-padded), out bf16 [rows, heads*dh]
+int attention_pad_dh(int dh);
+bool attention_bf16_supported(int tokens, int dh);
 void attention_bf16(const __nv_bfloat16* qkv, int n, int tokens, int heads, int dh, __nv_bfloat16* out, cudaStream_t s);
+void pad_qkv(const float* x, int64_t rows, int heads, int dh, int dhp, __nv_bfloat16* y, cudaStream_t s);
 
 // weight preparation
 // conv weight (cout, cin, taps) -> (cout, taps, cin); taps = kd*kh*kw

@@ -59,8 +59,11 @@ struct echo_shape {
   // implicit-GEMM conv / linear over a channels-last activation
   void contract(const Act& x, const ConvW& w, int k, int stride_hw, const float* rowvec, int64_t ld_rowvec, const Act* res,
                 const Act& out, cudaStream_t s) {
+    void* scratch = nullptr;
+    if (stride_hw == 2 && prec == ECHO_PREC_BF16 && x.dt == BF16) scratch = arena.alloc(x.bytes());
     if (dry) return;
     GemmArgs g;
+    g.scratch = scratch;
     g.A = x.p; g.a_dt = x.dt; g.n = x.n; g.d = x.d; g.h = x.h; g.w = x.w; g.cin = x.c; g.lda = x.c;
     g.od = out.d; g.oh = out.h; g.ow = out.w;
     g.kd = g.kh = g.kw = k; g.sd = 1; g.sh = g.sw = stride_hw; g.pd = g.ph = g.pw = k / 2;
@@ -121,9 +124,9 @@ struct echo_shape {
     Act l1 = new_act(x.n, x.d, x.h, x.w, C, adt);
     if (!dry) layer_norm(t0.p, t0.dt, rows, C, a.ln1.g, a.ln1.b, 1e-5f, l1.p, l1.dt, s);
     Act o = new_act(x.n, x.d, x.h, x.w, C, adt);
-    if (prec == ECHO_PREC_BF16 && adt == BF16 && tc_available()) {
-      Act qkv = new_act(x.n, x.d, x.h, x.w, 3 * C, BF16);
-      contract(l1, a.qkv, 1, 1, nullptr, 0, nullptr, qkv, s);
+    if (prec == ECHO_PREC_BF16 && adt == BF16 && a.qkv_pad.wb && attention_bf16_supported(tokens, a.dh)) {
+      Act qkv = new_act(x.n, x.d, x.h, x.w, a.qkv_pad.cout, BF16);
+      contract(l1, a.qkv_pad, 1, 1, nullptr, 0, nullptr, qkv, s);
       if (!dry) attention_bf16((const __nv_bfloat16*)qkv.p, x.n, tokens, a.heads, a.dh, (__nv_bfloat16*)o.p, s);
     } else {
       Act qkv = new_act(x.n, x.d, x.h, x.w, 3 * C, F32);

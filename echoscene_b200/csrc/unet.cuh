@@ -27,6 +27,7 @@ struct AttnW {
   NormW norm, ln1, ln3;
   ConvW proj_in, proj_out;
   ConvW qkv;        // [3C, C] = [to_q; to_k; to_v] of attn1 (bias-free)
+  ConvW qkv_pad;    // bf16 mode: same, every head zero-padded to attention_pad_dh(dh) rows -> [3*heads*dhp, C]
   ConvW attn1_out;  // [C, C] + bias
   ConvW attn2_out;  // [C, C] + bias, applied to attn2.to_v(context) (one context token: softmax == 1)
   ConvW v_only;     // attn1.to_v alone [C, C] (layout branch: one token, self-attention == to_out(to_v(x)))

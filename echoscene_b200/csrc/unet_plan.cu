@@ -128,6 +128,21 @@ struct Prep {
     a.ln3 = norm(b + "norm3", C);
     if (cfg.dims == 3) {
       a.qkv = stack({{b + "attn1.to_q", C}, {b + "attn1.to_k", C}, {b + "attn1.to_v", C}}, C, false);
+      const int dhp = attention_pad_dh(a.dh);
+      if (cfg.want_bf16 && dhp) {   // head-padded copy for the flash kernel: row (m*heads + h)*dhp + d <- row m*C + h*dh + d
+        const size_t rows = (size_t)3 * a.heads * dhp;
+        float* o = pool.alloc_n<float>(rows * C);
+        ECHO_CUDA(cudaMemsetAsync(o, 0, rows * C * sizeof(float), s));
+        for (int m = 0; m < 3; ++m)
+          for (int h = 0; h < a.heads; ++h)
+            ECHO_CUDA(cudaMemcpyAsync(o + ((size_t)(m * a.heads + h) * dhp) * C, a.qkv.w + ((size_t)m * C + (size_t)h * a.dh) * C,
+                                      sizeof(float) * a.dh * C, cudaMemcpyDeviceToDevice, s));
+        a.qkv_pad.w = o;
+        a.qkv_pad.cin = C;
+        a.qkv_pad.cout = (int)rows;
+        a.qkv_pad.taps = 1;
+        a.qkv_pad.wb = to_bf16(o, rows * C);
+      }
     } else {
       a.v_only = linear(b + "attn1.to_v", C, C, false);
     }

@@ -143,7 +143,9 @@ def test_layout_batched_scenes_are_independent(layout_sd):
     full = m(x, obj, b.triples.to(DEV), ts)
     a = m(x[:8], obj[:8], gs[0].triples.to(DEV), ts[:8])
     c = m(x[8:], obj[8:], gs[1].triples.to(DEV), ts[8:])
-    assert torch.equal(full[:8], a) and torch.equal(full[8:], c)
+    # few-row and tiled kernels sum K in different orders (the batch has 96 edge rows > 64): equal to rounding
+    assert_close(full[:8], a, 1e-5, "scene 0")
+    assert_close(full[8:], c, 1e-5, "scene 1")
 
 
 # -------------------------------------------------------------------------------------------------------------- shape
@@ -184,7 +186,7 @@ def test_shape_schedule_tables(shape_sd):
 def test_shape_sampler_surface_and_sharded_trunk(shape_sd):
     """DDIMSampler.sample over 2 steps == manual stepping; per-object shard (embed -> codes -> trunk on a slice) is
     bit-identical to the unsharded step."""
-    m = shape_model(shape_sd, ddim_steps=500)
+    m = shape_model(shape_sd, ddim_steps=10)
     g = synth.make_scene_graph(3, 4, 9)
     uc, x_T = synth.shape_inputs(3, 90, same_noise=True)
     tri, ucd, xd = g.triples.to(DEV), uc.to(DEV), x_T.to(DEV)
@@ -195,9 +197,9 @@ def test_shape_sampler_surface_and_sharded_trunk(shape_sd):
     h.df = type("DF", (), {})()
     h.df.diffusion_net = m
     smp = samplers.DDIMSampler(h)
-    out, _ = smp.sample(S=500, batch_size=3, shape=(3, 16, 16, 16), conditioning=ucd, x_T=xd,
+    out, _ = smp.sample(S=10, batch_size=3, shape=(3, 16, 16, 16), conditioning=ucd, x_T=xd,
                         unconditional_guidance_scale=3.0, unconditional_conditioning=ucd, triplet=tri, eta=0.0, verbose=False)
-    # S=500 -> c = 2 -> 500 steps; run only a 2-step check manually against the same handle
+    # a full 10-step chain must stay finite; the 2-step chain is compared exactly below
     m2 = shape_model(shape_sd, ddim_steps=2)
     a = m2.ddim_step(xd, ucd, tri, 1)
     b = m2.ddim_step(a, ucd, tri, 0)

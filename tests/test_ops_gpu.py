@@ -76,9 +76,9 @@ def test_group_norm(n, voxels, c, eps, silu):
     if silu:
         want = F.silu(want)
     want = want.permute(0, 2, 1)
-    xd = x.cuda()
+    xd, gd, bd = x.cuda(), gamma.cuda(), beta.cuda()
     out = torch.empty_like(xd)
-    _lib.check(_lib.lib().echo_op_group_norm(xd.data_ptr(), n, voxels, c, 32, gamma.cuda().data_ptr(), beta.cuda().data_ptr(),
+    _lib.check(_lib.lib().echo_op_group_norm(xd.data_ptr(), n, voxels, c, 32, gd.data_ptr(), bd.data_ptr(),
                                              eps, silu, out.data_ptr(), _lib.stream_ptr()))
     assert_close(out.cpu(), want, 1e-5, "group_norm")
 
@@ -89,9 +89,9 @@ def test_layer_norm(rows, c):
     x = torch.randn(rows, c, generator=g) * 3 - 1
     gamma, beta = torch.randn(c, generator=g), torch.randn(c, generator=g)
     want = F.layer_norm(x, (c,), gamma, beta, 1e-5)
-    xd = x.cuda()
+    xd, gd, bd = x.cuda(), gamma.cuda(), beta.cuda()
     out = torch.empty_like(xd)
-    _lib.check(_lib.lib().echo_op_layer_norm(xd.data_ptr(), rows, c, gamma.cuda().data_ptr(), beta.cuda().data_ptr(), 1e-5,
+    _lib.check(_lib.lib().echo_op_layer_norm(xd.data_ptr(), rows, c, gd.data_ptr(), bd.data_ptr(), 1e-5,
                                              out.data_ptr(), _lib.stream_ptr()))
     assert_close(out.cpu(), want, 1e-5, "layer_norm")
 
