@@ -98,43 +98,62 @@ __global__ void gn_partial_kernel(const T* __restrict__ x, int64_t V, int C, int
   }
 }
 
+// one warp per (object, group): lanes stride over the chunk partials, fixed-pattern shuffle tree in double
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int n, int nchunks, int groups, double count,
                                    float eps, float* __restrict__ stats) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= n * groups) return;
   const int obj = i / groups, g = i % groups;
   double a = 0.0, b = 0.0;
-  for (int c = 0; c < nchunks; ++c) {
-    const float* p = partial + (((int64_t)obj * nchunks + c) * groups + g) * 2;
-    a += (double)p[0];
-    b += (double)p[1];
+  for (int c = lane; c < nchunks; c += 32) {
+    const float2 p = *reinterpret_cast<const float2*>(partial + (((int64_t)obj * nchunks + c) * groups + g) * 2);
+    a += (double)p.x;
+    b += (double)p.y;
   }
-  const double mean = a / count;
-  double var = b / count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  stats[2 * i] = (float)mean;
-  stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane == 0) {
+    const double mean = a / count;
+    double var = b / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[2 * i] = (float)mean;
+    stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
 }
 
-template <class TI, class TO>
+// Block (row chunk, obj): thread (q, ry) owns channel quad q with its affine terms folded into (scale, shift) once,
+// and streams rows ry, ry+RY, ... of the chunk with 16-byte accesses.
+constexpr int GN_APPLY_ROWS = 64;
+template <class TI, class TO, bool FAST>
 __global__ void gn_apply_kernel(const TI* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, int64_t V, int C, int groups, int silu, int64_t nquads_total,
+                                const float* __restrict__ beta, int64_t V, int C, int groups, int silu, int nquad, int RY,
                                 TO* __restrict__ y) {
-  const int nquad = C / 4, cpg = C / groups;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nquads_total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / nquad;
-    const int c0 = (int)(i - row * nquad) * 4;
-    const int obj = (int)(row / V);
+  const int q = threadIdx.x % nquad, ry = threadIdx.x / nquad;
+  if (ry >= RY) return;
+  const int obj = blockIdx.y, cpg = C / groups, c0 = q * 4;
+  float sc[4], sh[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float* st = stats + ((int64_t)obj * groups + (c0 + j) / cpg) * 2;
+    sc[j] = st[1] * __ldg(gamma + c0 + j);
+    sh[j] = __ldg(beta + c0 + j) - st[0] * sc[j];
+  }
+  const int64_t r0 = (int64_t)blockIdx.x * GN_APPLY_ROWS;
+  const int64_t r1 = min(r0 + (int64_t)GN_APPLY_ROWS, V);
+  const TI* xb = x + ((int64_t)obj * V) * C + c0;
+  TO* yb = y + ((int64_t)obj * V) * C + c0;
+  for (int64_t r = r0 + ry; r < r1; r += RY) {
     float v[4];
-    load4<TI>(x + row * C + c0, v);
+    load4<TI>(xb + r * C, v);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int c = c0 + j;
-      const float* st = stats + ((int64_t)obj * groups + c / cpg) * 2;
-      float t = (v[j] - st[0]) * st[1] * __ldg(gamma + c) + __ldg(beta + c);
-      v[j] = silu ? silu_f(t) : t;
+      const float t = fmaf(v[j], sc[j], sh[j]);
+      v[j] = silu ? (FAST ? __fdividef(t, 1.f + __expf(-t)) : silu_f(t)) : t;
     }
-    store4<TO>(y + row * C + c0, v);
+    store4<TO>(yb + r * C, v);
   }
 }
 
@@ -271,12 +290,12 @@ __global__ void ncdhw_to_cl_kernel(const float* __restrict__ x, int n, int c, in
 }
 
 template <class TI>
-__global__ void cl_to_ncdhw_kernel(const TI* __restrict__ x, int n, int c, int64_t V, float* __restrict__ out) {
+__global__ void cl_to_ncdhw_kernel(const TI* __restrict__ x, int n, int c, int64_t V, int ld, float* __restrict__ out) {
   const int64_t total = (int64_t)n * c * V;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t v = i % V; const int64_t r = i / V;     // r = obj*c + ch
     const int64_t obj = r / c; const int ch = (int)(r - obj * c);
-    out[i] = load1<TI>(x + (obj * V + v) * c + ch);
+    out[i] = load1<TI>(x + (obj * V + v) * ld + ch);
   }
 }
 
@@ -374,7 +393,7 @@ __global__ void ddpm_update_kernel(const float* __restrict__ x, const float* __r
 
 // p_sample_ddim tail, sigma = 0 (samplers/ddim.py:252-261)
 template <class TE>
-__global__ void ddim_update_kernel(const float* __restrict__ x, const TE* __restrict__ e, int e_cl, int n, int c, int64_t V,
+__global__ void ddim_update_kernel(const float* __restrict__ x, const TE* __restrict__ e, int e_cl, int n, int c, int64_t V, int ld,
                                    const float* __restrict__ coef, float* __restrict__ out) {
   const float sa = coef[0], s1m = coef[1], sap = coef[2], sdir = coef[3];
   const int64_t total = (int64_t)n * c * V;
@@ -383,7 +402,7 @@ __global__ void ddim_update_kernel(const float* __restrict__ x, const TE* __rest
     if (e_cl) {
       const int64_t v = i % V; const int64_t r = i / V;
       const int64_t obj = r / c; const int ch = (int)(r - obj * c);
-      ev = load1<TE>(e + (obj * V + v) * c + ch);
+      ev = load1<TE>(e + (obj * V + v) * ld + ch);
     } else {
       ev = load1<TE>(e + i);
     }
@@ -460,19 +479,24 @@ void gn_stats(const Act& x, int groups, float eps, float* stats, float* partial,
     gn_partial_kernel<__nv_bfloat16><<<grid, threads, smem, s>>>((const __nv_bfloat16*)x.p, V, x.c, groups, nquad, RY, partial, nchunks);
   ECHO_LAUNCH_CHECK();
   const int tot = x.n * groups;
-  gn_finalize_kernel<<<cdiv(tot, 128), 128, 0, s>>>(partial, x.n, nchunks, groups, (double)V * (x.c / groups), eps, stats);
+  gn_finalize_kernel<<<cdiv((int64_t)tot * 32, 256), 256, 0, s>>>(partial, x.n, nchunks, groups, (double)V * (x.c / groups), eps, stats);
   ECHO_LAUNCH_CHECK();
 }
 
 void gn_apply(const Act& x, const float* stats, const float* gamma, const float* beta, int groups, bool silu, const Act& out,
               cudaStream_t s) {
-  const int64_t nq = x.rows() * (x.c / 4);
-  const int grid = grid_for(nq, 256);
-#define GA(TI, TO) gn_apply_kernel<TI, TO><<<grid, 256, 0, s>>>((const TI*)x.p, stats, gamma, beta, x.voxels(), x.c, groups, silu ? 1 : 0, nq, (TO*)out.p)
-  if (x.dt == F32 && out.dt == F32) GA(float, float);
-  else if (x.dt == F32) GA(float, __nv_bfloat16);
-  else if (out.dt == F32) GA(__nv_bfloat16, float);
-  else GA(__nv_bfloat16, __nv_bfloat16);
+  const int nquad = x.c / 4;
+  int RY = 256 / nquad;
+  if (RY < 1) RY = 1;
+  if (RY > GN_APPLY_ROWS) RY = GN_APPLY_ROWS;
+  const int threads = ((nquad * RY + 31) / 32) * 32;
+  const int64_t V = x.voxels();
+  dim3 grid(cdiv(V, GN_APPLY_ROWS), x.n);
+#define GA(TI, TO, FAST) gn_apply_kernel<TI, TO, FAST><<<grid, threads, 0, s>>>((const TI*)x.p, stats, gamma, beta, V, x.c, groups, silu ? 1 : 0, nquad, RY, (TO*)out.p)
+  if (x.dt == F32 && out.dt == F32) GA(float, float, false);
+  else if (x.dt == F32) GA(float, __nv_bfloat16, true);
+  else if (out.dt == F32) GA(__nv_bfloat16, float, false);
+  else GA(__nv_bfloat16, __nv_bfloat16, true);
 #undef GA
   ECHO_LAUNCH_CHECK();
 }
@@ -545,10 +569,10 @@ void ncdhw_to_cl(const float* x, int n, int c, int64_t V, void* out, DT odt, cud
   ECHO_LAUNCH_CHECK();
 }
 
-void cl_to_ncdhw(const void* x, DT xdt, int n, int c, int64_t V, float* out, cudaStream_t s) {
+void cl_to_ncdhw(const void* x, DT xdt, int n, int c, int64_t V, int ld, float* out, cudaStream_t s) {
   const int grid = grid_for((int64_t)n * c * V, 256);
-  if (xdt == F32) cl_to_ncdhw_kernel<float><<<grid, 256, 0, s>>>((const float*)x, n, c, V, out);
-  else cl_to_ncdhw_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, n, c, V, out);
+  if (xdt == F32) cl_to_ncdhw_kernel<float><<<grid, 256, 0, s>>>((const float*)x, n, c, V, ld, out);
+  else cl_to_ncdhw_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, n, c, V, ld, out);
   ECHO_LAUNCH_CHECK();
 }
 
@@ -608,11 +632,11 @@ void ddpm_update(const float* x, const float* eps, const float* noise, const flo
   ECHO_LAUNCH_CHECK();
 }
 
-void ddim_update(const float* x, const void* e, DT edt, bool e_cl, int n, int c, int64_t V, const float* coef4, float* out,
+void ddim_update(const float* x, const void* e, DT edt, bool e_cl, int n, int c, int64_t V, int ld, const float* coef4, float* out,
                  cudaStream_t s) {
   const int grid = grid_for((int64_t)n * c * V, 256);
-  if (edt == F32) ddim_update_kernel<float><<<grid, 256, 0, s>>>(x, (const float*)e, e_cl ? 1 : 0, n, c, V, coef4, out);
-  else ddim_update_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(x, (const __nv_bfloat16*)e, e_cl ? 1 : 0, n, c, V, coef4, out);
+  if (edt == F32) ddim_update_kernel<float><<<grid, 256, 0, s>>>(x, (const float*)e, e_cl ? 1 : 0, n, c, V, ld, coef4, out);
+  else ddim_update_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(x, (const __nv_bfloat16*)e, e_cl ? 1 : 0, n, c, V, ld, coef4, out);
   ECHO_LAUNCH_CHECK();
 }
 

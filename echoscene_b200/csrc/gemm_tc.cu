@@ -55,6 +55,7 @@ struct TcParams {
   int out_bf16;
   long long ldo;
   int relu;
+  int geglu;   // epilogue: tile columns are [a (block_n/2) | g (block_n/2)]; out = (a+ba) * gelu_erf(g+bg), out width cout/2
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------------
@@ -256,6 +257,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * MAX_BLOCK_N;
       const int n_base = n_blk * p.block_n;
+      if (p.geglu) {
+        // GEGLU fused into the producing GEMM (attention.py:39-46): the weight rows were permuted at load time so that
+        // one tile holds 128 `a` columns followed by their 128 gate columns
+        const int half = p.block_n >> 1;
+        for (int c = 0; c < half; c += 32) {
+          uint32_t va[32], vg[32];
+          tmem_ld32(taddr + c, va);
+          tmem_ld32(taddr + half + c, vg);
+          tmem_ld_wait();
+          if (valid) {
+            const float* ba = p.bias + n_base + c;
+            const float* bg = p.bias + n_base + half + c;
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float a = __uint_as_float(va[j]) + __ldg(ba + j);
+              const float g = __uint_as_float(vg[j]) + __ldg(bg + j);
+              f[j] = a * (0.5f * g * (1.f + erff(g * 0.70710678118654752440f)));
+            }
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + n_blk * half + c);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t w4[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[q * 8 + e * 2], f[q * 8 + e * 2 + 1]);
+                w4[e] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              op[q] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+          }
+        }
+      } else
       for (int c = 0; c < p.block_n; c += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + c, v);
@@ -414,6 +448,7 @@ bool gemm_tc_supported(const GemmArgs& g) {
   if (g.nb0 * g.nb1 != 1 || g.alpha != 1.f || g.act > 1) return false;
   if (g.cin % 16 != 0 || g.lda != g.cin || g.w_stride_k != 1 || g.w_stride_n != (int64_t)g.ktot()) return false;
   if (g.cout % 32 != 0 || pick_block_n(g.cout) == 0) return false;
+  if (g.epi == 1 && (g.cout % 256 != 0 || g.res || g.rowvec || !g.bias || g.out_dt != BF16 || g.act != 0)) return false;
   if (!((g.kd == 1 && g.kh == 1 && g.kw == 1) || (g.kd == 3 && g.kh == 3 && g.kw == 3))) return false;
   if (g.pd != g.kd / 2 || g.ph != g.kh / 2 || g.pw != g.kw / 2 || g.sd != 1 || g.sh != g.sw) return false;
   if (g.sh == 2) {
@@ -480,6 +515,8 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   p.bias = g.bias; p.rowvec = g.rowvec; p.ld_rowvec = g.ld_rowvec;
   p.res = g.res; p.res_bf16 = g.res_dt == BF16; p.ld_res = g.ld_res;
   p.out = g.out; p.out_bf16 = g.out_dt == BF16; p.ldo = g.ldo; p.relu = g.act == 1;
+  p.geglu = g.epi == 1;
+  if (p.geglu) { p.block_n = 256; p.num_n_tiles = g.cout / 256; }
 
   CUtensorMap map_a, map_b;
   {

@@ -1,17 +1,20 @@
 // Few-row linear layers: Y[M, nout] = epi( f(X)[M, K] @ W[nout, K]^T ), M = nodes or edges of one scene graph.
 //
-// These are the layout branch's ~100 contractions per step, the GraphTripleConv MLPs and every per-object vector
-// op of the shape step (time MLP, ResBlock emb_layers, attn2 to_v/to_out).  With M <= a few dozen rows they are
-// bound by streaming W from HBM once: each warp owns RN output features, the 32 lanes split K in 16-byte pieces
-// (512 contiguous bytes of a weight row per warp-load), X is re-read through L1 (it is tiny), and the cross-lane
-// reduction is a fixed-order shuffle tree, so results are deterministic.
+// These are the layout branch's ~180 contractions per step, the GraphTripleConv MLPs and every per-object vector op of
+// the shape step (time MLP, ResBlock emb_layers, attn2 to_v/to_out).  With a few dozen rows they are bound by streaming
+// W from HBM once, and — being tiny — by how many bytes are in flight: a launch must put >= ~1200 warps on the chip.
+//
+// Layout of one CTA: RN = 4 output features x MT rows, K split over the CTA's WK warps (1..8, chosen per launch so that
+// small-nout layers still fill the machine).  Inside a warp the 32 lanes split the K slice in 16-byte pieces (512
+// contiguous bytes of a weight row per warp-load, all RN x unroll loads issued before the FMAs), X is re-read through L1
+// (it is tiny).  Reduction: a halving butterfly over the lanes (62 shuffles for 64 accumulators instead of 320), then a
+// fixed-order sum over the WK warps through shared memory — deterministic, no atomics.
 #include "ops.cuh"
 
 namespace echo {
 namespace {
 
-constexpr int MT = 8;   // rows per pass (register tile)
-constexpr int RN = 4;   // output features per warp
+constexpr int RN = 4;   // output features per CTA
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
 
@@ -29,22 +32,42 @@ __device__ __forceinline__ void ldw4<__nv_bfloat16>(const __nv_bfloat16* p, floa
   v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
 }
 
-template <class TW>
-__global__ void __launch_bounds__(256) linear_rows_kernel(const LinArgs a) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int n0 = warp * RN;
-  if (n0 >= a.nout) return;
+// Halving butterfly: on return lane l holds the full sums of elements [base, base + N/32) in v[0 .. N/32).
+template <int N>
+__device__ __forceinline__ int butterfly(float (&v)[N], int lane) {
+  int base = 0;
+#pragma unroll
+  for (int off = 16, n = N; off >= 1; off >>= 1, n >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = up ? v[i] : v[i + n / 2];
+      const float keep = up ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+    if (up) base += n / 2;
+  }
+  return base;
+}
+
+template <class TW, int MT>
+__global__ void __launch_bounds__(256) linear_rows_kernel(const LinArgs a, int k_slice) {
+  constexpr int N = MT * RN;
+  extern __shared__ float part[];   // [WK][N]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, WK = blockDim.x >> 5;
+  const int n0 = blockIdx.x * RN;
   const int m0 = blockIdx.y * MT;
   const TW* __restrict__ W = reinterpret_cast<const TW*>(a.W);
   const int64_t ldw = a.ldw ? a.ldw : a.K;
+  const int k_beg = warp * k_slice;
+  const int k_end = min(a.K, k_beg + k_slice);
 
-  float acc[MT][RN];
+  float acc[N];
 #pragma unroll
-  for (int i = 0; i < MT; ++i)
-#pragma unroll
-    for (int j = 0; j < RN; ++j) acc[i][j] = 0.f;
+  for (int i = 0; i < N; ++i) acc[i] = 0.f;
 
-  for (int k = lane * 4; k < a.K; k += 128) {
+#pragma unroll 2
+  for (int k = k_beg + lane * 4; k < k_end; k += 128) {
     float w[RN][4];
 #pragma unroll
     for (int j = 0; j < RN; ++j) {
@@ -58,41 +81,50 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(const LinArgs a) {
         if (a.in_act == 1) { xv.x = silu_f(xv.x); xv.y = silu_f(xv.y); xv.z = silu_f(xv.z); xv.w = silu_f(xv.w); }
 #pragma unroll
         for (int j = 0; j < RN; ++j) {
-          acc[i][j] = fmaf(xv.x, w[j][0], acc[i][j]);
-          acc[i][j] = fmaf(xv.y, w[j][1], acc[i][j]);
-          acc[i][j] = fmaf(xv.z, w[j][2], acc[i][j]);
-          acc[i][j] = fmaf(xv.w, w[j][3], acc[i][j]);
+          float s = acc[i * RN + j];
+          s = fmaf(xv.x, w[j][0], s);
+          s = fmaf(xv.y, w[j][1], s);
+          s = fmaf(xv.z, w[j][2], s);
+          s = fmaf(xv.w, w[j][3], s);
+          acc[i * RN + j] = s;
         }
       }
     }
   }
+  const int base = butterfly<N>(acc, lane);
 #pragma unroll
-  for (int i = 0; i < MT; ++i)
+  for (int e = 0; e < N / 32; ++e) part[warp * N + base + e] = acc[e];
+  __syncthreads();
+  if (warp == 0) {
 #pragma unroll
-    for (int j = 0; j < RN; ++j) {
-      float v = acc[i][j];
-#pragma unroll
-      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      acc[i][j] = v;
-    }
-  // lane l writes output (i, j) = (l / RN, l % RN)
-  const int i = lane / RN, j = lane % RN;
-  if (i < MT) {
-    float v = 0.f;
-#pragma unroll
-    for (int ii = 0; ii < MT; ++ii)
-#pragma unroll
-      for (int jj = 0; jj < RN; ++jj)
-        if (ii == i && jj == j) v = acc[ii][jj];
-    const int m = m0 + i, n = n0 + j;
-    if (m < a.M && n < a.nout) {
-      if (a.bias) v += __ldg(a.bias + n);
-      if (a.act == 1) v = fmaxf(v, 0.f);
-      else if (a.act == 2) v = silu_f(v);
-      if (a.res) v += a.res[(int64_t)m * a.ld_res + n];
-      a.Y[(int64_t)m * a.ldy + n] = v;
+    for (int e = 0; e < N / 32; ++e) {
+      const int idx = lane * (N / 32) + e;   // (i, j) = (idx / RN, idx % RN)
+      float v = 0.f;
+      for (int wk = 0; wk < WK; ++wk) v += part[wk * N + idx];
+      const int m = m0 + idx / RN, n = n0 + idx % RN;
+      if (m < a.M && n < a.nout) {
+        if (a.bias) v += __ldg(a.bias + n);
+        if (a.act == 1) v = fmaxf(v, 0.f);
+        else if (a.act == 2) v = silu_f(v);
+        if (a.res) v += a.res[(int64_t)m * a.ld_res + n];
+        a.Y[(int64_t)m * a.ldy + n] = v;
+      }
     }
   }
+}
+
+template <class TW>
+void launch(const LinArgs& a, cudaStream_t s) {
+  const int MT = a.M <= 8 ? 8 : 16;
+  const int row_tiles = cdiv(a.M, MT);
+  const int base_warps = cdiv(a.nout, RN) * row_tiles;
+  int wk = 1;
+  while (wk < 8 && base_warps * wk < 1184 && a.K / (wk * 2) >= 128) wk *= 2;
+  const int k_slice = cdiv(cdiv(a.K, wk), 128) * 128;
+  dim3 grid(cdiv(a.nout, RN), row_tiles);
+  const size_t smem = (size_t)wk * MT * RN * sizeof(float);
+  if (MT == 8) linear_rows_kernel<TW, 8><<<grid, 32 * wk, smem, s>>>(a, k_slice);
+  else linear_rows_kernel<TW, 16><<<grid, 32 * wk, smem, s>>>(a, k_slice);
 }
 
 }  // namespace
@@ -103,10 +135,9 @@ void linear_rows(const LinArgs& a, cudaStream_t s) {
   ECHO_CHECK(a.K % 4 == 0 && a.ldx % 4 == 0 && ((uintptr_t)a.X % 16) == 0 && ((uintptr_t)a.W % 16) == 0,
              "linear_rows: K=%d ldx=%lld must be multiples of 4 and 16-byte aligned", a.K, (long long)a.ldx);
   if (a.M == 0) return;
-  const int warps = cdiv(a.nout, RN);
-  dim3 grid(cdiv((int64_t)warps * 32, 256), cdiv(a.M, MT));
-  if (a.w_dt == F32) linear_rows_kernel<float><<<grid, 256, 0, s>>>(a);
-  else linear_rows_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(a);
+  ECHO_CHECK(cdiv(a.M, 8) <= 65535, "linear_rows: too many rows");
+  if (a.w_dt == F32) launch<float>(a, s);
+  else launch<__nv_bfloat16>(a, s);
   ECHO_LAUNCH_CHECK();
 }
 

@@ -33,6 +33,7 @@ struct GemmArgs {
   DT out_dt = F32;
   int64_t ldo = 0;
   int act = 0;                      // 0 none, 1 relu
+  int epi = 0;                      // tcgen05 path only: 1 = GEGLU epilogue (W rows tiled [128 a | 128 g]; out width cout/2)
   float alpha = 1.f;                // scales the accumulator before the epilogue adds
   // batching: problem b = b0*nb1 + b1
   int nb0 = 1, nb1 = 1;
@@ -91,7 +92,8 @@ void concat_channels(const Act& a, const Act& b, const Act& out, cudaStream_t s)
 void upsample_hw2(const Act& x, const Act& out, cudaStream_t s);              // nearest x(1,2,2)
 void maxpool3d(const Act& x, int k, int stride, const Act& out, cudaStream_t s);
 void ncdhw_to_cl(const float* x, int n, int c, int64_t voxels, void* out, DT odt, cudaStream_t s);
-void cl_to_ncdhw(const void* x, DT xdt, int n, int c, int64_t voxels, float* out, cudaStream_t s);
+// x channels-last with row stride ld (>= c) -> out (n, c, voxels)
+void cl_to_ncdhw(const void* x, DT xdt, int n, int c, int64_t voxels, int ld, float* out, cudaStream_t s);
 void convert(const void* x, DT xdt, void* y, DT ydt, int64_t count, cudaStream_t s);
 // y[r, :] += v[r / rows_per_obj, :]
 void add_rowvec(void* y, DT ydt, int64_t rows, int C, const float* v, int64_t ldv, int64_t rows_per_obj, cudaStream_t s);
@@ -113,7 +115,7 @@ void flatten_ncdhw(const Act& x, float* out, cudaStream_t s);
 void ddpm_update(const float* x, const float* eps, const float* noise, const float* tab, int T, int t, int64_t count,
                  float* out, cudaStream_t s);
 // DDIM eta=0 on an NCDHW latent, e_t given channels-last (or NCDHW when e_cl == false)
-void ddim_update(const float* x_ncdhw, const void* e, DT edt, bool e_cl, int n, int c, int64_t voxels,
+void ddim_update(const float* x_ncdhw, const void* e, DT edt, bool e_cl, int n, int c, int64_t voxels, int e_ld,
                  const float* coef4 /* device, 4 floats */, float* out_ncdhw, cudaStream_t s);
 
 // attention (fp32, materialised scores): qkv [n*tokens, 3*heads*dh] -> out [n*tokens, heads*dh]

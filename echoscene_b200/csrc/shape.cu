@@ -148,10 +148,25 @@ struct echo_shape {
     // feed-forward (GEGLU)
     Act l3 = new_act(x.n, x.d, x.h, x.w, C, adt);
     if (!dry) layer_norm(t1.p, t1.dt, rows, C, a.ln3.g, a.ln3.b, 1e-5f, l3.p, l3.dt, s);
-    Act f1 = new_act(x.n, x.d, x.h, x.w, 8 * C, adt);
-    contract(l3, a.ff1, 1, 1, nullptr, 0, nullptr, f1, s);
     Act gg = new_act(x.n, x.d, x.h, x.w, 4 * C, adt);
-    if (!dry) geglu(f1.p, f1.dt, rows, 4 * C, gg.p, gg.dt, s);
+    bool fused = false;
+    if (prec == ECHO_PREC_BF16 && adt == BF16 && a.ff1_geglu.wb && tc_available()) {
+      fused = true;
+      if (!dry) {   // ff1 GEMM with the GEGLU applied in its epilogue: f1 (rows x 8C) is never written
+        GemmArgs g;
+        g.A = l3.p; g.a_dt = BF16; g.n = x.n; g.d = x.d; g.h = x.h; g.w = x.w; g.cin = C; g.lda = C;
+        g.od = x.d; g.oh = x.h; g.ow = x.w;
+        g.W = a.ff1_geglu.wb; g.w_dt = BF16; g.w_stride_n = C; g.cout = 8 * C; g.bias = a.ff1_geglu.b;
+        g.out = gg.p; g.out_dt = BF16; g.ldo = 4 * C; g.epi = 1;
+        if (gemm_tc_supported(g)) gemm_tc(g, s);
+        else fused = false;
+      }
+    }
+    if (!fused) {
+      Act f1 = new_act(x.n, x.d, x.h, x.w, 8 * C, adt);
+      contract(l3, a.ff1, 1, 1, nullptr, 0, nullptr, f1, s);
+      if (!dry) geglu(f1.p, f1.dt, rows, 4 * C, gg.p, gg.dt, s);
+    }
     Act t2 = new_act(x.n, x.d, x.h, x.w, C, adt);
     contract(gg, a.ff2, 1, 1, nullptr, 0, &t1, t2, s);
     contract(t2, a.proj_out, 1, 1, nullptr, 0, &x, out, s);
@@ -253,15 +268,18 @@ struct echo_shape {
       }
     }
     Act hn = gn(h, plan.out_norm, 1e-5f, true, adt, s);
-    Act e = new_act(h.n, h.d, h.h, h.w, d.out_channels, F32);
-    if (conv3d_small_cout_supported(hn.c, d.out_channels, plan.out_conv.taps)) {
+    const bool pad_out = prec == ECHO_PREC_BF16 && plan.out_conv_pad.wb && hn.dt == BF16;
+    Act e = new_act(h.n, h.d, h.h, h.w, pad_out ? plan.out_conv_pad.cout : d.out_channels, F32);
+    if (pad_out) {
+      contract(hn, plan.out_conv_pad, 3, 1, nullptr, 0, nullptr, e, s);        // tcgen05, 32 padded output channels
+    } else if (conv3d_small_cout_supported(hn.c, d.out_channels, plan.out_conv.taps)) {
       if (!dry) conv3d_small_cout(hn, plan.out_conv.w, plan.out_conv.b, d.out_channels, (float*)e.p, s);
     } else {
       contract(hn, plan.out_conv, 3, 1, nullptr, 0, nullptr, e, s);
     }
     if (!dry) {
-      if (ddim_index < 0) cl_to_ncdhw(e.p, F32, e.n, e.c, e.voxels(), out_local, s);
-      else ddim_update(x_local, e.p, F32, true, e.n, e.c, e.voxels(), d_coef + 4 * ddim_index, out_local, s);
+      if (ddim_index < 0) cl_to_ncdhw(e.p, F32, e.n, d.out_channels, e.voxels(), e.c, out_local, s);
+      else ddim_update(x_local, e.p, F32, true, e.n, d.out_channels, e.voxels(), e.c, d_coef + 4 * ddim_index, out_local, s);
     }
     arena.release(m0);
   }

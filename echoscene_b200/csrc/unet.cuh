@@ -32,6 +32,7 @@ struct AttnW {
   ConvW attn2_out;  // [C, C] + bias, applied to attn2.to_v(context) (one context token: softmax == 1)
   ConvW v_only;     // attn1.to_v alone [C, C] (layout branch: one token, self-attention == to_out(to_v(x)))
   ConvW ff1, ff2;   // [8C, C], [C, 4C]
+  ConvW ff1_geglu;  // bf16 mode: ff1 rows permuted per 256-row tile to [128 a | 128 g] for the fused GEGLU epilogue
   int v2_off = 0;   // column offset of attn2.to_v(context) in the stacked projection
 };
 struct BlockW {
@@ -50,6 +51,7 @@ struct UNetPlan {
   AttnW mid_at;
   NormW out_norm;
   ConvW out_conv;
+  ConvW out_conv_pad;       // bf16 mode: out conv zero-padded to 32 output channels so it runs on the tcgen05 kernel
   ConvW time0, time2;       // time_embed.0 / .2
   ConvW emb_stack;          // all ResBlock emb_layers.1 stacked [sum cout, 4*mc]
   ConvW v2_stack;           // all attn2.to_v stacked [sum C, context_dim] (bias-free)

@@ -153,6 +153,21 @@ struct Prep {
     v2_total += C;
     a.ff1 = linear(b + "ff.net.0.proj", C, 8 * C, true);
     a.ff2 = linear(b + "ff.net.2", 4 * C, C, true);
+    if (cfg.want_bf16 && cfg.dims == 3 && (4 * C) % 128 == 0) {
+      const int F = 4 * C, tiles = F / 128;
+      float* o = pool.alloc_n<float>((size_t)2 * F * C);
+      float* bo = pool.alloc_n<float>(2 * F);
+      for (int t = 0; t < tiles; ++t) {
+        ECHO_CUDA(cudaMemcpyAsync(o + (size_t)(t * 256) * C, a.ff1.w + (size_t)(t * 128) * C, sizeof(float) * 128 * C, cudaMemcpyDeviceToDevice, s));
+        ECHO_CUDA(cudaMemcpyAsync(o + (size_t)(t * 256 + 128) * C, a.ff1.w + (size_t)(F + t * 128) * C, sizeof(float) * 128 * C, cudaMemcpyDeviceToDevice, s));
+        ECHO_CUDA(cudaMemcpyAsync(bo + t * 256, a.ff1.b + t * 128, sizeof(float) * 128, cudaMemcpyDeviceToDevice, s));
+        ECHO_CUDA(cudaMemcpyAsync(bo + t * 256 + 128, a.ff1.b + F + t * 128, sizeof(float) * 128, cudaMemcpyDeviceToDevice, s));
+      }
+      a.ff1_geglu = a.ff1;
+      a.ff1_geglu.w = o;
+      a.ff1_geglu.b = bo;
+      a.ff1_geglu.wb = to_bf16(o, (size_t)2 * F * C);
+    }
     a.proj_out = conv(p + "proj_out", C, ch, 1);
     return a;
   }
@@ -234,6 +249,21 @@ void build_unet_plan(const WeightMap& wm, const UNetCfg& cfg, DevPool& pool, UNe
   }
   plan.out_norm = P.norm("out.0", mc);
   plan.out_conv = P.conv("out.2", mc, cfg.out_channels, 3);
+  if (cfg.want_bf16 && cfg.dims == 3 && cfg.out_channels < 32) {
+    // a 3-column GEMM wastes the tensor core far less than a scalar reduction wastes the SM: pad cout to 32 (zero rows)
+    const size_t row = (size_t)plan.out_conv.taps * mc;
+    float* o = pool.alloc_n<float>(32 * row);
+    float* b = pool.alloc_n<float>(32);
+    ECHO_CUDA(cudaMemsetAsync(o, 0, 32 * row * sizeof(float), s));
+    ECHO_CUDA(cudaMemsetAsync(b, 0, 32 * sizeof(float), s));
+    ECHO_CUDA(cudaMemcpyAsync(o, plan.out_conv.w, cfg.out_channels * row * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    ECHO_CUDA(cudaMemcpyAsync(b, plan.out_conv.b, cfg.out_channels * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    plan.out_conv_pad = plan.out_conv;
+    plan.out_conv_pad.cout = 32;
+    plan.out_conv_pad.w = o;
+    plan.out_conv_pad.b = b;
+    plan.out_conv_pad.wb = P.to_bf16(o, 32 * row);
+  }
   plan.emb_stack = P.stack(P.emb_items, emb, true);
   plan.v2_stack = P.stack(P.v2_items, cfg.context_dim, false);
   plan.emb_total = P.emb_total;
