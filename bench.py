@@ -88,6 +88,41 @@ def build_model(precision: str, dev):
     return m.to(dev), sd
 
 
+def layout_rate(dev, pk, precision, steps=200):
+    """Secondary figure (SURVEY §8d asks for it next to the headline): layout-steps/s at N = 16 — UNet1DModel forward +
+    DDPM update per step, chained; HBM roofline = live weight bytes once per step."""
+    from echoscene_b200 import arch, modules, synth
+    from oracle import cases
+    sd = arch.make_state_dict(arch.unet1d_specs(cases.layout_cfg()), cases.WEIGHT_SEED_LAYOUT)
+    m = modules.UNet1DModel(in_channels=8, model_channels=512, out_channels=8, num_res_blocks=2, attention_resolutions=[4, 2],
+                            channel_mult=[1, 1, 1, 1], num_heads=8, use_spatial_transformer=True, concat_dim=1280,
+                            crossattn_dim=1280, enable_t_emb=True, precision=precision, time_num=1000)
+    m.load_state_dict(sd)
+    m = m.to(dev)
+    g = synth.make_scene_graph(N_NODES, N_TRIPLES, 2)
+    tri = g.triples.to(dev)
+    obj_embed, x = synth.layout_inputs(N_NODES, 2)
+    obj_embed, x = obj_embed.to(dev), x.to(dev)
+    noise = torch.randn(steps, N_NODES, 8, device=dev)
+    m._ensure(N_NODES, N_TRIPLES)
+    m.frozen = True
+    for i in range(5):
+        x = m.ddpm_step(x, obj_embed, tri, 999 - i, noise[i])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for i in range(steps):
+        x = m.ddpm_step(x, obj_embed, tri, 994 - i, noise[i])
+    e1.record()
+    torch.cuda.synchronize()
+    m.frozen = False
+    ms = e0.elapsed_time(e1) / steps
+    live_bytes = 115.30e6 * (2 if precision == "bf16" else 4)    # SURVEY §8d: live parameters read once per step
+    ach = live_bytes / (ms * 1e-3) / 1e9
+    return {"value": 1e3 / ms, "unit": "layout-steps/s", "ms_per_step": ms, "n_nodes": N_NODES, "dtype": precision,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"]}}
+
+
 def conv_kernel_roofline(dev, pk):
     """The dominant kernel timed alone: tcgen05 implicit-GEMM conv 224@16^3 -> 224, N=16 objects (7 of these per step,
     SURVEY Appendix E).  CUDA events on the launching stream; L2 flushed between launches."""
@@ -176,8 +211,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -304,6 +339,8 @@ def main():
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": x.numel() * 4, "d2h_bytes_per_step": x.numel() * 4},
                 "roofline": roof}
+        if world == 1:
+            line["layout_branch"] = layout_rate(dev, pk, "bf16" if precision == "bf16" else "fp32")
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             rate, tcpu = cpu_reference_rate(2, 2, 1)

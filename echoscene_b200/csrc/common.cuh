@@ -84,6 +84,9 @@ struct Act {
   void* p = nullptr;
   DT dt = F32;
   int n = 0, d = 1, h = 1, w = 1, c = 0;
+  // optional per-column (sum, sumsq) partials written by the producing tcgen05 GEMM: [n * colsum_rows][c][2]
+  float* colsum = nullptr;
+  int colsum_rows = 0;
   int64_t voxels() const { return (int64_t)d * h * w; }
   int64_t rows() const { return (int64_t)n * d * h * w; }
   size_t bytes() const { return (size_t)rows() * c * dt_size(dt); }

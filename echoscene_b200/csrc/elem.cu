@@ -685,4 +685,44 @@ void attention_f32(const float* qkv, int n, int tokens, int heads, int dh, float
   gemm_simt(p, s);
 }
 
+// ---- GroupNorm statistics from the producing GEMM's column partials (gemm_tc.cu epilogue) ---------------------------
+namespace {
+// one warp per (object, group): reduce rows_per_obj x cpg (sum, sumsq) pairs in double, fixed order
+__global__ void gn_stats_from_colsum_kernel(const float* __restrict__ colsum, int n, int rows_per_obj, int C, int groups, double count,
+                                            float eps, float* __restrict__ stats) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= n * groups) return;
+  const int obj = i / groups, g = i % groups, cpg = C / groups;
+  const float* base = colsum + ((int64_t)obj * rows_per_obj * C + g * cpg) * 2;
+  double a = 0.0, b = 0.0;
+  const int total = rows_per_obj * cpg;
+  for (int k = lane; k < total; k += 32) {
+    const int r = k / cpg, c = k - r * cpg;
+    const float2 p = *reinterpret_cast<const float2*>(base + ((int64_t)r * C + c) * 2);
+    a += (double)p.x;
+    b += (double)p.y;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane == 0) {
+    const double mean = a / count;
+    double var = b / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[2 * i] = (float)mean;
+    stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+}  // namespace
+
+void gn_stats_from_colsum(const float* colsum, int n_obj, int rows_per_obj, int C, int groups, int64_t voxels, float eps, float* stats,
+                          cudaStream_t s) {
+  const int tot = n_obj * groups;
+  gn_stats_from_colsum_kernel<<<cdiv((int64_t)tot * 32, 256), 256, 0, s>>>(colsum, n_obj, rows_per_obj, C, groups,
+                                                                           (double)voxels * (C / groups), eps, stats);
+  ECHO_LAUNCH_CHECK();
+}
+
 }  // namespace echo

@@ -29,10 +29,15 @@ namespace {
 
 constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
 constexpr int MAX_BLOCK_N = 256;
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 12;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;       // 16 KiB
-constexpr int B_STAGE_BYTES = MAX_BLOCK_N * BLOCK_K * 2;   // 32 KiB (BLOCK_N rows used)
-constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int SMEM_LIMIT = 227 * 1024;                     // opt-in dynamic shared memory per CTA on sm_100
+constexpr int SMEM_FIXED = 1024 /*align*/ + 512 /*barriers + tmem ptr*/;
+// bytes in flight per SM is what hides the L2 latency of the TMA stream: use every stage that fits
+static inline int stages_for(int block_n) {
+  const int st = (SMEM_LIMIT - SMEM_FIXED) / (A_STAGE_BYTES + block_n * BLOCK_K * 2);
+  return st > MAX_STAGES ? MAX_STAGES : st;
+}
 constexpr int MAX_TAPS = 27;
 
 struct TcParams {
@@ -43,6 +48,7 @@ struct TcParams {
   int num_m_tiles, num_n_tiles, block_n;
   int cin, cout, taps, kblocks_per_tap;
   int obj_mul;                  // 4 for the space-to-depth input (obj index = obj*4 + phase), else 1
+  int stages;                   // depth of the smem ring
   int8_t tap_d[MAX_TAPS], tap_h[MAX_TAPS], tap_w[MAX_TAPS], tap_p[MAX_TAPS];
   // epilogue
   const float* bias;
@@ -55,6 +61,7 @@ struct TcParams {
   int out_bf16;
   long long ldo;
   int relu;
+  float* colsum;   // optional [num_m_tiles*4][cout][2] per-column (sum, sumsq) partials for the next GroupNorm
   int geglu;   // epilogue: tile columns are [a (block_n/2) | g (block_n/2)]; out = (a+ba) * gelu_erf(g+bg), out width cout/2
 };
 
@@ -136,6 +143,20 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// Halving butterfly over the 32 lanes: on return v[0] of lane l is the sum over all lanes of element l.
+__device__ __forceinline__ void col_butterfly(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = up ? v[i] : v[i + n / 2];
+      const float keep = up ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (8-row atoms of 1024 bytes)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
@@ -150,6 +171,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
+  const int STAGES = p.stages;
+  const int B_STAGE_BYTES = p.block_n * BLOCK_K * 2;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
   uint64_t* bars = (uint64_t*)(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
   uint64_t* full_bar = bars;                   // [STAGES]
@@ -295,8 +318,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tmem_ld32(taddr + c, v);
         tmem_ld_wait();
         const int n0 = n_base + c;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = 0.f;
         if (valid && n0 < p.cout) {
-          float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           if (p.bias) {
@@ -359,6 +384,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int q = 0; q < 8; ++q) op[q] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
           }
         }
+        if (p.colsum) {
+          // per-column (sum, sum of squares) over this warp's 32 voxels -> partial row (m_blk*4 + ew): the next
+          // GroupNorm's statistics come from these instead of a separate pass over the activation
+          float q2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) q2[j] = f[j] * f[j];
+          col_butterfly(f, lane);
+          col_butterfly(q2, lane);
+          if (n0 + lane < p.cout)
+            *reinterpret_cast<float2*>(p.colsum + (((long long)m_blk * 4 + ew) * p.cout + n0 + lane) * 2) = make_float2(f[0], q2[0]);
+        }
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[as]);
@@ -417,7 +453,7 @@ void tc_init() {
   }
   g_tc.encode = (EncodeTiledFn)fn;
   g_tc.sms = prop.multiProcessorCount;
-  if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+  if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
     cudaGetLastError();
     return;
   }
@@ -443,11 +479,19 @@ bool tc_available() {
   return g_tc.ok;
 }
 
+int gemm_tc_colsum_rows_per_obj(const GemmArgs& g) {
+  const int bw = pow2_floor(g.ow) > 128 ? 128 : pow2_floor(g.ow);
+  const int bh = pow2_floor(g.oh) > 128 / bw ? 128 / bw : pow2_floor(g.oh);
+  const int bd = 128 / (bw * bh);
+  return cdiv(g.ow, bw) * cdiv(g.oh, bh) * cdiv(g.od, bd) * 4;
+}
+
 bool gemm_tc_supported(const GemmArgs& g) {
   if (g.a_dt != BF16 || g.w_dt != BF16) return false;
   if (g.nb0 * g.nb1 != 1 || g.alpha != 1.f || g.act > 1) return false;
   if (g.cin % 16 != 0 || g.lda != g.cin || g.w_stride_k != 1 || g.w_stride_n != (int64_t)g.ktot()) return false;
   if (g.cout % 32 != 0 || pick_block_n(g.cout) == 0) return false;
+  if (g.epi == 1 && g.colsum) return false;
   if (g.epi == 1 && (g.cout % 256 != 0 || g.res || g.rowvec || !g.bias || g.out_dt != BF16 || g.act != 0)) return false;
   if (!((g.kd == 1 && g.kh == 1 && g.kw == 1) || (g.kd == 3 && g.kh == 3 && g.kw == 3))) return false;
   if (g.pd != g.kd / 2 || g.ph != g.kh / 2 || g.pw != g.kw / 2 || g.sd != 1 || g.sh != g.sw) return false;
@@ -515,6 +559,7 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   p.bias = g.bias; p.rowvec = g.rowvec; p.ld_rowvec = g.ld_rowvec;
   p.res = g.res; p.res_bf16 = g.res_dt == BF16; p.ld_res = g.ld_res;
   p.out = g.out; p.out_bf16 = g.out_dt == BF16; p.ldo = g.ldo; p.relu = g.act == 1;
+  p.colsum = g.colsum;
   p.geglu = g.epi == 1;
   if (p.geglu) { p.block_n = 256; p.num_n_tiles = g.cout / 256; }
 
@@ -542,7 +587,9 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < g_tc.sms ? tiles : g_tc.sms;
-  gemm_tc_kernel<<<grid, 256, SMEM_BYTES, s>>>(map_a, map_b, p);
+  p.stages = stages_for(p.block_n);
+  const int smem_bytes = p.stages * (A_STAGE_BYTES + p.block_n * BLOCK_K * 2) + SMEM_FIXED;
+  gemm_tc_kernel<<<grid, 256, smem_bytes, s>>>(map_a, map_b, p);
   ECHO_LAUNCH_CHECK();
 }
 

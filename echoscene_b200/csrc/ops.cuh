@@ -38,6 +38,7 @@ struct GemmArgs {
   // batching: problem b = b0*nb1 + b1
   int nb0 = 1, nb1 = 1;
   int64_t a_bs0 = 0, a_bs1 = 0, w_bs0 = 0, w_bs1 = 0, o_bs0 = 0, o_bs1 = 0;
+  float* colsum = nullptr;          // tcgen05 path: per-column (sum, sumsq) partials, gemm_tc_colsum_rows() x cout x 2 floats
   void* scratch = nullptr;          // tcgen05 path, stride-2 convs: room for a space-to-depth copy of A (same bytes)
   int64_t rows_out() const { return (int64_t)n * od * oh * ow; }
   int ktot() const { return kd * kh * kw * cin; }
@@ -48,6 +49,11 @@ void gemm_simt(const GemmArgs& g, cudaStream_t s);
 bool gemm_tc_supported(const GemmArgs& g);
 void gemm_tc(const GemmArgs& g, cudaStream_t s);
 bool tc_available();
+// rows of the column-sum partial buffer per OBJECT for this problem (the tcgen05 kernel writes 4 per 128-voxel tile)
+int gemm_tc_colsum_rows_per_obj(const GemmArgs& g);
+// GroupNorm statistics from column partials: stats[(obj, group)] = (mean, rstd)
+void gn_stats_from_colsum(const float* colsum, int n_obj, int rows_per_obj, int C, int groups, int64_t voxels, float eps, float* stats,
+                          cudaStream_t s);
 // precision: ECHO_PREC_*; BF16 falls back to the SIMT kernel (bf16 operands, fp32 accumulate) for shapes the
 // tensor-core kernel does not take (tiny channel counts).
 void gemm(const GemmArgs& g, int precision, cudaStream_t s);

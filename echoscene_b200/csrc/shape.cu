@@ -49,6 +49,17 @@ struct echo_shape {
     a.p = arena.alloc(a.bytes());
     return a;
   }
+  // activation whose producer (a tcgen05 GEMM) also emits the column partials the consuming GroupNorm needs
+  Act new_act_cs(int n, int dd, int h, int w, int c, DT dt) {
+    Act a = new_act(n, dd, h, w, c, dt);
+    if (prec == ECHO_PREC_BF16 && dt == BF16 && c % 32 == 0 && (dry || tc_available())) {
+      GemmArgs g;
+      g.od = dd; g.oh = h; g.ow = w;
+      a.colsum_rows = gemm_tc_colsum_rows_per_obj(g);
+      a.colsum = arena.alloc_n<float>((size_t)n * a.colsum_rows * c * 2);
+    }
+    return a;
+  }
   void lin(const float* X, int64_t ldx, int M, const ConvW& w, float* Y, int64_t ldy, int in_act, int act, cudaStream_t s) {
     if (dry) return;
     LinArgs a;
@@ -76,16 +87,19 @@ struct echo_shape {
     if (prec == ECHO_PREC_BF16 && w.wb && x.dt == BF16 && tc_available()) {
       GemmArgs t = g;
       t.W = w.wb; t.w_dt = BF16;
+      t.colsum = out.colsum;
       if (gemm_tc_supported(t)) { gemm_tc(t, s); return; }
     }
+    ECHO_CHECK(!out.colsum, "contract: column statistics were requested but the contraction left the tcgen05 path");
     gemm_simt(g, s);
   }
   Act gn(const Act& x, const NormW& nw, float eps, bool silu, DT odt, cudaStream_t s) {
     float* stats = arena.alloc_n<float>((size_t)x.n * 32 * 2);
-    float* partial = arena.alloc_n<float>(gn_partial_floats(x, 32));
+    float* partial = x.colsum ? nullptr : arena.alloc_n<float>(gn_partial_floats(x, 32));
     Act o = new_act(x.n, x.d, x.h, x.w, x.c, odt);
     if (!dry) {
-      gn_stats(x, 32, eps, stats, partial, s);
+      if (x.colsum) gn_stats_from_colsum(x.colsum, x.n, x.colsum_rows, x.c, 32, x.voxels(), eps, stats, s);   // no pass over x
+      else gn_stats(x, 32, eps, stats, partial, s);
       gn_apply(x, stats, nw.g, nw.b, 32, silu, o, s);
     }
     return o;
@@ -93,10 +107,10 @@ struct echo_shape {
 
   // ResBlock._forward (openai_model_3d.py:294-314)
   Act res_block(const Act& x, const ResW& r, int n_local, cudaStream_t s) {
-    Act out = new_act(x.n, x.d, x.h, x.w, r.cout, adt);
+    Act out = new_act_cs(x.n, x.d, x.h, x.w, r.cout, adt);
     const size_t m = arena.mark();
     Act a1 = gn(x, r.n1, 1e-5f, true, adt, s);
-    Act h1 = new_act(x.n, x.d, x.h, x.w, r.cout, adt);
+    Act h1 = new_act_cs(x.n, x.d, x.h, x.w, r.cout, adt);
     contract(a1, r.c1, 3, 1, embout + r.emb_off, plan.emb_total, nullptr, h1, s);
     Act a2 = gn(h1, r.n2, 1e-5f, true, adt, s);
     if (r.has_skip) {
@@ -113,7 +127,7 @@ struct echo_shape {
 
   // SpatialTransformer3D + BasicTransformerBlock (attention.py:334-351, 237-245)
   Act transformer(const Act& x, const AttnW& a, int attn_index, cudaStream_t s) {
-    Act out = new_act(x.n, x.d, x.h, x.w, x.c, adt);
+    Act out = new_act_cs(x.n, x.d, x.h, x.w, x.c, adt);
     const size_t m = arena.mark();
     const int C = a.C, tokens = (int)x.voxels();
     const int64_t rows = x.rows();
@@ -236,14 +250,14 @@ struct echo_shape {
     int ai = 0;
     for (auto& b : plan.in_blocks) {
       if (b.kind == BlockW::CONV_IN) {
-        Act o = new_act(h.n, h.d, h.h, h.w, b.conv.cout, adt);
+        Act o = new_act(h.n, h.d, h.h, h.w, b.conv.cout, adt);   // stem: SIMT path (3 input channels), no column partials
         contract(h, b.conv, 3, 1, nullptr, 0, nullptr, o, s);
         h = o;
       } else if (b.kind == BlockW::RES) {
         h = res_block(h, b.res, n_local, s);
         if (b.attn) h = transformer(h, b.at, ai++, s);
       } else {   // Downsample: Conv3d k3 stride (1,2,2) pad 1 (openai_model_3d.py:188-192)
-        Act o = new_act(h.n, h.d, (h.h + 2 - 3) / 2 + 1, (h.w + 2 - 3) / 2 + 1, b.conv.cout, adt);
+        Act o = new_act_cs(h.n, h.d, (h.h + 2 - 3) / 2 + 1, (h.w + 2 - 3) / 2 + 1, b.conv.cout, adt);
         contract(h, b.conv, 3, 2, nullptr, 0, nullptr, o, s);
         h = o;
       }
@@ -262,7 +276,7 @@ struct echo_shape {
       if (b.up) {   // nearest x(1,2,2) then Conv3d k3 (openai_model_3d.py:150-157)
         Act up = new_act(h.n, h.d, h.h * 2, h.w * 2, h.c, adt);
         if (!dry) upsample_hw2(h, up, s);
-        Act o = new_act(up.n, up.d, up.h, up.w, b.conv.cout, adt);
+        Act o = new_act_cs(up.n, up.d, up.h, up.w, b.conv.cout, adt);
         contract(up, b.conv, 3, 1, nullptr, 0, nullptr, o, s);
         h = o;
       }
