@@ -50,7 +50,9 @@ __device__ __forceinline__ int butterfly(float (&v)[N], int lane) {
   return base;
 }
 
-template <class TW, int MT>
+// (code size matters here: the kernel runs ~1 iteration per warp, so it is instruction-fetch bound when over-unrolled;
+//  the SiLU-on-load variant is a separate instantiation and the K loop is not unrolled)
+template <class TW, int MT, bool IN_SILU>
 __global__ void __launch_bounds__(256) linear_rows_kernel(const LinArgs a, int k_slice) {
   constexpr int N = MT * RN;
   extern __shared__ float part[];   // [WK][N]
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(const LinArgs a, int k
 #pragma unroll
   for (int i = 0; i < N; ++i) acc[i] = 0.f;
 
-#pragma unroll 2
+#pragma unroll 1
   for (int k = k_beg + lane * 4; k < k_end; k += 128) {
     float w[RN][4];
 #pragma unroll
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(const LinArgs a, int k
     for (int i = 0; i < MT; ++i) {
       if (m0 + i < a.M) {
         float4 xv = *reinterpret_cast<const float4*>(a.X + (int64_t)(m0 + i) * a.ldx + k);
-        if (a.in_act == 1) { xv.x = silu_f(xv.x); xv.y = silu_f(xv.y); xv.z = silu_f(xv.z); xv.w = silu_f(xv.w); }
+        if (IN_SILU) { xv.x = silu_f(xv.x); xv.y = silu_f(xv.y); xv.z = silu_f(xv.z); xv.w = silu_f(xv.w); }
 #pragma unroll
         for (int j = 0; j < RN; ++j) {
           float s = acc[i * RN + j];
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(const LinArgs a, int k
 
 template <class TW>
 void launch(const LinArgs& a, cudaStream_t s) {
-  const int MT = a.M <= 8 ? 8 : 16;
+  constexpr int MT = 8;
   const int row_tiles = cdiv(a.M, MT);
   const int base_warps = cdiv(a.nout, RN) * row_tiles;
   int wk = 1;
@@ -123,8 +125,8 @@ void launch(const LinArgs& a, cudaStream_t s) {
   const int k_slice = cdiv(cdiv(a.K, wk), 128) * 128;
   dim3 grid(cdiv(a.nout, RN), row_tiles);
   const size_t smem = (size_t)wk * MT * RN * sizeof(float);
-  if (MT == 8) linear_rows_kernel<TW, 8><<<grid, 32 * wk, smem, s>>>(a, k_slice);
-  else linear_rows_kernel<TW, 16><<<grid, 32 * wk, smem, s>>>(a, k_slice);
+  if (a.in_act == 1) linear_rows_kernel<TW, MT, true><<<grid, 32 * wk, smem, s>>>(a, k_slice);
+  else linear_rows_kernel<TW, MT, false><<<grid, 32 * wk, smem, s>>>(a, k_slice);
 }
 
 }  // namespace

@@ -23,7 +23,10 @@ struct echo_shape {
   DevPool pool;
   UNetPlan plan;
   Gcn gcn;
-  Arena arena;
+  Arena arena;        // trunk temporaries (main stream)
+  Arena side_arena;   // shape_embeddings temporaries (side stream: must not alias the trunk's stack)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool dry = false;
   int prec = ECHO_PREC_FP32;
   DT adt = F32;   // trunk activation dtype
@@ -43,12 +46,13 @@ struct echo_shape {
   std::vector<int> a2_off;
 
   // ---- helpers (all respect `dry`) ----
-  Act new_act(int n, int dd, int h, int w, int c, DT dt) {
+  Act new_act_in(Arena& A, int n, int dd, int h, int w, int c, DT dt) {
     Act a;
     a.n = n; a.d = dd; a.h = h; a.w = w; a.c = c; a.dt = dt;
-    a.p = arena.alloc(a.bytes());
+    a.p = A.alloc(a.bytes());
     return a;
   }
+  Act new_act(int n, int dd, int h, int w, int c, DT dt) { return new_act_in(arena, n, dd, h, w, c, dt); }
   // activation whose producer (a tcgen05 GEMM) also emits the column partials the consuming GroupNorm needs
   Act new_act_cs(int n, int dd, int h, int w, int c, DT dt) {
     Act a = new_act(n, dd, h, w, c, dt);
@@ -190,20 +194,20 @@ struct echo_shape {
 
   // shape_embeddings stack on local objects (openai_model_3d.py:757-764): x_cl (n,16,16,16,3) f32 -> codes (n,64)
   void embed(const Act& xcl, float* codes_out, cudaStream_t s) {
-    const size_t m = arena.mark();
-    Act c0 = new_act(xcl.n, xcl.d, xcl.h, xcl.w, 32, F32);
+    Arena& A = side_arena;
+    A.release(0);
+    Act c0 = new_act_in(A, xcl.n, xcl.d, xcl.h, xcl.w, 32, F32);
     contract(xcl, se_conv0, 3, 1, nullptr, 0, nullptr, c0, s);
-    Act p0 = new_act(xcl.n, xcl.d / 2, xcl.h / 2, xcl.w / 2, 32, F32);
+    Act p0 = new_act_in(A, xcl.n, xcl.d / 2, xcl.h / 2, xcl.w / 2, 32, F32);
     if (!dry) maxpool3d(c0, 2, 2, p0, s);
-    Act c1 = new_act(p0.n, p0.d, p0.h, p0.w, 64, F32);
+    Act c1 = new_act_in(A, p0.n, p0.d, p0.h, p0.w, 64, F32);
     contract(p0, se_conv2, 3, 1, nullptr, 0, nullptr, c1, s);
-    Act p1 = new_act(c1.n, (c1.d - 2) / 4 + 1, (c1.h - 2) / 4 + 1, (c1.w - 2) / 4 + 1, 64, F32);
+    Act p1 = new_act_in(A, c1.n, (c1.d - 2) / 4 + 1, (c1.h - 2) / 4 + 1, (c1.w - 2) / 4 + 1, 64, F32);
     if (!dry) maxpool3d(c1, 2, 4, p1, s);
-    float* flat = arena.alloc_n<float>((size_t)p1.rows() * 64);
+    float* flat = A.alloc_n<float>((size_t)p1.rows() * 64);
     if (!dry) flatten_ncdhw(p1, flat, s);
     ECHO_CHECK((int)p1.voxels() * 64 == se_lin.cin, "shape_embeddings: flatten width %d != %d", (int)p1.voxels() * 64, se_lin.cin);
     lin(flat, se_lin.cin, xcl.n, se_lin, codes_out, d.gconv_dim, 0, 0, s);
-    arena.release(m);
   }
 
   // everything after the codes are known.  out: e_t (ddim_index < 0) or x_prev, NCDHW f32, local objects.
@@ -215,34 +219,51 @@ struct echo_shape {
     if (!dry) timestep_embedding_tab(t_all, freqs, N, mc, temb, s);
     lin(temb, mc, N, plan.time0, e1, E, 0, 2, s);
     lin(e1, E, N, plan.time2, emb, E, 0, 0, s);
+    // ---- fork: the echo chain (shape codes -> node features -> 5-layer GCN -> attn2 vectors) is only needed by the
+    //      first SpatialTransformer (input block 4), so it runs on a side stream under the first ~1 ms of the trunk ----
+    cudaStream_t q = s;
+    if (!dry) {
+      ECHO_CUDA(cudaEventRecord(ev_fork, s));
+      ECHO_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+      q = side;
+    }
+    if (!codes_all) {   // unsharded: embed here (sharded callers all-gathered the codes between embed and trunk)
+      embed(xcl, codes, q);
+      codes_all = codes;
+    }
     // node features [obj_embed | code | t_emb] (openai_model_3d.py:808-812)
     if (!dry) {
-      copy_cols(uc_all, ctx, N, ctx, node, nd, s);
-      copy_cols(codes_all, gd, N, gd, node + ctx, nd, s);
+      copy_cols(uc_all, ctx, N, ctx, node, nd, q);
+      copy_cols(codes_all, gd, N, gd, node + ctx, nd, q);
     }
-    if (d.enable_t_emb) lin(emb, E, N, time_emb_lin, node + ctx + gd, nd, 0, 0, s);
+    if (d.enable_t_emb) lin(emb, E, N, time_emb_lin, node + ctx + gd, nd, 0, 0, q);
     if (!dry) {
-      if (T > 0) embedding_rows(pred_table, 2 * gd, g->triples, 3, 1, T, pred, 2 * gd, s);
-      gcn.forward(g, node, pred, latent, nullptr, s);
+      if (T > 0) embedding_rows(pred_table, 2 * gd, g->triples, 3, 1, T, pred, 2 * gd, q);
+      gcn.forward(g, node, pred, latent, nullptr, q);
     }
-    // per-object vectors of the local objects
-    const float* emb_loc = emb + (size_t)obj_begin * E;
     const float* lat_loc = latent + (size_t)obj_begin * ctx;
-    lin(emb_loc, E, n_local, plan.emb_stack, embout, plan.emb_total, 1, 0, s);
     {
       ConvW v = plan.v2_stack;
-      lin(lat_loc, ctx, n_local, v, v2, plan.v2_total, 0, 0, s);
+      lin(lat_loc, ctx, n_local, v, v2, plan.v2_total, 0, 0, q);
     }
     {
       int ai = 0;
       auto a2 = [&](const AttnW& a) {
-        lin(v2 + a.v2_off, plan.v2_total, n_local, a.attn2_out, a2vec + a2_off[ai], a2_total, 0, 0, s);
+        lin(v2 + a.v2_off, plan.v2_total, n_local, a.attn2_out, a2vec + a2_off[ai], a2_total, 0, 0, q);
         ++ai;
       };
       for (auto& b : plan.in_blocks) if (b.attn) a2(b.at);
       a2(plan.mid_at);
       for (auto& b : plan.out_blocks) if (b.attn) a2(b.at);
     }
+    bool joined = dry;
+    if (!dry) ECHO_CUDA(cudaEventRecord(ev_join, side));
+    auto join = [&]() {
+      if (!joined) { ECHO_CUDA(cudaStreamWaitEvent(s, ev_join, 0)); joined = true; }
+    };
+    // per-object time-embedding projections of the local objects (main stream: the first ResBlock needs them)
+    const float* emb_loc = emb + (size_t)obj_begin * E;
+    lin(emb_loc, E, n_local, plan.emb_stack, embout, plan.emb_total, 1, 0, s);
     // ---- UNet trunk ----
     const size_t m0 = arena.mark();
     std::vector<Act> hs;
@@ -255,7 +276,7 @@ struct echo_shape {
         h = o;
       } else if (b.kind == BlockW::RES) {
         h = res_block(h, b.res, n_local, s);
-        if (b.attn) h = transformer(h, b.at, ai++, s);
+        if (b.attn) { join(); h = transformer(h, b.at, ai++, s); }
       } else {   // Downsample: Conv3d k3 stride (1,2,2) pad 1 (openai_model_3d.py:188-192)
         Act o = new_act_cs(h.n, h.d, (h.h + 2 - 3) / 2 + 1, (h.w + 2 - 3) / 2 + 1, b.conv.cout, adt);
         contract(h, b.conv, 3, 2, nullptr, 0, nullptr, o, s);
@@ -264,6 +285,7 @@ struct echo_shape {
       hs.push_back(h);
     }
     h = res_block(h, plan.mid0, n_local, s);
+    join();
     h = transformer(h, plan.mid_at, ai++, s);
     h = res_block(h, plan.mid2, n_local, s);
     for (auto& b : plan.out_blocks) {
@@ -308,14 +330,9 @@ struct echo_shape {
     const int L = d.latent_size;
     Act xcl = new_act(n_local, L, L, L, d.in_channels, F32);
     if (!dry && n_local > 0) ncdhw_to_cl(x_local, n_local, d.in_channels, (int64_t)L * L * L, xcl.p, F32, s);
-    const float* codes_use = codes_all;
-    if (!codes_all) {
-      ECHO_CHECK(n_local == g->n_nodes && obj_begin == 0, "shape: codes of all nodes are required when the trunk is sharded");
-      embed(xcl, codes, s);
-      codes_use = codes;
-    }
+    if (!codes_all) ECHO_CHECK(n_local == g->n_nodes && obj_begin == 0, "shape: codes of all nodes are required when the trunk is sharded");
     if (n_local == 0) return;
-    trunk(g, x_local, xcl, obj_begin, n_local, codes_use, uc_all, t_all, ddim_index, out_local, s);
+    trunk(g, x_local, xcl, obj_begin, n_local, codes_all, uc_all, t_all, ddim_index, out_local, s);
   }
 };
 
@@ -483,6 +500,9 @@ echo_shape* shape_create(const echo_shape_desc_t* desc, const echo_weight_t* wei
       h->arena.base = nullptr;
       h->arena.cap = ~size_t(0) >> 1;
       h->arena.off = h->arena.high = 0;
+      h->side_arena.base = nullptr;
+      h->side_arena.cap = ~size_t(0) >> 1;
+      h->side_arena.off = h->side_arena.high = 0;
       if (d.max_local_nodes == d.max_nodes) h->run(&fake, nullptr, 0, d.max_nodes, nullptr, nullptr, nullptr, -1, nullptr, s);
       else {
         h->run(&fake, nullptr, 0, d.max_local_nodes, (const float*)8, nullptr, nullptr, -1, nullptr, s);
@@ -495,10 +515,16 @@ echo_shape* shape_create(const echo_shape_desc_t* desc, const echo_weight_t* wei
       h->dry = false;
       const size_t need = h->arena.high + (size_t(1) << 20);
       h->arena.init(need);
+      const size_t need_side = h->side_arena.high + (size_t(1) << 20);
+      h->side_arena.init(need_side);
     }
+    ECHO_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    ECHO_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    ECHO_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     return h;
   } catch (...) {
     h->arena.destroy();
+    h->side_arena.destroy();
     h->pool.destroy();
     delete h;
     throw;
@@ -507,7 +533,11 @@ echo_shape* shape_create(const echo_shape_desc_t* desc, const echo_weight_t* wei
 
 void shape_destroy(echo_shape* h) {
   if (!h) return;
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   h->arena.destroy();
+  h->side_arena.destroy();
   h->pool.destroy();
   delete h;
 }
