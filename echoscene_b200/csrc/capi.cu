@@ -2,6 +2,7 @@
 // point returns a code and leaves the message in thread-local storage.
 #include "unet.cuh"
 
+#include <atomic>
 #include <functional>
 #include <algorithm>
 
@@ -99,7 +100,9 @@ int echo_graph_create(echo_graph_t** out, const int64_t* triples_dev, int32_t T,
     // subject roles first (ascending t), then object roles: the order scatter_add visits them (graph.py:176-177)
     for (int t = 0; t < T; ++t) items[fill[si[t]]++] = t * 2 + 0;
     for (int t = 0; t < T; ++t) items[fill[oi[t]]++] = t * 2 + 1;
+    static std::atomic<uint64_t> next_id{1};
     echo_graph* g = new echo_graph();
+    g->id = next_id++;
     g->n_nodes = N;
     g->n_triples = T;
     auto up = [&](const void* src, size_t bytes) {

@@ -87,6 +87,9 @@ struct Act {
   // optional per-column (sum, sumsq) partials written by the producing tcgen05 GEMM: [n * colsum_rows][c][2]
   float* colsum = nullptr;
   int colsum_rows = 0;
+  // a channel concat [A | B] of two such tensors: partials of B and the split point (channels of A)
+  float* colsum2 = nullptr;
+  int c_split = 0;
   int64_t voxels() const { return (int64_t)d * h * w; }
   int64_t rows() const { return (int64_t)n * d * h * w; }
   size_t bytes() const { return (size_t)rows() * c * dt_size(dt); }

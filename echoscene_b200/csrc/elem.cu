@@ -157,6 +157,51 @@ __global__ void gn_apply_kernel(const TI* __restrict__ x, const float* __restric
   }
 }
 
+// bf16 -> bf16 fast path: 8 channels (16 bytes) per thread, four rows in flight per thread
+__global__ void __launch_bounds__(256) gn_apply_bf16x8_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              int64_t V, int C, int groups, int silu, int noct, int RY, int rows_per_block,
+                                                              __nv_bfloat16* __restrict__ y) {
+  const int q = threadIdx.x % noct, ry = threadIdx.x / noct;
+  if (ry >= RY) return;
+  const int obj = blockIdx.y, cpg = C / groups, c0 = q * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float* st = stats + ((int64_t)obj * groups + (c0 + j) / cpg) * 2;
+    sc[j] = st[1] * __ldg(gamma + c0 + j);
+    sh[j] = __ldg(beta + c0 + j) - st[0] * sc[j];
+  }
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(r0 + (int64_t)rows_per_block, V);
+  const __nv_bfloat16* xb = x + ((int64_t)obj * V) * C + c0;
+  __nv_bfloat16* yb = y + ((int64_t)obj * V) * C + c0;
+  for (int64_t r = r0 + ry; r < r1; r += 4 * RY) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (r + k * RY < r1) u[k] = __ldg(reinterpret_cast<const uint4*>(xb + (r + k * RY) * C));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (r + k * RY >= r1) break;
+      uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+        float a = fmaf(__low2float(h2), sc[2 * e], sh[2 * e]);
+        float b = fmaf(__high2float(h2), sc[2 * e + 1], sh[2 * e + 1]);
+        if (silu) {
+          a = __fdividef(a, 1.f + __expf(-a));
+          b = __fdividef(b, 1.f + __expf(-b));
+        }
+        const __nv_bfloat162 o2 = __floats2bfloat162_rn(a, b);
+        w[e] = *reinterpret_cast<const uint32_t*>(&o2);
+      }
+      *reinterpret_cast<uint4*>(yb + (r + k * RY) * C) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
 // rows variant: one warp per (row, group)
 __global__ void gn_rows_kernel(const float* __restrict__ x, int M, int C, int groups, const float* __restrict__ gamma,
                                const float* __restrict__ beta, float eps, int silu, float* __restrict__ y) {
@@ -212,6 +257,65 @@ __global__ void layer_norm_kernel(const TI* __restrict__ x, int64_t rows, int C,
     v[2] = (v[2] - mean) * rstd * gm.z + bt.z;
     v[3] = (v[3] - mean) * rstd * gm.w + bt.w;
     store4<TO>(y + row * C + q * 4, v);
+  }
+}
+
+// bf16 -> bf16 LayerNorm with the row held in registers (C <= 768): one global read, 16-byte accesses
+__global__ void __launch_bounds__(256) layer_norm_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int C,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                              __nv_bfloat16* __restrict__ y) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nch = C >> 3;
+  const __nv_bfloat16* p = x + row * C;
+  float v[3][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int ch = lane + 32 * k;
+    if (ch < nch) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(p) + ch);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+        v[k][2 * e] = __low2float(h2);
+        v[k][2 * e + 1] = __high2float(h2);
+        s += v[k][2 * e] + v[k][2 * e + 1];
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    if (lane + 32 * k < nch) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = v[k][e] - mean; ss = fmaf(d, d, ss); }
+    }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss / C + eps);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int ch = lane + 32 * k;
+    if (ch < nch) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + ch * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + ch * 8 + 4));
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      uint32_t w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 o2 = __floats2bfloat162_rn((v[k][2 * e] - mean) * rstd * gm[2 * e] + bt[2 * e],
+                                                        (v[k][2 * e + 1] - mean) * rstd * gm[2 * e + 1] + bt[2 * e + 1]);
+        w[e] = *reinterpret_cast<const uint32_t*>(&o2);
+      }
+      *(reinterpret_cast<uint4*>(y + row * C) + ch) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
   }
 }
 
@@ -485,6 +589,18 @@ void gn_stats(const Act& x, int groups, float eps, float* stats, float* partial,
 
 void gn_apply(const Act& x, const float* stats, const float* gamma, const float* beta, int groups, bool silu, const Act& out,
               cudaStream_t s) {
+  if (x.dt == BF16 && out.dt == BF16 && x.c % 8 == 0 && x.c / 8 <= 256) {
+    const int noct = x.c / 8;
+    const int RY = 256 / noct;
+    const int threads = ((noct * RY + 31) / 32) * 32;
+    const int64_t V = x.voxels();
+    const int rows_per_block = 16 * RY;   // 4 passes of 4 rows in flight per thread
+    dim3 grid(cdiv(V, rows_per_block), x.n);
+    gn_apply_bf16x8_kernel<<<grid, threads, 0, s>>>((const __nv_bfloat16*)x.p, stats, gamma, beta, V, x.c, groups, silu ? 1 : 0, noct, RY,
+                                                    rows_per_block, (__nv_bfloat16*)out.p);
+    ECHO_LAUNCH_CHECK();
+    return;
+  }
   const int nquad = x.c / 4;
   int RY = 256 / nquad;
   if (RY < 1) RY = 1;
@@ -512,6 +628,11 @@ void layer_norm(const void* x, DT xdt, int64_t rows, int C, const float* gamma, 
                 cudaStream_t s) {
   ECHO_CHECK(C % 4 == 0, "layer_norm: C %% 4");
   const int grid = cdiv(rows * 32, 256);
+  if (xdt == BF16 && ydt == BF16 && C % 8 == 0 && C <= 768) {
+    layer_norm_bf16_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, rows, C, gamma, beta, eps, (__nv_bfloat16*)y);
+    ECHO_LAUNCH_CHECK();
+    return;
+  }
 #define LN(TI, TO) layer_norm_kernel<TI, TO><<<grid, 256, 0, s>>>((const TI*)x, rows, C, gamma, beta, eps, (TO*)y)
   if (xdt == F32 && ydt == F32) LN(float, float);
   else if (xdt == F32) LN(float, __nv_bfloat16);
@@ -566,6 +687,28 @@ void ncdhw_to_cl(const float* x, int n, int c, int64_t V, void* out, DT odt, cud
   const int grid = grid_for((int64_t)n * c * V, 256);
   if (odt == F32) ncdhw_to_cl_kernel<float><<<grid, 256, 0, s>>>(x, n, c, V, (float*)out);
   else ncdhw_to_cl_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(x, n, c, V, (__nv_bfloat16*)out);
+  ECHO_LAUNCH_CHECK();
+}
+
+namespace {
+// NCDHW fp32 -> channels-last bf16 with the channel dimension zero-padded to cpad (one thread per voxel, 16-byte stores)
+__global__ void ncdhw_to_cl_pad16_kernel(const float* __restrict__ x, int n, int c, int64_t V, __nv_bfloat16* __restrict__ out) {
+  const int64_t rows = (int64_t)n * V;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t obj = r / V, v = r - obj * V;
+    __align__(16) __nv_bfloat16 t[16];
+#pragma unroll
+    for (int ch = 0; ch < 16; ++ch) t[ch] = __float2bfloat16(ch < c ? x[(obj * c + ch) * V + v] : 0.f);
+    uint4* o = reinterpret_cast<uint4*>(out + r * 16);
+    o[0] = reinterpret_cast<const uint4*>(t)[0];
+    o[1] = reinterpret_cast<const uint4*>(t)[1];
+  }
+}
+}  // namespace
+
+void ncdhw_to_cl_pad16(const float* x, int n, int c, int64_t V, __nv_bfloat16* out, cudaStream_t s) {
+  ECHO_CHECK(c <= 16, "ncdhw_to_cl_pad16: c > 16");
+  ncdhw_to_cl_pad16_kernel<<<grid_for((int64_t)n * V, 256), 256, 0, s>>>(x, n, c, V, out);
   ECHO_LAUNCH_CHECK();
 }
 
@@ -716,6 +859,46 @@ __global__ void gn_stats_from_colsum_kernel(const float* __restrict__ colsum, in
   }
 }
 }  // namespace
+
+namespace {
+// channel concat [A (CA channels) | B (CB channels)] of two tensors that each carry column partials
+__global__ void gn_stats_from_colsum2_kernel(const float* __restrict__ csa, int CA, const float* __restrict__ csb, int CB, int n,
+                                             int rows_per_obj, int groups, double count, float eps, float* __restrict__ stats) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= n * groups) return;
+  const int obj = i / groups, g = i % groups, C = CA + CB, cpg = C / groups;
+  double a = 0.0, b = 0.0;
+  const int total = rows_per_obj * cpg;
+  for (int k = lane; k < total; k += 32) {
+    const int r = k / cpg, c = g * cpg + (k - r * cpg);
+    const float* src = c < CA ? csa + (((int64_t)obj * rows_per_obj + r) * CA + c) * 2
+                              : csb + (((int64_t)obj * rows_per_obj + r) * CB + (c - CA)) * 2;
+    const float2 p = *reinterpret_cast<const float2*>(src);
+    a += (double)p.x;
+    b += (double)p.y;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane == 0) {
+    const double mean = a / count;
+    double var = b / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[2 * i] = (float)mean;
+    stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+}  // namespace
+
+void gn_stats_from_colsum2(const float* csa, int CA, const float* csb, int CB, int n_obj, int rows_per_obj, int groups, int64_t voxels,
+                           float eps, float* stats, cudaStream_t s) {
+  const int tot = n_obj * groups;
+  gn_stats_from_colsum2_kernel<<<cdiv((int64_t)tot * 32, 256), 256, 0, s>>>(csa, CA, csb, CB, n_obj, rows_per_obj, groups,
+                                                                            (double)voxels * ((CA + CB) / groups), eps, stats);
+  ECHO_LAUNCH_CHECK();
+}
 
 void gn_stats_from_colsum(const float* colsum, int n_obj, int rows_per_obj, int C, int groups, int64_t voxels, float eps, float* stats,
                           cudaStream_t s) {

@@ -10,6 +10,7 @@
 #include "unet.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 using namespace echo;
 
@@ -28,6 +29,14 @@ struct echo_layout {
   float *temb = nullptr, *e1 = nullptr, *emb = nullptr, *node = nullptr, *pred = nullptr, *latent = nullptr;
   float *embout = nullptr, *v2 = nullptr, *a2vec = nullptr, *eps = nullptr;
   int64_t* t_dev = nullptr;
+  // CUDA-graph replay of one DDPM iteration (layout_step)
+  float *sx = nullptr, *sobj = nullptr, *snoise = nullptr, *sout = nullptr;
+  int* t_slot = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  uint64_t gkey_id = 0;
+  int gkey_n = -1;
+  int64_t graph_launches = 0;
+  bool graph_failed = false;
   std::vector<int> a2_off;
   int a2_total = 0;
   int N = 0;   // rows of the current call
@@ -288,6 +297,11 @@ echo_layout* layout_create(const echo_layout_desc_t* desc, const echo_weight_t* 
     h->a2vec = h->pool.alloc_n<float>(N * h->a2_total);
     h->eps = h->pool.alloc_n<float>(N * d.out_channels);
     h->t_dev = h->pool.alloc_n<int64_t>(N);
+    h->sx = h->pool.alloc_n<float>(N * d.out_channels);
+    h->snoise = h->pool.alloc_n<float>(N * d.out_channels);
+    h->sout = h->pool.alloc_n<float>(N * d.out_channels);
+    h->sobj = h->pool.alloc_n<float>(N * d.obj_embed_dim);
+    h->t_slot = h->pool.alloc_n<int>(4);
     {
       int off = 0;
       auto add = [&](const AttnW& a) { h->a2_off.push_back(off); off += a.C; };
@@ -313,6 +327,7 @@ echo_layout* layout_create(const echo_layout_desc_t* desc, const echo_weight_t* 
 
 void layout_destroy(echo_layout* h) {
   if (!h) return;
+  if (h->gexec) cudaGraphExecDestroy(h->gexec);
   h->arena.destroy();
   h->pool.destroy();
   delete h;
@@ -323,13 +338,101 @@ void layout_forward(echo_layout* h, const echo_graph* g, const float* box_t, con
   h->forward(g, box_t, obj_embed, t, eps_out, s);
 }
 
+// ---- one DDPM iteration as a replayed CUDA graph ------------------------------------------------------------------
+// The layout step is ~320 dependent launches of microsecond kernels: issued one by one it is bound by launch latency,
+// not by the GPU.  The step is therefore captured once per (scene graph, node count) into a CUDA graph whose kernels
+// read the timestep from a device slot and the inputs from handle-owned staging buffers; an iteration is then
+// 1 staging kernel + 1 graph launch + 1 copy-out kernel.  ECHO_NO_GRAPH=1 disables it (per-kernel profiling).
+namespace {
+__global__ void layout_stage_in_kernel(const float* __restrict__ x, const float* __restrict__ obj, const float* __restrict__ noise,
+                                       int nx, int nobj, float* __restrict__ sx, float* __restrict__ sobj, float* __restrict__ snoise,
+                                       int* __restrict__ t_slot, int t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *t_slot = t;
+  if (i < nx) { sx[i] = x[i]; snoise[i] = noise[i]; }
+  if (i < nobj) sobj[i] = obj[i];
+}
+__global__ void layout_fill_t_kernel(const int* __restrict__ t_slot, int64_t* __restrict__ t_dev, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) t_dev[i] = *t_slot;
+}
+// same arithmetic as ddpm_update_kernel (elem.cu), timestep read from the device slot
+__global__ void layout_ddpm_update_kernel(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ noise,
+                                          const float* __restrict__ tab, int T, const int* __restrict__ t_slot, int count,
+                                          float* __restrict__ out) {
+  const int t = *t_slot;
+  const float a = tab[t], b = tab[T + t], c1 = tab[2 * T + t], c2 = tab[3 * T + t], lv = tab[4 * T + t];
+  const float sig = (t == 0 ? 0.f : 1.f) * expf(0.5f * lv);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) {
+    const float x0 = __fsub_rn(__fmul_rn(a, x[i]), __fmul_rn(b, eps[i]));
+    const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, x[i]));
+    out[i] = __fadd_rn(mean, __fmul_rn(sig, noise[i]));
+  }
+}
+__global__ void layout_copy_out_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+}  // namespace
+
 void layout_step(echo_layout* h, const echo_graph* g, const float* x_t, const float* obj_embed, int t, const float* noise, float* x_prev,
                  cudaStream_t s) {
   ECHO_CHECK(t >= 0 && t < h->d.time_num, "layout_step: t=%d outside [0, %d)", t, h->d.time_num);
   ECHO_CHECK(g, "layout_step: null graph");
-  fill_i64(h->t_dev, g->n_nodes, t, s);
-  h->forward(g, x_t, obj_embed, h->t_dev, h->eps, s);
-  ddpm_update(x_t, h->eps, noise, h->d_tab, h->d.time_num, t, (int64_t)g->n_nodes * h->d.out_channels, x_prev, s);
+  const int N = g->n_nodes, nx = N * h->d.out_channels, nobj = N * h->d.obj_embed_dim;
+  if (N == 0) return;
+  ECHO_CHECK(N <= h->d.max_nodes && h->d.in_channels == h->d.out_channels, "layout_step: graph exceeds handle capacity");
+  static const bool no_graph = getenv("ECHO_NO_GRAPH") != nullptr;
+  if (no_graph || h->graph_failed) {
+    fill_i64(h->t_dev, N, t, s);
+    h->forward(g, x_t, obj_embed, h->t_dev, h->eps, s);
+    ddpm_update(x_t, h->eps, noise, h->d_tab, h->d.time_num, t, (int64_t)nx, x_prev, s);
+    return;
+  }
+  const int mx = nx > nobj ? nx : nobj;
+  layout_stage_in_kernel<<<cdiv(mx, 256), 256, 0, s>>>(x_t, obj_embed, noise, nx, nobj, h->sx, h->sobj, h->snoise, h->t_slot, t);
+  ECHO_LAUNCH_CHECK();
+  if (!h->gexec || h->gkey_id != g->id || h->gkey_n != N) {
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    const int64_t before = g_launches;
+    cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+      try {
+        layout_fill_t_kernel<<<cdiv(N, 128), 128, 0, s>>>(h->t_slot, h->t_dev, N);
+        ECHO_LAUNCH_CHECK();
+        h->forward(g, h->sx, h->sobj, h->t_dev, h->eps, s);
+        layout_ddpm_update_kernel<<<cdiv(nx, 128), 128, 0, s>>>(h->sx, h->eps, h->snoise, h->d_tab, h->d.time_num, h->t_slot, nx, h->sout);
+        ECHO_LAUNCH_CHECK();
+      } catch (...) {
+        cudaStreamEndCapture(s, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        throw;
+      }
+      e = cudaStreamEndCapture(s, &graph);
+    }
+    if (e == cudaSuccess && graph) e = cudaGraphInstantiate(&h->gexec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (e != cudaSuccess || !h->gexec) {   // capture unavailable on this stream: run the kernels directly from now on
+      cudaGetLastError();
+      h->gexec = nullptr;
+      h->graph_failed = true;
+      fill_i64(h->t_dev, N, t, s);
+      h->forward(g, x_t, obj_embed, h->t_dev, h->eps, s);
+      ddpm_update(x_t, h->eps, noise, h->d_tab, h->d.time_num, t, (int64_t)nx, x_prev, s);
+      return;
+    }
+    h->graph_launches = g_launches - before;
+    g_launches = before;
+    h->gkey_id = g->id;
+    h->gkey_n = N;
+  }
+  ECHO_CUDA(cudaGraphLaunch(h->gexec, s));
+  count_launch((int)h->graph_launches);
+  layout_copy_out_kernel<<<cdiv(nx, 128), 128, 0, s>>>(h->sout, x_prev, nx);
+  ECHO_LAUNCH_CHECK();
 }
 
 }  // namespace echo

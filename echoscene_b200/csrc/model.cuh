@@ -51,6 +51,7 @@ struct Mat {
 
 // ---- opaque C handles ---------------------------------------------------------------------------------------------
 struct echo_graph {
+  uint64_t id = 0;              // unique per created graph (keys cached CUDA graphs; pointers can be recycled)
   int n_nodes = 0, n_triples = 0;
   int64_t* triples = nullptr;   // (T,3) int64 device copy
   int* s_idx = nullptr;         // (T)

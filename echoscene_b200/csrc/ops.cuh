@@ -52,6 +52,8 @@ bool tc_available();
 // rows of the column-sum partial buffer per OBJECT for this problem (the tcgen05 kernel writes 4 per 128-voxel tile)
 int gemm_tc_colsum_rows_per_obj(const GemmArgs& g);
 // GroupNorm statistics from column partials: stats[(obj, group)] = (mean, rstd)
+void gn_stats_from_colsum2(const float* csa, int CA, const float* csb, int CB, int n_obj, int rows_per_obj, int groups, int64_t voxels,
+                           float eps, float* stats, cudaStream_t s);
 void gn_stats_from_colsum(const float* colsum, int n_obj, int rows_per_obj, int C, int groups, int64_t voxels, float eps, float* stats,
                           cudaStream_t s);
 // precision: ECHO_PREC_*; BF16 falls back to the SIMT kernel (bf16 operands, fp32 accumulate) for shapes the
@@ -98,6 +100,7 @@ void concat_channels(const Act& a, const Act& b, const Act& out, cudaStream_t s)
 void upsample_hw2(const Act& x, const Act& out, cudaStream_t s);              // nearest x(1,2,2)
 void maxpool3d(const Act& x, int k, int stride, const Act& out, cudaStream_t s);
 void ncdhw_to_cl(const float* x, int n, int c, int64_t voxels, void* out, DT odt, cudaStream_t s);
+void ncdhw_to_cl_pad16(const float* x, int n, int c, int64_t voxels, __nv_bfloat16* out, cudaStream_t s);   // channels zero-padded to 16
 // x channels-last with row stride ld (>= c) -> out (n, c, voxels)
 void cl_to_ncdhw(const void* x, DT xdt, int n, int c, int64_t voxels, int ld, float* out, cudaStream_t s);
 void convert(const void* x, DT xdt, void* y, DT ydt, int64_t count, cudaStream_t s);

@@ -102,7 +102,9 @@ struct echo_shape {
     float* partial = x.colsum ? nullptr : arena.alloc_n<float>(gn_partial_floats(x, 32));
     Act o = new_act(x.n, x.d, x.h, x.w, x.c, odt);
     if (!dry) {
-      if (x.colsum) gn_stats_from_colsum(x.colsum, x.n, x.colsum_rows, x.c, 32, x.voxels(), eps, stats, s);   // no pass over x
+      if (x.colsum && x.colsum2)
+        gn_stats_from_colsum2(x.colsum, x.c_split, x.colsum2, x.c - x.c_split, x.n, x.colsum_rows, 32, x.voxels(), eps, stats, s);
+      else if (x.colsum) gn_stats_from_colsum(x.colsum, x.n, x.colsum_rows, x.c, 32, x.voxels(), eps, stats, s);   // no pass over x
       else gn_stats(x, 32, eps, stats, partial, s);
       gn_apply(x, stats, nw.g, nw.b, 32, silu, o, s);
     }
@@ -271,9 +273,18 @@ struct echo_shape {
     int ai = 0;
     for (auto& b : plan.in_blocks) {
       if (b.kind == BlockW::CONV_IN) {
-        Act o = new_act(h.n, h.d, h.h, h.w, b.conv.cout, adt);   // stem: SIMT path (3 input channels), no column partials
-        contract(h, b.conv, 3, 1, nullptr, 0, nullptr, o, s);
-        h = o;
+        if (prec == ECHO_PREC_BF16 && plan.stem_pad.wb && adt == BF16) {
+          // stem on the tensor cores: latent re-laid as bf16 channels-last with 3 -> 16 zero-padded channels
+          Act x16 = new_act(h.n, h.d, h.h, h.w, 16, BF16);
+          if (!dry) ncdhw_to_cl_pad16(x_local, h.n, d.in_channels, h.voxels(), (__nv_bfloat16*)x16.p, s);
+          Act o = new_act_cs(h.n, h.d, h.h, h.w, b.conv.cout, adt);
+          contract(x16, plan.stem_pad, 3, 1, nullptr, 0, nullptr, o, s);
+          h = o;
+        } else {
+          Act o = new_act(h.n, h.d, h.h, h.w, b.conv.cout, adt);   // fp32 parity mode: SIMT path (K = 81)
+          contract(h, b.conv, 3, 1, nullptr, 0, nullptr, o, s);
+          h = o;
+        }
       } else if (b.kind == BlockW::RES) {
         h = res_block(h, b.res, n_local, s);
         if (b.attn) { join(); h = transformer(h, b.at, ai++, s); }
@@ -293,6 +304,9 @@ struct echo_shape {
       hs.pop_back();
       Act cat = new_act(h.n, h.d, h.h, h.w, h.c + sk.c, adt);
       if (!dry) concat_channels(h, sk, cat, s);
+      if (h.colsum && sk.colsum && h.colsum_rows == sk.colsum_rows) {   // GroupNorm statistics of the concat from both producers
+        cat.colsum = h.colsum; cat.colsum_rows = h.colsum_rows; cat.colsum2 = sk.colsum; cat.c_split = h.c;
+      }
       h = res_block(cat, b.res, n_local, s);
       if (b.attn) h = transformer(h, b.at, ai++, s);
       if (b.up) {   // nearest x(1,2,2) then Conv3d k3 (openai_model_3d.py:150-157)

@@ -51,6 +51,7 @@ struct UNetPlan {
   AttnW mid_at;
   NormW out_norm;
   ConvW out_conv;
+  ConvW stem_pad;           // bf16 mode: stem conv with cin zero-padded 3 -> 16 so it runs on the tcgen05 kernel
   ConvW out_conv_pad;       // bf16 mode: out conv zero-padded to 32 output channels so it runs on the tcgen05 kernel
   ConvW time0, time2;       // time_embed.0 / .2
   ConvW emb_stack;          // all ResBlock emb_layers.1 stacked [sum cout, 4*mc]

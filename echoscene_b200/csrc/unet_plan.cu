@@ -247,6 +247,22 @@ void build_unet_plan(const WeightMap& wm, const UNetCfg& cfg, DevPool& pool, UNe
       plan.out_blocks.push_back(b);
     }
   }
+  if (cfg.want_bf16 && cfg.dims == 3 && cfg.in_channels < 16) {
+    // stem: pad the input channels to one UMMA K step (16); the padded activation channels are zero as well
+    const ConvW& c = plan.in_blocks[0].conv;
+    const size_t n_src = (size_t)c.cout * c.taps * c.cin, n_dst = (size_t)c.cout * c.taps * 16;
+    std::vector<float> hsrc(n_src), hdst(n_dst, 0.f);
+    ECHO_CUDA(cudaStreamSynchronize(s));
+    ECHO_CUDA(cudaMemcpy(hsrc.data(), c.w, n_src * sizeof(float), cudaMemcpyDeviceToHost));
+    for (size_t r = 0; r < (size_t)c.cout * c.taps; ++r)
+      for (int ch = 0; ch < c.cin; ++ch) hdst[r * 16 + ch] = hsrc[r * c.cin + ch];
+    float* o = pool.alloc_n<float>(n_dst);
+    ECHO_CUDA(cudaMemcpy(o, hdst.data(), n_dst * sizeof(float), cudaMemcpyHostToDevice));
+    plan.stem_pad = c;
+    plan.stem_pad.cin = 16;
+    plan.stem_pad.w = o;
+    plan.stem_pad.wb = P.to_bf16(o, n_dst);
+  }
   plan.out_norm = P.norm("out.0", mc);
   plan.out_conv = P.conv("out.2", mc, cfg.out_channels, 3);
   if (cfg.want_bf16 && cfg.dims == 3 && cfg.out_channels < 32) {
