@@ -21,6 +21,7 @@
 #include "ops.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 #include <mutex>
 
 namespace echo {
@@ -34,8 +35,8 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;       // 16 KiB
 constexpr int SMEM_LIMIT = 227 * 1024;                     // opt-in dynamic shared memory per CTA on sm_100
 constexpr int SMEM_FIXED = 1024 /*align*/ + 512 /*barriers + tmem ptr*/;
 // bytes in flight per SM is what hides the L2 latency of the TMA stream: use every stage that fits
-static inline int stages_for(int block_n) {
-  const int st = (SMEM_LIMIT - SMEM_FIXED) / (A_STAGE_BYTES + block_n * BLOCK_K * 2);
+static inline int stages_for(int b_rows) {
+  const int st = (SMEM_LIMIT - SMEM_FIXED) / (A_STAGE_BYTES + b_rows * BLOCK_K * 2);
   return st > MAX_STAGES ? MAX_STAGES : st;
 }
 constexpr int MAX_TAPS = 27;
@@ -143,6 +144,58 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// ---- CTA-pair (cta_group::2) variants: two CTAs of a cluster share one UMMA of M = 256; each stages its own 128 rows
+//      of A and HALF of the B tile, which is what brings the per-SM operand traffic under the 64 B/clk L2->SM port ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 remAddr32;\n"
+      "mapa.shared::cluster.u32 remAddr32, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> CTA 0's copy
+__device__ __forceinline__ void tma_load_5d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate));
+}
+// commit of cta_group::2 MMAs: arrives on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
 // Halving butterfly over the 32 lanes: on return v[0] of lane l is the sum over all lanes of element l.
 __device__ __forceinline__ void col_butterfly(float (&v)[32], int lane) {
 #pragma unroll
@@ -166,73 +219,101 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 
+// CTA2 = false: one CTA per 128 x block_n tile (cta_group::1).
+// CTA2 = true : a cluster of two CTAs per 256 x block_n tile (cta_group::2, launched with cluster dims {2,1,1}); the
+//               pair's leader (rank 0) issues the MMAs, both CTAs run their own TMA producer and epilogue.
+template <bool CTA2>
 __global__ void __launch_bounds__(256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
   const int STAGES = p.stages;
-  const int B_STAGE_BYTES = p.block_n * BLOCK_K * 2;
+  const int B_ROWS = CTA2 ? (p.block_n >> 1) : p.block_n;   // rows of the B tile staged by THIS CTA
+  const int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
   uint64_t* bars = (uint64_t*)(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
-  uint64_t* full_bar = bars;                   // [STAGES]
+  uint64_t* full_bar = bars;                   // [STAGES]  (CTA2: the leader's copy is the one in use)
   uint64_t* empty_bar = bars + STAGES;         // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;     // [2]
-  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]       (CTA2: the leader's copy is the one in use)
   uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
 
+  if (CTA2) cluster_sync_all();   // both CTAs resident before the paired TMEM allocation
   if (warp == 1 && elect_one()) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], CTA2 ? 2 : 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CTA2 ? 256 : 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (CTA2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  // tile schedule: CTA2 walks (n_blk, m_pair) pairs, this CTA owning m_blk = 2*m_pair + rank
+  const int sched_m = CTA2 ? (p.num_m_tiles >> 1) : p.num_m_tiles;
+  const int num_tiles = sched_m * p.num_n_tiles;
+  const int tile0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tstride = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int kblocks = p.taps * p.kblocks_per_tap;
-  const uint32_t stage_bytes = (uint32_t)A_STAGE_BYTES + (uint32_t)p.block_n * BLOCK_K * 2;
+  const uint32_t stage_bytes = (uint32_t)A_STAGE_BYTES + (uint32_t)B_STAGE_BYTES;
 
   if (warp == 0) {
     // ================= TMA producer =================
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_blk = tile / p.num_m_tiles, m_blk = tile - n_blk * p.num_m_tiles;
+      for (int tile = tile0; tile < num_tiles; tile += tstride) {
+        const int n_blk = tile / sched_m, mm = tile - n_blk * sched_m;
+        const int m_blk = CTA2 ? 2 * mm + (int)rank : mm;
         int r = m_blk;
         const int tw = r % p.tiles_w; r /= p.tiles_w;
         const int th = r % p.tiles_h; r /= p.tiles_h;
         const int td = r % p.tiles_d; const int obj = r / p.tiles_d;
         const int w0 = tw * p.bw, h0 = th * p.bh, d0 = td * p.bd;
+        const int n_row0 = n_blk * p.block_n + (CTA2 ? (int)rank * B_ROWS : 0);
         for (int tap = 0; tap < p.taps; ++tap) {
           const int cw = w0 + p.tap_w[tap], chh = h0 + p.tap_h[tap], cd = d0 + p.tap_d[tap];
           const int cn = obj * p.obj_mul + p.tap_p[tap];
           for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-            tma_load_5d(&map_a, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, cw, chh, cd, cn);
-            tma_load_2d(&map_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, tap * p.cin + kb * BLOCK_K, n_blk * p.block_n);
+            if (CTA2) {
+              // both CTAs' copies complete on the LEADER's full barrier (2 arrivals + the bytes of both CTAs)
+              if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
+              else mbar_arrive_remote(&full_bar[stage], 0);
+              tma_load_5d_2sm(&map_a, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, cw, chh, cd, cn);
+              tma_load_2d_2sm(&map_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, tap * p.cin + kb * BLOCK_K, n_row0);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+              tma_load_5d(&map_a, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, cw, chh, cd, cn);
+              tma_load_2d(&map_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, tap * p.cin + kb * BLOCK_K, n_row0);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    // instruction descriptor: D=f32, A=B=bf16, both K-major, N = block_n, M = 128
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+  } else if (warp == 1 && leader) {
+    // ================= MMA issuer (the pair's leader CTA only) =================
+    // instruction descriptor: D=f32, A=B=bf16, both K-major, N = block_n, M = 128 (or 256 across the CTA pair)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
+                           ((uint32_t)((CTA2 ? 2 * BLOCK_M : BLOCK_M) >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
     int iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+    for (int tile = tile0; tile < num_tiles; tile += tstride, ++iter) {
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
       mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -248,11 +329,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
             int nk = (p.cin - kb * BLOCK_K + UMMA_K - 1) / UMMA_K;   // skip the zero-filled channel tail
             nk = nk > BLOCK_K / UMMA_K ? BLOCK_K / UMMA_K : nk;
-            for (int k = 0; k < nk; ++k)
-              umma_bf16(tmem_d, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
-                        (kb_total | k) != 0 ? 1u : 0u);
-            umma_commit(&empty_bar[stage]);                         // frees the smem slot when these MMAs retire
-            if (kb_total == kblocks - 1) umma_commit(&tmem_full[as]);   // accumulator complete -> epilogue
+            if (CTA2) {
+              for (int k = 0; k < nk; ++k)
+                umma_bf16_2sm(tmem_d, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
+                              (kb_total | k) != 0 ? 1u : 0u);
+              umma_commit_2sm(&empty_bar[stage]);                          // frees the slot in BOTH CTAs
+              if (kb_total == kblocks - 1) umma_commit_2sm(&tmem_full[as]);   // both epilogues
+            } else {
+              for (int k = 0; k < nk; ++k)
+                umma_bf16(tmem_d, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
+                          (kb_total | k) != 0 ? 1u : 0u);
+              umma_commit(&empty_bar[stage]);                         // frees the smem slot when these MMAs retire
+              if (kb_total == kblocks - 1) umma_commit(&tmem_full[as]);   // accumulator complete -> epilogue
+            }
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -265,10 +354,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int row = ew * 32 + lane;                // tile row = box voxel index
     const int ww = row % p.bw, hh = (row / p.bw) % p.bh, dd = row / (p.bw * p.bh);
     int iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+    for (int tile = tile0; tile < num_tiles; tile += tstride, ++iter) {
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
-      const int n_blk = tile / p.num_m_tiles, m_blk = tile - n_blk * p.num_m_tiles;
+      const int n_blk = tile / sched_m, mm = tile - n_blk * sched_m;
+      const int m_blk = CTA2 ? 2 * mm + (int)rank : mm;
       int r = m_blk;
       const int tw = r % p.tiles_w; r /= p.tiles_w;
       const int th = r % p.tiles_h; r /= p.tiles_h;
@@ -397,15 +487,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[as]);
+      if (CTA2 && !leader) mbar_arrive_remote(&tmem_empty[as], 0);   // the leader's MMA warp owns the accumulator ring
+      else mbar_arrive(&tmem_empty[as]);
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();   // (pair) nobody still signals a barrier or reads TMEM of an exited CTA
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    if (CTA2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -453,7 +545,8 @@ void tc_init() {
   }
   g_tc.encode = (EncodeTiledFn)fn;
   g_tc.sms = prop.multiProcessorCount;
-  if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
+  if (cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
     cudaGetLastError();
     return;
   }
@@ -562,6 +655,9 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   p.colsum = g.colsum;
   p.geglu = g.epi == 1;
   if (p.geglu) { p.block_n = 256; p.num_n_tiles = g.cout / 256; }
+  // CTA pairs (cta_group::2) whenever the 128-row tiles pair up: halves the B bytes each SM has to pull from L2
+  static const int mode_env = getenv("ECHO_TC_MODE") ? atoi(getenv("ECHO_TC_MODE")) : 0;   // 1 / 2 force a mode (tests, profiling)
+  const bool cta2 = mode_env != 1 && (p.num_m_tiles % 2 == 0) && (p.block_n % 16 == 0);
 
   CUtensorMap map_a, map_b;
   {
@@ -578,18 +674,37 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   {
     const cuuint64_t dims[2] = {(cuuint64_t)g.ktot(), (cuuint64_t)g.cout};
     const cuuint64_t strides[1] = {(cuuint64_t)g.ktot() * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.block_n};
+    const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(cta2 ? p.block_n / 2 : p.block_n)};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = g_tc.encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)g.W, dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ECHO_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
   }
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int grid = tiles < g_tc.sms ? tiles : g_tc.sms;
-  p.stages = stages_for(p.block_n);
-  const int smem_bytes = p.stages * (A_STAGE_BYTES + p.block_n * BLOCK_K * 2) + SMEM_FIXED;
-  gemm_tc_kernel<<<grid, 256, smem_bytes, s>>>(map_a, map_b, p);
+  const int tiles = p.num_m_tiles * p.num_n_tiles;   // 128-row CTA tiles in both modes
+  const int b_rows = cta2 ? p.block_n / 2 : p.block_n;
+  p.stages = stages_for(b_rows);
+  const int smem_bytes = p.stages * (A_STAGE_BYTES + b_rows * BLOCK_K * 2) + SMEM_FIXED;
+  if (cta2) {
+    int grid = tiles < (g_tc.sms & ~1) ? tiles : (g_tc.sms & ~1);   // whole CTA pairs, one CTA per SM
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ECHO_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, map_a, map_b, p));
+  } else {
+    const int grid = tiles < g_tc.sms ? tiles : g_tc.sms;
+    gemm_tc_kernel<false><<<grid, 256, smem_bytes, s>>>(map_a, map_b, p);
+  }
   ECHO_LAUNCH_CHECK();
 }
 
