@@ -10,6 +10,7 @@ struct echo_layout;
 struct echo_shape;
 
 namespace echo {
+void set_tc_mode(int);
 const char* last_error();
 echo_layout* layout_create(const echo_layout_desc_t*, const echo_weight_t*, int);
 void layout_destroy(echo_layout*);
@@ -73,6 +74,7 @@ int echo_has_tcgen05(void) {
   guard([&] { r = tc_available() ? 1 : 0; });
   return r;
 }
+void echo_debug_set_tc_mode(int mode) { echo::set_tc_mode(mode); }
 int64_t echo_launch_count(void) { return g_launches; }
 void echo_launch_count_reset(void) { g_launches = 0; }
 

@@ -526,6 +526,7 @@ struct TcState {
   int sms = 148;
 };
 TcState g_tc;
+int g_tc_mode = 0;   // 0 = automatic, 1 = one CTA per tile, 2 = CTA pairs where possible (echo_debug_set_tc_mode)
 std::mutex g_tc_mu;
 
 void tc_init() {
@@ -566,6 +567,8 @@ int pick_block_n(int cout) {
 }
 
 }  // namespace
+
+void set_tc_mode(int m) { g_tc_mode = m; }
 
 bool tc_available() {
   tc_init();
@@ -657,7 +660,8 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   if (p.geglu) { p.block_n = 256; p.num_n_tiles = g.cout / 256; }
   // CTA pairs (cta_group::2) whenever the 128-row tiles pair up: halves the B bytes each SM has to pull from L2
   static const int mode_env = getenv("ECHO_TC_MODE") ? atoi(getenv("ECHO_TC_MODE")) : 0;   // 1 / 2 force a mode (tests, profiling)
-  const bool cta2 = mode_env != 1 && (p.num_m_tiles % 2 == 0) && (p.block_n % 16 == 0);
+  const int mode = g_tc_mode ? g_tc_mode : mode_env;
+  const bool cta2 = mode != 1 && (p.num_m_tiles % 2 == 0) && (p.block_n % 16 == 0);
 
   CUtensorMap map_a, map_b;
   {

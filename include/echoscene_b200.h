@@ -116,6 +116,8 @@ ECHO_API int echo_has_tcgen05(void);
 /* kernels launched by this library on the calling thread since the last reset (bench.py's gpu_launches). */
 ECHO_API int64_t echo_launch_count(void);
 ECHO_API void echo_launch_count_reset(void);
+/* tuning/profiling knob of the tcgen05 GEMM: 0 = automatic, 1 = one CTA per 128-row tile, 2 = CTA pairs (cta_group::2). */
+ECHO_API void echo_debug_set_tc_mode(int mode);
 
 /* ---- graph: edges = stack([s, o]) of `triples` (T,3) int64 [s,p,o] — denoise_net.py:759-761, graph.py:142-143 */
 ECHO_API int echo_graph_create(echo_graph_t** out, const int64_t* triples_dev, int32_t n_triples, int32_t n_nodes, void* stream);
