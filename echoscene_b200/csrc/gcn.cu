@@ -101,7 +101,7 @@ Mat plain_linear(const WeightMap& wm, const std::string& lin, int nout, int K, D
 
 // Few-row kernel up to 64 rows, tiled SIMT GEMM above (batched scene graphs: hundreds of nodes / thousands of edges).
 void linear_auto(const LinArgs& a, cudaStream_t s) {
-  if (a.M <= 64 || a.in_act != 0 || a.act == 2) {
+  if (a.M <= 64 || a.in_act != 0 || a.act == 2 || a.pro != PRO_NONE || a.X2 || a.res2) {
     linear_rows(a, s);
     return;
   }

@@ -43,62 +43,79 @@ struct echo_layout {
 
   float* buf(int C) { return arena.alloc_n<float>((size_t)N * C); }
 
-  void lin(const float* X, int64_t ldx, const ConvW& w, float* Y, int64_t ldy, const float* res, int64_t ld_res, int in_act, int act,
-           cudaStream_t s) {
+  // input of a fused Linear: (possibly concatenated) rows + the elementwise op that precedes the Linear in the network
+  struct In {
+    const float* X = nullptr; int C = 0; int64_t ld = 0;   // ld = 0: rows are dense (C, or 2C for the GEGLU input)
+    const float* X2 = nullptr; int C2 = 0;
+    int pro = PRO_NONE; const NormW* nw = nullptr; float eps = 1e-5f; bool silu = false;
+    int width() const { return C + C2; }
+  };
+  static In plain(const float* X, int C) { In i; i.X = X; i.C = C; return i; }
+
+  void lin(const In& in, const ConvW& w, float* Y, int64_t ldy, const float* res, int64_t ld_res, int act, cudaStream_t s,
+           const float* res2 = nullptr, int64_t ld_res2 = 0) {
     LinArgs a;
-    a.X = X; a.ldx = ldx; a.M = N; a.K = w.cin; a.nout = w.cout; a.bias = w.b; a.Y = Y; a.ldy = ldy;
-    a.res = res; a.ld_res = ld_res; a.in_act = in_act; a.act = act;
+    a.X = in.X; a.ldx = in.ld ? in.ld : (in.pro == PRO_GEGLU ? 2 * in.C : in.C); a.M = N; a.K = w.cin; a.nout = w.cout; a.bias = w.b; a.Y = Y; a.ldy = ldy;
+    if (in.X2) { a.X2 = in.X2; a.ldx2 = in.C2; a.K1 = in.C; }
+    a.res = res; a.ld_res = ld_res; a.res2 = res2; a.ld_res2 = ld_res2; a.act = act;
+    a.pro = in.pro;
+    if (in.nw) { a.gamma = in.nw->g; a.beta = in.nw->b; }
+    a.eps = in.eps; a.pro_act = in.silu ? 1 : 0;
+    if (in.pro == PRO_GN) a.cpg = in.width() / 32;
+    ECHO_CHECK((in.pro == PRO_GEGLU ? in.C : in.width()) == w.cin, "layout: linear input width %d != %d", in.width(), w.cin);
     if (prec == ECHO_PREC_BF16 && w.wb && N <= 64) { a.W = w.wb; a.w_dt = BF16; }
     else { a.W = w.w; a.w_dt = F32; }
     linear_auto(a, s);
   }
+  void lin(const float* X, int64_t ldx, const ConvW& w, float* Y, int64_t ldy, const float* res, int64_t ld_res, int in_act, int act,
+           cudaStream_t s) {
+    In i = plain(X, w.cin);
+    i.ld = ldx;
+    if (in_act == 1) i.pro = PRO_SILU;
+    lin(i, w, Y, ldy, res, ld_res, act, s);
+  }
 
-  // ResBlock._forward on length-1 signals (denoise_net.py:293-313)
-  float* res_block(const float* x, const ResW& r, cudaStream_t s) {
+  // ResBlock._forward on length-1 signals (denoise_net.py:293-313): GroupNorm+SiLU are prologues of the two Linears
+  float* res_block(const In& x, const ResW& r, cudaStream_t s) {
     float* out = buf(r.cout);
     const size_t m = arena.mark();
-    float* a1 = buf(r.cin);
-    gn_rows(x, N, r.cin, 32, r.n1.g, r.n1.b, 1e-5f, true, a1, s);
+    In a1 = x; a1.pro = PRO_GN; a1.nw = &r.n1; a1.eps = 1e-5f; a1.silu = true;
     float* h1 = buf(r.cout);
-    lin(a1, r.cin, r.c1, h1, r.cout, embout + r.emb_off, plan.emb_total, 0, 0, s);
-    float* a2 = buf(r.cout);
-    gn_rows(h1, N, r.cout, 32, r.n2.g, r.n2.b, 1e-5f, true, a2, s);
-    const float* skip = x;
+    lin(a1, r.c1, h1, r.cout, embout + r.emb_off, plan.emb_total, 0, s);
+    const float* skip = x.X;
     if (r.has_skip) {
       float* sk = buf(r.cout);
-      lin(x, r.cin, r.skip, sk, r.cout, nullptr, 0, 0, 0, s);
+      lin(x, r.skip, sk, r.cout, nullptr, 0, 0, s);
       skip = sk;
+    } else {
+      ECHO_CHECK(!x.X2, "layout: identity skip over a concatenated input");
     }
-    lin(a2, r.cout, r.c2, out, r.cout, skip, r.cout, 0, 0, s);
+    In a2 = plain(h1, r.cout); a2.pro = PRO_GN; a2.nw = &r.n2; a2.eps = 1e-5f; a2.silu = true;
+    lin(a2, r.c2, out, r.cout, skip, r.cout, 0, s);
     arena.release(m);
     return out;
   }
 
-  // SpatialTransformer1D with one token per object (attention.py:353-396, 222-245)
+  // SpatialTransformer1D with one token per object (attention.py:353-396, 222-245): 6 fused Linears
   float* transformer(const float* x, const AttnW& a, int ai, cudaStream_t s) {
     const int C = a.C;
     float* out = buf(C);
     const size_t m = arena.mark();
-    float* xn = buf(C);
-    gn_rows(x, N, C, 32, a.norm.g, a.norm.b, 1e-6f, false, xn, s);
+    In xn = plain(x, C); xn.pro = PRO_GN; xn.nw = &a.norm; xn.eps = 1e-6f;            // Normalize (eps 1e-6) -> proj_in
     float* t0 = buf(C);
-    lin(xn, C, a.proj_in, t0, C, nullptr, 0, 0, 0, s);
-    float* l1 = buf(C);
-    layer_norm(t0, F32, N, C, a.ln1.g, a.ln1.b, 1e-5f, l1, F32, s);
+    lin(xn, a.proj_in, t0, C, nullptr, 0, 0, s);
+    In l1 = plain(t0, C); l1.pro = PRO_LN; l1.nw = &a.ln1;                             // norm1 -> attn1.to_v (softmax over one key == 1)
     float* v = buf(C);
-    lin(l1, C, a.v_only, v, C, nullptr, 0, 0, 0, s);                 // attn1: softmax over one key == 1
-    float* t1 = buf(C);
-    lin(v, C, a.attn1_out, t1, C, t0, C, 0, 0, s);
-    add_rowvec(t1, F32, N, C, a2vec + a2_off[ai], a2_total, 1, s);   // attn2: to_out(to_v(context)) + x
-    float* l3 = buf(C);
-    layer_norm(t1, F32, N, C, a.ln3.g, a.ln3.b, 1e-5f, l3, F32, s);
+    lin(l1, a.v_only, v, C, nullptr, 0, 0, s);
+    float* t1 = buf(C);                                                                 // to_out + x + [attn2: to_out(to_v(context))]
+    lin(plain(v, C), a.attn1_out, t1, C, t0, C, 0, s, a2vec + a2_off[ai], a2_total);
+    In l3 = plain(t1, C); l3.pro = PRO_LN; l3.nw = &a.ln3;                             // norm3 -> GEGLU proj
     float* f1 = buf(8 * C);
-    lin(l3, C, a.ff1, f1, 8 * C, nullptr, 0, 0, 0, s);
-    float* gg = buf(4 * C);
-    geglu(f1, F32, N, 4 * C, gg, F32, s);
+    lin(l3, a.ff1, f1, 8 * C, nullptr, 0, 0, s);
+    In gg = plain(f1, 4 * C); gg.pro = PRO_GEGLU;                                       // a * gelu(g) -> ff.net.2, + x
     float* t2 = buf(C);
-    lin(gg, 4 * C, a.ff2, t2, C, t1, C, 0, 0, s);
-    lin(t2, C, a.proj_out, out, C, x, C, 0, 0, s);
+    lin(gg, a.ff2, t2, C, t1, C, 0, s);
+    lin(plain(t2, C), a.proj_out, out, C, x, C, 0, s);
     arena.release(m);
     return out;
   }
@@ -145,7 +162,7 @@ struct echo_layout {
         lin(box_t, d.in_channels, b.conv, o, b.conv.cout, nullptr, 0, 0, 0, s);
         h = o; hc = b.conv.cout;
       } else if (b.kind == BlockW::RES) {
-        h = res_block(h, b.res, s); hc = b.res.cout;
+        h = res_block(plain(h, hc), b.res, s); hc = b.res.cout;
         if (b.attn) h = transformer(h, b.at, ai++, s);
       } else {   // Downsample: Conv1d k3 stride 2 pad 1 on length 1 -> centre tap (denoise_net.py:172-198)
         float* o = buf(b.conv.cout);
@@ -154,16 +171,15 @@ struct echo_layout {
       }
       hs.push_back({h, hc});
     }
-    h = res_block(h, plan.mid0, s);
+    h = res_block(plain(h, hc), plan.mid0, s);
     h = transformer(h, plan.mid_at, ai++, s);
-    h = res_block(h, plan.mid2, s);
+    h = res_block(plain(h, plan.mid0.cout), plan.mid2, s);
     hc = plan.mid2.cout;
     for (auto& b : plan.out_blocks) {
       auto sk = hs.back();
       hs.pop_back();
-      float* cat = buf(hc + sk.second);
-      copy_cols(h, hc, N, hc, cat, hc + sk.second, s);
-      copy_cols(sk.first, sk.second, N, sk.second, cat + hc, hc + sk.second, s);
+      In cat = plain(h, hc);   // th.cat([h, hs.pop()], dim=1) is never materialised: the fused Linears read both sources
+      cat.X2 = sk.first; cat.C2 = sk.second;
       h = res_block(cat, b.res, s); hc = b.res.cout;
       if (b.attn) h = transformer(h, b.at, ai++, s);
       if (b.up) {   // Upsample: scale_factor 1 (denoise_net.py:154) then Conv1d k3 -> centre tap
@@ -172,12 +188,11 @@ struct echo_layout {
         h = o; hc = b.conv.cout;
       }
     }
-    float* hn = buf(hc);
-    gn_rows(h, N, hc, 32, plan.out_norm.g, plan.out_norm.b, 1e-5f, true, hn, s);
     {
       const int p = prec;
       prec = ECHO_PREC_FP32;
-      lin(hn, hc, plan.out_conv, eps_out, d.out_channels, nullptr, 0, 0, 0, s);
+      In hn = plain(h, hc); hn.pro = PRO_GN; hn.nw = &plan.out_norm; hn.eps = 1e-5f; hn.silu = true;
+      lin(hn, plan.out_conv, eps_out, d.out_channels, nullptr, 0, 0, s);
       prec = p;
     }
   }

@@ -1,22 +1,29 @@
-// Few-row linear layers: Y[M, nout] = epi( f(X)[M, K] @ W[nout, K]^T ), M = nodes or edges of one scene graph.
+// Few-row linear layers: Y[M, nout] = epi( pro(X)[M, K] @ W[nout, K]^T ), M = nodes or edges of one scene graph.
 //
-// These are the layout branch's ~180 contractions per step, the GraphTripleConv MLPs and every per-object vector op of
-// the shape step (time MLP, ResBlock emb_layers, attn2 to_v/to_out).  With a few dozen rows they are bound by streaming
-// W from HBM once, and — being tiny — by how many bytes are in flight: a launch must put >= ~1200 warps on the chip.
-//
-// Layout of one CTA: RN = 4 output features x MT rows, K split over the CTA's WK warps (1..8, chosen per launch so that
-// small-nout layers still fill the machine).  Inside a warp the 32 lanes split the K slice in 16-byte pieces (512
-// contiguous bytes of a weight row per warp-load, all RN x unroll loads issued before the FMAs), X is re-read through L1
-// (it is tiny).  Reduction: a halving butterfly over the lanes (62 shuffles for 64 accumulators instead of 320), then a
-// fixed-order sum over the WK warps through shared memory — deterministic, no atomics.
+// These are the layout branch's contractions, the GraphTripleConv MLPs and every per-object vector op of the shape step
+// (time MLP, ResBlock emb_layers, attn2 to_v/to_out).  With a few dozen rows they are bound by streaming W once and —
+// being tiny — by latency and launch count, so the kernel (a) puts >= ~1200 warps on the chip per launch (RN = 4 output
+// features x MT = 8 rows per CTA, K split over the CTA's 1..8 warps) and (b) absorbs the elementwise op that precedes
+// the Linear in the network as a PROLOGUE applied while X is loaded, so a ResBlock or transformer block of the layout
+// denoiser is 2-6 launches instead of 6-12:
+//   PRO_SILU   x -> silu(x)                                   (emb_layers: Linear(SiLU(emb)))
+//   PRO_GN     GroupNorm(32 groups)(+SiLU): a group is 16 or 32 consecutive channels = 4 or 8 adjacent lanes of the warp,
+//              so its statistics are a 2-3 step shuffle — no pass over X, no extra kernel
+//   PRO_LN     LayerNorm: each warp first reduces its rows over the full K (X is tiny and L1-resident)
+//   PRO_GEGLU  x = a * gelu_erf(g) with [a | g] the two halves of a 2K-wide row        (attention.py:39-46)
+// X may be the channel concat [X1 | X2] of two tensors (skip connections), and the epilogue takes two residuals.
+// Reduction: a halving butterfly over the lanes (31 shuffles for 32 accumulators), then a fixed-order sum over the
+// warps through shared memory — deterministic, no atomics.
 #include "ops.cuh"
 
 namespace echo {
 namespace {
 
 constexpr int RN = 4;   // output features per CTA
+constexpr int MT = 8;   // rows per CTA
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
 template <class TW>
 __device__ __forceinline__ void ldw4(const TW* p, float (&v)[4]);
@@ -50,9 +57,13 @@ __device__ __forceinline__ int butterfly(float (&v)[N], int lane) {
   return base;
 }
 
-// (code size matters here: the kernel runs ~1 iteration per warp, so it is instruction-fetch bound when over-unrolled;
-//  the SiLU-on-load variant is a separate instantiation and the K loop is not unrolled)
-template <class TW, int MT, bool IN_SILU>
+// element (m, k..k+3) of the (possibly concatenated) input
+__device__ __forceinline__ float4 load_x(const LinArgs& a, int m, int k) {
+  if (a.X2 && k >= a.K1) return *reinterpret_cast<const float4*>(a.X2 + (int64_t)m * a.ldx2 + (k - a.K1));
+  return *reinterpret_cast<const float4*>(a.X + (int64_t)m * a.ldx + k);
+}
+
+template <class TW, int PRO>
 __global__ void __launch_bounds__(256) linear_rows_kernel(const LinArgs a, int k_slice) {
   constexpr int N = MT * RN;
   extern __shared__ float part[];   // [WK][N]
@@ -64,23 +75,86 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(const LinArgs a, int k
   const int k_beg = warp * k_slice;
   const int k_end = min(a.K, k_beg + k_slice);
 
+  // LayerNorm statistics of this CTA's rows over the whole K (two-pass, fp32)
+  float ln_mean[MT], ln_rstd[MT];
+  if (PRO == PRO_LN) {
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      ln_mean[i] = 0.f;
+      ln_rstd[i] = 0.f;
+      if (m0 + i < a.M) {
+        float s = 0.f;
+        for (int k = lane * 4; k < a.K; k += 128) { const float4 x = load_x(a, m0 + i, k); s += (x.x + x.y) + (x.z + x.w); }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s / a.K;
+        float ss = 0.f;
+        for (int k = lane * 4; k < a.K; k += 128) {
+          const float4 x = load_x(a, m0 + i, k);
+          const float d0 = x.x - mean, d1 = x.y - mean, d2 = x.z - mean, d3 = x.w - mean;
+          ss += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        ln_mean[i] = mean;
+        ln_rstd[i] = rsqrtf(ss / a.K + a.eps);
+      }
+    }
+  }
+
   float acc[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) acc[i] = 0.f;
 
 #pragma unroll 1
-  for (int k = k_beg + lane * 4; k < k_end; k += 128) {
+  for (int kb = k_beg; kb < k_end; kb += 128) {
+    const int k = kb + lane * 4;
+    const bool kin = k < k_end;
     float w[RN][4];
 #pragma unroll
     for (int j = 0; j < RN; ++j) {
-      if (n0 + j < a.nout) ldw4<TW>(W + (int64_t)(n0 + j) * ldw + k, w[j]);
+      if (kin && n0 + j < a.nout) ldw4<TW>(W + (int64_t)(n0 + j) * ldw + k, w[j]);
       else w[j][0] = w[j][1] = w[j][2] = w[j][3] = 0.f;
+    }
+    float4 gm = make_float4(1.f, 1.f, 1.f, 1.f), bt = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((PRO == PRO_GN || PRO == PRO_LN) && kin) {
+      gm = __ldg(reinterpret_cast<const float4*>(a.gamma + k));
+      bt = __ldg(reinterpret_cast<const float4*>(a.beta + k));
     }
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
-      if (m0 + i < a.M) {
-        float4 xv = *reinterpret_cast<const float4*>(a.X + (int64_t)(m0 + i) * a.ldx + k);
-        if (IN_SILU) { xv.x = silu_f(xv.x); xv.y = silu_f(xv.y); xv.z = silu_f(xv.z); xv.w = silu_f(xv.w); }
+      const bool rin = m0 + i < a.M;   // warp-uniform
+      float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rin && kin) {
+        xv = load_x(a, m0 + i, k);
+        if (PRO == PRO_GEGLU) {
+          const float4 g = *reinterpret_cast<const float4*>(a.X + (int64_t)(m0 + i) * a.ldx + a.K + k);
+          xv.x *= gelu_erf(g.x); xv.y *= gelu_erf(g.y); xv.z *= gelu_erf(g.z); xv.w *= gelu_erf(g.w);
+        }
+      }
+      if (PRO == PRO_SILU) { xv.x = silu_f(xv.x); xv.y = silu_f(xv.y); xv.z = silu_f(xv.z); xv.w = silu_f(xv.w); }
+      if (PRO == PRO_GN) {
+        if (rin) {   // group = cpg consecutive channels = cpg/4 adjacent lanes (K % 128 == 0: every lane is in range)
+          const int gl = a.cpg >> 2;
+          float s = (xv.x + xv.y) + (xv.z + xv.w);
+          for (int o = 1; o < gl; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          const float mean = s / a.cpg;
+          const float d0 = xv.x - mean, d1 = xv.y - mean, d2 = xv.z - mean, d3 = xv.w - mean;
+          float ss = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+          for (int o = 1; o < gl; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+          const float rstd = rsqrtf(ss / a.cpg + a.eps);
+          xv.x = d0 * rstd * gm.x + bt.x; xv.y = d1 * rstd * gm.y + bt.y;
+          xv.z = d2 * rstd * gm.z + bt.z; xv.w = d3 * rstd * gm.w + bt.w;
+          if (a.pro_act) { xv.x = silu_f(xv.x); xv.y = silu_f(xv.y); xv.z = silu_f(xv.z); xv.w = silu_f(xv.w); }
+        }
+      }
+      if (PRO == PRO_LN) {
+        if (rin && kin) {
+          xv.x = (xv.x - ln_mean[i]) * ln_rstd[i] * gm.x + bt.x; xv.y = (xv.y - ln_mean[i]) * ln_rstd[i] * gm.y + bt.y;
+          xv.z = (xv.z - ln_mean[i]) * ln_rstd[i] * gm.z + bt.z; xv.w = (xv.w - ln_mean[i]) * ln_rstd[i] * gm.w + bt.w;
+        }
+      }
+      if (rin) {
 #pragma unroll
         for (int j = 0; j < RN; ++j) {
           float s = acc[i * RN + j];
@@ -109,15 +183,20 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(const LinArgs a, int k
         if (a.act == 1) v = fmaxf(v, 0.f);
         else if (a.act == 2) v = silu_f(v);
         if (a.res) v += a.res[(int64_t)m * a.ld_res + n];
+        if (a.res2) v += a.res2[(int64_t)m * a.ld_res2 + n];
         a.Y[(int64_t)m * a.ldy + n] = v;
       }
     }
   }
 }
 
+template <class TW, int PRO>
+void launch_pro(const LinArgs& a, dim3 grid, int wk, int k_slice, size_t smem, cudaStream_t s) {
+  linear_rows_kernel<TW, PRO><<<grid, 32 * wk, smem, s>>>(a, k_slice);
+}
+
 template <class TW>
 void launch(const LinArgs& a, cudaStream_t s) {
-  constexpr int MT = 8;
   const int row_tiles = cdiv(a.M, MT);
   const int base_warps = cdiv(a.nout, RN) * row_tiles;
   int wk = 1;
@@ -125,17 +204,31 @@ void launch(const LinArgs& a, cudaStream_t s) {
   const int k_slice = cdiv(cdiv(a.K, wk), 128) * 128;
   dim3 grid(cdiv(a.nout, RN), row_tiles);
   const size_t smem = (size_t)wk * MT * RN * sizeof(float);
-  if (a.in_act == 1) linear_rows_kernel<TW, MT, true><<<grid, 32 * wk, smem, s>>>(a, k_slice);
-  else linear_rows_kernel<TW, MT, false><<<grid, 32 * wk, smem, s>>>(a, k_slice);
+  switch (a.pro) {
+    case PRO_NONE: launch_pro<TW, PRO_NONE>(a, grid, wk, k_slice, smem, s); break;
+    case PRO_SILU: launch_pro<TW, PRO_SILU>(a, grid, wk, k_slice, smem, s); break;
+    case PRO_GN: launch_pro<TW, PRO_GN>(a, grid, wk, k_slice, smem, s); break;
+    case PRO_LN: launch_pro<TW, PRO_LN>(a, grid, wk, k_slice, smem, s); break;
+    case PRO_GEGLU: launch_pro<TW, PRO_GEGLU>(a, grid, wk, k_slice, smem, s); break;
+    default: fail(ECHO_ERR_INVALID, "linear_rows: unknown prologue %d", a.pro);
+  }
 }
 
 }  // namespace
 
-void linear_rows(const LinArgs& a, cudaStream_t s) {
+bool linear_rows_gn_supported(int K, int cpg) { return K % 128 == 0 && (cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32 || cpg == 64 || cpg == 128); }
+
+void linear_rows(const LinArgs& a_in, cudaStream_t s) {
+  LinArgs a = a_in;
+  if (a.in_act == 1 && a.pro == PRO_NONE) a.pro = PRO_SILU;   // legacy spelling
   ECHO_CHECK(a.X && a.W && a.Y, "linear_rows: null operand");
   ECHO_CHECK(a.ldw % 4 == 0, "linear_rows: ldw %% 4");
   ECHO_CHECK(a.K % 4 == 0 && a.ldx % 4 == 0 && ((uintptr_t)a.X % 16) == 0 && ((uintptr_t)a.W % 16) == 0,
              "linear_rows: K=%d ldx=%lld must be multiples of 4 and 16-byte aligned", a.K, (long long)a.ldx);
+  if (a.X2) ECHO_CHECK(a.K1 % 4 == 0 && a.ldx2 % 4 == 0 && ((uintptr_t)a.X2 % 16) == 0 && a.K1 > 0 && a.K1 < a.K && a.pro != PRO_GEGLU,
+                       "linear_rows: bad concat input");
+  if (a.pro == PRO_GN) ECHO_CHECK(a.gamma && a.beta && linear_rows_gn_supported(a.K, a.cpg), "linear_rows: GroupNorm prologue needs K %% 128 == 0 and a power-of-two group of >= 4 channels (K=%d cpg=%d)", a.K, a.cpg);
+  if (a.pro == PRO_LN) ECHO_CHECK(a.gamma && a.beta, "linear_rows: LayerNorm prologue needs gamma/beta");
   if (a.M == 0) return;
   ECHO_CHECK(cdiv(a.M, 8) <= 65535, "linear_rows: too many rows");
   if (a.w_dt == F32) launch<float>(a, s);

@@ -63,10 +63,24 @@ void gemm(const GemmArgs& g, int precision, cudaStream_t s);
 // ---------------------------------------------------------------------------------------------------------------
 // Few-row ("skinny") linear: Y[M, nout] = epi( f(X)[M, K] @ W[nout, K]^T ), M = nodes/edges.  HBM-bound on W.
 // ---------------------------------------------------------------------------------------------------------------
+enum LinPrologue : int { PRO_NONE = 0, PRO_SILU = 1, PRO_GN = 2, PRO_LN = 3, PRO_GEGLU = 4 };
 struct LinArgs {
   const float* X = nullptr;
   int64_t ldx = 0;
   int M = 0, K = 0, nout = 0;
+  // optional channel concat: columns [0, K1) come from X, [K1, K) from X2
+  const float* X2 = nullptr;
+  int64_t ldx2 = 0;
+  int K1 = 0;
+  // prologue applied to X while it is loaded (see linear.cu)
+  int pro = PRO_NONE;
+  int pro_act = 0;             // PRO_GN: SiLU after the affine normalisation
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  float eps = 1e-5f;
+  int cpg = 0;                 // PRO_GN: channels per group
+  const float* res2 = nullptr; // second residual [M, ld_res2]
+  int64_t ld_res2 = 0;
   const void* W = nullptr;     // [nout, K] row-major, row stride ldw (0 = K)
   DT w_dt = F32;
   int64_t ldw = 0;
@@ -79,6 +93,7 @@ struct LinArgs {
   int act = 0;                 // 0 none, 1 relu, 2 silu (before res)
 };
 void linear_rows(const LinArgs& a, cudaStream_t s);
+bool linear_rows_gn_supported(int K, int cpg);
 
 // ---------------------------------------------------------------------------------------------------------------
 // normalisations / elementwise
