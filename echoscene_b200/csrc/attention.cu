@@ -207,6 +207,7 @@ int attention_pad_dh(int dh) { return dh <= 64 ? 64 : (dh <= 96 ? 96 : 0); }
 bool attention_bf16_supported(int tokens, int dh) { return tokens % 64 == 0 && tokens > 0 && attention_pad_dh(dh) != 0 && dh % 2 == 0; }
 
 void attention_bf16(const __nv_bfloat16* qkv, int n, int tokens, int heads, int dh, __nv_bfloat16* out, cudaStream_t s) {
+  if (dbg_skip("flash")) return;
   ECHO_CHECK(attention_bf16_supported(tokens, dh), "attention_bf16: tokens=%d dh=%d unsupported", tokens, dh);
   const int dhp = attention_pad_dh(dh);
   const float scale_log2e = (1.0f / sqrtf((float)dh)) * 1.4426950408889634f;

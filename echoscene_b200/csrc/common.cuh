@@ -87,13 +87,15 @@ struct Act {
   // optional per-column (sum, sumsq) partials written by the producing tcgen05 GEMM: [n * colsum_rows][c][2]
   float* colsum = nullptr;
   int colsum_rows = 0;
-  // a channel concat [A | B] of two such tensors: partials of B and the split point (channels of A)
-  float* colsum2 = nullptr;
-  int c_split = 0;
   int64_t voxels() const { return (int64_t)d * h * w; }
   int64_t rows() const { return (int64_t)n * d * h * w; }
   size_t bytes() const { return (size_t)rows() * c * dt_size(dt); }
 };
+
+// debugging aids (runtime.cu): ECHO_SKIP=name,name drops whole kernel classes from a step (WRONG results; in-situ cost
+// attribution by difference), ECHO_TRACE=1 prints one line per contraction launch to stderr
+bool dbg_skip(const char* name);
+bool dbg_trace();
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

@@ -589,6 +589,7 @@ void gn_stats(const Act& x, int groups, float eps, float* stats, float* partial,
 
 void gn_apply(const Act& x, const float* stats, const float* gamma, const float* beta, int groups, bool silu, const Act& out,
               cudaStream_t s) {
+  if (dbg_skip("gn_apply")) return;
   if (x.dt == BF16 && out.dt == BF16 && x.c % 8 == 0 && x.c / 8 <= 256) {
     const int noct = x.c / 8;
     const int RY = 256 / noct;
@@ -626,6 +627,7 @@ void gn_rows(const float* x, int M, int C, int groups, const float* gamma, const
 
 void layer_norm(const void* x, DT xdt, int64_t rows, int C, const float* gamma, const float* beta, float eps, void* y, DT ydt,
                 cudaStream_t s) {
+  if (dbg_skip("layer_norm")) return;
   ECHO_CHECK(C % 4 == 0, "layer_norm: C %% 4");
   const int grid = cdiv(rows * 32, 256);
   if (xdt == BF16 && ydt == BF16 && C % 8 == 0 && C <= 768) {
@@ -656,6 +658,7 @@ void geglu(const void* x, DT xdt, int64_t rows, int F, void* y, DT ydt, cudaStre
 }
 
 void concat_channels(const Act& a, const Act& b, const Act& out, cudaStream_t s) {
+  if (dbg_skip("concat")) return;
   ECHO_CHECK(a.dt == b.dt && a.dt == out.dt && a.rows() == b.rows() && out.c == a.c + b.c && a.c % 4 == 0 && b.c % 4 == 0,
              "concat: mismatch");
   const int64_t nq = a.rows() * (out.c / 4);
@@ -666,6 +669,7 @@ void concat_channels(const Act& a, const Act& b, const Act& out, cudaStream_t s)
 }
 
 void upsample_hw2(const Act& x, const Act& out, cudaStream_t s) {
+  if (dbg_skip("upsample")) return;
   ECHO_CHECK(out.h == 2 * x.h && out.w == 2 * x.w && out.d == x.d && out.c == x.c && x.dt == out.dt && x.c % 4 == 0, "upsample: mismatch");
   const int64_t nq = out.rows() * (x.c / 4);
   const int grid = grid_for(nq, 256);
@@ -830,81 +834,110 @@ void attention_f32(const float* qkv, int n, int tokens, int heads, int dh, float
 
 // ---- GroupNorm statistics from the producing GEMM's column partials (gemm_tc.cu epilogue) ---------------------------
 namespace {
-// one warp per (object, group): reduce rows_per_obj x cpg (sum, sumsq) pairs in double, fixed order
-__global__ void gn_stats_from_colsum_kernel(const float* __restrict__ colsum, int n, int rows_per_obj, int C, int groups, double count,
-                                            float eps, float* __restrict__ stats) {
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (i >= n * groups) return;
-  const int obj = i / groups, g = i % groups, cpg = C / groups;
-  const float* base = colsum + ((int64_t)obj * rows_per_obj * C + g * cpg) * 2;
-  double a = 0.0, b = 0.0;
-  const int total = rows_per_obj * cpg;
-  for (int k = lane; k < total; k += 32) {
-    const int r = k / cpg, c = k - r * cpg;
-    const float2 p = *reinterpret_cast<const float2*>(base + ((int64_t)r * C + c) * 2);
-    a += (double)p.x;
-    b += (double)p.y;
+// GroupNorm(+SiLU) whose statistics come from the column partials the producing tcgen05 GEMM left behind
+// ([obj][rows_per_obj tiles][C][2] = per-tile (sum, sumsq) per channel): every block first folds the partials of ITS
+// object into per-group (mean, rstd) in shared memory (fp64, fixed order), then streams its rows.  No statistics kernel
+// and no statistics pass over the activation.  The input may be the channel concat [A | B] of two tensors (skip
+// connections, openai_model_3d.py:857-858): both are read in place and the raw concat is written next to the
+// normalised output for the ResBlock's 1x1 skip convolution, so the concat is never a pass of its own.
+__global__ void __launch_bounds__(256) gn_apply_cs_kernel(const __nv_bfloat16* __restrict__ xa, int CA, const float* __restrict__ csa,
+                                                          const __nv_bfloat16* __restrict__ xb, int CB, const float* __restrict__ csb,
+                                                          int R, double count, float eps, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, int64_t V, int groups, int silu, int noct, int RY,
+                                                          int rows_per_block, __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ ycat) {
+  extern __shared__ double gn_sm[];           // [C][2] channel sums, then [groups][2] floats
+  const int C = CA + CB, obj = blockIdx.y, cpg = C / groups;
+  float* gst = reinterpret_cast<float*>(gn_sm + 2 * C);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const bool in_a = c < CA;
+    const float* src = in_a ? csa + ((int64_t)obj * R * CA + c) * 2 : csb + ((int64_t)obj * R * CB + (c - CA)) * 2;
+    const int64_t ld = (in_a ? CA : CB) * 2;
+    double a = 0.0, b = 0.0;
+    for (int r = 0; r < R; ++r) {
+      const float2 v = *reinterpret_cast<const float2*>(src + r * ld);
+      a += (double)v.x;
+      b += (double)v.y;
+    }
+    gn_sm[2 * c] = a;
+    gn_sm[2 * c + 1] = b;
   }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, o);
-    b += __shfl_xor_sync(0xffffffffu, b, o);
-  }
-  if (lane == 0) {
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    double a = 0.0, b = 0.0;
+    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) { a += gn_sm[2 * c]; b += gn_sm[2 * c + 1]; }
     const double mean = a / count;
     double var = b / count - mean * mean;
     if (var < 0.0) var = 0.0;
-    stats[2 * i] = (float)mean;
-    stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    gst[2 * threadIdx.x] = (float)mean;
+    gst[2 * threadIdx.x + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const int q = threadIdx.x % noct, ry = threadIdx.x / noct;
+  if (ry >= RY) return;
+  const int c0 = q * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float* st = gst + ((c0 + j) / cpg) * 2;
+    sc[j] = st[1] * __ldg(gamma + c0 + j);
+    sh[j] = __ldg(beta + c0 + j) - st[0] * sc[j];
+  }
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(r0 + (int64_t)rows_per_block, V);
+  const bool in_a = c0 < CA;
+  const int Cs = in_a ? CA : CB;
+  const __nv_bfloat16* xs = (in_a ? xa + c0 : xb + (c0 - CA)) + ((int64_t)obj * V) * Cs;
+  __nv_bfloat16* yb = y + ((int64_t)obj * V) * C + c0;
+  __nv_bfloat16* cb = ycat ? ycat + ((int64_t)obj * V) * C + c0 : nullptr;
+  for (int64_t r = r0 + ry; r < r1; r += 4 * RY) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (r + k * RY < r1) u[k] = __ldg(reinterpret_cast<const uint4*>(xs + (r + k * RY) * Cs));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (r + k * RY >= r1) break;
+      if (cb) *reinterpret_cast<uint4*>(cb + (r + k * RY) * C) = u[k];
+      uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+        float a = fmaf(__low2float(h2), sc[2 * e], sh[2 * e]);
+        float b = fmaf(__high2float(h2), sc[2 * e + 1], sh[2 * e + 1]);
+        if (silu) {
+          a = __fdividef(a, 1.f + __expf(-a));
+          b = __fdividef(b, 1.f + __expf(-b));
+        }
+        const __nv_bfloat162 o2 = __floats2bfloat162_rn(a, b);
+        w[e] = *reinterpret_cast<const uint32_t*>(&o2);
+      }
+      *reinterpret_cast<uint4*>(yb + (r + k * RY) * C) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
   }
 }
 }  // namespace
 
-namespace {
-// channel concat [A (CA channels) | B (CB channels)] of two tensors that each carry column partials
-__global__ void gn_stats_from_colsum2_kernel(const float* __restrict__ csa, int CA, const float* __restrict__ csb, int CB, int n,
-                                             int rows_per_obj, int groups, double count, float eps, float* __restrict__ stats) {
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (i >= n * groups) return;
-  const int obj = i / groups, g = i % groups, C = CA + CB, cpg = C / groups;
-  double a = 0.0, b = 0.0;
-  const int total = rows_per_obj * cpg;
-  for (int k = lane; k < total; k += 32) {
-    const int r = k / cpg, c = g * cpg + (k - r * cpg);
-    const float* src = c < CA ? csa + (((int64_t)obj * rows_per_obj + r) * CA + c) * 2
-                              : csb + (((int64_t)obj * rows_per_obj + r) * CB + (c - CA)) * 2;
-    const float2 p = *reinterpret_cast<const float2*>(src);
-    a += (double)p.x;
-    b += (double)p.y;
-  }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, o);
-    b += __shfl_xor_sync(0xffffffffu, b, o);
-  }
-  if (lane == 0) {
-    const double mean = a / count;
-    double var = b / count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    stats[2 * i] = (float)mean;
-    stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
-  }
-}
-}  // namespace
-
-void gn_stats_from_colsum2(const float* csa, int CA, const float* csb, int CB, int n_obj, int rows_per_obj, int groups, int64_t voxels,
-                           float eps, float* stats, cudaStream_t s) {
-  const int tot = n_obj * groups;
-  gn_stats_from_colsum2_kernel<<<cdiv((int64_t)tot * 32, 256), 256, 0, s>>>(csa, CA, csb, CB, n_obj, rows_per_obj, groups,
-                                                                            (double)voxels * ((CA + CB) / groups), eps, stats);
-  ECHO_LAUNCH_CHECK();
+bool gn_apply_cs_supported(const Act& xa, const Act* xb, const Act& out) {
+  const int C = xa.c + (xb ? xb->c : 0);
+  if (xa.dt != BF16 || out.dt != BF16 || !xa.colsum || xa.c % 8 || C % 32 || C / 8 > 256 || out.c != C) return false;
+  if (xb && (xb->dt != BF16 || !xb->colsum || xb->c % 8 || xb->colsum_rows != xa.colsum_rows || xb->rows() != xa.rows())) return false;
+  return true;
 }
 
-void gn_stats_from_colsum(const float* colsum, int n_obj, int rows_per_obj, int C, int groups, int64_t voxels, float eps, float* stats,
-                          cudaStream_t s) {
-  const int tot = n_obj * groups;
-  gn_stats_from_colsum_kernel<<<cdiv((int64_t)tot * 32, 256), 256, 0, s>>>(colsum, n_obj, rows_per_obj, C, groups,
-                                                                           (double)voxels * (C / groups), eps, stats);
+void gn_apply_cs(const Act& xa, const Act* xb, const float* gamma, const float* beta, int groups, float eps, bool silu, const Act& out,
+                 const Act* cat, cudaStream_t s) {
+  if (dbg_skip("gn_apply")) return;
+  ECHO_CHECK(gn_apply_cs_supported(xa, xb, out), "gn_apply_cs: unsupported operands");
+  const int C = out.c, noct = C / 8, RY = 256 / noct;
+  const int threads = ((noct * RY + 31) / 32) * 32;
+  const int64_t V = xa.voxels();
+  const int rows_per_block = 16 * RY;   // 4 passes of 4 rows in flight per thread
+  dim3 grid(cdiv(V, rows_per_block), xa.n);
+  const size_t smem = (size_t)C * 2 * sizeof(double) + (size_t)groups * 2 * sizeof(float);
+  gn_apply_cs_kernel<<<grid, threads, smem, s>>>((const __nv_bfloat16*)xa.p, xa.c, xa.colsum, xb ? (const __nv_bfloat16*)xb->p : nullptr,
+                                                 xb ? xb->c : 0, xb ? xb->colsum : nullptr, xa.colsum_rows,
+                                                 (double)V * (C / groups), eps, gamma, beta, V, groups, silu ? 1 : 0, noct, RY, rows_per_block,
+                                                 (__nv_bfloat16*)out.p, cat ? (__nv_bfloat16*)cat->p : nullptr);
   ECHO_LAUNCH_CHECK();
 }
 

@@ -13,9 +13,10 @@
 // 64 x BLOCK_N by a 2-D TMA map.  Stride-(1,2,2) convolutions read a 4-phase space-to-depth copy of the input (one
 // cheap streaming pre-pass), which turns every tap into a unit-stride box of one phase.
 //
-// Warp roles (256 threads, 1 CTA / SM, persistent over tiles): warp 0 = TMA producer (one elected lane), warp 1 = MMA
+// Warp roles (384 threads, 1 CTA / SM, persistent over tiles): warp 0 = TMA producer (one elected lane), warp 1 = MMA
 // issuer (one elected lane issues tcgen05.mma kind::f16, M=128, N=BLOCK_N, K=16), warp 2 = TMEM allocator,
-// warps 4-7 = epilogue (each owns 32 TMEM lanes = 32 output voxels).  Pipelines: STAGES-deep smem ring (full/empty
+// warps 4-11 = epilogue: warp w owns TMEM lanes 32*(w%4).. (32 output voxels) and the 32-column chunks of parity
+// (w-4)/4, so two warps per SM sub-partition drain one accumulator (the epilogue is instruction-issue bound).  Pipelines: STAGES-deep smem ring (full/empty
 // mbarriers, tcgen05.commit releases slots) and a 2-deep TMEM accumulator ring so the epilogue of tile i overlaps
 // the main loop of tile i+1.
 #include "ops.cuh"
@@ -33,10 +34,12 @@ constexpr int MAX_BLOCK_N = 256;
 constexpr int MAX_STAGES = 12;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;       // 16 KiB
 constexpr int SMEM_LIMIT = 227 * 1024;                     // opt-in dynamic shared memory per CTA on sm_100
-constexpr int SMEM_FIXED = 1024 /*align*/ + 512 /*barriers + tmem ptr*/;
+constexpr int NUM_THREADS = 384;
+constexpr int SMEM_CS_BYTES = 2 * 2 * 4 * 32 * 8;          // column-statistics exchange: [col group][parity][warp][32] float2
+constexpr int SMEM_FIXED = 1024 /*align*/ + 512 /*barriers + tmem ptr*/ + SMEM_CS_BYTES;
 // bytes in flight per SM is what hides the L2 latency of the TMA stream: use every stage that fits
-static inline int stages_for(int b_rows) {
-  const int st = (SMEM_LIMIT - SMEM_FIXED) / (A_STAGE_BYTES + b_rows * BLOCK_K * 2);
+static inline int stages_for(int b_rows, int msub) {
+  const int st = (SMEM_LIMIT - SMEM_FIXED) / (msub * A_STAGE_BYTES + b_rows * BLOCK_K * 2);
   return st > MAX_STAGES ? MAX_STAGES : st;
 }
 constexpr int MAX_TAPS = 27;
@@ -62,7 +65,7 @@ struct TcParams {
   int out_bf16;
   long long ldo;
   int relu;
-  float* colsum;   // optional [num_m_tiles*4][cout][2] per-column (sum, sumsq) partials for the next GroupNorm
+  float* colsum;   // optional [num_m_tiles][cout][2] per-column (sum, sumsq) partials for the next GroupNorm
   int geglu;   // epilogue: tile columns are [a (block_n/2) | g (block_n/2)]; out = (a+ba) * gelu_erf(g+bg), out width cout/2
 };
 
@@ -196,6 +199,25 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
                : "memory");
 }
 
+// GELU(g) = 0.5 g (1 + erf(g / sqrt 2)) with erf from Abramowitz & Stegun 7.1.26 (|error| < 1.5e-7 + the ulp-level error
+// of ex2.approx / rcp.approx): 2 MUFU + ~12 ALU instructions per element instead of erff's branchy polynomial; the
+// GEGLU epilogue is instruction-issue bound (attention.py:39-46 uses the exact erf form, F.gelu default).
+__device__ __forceinline__ float gelu_erf_fast(float g) {
+  const float x = fabsf(g) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, x, 1.f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-x * x * 1.44269504088896340736f));
+  const float erf_abs = fmaf(-poly, e, 1.f);          // erf(|g| / sqrt 2)
+  const float erf_s = copysignf(erf_abs, g);
+  return 0.5f * g * (1.f + erf_s);
+}
+
 // Halving butterfly over the 32 lanes: on return v[0] of lane l is the sum over all lanes of element l.
 __device__ __forceinline__ void col_butterfly(float (&v)[32], int lane) {
 #pragma unroll
@@ -219,25 +241,47 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 
-// CTA2 = false: one CTA per 128 x block_n tile (cta_group::1).
-// CTA2 = true : a cluster of two CTAs per 256 x block_n tile (cta_group::2, launched with cluster dims {2,1,1}); the
-//               pair's leader (rank 0) issues the MMAs, both CTAs run their own TMA producer and epilogue.
-template <bool CTA2>
-__global__ void __launch_bounds__(256, 1)
+// Where the output rows of one 128-row sub-block live: box coordinates inside the object grid.
+struct SubTile {
+  int obj, w0, h0, d0;
+};
+__device__ __forceinline__ SubTile sub_tile(const TcParams& p, int m_blk) {
+  SubTile t;
+  int r = m_blk;
+  const int tw = r % p.tiles_w; r /= p.tiles_w;
+  const int th = r % p.tiles_h; r /= p.tiles_h;
+  const int td = r % p.tiles_d;
+  t.obj = r / p.tiles_d;
+  t.w0 = tw * p.bw; t.h0 = th * p.bh; t.d0 = td * p.bd;
+  return t;
+}
+
+// CTA2 = false: one CTA per (MSUB*128) x block_n tile (cta_group::1).
+// CTA2 = true : a cluster of two CTAs per (MSUB*256) x block_n tile (cta_group::2, launched with cluster dims {2,1,1});
+//               the pair's leader (rank 0) issues the MMAs, both CTAs run their own TMA producer and epilogue.
+// MSUB = 2    : every CTA owns TWO 128-row sub-blocks that share each staged B tile (two accumulators of block_n
+//               columns fill TMEM, so the accumulator ring is one deep).  The main loop is bound by the ~56 B/clk an SM
+//               can pull from L2; sharing B between two A tiles cuts the bytes per MMA from (16 KiB + B/2) / 1 to
+//               (32 KiB + B/2) / 2, which is what makes the long-K convolutions MMA-bound.
+template <bool CTA2, int MSUB>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
+  constexpr int A_BYTES = MSUB * A_STAGE_BYTES;            // per stage: MSUB sub-block tiles back to back
+  constexpr int ACC_SLOTS = MSUB == 1 ? 2 : 1;
   const int STAGES = p.stages;
   const int B_ROWS = CTA2 ? (p.block_n >> 1) : p.block_n;   // rows of the B tile staged by THIS CTA
   const int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
-  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = (uint64_t*)(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint8_t* smem_b = smem + STAGES * A_BYTES;
+  uint64_t* bars = (uint64_t*)(smem + STAGES * (A_BYTES + B_STAGE_BYTES));
   uint64_t* full_bar = bars;                   // [STAGES]  (CTA2: the leader's copy is the one in use)
   uint64_t* empty_bar = bars + STAGES;         // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;     // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]       (CTA2: the leader's copy is the one in use)
   uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * STAGES + 4);
+  float2* cs_smem = (float2*)((uint8_t*)bars + 512);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
@@ -246,7 +290,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (CTA2) cluster_sync_all();   // both CTAs resident before the paired TMEM allocation
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], CTA2 ? 2 : 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CTA2 ? 256 : 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CTA2 ? 512 : 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
     if (CTA2) {
@@ -262,13 +306,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  // tile schedule: CTA2 walks (n_blk, m_pair) pairs, this CTA owning m_blk = 2*m_pair + rank
-  const int sched_m = CTA2 ? (p.num_m_tiles >> 1) : p.num_m_tiles;
+  // tile schedule: CTA tiles of MSUB sub-blocks; CTA2 walks (n_blk, m_pair) pairs, this CTA owning m index 2*m_pair + rank
+  const int cta_m_tiles = p.num_m_tiles / MSUB;
+  const int sched_m = CTA2 ? (cta_m_tiles >> 1) : cta_m_tiles;
   const int num_tiles = sched_m * p.num_n_tiles;
   const int tile0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tstride = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int kblocks = p.taps * p.kblocks_per_tap;
-  const uint32_t stage_bytes = (uint32_t)A_STAGE_BYTES + (uint32_t)B_STAGE_BYTES;
+  const uint32_t stage_bytes = (uint32_t)A_BYTES + (uint32_t)B_STAGE_BYTES;
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -277,29 +322,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tstride) {
         const int n_blk = tile / sched_m, mm = tile - n_blk * sched_m;
-        const int m_blk = CTA2 ? 2 * mm + (int)rank : mm;
-        int r = m_blk;
-        const int tw = r % p.tiles_w; r /= p.tiles_w;
-        const int th = r % p.tiles_h; r /= p.tiles_h;
-        const int td = r % p.tiles_d; const int obj = r / p.tiles_d;
-        const int w0 = tw * p.bw, h0 = th * p.bh, d0 = td * p.bd;
+        const int m_cta = CTA2 ? 2 * mm + (int)rank : mm;
+        SubTile st[MSUB];
+#pragma unroll
+        for (int j = 0; j < MSUB; ++j) st[j] = sub_tile(p, m_cta * MSUB + j);
         const int n_row0 = n_blk * p.block_n + (CTA2 ? (int)rank * B_ROWS : 0);
         for (int tap = 0; tap < p.taps; ++tap) {
-          const int cw = w0 + p.tap_w[tap], chh = h0 + p.tap_h[tap], cd = d0 + p.tap_d[tap];
-          const int cn = obj * p.obj_mul + p.tap_p[tap];
           for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (CTA2) {
               // both CTAs' copies complete on the LEADER's full barrier (2 arrivals + the bytes of both CTAs)
               if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
               else mbar_arrive_remote(&full_bar[stage], 0);
-              tma_load_5d_2sm(&map_a, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, cw, chh, cd, cn);
-              tma_load_2d_2sm(&map_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, tap * p.cin + kb * BLOCK_K, n_row0);
             } else {
               mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-              tma_load_5d(&map_a, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, cw, chh, cd, cn);
-              tma_load_2d(&map_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, tap * p.cin + kb * BLOCK_K, n_row0);
             }
+#pragma unroll
+            for (int j = 0; j < MSUB; ++j) {
+              uint8_t* dst = smem_a + stage * A_BYTES + j * A_STAGE_BYTES;
+              const int cw = st[j].w0 + p.tap_w[tap], chh = st[j].h0 + p.tap_h[tap], cd = st[j].d0 + p.tap_d[tap];
+              const int cn = st[j].obj * p.obj_mul + p.tap_p[tap];
+              if (CTA2) tma_load_5d_2sm(&map_a, &full_bar[stage], dst, kb * BLOCK_K, cw, chh, cd, cn);
+              else tma_load_5d(&map_a, &full_bar[stage], dst, kb * BLOCK_K, cw, chh, cd, cn);
+            }
+            if (CTA2) tma_load_2d_2sm(&map_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, tap * p.cin + kb * BLOCK_K, n_row0);
+            else tma_load_2d(&map_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, tap * p.cin + kb * BLOCK_K, n_row0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -314,8 +361,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint32_t phase = 0;
     int iter = 0;
     for (int tile = tile0; tile < num_tiles; tile += tstride, ++iter) {
-      const int as = iter & 1;
-      const uint32_t aphase = (iter >> 1) & 1;
+      const int as = iter % ACC_SLOTS;
+      const uint32_t aphase = (iter / ACC_SLOTS) & 1;
       mbar_wait(&tmem_empty[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * MAX_BLOCK_N;
@@ -325,20 +372,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
             const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
             int nk = (p.cin - kb * BLOCK_K + UMMA_K - 1) / UMMA_K;   // skip the zero-filled channel tail
             nk = nk > BLOCK_K / UMMA_K ? BLOCK_K / UMMA_K : nk;
+            for (int k = 0; k < nk; ++k) {
+              const uint64_t koff = (uint64_t)(k * UMMA_K * 2 / 16);
+              const uint32_t acc = (kb_total | k) != 0 ? 1u : 0u;
+#pragma unroll
+              for (int j = 0; j < MSUB; ++j) {
+                const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * A_BYTES + j * A_STAGE_BYTES));
+                if (CTA2) umma_bf16_2sm(tmem_d + j * MAX_BLOCK_N, da + koff, db + koff, idesc, acc);
+                else umma_bf16(tmem_d + j * MAX_BLOCK_N, da + koff, db + koff, idesc, acc);
+              }
+            }
             if (CTA2) {
-              for (int k = 0; k < nk; ++k)
-                umma_bf16_2sm(tmem_d, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
-                              (kb_total | k) != 0 ? 1u : 0u);
               umma_commit_2sm(&empty_bar[stage]);                          // frees the slot in BOTH CTAs
               if (kb_total == kblocks - 1) umma_commit_2sm(&tmem_full[as]);   // both epilogues
             } else {
-              for (int k = 0; k < nk; ++k)
-                umma_bf16(tmem_d, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
-                          (kb_total | k) != 0 ? 1u : 0u);
               umma_commit(&empty_bar[stage]);                         // frees the smem slot when these MMAs retire
               if (kb_total == kblocks - 1) umma_commit(&tmem_full[as]);   // accumulator complete -> epilogue
             }
@@ -350,31 +400,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ================= epilogue: TMEM -> registers -> global =================
-    const int ew = warp - 4;                       // TMEM lanes [32*ew, 32*ew+32)
+    const int ew = (warp - 4) & 3;                 // TMEM lanes [32*ew, 32*ew+32)
+    const int cg = (warp - 4) >> 2;                // column group: 32-wide chunks with (chunk index & 1) == cg
     const int row = ew * 32 + lane;                // tile row = box voxel index
+    int cs_par = 0;
     const int ww = row % p.bw, hh = (row / p.bw) % p.bh, dd = row / (p.bw * p.bh);
     int iter = 0;
     for (int tile = tile0; tile < num_tiles; tile += tstride, ++iter) {
-      const int as = iter & 1;
-      const uint32_t aphase = (iter >> 1) & 1;
+      const int as = iter % ACC_SLOTS;
+      const uint32_t aphase = (iter / ACC_SLOTS) & 1;
       const int n_blk = tile / sched_m, mm = tile - n_blk * sched_m;
-      const int m_blk = CTA2 ? 2 * mm + (int)rank : mm;
-      int r = m_blk;
-      const int tw = r % p.tiles_w; r /= p.tiles_w;
-      const int th = r % p.tiles_h; r /= p.tiles_h;
-      const int td = r % p.tiles_d; const int obj = r / p.tiles_d;
-      const int ow_ = tw * p.bw + ww, oh_ = th * p.bh + hh, od_ = td * p.bd + dd;
-      const bool valid = ow_ < p.ow && oh_ < p.oh && od_ < p.od;
-      const long long orow = (((long long)obj * p.od + od_) * p.oh + oh_) * p.ow + ow_;
+      const int m_cta = CTA2 ? 2 * mm + (int)rank : mm;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * MAX_BLOCK_N;
+#pragma unroll 1
+      for (int sub = 0; sub < MSUB; ++sub) {
+      const int m_blk = m_cta * MSUB + sub;
+      const SubTile stl = sub_tile(p, m_blk);
+      const int obj = stl.obj;
+      const int ow_ = stl.w0 + ww, oh_ = stl.h0 + hh, od_ = stl.d0 + dd;
+      const bool valid = ow_ < p.ow && oh_ < p.oh && od_ < p.od;
+      const long long orow = (((long long)obj * p.od + od_) * p.oh + oh_) * p.ow + ow_;
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (as + sub) * MAX_BLOCK_N;
       const int n_base = n_blk * p.block_n;
       if (p.geglu) {
         // GEGLU fused into the producing GEMM (attention.py:39-46): the weight rows were permuted at load time so that
         // one tile holds 128 `a` columns followed by their 128 gate columns
         const int half = p.block_n >> 1;
-        for (int c = 0; c < half; c += 32) {
+        for (int c = 32 * cg; c < half; c += 64) {
           uint32_t va[32], vg[32];
           tmem_ld32(taddr + c, va);
           tmem_ld32(taddr + half + c, vg);
@@ -387,7 +440,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int j = 0; j < 32; ++j) {
               const float a = __uint_as_float(va[j]) + __ldg(ba + j);
               const float g = __uint_as_float(vg[j]) + __ldg(bg + j);
-              f[j] = a * (0.5f * g * (1.f + erff(g * 0.70710678118654752440f)));
+              f[j] = a * gelu_erf_fast(g);
             }
             uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + n_blk * half + c);
 #pragma unroll
@@ -403,7 +456,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       } else
-      for (int c = 0; c < p.block_n; c += 32) {
+      for (int c = 32 * cg; c < p.block_n; c += 64) {
         uint32_t v[32];
         tmem_ld32(taddr + c, v);
         tmem_ld_wait();
@@ -475,17 +528,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
         if (p.colsum) {
-          // per-column (sum, sum of squares) over this warp's 32 voxels -> partial row (m_blk*4 + ew): the next
-          // GroupNorm's statistics come from these instead of a separate pass over the activation
+          // per-column (sum, sum of squares) over the sub-block's 128 voxels -> partial row m_blk: the next GroupNorm's
+          // statistics come from these instead of a separate pass over the activation.  Lanes hold the sums over
+          // their warp's 32 voxels after the butterflies; the four warps of this column group meet in shared memory
+          // (fixed summation order -> run-to-run reproducible).
           float q2[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) q2[j] = f[j] * f[j];
           col_butterfly(f, lane);
           col_butterfly(q2, lane);
-          if (n0 + lane < p.cout)
-            *reinterpret_cast<float2*>(p.colsum + (((long long)m_blk * 4 + ew) * p.cout + n0 + lane) * 2) = make_float2(f[0], q2[0]);
+          float2* buf = cs_smem + ((cg * 2 + cs_par) * 4) * 32;
+          buf[ew * 32 + lane] = make_float2(f[0], q2[0]);
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + cg) : "memory");
+          if (ew == 0 && n0 + lane < p.cout) {
+            const float2 a0 = buf[lane], a1 = buf[32 + lane], a2 = buf[64 + lane], a3 = buf[96 + lane];
+            *reinterpret_cast<float2*>(p.colsum + ((long long)m_blk * p.cout + n0 + lane) * 2) =
+                make_float2((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y));
+          }
+          cs_par ^= 1;
         }
       }
+      }   // sub
       tc_fence_before();
       if (CTA2 && !leader) mbar_arrive_remote(&tmem_empty[as], 0);   // the leader's MMA warp owns the accumulator ring
       else mbar_arrive(&tmem_empty[as]);
@@ -546,8 +609,10 @@ void tc_init() {
   }
   g_tc.encode = (EncodeTiledFn)fn;
   g_tc.sms = prop.multiProcessorCount;
-  if (cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
-      cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
+  if (cudaFuncSetAttribute(gemm_tc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_tc_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_tc_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
     cudaGetLastError();
     return;
   }
@@ -560,10 +625,22 @@ int pow2_floor(int v) {
   return p;
 }
 
-int pick_block_n(int cout) {
-  for (int bn = 256; bn >= 32; bn -= 32)
-    if (cout % bn == 0) return bn;
-  return 0;
+// Tile width: multiples of 32 up to 256.  One wave of the persistent grid runs one tile per SM, so the cost of a choice
+// is waves x (block_n + a fixed per-tile overhead: epilogue tail, A re-read); a partial last n-tile is fine (TMA zero
+// fills weight rows >= cout, the epilogue masks whole 32-column chunks).  E.g. cout 672 on 32 m-tiles: 224 -> 96 tiles
+// on 148 SMs, 192 -> 128 tiles in the same single wave.
+int pick_block_n(int cout, int m_tiles, int sms) {
+  if (cout % 32 != 0) return 0;
+  int best = 0;
+  long long best_cost = 0;
+  for (int bn = 256; bn >= 64; bn -= 32) {
+    const int n_tiles = (cout + bn - 1) / bn;
+    const long long waves = ((long long)m_tiles * n_tiles + sms - 1) / sms;
+    const long long cost = waves * (bn + 16);
+    if (!best || cost < best_cost) { best = bn; best_cost = cost; }
+  }
+  if (cout < 64) best = cout;
+  return best;
 }
 
 }  // namespace
@@ -579,14 +656,14 @@ int gemm_tc_colsum_rows_per_obj(const GemmArgs& g) {
   const int bw = pow2_floor(g.ow) > 128 ? 128 : pow2_floor(g.ow);
   const int bh = pow2_floor(g.oh) > 128 / bw ? 128 / bw : pow2_floor(g.oh);
   const int bd = 128 / (bw * bh);
-  return cdiv(g.ow, bw) * cdiv(g.oh, bh) * cdiv(g.od, bd) * 4;
+  return cdiv(g.ow, bw) * cdiv(g.oh, bh) * cdiv(g.od, bd);
 }
 
 bool gemm_tc_supported(const GemmArgs& g) {
   if (g.a_dt != BF16 || g.w_dt != BF16) return false;
   if (g.nb0 * g.nb1 != 1 || g.alpha != 1.f || g.act > 1) return false;
   if (g.cin % 16 != 0 || g.lda != g.cin || g.w_stride_k != 1 || g.w_stride_n != (int64_t)g.ktot()) return false;
-  if (g.cout % 32 != 0 || pick_block_n(g.cout) == 0) return false;
+  if (g.cout % 32 != 0) return false;
   if (g.epi == 1 && g.colsum) return false;
   if (g.epi == 1 && (g.cout % 256 != 0 || g.res || g.rowvec || !g.bias || g.out_dt != BF16 || g.act != 0)) return false;
   if (!((g.kd == 1 && g.kh == 1 && g.kw == 1) || (g.kd == 3 && g.kh == 3 && g.kw == 3))) return false;
@@ -611,6 +688,10 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   ECHO_CHECK(tc_available(), "gemm_tc: tcgen05 path unavailable on this device");
   ECHO_CHECK(gemm_tc_supported(g), "gemm_tc: unsupported problem");
   if (g.rows_out() == 0) return;
+  if (dbg_skip("gemm_tc")) return;
+  if (dbg_trace())
+    fprintf(stderr, "[echo-trace] gemm_tc rows=%lld grid=%dx%dx%d cin=%d cout=%d k=%d stride=%d epi=%d colsum=%d res=%d\n", (long long)g.rows_out(),
+            g.od, g.oh, g.ow, g.cin, g.cout, g.kd, g.sh, g.epi, g.colsum ? 1 : 0, g.res ? 1 : 0);
   const bool s2 = g.sh == 2;
   const __nv_bfloat16* a_ptr = (const __nv_bfloat16*)g.A;
   int in_h = g.h, in_w = g.w, in_objs = g.n;
@@ -633,8 +714,8 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   p.bd = 128 / (p.bw * p.bh);
   p.tiles_w = cdiv(g.ow, p.bw); p.tiles_h = cdiv(g.oh, p.bh); p.tiles_d = cdiv(g.od, p.bd);
   p.num_m_tiles = g.n * p.tiles_d * p.tiles_h * p.tiles_w;
-  p.block_n = pick_block_n(g.cout);
-  p.num_n_tiles = g.cout / p.block_n;
+  p.block_n = pick_block_n(g.cout, p.num_m_tiles, g_tc.sms);
+  p.num_n_tiles = cdiv(g.cout, p.block_n);
   p.cin = g.cin; p.cout = g.cout; p.taps = g.kd * g.kh * g.kw;
   p.kblocks_per_tap = cdiv(g.cin, BLOCK_K);
   p.obj_mul = s2 ? 4 : 1;
@@ -685,16 +766,28 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ECHO_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
   }
-  const int tiles = p.num_m_tiles * p.num_n_tiles;   // 128-row CTA tiles in both modes
+  // two sub-blocks per CTA (MSUB = 2) when the main loop is long enough to pay for the one-deep accumulator ring and
+  // the coarser tiles do not cost more waves than they save bytes (an MSUB=2 tile runs ~1.6x as long as a plain one)
+  static const int msub_env = getenv("ECHO_TC_MSUB") ? atoi(getenv("ECHO_TC_MSUB")) : 0;
+  int msub = 1;
+  if (!p.geglu && p.num_m_tiles % (cta2 ? 4 : 2) == 0 && p.taps * p.kblocks_per_tap >= 32) {
+    const long long w1 = ((long long)p.num_m_tiles * p.num_n_tiles + g_tc.sms - 1) / g_tc.sms;
+    const long long w2 = ((long long)(p.num_m_tiles / 2) * p.num_n_tiles + g_tc.sms - 1) / g_tc.sms;
+    if (w2 * 16 < w1 * 10) msub = 2;
+  }
+  if (msub_env == 1) msub = 1;
+  if (msub_env == 2 && p.num_m_tiles % (cta2 ? 4 : 2) == 0 && !p.geglu) msub = 2;
+  const int tiles = p.num_m_tiles / msub * p.num_n_tiles;   // CTA tiles
   const int b_rows = cta2 ? p.block_n / 2 : p.block_n;
-  p.stages = stages_for(b_rows);
-  const int smem_bytes = p.stages * (A_STAGE_BYTES + b_rows * BLOCK_K * 2) + SMEM_FIXED;
+  p.stages = stages_for(b_rows, msub);
+  ECHO_CHECK(p.stages >= 2, "gemm_tc: tile does not fit shared memory");
+  const int smem_bytes = p.stages * (msub * A_STAGE_BYTES + b_rows * BLOCK_K * 2) + SMEM_FIXED;
   if (cta2) {
     int grid = tiles < (g_tc.sms & ~1) ? tiles : (g_tc.sms & ~1);   // whole CTA pairs, one CTA per SM
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(256);
+    cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -704,10 +797,12 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    ECHO_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, map_a, map_b, p));
+    if (msub == 2) ECHO_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, 2>, map_a, map_b, p));
+    else ECHO_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, 1>, map_a, map_b, p));
   } else {
     const int grid = tiles < g_tc.sms ? tiles : g_tc.sms;
-    gemm_tc_kernel<false><<<grid, 256, smem_bytes, s>>>(map_a, map_b, p);
+    if (msub == 2) gemm_tc_kernel<false, 2><<<grid, NUM_THREADS, smem_bytes, s>>>(map_a, map_b, p);
+    else gemm_tc_kernel<false, 1><<<grid, NUM_THREADS, smem_bytes, s>>>(map_a, map_b, p);
   }
   ECHO_LAUNCH_CHECK();
 }

@@ -219,6 +219,7 @@ void launch(const LinArgs& a, cudaStream_t s) {
 bool linear_rows_gn_supported(int K, int cpg) { return K % 128 == 0 && (cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32 || cpg == 64 || cpg == 128); }
 
 void linear_rows(const LinArgs& a_in, cudaStream_t s) {
+  if (dbg_skip("linear_rows")) return;
   LinArgs a = a_in;
   if (a.in_act == 1 && a.pro == PRO_NONE) a.pro = PRO_SILU;   // legacy spelling
   ECHO_CHECK(a.X && a.W && a.Y, "linear_rows: null operand");

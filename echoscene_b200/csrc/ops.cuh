@@ -49,13 +49,13 @@ void gemm_simt(const GemmArgs& g, cudaStream_t s);
 bool gemm_tc_supported(const GemmArgs& g);
 void gemm_tc(const GemmArgs& g, cudaStream_t s);
 bool tc_available();
-// rows of the column-sum partial buffer per OBJECT for this problem (the tcgen05 kernel writes 4 per 128-voxel tile)
+// rows of the column-sum partial buffer per OBJECT for this problem (the tcgen05 kernel writes one per 128-voxel tile)
 int gemm_tc_colsum_rows_per_obj(const GemmArgs& g);
-// GroupNorm statistics from column partials: stats[(obj, group)] = (mean, rstd)
-void gn_stats_from_colsum2(const float* csa, int CA, const float* csb, int CB, int n_obj, int rows_per_obj, int groups, int64_t voxels,
-                           float eps, float* stats, cudaStream_t s);
-void gn_stats_from_colsum(const float* colsum, int n_obj, int rows_per_obj, int C, int groups, int64_t voxels, float eps, float* stats,
-                          cudaStream_t s);
+// GroupNorm(+SiLU) with the statistics folded from the producer's column partials inside the apply kernel; `xb` != null:
+// the input is the channel concat [xa | xb] (read in place), `cat` != null additionally receives the raw concat.
+bool gn_apply_cs_supported(const Act& xa, const Act* xb, const Act& out);
+void gn_apply_cs(const Act& xa, const Act* xb, const float* gamma, const float* beta, int groups, float eps, bool silu, const Act& out,
+                 const Act* cat, cudaStream_t s);
 // precision: ECHO_PREC_*; BF16 falls back to the SIMT kernel (bf16 operands, fp32 accumulate) for shapes the
 // tensor-core kernel does not take (tiny channel counts).
 void gemm(const GemmArgs& g, int precision, cudaStream_t s);

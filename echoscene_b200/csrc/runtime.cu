@@ -2,6 +2,7 @@
 #include "model.cuh"
 
 #include <string.h>
+#include <stdlib.h>
 
 namespace echo {
 
@@ -21,6 +22,19 @@ void fail(int code, const char* fmt, ...) {
   vsnprintf(buf, sizeof(buf), fmt, ap);
   va_end(ap);
   throw Error(code, buf);
+}
+
+bool dbg_skip(const char* name) {
+  static const char* env = getenv("ECHO_SKIP");
+  if (!env) return false;
+  const size_t n = strlen(name);
+  for (const char* p = env; (p = strstr(p, name)) != nullptr; p += n)
+    if ((p == env || p[-1] == ',') && (p[n] == 0 || p[n] == ',')) return true;
+  return false;
+}
+bool dbg_trace() {
+  static const bool on = getenv("ECHO_TRACE") != nullptr;
+  return on;
 }
 
 void WeightMap::load(const echo_weight_t* w, int n) {

@@ -98,24 +98,32 @@ struct echo_shape {
     gemm_simt(g, s);
   }
   Act gn(const Act& x, const NormW& nw, float eps, bool silu, DT odt, cudaStream_t s) {
-    float* stats = arena.alloc_n<float>((size_t)x.n * 32 * 2);
-    float* partial = x.colsum ? nullptr : arena.alloc_n<float>(gn_partial_floats(x, 32));
     Act o = new_act(x.n, x.d, x.h, x.w, x.c, odt);
+    if (x.colsum && gn_apply_cs_supported(x, nullptr, o)) {   // statistics from the producer's column partials: one kernel
+      if (!dry) gn_apply_cs(x, nullptr, nw.g, nw.b, 32, eps, silu, o, nullptr, s);
+      return o;
+    }
+    float* stats = arena.alloc_n<float>((size_t)x.n * 32 * 2);
+    float* partial = arena.alloc_n<float>(gn_partial_floats(x, 32));
     if (!dry) {
-      if (x.colsum && x.colsum2)
-        gn_stats_from_colsum2(x.colsum, x.c_split, x.colsum2, x.c - x.c_split, x.n, x.colsum_rows, 32, x.voxels(), eps, stats, s);
-      else if (x.colsum) gn_stats_from_colsum(x.colsum, x.n, x.colsum_rows, x.c, 32, x.voxels(), eps, stats, s);   // no pass over x
-      else gn_stats(x, 32, eps, stats, partial, s);
+      gn_stats(x, 32, eps, stats, partial, s);
       gn_apply(x, stats, nw.g, nw.b, 32, silu, o, s);
     }
     return o;
   }
 
-  // ResBlock._forward (openai_model_3d.py:294-314)
-  Act res_block(const Act& x, const ResW& r, int n_local, cudaStream_t s) {
+  // ResBlock._forward (openai_model_3d.py:294-314).  `ca`/`cb` != null: x is the (not yet written) channel concat
+  // [ca | cb] of a skip connection; the first GroupNorm reads both halves in place and writes x on the side.
+  Act res_block(const Act& x, const ResW& r, int n_local, cudaStream_t s, const Act* ca = nullptr, const Act* cb = nullptr) {
     Act out = new_act_cs(x.n, x.d, x.h, x.w, r.cout, adt);
     const size_t m = arena.mark();
-    Act a1 = gn(x, r.n1, 1e-5f, true, adt, s);
+    Act a1;
+    if (ca) {
+      a1 = new_act(x.n, x.d, x.h, x.w, x.c, adt);
+      if (!dry) gn_apply_cs(*ca, cb, r.n1.g, r.n1.b, 32, 1e-5f, true, a1, &x, s);
+    } else {
+      a1 = gn(x, r.n1, 1e-5f, true, adt, s);
+    }
     Act h1 = new_act_cs(x.n, x.d, x.h, x.w, r.cout, adt);
     contract(a1, r.c1, 3, 1, embout + r.emb_off, plan.emb_total, nullptr, h1, s);
     Act a2 = gn(h1, r.n2, 1e-5f, true, adt, s);
@@ -303,11 +311,12 @@ struct echo_shape {
       Act sk = hs.back();
       hs.pop_back();
       Act cat = new_act(h.n, h.d, h.h, h.w, h.c + sk.c, adt);
-      if (!dry) concat_channels(h, sk, cat, s);
-      if (h.colsum && sk.colsum && h.colsum_rows == sk.colsum_rows) {   // GroupNorm statistics of the concat from both producers
-        cat.colsum = h.colsum; cat.colsum_rows = h.colsum_rows; cat.colsum2 = sk.colsum; cat.c_split = h.c;
+      if (h.colsum && gn_apply_cs_supported(h, &sk, cat)) {   // concat fused into the ResBlock's first GroupNorm
+        h = res_block(cat, b.res, n_local, s, &h, &sk);
+      } else {
+        if (!dry) concat_channels(h, sk, cat, s);
+        h = res_block(cat, b.res, n_local, s);
       }
-      h = res_block(cat, b.res, n_local, s);
       if (b.attn) h = transformer(h, b.at, ai++, s);
       if (b.up) {   // nearest x(1,2,2) then Conv3d k3 (openai_model_3d.py:150-157)
         Act up = new_act(h.n, h.d, h.h * 2, h.w * 2, h.c, adt);
