@@ -42,7 +42,7 @@ static inline int stages_for(int b_rows, int msub) {
   const int st = (SMEM_LIMIT - SMEM_FIXED) / (msub * A_STAGE_BYTES + b_rows * BLOCK_K * 2);
   return st > MAX_STAGES ? MAX_STAGES : st;
 }
-constexpr int MAX_TAPS = 27;
+constexpr int MAX_TAPS = 48;   // 27 taps of a 3x3x3 kernel, or 4 phases x 12 folded taps of a conv after a nearest x(1,2,2) upsample
 
 struct TcParams {
   // problem
@@ -50,6 +50,8 @@ struct TcParams {
   int bd, bh, bw;               // tile box (bd*bh*bw == 128)
   int tiles_d, tiles_h, tiles_w;
   int num_m_tiles, num_n_tiles, block_n;
+  int up;                       // conv after nearest x(1,2,2) upsample, evaluated per output phase on the LOW-resolution input
+  int vm_tiles;                 // schedulable 128-row sub-blocks: num_m_tiles, or 4 x num_m_tiles (phase-major) when up
   int cin, cout, taps, kblocks_per_tap;
   int obj_mul;                  // 4 for the space-to-depth input (obj index = obj*4 + phase), else 1
   int stages;                   // depth of the smem ring
@@ -243,11 +245,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 
 // Where the output rows of one 128-row sub-block live: box coordinates inside the object grid.
 struct SubTile {
-  int obj, w0, h0, d0;
+  int obj, w0, h0, d0, phase, m_blk;
 };
-__device__ __forceinline__ SubTile sub_tile(const TcParams& p, int m_blk) {
+__device__ __forceinline__ SubTile sub_tile(const TcParams& p, int vm) {
   SubTile t;
-  int r = m_blk;
+  t.phase = 0;
+  t.m_blk = vm;
+  if (p.up) { t.phase = vm / p.num_m_tiles; t.m_blk = vm - t.phase * p.num_m_tiles; }
+  int r = t.m_blk;
   const int tw = r % p.tiles_w; r /= p.tiles_w;
   const int th = r % p.tiles_h; r /= p.tiles_h;
   const int td = r % p.tiles_d;
@@ -307,7 +312,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr;
 
   // tile schedule: CTA tiles of MSUB sub-blocks; CTA2 walks (n_blk, m_pair) pairs, this CTA owning m index 2*m_pair + rank
-  const int cta_m_tiles = p.num_m_tiles / MSUB;
+  const int cta_m_tiles = p.vm_tiles / MSUB;
   const int sched_m = CTA2 ? (cta_m_tiles >> 1) : cta_m_tiles;
   const int num_tiles = sched_m * p.num_n_tiles;
   const int tile0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -327,7 +332,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < MSUB; ++j) st[j] = sub_tile(p, m_cta * MSUB + j);
         const int n_row0 = n_blk * p.block_n + (CTA2 ? (int)rank * B_ROWS : 0);
-        for (int tap = 0; tap < p.taps; ++tap) {
+        const int tap_end = (st[0].phase + 1) * p.taps;   // all sub-blocks of a tile share the phase (host checks)
+        for (int tap = st[0].phase * p.taps; tap < tap_end; ++tap) {
           for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (CTA2) {
@@ -415,12 +421,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_after();
 #pragma unroll 1
       for (int sub = 0; sub < MSUB; ++sub) {
-      const int m_blk = m_cta * MSUB + sub;
-      const SubTile stl = sub_tile(p, m_blk);
+      const SubTile stl = sub_tile(p, m_cta * MSUB + sub);
       const int obj = stl.obj;
       const int ow_ = stl.w0 + ww, oh_ = stl.h0 + hh, od_ = stl.d0 + dd;
       const bool valid = ow_ < p.ow && oh_ < p.oh && od_ < p.od;
-      const long long orow = (((long long)obj * p.od + od_) * p.oh + oh_) * p.ow + ow_;
+      const long long orow = p.up ? (((long long)obj * p.od + od_) * (2 * p.oh) + 2 * oh_ + (stl.phase >> 1)) * (2 * p.ow) + 2 * ow_ + (stl.phase & 1)
+                                  : (((long long)obj * p.od + od_) * p.oh + oh_) * p.ow + ow_;
+      const long long cs_row = p.up ? (long long)stl.m_blk * 4 + stl.phase : stl.m_blk;
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (as + sub) * MAX_BLOCK_N;
       const int n_base = n_blk * p.block_n;
       if (p.geglu) {
@@ -542,7 +549,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           asm volatile("bar.sync %0, 128;" ::"r"(1 + cg) : "memory");
           if (ew == 0 && n0 + lane < p.cout) {
             const float2 a0 = buf[lane], a1 = buf[32 + lane], a2 = buf[64 + lane], a3 = buf[96 + lane];
-            *reinterpret_cast<float2*>(p.colsum + ((long long)m_blk * p.cout + n0 + lane) * 2) =
+            *reinterpret_cast<float2*>(p.colsum + (cs_row * p.cout + n0 + lane) * 2) =
                 make_float2((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y));
           }
           cs_par ^= 1;
@@ -653,15 +660,20 @@ bool tc_available() {
 }
 
 int gemm_tc_colsum_rows_per_obj(const GemmArgs& g) {
-  const int bw = pow2_floor(g.ow) > 128 ? 128 : pow2_floor(g.ow);
-  const int bh = pow2_floor(g.oh) > 128 / bw ? 128 / bw : pow2_floor(g.oh);
+  const int gw = g.up2 ? g.ow / 2 : g.ow, gh = g.up2 ? g.oh / 2 : g.oh;   // the grid the 128-voxel boxes tile
+  const int bw = pow2_floor(gw) > 128 ? 128 : pow2_floor(gw);
+  const int bh = pow2_floor(gh) > 128 / bw ? 128 / bw : pow2_floor(gh);
   const int bd = 128 / (bw * bh);
-  return cdiv(g.ow, bw) * cdiv(g.oh, bh) * cdiv(g.od, bd);
+  return cdiv(gw, bw) * cdiv(gh, bh) * cdiv(g.od, bd) * (g.up2 ? 4 : 1);
 }
 
 bool gemm_tc_supported(const GemmArgs& g) {
   if (g.a_dt != BF16 || g.w_dt != BF16) return false;
   if (g.nb0 * g.nb1 != 1 || g.alpha != 1.f || g.act > 1) return false;
+  if (g.up2) {   // W = [cout][4 phases][12 folded taps][cin] (fold_upsample_weight)
+    if (g.kd != 3 || g.kh != 3 || g.kw != 3 || g.sd != 1 || g.sh != 1 || g.sw != 1 || g.od != g.d || g.oh != 2 * g.h || g.ow != 2 * g.w) return false;
+    if (g.cin % 16 != 0 || g.lda != g.cin || g.w_stride_k != 1 || g.w_stride_n != (int64_t)48 * g.cin || g.epi || g.res) return false;
+  } else
   if (g.cin % 16 != 0 || g.lda != g.cin || g.w_stride_k != 1 || g.w_stride_n != (int64_t)g.ktot()) return false;
   if (g.cout % 32 != 0) return false;
   if (g.epi == 1 && g.colsum) return false;
@@ -672,7 +684,7 @@ bool gemm_tc_supported(const GemmArgs& g) {
     if (g.kd != 3 || (g.h & 1) || (g.w & 1) || !g.scratch) return false;
     if (g.oh != g.h / 2 || g.ow != g.w / 2) return false;
   } else if (g.sh == 1) {
-    if (g.od != g.d || g.oh != g.h || g.ow != g.w) return false;
+    if (!g.up2 && (g.od != g.d || g.oh != g.h || g.ow != g.w)) return false;
   } else {
     return false;
   }
@@ -690,8 +702,8 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   if (g.rows_out() == 0) return;
   if (dbg_skip("gemm_tc")) return;
   if (dbg_trace())
-    fprintf(stderr, "[echo-trace] gemm_tc rows=%lld grid=%dx%dx%d cin=%d cout=%d k=%d stride=%d epi=%d colsum=%d res=%d\n", (long long)g.rows_out(),
-            g.od, g.oh, g.ow, g.cin, g.cout, g.kd, g.sh, g.epi, g.colsum ? 1 : 0, g.res ? 1 : 0);
+    fprintf(stderr, "[echo-trace] gemm_tc rows=%lld grid=%dx%dx%d cin=%d cout=%d k=%d stride=%d epi=%d colsum=%d res=%d up=%d\n", (long long)g.rows_out(),
+            g.od, g.oh, g.ow, g.cin, g.cout, g.kd, g.sh, g.epi, g.colsum ? 1 : 0, g.res ? 1 : 0, g.up2);
   const bool s2 = g.sh == 2;
   const __nv_bfloat16* a_ptr = (const __nv_bfloat16*)g.A;
   int in_h = g.h, in_w = g.w, in_objs = g.n;
@@ -708,17 +720,31 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   }
   TcParams p;
   memset(&p, 0, sizeof(p));
-  p.n_obj = g.n; p.od = g.od; p.oh = g.oh; p.ow = g.ow;
-  p.bw = pow2_floor(g.ow) > 128 ? 128 : pow2_floor(g.ow);
-  p.bh = pow2_floor(g.oh) > 128 / p.bw ? 128 / p.bw : pow2_floor(g.oh);
+  const bool up = g.up2 != 0;
+  p.up = up ? 1 : 0;
+  p.n_obj = g.n; p.od = g.od; p.oh = up ? g.h : g.oh; p.ow = up ? g.w : g.ow;   // the grid the 128-voxel boxes tile
+  p.bw = pow2_floor(p.ow) > 128 ? 128 : pow2_floor(p.ow);
+  p.bh = pow2_floor(p.oh) > 128 / p.bw ? 128 / p.bw : pow2_floor(p.oh);
   p.bd = 128 / (p.bw * p.bh);
-  p.tiles_w = cdiv(g.ow, p.bw); p.tiles_h = cdiv(g.oh, p.bh); p.tiles_d = cdiv(g.od, p.bd);
+  p.tiles_w = cdiv(p.ow, p.bw); p.tiles_h = cdiv(p.oh, p.bh); p.tiles_d = cdiv(p.od, p.bd);
   p.num_m_tiles = g.n * p.tiles_d * p.tiles_h * p.tiles_w;
-  p.block_n = pick_block_n(g.cout, p.num_m_tiles, g_tc.sms);
+  p.vm_tiles = p.num_m_tiles * (up ? 4 : 1);
+  p.block_n = pick_block_n(g.cout, p.vm_tiles, g_tc.sms);
   p.num_n_tiles = cdiv(g.cout, p.block_n);
-  p.cin = g.cin; p.cout = g.cout; p.taps = g.kd * g.kh * g.kw;
+  p.cin = g.cin; p.cout = g.cout; p.taps = up ? 12 : g.kd * g.kh * g.kw;
   p.kblocks_per_tap = cdiv(g.cin, BLOCK_K);
   p.obj_mul = s2 ? 4 : 1;
+  if (up) {
+    // output voxel (d, 2y+py, 2x+px) reads low-res rows {y+py-1, y+py}: tap (kd, a, b) of phase (py, px)
+    for (int ph = 0; ph < 4; ++ph)
+      for (int t = 0; t < 12; ++t) {
+        const int kd = t >> 2, a = (t >> 1) & 1, b = t & 1;
+        p.tap_d[ph * 12 + t] = (int8_t)(kd - 1);
+        p.tap_h[ph * 12 + t] = (int8_t)((ph >> 1) - 1 + a);
+        p.tap_w[ph * 12 + t] = (int8_t)((ph & 1) - 1 + b);
+        p.tap_p[ph * 12 + t] = 0;
+      }
+  } else
   for (int t = 0; t < p.taps; ++t) {
     const int kd = t / (g.kh * g.kw), kh = (t / g.kw) % g.kh, kw = t % g.kw;
     p.tap_d[t] = (int8_t)(kd - g.pd);
@@ -742,7 +768,7 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   // CTA pairs (cta_group::2) whenever the 128-row tiles pair up: halves the B bytes each SM has to pull from L2
   static const int mode_env = getenv("ECHO_TC_MODE") ? atoi(getenv("ECHO_TC_MODE")) : 0;   // 1 / 2 force a mode (tests, profiling)
   const int mode = g_tc_mode ? g_tc_mode : mode_env;
-  const bool cta2 = mode != 1 && (p.num_m_tiles % 2 == 0) && (p.block_n % 16 == 0);
+  const bool cta2 = mode != 1 && (p.num_m_tiles % 2 == 0) && (p.block_n % 16 == 0);   // (a pair never straddles two phases)
 
   CUtensorMap map_a, map_b;
   {
@@ -757,8 +783,9 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
     ECHO_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed: %d", (int)r);
   }
   {
-    const cuuint64_t dims[2] = {(cuuint64_t)g.ktot(), (cuuint64_t)g.cout};
-    const cuuint64_t strides[1] = {(cuuint64_t)g.ktot() * 2};
+    const cuuint64_t ktot = up ? (cuuint64_t)48 * g.cin : (cuuint64_t)g.ktot();
+    const cuuint64_t dims[2] = {ktot, (cuuint64_t)g.cout};
+    const cuuint64_t strides[1] = {ktot * 2};
     const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(cta2 ? p.block_n / 2 : p.block_n)};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = g_tc.encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)g.W, dims, strides, box, estr,
@@ -771,13 +798,13 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   static const int msub_env = getenv("ECHO_TC_MSUB") ? atoi(getenv("ECHO_TC_MSUB")) : 0;
   int msub = 1;
   if (!p.geglu && p.num_m_tiles % (cta2 ? 4 : 2) == 0 && p.taps * p.kblocks_per_tap >= 32) {
-    const long long w1 = ((long long)p.num_m_tiles * p.num_n_tiles + g_tc.sms - 1) / g_tc.sms;
-    const long long w2 = ((long long)(p.num_m_tiles / 2) * p.num_n_tiles + g_tc.sms - 1) / g_tc.sms;
+    const long long w1 = ((long long)p.vm_tiles * p.num_n_tiles + g_tc.sms - 1) / g_tc.sms;
+    const long long w2 = ((long long)(p.vm_tiles / 2) * p.num_n_tiles + g_tc.sms - 1) / g_tc.sms;
     if (w2 * 16 < w1 * 10) msub = 2;
   }
   if (msub_env == 1) msub = 1;
   if (msub_env == 2 && p.num_m_tiles % (cta2 ? 4 : 2) == 0 && !p.geglu) msub = 2;
-  const int tiles = p.num_m_tiles / msub * p.num_n_tiles;   // CTA tiles
+  const int tiles = p.vm_tiles / msub * p.num_n_tiles;   // CTA tiles
   const int b_rows = cta2 ? p.block_n / 2 : p.block_n;
   p.stages = stages_for(b_rows, msub);
   ECHO_CHECK(p.stages >= 2, "gemm_tc: tile does not fit shared memory");

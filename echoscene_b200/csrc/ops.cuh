@@ -34,6 +34,8 @@ struct GemmArgs {
   int64_t ldo = 0;
   int act = 0;                      // 0 none, 1 relu
   int epi = 0;                      // tcgen05 path only: 1 = GEGLU epilogue (W rows tiled [128 a | 128 g]; out width cout/2)
+  int up2 = 0;                      // tcgen05 path only: the conv follows a nearest x(1,2,2) upsample of A (openai_model_3d.py:150-157);
+                                    // A is the LOW-resolution tensor (d,h,w), the output grid is (d,2h,2w), W = fold_upsample_weight()
   float alpha = 1.f;                // scales the accumulator before the epilogue adds
   // batching: problem b = b0*nb1 + b1
   int nb0 = 1, nb1 = 1;
@@ -152,6 +154,10 @@ void attention_bf16(const __nv_bfloat16* qkv, int n, int tokens, int heads, int 
 void pad_qkv(const float* x, int64_t rows, int heads, int dh, int dhp, __nv_bfloat16* y, cudaStream_t s);
 
 // weight preparation
+// 3x3x3 conv after nearest x(1,2,2) upsample == 4 output-phase convs with 3x2x2 taps on the low-res input (the two
+// high-res rows that map to one low-res row share it, so their weights add): w [cout][27][cin] fp32 (tap-major) ->
+// out [cout][4 phases (py,px)][12 taps (kd,a,b)][cin] fp32, host-side (runs once at handle creation)
+void fold_upsample_weight(const float* w_host, int cout, int cin, float* out_host);
 // conv weight (cout, cin, taps) -> (cout, taps, cin); taps = kd*kh*kw
 void repack_conv_weight(const float* w, int cout, int cin, int taps, float* out, cudaStream_t s);
 // centre tap of a Conv1d(k=3) weight (cout, cin, 3) -> (cout, cin)

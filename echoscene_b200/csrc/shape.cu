@@ -54,11 +54,11 @@ struct echo_shape {
   }
   Act new_act(int n, int dd, int h, int w, int c, DT dt) { return new_act_in(arena, n, dd, h, w, c, dt); }
   // activation whose producer (a tcgen05 GEMM) also emits the column partials the consuming GroupNorm needs
-  Act new_act_cs(int n, int dd, int h, int w, int c, DT dt) {
+  Act new_act_cs(int n, int dd, int h, int w, int c, DT dt, bool up2 = false) {
     Act a = new_act(n, dd, h, w, c, dt);
     if (prec == ECHO_PREC_BF16 && dt == BF16 && c % 32 == 0 && (dry || tc_available())) {
       GemmArgs g;
-      g.od = dd; g.oh = h; g.ow = w;
+      g.od = dd; g.oh = h; g.ow = w; g.up2 = up2 ? 1 : 0;
       a.colsum_rows = gemm_tc_colsum_rows_per_obj(g);
       a.colsum = arena.alloc_n<float>((size_t)n * a.colsum_rows * c * 2);
     }
@@ -319,11 +319,27 @@ struct echo_shape {
       }
       if (b.attn) h = transformer(h, b.at, ai++, s);
       if (b.up) {   // nearest x(1,2,2) then Conv3d k3 (openai_model_3d.py:150-157)
-        Act up = new_act(h.n, h.d, h.h * 2, h.w * 2, h.c, adt);
-        if (!dry) upsample_hw2(h, up, s);
-        Act o = new_act_cs(up.n, up.d, up.h, up.w, b.conv.cout, adt);
-        contract(up, b.conv, 3, 1, nullptr, 0, nullptr, o, s);
-        h = o;
+        if (prec == ECHO_PREC_BF16 && adt == BF16 && b.up_fold.wb) {
+          // upsample folded into the conv: four output phases, 12 taps each, on the low-resolution tensor
+          Act o = new_act_cs(h.n, h.d, h.h * 2, h.w * 2, b.conv.cout, adt, true);
+          if (!dry) {
+            GemmArgs g;
+            g.A = h.p; g.a_dt = BF16; g.n = h.n; g.d = h.d; g.h = h.h; g.w = h.w; g.cin = h.c; g.lda = h.c;
+            g.od = o.d; g.oh = o.h; g.ow = o.w; g.up2 = 1;
+            g.kd = g.kh = g.kw = 3; g.pd = g.ph = g.pw = 1;
+            g.W = b.up_fold.wb; g.w_dt = BF16; g.w_stride_n = (int64_t)48 * h.c; g.cout = b.conv.cout; g.bias = b.up_fold.b;
+            g.out = o.p; g.out_dt = BF16; g.ldo = o.c; g.colsum = o.colsum;
+            ECHO_CHECK(gemm_tc_supported(g), "upsample conv: folded contraction not supported");
+            gemm_tc(g, s);
+          }
+          h = o;
+        } else {
+          Act up = new_act(h.n, h.d, h.h * 2, h.w * 2, h.c, adt);
+          if (!dry) upsample_hw2(h, up, s);
+          Act o = new_act_cs(up.n, up.d, up.h, up.w, b.conv.cout, adt);
+          contract(up, b.conv, 3, 1, nullptr, 0, nullptr, o, s);
+          h = o;
+        }
       }
     }
     Act hn = gn(h, plan.out_norm, 1e-5f, true, adt, s);

@@ -42,6 +42,7 @@ struct BlockW {
   AttnW at;
   bool up = false;
   ConvW conv;   // CONV_IN / DOWN op / Upsample conv
+  ConvW up_fold;  // bf16 mode, Upsample conv: weights folded per output phase (fold_upsample_weight), taps = 48
   int ds = 1;
 };
 

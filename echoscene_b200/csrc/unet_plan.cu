@@ -242,6 +242,19 @@ void build_unet_plan(const WeightMap& wm, const UNetCfg& cfg, DevPool& pool, UNe
       if (level && i == cfg.num_res_blocks) {
         b.up = true;
         b.conv = P.conv(p + std::to_string(k) + ".conv", ch, ch, 3);
+        if (cfg.want_bf16 && cfg.dims == 3) {   // fold the nearest upsample into the conv: 12 taps per output phase
+          const size_t n_src = (size_t)ch * 27 * ch, n_dst = (size_t)ch * 48 * ch;
+          std::vector<float> hsrc(n_src), hdst(n_dst);
+          ECHO_CUDA(cudaStreamSynchronize(s));
+          ECHO_CUDA(cudaMemcpy(hsrc.data(), b.conv.w, n_src * sizeof(float), cudaMemcpyDeviceToHost));
+          fold_upsample_weight(hsrc.data(), ch, ch, hdst.data());
+          float* o = pool.alloc_n<float>(n_dst);
+          ECHO_CUDA(cudaMemcpy(o, hdst.data(), n_dst * sizeof(float), cudaMemcpyHostToDevice));
+          b.up_fold = b.conv;
+          b.up_fold.taps = 48;
+          b.up_fold.w = o;
+          b.up_fold.wb = P.to_bf16(o, n_dst);
+        }
         ds /= 2;
       }
       plan.out_blocks.push_back(b);

@@ -180,6 +180,11 @@ ECHO_API int echo_shape_schedule(const echo_shape_t* h, float* host_coef_out, in
 ECHO_API int echo_op_conv3d(const float* x, int32_t n, int32_t d, int32_t h, int32_t w, int32_t cin,
                    const float* weight, const float* bias, int32_t cout, int32_t ksize,
                    int32_t stride_d, int32_t stride_hw, float* out, int32_t precision, void* stream);
+/* Upsample (nearest x(1,2,2), openai_model_3d.py:150-155) followed by Conv3d k3 p1 (:156-157), evaluated as four
+ * output-phase convolutions with folded 3x2x2 taps on the low-resolution input: x (n,d,h,w,cin) -> out (n,d,2h,2w,cout).
+ * ECHO_PREC_BF16 only. */
+ECHO_API int echo_op_upconv3d(const float* x, int32_t n, int32_t d, int32_t h, int32_t w, int32_t cin,
+                     const float* weight, const float* bias, int32_t cout, float* out, int32_t precision, void* stream);
 ECHO_API int echo_op_linear(const float* x, int64_t rows, int32_t cin, const float* weight, const float* bias, int32_t cout,
                    float* out, int32_t precision, void* stream);
 ECHO_API int echo_op_group_norm(const float* x, int32_t n, int64_t voxels, int32_t c, int32_t groups, const float* gamma,

@@ -150,7 +150,26 @@ def test_conv3d_tcgen05(cin, cout, dhw, k, stride):
     assert_close(got, want, 1e-2, f"tcgen05 conv {cin}->{cout} k{k} s{stride}")   # output rounded to bf16 (2^-9)
 
 
-@pytest.mark.parametrize("n,tokens,heads,dh", [(2, 1024, 8, 56), (2, 256, 8, 84)])
+@pytest.mark.parametrize("n,c,cout,dhw", [(16, 448, 448, (16, 8, 8)), (4, 672, 672, (16, 4, 4)), (3, 64, 96, (4, 4, 8))])
+def test_upsample_conv_folded(n, c, cout, dhw):
+    """Upsample(nearest x(1,2,2)) + Conv3d k3 (openai_model_3d.py:150-157) as four phase convolutions on the low-res input."""
+    _need_tc()
+    g = torch.Generator().manual_seed(c + cout)
+    x = torch.randn(n, c, *dhw, generator=g).bfloat16().float()
+    w = (torch.randn(cout, c, 3, 3, 3, generator=g) / (c * 27) ** 0.5)
+    b = torch.randn(cout, generator=g)
+    up = F.interpolate(x, (dhw[0], dhw[1] * 2, dhw[2] * 2), mode="nearest")
+    want = F.conv3d(up, w, b, padding=1)
+    xc = _cl(x).cuda()
+    out = torch.empty(n, dhw[0], 2 * dhw[1], 2 * dhw[2], cout, device="cuda")
+    wd, bd = w.cuda().contiguous(), b.cuda()
+    _lib.check(_lib.lib().echo_op_upconv3d(xc.data_ptr(), n, *dhw, c, wd.data_ptr(), bd.data_ptr(), cout, out.data_ptr(),
+                                           _lib.PREC_BF16, _lib.stream_ptr()))
+    # folded weights are rounded to bf16 after the fp32 fold (2^-9 each) and the output is rounded to bf16
+    assert_close(out.permute(0, 4, 1, 2, 3).cpu(), want, 1.5e-2, "folded upsample conv")
+
+
+@pytest.mark.parametrize("n,tokens,heads,dh", [(2, 1024, 8, 56), (2, 256, 8, 84), (16, 1024, 8, 56), (40, 256, 8, 84)])
 def test_attention_bf16(n, tokens, heads, dh):
     _need_tc()
     g = torch.Generator().manual_seed(tokens + dh)
