@@ -284,6 +284,8 @@ int echo_op_conv3d(const float* x, int32_t n, int32_t d, int32_t h, int32_t w, i
       g.A = xb; g.a_dt = BF16; g.W = wb; g.w_dt = BF16; g.out = ob; g.out_dt = BF16;
       static Scratch s2d;
       if (stride_hw == 2) g.scratch = s2d.get((size_t)rows_in * cin * 2);
+      static Scratch skws;
+      if (const size_t wsb = gemm_tc_splitk_ws_bytes(g)) g.splitk_ws = skws.get(wsb);
       ECHO_CHECK(gemm_tc_supported(g), "op_conv3d: shape not supported by the tcgen05 kernel");
       gemm_tc(g, s);
       convert(ob, BF16, out, F32, rows_out * cout, s);

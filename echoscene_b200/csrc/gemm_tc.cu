@@ -52,6 +52,9 @@ struct TcParams {
   int num_m_tiles, num_n_tiles, block_n;
   int up;                       // conv after nearest x(1,2,2) upsample, evaluated per output phase on the LOW-resolution input
   int vm_tiles;                 // schedulable 128-row sub-blocks: num_m_tiles, or 4 x num_m_tiles (phase-major) when up
+  int splitk;                   // > 1: the taps are cut into `splitk` equal groups, one CTA tile per group; raw fp32 partial
+                                // sums go to out + ks * rows * ldo (splitk_reduce_kernel finishes the epilogue)
+  long long total_rows;
   int cin, cout, taps, kblocks_per_tap;
   int obj_mul;                  // 4 for the space-to-depth input (obj index = obj*4 + phase), else 1
   int stages;                   // depth of the smem ring
@@ -314,10 +317,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // tile schedule: CTA tiles of MSUB sub-blocks; CTA2 walks (n_blk, m_pair) pairs, this CTA owning m index 2*m_pair + rank
   const int cta_m_tiles = p.vm_tiles / MSUB;
   const int sched_m = CTA2 ? (cta_m_tiles >> 1) : cta_m_tiles;
-  const int num_tiles = sched_m * p.num_n_tiles;
+  const int mn_tiles = sched_m * p.num_n_tiles;
+  const int num_tiles = mn_tiles * p.splitk;               // tile = ks * mn_tiles + n_blk * sched_m + mm
+  const int taps_per_split = p.taps / p.splitk;
   const int tile0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tstride = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int kblocks = p.taps * p.kblocks_per_tap;
+  const int kblocks = taps_per_split * p.kblocks_per_tap;
   const uint32_t stage_bytes = (uint32_t)A_BYTES + (uint32_t)B_STAGE_BYTES;
 
   if (warp == 0) {
@@ -326,14 +331,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tstride) {
-        const int n_blk = tile / sched_m, mm = tile - n_blk * sched_m;
+        const int ks = tile / mn_tiles, tmn = tile - ks * mn_tiles;
+        const int n_blk = tmn / sched_m, mm = tmn - n_blk * sched_m;
         const int m_cta = CTA2 ? 2 * mm + (int)rank : mm;
         SubTile st[MSUB];
 #pragma unroll
         for (int j = 0; j < MSUB; ++j) st[j] = sub_tile(p, m_cta * MSUB + j);
         const int n_row0 = n_blk * p.block_n + (CTA2 ? (int)rank * B_ROWS : 0);
-        const int tap_end = (st[0].phase + 1) * p.taps;   // all sub-blocks of a tile share the phase (host checks)
-        for (int tap = st[0].phase * p.taps; tap < tap_end; ++tap) {
+        // all sub-blocks of a tile share the phase (host checks); split-K walks its own group of taps
+        const int tap_begin = st[0].phase * p.taps + ks * taps_per_split, tap_end = tap_begin + taps_per_split;
+        for (int tap = tap_begin; tap < tap_end; ++tap) {
           for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (CTA2) {
@@ -373,7 +380,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * MAX_BLOCK_N;
       int kb_total = 0;
-      for (int tap = 0; tap < p.taps; ++tap) {
+      for (int tap = 0; tap < taps_per_split; ++tap) {
         for (int kb = 0; kb < p.kblocks_per_tap; ++kb, ++kb_total) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -415,7 +422,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int tile = tile0; tile < num_tiles; tile += tstride, ++iter) {
       const int as = iter % ACC_SLOTS;
       const uint32_t aphase = (iter / ACC_SLOTS) & 1;
-      const int n_blk = tile / sched_m, mm = tile - n_blk * sched_m;
+      const int ks = tile / mn_tiles, tmn = tile - ks * mn_tiles;
+      const int n_blk = tmn / sched_m, mm = tmn - n_blk * sched_m;
       const int m_cta = CTA2 ? 2 * mm + (int)rank : mm;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
@@ -425,8 +433,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int obj = stl.obj;
       const int ow_ = stl.w0 + ww, oh_ = stl.h0 + hh, od_ = stl.d0 + dd;
       const bool valid = ow_ < p.ow && oh_ < p.oh && od_ < p.od;
-      const long long orow = p.up ? (((long long)obj * p.od + od_) * (2 * p.oh) + 2 * oh_ + (stl.phase >> 1)) * (2 * p.ow) + 2 * ow_ + (stl.phase & 1)
-                                  : (((long long)obj * p.od + od_) * p.oh + oh_) * p.ow + ow_;
+      const long long orow = (p.up ? (((long long)obj * p.od + od_) * (2 * p.oh) + 2 * oh_ + (stl.phase >> 1)) * (2 * p.ow) + 2 * ow_ + (stl.phase & 1)
+                                   : (((long long)obj * p.od + od_) * p.oh + oh_) * p.ow + ow_) + ks * p.total_rows;
       const long long cs_row = p.up ? (long long)stl.m_blk * 4 + stl.phase : stl.m_blk;
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (as + sub) * MAX_BLOCK_N;
       const int n_base = n_blk * p.block_n;
@@ -632,22 +640,156 @@ int pow2_floor(int v) {
   return p;
 }
 
-// Tile width: multiples of 32 up to 256.  One wave of the persistent grid runs one tile per SM, so the cost of a choice
-// is waves x (block_n + a fixed per-tile overhead: epilogue tail, A re-read); a partial last n-tile is fine (TMA zero
-// fills weight rows >= cout, the epilogue masks whole 32-column chunks).  E.g. cout 672 on 32 m-tiles: 224 -> 96 tiles
-// on 148 SMs, 192 -> 128 tiles in the same single wave.
-int pick_block_n(int cout, int m_tiles, int sms) {
-  if (cout % 32 != 0) return 0;
-  int best = 0;
-  long long best_cost = 0;
-  for (int bn = 256; bn >= 64; bn -= 32) {
-    const int n_tiles = (cout + bn - 1) / bn;
-    const long long waves = ((long long)m_tiles * n_tiles + sms - 1) / sms;
-    const long long cost = waves * (bn + 16);
-    if (!best || cost < best_cost) { best = bn; best_cost = cost; }
+// ---- launch plan ------------------------------------------------------------------------------------------------
+// block_n : tile width, multiples of 32 up to 256 (a partial last n-tile is fine: TMA zero-fills weight rows >= cout, the
+//           epilogue masks whole 32-column chunks)
+// msub    : 128-row sub-blocks per CTA (2 = share every staged B tile between two A tiles, one-deep accumulator ring)
+// splitk  : tap groups of a 3x3x3 conv run as separate CTA tiles writing fp32 partials (finished by
+//           splitk_reduce_kernel) -- for the coarse levels whose few output tiles would leave most SMs idle
+// chosen by a small cycle model: a persistent grid runs `waves` rounds of one tile per SM; a k-block stage costs
+// max(MMA time, bytes / ~52 B/clk an SM pulls from L2 through TMA); the epilogue overlaps the next tile only when the
+// accumulator ring is two deep (msub == 1).
+struct TcPlan {
+  int block_n = 0, msub = 1, splitk = 1;
+  bool cta2 = false;
+};
+
+struct TcGeom {
+  int bw, bh, bd, tiles_w, tiles_h, tiles_d, num_m_tiles, vm_tiles, taps, kblocks_per_tap;
+};
+
+TcGeom tc_geom(const GemmArgs& g) {
+  TcGeom t;
+  const bool up = g.up2 != 0;
+  const int gw = up ? g.w : g.ow, gh = up ? g.h : g.oh;
+  t.bw = pow2_floor(gw) > 128 ? 128 : pow2_floor(gw);
+  t.bh = pow2_floor(gh) > 128 / t.bw ? 128 / t.bw : pow2_floor(gh);
+  t.bd = 128 / (t.bw * t.bh);
+  t.tiles_w = cdiv(gw, t.bw); t.tiles_h = cdiv(gh, t.bh); t.tiles_d = cdiv(g.od, t.bd);
+  t.num_m_tiles = g.n * t.tiles_d * t.tiles_h * t.tiles_w;
+  t.vm_tiles = t.num_m_tiles * (up ? 4 : 1);
+  t.taps = up ? 12 : g.kd * g.kh * g.kw;
+  t.kblocks_per_tap = cdiv(g.cin, BLOCK_K);
+  return t;
+}
+
+TcPlan tc_plan(const GemmArgs& g, const TcGeom& t, int sms) {
+  static const int mode_env = getenv("ECHO_TC_MODE") ? atoi(getenv("ECHO_TC_MODE")) : 0;   // 1 / 2 force a mode (tests, profiling)
+  static const int msub_env = getenv("ECHO_TC_MSUB") ? atoi(getenv("ECHO_TC_MSUB")) : 0;
+  static const int split_env = getenv("ECHO_TC_SPLITK") ? atoi(getenv("ECHO_TC_SPLITK")) : 0;   // 1 = never split
+  const int mode = g_tc_mode ? g_tc_mode : mode_env;
+  TcPlan best;
+  double best_cost = 0;
+  const bool geglu = g.epi == 1;
+  const bool can_split = g.splitk_ws && !geglu && !g.up2 && t.taps == 27 && g.sh == 1 && ((int64_t)g.od * g.oh * g.ow) % 128 == 0 &&
+                         g.out_dt == BF16 && split_env != 1;
+  for (int bn = 256; bn >= 32; bn -= 32) {
+    if (geglu && bn != 256) continue;
+    if (bn > g.cout && bn != 32 && bn - 32 >= g.cout) continue;   // never wider than needed
+    const int n_tiles = cdiv(g.cout, bn);
+    const bool cta2 = mode != 1 && t.num_m_tiles % 2 == 0 && bn % 32 == 0;
+    for (int msub = 1; msub <= 2; ++msub) {
+      if (msub == 2 && (geglu || t.num_m_tiles % (cta2 ? 4 : 2) != 0)) continue;
+      if (msub_env && msub != msub_env && !(msub_env == 2 && (geglu || t.num_m_tiles % (cta2 ? 4 : 2) != 0))) continue;
+      const int b_rows = cta2 ? bn / 2 : bn;
+      if (stages_for(b_rows, msub) < 3) continue;
+      for (int sk = 1; sk <= (can_split ? 3 : 1); sk += 2) {
+        const long long tiles = (long long)(t.vm_tiles / msub) * n_tiles * sk;
+        const long long waves = (tiles + sms - 1) / sms;
+        const double mma = msub * 4.0 * (bn / 2.0);
+        const double feed = (msub * 16384.0 + b_rows * 128.0) / 52.0;
+        const double stage = mma > feed ? mma : feed;
+        const double mainloop = (double)t.taps * t.kblocks_per_tap / sk * stage;
+        const double epi = msub * (1500.0 + 12.0 * bn);
+        double cost = msub == 2 ? waves * (mainloop + epi) : waves * mainloop + epi;
+        cost += 2500.0;                                         // launch + prologue
+        if (sk > 1) cost += 6000.0 + 2500.0;                    // the reduce pass: a second (small) kernel
+        if (!best.block_n || cost < best_cost) {
+          best.block_n = bn; best.msub = msub; best.splitk = sk; best.cta2 = cta2;
+          best_cost = cost;
+        }
+      }
+    }
   }
-  if (cout < 64) best = cout;
   return best;
+}
+
+// Second half of a split-K contraction: out = sum_ks partial[ks] + bias + rowvec[obj] + res, rounded to bf16, plus the
+// per-(128-row group, column) GroupNorm partials the single-pass epilogue would have written.  One block = 128 rows x
+// 64 columns; thread = (row lane 0..31, column octet 0..7); rows are consecutive, so a group never straddles two objects
+// (voxels % 128 == 0 is required by the plan).
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int splitk, long long rows, int cout,
+                                                            const float* __restrict__ bias, const float* __restrict__ rowvec,
+                                                            long long ld_rowvec, long long rows_per_obj,
+                                                            const __nv_bfloat16* __restrict__ res, long long ld_res, int relu,
+                                                            __nv_bfloat16* __restrict__ out, long long ldo, float* __restrict__ colsum) {
+  __shared__ float2 red[32][64];
+  const int c8 = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int col = blockIdx.y * 64 + c8 * 8;
+  const long long row0 = (long long)blockIdx.x * 128;
+  const bool col_ok = col < cout;
+  float sum[8], sq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
+  float add[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) add[j] = 0.f;
+  if (col_ok && bias) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col)), b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+    add[0] = b0.x; add[1] = b0.y; add[2] = b0.z; add[3] = b0.w; add[4] = b1.x; add[5] = b1.y; add[6] = b1.z; add[7] = b1.w;
+  }
+  if (col_ok && rowvec) {
+    const float* rv = rowvec + (row0 / rows_per_obj) * ld_rowvec + col;
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(rv)), b1 = __ldg(reinterpret_cast<const float4*>(rv + 4));
+    add[0] += b0.x; add[1] += b0.y; add[2] += b0.z; add[3] += b0.w; add[4] += b1.x; add[5] += b1.y; add[6] += b1.z; add[7] += b1.w;
+  }
+  if (col_ok) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long r = row0 + rl + 32 * i;
+      if (r >= rows) break;
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = add[j];
+      for (int ks = 0; ks < splitk; ++ks) {
+        const float* wp = ws + ((long long)ks * rows + r) * cout + col;
+        const float4 a0 = *reinterpret_cast<const float4*>(wp), a1 = *reinterpret_cast<const float4*>(wp + 4);
+        f[0] += a0.x; f[1] += a0.y; f[2] += a0.z; f[3] += a0.w; f[4] += a1.x; f[5] += a1.y; f[6] += a1.z; f[7] += a1.w;
+      }
+      if (res) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(res + r * ld_res + col));
+        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[e]);
+          f[2 * e] += __low2float(h2);
+          f[2 * e + 1] += __high2float(h2);
+        }
+      }
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      uint32_t w4[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+        w4[e] = *reinterpret_cast<uint32_t*>(&h2);
+      }
+      *reinterpret_cast<uint4*>(out + r * ldo + col) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sum[j] += f[j]; sq[j] = fmaf(f[j], f[j], sq[j]); }
+    }
+  }
+  if (!colsum) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[rl][c8 * 8 + j] = make_float2(sum[j], sq[j]);
+  __syncthreads();
+  if (threadIdx.x < 64 && blockIdx.y * 64 + threadIdx.x < cout) {
+    float a = 0.f, b = 0.f;
+    for (int r = 0; r < 32; ++r) { a += red[r][threadIdx.x].x; b += red[r][threadIdx.x].y; }
+    *reinterpret_cast<float2*>(colsum + ((long long)blockIdx.x * cout + blockIdx.y * 64 + threadIdx.x) * 2) = make_float2(a, b);
+  }
 }
 
 }  // namespace
@@ -660,11 +802,19 @@ bool tc_available() {
 }
 
 int gemm_tc_colsum_rows_per_obj(const GemmArgs& g) {
-  const int gw = g.up2 ? g.ow / 2 : g.ow, gh = g.up2 ? g.oh / 2 : g.oh;   // the grid the 128-voxel boxes tile
-  const int bw = pow2_floor(gw) > 128 ? 128 : pow2_floor(gw);
-  const int bh = pow2_floor(gh) > 128 / bw ? 128 / bw : pow2_floor(gh);
-  const int bd = 128 / (bw * bh);
-  return cdiv(gw, bw) * cdiv(gh, bh) * cdiv(g.od, bd) * (g.up2 ? 4 : 1);
+  GemmArgs t = g;
+  t.n = 1;
+  if (t.up2) { t.h = t.oh / 2; t.w = t.ow / 2; }
+  const TcGeom ge = tc_geom(t);
+  return ge.vm_tiles;
+}
+
+size_t gemm_tc_splitk_ws_bytes(const GemmArgs& g) {
+  if (!tc_available() || g.kd != 3 || g.sh != 1 || g.up2 || g.epi) return 0;
+  // only problems that cannot fill two waves of 128 x 224 tiles are worth a second pass over fp32 partials; when a
+  // workspace is offered the plan decides: size it for the deepest split
+  if ((long long)cdiv(g.rows_out(), 128) * cdiv(g.cout, 224) >= 2LL * g_tc.sms) return 0;
+  return (size_t)3 * g.rows_out() * g.cout * sizeof(float);
 }
 
 bool gemm_tc_supported(const GemmArgs& g) {
@@ -676,6 +826,7 @@ bool gemm_tc_supported(const GemmArgs& g) {
   } else
   if (g.cin % 16 != 0 || g.lda != g.cin || g.w_stride_k != 1 || g.w_stride_n != (int64_t)g.ktot()) return false;
   if (g.cout % 32 != 0) return false;
+  if (g.splitk_ws && ((uintptr_t)g.splitk_ws % 16)) return false;
   if (g.epi == 1 && g.colsum) return false;
   if (g.epi == 1 && (g.cout % 256 != 0 || g.res || g.rowvec || !g.bias || g.out_dt != BF16 || g.act != 0)) return false;
   if (!((g.kd == 1 && g.kh == 1 && g.kw == 1) || (g.kd == 3 && g.kh == 3 && g.kw == 3))) return false;
@@ -701,9 +852,6 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   ECHO_CHECK(gemm_tc_supported(g), "gemm_tc: unsupported problem");
   if (g.rows_out() == 0) return;
   if (dbg_skip("gemm_tc")) return;
-  if (dbg_trace())
-    fprintf(stderr, "[echo-trace] gemm_tc rows=%lld grid=%dx%dx%d cin=%d cout=%d k=%d stride=%d epi=%d colsum=%d res=%d up=%d\n", (long long)g.rows_out(),
-            g.od, g.oh, g.ow, g.cin, g.cout, g.kd, g.sh, g.epi, g.colsum ? 1 : 0, g.res ? 1 : 0, g.up2);
   const bool s2 = g.sh == 2;
   const __nv_bfloat16* a_ptr = (const __nv_bfloat16*)g.A;
   int in_h = g.h, in_w = g.w, in_objs = g.n;
@@ -721,18 +869,24 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   TcParams p;
   memset(&p, 0, sizeof(p));
   const bool up = g.up2 != 0;
+  const TcGeom ge = tc_geom(g);
+  const TcPlan plan = tc_plan(g, ge, g_tc.sms);
+  ECHO_CHECK(plan.block_n > 0, "gemm_tc: no launch plan");
+  if (dbg_trace())
+    fprintf(stderr, "[echo-trace] gemm_tc rows=%lld cin=%d cout=%d k=%d stride=%d epi=%d up=%d bn=%d msub=%d splitk=%d cta2=%d\n",
+            (long long)g.rows_out(), g.cin, g.cout, g.kd, g.sh, g.epi, g.up2, plan.block_n, plan.msub, plan.splitk, plan.cta2 ? 1 : 0);
   p.up = up ? 1 : 0;
   p.n_obj = g.n; p.od = g.od; p.oh = up ? g.h : g.oh; p.ow = up ? g.w : g.ow;   // the grid the 128-voxel boxes tile
-  p.bw = pow2_floor(p.ow) > 128 ? 128 : pow2_floor(p.ow);
-  p.bh = pow2_floor(p.oh) > 128 / p.bw ? 128 / p.bw : pow2_floor(p.oh);
-  p.bd = 128 / (p.bw * p.bh);
-  p.tiles_w = cdiv(p.ow, p.bw); p.tiles_h = cdiv(p.oh, p.bh); p.tiles_d = cdiv(p.od, p.bd);
-  p.num_m_tiles = g.n * p.tiles_d * p.tiles_h * p.tiles_w;
-  p.vm_tiles = p.num_m_tiles * (up ? 4 : 1);
-  p.block_n = pick_block_n(g.cout, p.vm_tiles, g_tc.sms);
+  p.bw = ge.bw; p.bh = ge.bh; p.bd = ge.bd;
+  p.tiles_w = ge.tiles_w; p.tiles_h = ge.tiles_h; p.tiles_d = ge.tiles_d;
+  p.num_m_tiles = ge.num_m_tiles;
+  p.vm_tiles = ge.vm_tiles;
+  p.block_n = plan.block_n;
   p.num_n_tiles = cdiv(g.cout, p.block_n);
-  p.cin = g.cin; p.cout = g.cout; p.taps = up ? 12 : g.kd * g.kh * g.kw;
-  p.kblocks_per_tap = cdiv(g.cin, BLOCK_K);
+  p.cin = g.cin; p.cout = g.cout; p.taps = ge.taps;
+  p.kblocks_per_tap = ge.kblocks_per_tap;
+  p.splitk = plan.splitk;
+  p.total_rows = g.rows_out();
   p.obj_mul = s2 ? 4 : 1;
   if (up) {
     // output voxel (d, 2y+py, 2x+px) reads low-res rows {y+py-1, y+py}: tap (kd, a, b) of phase (py, px)
@@ -764,11 +918,12 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   p.out = g.out; p.out_bf16 = g.out_dt == BF16; p.ldo = g.ldo; p.relu = g.act == 1;
   p.colsum = g.colsum;
   p.geglu = g.epi == 1;
-  if (p.geglu) { p.block_n = 256; p.num_n_tiles = g.cout / 256; }
+  if (plan.splitk > 1) {   // raw fp32 partials into the workspace; splitk_reduce_kernel applies the epilogue terms
+    p.bias = nullptr; p.rowvec = nullptr; p.res = nullptr; p.colsum = nullptr; p.relu = 0;
+    p.out = g.splitk_ws; p.out_bf16 = 0; p.ldo = g.cout;
+  }
   // CTA pairs (cta_group::2) whenever the 128-row tiles pair up: halves the B bytes each SM has to pull from L2
-  static const int mode_env = getenv("ECHO_TC_MODE") ? atoi(getenv("ECHO_TC_MODE")) : 0;   // 1 / 2 force a mode (tests, profiling)
-  const int mode = g_tc_mode ? g_tc_mode : mode_env;
-  const bool cta2 = mode != 1 && (p.num_m_tiles % 2 == 0) && (p.block_n % 16 == 0);   // (a pair never straddles two phases)
+  const bool cta2 = plan.cta2;   // (a pair never straddles two phases: num_m_tiles is even)
 
   CUtensorMap map_a, map_b;
   {
@@ -793,18 +948,8 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ECHO_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
   }
-  // two sub-blocks per CTA (MSUB = 2) when the main loop is long enough to pay for the one-deep accumulator ring and
-  // the coarser tiles do not cost more waves than they save bytes (an MSUB=2 tile runs ~1.6x as long as a plain one)
-  static const int msub_env = getenv("ECHO_TC_MSUB") ? atoi(getenv("ECHO_TC_MSUB")) : 0;
-  int msub = 1;
-  if (!p.geglu && p.num_m_tiles % (cta2 ? 4 : 2) == 0 && p.taps * p.kblocks_per_tap >= 32) {
-    const long long w1 = ((long long)p.vm_tiles * p.num_n_tiles + g_tc.sms - 1) / g_tc.sms;
-    const long long w2 = ((long long)(p.vm_tiles / 2) * p.num_n_tiles + g_tc.sms - 1) / g_tc.sms;
-    if (w2 * 16 < w1 * 10) msub = 2;
-  }
-  if (msub_env == 1) msub = 1;
-  if (msub_env == 2 && p.num_m_tiles % (cta2 ? 4 : 2) == 0 && !p.geglu) msub = 2;
-  const int tiles = p.vm_tiles / msub * p.num_n_tiles;   // CTA tiles
+  const int msub = plan.msub;
+  const int tiles = p.vm_tiles / msub * p.num_n_tiles * p.splitk;   // CTA tiles
   const int b_rows = cta2 ? p.block_n / 2 : p.block_n;
   p.stages = stages_for(b_rows, msub);
   ECHO_CHECK(p.stages >= 2, "gemm_tc: tile does not fit shared memory");
@@ -832,6 +977,13 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
     else gemm_tc_kernel<false, 1><<<grid, NUM_THREADS, smem_bytes, s>>>(map_a, map_b, p);
   }
   ECHO_LAUNCH_CHECK();
+  if (plan.splitk > 1) {
+    dim3 rgrid(cdiv(g.rows_out(), 128), cdiv(g.cout, 64));
+    splitk_reduce_kernel<<<rgrid, 256, 0, s>>>((const float*)g.splitk_ws, plan.splitk, g.rows_out(), g.cout, g.bias, g.rowvec, g.ld_rowvec,
+                                               (long long)g.od * g.oh * g.ow, (const __nv_bfloat16*)g.res, g.ld_res, g.act == 1 ? 1 : 0,
+                                               (__nv_bfloat16*)g.out, g.ldo, g.colsum);
+    ECHO_LAUNCH_CHECK();
+  }
 }
 
 }  // namespace echo

@@ -42,6 +42,7 @@ struct GemmArgs {
   int64_t a_bs0 = 0, a_bs1 = 0, w_bs0 = 0, w_bs1 = 0, o_bs0 = 0, o_bs1 = 0;
   float* colsum = nullptr;          // tcgen05 path: per-column (sum, sumsq) partials, gemm_tc_colsum_rows() x cout x 2 floats
   void* scratch = nullptr;          // tcgen05 path, stride-2 convs: room for a space-to-depth copy of A (same bytes)
+  void* splitk_ws = nullptr;        // tcgen05 path: gemm_tc_splitk_ws_bytes() of scratch lets the plan split K over tap groups
   int64_t rows_out() const { return (int64_t)n * od * oh * ow; }
   int ktot() const { return kd * kh * kw * cin; }
 };
@@ -53,6 +54,8 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s);
 bool tc_available();
 // rows of the column-sum partial buffer per OBJECT for this problem (the tcgen05 kernel writes one per 128-voxel tile)
 int gemm_tc_colsum_rows_per_obj(const GemmArgs& g);
+// bytes of fp32 workspace that let gemm_tc() split the reduction of this problem (0: never split)
+size_t gemm_tc_splitk_ws_bytes(const GemmArgs& g);
 // GroupNorm(+SiLU) with the statistics folded from the producer's column partials inside the apply kernel; `xb` != null:
 // the input is the channel concat [xa | xb] (read in place), `cat` != null additionally receives the raw concat.
 bool gn_apply_cs_supported(const Act& xa, const Act* xb, const Act& out);

@@ -75,7 +75,14 @@ struct echo_shape {
   void contract(const Act& x, const ConvW& w, int k, int stride_hw, const float* rowvec, int64_t ld_rowvec, const Act* res,
                 const Act& out, cudaStream_t s) {
     void* scratch = nullptr;
+    void* splitk_ws = nullptr;
     if (stride_hw == 2 && prec == ECHO_PREC_BF16 && x.dt == BF16) scratch = arena.alloc(x.bytes());
+    if (k == 3 && stride_hw == 1 && prec == ECHO_PREC_BF16 && x.dt == BF16 && out.dt == BF16 && (!res || res->dt == BF16)) {
+      GemmArgs q;   // coarse levels: offer a workspace so the plan may split the taps over more CTAs
+      q.n = x.n; q.od = out.d; q.oh = out.h; q.ow = out.w; q.kd = q.kh = q.kw = 3; q.sh = q.sw = 1; q.cout = w.cout;
+      const size_t wsb = gemm_tc_splitk_ws_bytes(q);
+      if (wsb) splitk_ws = arena.alloc(wsb);
+    }
     if (dry) return;
     GemmArgs g;
     g.scratch = scratch;
@@ -92,6 +99,7 @@ struct echo_shape {
       GemmArgs t = g;
       t.W = w.wb; t.w_dt = BF16;
       t.colsum = out.colsum;
+      t.splitk_ws = splitk_ws;
       if (gemm_tc_supported(t)) { gemm_tc(t, s); return; }
     }
     ECHO_CHECK(!out.colsum, "contract: column statistics were requested but the contraction left the tcgen05 path");
