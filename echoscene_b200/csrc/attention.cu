@@ -64,6 +64,8 @@ __global__ void __launch_bounds__(NTHREADS) flash_attn_kernel(const __nv_bfloat1
   __nv_bfloat16* Ks = Qs + BQT * LDS;     // [2][BKV][LDS]
   __nv_bfloat16* Vs = Ks + 2 * BKV * LDS; // [2][BKV][LDS]
 
+  griddep_launch();
+  griddep_wait();
   const int qt = blockIdx.x, head = blockIdx.y, obj = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ld = (int64_t)3 * heads * DHP;
@@ -248,7 +250,7 @@ static void launch_flash(const __nv_bfloat16* qkv, int n, int tokens, int heads,
     ECHO_CUDA(cudaFuncSetAttribute(flash_attn_kernel<DHP, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  flash_attn_kernel<DHP, MT><<<grid, NTHREADS, smem, s>>>(qkv, tokens, heads, dh, scale_log2e, out);
+  launch_pdl(flash_attn_kernel<DHP, MT>, grid, dim3(NTHREADS), smem, s, qkv, tokens, heads, dh, scale_log2e, out);
 }
 
 void attention_bf16(const __nv_bfloat16* qkv, int n, int tokens, int heads, int dh, __nv_bfloat16* out, cudaStream_t s) {

@@ -400,8 +400,18 @@ int echo_op_attention(const float* qkv, int32_t n, int32_t tokens, int32_t heads
       ECHO_CHECK(tc_available(), "op_attention: bf16 precision needs sm_100a");
       ECHO_CHECK(attention_bf16_supported(tokens, dh), "op_attention: tokens=%d dh=%d not supported by the flash kernel", tokens, dh);
       const int dhp = attention_pad_dh(dh);
-      __nv_bfloat16* qb = (__nv_bfloat16*)g_scratch[1].get((size_t)rows * 3 * heads * dhp * 2);
       __nv_bfloat16* ob = (__nv_bfloat16*)g_scratch[3].get((size_t)rows * C * 2);
+      if (dhp == 64 && attention_tc_supported(tokens, dh)) {   // the tcgen05 kernel (what the shape step runs at 1024 tokens)
+        __nv_bfloat16* qk = (__nv_bfloat16*)g_scratch[1].get((size_t)rows * 2 * heads * 64 * 2);
+        __nv_bfloat16* vt = (__nv_bfloat16*)g_scratch[2].get((size_t)rows * heads * 64 * 2);
+        split_qkv_tc(qkv, n, tokens, heads, dh, qk, vt, s);
+        attention_tc(qk, vt, n, tokens, heads, dh, ob, s);
+        convert(ob, BF16, out, F32, rows * C, s);
+        ECHO_CUDA(cudaStreamSynchronize(s));
+        ECHO_CHECK(attention_tc_error() == 0, "op_attention: tcgen05 kernel found a misaligned shared-memory window");
+        return;
+      }
+      __nv_bfloat16* qb = (__nv_bfloat16*)g_scratch[1].get((size_t)rows * 3 * heads * dhp * 2);
       pad_qkv(qkv, rows, heads, dh, dhp, qb, s);
       attention_bf16(qb, n, tokens, heads, dh, ob, s);
       convert(ob, BF16, out, F32, rows * C, s);

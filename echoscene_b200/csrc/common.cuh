@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <string.h>
 #include <string>
 #include <stdexcept>
 
@@ -96,6 +97,32 @@ struct Act {
 // attribution by difference), ECHO_TRACE=1 prints one line per contraction launch to stderr
 bool dbg_skip(const char* name);
 bool dbg_trace();
+
+// ---- programmatic dependent launch: the next kernel of the stream is scheduled while this one drains; everything it
+//      does before griddep_wait() (barrier init, TMEM allocation, descriptor prefetch, parameter math) overlaps the tail
+//      of its predecessor.  Rule: a kernel launched through launch_pdl() MUST execute griddep_wait() before it touches
+//      global memory another kernel may write or may still be reading (the wait returns once the predecessor grid has
+//      completed and its writes are visible; dependency chains stay transitive because every link waits).
+#ifdef __CUDACC__
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool pdl_enabled();   // ECHO_NO_PDL=1 turns the attribute off (A/B timing)
+template <class... KArgs, class... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  ECHO_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

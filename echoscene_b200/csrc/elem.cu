@@ -264,6 +264,8 @@ __global__ void layer_norm_kernel(const TI* __restrict__ x, int64_t rows, int C,
 __global__ void __launch_bounds__(256) layer_norm_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int C,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                               __nv_bfloat16* __restrict__ y) {
+  griddep_launch();
+  griddep_wait();
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -631,7 +633,7 @@ void layer_norm(const void* x, DT xdt, int64_t rows, int C, const float* gamma, 
   ECHO_CHECK(C % 4 == 0, "layer_norm: C %% 4");
   const int grid = cdiv(rows * 32, 256);
   if (xdt == BF16 && ydt == BF16 && C % 8 == 0 && C <= 768) {
-    layer_norm_bf16_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, rows, C, gamma, beta, eps, (__nv_bfloat16*)y);
+    launch_pdl(layer_norm_bf16_kernel, dim3(grid), dim3(256), 0, s, (const __nv_bfloat16*)x, rows, C, gamma, beta, eps, (__nv_bfloat16*)y);
     ECHO_LAUNCH_CHECK();
     return;
   }
@@ -867,6 +869,8 @@ __global__ void __launch_bounds__(256) gn_apply_cs_kernel(const __nv_bfloat16* _
                                                           const float* __restrict__ beta, int64_t V, int groups, int silu, int noct, int RY,
                                                           int rows_per_block, __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ ycat) {
   extern __shared__ double gn_sm[];           // [C][2] channel sums, then [groups][2] floats
+  griddep_launch();
+  griddep_wait();
   const int C = CA + CB, obj = blockIdx.y, cpg = C / groups;
   float* gst = reinterpret_cast<float*>(gn_sm + 2 * C);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -955,10 +959,10 @@ void gn_apply_cs(const Act& xa, const Act* xb, const float* gamma, const float* 
   const int rows_per_block = 16 * RY;   // 4 passes of 4 rows in flight per thread
   dim3 grid(cdiv(V, rows_per_block), xa.n);
   const size_t smem = (size_t)C * 2 * sizeof(double) + (size_t)groups * 2 * sizeof(float);
-  gn_apply_cs_kernel<<<grid, threads, smem, s>>>((const __nv_bfloat16*)xa.p, xa.c, xa.colsum, xb ? (const __nv_bfloat16*)xb->p : nullptr,
-                                                 xb ? xb->c : 0, xb ? xb->colsum : nullptr, xa.colsum_rows,
-                                                 (double)V * (C / groups), eps, gamma, beta, V, groups, silu ? 1 : 0, noct, RY, rows_per_block,
-                                                 (__nv_bfloat16*)out.p, cat ? (__nv_bfloat16*)cat->p : nullptr);
+  launch_pdl(gn_apply_cs_kernel, grid, dim3(threads), smem, s, (const __nv_bfloat16*)xa.p, xa.c, (const float*)xa.colsum,
+             xb ? (const __nv_bfloat16*)xb->p : (const __nv_bfloat16*)nullptr, xb ? xb->c : 0, xb ? (const float*)xb->colsum : (const float*)nullptr,
+             xa.colsum_rows, (double)V * (C / groups), eps, gamma, beta, V, groups, silu ? 1 : 0, noct, RY, rows_per_block,
+             (__nv_bfloat16*)out.p, cat ? (__nv_bfloat16*)cat->p : (__nv_bfloat16*)nullptr);
   ECHO_LAUNCH_CHECK();
 }
 

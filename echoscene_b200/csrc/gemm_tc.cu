@@ -20,12 +20,15 @@
 // mbarriers, tcgen05.commit releases slots) and a 2-deep TMEM accumulator ring so the epilogue of tile i overlaps
 // the main loop of tile i+1.
 #include "ops.cuh"
+#include "tc_ptx.cuh"
 
 #include <cuda.h>
 #include <stdlib.h>
 #include <mutex>
 
 namespace echo {
+
+using namespace ptx;
 
 namespace {
 
@@ -71,138 +74,9 @@ struct TcParams {
   long long ldo;
   int relu;
   float* colsum;   // optional [num_m_tiles][cout][2] per-column (sum, sumsq) partials for the next GroupNorm
+  int out_t;   // bf16 output stored transposed per object: out[(obj * cout + n) * voxels + voxel] (V^T for the tcgen05 attention)
   int geglu;   // epilogue: tile columns are [a (block_n/2) | g (block_n/2)]; out = (a+ba) * gelu_erf(g+bg), out width cout/2
 };
-
-// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n"
-      ".reg .b32 %%rx;\n"
-      ".reg .pred %%px;\n"
-      "elect.sync %%rx|%%px, %1;\n"
-      "@%%px mov.s32 %0, 1;\n"
-      "}\n"
-      : "+r"(pred)
-      : "r"(0xFFFFFFFFu));
-  return pred != 0;
-}
-__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                   smem_u32(dst)),
-               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate));
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// ---- CTA-pair (cta_group::2) variants: two CTAs of a cluster share one UMMA of M = 256; each stages its own 128 rows
-//      of A and HALF of the B tile, which is what brings the per-SM operand traffic under the 64 B/clk L2->SM port ----
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
-  asm volatile(
-      "{\n"
-      ".reg .b32 remAddr32;\n"
-      "mapa.shared::cluster.u32 remAddr32, %0, %1;\n"
-      "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(cta)
-      : "memory");
-}
-constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> CTA 0's copy
-__device__ __forceinline__ void tma_load_5d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                   smem_u32(dst)),
-               "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate));
-}
-// commit of cta_group::2 MMAs: arrives on the barrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"((uint16_t)3)
-               : "memory");
-}
 
 // GELU(g) = 0.5 g (1 + erf(g / sqrt 2)) with erf from Abramowitz & Stegun 7.1.26 (|error| < 1.5e-7 + the ulp-level error
 // of ex2.approx / rcp.approx): 2 MUFU + ~12 ALU instructions per element instead of erff's branchy polynomial; the
@@ -237,14 +111,6 @@ __device__ __forceinline__ void col_butterfly(float (&v)[32], int lane) {
   }
 }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (8-row atoms of 1024 bytes)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)(1024 >> 4) << 32;   // stride byte offset between 8-row groups
-  d |= (uint64_t)1 << 46;             // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;             // SWIZZLE_128B
-  return d;
-}
 
 // Where the output rows of one 128-row sub-block live: box coordinates inside the object grid.
 struct SubTile {
@@ -295,6 +161,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
 
+  griddep_launch();               // the next kernel may be scheduled as SMs free up (it waits for our completion itself)
   if (CTA2) cluster_sync_all();   // both CTAs resident before the paired TMEM allocation
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], CTA2 ? 2 : 1); mbar_init(&empty_bar[i], 1); }
@@ -313,6 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (CTA2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  griddep_wait();                 // everything above overlapped the predecessor's tail; from here on we read its output
 
   // tile schedule: CTA tiles of MSUB sub-blocks; CTA2 walks (n_blk, m_pair) pairs, this CTA owning m index 2*m_pair + rank
   const int cta_m_tiles = p.vm_tiles / MSUB;
@@ -524,7 +392,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           }
-          if (p.out_bf16) {
+          if (p.out_t) {
+            // lanes are consecutive voxels of one object: each column is a 64-byte run of the transposed tensor
+            const long long vox = (long long)p.od * p.oh * p.ow;
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + ((long long)obj * p.cout + n0) * vox + (orow - (long long)obj * vox);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) op[(long long)j * vox] = __float2bfloat16(f[j]);
+          } else if (p.out_bf16) {
             uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + n0);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -581,6 +455,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
 // 4-phase space-to-depth of a channels-last tensor: out[(obj*4 + ph*2 + pw), d, h/2, w/2, c] = x[obj, d, 2h'+ph, 2w'+pw, c]
 __global__ void s2d_kernel(const __nv_bfloat16* __restrict__ x, int n, int d, int h, int w, int C, long long nvec, __nv_bfloat16* __restrict__ out) {
+  griddep_launch();
+  griddep_wait();
   const int cv = C / 8, h2 = h / 2, w2 = w / 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     const int c8 = (int)(i % cv); long long r = i / cv;
@@ -724,6 +600,8 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
                                                             const __nv_bfloat16* __restrict__ res, long long ld_res, int relu,
                                                             __nv_bfloat16* __restrict__ out, long long ldo, float* __restrict__ colsum) {
   __shared__ float2 red[32][64];
+  griddep_launch();
+  griddep_wait();
   const int c8 = threadIdx.x & 7, rl = threadIdx.x >> 3;
   const int col = blockIdx.y * 64 + c8 * 8;
   const long long row0 = (long long)blockIdx.x * 128;
@@ -796,6 +674,19 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 
 void set_tc_mode(int m) { g_tc_mode = m; }
 
+// 2-D bf16 tensor map, SWIZZLE_128B (for the other tcgen05 kernels of the library: flash_tc.cu)
+void tc_encode_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes, uint32_t box_inner,
+                       uint32_t box_outer) {
+  ECHO_CHECK(tc_available(), "tcgen05 path unavailable on this device");
+  const cuuint64_t dims[2] = {inner, outer};
+  const cuuint64_t strides[1] = {row_stride_bytes};
+  const cuuint32_t box[2] = {box_inner, box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_tc.encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ECHO_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d) failed: %d", (int)r);
+}
+
 bool tc_available() {
   tc_init();
   return g_tc.ok;
@@ -826,6 +717,7 @@ bool gemm_tc_supported(const GemmArgs& g) {
   } else
   if (g.cin % 16 != 0 || g.lda != g.cin || g.w_stride_k != 1 || g.w_stride_n != (int64_t)g.ktot()) return false;
   if (g.cout % 32 != 0) return false;
+  if (g.out_t && (g.out_dt != BF16 || g.epi || g.up2 || g.splitk_ws || g.colsum)) return false;
   if (g.splitk_ws && ((uintptr_t)g.splitk_ws % 16)) return false;
   if (g.epi == 1 && g.colsum) return false;
   if (g.epi == 1 && (g.cout % 256 != 0 || g.res || g.rowvec || !g.bias || g.out_dt != BF16 || g.act != 0)) return false;
@@ -859,7 +751,7 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
     const long long nvec = (long long)g.n * g.d * g.h * g.w * (g.cin / 8);
     long long blocks = (nvec + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    s2d_kernel<<<(int)blocks, 256, 0, s>>>(a_ptr, g.n, g.d, g.h, g.w, g.cin, nvec, (__nv_bfloat16*)g.scratch);
+    launch_pdl(s2d_kernel, dim3((int)blocks), dim3(256), 0, s, a_ptr, g.n, g.d, g.h, g.w, g.cin, nvec, (__nv_bfloat16*)g.scratch);
     ECHO_LAUNCH_CHECK();
     a_ptr = (const __nv_bfloat16*)g.scratch;
     in_h = g.h / 2;
@@ -917,6 +809,7 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   p.res = g.res; p.res_bf16 = g.res_dt == BF16; p.ld_res = g.ld_res;
   p.out = g.out; p.out_bf16 = g.out_dt == BF16; p.ldo = g.ldo; p.relu = g.act == 1;
   p.colsum = g.colsum;
+  p.out_t = g.out_t;
   p.geglu = g.epi == 1;
   if (plan.splitk > 1) {   // raw fp32 partials into the workspace; splitk_reduce_kernel applies the epilogue terms
     p.bias = nullptr; p.rowvec = nullptr; p.res = nullptr; p.colsum = nullptr; p.relu = 0;
@@ -962,26 +855,28 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     if (msub == 2) ECHO_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, 2>, map_a, map_b, p));
     else ECHO_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, 1>, map_a, map_b, p));
   } else {
     const int grid = tiles < g_tc.sms ? tiles : g_tc.sms;
-    if (msub == 2) gemm_tc_kernel<false, 2><<<grid, NUM_THREADS, smem_bytes, s>>>(map_a, map_b, p);
-    else gemm_tc_kernel<false, 1><<<grid, NUM_THREADS, smem_bytes, s>>>(map_a, map_b, p);
+    if (msub == 2) launch_pdl(gemm_tc_kernel<false, 2>, dim3(grid), dim3(NUM_THREADS), smem_bytes, s, map_a, map_b, p);
+    else launch_pdl(gemm_tc_kernel<false, 1>, dim3(grid), dim3(NUM_THREADS), smem_bytes, s, map_a, map_b, p);
   }
   ECHO_LAUNCH_CHECK();
   if (plan.splitk > 1) {
     dim3 rgrid(cdiv(g.rows_out(), 128), cdiv(g.cout, 64));
-    splitk_reduce_kernel<<<rgrid, 256, 0, s>>>((const float*)g.splitk_ws, plan.splitk, g.rows_out(), g.cout, g.bias, g.rowvec, g.ld_rowvec,
-                                               (long long)g.od * g.oh * g.ow, (const __nv_bfloat16*)g.res, g.ld_res, g.act == 1 ? 1 : 0,
-                                               (__nv_bfloat16*)g.out, g.ldo, g.colsum);
+    launch_pdl(splitk_reduce_kernel, rgrid, dim3(256), 0, s, (const float*)g.splitk_ws, plan.splitk, (long long)g.rows_out(), g.cout, g.bias,
+               g.rowvec, (long long)g.ld_rowvec, (long long)g.od * g.oh * g.ow, (const __nv_bfloat16*)g.res, (long long)g.ld_res,
+               g.act == 1 ? 1 : 0, (__nv_bfloat16*)g.out, (long long)g.ldo, g.colsum);
     ECHO_LAUNCH_CHECK();
   }
 }

@@ -34,6 +34,7 @@ struct GemmArgs {
   int64_t ldo = 0;
   int act = 0;                      // 0 none, 1 relu
   int epi = 0;                      // tcgen05 path only: 1 = GEGLU epilogue (W rows tiled [128 a | 128 g]; out width cout/2)
+  int out_t = 0;                    // tcgen05 path only: bf16 output stored transposed per object, out[(obj*cout + n)*voxels + voxel]
   int up2 = 0;                      // tcgen05 path only: the conv follows a nearest x(1,2,2) upsample of A (openai_model_3d.py:150-157);
                                     // A is the LOW-resolution tensor (d,h,w), the output grid is (d,2h,2w), W = fold_upsample_weight()
   float alpha = 1.f;                // scales the accumulator before the epilogue adds
@@ -151,6 +152,12 @@ void ddim_update(const float* x_ncdhw, const void* e, DT edt, bool e_cl, int n, 
 void attention_f32(const float* qkv, int n, int tokens, int heads, int dh, float* scores_ws, float* out, cudaStream_t s);
 size_t attention_f32_ws_floats(int n, int tokens, int heads);
 // attention (bf16 flash kernel): qkv bf16 [rows, 3*heads*attention_pad_dh(dh)] (heads zero-padded), out bf16 [rows, heads*dh]
+// attention (tcgen05 flash kernel, flash_tc.cu): qk bf16 [rows, 2*heads*64] (q then k, heads zero-padded to 64), vt bf16
+// [(n*heads*64), tokens] (V transposed per (object, head)), out bf16 [rows, heads*dh]
+bool attention_tc_supported(int tokens, int dh);
+void attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vt, int n, int tokens, int heads, int dh, __nv_bfloat16* out, cudaStream_t s);
+void split_qkv_tc(const float* qkv, int n, int tokens, int heads, int dh, __nv_bfloat16* qk, __nv_bfloat16* vt, cudaStream_t s);
+int attention_tc_error();   // 1 if a block ever found its shared-memory window misaligned (results invalid)
 int attention_pad_dh(int dh);
 bool attention_bf16_supported(int tokens, int dh);
 void attention_bf16(const __nv_bfloat16* qkv, int n, int tokens, int heads, int dh, __nv_bfloat16* out, cudaStream_t s);

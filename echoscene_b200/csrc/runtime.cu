@@ -32,6 +32,10 @@ bool dbg_skip(const char* name) {
     if ((p == env || p[-1] == ',') && (p[n] == 0 || p[n] == ',')) return true;
   return false;
 }
+bool pdl_enabled() {
+  static const bool on = getenv("ECHO_NO_PDL") == nullptr;
+  return on;
+}
 bool dbg_trace() {
   static const bool on = getenv("ECHO_TRACE") != nullptr;
   return on;

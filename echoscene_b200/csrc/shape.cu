@@ -160,7 +160,28 @@ struct echo_shape {
     Act l1 = new_act(x.n, x.d, x.h, x.w, C, adt);
     if (!dry) layer_norm(t0.p, t0.dt, rows, C, a.ln1.g, a.ln1.b, 1e-5f, l1.p, l1.dt, s);
     Act o = new_act(x.n, x.d, x.h, x.w, C, adt);
-    if (prec == ECHO_PREC_BF16 && adt == BF16 && a.qkv_pad.wb && attention_bf16_supported(tokens, a.dh)) {
+    if (prec == ECHO_PREC_BF16 && adt == BF16 && a.qkv_pad.wb && attention_pad_dh(a.dh) == 64 && (dry || attention_tc_supported(tokens, a.dh))) {
+      // tcgen05 attention: q,k projected into [rows, 2*heads*64]; v projected straight into V^T per (object, head)
+      const int hd = a.heads * 64;
+      ConvW wqk = a.qkv_pad, wv = a.qkv_pad;
+      wqk.cout = 2 * hd;
+      wv.cout = hd;
+      wv.w = a.qkv_pad.w + (size_t)2 * hd * C;
+      wv.wb = a.qkv_pad.wb + (size_t)2 * hd * C;
+      Act qk = new_act(x.n, x.d, x.h, x.w, 2 * hd, BF16);
+      contract(l1, wqk, 1, 1, nullptr, 0, nullptr, qk, s);
+      __nv_bfloat16* vt = (__nv_bfloat16*)arena.alloc((size_t)x.n * hd * tokens * sizeof(__nv_bfloat16));
+      if (!dry) {
+        GemmArgs g;
+        g.A = l1.p; g.a_dt = BF16; g.n = x.n; g.d = x.d; g.h = x.h; g.w = x.w; g.cin = C; g.lda = C;
+        g.od = x.d; g.oh = x.h; g.ow = x.w;
+        g.W = wv.wb; g.w_dt = BF16; g.w_stride_n = C; g.cout = hd;
+        g.out = vt; g.out_dt = BF16; g.ldo = hd; g.out_t = 1;
+        ECHO_CHECK(gemm_tc_supported(g), "attention: V^T projection not supported by the tcgen05 kernel");
+        gemm_tc(g, s);
+        attention_tc((const __nv_bfloat16*)qk.p, vt, x.n, tokens, a.heads, a.dh, (__nv_bfloat16*)o.p, s);
+      }
+    } else if (prec == ECHO_PREC_BF16 && adt == BF16 && a.qkv_pad.wb && attention_bf16_supported(tokens, a.dh)) {
       Act qkv = new_act(x.n, x.d, x.h, x.w, a.qkv_pad.cout, BF16);
       contract(l1, a.qkv_pad, 1, 1, nullptr, 0, nullptr, qkv, s);
       if (!dry) attention_bf16((const __nv_bfloat16*)qkv.p, x.n, tokens, a.heads, a.dh, (__nv_bfloat16*)o.p, s);

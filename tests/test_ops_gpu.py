@@ -169,7 +169,8 @@ def test_upsample_conv_folded(n, c, cout, dhw):
     assert_close(out.permute(0, 4, 1, 2, 3).cpu(), want, 1.5e-2, "folded upsample conv")
 
 
-@pytest.mark.parametrize("n,tokens,heads,dh", [(2, 1024, 8, 56), (2, 256, 8, 84), (16, 1024, 8, 56), (40, 256, 8, 84)])
+@pytest.mark.parametrize("n,tokens,heads,dh", [(2, 1024, 8, 56), (2, 256, 8, 84), (16, 1024, 8, 56), (40, 256, 8, 84), (3, 128, 8, 56),
+                                               (2, 256, 4, 64), (1, 64, 8, 56)])
 def test_attention_bf16(n, tokens, heads, dh):
     _need_tc()
     g = torch.Generator().manual_seed(tokens + dh)
