@@ -75,6 +75,20 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(const LinArgs a, int k
   const int k_beg = warp * k_slice;
   const int k_end = min(a.K, k_beg + k_slice);
 
+  // Programmatic dependent launch: this grid is scheduled while its predecessor still runs.  The weights are constants,
+  // so this warp's slice of W is pulled into L2 NOW -- the HBM latency of a few-row layer (its whole cost besides
+  // launch) hides under the previous layer; only X has to wait for the predecessor to finish.
+  griddep_launch();
+  {
+    constexpr int EPL = 128 / (int)sizeof(TW);   // elements per 128-byte line
+#pragma unroll
+    for (int j = 0; j < RN; ++j)
+      if (n0 + j < a.nout)
+        for (int k = k_beg + lane * EPL; k < k_end; k += 32 * EPL)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(W + (int64_t)(n0 + j) * ldw + k));
+  }
+  griddep_wait();
+
   // LayerNorm statistics of this CTA's rows over the whole K (two-pass, fp32)
   float ln_mean[MT], ln_rstd[MT];
   if (PRO == PRO_LN) {
@@ -192,7 +206,7 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(const LinArgs a, int k
 
 template <class TW, int PRO>
 void launch_pro(const LinArgs& a, dim3 grid, int wk, int k_slice, size_t smem, cudaStream_t s) {
-  linear_rows_kernel<TW, PRO><<<grid, 32 * wk, smem, s>>>(a, k_slice);
+  launch_pdl(linear_rows_kernel<TW, PRO>, grid, dim3(32 * wk), smem, s, a, k_slice);
 }
 
 template <class TW>
