@@ -25,6 +25,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 #include <mutex>
+#include <utility>
+#include <vector>
 
 namespace echo {
 
@@ -674,6 +676,38 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 
 void set_tc_mode(int m) { g_tc_mode = m; }
 
+// ---- in-situ timing probe (bench.py's roofline): CUDA events on the launching stream around every launch of ONE
+//      contraction shape while a real step runs, so the kernel is timed warm, between its actual neighbours ----
+namespace {
+struct TcProbe {
+  bool on = false;
+  long long rows = 0;
+  int cin = 0, cout = 0, k = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+  size_t used = 0;
+} g_probe;
+}  // namespace
+
+void tc_probe_begin(long long rows, int cin, int cout, int k) {
+  g_probe.on = true;
+  g_probe.rows = rows; g_probe.cin = cin; g_probe.cout = cout; g_probe.k = k;
+  g_probe.used = 0;
+}
+
+// average milliseconds per probed launch and the number of launches seen (call after the stream has been synchronised)
+int tc_probe_end(double* avg_ms) {
+  g_probe.on = false;
+  double tot = 0.0;
+  for (size_t i = 0; i < g_probe.used; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_probe.ev[i].first, g_probe.ev[i].second) == cudaSuccess) tot += ms;
+  }
+  const int n = (int)g_probe.used;
+  if (avg_ms) *avg_ms = n ? tot / n : 0.0;
+  g_probe.used = 0;
+  return n;
+}
+
 // 2-D bf16 tensor map, SWIZZLE_128B (for the other tcgen05 kernels of the library: flash_tc.cu)
 void tc_encode_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes, uint32_t box_inner,
                        uint32_t box_outer) {
@@ -847,6 +881,17 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   p.stages = stages_for(b_rows, msub);
   ECHO_CHECK(p.stages >= 2, "gemm_tc: tile does not fit shared memory");
   const int smem_bytes = p.stages * (msub * A_STAGE_BYTES + b_rows * BLOCK_K * 2) + SMEM_FIXED;
+  const bool probed = g_probe.on && g.rows_out() == g_probe.rows && g.cin == g_probe.cin && g.cout == g_probe.cout && g.kd == g_probe.k &&
+                      !g.up2 && g.sh == 1;
+  if (probed) {
+    if (g_probe.used == g_probe.ev.size()) {
+      cudaEvent_t a, b;
+      ECHO_CUDA(cudaEventCreate(&a));
+      ECHO_CUDA(cudaEventCreate(&b));
+      g_probe.ev.emplace_back(a, b);
+    }
+    ECHO_CUDA(cudaEventRecord(g_probe.ev[g_probe.used].first, s));
+  }
   if (cta2) {
     int grid = tiles < (g_tc.sms & ~1) ? tiles : (g_tc.sms & ~1);   // whole CTA pairs, one CTA per SM
     cudaLaunchConfig_t cfg;
@@ -872,6 +917,7 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
     else launch_pdl(gemm_tc_kernel<false, 1>, dim3(grid), dim3(NUM_THREADS), smem_bytes, s, map_a, map_b, p);
   }
   ECHO_LAUNCH_CHECK();
+  if (probed) ECHO_CUDA(cudaEventRecord(g_probe.ev[g_probe.used++].second, s));
   if (plan.splitk > 1) {
     dim3 rgrid(cdiv(g.rows_out(), 128), cdiv(g.cout, 64));
     launch_pdl(splitk_reduce_kernel, rgrid, dim3(256), 0, s, (const float*)g.splitk_ws, plan.splitk, (long long)g.rows_out(), g.cout, g.bias,

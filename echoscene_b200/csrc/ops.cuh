@@ -53,6 +53,9 @@ void gemm_simt(const GemmArgs& g, cudaStream_t s);
 bool gemm_tc_supported(const GemmArgs& g);
 void gemm_tc(const GemmArgs& g, cudaStream_t s);
 bool tc_available();
+// timing probe: CUDA events around every gemm_tc launch of one shape while steps run (bench.py roofline)
+void tc_probe_begin(long long rows, int cin, int cout, int k);
+int tc_probe_end(double* avg_ms);
 // rows of the column-sum partial buffer per OBJECT for this problem (the tcgen05 kernel writes one per 128-voxel tile)
 int gemm_tc_colsum_rows_per_obj(const GemmArgs& g);
 // bytes of fp32 workspace that let gemm_tc() split the reduction of this problem (0: never split)

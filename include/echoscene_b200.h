@@ -118,6 +118,11 @@ ECHO_API int64_t echo_launch_count(void);
 ECHO_API void echo_launch_count_reset(void);
 /* tuning/profiling knob of the tcgen05 GEMM: 0 = automatic, 1 = one CTA per 128-row tile, 2 = CTA pairs (cta_group::2). */
 ECHO_API void echo_debug_set_tc_mode(int mode);
+/* Measurement aid (bench.py roofline): between begin and end, every tcgen05 contraction launch with this output row
+ * count / cin / cout / kernel size is bracketed by CUDA events on its launching stream; end returns the number of
+ * launches seen and their average duration in milliseconds (synchronise the stream first). */
+ECHO_API void echo_debug_probe_begin(int64_t rows, int32_t cin, int32_t cout, int32_t ksize);
+ECHO_API int32_t echo_debug_probe_end(double* avg_ms);
 
 /* ---- graph: edges = stack([s, o]) of `triples` (T,3) int64 [s,p,o] — denoise_net.py:759-761, graph.py:142-143 */
 ECHO_API int echo_graph_create(echo_graph_t** out, const int64_t* triples_dev, int32_t n_triples, int32_t n_nodes, void* stream);
