@@ -250,14 +250,20 @@ def main():
     codes_all = torch.empty(n_total, 64, device=dev)
     L = _lib.lib()
 
+    xstream = torch.cuda.Stream(device=dev) if world > 1 else None
+
     def step(xin, xout, i):
         index = DDIM_STEPS - 1 - (i % DDIM_STEPS)
         if world == 1:
             m.ddim_step(xin, uc_all, tri, index, out=xout)
         else:
-            codes = m.embed_local(xin, n_total, tri.shape[0])
-            dist.all_gather_into_tensor(codes_all, codes)          # the echo exchange: (16,64) fp32 per rank over NVLink
-            m.trunk_local(xin, obj_begin, codes_all, uc_all, tri, index=index, out=xout)
+            # embed + the echo exchange ((16,64) fp32 per rank, NCCL over NVLink) on their own stream; the trunk starts at
+            # once and only its echo chain (GCN -> cross-attention vectors, needed at input block 4) waits for the codes
+            xstream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(xstream):
+                codes = m.embed_local(xin, n_total, tri.shape[0])
+                dist.all_gather_into_tensor(codes_all, codes)
+            m.trunk_local(xin, obj_begin, codes_all, uc_all, tri, index=index, out=xout, codes_stream=xstream)
 
     m._ensure(n_total, tri.shape[0], N_NODES if world > 1 else None)
     m.frozen = True

@@ -85,6 +85,7 @@ PROTOTYPES = {
     "echo_shape_step": (C.c_int, [_P, _P, _P, _P, _I, _P, _P]),
     "echo_shape_embed": (C.c_int, [_P, _P, _I, _P, _P]),
     "echo_shape_trunk": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _P, _I, _P, _P]),
+    "echo_shape_trunk_async": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _P, _I, _P, _P, _P]),
     "echo_shape_latent": (C.c_int, [_P, _I, _P, _P]),
     "echo_shape_destroy": (None, [_P]),
     "echo_shape_schedule": (C.c_int, [_P, _P, _P]),

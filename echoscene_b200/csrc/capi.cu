@@ -24,7 +24,7 @@ void shape_forward(echo_shape*, const echo_graph*, const float*, const float*, c
 void shape_step(echo_shape*, const echo_graph*, const float*, const float*, int, float*, cudaStream_t);
 void shape_embed(echo_shape*, const float*, int, float*, cudaStream_t);
 void shape_trunk(echo_shape*, const echo_graph*, const float*, int, int, const float*, const float*, const int64_t*, int, float*,
-                 cudaStream_t);
+                 cudaStream_t, cudaStream_t);
 const float* shape_latent(const echo_shape*);
 int shape_context_dim(const echo_shape*);
 void shape_tables(const echo_shape*, const std::vector<float>**, const std::vector<int32_t>**);
@@ -235,7 +235,16 @@ int echo_shape_trunk(echo_shape_t* h, const echo_graph_t* g, const float* x_loca
                      void* stream) {
   return guard([&] {
     ECHO_CHECK(h && g && codes_all && obj_embed_all && (n_local == 0 || (x_local && out_local)), "shape_trunk: null argument");
-    shape_trunk(h, g, x_local, obj_begin, n_local, codes_all, obj_embed_all, t_all, ddim_index, out_local, (cudaStream_t)stream);
+    shape_trunk(h, g, x_local, obj_begin, n_local, codes_all, obj_embed_all, t_all, ddim_index, out_local, (cudaStream_t)stream, nullptr);
+  });
+}
+int echo_shape_trunk_async(echo_shape_t* h, const echo_graph_t* g, const float* x_local, int32_t obj_begin, int32_t n_local,
+                           const float* codes_all, const float* obj_embed_all, const int64_t* t_all, int32_t ddim_index,
+                           float* out_local, void* codes_stream, void* stream) {
+  return guard([&] {
+    ECHO_CHECK(h && g && codes_all && obj_embed_all && (n_local == 0 || (x_local && out_local)), "shape_trunk_async: null argument");
+    shape_trunk(h, g, x_local, obj_begin, n_local, codes_all, obj_embed_all, t_all, ddim_index, out_local, (cudaStream_t)stream,
+                (cudaStream_t)codes_stream);
   });
 }
 int echo_shape_latent(const echo_shape_t* h, int32_t n_nodes, float* out_dev, void* stream) {

@@ -26,7 +26,7 @@ struct echo_shape {
   Arena arena;        // trunk temporaries (main stream)
   Arena side_arena;   // shape_embeddings temporaries (side stream: must not alias the trunk's stack)
   cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_codes = nullptr;
   bool dry = false;
   int prec = ECHO_PREC_FP32;
   DT adt = F32;   // trunk activation dtype
@@ -232,9 +232,9 @@ struct echo_shape {
   }
 
   // shape_embeddings stack on local objects (openai_model_3d.py:757-764): x_cl (n,16,16,16,3) f32 -> codes (n,64)
-  void embed(const Act& xcl, float* codes_out, cudaStream_t s) {
+  void embed(const Act& xcl, float* codes_out, cudaStream_t s, size_t base_mark = 0) {
     Arena& A = side_arena;
-    A.release(0);
+    A.release(base_mark);
     Act c0 = new_act_in(A, xcl.n, xcl.d, xcl.h, xcl.w, 32, F32);
     contract(xcl, se_conv0, 3, 1, nullptr, 0, nullptr, c0, s);
     Act p0 = new_act_in(A, xcl.n, xcl.d / 2, xcl.h / 2, xcl.w / 2, 32, F32);
@@ -251,7 +251,8 @@ struct echo_shape {
 
   // everything after the codes are known.  out: e_t (ddim_index < 0) or x_prev, NCDHW f32, local objects.
   void trunk(const echo_graph* g, const float* x_local, const Act& xcl, int obj_begin, int n_local, const float* codes_all,
-             const float* uc_all, const int64_t* t_all, int ddim_index, float* out_local, cudaStream_t s) {
+             const float* uc_all, const int64_t* t_all, int ddim_index, float* out_local, cudaStream_t s,
+             cudaStream_t codes_stream = nullptr) {
     const int N = g->n_nodes, T = g->n_triples, mc = d.model_channels, E = 4 * mc, ctx = d.context_dim, gd = d.gconv_dim;
     const int nd = ctx + gd + (d.enable_t_emb ? gd : 0);
     // timestep embedding + time MLP for ALL nodes (the GCN needs every node's t_emb)
@@ -264,6 +265,10 @@ struct echo_shape {
     if (!dry) {
       ECHO_CUDA(cudaEventRecord(ev_fork, s));
       ECHO_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+      if (codes_stream && codes_stream != s) {   // the all-gathered codes arrive on another stream: only the echo chain waits
+        ECHO_CUDA(cudaEventRecord(ev_codes, codes_stream));
+        ECHO_CUDA(cudaStreamWaitEvent(side, ev_codes, 0));
+      }
       q = side;
     }
     if (!codes_all) {   // unsharded: embed here (sharded callers all-gathered the codes between embed and trunk)
@@ -388,8 +393,18 @@ struct echo_shape {
     arena.release(m0);
   }
 
+  // shape_embeddings on local objects with every temporary (incl. the channels-last copy) in the side arena, so it may
+  // run on another stream while the trunk of the same step is already using the main arena
+  void embed_entry(const float* x_local, int n_local, float* codes_out, cudaStream_t s) {
+    side_arena.release(0);
+    const int L = d.latent_size;
+    Act xcl = new_act_in(side_arena, n_local, L, L, L, d.in_channels, F32);
+    if (!dry) ncdhw_to_cl(x_local, n_local, d.in_channels, (int64_t)L * L * L, xcl.p, F32, s);
+    embed(xcl, codes_out, s, side_arena.mark());
+  }
+
   void run(const echo_graph* g, const float* x_local, int obj_begin, int n_local, const float* codes_all, const float* uc_all,
-           const int64_t* t_all, int ddim_index, float* out_local, cudaStream_t s) {
+           const int64_t* t_all, int ddim_index, float* out_local, cudaStream_t s, cudaStream_t codes_stream = nullptr) {
     ECHO_CHECK(g && g->n_nodes <= d.max_nodes && g->n_triples <= d.max_triples, "shape: graph exceeds handle capacity");
     ECHO_CHECK(n_local >= 0 && n_local <= d.max_local_nodes && obj_begin >= 0 && obj_begin + n_local <= g->n_nodes,
                "shape: bad local range [%d, %d) of %d nodes (capacity %d)", obj_begin, obj_begin + n_local, g->n_nodes, d.max_local_nodes);
@@ -400,7 +415,7 @@ struct echo_shape {
     if (!dry && n_local > 0) ncdhw_to_cl(x_local, n_local, d.in_channels, (int64_t)L * L * L, xcl.p, F32, s);
     if (!codes_all) ECHO_CHECK(n_local == g->n_nodes && obj_begin == 0, "shape: codes of all nodes are required when the trunk is sharded");
     if (n_local == 0) return;
-    trunk(g, x_local, xcl, obj_begin, n_local, codes_all, uc_all, t_all, ddim_index, out_local, s);
+    trunk(g, x_local, xcl, obj_begin, n_local, codes_all, uc_all, t_all, ddim_index, out_local, s, codes_stream);
   }
 };
 
@@ -575,10 +590,7 @@ echo_shape* shape_create(const echo_shape_desc_t* desc, const echo_weight_t* wei
       else {
         h->run(&fake, nullptr, 0, d.max_local_nodes, (const float*)8, nullptr, nullptr, -1, nullptr, s);
         // embed-only path
-        h->arena.release(0);
-        const int L = d.latent_size;
-        Act xcl = h->new_act(d.max_local_nodes, L, L, L, d.in_channels, F32);
-        h->embed(xcl, nullptr, s);
+        h->embed_entry(nullptr, d.max_local_nodes, nullptr, s);
       }
       h->dry = false;
       const size_t need = h->arena.high + (size_t(1) << 20);
@@ -589,6 +601,7 @@ echo_shape* shape_create(const echo_shape_desc_t* desc, const echo_weight_t* wei
     ECHO_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
     ECHO_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     ECHO_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    ECHO_CUDA(cudaEventCreateWithFlags(&h->ev_codes, cudaEventDisableTiming));
     return h;
   } catch (...) {
     h->arena.destroy();
@@ -604,6 +617,7 @@ void shape_destroy(echo_shape* h) {
   if (h->side) cudaStreamDestroy(h->side);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_codes) cudaEventDestroy(h->ev_codes);
   h->arena.destroy();
   h->side_arena.destroy();
   h->pool.destroy();
@@ -623,15 +637,11 @@ void shape_step(echo_shape* h, const echo_graph* g, const float* x, const float*
 void shape_embed(echo_shape* h, const float* x_local, int n_local, float* codes_out, cudaStream_t s) {
   ECHO_CHECK(n_local >= 0 && n_local <= h->d.max_local_nodes, "shape_embed: n_local %d exceeds capacity", n_local);
   if (n_local == 0) return;
-  h->arena.release(0);
-  const int L = h->d.latent_size;
-  Act xcl = h->new_act(n_local, L, L, L, h->d.in_channels, F32);
-  ncdhw_to_cl(x_local, n_local, h->d.in_channels, (int64_t)L * L * L, xcl.p, F32, s);
-  h->embed(xcl, codes_out, s);
+  h->embed_entry(x_local, n_local, codes_out, s);
 }
 
 void shape_trunk(echo_shape* h, const echo_graph* g, const float* x_local, int obj_begin, int n_local, const float* codes_all,
-                 const float* uc_all, const int64_t* t_all, int ddim_index, float* out_local, cudaStream_t s) {
+                 const float* uc_all, const int64_t* t_all, int ddim_index, float* out_local, cudaStream_t s, cudaStream_t codes_stream) {
   ECHO_CHECK(codes_all, "shape_trunk: codes_all is required");
   const int64_t* t_use = t_all;
   if (!t_all) {
@@ -639,7 +649,7 @@ void shape_trunk(echo_shape* h, const echo_graph* g, const float* x_local, int o
     fill_i64(h->t_dev, g->n_nodes, h->h_ts[ddim_index], s);
     t_use = h->t_dev;
   }
-  h->run(g, x_local, obj_begin, n_local, codes_all, uc_all, t_use, ddim_index, out_local, s);
+  h->run(g, x_local, obj_begin, n_local, codes_all, uc_all, t_use, ddim_index, out_local, s, codes_stream);
 }
 
 }  // namespace echo

@@ -418,7 +418,9 @@ class UNet3DModel(_SpecModule):
 
     @torch.no_grad()
     def trunk_local(self, x_local, obj_begin, codes_all, obj_embed_all, triples, index: int = -1, timesteps_all=None,
-                    out: Optional[torch.Tensor] = None):
+                    out: Optional[torch.Tensor] = None, codes_stream: Optional[torch.cuda.Stream] = None):
+        """codes_stream: the stream the embed + all-gather of `codes_all` were queued on; when given, only the echo chain
+        waits for it and the first trunk blocks overlap the exchange."""
         _lib.require_cuda(x_local, codes_all, obj_embed_all, triples)
         n = codes_all.shape[0]
         nl = x_local.shape[0]
@@ -429,6 +431,11 @@ class UNet3DModel(_SpecModule):
         codes_all = codes_all.float().contiguous()
         out = torch.empty_like(x_local) if out is None else out
         t = None if timesteps_all is None else timesteps_all.to(torch.int64).contiguous()
+        if codes_stream is not None:
+            _lib.check(_lib.lib().echo_shape_trunk_async(self._handle, g.h, _lib.ptr(x_local), int(obj_begin), nl,
+                                                         _lib.ptr(codes_all), _lib.ptr(obj_embed_all), _lib.ptr(t), int(index),
+                                                         _lib.ptr(out), codes_stream.cuda_stream, _lib.stream_ptr()))
+            return out
         _lib.check(_lib.lib().echo_shape_trunk(self._handle, g.h, _lib.ptr(x_local), int(obj_begin), nl,
                                                _lib.ptr(codes_all), _lib.ptr(obj_embed_all), _lib.ptr(t), int(index),
                                                _lib.ptr(out), _lib.stream_ptr()))

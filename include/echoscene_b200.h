@@ -169,6 +169,12 @@ ECHO_API int echo_shape_embed(echo_shape_t* h, const float* x_local, int32_t n_l
 ECHO_API int echo_shape_trunk(echo_shape_t* h, const echo_graph_t* g, const float* x_local, int32_t obj_begin, int32_t n_local,
                      const float* codes_all, const float* obj_embed_all, const int64_t* timesteps_all,
                      int32_t ddim_index /* < 0: no sampler update, write e_t */, float* out_local, void* stream);
+/* Same, for a sharded step whose all-gather runs on its own stream: `codes_all` is produced by work already queued on
+ * `codes_stream` (the embed + NCCL all-gather); only the echo chain (GCN -> cross-attention vectors) waits for it, the
+ * trunk's first blocks start at once on `stream` and meet the echo chain at the first SpatialTransformer. */
+ECHO_API int echo_shape_trunk_async(echo_shape_t* h, const echo_graph_t* g, const float* x_local, int32_t obj_begin, int32_t n_local,
+                           const float* codes_all, const float* obj_embed_all, const int64_t* timesteps_all,
+                           int32_t ddim_index, float* out_local, void* codes_stream, void* stream);
 /* copies latent_shape_rel of the last forward/trunk call, (n_nodes, context_dim) f32, into out_dev. */
 ECHO_API int echo_shape_latent(const echo_shape_t* h, int32_t n_nodes, float* out_dev, void* stream);
 ECHO_API void echo_shape_destroy(echo_shape_t* h);

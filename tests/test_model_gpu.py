@@ -249,3 +249,62 @@ def test_full_size_determinism_n16(shape_sd):
     b = m.ddim_step(x_T.to(DEV), uc.to(DEV), g.triples.to(DEV), 99)
     assert torch.equal(a, b) and torch.isfinite(a).all()
     assert (a[0] - a[1]).abs().max() > 0
+
+
+def test_shape_bf16_full_size_matches_small_batches(shape_sd):
+    """BASELINE config 2 size in the tensor-core mode: 4 disjoint scenes of 4 nodes batched into one N = 16 step.
+    The launch plans differ with the object count (sub-blocks per CTA, split-K, tile widths), so the full-size step is
+    checked (a) against the fp32 parity path on the same inputs at the bf16 tolerance (the fp32 path is pinned to the
+    reference at 1e-3 by the golden fixtures) and (b) against each scene stepped alone in bf16: only summation order
+    differs, but every layer re-rounds to bf16, so two bf16 evaluations sit ~sqrt(2) x the bf16-vs-fp32 distance apart
+    (measured 0.9e-2 rel-L2); a broken plan would be O(1) off."""
+    if not _lib.lib().echo_has_tcgen05():
+        pytest.skip("tcgen05 kernels not available")
+    m = shape_model(shape_sd, precision="bf16")
+    gs = [synth.make_scene_graph(4, 6, 10 + i) for i in range(4)]
+    b = synth.batch_scene_graphs(gs)
+    uc, x = synth.shape_inputs(16, 77, same_noise=False)
+    ts = torch.full((16,), 501, dtype=torch.int64)
+    full = m(x.to(DEV), uc.to(DEV), b.triples.to(DEV), ts.to(DEV))
+    assert torch.isfinite(full).all()
+    m32 = shape_model(shape_sd)
+    want = m32(x.to(DEV), uc.to(DEV), b.triples.to(DEV), ts.to(DEV))
+    assert_close(full, want, BF16_TOL, "N=16 bf16 step vs the fp32 parity path")
+    for i, g in enumerate(gs):
+        sl = slice(4 * i, 4 * i + 4)
+        alone = m(x[sl].to(DEV), uc[sl].to(DEV), g.triples.to(DEV), ts[sl].to(DEV))
+        assert_close(full[sl], alone, 2e-2, f"scene {i} inside the N=16 batch vs alone")
+
+
+def test_shape_bf16_n32_finite_and_deterministic(shape_sd):
+    """BASELINE config 3 size (N = 32, T = 128), S = 250 schedule: finite, run-to-run bit-identical."""
+    if not _lib.lib().echo_has_tcgen05():
+        pytest.skip("tcgen05 kernels not available")
+    m = shape_model(shape_sd, precision="bf16", ddim_steps=250)
+    g = synth.make_scene_graph(32, 128, 3)
+    uc, x_T = synth.shape_inputs(32, 3, same_noise=True)
+    a = m.ddim_step(x_T.to(DEV), uc.to(DEV), g.triples.to(DEV), 249)
+    b = m.ddim_step(x_T.to(DEV), uc.to(DEV), g.triples.to(DEV), 249)
+    assert torch.equal(a, b) and torch.isfinite(a).all()
+
+
+def test_sharded_trunk_with_codes_on_their_own_stream(shape_sd):
+    """echo_shape_trunk_async: embed + (stand-in for the) all-gather queued on a second stream, trunk on the current one;
+    result is bit-identical to the unsharded step."""
+    m = shape_model(shape_sd, ddim_steps=2)
+    g = synth.make_scene_graph(3, 4, 9)
+    uc, x_T = synth.shape_inputs(3, 90, same_noise=True)
+    tri, ucd, xd = g.triples.to(DEV), uc.to(DEV), x_T.to(DEV)
+    full = m.ddim_step(xd, ucd, tri, 1)
+    ms = shape_model(shape_sd, ddim_steps=2)
+    s2 = torch.cuda.Stream()
+    codes_all = torch.empty(3, 64, device=DEV)
+    outs = []
+    for (lo, hi) in [(0, 2), (2, 3)]:
+        s2.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s2):
+            codes_all[0:2] = ms.embed_local(xd[:2], 3, 4)     # every "rank"'s codes (the all-gather)
+            codes_all[2:3] = ms.embed_local(xd[2:], 3, 4)
+        outs.append(ms.trunk_local(xd[lo:hi], lo, codes_all, ucd, tri, index=1, codes_stream=s2))
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat(outs), full)
