@@ -725,6 +725,20 @@ void cl_to_ncdhw(const void* x, DT xdt, int n, int c, int64_t V, int ld, float* 
   ECHO_LAUNCH_CHECK();
 }
 
+namespace {
+__global__ void silu_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    y[i] = v / (1.f + expf(-v));
+  }
+}
+}  // namespace
+
+void silu_f32(const float* x, float* y, int64_t count, cudaStream_t s) {
+  silu_f32_kernel<<<grid_for(count, 256), 256, 0, s>>>(x, y, count);
+  ECHO_LAUNCH_CHECK();
+}
+
 void convert(const void* x, DT xdt, void* y, DT ydt, int64_t count, cudaStream_t s) {
   const int grid = grid_for(count, 256);
   if (xdt == F32 && ydt == BF16) convert_kernel<float, __nv_bfloat16><<<grid, 256, 0, s>>>((const float*)x, (__nv_bfloat16*)y, count);
@@ -956,7 +970,10 @@ void gn_apply_cs(const Act& xa, const Act* xb, const float* gamma, const float* 
   const int C = out.c, noct = C / 8, RY = 256 / noct;
   const int threads = ((noct * RY + 31) / 32) * 32;
   const int64_t V = xa.voxels();
-  const int rows_per_block = 16 * RY;   // 4 passes of 4 rows in flight per thread
+  // 4 passes of 4 rows in flight per thread, fewer when that would leave the chip with less than ~2 blocks per SM (the
+  // coarse levels are latency-, not bandwidth-bound)
+  int rows_per_block = 16 * RY;
+  while (rows_per_block > 2 * RY && (int64_t)cdiv(V, rows_per_block) * xa.n < 2 * 148) rows_per_block -= 2 * RY;
   dim3 grid(cdiv(V, rows_per_block), xa.n);
   const size_t smem = (size_t)C * 2 * sizeof(double) + (size_t)groups * 2 * sizeof(float);
   launch_pdl(gn_apply_cs_kernel, grid, dim3(threads), smem, s, (const __nv_bfloat16*)xa.p, xa.c, (const float*)xa.colsum,

@@ -342,10 +342,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       } else
       for (int c = 32 * cg; c < p.block_n; c += 64) {
+        const int n0 = n_base + c;
+        // bf16 residual of this chunk: requested BEFORE the TMEM read so its L2 round trip overlaps it (the epilogue of a
+        // short-K contraction is a chain of such round trips)
+        uint4 rres[4];
+        const bool has_res = p.res && p.res_bf16 && valid && n0 < p.cout;
+        if (has_res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + orow * p.ld_res + n0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rres[q] = __ldg(rp + q);
+        }
         uint32_t v[32];
         tmem_ld32(taddr + c, v);
         tmem_ld_wait();
-        const int n0 = n_base + c;
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = 0.f;
@@ -369,10 +378,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           if (p.res) {
             if (p.res_bf16) {
-              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + orow * p.ld_res + n0);
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const uint4 u = __ldg(rp + q);
+                const uint4 u = rres[q];
                 const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {

@@ -26,7 +26,7 @@ struct echo_layout {
   const float* freqs = nullptr;
   std::vector<float> h_tab;
   float* d_tab = nullptr;
-  float *temb = nullptr, *e1 = nullptr, *emb = nullptr, *node = nullptr, *pred = nullptr, *latent = nullptr;
+  float *temb = nullptr, *e1 = nullptr, *emb = nullptr, *emb_act = nullptr, *node = nullptr, *pred = nullptr, *latent = nullptr;
   float *embout = nullptr, *v2 = nullptr, *a2vec = nullptr, *eps = nullptr;
   int64_t* t_dev = nullptr;
   // CUDA-graph replay of one DDPM iteration (layout_step)
@@ -141,7 +141,9 @@ struct echo_layout {
     }
     if (T > 0) embedding_rows(pred_table, 2 * gd, g->triples, 3, 1, T, pred, 2 * gd, s);
     gcn.forward(g, node, pred, latent, nullptr, s);
-    lin(emb, E, plan.emb_stack, embout, plan.emb_total, nullptr, 0, 1, 0, s);
+    // all 22 emb_layers share SiLU(emb): activate once instead of in every warp of the stacked projection
+    silu_f32(emb, emb_act, (int64_t)N * E, s);
+    lin(emb_act, E, plan.emb_stack, embout, plan.emb_total, nullptr, 0, 0, 0, s);
     lin(latent, d.context_dim, plan.v2_stack, v2, plan.v2_total, nullptr, 0, 0, 0, s);
     {
       int ai = 0;
@@ -303,6 +305,7 @@ echo_layout* layout_create(const echo_layout_desc_t* desc, const echo_weight_t* 
     h->temb = h->pool.alloc_n<float>(N * mc);
     h->e1 = h->pool.alloc_n<float>(N * E);
     h->emb = h->pool.alloc_n<float>(N * E);
+    h->emb_act = h->pool.alloc_n<float>(N * E);
     h->node = h->pool.alloc_n<float>(N * gdsc.input_dim_obj);
     h->pred = h->pool.alloc_n<float>(T * 2 * gd);
     h->latent = h->pool.alloc_n<float>(N * d.context_dim);

@@ -128,6 +128,8 @@ void ncdhw_to_cl_pad16(const float* x, int n, int c, int64_t voxels, __nv_bfloat
 // x channels-last with row stride ld (>= c) -> out (n, c, voxels)
 void cl_to_ncdhw(const void* x, DT xdt, int n, int c, int64_t voxels, int ld, float* out, cudaStream_t s);
 void convert(const void* x, DT xdt, void* y, DT ydt, int64_t count, cudaStream_t s);
+// y = x * sigmoid(x) (the SiLU in front of every ResBlock's emb_layers Linear, applied once to the shared time embedding)
+void silu_f32(const float* x, float* y, int64_t count, cudaStream_t s);
 // y[r, :] += v[r / rows_per_obj, :]
 void add_rowvec(void* y, DT ydt, int64_t rows, int C, const float* v, int64_t ldv, int64_t rows_per_obj, cudaStream_t s);
 // in-place row softmax of S [rows, cols] (fp32)

@@ -26,6 +26,8 @@ struct echo_shape {
   Arena arena;        // trunk temporaries (main stream)
   Arena side_arena;   // shape_embeddings temporaries (side stream: must not alias the trunk's stack)
   cudaStream_t side = nullptr;
+  cudaStream_t side2 = nullptr;   // ResBlock 1x1 skip convolutions: independent of the GN -> conv -> GN chain, they fill its tails
+  cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_codes = nullptr;
   bool dry = false;
   int prec = ECHO_PREC_FP32;
@@ -39,7 +41,7 @@ struct echo_shape {
   std::vector<int32_t> h_ts;
   float* d_coef = nullptr;
   // persistent per-step buffers
-  float *temb = nullptr, *e1 = nullptr, *emb = nullptr, *node = nullptr, *pred = nullptr, *latent = nullptr, *codes = nullptr;
+  float *temb = nullptr, *e1 = nullptr, *emb = nullptr, *emb_act = nullptr, *node = nullptr, *pred = nullptr, *latent = nullptr, *codes = nullptr;
   float *embout = nullptr, *v2 = nullptr, *a2vec = nullptr;
   int64_t* t_dev = nullptr;
   int a2_total = 0;
@@ -132,16 +134,28 @@ struct echo_shape {
     } else {
       a1 = gn(x, r.n1, 1e-5f, true, adt, s);
     }
+    // 1x1 skip conv (Cin != Cout): independent of the GN -> conv -> GN chain below, so it goes to its own stream right
+    // after the first GroupNorm (which completes x when x is a fused concat) and runs in the tails of conv1 / GN2
+    Act sk;
+    bool forked = false;
+    if (r.has_skip) {
+      static const bool no_side2 = getenv("ECHO_NO_SIDE2") != nullptr;
+      sk = new_act(x.n, x.d, x.h, x.w, r.cout, adt);
+      forked = !dry && !no_side2 && side2;
+      if (forked) {
+        ECHO_CUDA(cudaEventRecord(ev_fork2, s));
+        ECHO_CUDA(cudaStreamWaitEvent(side2, ev_fork2, 0));
+        contract(x, r.skip, 1, 1, nullptr, 0, nullptr, sk, side2);
+        ECHO_CUDA(cudaEventRecord(ev_join2, side2));
+      } else {
+        contract(x, r.skip, 1, 1, nullptr, 0, nullptr, sk, s);
+      }
+    }
     Act h1 = new_act_cs(x.n, x.d, x.h, x.w, r.cout, adt);
     contract(a1, r.c1, 3, 1, embout + r.emb_off, plan.emb_total, nullptr, h1, s);
     Act a2 = gn(h1, r.n2, 1e-5f, true, adt, s);
-    if (r.has_skip) {
-      Act sk = new_act(x.n, x.d, x.h, x.w, r.cout, adt);
-      contract(x, r.skip, 1, 1, nullptr, 0, nullptr, sk, s);
-      contract(a2, r.c2, 3, 1, nullptr, 0, &sk, out, s);
-    } else {
-      contract(a2, r.c2, 3, 1, nullptr, 0, &x, out, s);
-    }
+    if (forked) ECHO_CUDA(cudaStreamWaitEvent(s, ev_join2, 0));
+    contract(a2, r.c2, 3, 1, nullptr, 0, r.has_skip ? &sk : &x, out, s);
     arena.release(m);
     (void)n_local;
     return out;
@@ -307,7 +321,8 @@ struct echo_shape {
     };
     // per-object time-embedding projections of the local objects (main stream: the first ResBlock needs them)
     const float* emb_loc = emb + (size_t)obj_begin * E;
-    lin(emb_loc, E, n_local, plan.emb_stack, embout, plan.emb_total, 1, 0, s);
+    if (!dry) silu_f32(emb_loc, emb_act, (int64_t)n_local * E, s);   // shared by all 17 emb_layers
+    lin(emb_act, E, n_local, plan.emb_stack, embout, plan.emb_total, 0, 0, s);
     // ---- UNet trunk ----
     const size_t m0 = arena.mark();
     std::vector<Act> hs;
@@ -557,6 +572,7 @@ echo_shape* shape_create(const echo_shape_desc_t* desc, const echo_weight_t* wei
     h->temb = h->pool.alloc_n<float>(N * mc);
     h->e1 = h->pool.alloc_n<float>(N * E);
     h->emb = h->pool.alloc_n<float>(N * E);
+    h->emb_act = h->pool.alloc_n<float>(NL * E);
     h->node = h->pool.alloc_n<float>(N * gdsc.input_dim_obj);
     h->pred = h->pool.alloc_n<float>(T * 2 * gd);
     h->latent = h->pool.alloc_n<float>(N * ctx);
@@ -599,6 +615,9 @@ echo_shape* shape_create(const echo_shape_desc_t* desc, const echo_weight_t* wei
       h->side_arena.init(need_side);
     }
     ECHO_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    ECHO_CUDA(cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking));
+    ECHO_CUDA(cudaEventCreateWithFlags(&h->ev_fork2, cudaEventDisableTiming));
+    ECHO_CUDA(cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
     ECHO_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     ECHO_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     ECHO_CUDA(cudaEventCreateWithFlags(&h->ev_codes, cudaEventDisableTiming));
@@ -615,6 +634,9 @@ echo_shape* shape_create(const echo_shape_desc_t* desc, const echo_weight_t* wei
 void shape_destroy(echo_shape* h) {
   if (!h) return;
   if (h->side) cudaStreamDestroy(h->side);
+  if (h->side2) cudaStreamDestroy(h->side2);
+  if (h->ev_fork2) cudaEventDestroy(h->ev_fork2);
+  if (h->ev_join2) cudaEventDestroy(h->ev_join2);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev_codes) cudaEventDestroy(h->ev_codes);
