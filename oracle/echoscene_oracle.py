@@ -67,11 +67,11 @@ def graph_triple_conv(sd: SD, p: str, obj_vecs: Tensor, pred_vecs: Tensor, edges
     new_t = gcn_mlp(sd, p + "net1", cur_t)                      # graph.py:152
     hid = (new_t.shape[1] - dp) // 2
     new_s, new_p, new_o = new_t[:, :hid], new_t[:, hid:hid + dp], new_t[:, hid + dp:]   # :156-158
-    pooled = torch.zeros(n_obj, hid, dtype=obj_vecs.dtype)
+    pooled = torch.zeros(n_obj, hid, dtype=obj_vecs.dtype, device=obj_vecs.device)
     pooled = pooled.index_add(0, s_idx, new_s)                  # scatter_add, graph.py:176
     pooled = pooled.index_add(0, o_idx, new_o)                  # graph.py:177
-    counts = torch.zeros(n_obj, dtype=obj_vecs.dtype)
-    ones = torch.ones(n_tri, dtype=obj_vecs.dtype)
+    counts = torch.zeros(n_obj, dtype=obj_vecs.dtype, device=obj_vecs.device)
+    ones = torch.ones(n_tri, dtype=obj_vecs.dtype, device=obj_vecs.device)
     counts = counts.index_add(0, s_idx, ones).index_add(0, o_idx, ones)    # :191-192
     pooled = pooled / counts.clamp(min=1).view(-1, 1)           # :198-199
     new_obj = gcn_mlp(sd, p + "net2", pooled)                   # :203
@@ -107,7 +107,7 @@ def edges_of(triples: Tensor) -> Tuple[Tensor, Tensor]:
 def timestep_embedding(t: Tensor, dim: int, max_period: float = 10000.0) -> Tensor:
     """[cos(t f) | sin(t f)], f_i = exp(-ln(max_period) i / half).  ldm_diffusion_util.py:174-194."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32, device=t.device) / half)
     args = t[:, None].float() * freqs[None]
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     if dim % 2:
