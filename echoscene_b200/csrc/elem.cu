@@ -871,8 +871,9 @@ void attention_f32(const float* qkv, int n, int tokens, int heads, int dh, float
 
 // ---- GroupNorm statistics from the producing GEMM's column partials (gemm_tc.cu epilogue) ---------------------------
 namespace {
-// GroupNorm(+SiLU) whose statistics come from the column partials the producing tcgen05 GEMM left behind
-// ([obj][rows_per_obj tiles][C][2] = per-tile (sum, sumsq) per channel): every block first folds the partials of ITS
+// GroupNorm(+SiLU) whose statistics come from the partials the producing tcgen05 GEMM left behind
+// ([obj][rows_per_obj tiles][C/32 chunks][8 slots][2] = per-tile (sum, sumsq) of 7-channel blocks; every group of this
+// network is a whole number of such blocks because the channel counts are multiples of 224): every block first folds the partials of ITS
 // object into per-group (mean, rstd) in shared memory (fp64, fixed order), then streams its rows.  No statistics kernel
 // and no statistics pass over the activation.  The input may be the channel concat [A | B] of two tensors (skip
 // connections, openai_model_3d.py:857-858): both are read in place and the raw concat is written next to the
@@ -887,23 +888,36 @@ __global__ void __launch_bounds__(256) gn_apply_cs_kernel(const __nv_bfloat16* _
   griddep_wait();
   const int C = CA + CB, obj = blockIdx.y, cpg = C / groups;
   float* gst = reinterpret_cast<float*>(gn_sm + 2 * C);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const bool in_a = c < CA;
-    const float* src = in_a ? csa + ((int64_t)obj * R * CA + c) * 2 : csb + ((int64_t)obj * R * CB + (c - CA)) * 2;
-    const int64_t ld = (in_a ? CA : CB) * 2;
-    double a = 0.0, b = 0.0;
+  // phase 1: totals of every 7-channel block over the object's R tile partials.  A partial row is [chunk][8 slots][2]:
+  // slot s of 32-column chunk q holds the part of block 32q/7 + s that lies inside the chunk (gemm_tc.cu epilogue).
+  const int nblocks = C / 7;
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+    const bool in_a = b * 7 < CA;
+    const int lb = in_a ? b : b - CA / 7;                 // block index inside its producer
+    const int nch = (in_a ? CA : CB) >> 5;
+    const float* src = (in_a ? csa : csb) + (int64_t)obj * R * nch * 16;
+    const int q1 = (lb * 7) >> 5, q2 = (lb * 7 + 6) >> 5;
+    const int i1 = (q1 * 8 + (lb - (q1 * 32) / 7)) * 2, i2 = (q2 * 8 + (lb - (q2 * 32) / 7)) * 2;
+    double a = 0.0, bsum = 0.0;
     for (int r = 0; r < R; ++r) {
-      const float2 v = *reinterpret_cast<const float2*>(src + r * ld);
+      const float* row = src + (int64_t)r * nch * 16;
+      const float2 v = *reinterpret_cast<const float2*>(row + i1);
       a += (double)v.x;
-      b += (double)v.y;
+      bsum += (double)v.y;
+      if (q2 != q1) {
+        const float2 w = *reinterpret_cast<const float2*>(row + i2);
+        a += (double)w.x;
+        bsum += (double)w.y;
+      }
     }
-    gn_sm[2 * c] = a;
-    gn_sm[2 * c + 1] = b;
+    gn_sm[2 * b] = a;
+    gn_sm[2 * b + 1] = bsum;
   }
   __syncthreads();
   if (threadIdx.x < groups) {
+    const int bpg = cpg / 7;
     double a = 0.0, b = 0.0;
-    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) { a += gn_sm[2 * c]; b += gn_sm[2 * c + 1]; }
+    for (int k = threadIdx.x * bpg; k < (threadIdx.x + 1) * bpg; ++k) { a += gn_sm[2 * k]; b += gn_sm[2 * k + 1]; }
     const double mean = a / count;
     double var = b / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -958,8 +972,8 @@ __global__ void __launch_bounds__(256) gn_apply_cs_kernel(const __nv_bfloat16* _
 
 bool gn_apply_cs_supported(const Act& xa, const Act* xb, const Act& out) {
   const int C = xa.c + (xb ? xb->c : 0);
-  if (xa.dt != BF16 || out.dt != BF16 || !xa.colsum || xa.c % 8 || C % 32 || C / 8 > 256 || out.c != C) return false;
-  if (xb && (xb->dt != BF16 || !xb->colsum || xb->c % 8 || xb->colsum_rows != xa.colsum_rows || xb->rows() != xa.rows())) return false;
+  if (xa.dt != BF16 || out.dt != BF16 || !xa.colsum || xa.c % 224 || C % 224 || C / 8 > 256 || out.c != C) return false;
+  if (xb && (xb->dt != BF16 || !xb->colsum || xb->c % 224 || xb->colsum_rows != xa.colsum_rows || xb->rows() != xa.rows())) return false;
   return true;
 }
 

@@ -40,8 +40,11 @@ constexpr int MAX_STAGES = 12;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;       // 16 KiB
 constexpr int SMEM_LIMIT = 227 * 1024;                     // opt-in dynamic shared memory per CTA on sm_100
 constexpr int NUM_THREADS = 384;
-constexpr int SMEM_CS_BYTES = 2 * 2 * 4 * 32 * 8;          // column-statistics exchange: [col group][parity][warp][32] float2
-constexpr int SMEM_FIXED = 1024 /*align*/ + 512 /*barriers + tmem ptr*/ + SMEM_CS_BYTES;
+constexpr int CS_SB = 7;                                   // channels per statistics block (see the epilogue): C % 224 == 0
+constexpr int CS_SLOTS = 8;                                // block slots per 32-column chunk (at most 6 are live)
+constexpr int SMEM_CS_BYTES = 2 * 4 * (MAX_BLOCK_N / 32) * CS_SLOTS * 8;   // [sub-block parity][row-quarter warp][chunk][slot] float2
+constexpr int SMEM_ADD_BYTES = 2 * 2 * MAX_BLOCK_N * 4;    // per-column epilogue addend (bias + rowvec): [tile parity][sub-block][column]
+constexpr int SMEM_FIXED = 1024 /*align*/ + 512 /*barriers + tmem ptr*/ + SMEM_CS_BYTES + SMEM_ADD_BYTES;
 // bytes in flight per SM is what hides the L2 latency of the TMA stream: use every stage that fits
 static inline int stages_for(int b_rows, int msub) {
   const int st = (SMEM_LIMIT - SMEM_FIXED) / (msub * A_STAGE_BYTES + b_rows * BLOCK_K * 2);
@@ -75,8 +78,9 @@ struct TcParams {
   int out_bf16;
   long long ldo;
   int relu;
-  float* colsum;   // optional [num_m_tiles][cout][2] per-column (sum, sumsq) partials for the next GroupNorm
+  float* colsum;   // optional [num_m_tiles][cout/32 chunks][8 slots][2]: (sum, sumsq) of the 7-channel blocks each chunk touches
   int out_t;   // bf16 output stored transposed per object: out[(obj * cout + n) * voxels + voxel] (V^T for the tcgen05 attention)
+  unsigned long long* dbg;   // optional timeline of CTA 0 (globaltimer ns): see tc_timeline_*
   int geglu;   // epilogue: tile columns are [a (block_n/2) | g (block_n/2)]; out = (a+ba) * gelu_erf(g+bg), out width cout/2
 };
 
@@ -99,6 +103,23 @@ __device__ __forceinline__ float gelu_erf_fast(float g) {
   return 0.5f * g * (1.f + erf_s);
 }
 
+// Sum of 8 per-lane values over the 32 lanes: three halving stages (8 -> 4 -> 2 -> 1 values) and two plain ones; on return
+// v[0] of lane l is the total of element l >> 2 (9 shuffles).
+__device__ __forceinline__ void slot_butterfly(float (&v)[8], int lane) {
+#pragma unroll
+  for (int off = 16, n = 8; off >= 4; off >>= 1, n >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = up ? v[i] : v[i + n / 2];
+      const float keep = up ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 // Halving butterfly over the 32 lanes: on return v[0] of lane l is the sum over all lanes of element l.
 __device__ __forceinline__ void col_butterfly(float (&v)[32], int lane) {
 #pragma unroll
@@ -115,6 +136,17 @@ __device__ __forceinline__ void col_butterfly(float (&v)[32], int lane) {
 
 
 // Where the output rows of one 128-row sub-block live: box coordinates inside the object grid.
+// debug timeline: CTA 0 appends (tag, globaltimer) pairs; tags: 1 setup done, 2 TMA issued first stage of a tile, 3 MMA saw the
+// first full stage of a tile, 4 MMA committed a tile, 5 epilogue got a tile, 6 epilogue finished a tile, 7 kernel end
+__device__ __forceinline__ void dbg_mark(const TcParams& p, int tag, int tile) {
+  if (p.dbg && blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned long long i = atomicAdd(p.dbg, 1ULL);
+    if (i < 4000) { p.dbg[1 + 2 * i] = ((unsigned long long)tag << 32) | (unsigned)tile; p.dbg[2 + 2 * i] = t; }
+  }
+}
+
 struct SubTile {
   int obj, w0, h0, d0, phase, m_blk;
 };
@@ -158,6 +190,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]       (CTA2: the leader's copy is the one in use)
   uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * STAGES + 4);
   float2* cs_smem = (float2*)((uint8_t*)bars + 512);
+  float* add_smem = (float*)((uint8_t*)bars + 512 + SMEM_CS_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
@@ -183,6 +216,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   griddep_wait();                 // everything above overlapped the predecessor's tail; from here on we read its output
+  if (threadIdx.x == 0) dbg_mark(p, 1, 0);
 
   // tile schedule: CTA tiles of MSUB sub-blocks; CTA2 walks (n_blk, m_pair) pairs, this CTA owning m index 2*m_pair + rank
   const int cta_m_tiles = p.vm_tiles / MSUB;
@@ -210,6 +244,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int n_row0 = n_blk * p.block_n + (CTA2 ? (int)rank * B_ROWS : 0);
         // all sub-blocks of a tile share the phase (host checks); split-K walks its own group of taps
         const int tap_begin = st[0].phase * p.taps + ks * taps_per_split, tap_end = tap_begin + taps_per_split;
+        dbg_mark(p, 2, tile);
         for (int tap = tap_begin; tap < tap_end; ++tap) {
           for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -254,6 +289,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kb = 0; kb < p.kblocks_per_tap; ++kb, ++kb_total) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (kb_total == 0 && lane == 0) dbg_mark(p, 3, tile);
           if (elect_one()) {
             const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
             int nk = (p.cin - kb * BLOCK_K + UMMA_K - 1) / UMMA_K;   // skip the zero-filled channel tail
@@ -280,6 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if (lane == 0) dbg_mark(p, 4, tile);
     }
   } else if (warp >= 4) {
     // ================= epilogue: TMEM -> registers -> global =================
@@ -295,8 +332,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int ks = tile / mn_tiles, tmn = tile - ks * mn_tiles;
       const int n_blk = tmn / sched_m, mm = tmn - n_blk * sched_m;
       const int m_cta = CTA2 ? 2 * mm + (int)rank : mm;
+      // per-column addend (bias + this object's rowvec) of each sub-block, staged in shared memory while the main loop
+      // of this tile is still running: the epilogue proper then has no global round trip per chunk besides the residual
+      float* addv = add_smem + (iter & 1) * 2 * MAX_BLOCK_N;
+      const bool use_add = !p.geglu && (p.bias || p.rowvec);
+      if (use_add) {
+        const int t = threadIdx.x - 128;
+#pragma unroll
+        for (int sub = 0; sub < MSUB; ++sub) {
+          if (t < p.block_n) {
+            const int n = n_blk * p.block_n + t;
+            float a = 0.f;
+            if (n < p.cout) {
+              if (p.bias) a = __ldg(p.bias + n);
+              if (p.rowvec) a += __ldg(p.rowvec + (long long)sub_tile(p, m_cta * MSUB + sub).obj * p.ld_rowvec + n);
+            }
+            addv[sub * MAX_BLOCK_N + t] = a;
+          }
+        }
+        asm volatile("bar.sync 3, 256;" ::: "memory");   // the eight epilogue warps
+      }
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
+      if (threadIdx.x == 128) dbg_mark(p, 5, tile);
 #pragma unroll 1
       for (int sub = 0; sub < MSUB; ++sub) {
       const SubTile stl = sub_tile(p, m_cta * MSUB + sub);
@@ -311,149 +369,196 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (p.geglu) {
         // GEGLU fused into the producing GEMM (attention.py:39-46): the weight rows were permuted at load time so that
         // one tile holds 128 `a` columns followed by their 128 gate columns
-        const int half = p.block_n >> 1;
-        for (int c = 32 * cg; c < half; c += 64) {
-          uint32_t va[32], vg[32];
-          tmem_ld32(taddr + c, va);
-          tmem_ld32(taddr + half + c, vg);
-          tmem_ld_wait();
-          if (valid) {
-            const float* ba = p.bias + n_base + c;
-            const float* bg = p.bias + n_base + half + c;
-            float f[32];
+        // This epilogue is what bounds the ff1 contraction (K = C is short): it runs in 16-column pieces, the TMEM read of
+        // piece i+1 in flight while piece i is evaluated, biases fetched as float4.  Pieces of this warp: columns
+        // 32*cg + 64*k + {0, 16} of the `a` half (block_n = 256 -> four pieces).
+        const int half = p.block_n >> 1;   // 128
+        uint32_t va[2][16], vg[2][16];
+        tmem_ld16(taddr + 32 * cg, va[0]);
+        tmem_ld16(taddr + half + 32 * cg, vg[0]);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float a = __uint_as_float(va[j]) + __ldg(ba + j);
-              const float g = __uint_as_float(vg[j]) + __ldg(bg + j);
-              f[j] = a * gelu_erf_fast(g);
+        for (int i = 0; i < 4; ++i) {
+          const int c = 32 * cg + 64 * (i >> 1) + 16 * (i & 1);
+          tmem_ld_wait();
+          if (i + 1 < 4) {
+            const int cn = 32 * cg + 64 * ((i + 1) >> 1) + 16 * ((i + 1) & 1);
+            tmem_ld16(taddr + cn, va[(i + 1) & 1]);
+            tmem_ld16(taddr + half + cn, vg[(i + 1) & 1]);
+          }
+          if (valid) {
+            const float4* ba = reinterpret_cast<const float4*>(p.bias + n_base + c);
+            const float4* bg = reinterpret_cast<const float4*>(p.bias + n_base + half + c);
+            uint32_t w8[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 b1 = __ldg(ba + q), b2 = __ldg(bg + q);
+              const float a0 = __uint_as_float(va[i & 1][4 * q]) + b1.x, a1 = __uint_as_float(va[i & 1][4 * q + 1]) + b1.y;
+              const float a2 = __uint_as_float(va[i & 1][4 * q + 2]) + b1.z, a3 = __uint_as_float(va[i & 1][4 * q + 3]) + b1.w;
+              const float g0 = __uint_as_float(vg[i & 1][4 * q]) + b2.x, g1 = __uint_as_float(vg[i & 1][4 * q + 1]) + b2.y;
+              const float g2 = __uint_as_float(vg[i & 1][4 * q + 2]) + b2.z, g3 = __uint_as_float(vg[i & 1][4 * q + 3]) + b2.w;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(a0 * gelu_erf_fast(g0), a1 * gelu_erf_fast(g1));
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(a2 * gelu_erf_fast(g2), a3 * gelu_erf_fast(g3));
+              w8[2 * q] = *reinterpret_cast<uint32_t*>(&h0);
+              w8[2 * q + 1] = *reinterpret_cast<uint32_t*>(&h1);
             }
             uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + n_blk * half + c);
+            op[0] = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+            op[1] = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+          }
+        }
+      } else {
+        // 32-column chunks c = 32*cg + 64*k (k < 4).  Software pipeline: the residual rows of chunk k+1 are requested
+        // before chunk k is evaluated (an L2 round trip each), the per-column addends come from shared memory.
+        const bool res16 = p.res && p.res_bf16;
+        const __nv_bfloat16* res_row = res16 ? reinterpret_cast<const __nv_bfloat16*>(p.res) + orow * p.ld_res + n_base : nullptr;
+        float2* csb = cs_smem + (cs_par * 4 + ew) * (MAX_BLOCK_N / 32) * CS_SLOTS;
+        uint4 rres[2][4];
+        const int c0 = 32 * cg;
+        if (c0 < p.block_n) {
+          if (res16 && valid && n_base + c0 < p.cout) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint32_t w4[4];
+            for (int q = 0; q < 4; ++q) rres[0][q] = __ldg(reinterpret_cast<const uint4*>(res_row + c0) + q);
+          }
+        }
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[q * 8 + e * 2], f[q * 8 + e * 2 + 1]);
-                w4[e] = *reinterpret_cast<uint32_t*>(&h2);
+        for (int k = 0; k < 4; ++k) {
+          const int c = 32 * cg + 64 * k;
+          if (c >= p.block_n) break;
+          const int n0 = n_base + c;
+          uint32_t v[32];
+          tmem_ld32(taddr + c, v);
+          const int cn = c + 64;
+          if (k + 1 < 4 && cn < p.block_n) {
+            if (res16 && valid && n_base + cn < p.cout) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) rres[(k + 1) & 1][q] = __ldg(reinterpret_cast<const uint4*>(res_row + cn) + q);
+            }
+          }
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = 0.f;
+          if (valid && n0 < p.cout) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (use_add) {
+              const float4* ap = reinterpret_cast<const float4*>(addv + sub * MAX_BLOCK_N + c);
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b = ap[j >> 2];
+                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
               }
-              op[q] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
             }
-          }
-        }
-      } else
-      for (int c = 32 * cg; c < p.block_n; c += 64) {
-        const int n0 = n_base + c;
-        // bf16 residual of this chunk: requested BEFORE the TMEM read so its L2 round trip overlaps it (the epilogue of a
-        // short-K contraction is a chain of such round trips)
-        uint4 rres[4];
-        const bool has_res = p.res && p.res_bf16 && valid && n0 < p.cout;
-        if (has_res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + orow * p.ld_res + n0);
+            if (p.res) {
+              if (p.res_bf16) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) rres[q] = __ldg(rp + q);
-        }
-        uint32_t v[32];
-        tmem_ld32(taddr + c, v);
-        tmem_ld_wait();
-        float f[32];
+                for (int q = 0; q < 4; ++q) {
+                  const uint4 u = rres[k & 1][q];
+                  const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = 0.f;
-        if (valid && n0 < p.cout) {
+                  for (int e = 0; e < 4; ++e) {
+                    const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[e]);
+                    f[q * 8 + e * 2] += __low2float(h2);
+                    f[q * 8 + e * 2 + 1] += __high2float(h2);
+                  }
+                }
+              } else {
+                const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + orow * p.ld_res + n0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-            }
-          }
-          if (p.rowvec) {
-            const float* rv = p.rowvec + (long long)obj * p.ld_rowvec + n0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(rv + j));
-              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-            }
-          }
-          if (p.res) {
-            if (p.res_bf16) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 u = rres[q];
-                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[e]);
-                  f[q * 8 + e * 2] += __low2float(h2);
-                  f[q * 8 + e * 2 + 1] += __high2float(h2);
+                for (int q = 0; q < 8; ++q) {
+                  const float4 u = __ldg(rp + q);
+                  f[q * 4] += u.x; f[q * 4 + 1] += u.y; f[q * 4 + 2] += u.z; f[q * 4 + 3] += u.w;
                 }
               }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (p.out_t) {
+              // lanes are consecutive voxels of one object: each column is a 64-byte run of the transposed tensor
+              const long long vox = (long long)p.od * p.oh * p.ow;
+              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + ((long long)obj * p.cout + n0) * vox + (orow - (long long)obj * vox);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) op[(long long)j * vox] = __float2bfloat16(f[j]);
+            } else if (p.out_bf16) {
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + n0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint32_t w4[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(f[q * 8 + e * 2], f[q * 8 + e * 2 + 1]);
+                  w4[e] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                op[q] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+              }
             } else {
-              const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + orow * p.ld_res + n0);
+              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + n0);
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 u = __ldg(rp + q);
-                f[q * 4] += u.x; f[q * 4 + 1] += u.y; f[q * 4 + 2] += u.z; f[q * 4 + 3] += u.w;
-              }
+              for (int q = 0; q < 8; ++q) op[q] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
             }
           }
-          if (p.relu) {
+          if (p.colsum) {
+            // GroupNorm statistics of the NEXT layer, gathered here instead of in a pass over the activation.  Every
+            // GroupNorm group of this network is a run of whole 7-channel blocks (channel counts are multiples of 224 =
+            // 32 groups x 7), so each thread first folds its row's 32 values into the <= 6 blocks this chunk touches
+            // (block b0 + s <-> slot s, b0 = 32q / 7; `off` = position of the chunk's first column inside its block) and
+            // only those slot sums cross lanes: 18 shuffles per chunk instead of 62.
+            const int off = n0 % CS_SB;
+            float tot[5], lo[5], qtot[5], qlo[5];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (p.out_t) {
-            // lanes are consecutive voxels of one object: each column is a 64-byte run of the transposed tensor
-            const long long vox = (long long)p.od * p.oh * p.ow;
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + ((long long)obj * p.cout + n0) * vox + (orow - (long long)obj * vox);
+            for (int a = 0; a < 5; ++a) tot[a] = lo[a] = qtot[a] = qlo[a] = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) op[(long long)j * vox] = __float2bfloat16(f[j]);
-          } else if (p.out_bf16) {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + n0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint32_t w4[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[q * 8 + e * 2], f[q * 8 + e * 2 + 1]);
-                w4[e] = *reinterpret_cast<uint32_t*>(&h2);
+            for (int j = 0; j < 32; ++j) {
+              const int a = j / CS_SB, r = j % CS_SB;
+              tot[a] += f[j];
+              qtot[a] = fmaf(f[j], f[j], qtot[a]);
+              if (r + off < CS_SB) {   // still inside slot a; otherwise it already belongs to slot a + 1
+                lo[a] += f[j];
+                qlo[a] = fmaf(f[j], f[j], qlo[a]);
               }
-              op[q] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
             }
-          } else {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + n0);
+            float ss[8], sq[8];
+            ss[0] = lo[0]; sq[0] = qlo[0];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) op[q] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+            for (int k = 1; k < 5; ++k) { ss[k] = (tot[k - 1] - lo[k - 1]) + lo[k]; sq[k] = (qtot[k - 1] - qlo[k - 1]) + qlo[k]; }
+            ss[5] = tot[4] - lo[4]; sq[5] = qtot[4] - qlo[4];
+            ss[6] = ss[7] = sq[6] = sq[7] = 0.f;
+            slot_butterfly(ss, lane);
+            slot_butterfly(sq, lane);
+            if ((lane & 3) == 0) csb[(c >> 5) * CS_SLOTS + (lane >> 2)] = make_float2(ss[0], sq[0]);
           }
         }
         if (p.colsum) {
-          // per-column (sum, sum of squares) over the sub-block's 128 voxels -> partial row m_blk: the next GroupNorm's
-          // statistics come from these instead of a separate pass over the activation.  Lanes hold the sums over
-          // their warp's 32 voxels after the butterflies; the four warps of this column group meet in shared memory
-          // (fixed summation order -> run-to-run reproducible).
-          float q2[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) q2[j] = f[j] * f[j];
-          col_butterfly(f, lane);
-          col_butterfly(q2, lane);
-          float2* buf = cs_smem + ((cg * 2 + cs_par) * 4) * 32;
-          buf[ew * 32 + lane] = make_float2(f[0], q2[0]);
+          // -> partial row of this sub-block, [chunk][slot] (sum, sumsq).  One barrier per sub-block for the four warps of
+          // this column group, fixed summation order (run-to-run reproducible); buffers alternate between sub-blocks so
+          // nobody waits for the readers.
           asm volatile("bar.sync %0, 128;" ::"r"(1 + cg) : "memory");
-          if (ew == 0 && n0 + lane < p.cout) {
-            const float2 a0 = buf[lane], a1 = buf[32 + lane], a2 = buf[64 + lane], a3 = buf[96 + lane];
-            *reinterpret_cast<float2*>(p.colsum + (cs_row * p.cout + n0 + lane) * 2) =
-                make_float2((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y));
+          const int t = ew * 32 + lane;                              // 0..127 within the column group
+          if (t < 4 * CS_SLOTS) {                                    // (chunk k of this group, slot)
+            const int c = 32 * cg + 64 * (t / CS_SLOTS), slot = t % CS_SLOTS;
+            if (c < p.block_n && n_base + c < p.cout) {
+              constexpr int WS = (MAX_BLOCK_N / 32) * CS_SLOTS;        // one warp's region
+              const float2* b0 = cs_smem + (cs_par * 4) * WS + (c >> 5) * CS_SLOTS + slot;
+              const float2 a0 = b0[0], a1 = b0[WS], a2 = b0[2 * WS], a3 = b0[3 * WS];
+              const long long nchunks = p.cout >> 5;
+              *reinterpret_cast<float2*>(p.colsum + ((cs_row * nchunks + ((n_base + c) >> 5)) * CS_SLOTS + slot) * 2) =
+                  make_float2((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y));
+            }
           }
           cs_par ^= 1;
         }
       }
       }   // sub
+      if (threadIdx.x == 128) dbg_mark(p, 6, tile);
       tc_fence_before();
       if (CTA2 && !leader) mbar_arrive_remote(&tmem_empty[as], 0);   // the leader's MMA warp owns the accumulator ring
       else mbar_arrive(&tmem_empty[as]);
     }
   }
 
+  if (threadIdx.x == 0) dbg_mark(p, 7, 0);
   tc_fence_before();
   if (CTA2) cluster_sync_all(); else __syncthreads();   // (pair) nobody still signals a barrier or reads TMEM of an exited CTA
   if (warp == 2) {
@@ -673,10 +778,25 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 #pragma unroll
   for (int j = 0; j < 8; ++j) red[rl][c8 * 8 + j] = make_float2(sum[j], sq[j]);
   __syncthreads();
-  if (threadIdx.x < 64 && blockIdx.y * 64 + threadIdx.x < cout) {
+  __shared__ float2 colt[64];
+  if (threadIdx.x < 64) {
     float a = 0.f, b = 0.f;
-    for (int r = 0; r < 32; ++r) { a += red[r][threadIdx.x].x; b += red[r][threadIdx.x].y; }
-    *reinterpret_cast<float2*>(colsum + ((long long)blockIdx.x * cout + blockIdx.y * 64 + threadIdx.x) * 2) = make_float2(a, b);
+    if (blockIdx.y * 64 + threadIdx.x < cout)
+      for (int r = 0; r < 32; ++r) { a += red[r][threadIdx.x].x; b += red[r][threadIdx.x].y; }
+    colt[threadIdx.x] = make_float2(a, b);
+  }
+  __syncthreads();
+  // same partial-row format as the single-pass epilogue: [row tile][32-column chunk][slot] = sums of the 7-channel blocks
+  if (threadIdx.x < 2 * CS_SLOTS) {
+    const int ql = threadIdx.x / CS_SLOTS, slot = threadIdx.x % CS_SLOTS;
+    const int q = blockIdx.y * 2 + ql, n0 = 32 * q;
+    if (n0 < cout) {
+      const int b = n0 / CS_SB + slot;
+      const int lo = max(n0, b * CS_SB), hi = min(min(n0 + 32, (b + 1) * CS_SB), cout);
+      float a = 0.f, bb = 0.f;
+      for (int c = lo; c < hi; ++c) { a += colt[c - blockIdx.y * 64].x; bb += colt[c - blockIdx.y * 64].y; }
+      *reinterpret_cast<float2*>(colsum + (((long long)blockIdx.x * (cout >> 5) + q) * CS_SLOTS + slot) * 2) = make_float2(a, bb);
+    }
   }
 }
 
@@ -688,6 +808,7 @@ void set_tc_mode(int m) { g_tc_mode = m; }
 //      contraction shape while a real step runs, so the kernel is timed warm, between its actual neighbours ----
 namespace {
 struct TcProbe {
+  unsigned long long* timeline = nullptr;   // device buffer handed to the NEXT probed launch (then cleared)
   bool on = false;
   long long rows = 0;
   int cin = 0, cout = 0, k = 0;
@@ -701,6 +822,9 @@ void tc_probe_begin(long long rows, int cin, int cout, int k) {
   g_probe.rows = rows; g_probe.cin = cin; g_probe.cout = cout; g_probe.k = k;
   g_probe.used = 0;
 }
+
+// the next probed launch records the timeline of its CTA 0 into `buf` (device, >= 8001 u64, zeroed by the caller)
+void tc_probe_timeline(unsigned long long* buf) { g_probe.timeline = buf; }
 
 // average milliseconds per probed launch and the number of launches seen (call after the stream has been synchronised)
 int tc_probe_end(double* avg_ms) {
@@ -741,6 +865,9 @@ int gemm_tc_colsum_rows_per_obj(const GemmArgs& g) {
   const TcGeom ge = tc_geom(t);
   return ge.vm_tiles;
 }
+
+// floats of one partial row ([chunk][slot][2]) for `c` channels; 0 if c does not decompose into 7-channel blocks per group
+size_t gemm_tc_colsum_row_floats(int c) { return c % (32 * CS_SB) == 0 ? (size_t)(c / 32) * CS_SLOTS * 2 : 0; }
 
 size_t gemm_tc_splitk_ws_bytes(const GemmArgs& g) {
   if (!tc_available() || g.kd != 3 || g.sh != 1 || g.up2 || g.epi) return 0;
@@ -891,6 +1018,7 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   const int smem_bytes = p.stages * (msub * A_STAGE_BYTES + b_rows * BLOCK_K * 2) + SMEM_FIXED;
   const bool probed = g_probe.on && g.rows_out() == g_probe.rows && g.cin == g_probe.cin && g.cout == g_probe.cout && g.kd == g_probe.k &&
                       !g.up2 && g.sh == 1;
+  if (probed && g_probe.timeline) { p.dbg = g_probe.timeline; g_probe.timeline = nullptr; }
   if (probed) {
     if (g_probe.used == g_probe.ev.size()) {
       cudaEvent_t a, b;

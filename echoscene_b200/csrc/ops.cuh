@@ -56,8 +56,12 @@ bool tc_available();
 // timing probe: CUDA events around every gemm_tc launch of one shape while steps run (bench.py roofline)
 void tc_probe_begin(long long rows, int cin, int cout, int k);
 int tc_probe_end(double* avg_ms);
+void tc_probe_timeline(unsigned long long* buf);
 // rows of the column-sum partial buffer per OBJECT for this problem (the tcgen05 kernel writes one per 128-voxel tile)
 int gemm_tc_colsum_rows_per_obj(const GemmArgs& g);
+// floats of one partial row for a tensor with c channels: [c/32 chunks][8 slots][2] -- (sum, sumsq) of the 7-channel blocks
+// every 32-column chunk touches (slot s of chunk q <-> block 32q/7 + s); 0 when c is not a multiple of 224 (32 groups x 7)
+size_t gemm_tc_colsum_row_floats(int c);
 // bytes of fp32 workspace that let gemm_tc() split the reduction of this problem (0: never split)
 size_t gemm_tc_splitk_ws_bytes(const GemmArgs& g);
 // GroupNorm(+SiLU) with the statistics folded from the producer's column partials inside the apply kernel; `xb` != null:

@@ -58,11 +58,11 @@ struct echo_shape {
   // activation whose producer (a tcgen05 GEMM) also emits the column partials the consuming GroupNorm needs
   Act new_act_cs(int n, int dd, int h, int w, int c, DT dt, bool up2 = false) {
     Act a = new_act(n, dd, h, w, c, dt);
-    if (prec == ECHO_PREC_BF16 && dt == BF16 && c % 32 == 0 && (dry || tc_available())) {
+    if (prec == ECHO_PREC_BF16 && dt == BF16 && gemm_tc_colsum_row_floats(c) && (dry || tc_available())) {
       GemmArgs g;
       g.od = dd; g.oh = h; g.ow = w; g.up2 = up2 ? 1 : 0;
       a.colsum_rows = gemm_tc_colsum_rows_per_obj(g);
-      a.colsum = arena.alloc_n<float>((size_t)n * a.colsum_rows * c * 2);
+      a.colsum = arena.alloc_n<float>((size_t)n * a.colsum_rows * gemm_tc_colsum_row_floats(c));
     }
     return a;
   }

@@ -123,6 +123,9 @@ ECHO_API void echo_debug_set_tc_mode(int mode);
  * launches seen and their average duration in milliseconds (synchronise the stream first). */
 ECHO_API void echo_debug_probe_begin(int64_t rows, int32_t cin, int32_t cout, int32_t ksize);
 ECHO_API int32_t echo_debug_probe_end(double* avg_ms);
+/* The next probed launch writes the timeline of its first CTA (tag << 32 | tile, globaltimer ns pairs after a count word)
+ * into buf_dev (device memory, >= 8001 x 8 bytes, zeroed by the caller): where a tile's time goes (tools/gemm_timeline.py). */
+ECHO_API void echo_debug_probe_timeline(void* buf_dev);
 
 /* ---- graph: edges = stack([s, o]) of `triples` (T,3) int64 [s,p,o] — denoise_net.py:759-761, graph.py:142-143 */
 ECHO_API int echo_graph_create(echo_graph_t** out, const int64_t* triples_dev, int32_t n_triples, int32_t n_nodes, void* stream);
