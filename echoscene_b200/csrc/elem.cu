@@ -942,11 +942,20 @@ __global__ void __launch_bounds__(256) gn_apply_cs_kernel(const __nv_bfloat16* _
   const __nv_bfloat16* xs = (in_a ? xa + c0 : xb + (c0 - CA)) + ((int64_t)obj * V) * Cs;
   __nv_bfloat16* yb = y + ((int64_t)obj * V) * C + c0;
   __nv_bfloat16* cb = ycat ? ycat + ((int64_t)obj * V) * C + c0 : nullptr;
+  // software pipeline: the four rows of the NEXT pass are requested before this pass is evaluated (a pass is one memory
+  // round trip otherwise, and this kernel is then latency-, not bandwidth-bound)
+  uint4 un[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (r0 + ry + k * RY < r1) un[k] = __ldg(reinterpret_cast<const uint4*>(xs + (r0 + ry + k * RY) * Cs));
   for (int64_t r = r0 + ry; r < r1; r += 4 * RY) {
     uint4 u[4];
 #pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = un[k];
+    const int64_t rn = r + 4 * RY;
+#pragma unroll
     for (int k = 0; k < 4; ++k)
-      if (r + k * RY < r1) u[k] = __ldg(reinterpret_cast<const uint4*>(xs + (r + k * RY) * Cs));
+      if (rn + k * RY < r1) un[k] = __ldg(reinterpret_cast<const uint4*>(xs + (rn + k * RY) * Cs));
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (r + k * RY >= r1) break;
