@@ -12,6 +12,8 @@ Reference constructors this mirrors (names/shapes only, no code shared):
   UNet1DModel                            model/networks/diffusion_layout/denoise_net.py:451-756
   UNet3DModel                            model/networks/diffusion_shape/openai_model_3d.py:452-782
   BasicTransformerBlock/SpatialTransformer{1D,3D}  model/networks/diffusion_shape/attention.py:222-396
+  VQVAE (decode path), Decoder3D, VectorQuantizer  model/networks/vqvae_networks/network.py:56-103,
+                                                   vqvae_modules.py:61-195,292-409, quantizer.py:10-43
 """
 from __future__ import annotations
 
@@ -310,6 +312,59 @@ def unet3d_specs(cfg: UNet3DConfig) -> Specs:
 # --------------------------------------------------------------------------------------
 # initialisation
 # --------------------------------------------------------------------------------------
+
+
+@dataclass
+class VQVAEConfig:
+    """model.params of config/vqvae_snet.yaml:5-19 (the decode half)."""
+    embed_dim: int = 3
+    n_embed: int = 8192
+    z_channels: int = 3
+    resolution: int = 64
+    out_ch: int = 1
+    ch: int = 64
+    ch_mult: Tuple[int, ...] = (1, 2, 4)
+    num_res_blocks: int = 1
+
+    @property
+    def latent_size(self) -> int:
+        return self.resolution // 2 ** (len(self.ch_mult) - 1)
+
+
+def _vq_resnet(sp: Dict, name: str, cin: int, cout: int):
+    """ResnetBlock with temb_channels = 0 (vqvae_modules.py:61-127): norm1, conv1, norm2, conv2 (+ 1x1 nin_shortcut)."""
+    _norm(sp, name + ".norm1", cin)
+    _conv(sp, name + ".conv1", cin, cout, 3, 3)
+    _norm(sp, name + ".norm2", cout)
+    _conv(sp, name + ".conv2", cout, cout, 3, 3)
+    if cin != cout:
+        _conv(sp, name + ".nin_shortcut", cin, cout, 1, 3)
+
+
+def vqvae_decode_specs(cfg: VQVAEConfig) -> Specs:
+    """The part of the VQVAE state_dict that `VQVAE.decode_no_quant` touches (network.py:95-103): codebook,
+    post_quant_conv, Decoder3D (vqvae_modules.py:292-409; attn_resolutions = [] -> only mid.attn_1)."""
+    sp: Dict[str, ParamSpec] = OrderedDict()
+    sp["quantize.embedding.weight"] = ParamSpec((cfg.n_embed, cfg.embed_dim), "normal")
+    _conv(sp, "post_quant_conv", cfg.embed_dim, cfg.z_channels, 1, 3)
+    nres = len(cfg.ch_mult)
+    block_in = cfg.ch * cfg.ch_mult[-1]
+    _conv(sp, "decoder.conv_in", cfg.z_channels, block_in, 3, 3)
+    _vq_resnet(sp, "decoder.mid.block_1", block_in, block_in)
+    _norm(sp, "decoder.mid.attn_1.norm", block_in)
+    for n in ("q", "k", "v", "proj_out"):
+        _conv(sp, "decoder.mid.attn_1." + n, block_in, block_in, 1, 3)
+    _vq_resnet(sp, "decoder.mid.block_2", block_in, block_in)
+    for lvl in reversed(range(nres)):
+        block_out = cfg.ch * cfg.ch_mult[lvl]
+        for i in range(cfg.num_res_blocks):
+            _vq_resnet(sp, f"decoder.up.{lvl}.block.{i}", block_in, block_out)
+            block_in = block_out
+        if lvl != 0:
+            _conv(sp, f"decoder.up.{lvl}.upsample.conv", block_in, block_in, 3, 3)
+    _norm(sp, "decoder.norm_out", block_in)
+    _conv(sp, "decoder.conv_out", block_in, cfg.out_ch, 3, 3)
+    return sp
 
 
 def init_tensor(spec: ParamSpec, gen: torch.Generator, rerandomize_zero: bool = False,

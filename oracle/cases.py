@@ -15,6 +15,7 @@ from echoscene_b200 import arch, synth
 WEIGHT_SEED_GCN = 10
 WEIGHT_SEED_LAYOUT = 11
 WEIGHT_SEED_SHAPE = 12
+WEIGHT_SEED_VQVAE = 13
 
 
 @dataclass
@@ -69,3 +70,16 @@ def shape_step_inputs(case: GraphCase, cfg: arch.UNet3DConfig, same_noise: bool 
     uc, x = synth.shape_inputs(case.n_nodes, case.seed + 400, cfg.context_dim, same_noise=same_noise)
     t = torch.tensor([991, 501, 1, 251, 11, 741, 331, 91][: case.n_nodes], dtype=torch.int64)
     return g, uc, x, t
+
+
+def vqvae_cfg() -> arch.VQVAEConfig:
+    return arch.VQVAEConfig()
+
+
+VQVAE_CASE_OBJECTS = 2
+
+
+def vqvae_inputs(n: int = VQVAE_CASE_OBJECTS, seed: int = 6):
+    """latents as the DDIM chain leaves them: (n, 3, 16, 16, 16), O(1) values"""
+    gen = torch.Generator().manual_seed(seed + 500)
+    return torch.randn(n, 3, 16, 16, 16, generator=gen)

@@ -389,3 +389,82 @@ def shape_chain(sd: SD, cfg, uc: Tensor, triples: Tensor, x_T: Tensor, S: int, n
         e_t = unet3d_forward(sd, cfg, x, uc, triples, ts)
         x, _ = ddim_update(sch, x, e_t, total - i - 1)
     return x
+
+
+# --------------------------------------------------------------------------------------
+# VQ-VAE decode: the step right after the shape chain, EchoToShape.rel2shape -> decode_no_quant
+# (echo2shape.py:522; vqvae_networks/network.py:95-103)
+# --------------------------------------------------------------------------------------
+
+
+def vq_quantize(sd: SD, z: Tensor) -> Tuple[Tensor, Tensor]:
+    """VectorQuantizer.forward(z, is_voxel=True) in eval: nearest codebook entry per voxel.  quantizer.py:68-99.
+    z (B, C, D, H, W) -> (z_q (B, C, D, H, W), indices (B*D*H*W,)).  The straight-through form z + (z_q - z) is kept:
+    it is what the reference returns, rounding included."""
+    e = sd["quantize.embedding.weight"]
+    zp = z.permute(0, 2, 3, 4, 1).contiguous()                      # b d h w c
+    zf = zp.view(-1, e.shape[1])
+    d = torch.sum(zf ** 2, dim=1, keepdim=True) + torch.sum(e ** 2, dim=1) - 2 * torch.einsum("bd,dn->bn", zf, e.t())
+    idx = torch.argmin(d, dim=1)
+    z_q = F.embedding(idx, e).view(zp.shape)
+    z_q = zp + (z_q - zp)
+    return z_q.permute(0, 4, 1, 2, 3).contiguous(), idx
+
+
+def _vq_norm(sd: SD, p: str, x: Tensor) -> Tensor:
+    """Normalize(): GroupNorm(32 groups, eps 1e-6, affine) for C in {64, 128, 256}.  vqvae_modules.py:13-22."""
+    return F.group_norm(x, 32, sd[p + ".weight"], sd[p + ".bias"], 1e-6)
+
+
+def _swish(x: Tensor) -> Tensor:
+    return x * torch.sigmoid(x)                                      # vqvae_modules.py:9-11
+
+
+def _conv3(sd: SD, p: str, x: Tensor, pad: int) -> Tensor:
+    return F.conv3d(x, sd[p + ".weight"], sd[p + ".bias"], padding=pad)
+
+
+def vq_resnet_block(sd: SD, p: str, x: Tensor) -> Tensor:
+    """ResnetBlock.forward with temb = None, dropout 0.  vqvae_modules.py:107-127."""
+    h = _conv3(sd, p + ".conv1", _swish(_vq_norm(sd, p + ".norm1", x)), 1)
+    h = _conv3(sd, p + ".conv2", _swish(_vq_norm(sd, p + ".norm2", h)), 1)
+    if (p + ".nin_shortcut.weight") in sd:
+        x = _conv3(sd, p + ".nin_shortcut", x, 0)
+    return x + h
+
+
+def vq_attn_block(sd: SD, p: str, x: Tensor) -> Tensor:
+    """AttnBlock.forward: single-head attention over all voxels, scale C^-0.5.  vqvae_modules.py:158-189."""
+    h_ = _vq_norm(sd, p + ".norm", x)
+    q, k, v = (_conv3(sd, p + "." + n, h_, 0) for n in ("q", "k", "v"))
+    b, c = q.shape[:2]
+    q = q.reshape(b, c, -1).permute(0, 2, 1)
+    k = k.reshape(b, c, -1)
+    w_ = torch.bmm(q, k) * (int(c) ** (-0.5))
+    w_ = F.softmax(w_, dim=2)
+    v = v.reshape(b, c, -1)
+    h_ = torch.bmm(v, w_.permute(0, 2, 1)).reshape(x.shape)
+    return x + _conv3(sd, p + ".proj_out", h_, 0)
+
+
+def vq_decoder(sd: SD, cfg, z: Tensor, p: str = "decoder") -> Tensor:
+    """Decoder3D.forward.  vqvae_modules.py:377-409."""
+    h = _conv3(sd, p + ".conv_in", z, 1)
+    h = vq_resnet_block(sd, p + ".mid.block_1", h)
+    h = vq_attn_block(sd, p + ".mid.attn_1", h)
+    h = vq_resnet_block(sd, p + ".mid.block_2", h)
+    for lvl in reversed(range(len(cfg.ch_mult))):
+        for i in range(cfg.num_res_blocks):
+            h = vq_resnet_block(sd, f"{p}.up.{lvl}.block.{i}", h)
+        if lvl != 0:
+            h = F.interpolate(h, scale_factor=2.0, mode="nearest")  # Upsample, vqvae_modules.py:35-39
+            h = _conv3(sd, f"{p}.up.{lvl}.upsample.conv", h, 1)
+    h = F.gelu(_vq_norm(sd, p + ".norm_out", h))                    # activ = 'gelu' (exact erf), :300-305,404-407
+    return _conv3(sd, p + ".conv_out", h, 1)
+
+
+def vqvae_decode_no_quant(sd: SD, cfg, h: Tensor) -> Tensor:
+    """VQVAE.decode_no_quant(h): quantize -> post_quant_conv -> decoder.  network.py:95-103."""
+    quant, _ = vq_quantize(sd, h)
+    quant = _conv3(sd, "post_quant_conv", quant, 0)
+    return vq_decoder(sd, cfg, quant)

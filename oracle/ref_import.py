@@ -76,4 +76,6 @@ def load():
     ns.ldm_util = u
     s = importlib.import_module("model.networks.diffusion_shape.samplers.ddim")
     ns.DDIMSampler = s.DDIMSampler
+    v = importlib.import_module("model.networks.vqvae_networks.network")
+    ns.VQVAE = v.VQVAE
     return ns

@@ -72,3 +72,23 @@ def test_schedules_closed_form():
     x = torch.randn(4, 8)
     e = torch.randn(4, 8)
     assert torch.equal(orc.ddpm_update(d, x, e, 0, torch.randn(4, 8)), orc.ddpm_update(d, x, e, 0, torch.zeros(4, 8)))
+
+
+def test_vqvae_decode_oracle_vs_reference():
+    """VQVAE.decode_no_quant (quantize -> post_quant_conv -> Decoder3D) against the reference's output for
+    the seeded case of oracle/gen_golden_vqvae.py; one object is decoded here (objects are independent)."""
+    pin = json.load(open(os.path.join(GOLD, "PINNING.json")))["cases"]["vqvae_decode_no_quant"]
+    assert pin["rel_l2"] < 1e-6 and pin["indices_equal"] and pin["quant_equal"]
+    cfg = cases.vqvae_cfg()
+    specs = arch.vqvae_decode_specs(cfg)
+    assert arch.count_params(specs) == pin["params"]
+    sd = arch.make_state_dict(specs, cases.WEIGHT_SEED_VQVAE)
+    z = cases.vqvae_inputs()[:1]
+    G = gold("vqvae_decode.pt")
+    quant, idx = orc.vq_quantize(sd, z)
+    assert torch.equal(idx.to(torch.int32), G["indices"][: idx.numel()])          # integer work: bit-exact
+    assert torch.equal(quant, G["quant"][:1])
+    with torch.no_grad():
+        dec = orc.vqvae_decode_no_quant(sd, cfg, z)
+    assert dec.shape == (1, 1, 64, 64, 64)
+    assert max(rel_err(dec[:, :, ::2, ::2, ::2], G["dec_sub"][:1])) < TOL
