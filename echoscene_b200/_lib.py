@@ -55,6 +55,12 @@ class ShapeDesc(C.Structure):
                 ("linear_end", C.c_float)]
 
 
+class VqvaeDesc(C.Structure):
+    _fields_ = [("embed_dim", C.c_int32), ("n_embed", C.c_int32), ("z_channels", C.c_int32), ("latent_size", C.c_int32),
+                ("ch", C.c_int32), ("num_levels", C.c_int32), ("ch_mult", C.c_int32 * 8), ("num_res_blocks", C.c_int32),
+                ("out_ch", C.c_int32), ("max_objects", C.c_int32), ("precision", C.c_int32)]
+
+
 _P = C.c_void_p
 _I = C.c_int32
 _L = C.c_int64
@@ -90,6 +96,9 @@ PROTOTYPES = {
     "echo_shape_latent": (C.c_int, [_P, _I, _P, _P]),
     "echo_shape_destroy": (None, [_P]),
     "echo_shape_schedule": (C.c_int, [_P, _P, _P]),
+    "echo_vqvae_create": (C.c_int, [C.POINTER(_P), C.POINTER(VqvaeDesc), C.POINTER(Weight), _I]),
+    "echo_vqvae_decode": (C.c_int, [_P, _P, _I, _P, _P, _P]),
+    "echo_vqvae_destroy": (None, [_P]),
     "echo_op_conv3d": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "echo_op_upconv3d": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P]),
     "echo_op_linear": (C.c_int, [_P, _L, _I, _P, _P, _I, _P, _I, _P]),

@@ -26,6 +26,9 @@ void shape_embed(echo_shape*, const float*, int, float*, cudaStream_t);
 void shape_trunk(echo_shape*, const echo_graph*, const float*, int, int, const float*, const float*, const int64_t*, int, float*,
                  cudaStream_t, cudaStream_t);
 const float* shape_latent(const echo_shape*);
+echo_vqvae* vqvae_create(const echo_vqvae_desc_t*, const echo_weight_t*, int);
+void vqvae_destroy(echo_vqvae*);
+void vqvae_decode(echo_vqvae*, const float*, int, float*, int*, cudaStream_t);
 int shape_context_dim(const echo_shape*);
 void shape_tables(const echo_shape*, const std::vector<float>**, const std::vector<int32_t>**);
 bool conv3d_small_cout_supported(int cin, int cout, int taps);
@@ -256,6 +259,20 @@ int echo_shape_latent(const echo_shape_t* h, int32_t n_nodes, float* out_dev, vo
   });
 }
 void echo_shape_destroy(echo_shape_t* h) { shape_destroy(h); }
+
+int echo_vqvae_create(echo_vqvae_t** out, const echo_vqvae_desc_t* desc, const echo_weight_t* weights, int32_t n_weights) {
+  return guard([&] {
+    ECHO_CHECK(out && desc && (weights || n_weights == 0), "vqvae_create: null argument");
+    *out = vqvae_create(desc, weights, n_weights);
+  });
+}
+int echo_vqvae_decode(echo_vqvae_t* h, const float* latents, int32_t n, float* sdf_out, int32_t* indices_out, void* stream) {
+  return guard([&] {
+    ECHO_CHECK(h && (n == 0 || (latents && sdf_out)), "vqvae_decode: null argument");
+    vqvae_decode(h, latents, n, sdf_out, indices_out, (cudaStream_t)stream);
+  });
+}
+void echo_vqvae_destroy(echo_vqvae_t* h) { vqvae_destroy(h); }
 int echo_shape_schedule(const echo_shape_t* h, float* host_coef_out, int32_t* host_ts_out) {
   return guard([&] {
     ECHO_CHECK(h, "shape_schedule: null handle");

@@ -120,19 +120,6 @@ __device__ __forceinline__ void slot_butterfly(float (&v)[8], int lane) {
   v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-// Halving butterfly over the 32 lanes: on return v[0] of lane l is the sum over all lanes of element l.
-__device__ __forceinline__ void col_butterfly(float (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < n / 2; ++i) {
-      const float send = up ? v[i] : v[i + n / 2];
-      const float keep = up ? v[i + n / 2] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-}
 
 
 // Where the output rows of one 128-row sub-block live: box coordinates inside the object grid.

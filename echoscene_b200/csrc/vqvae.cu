@@ -1,0 +1,366 @@
+// VQ-VAE decode: VQVAE.decode_no_quant (vqvae_networks/network.py:95-103) -- the step right after the shape chain
+// (EchoToShape.rel2shape, echo2shape.py:522).  latents (n, 3, 16, 16, 16) -> SDF (n, 1, 64, 64, 64):
+//   VectorQuantizer (quantizer.py:68-99, nearest of 8192 codes per voxel, straight-through value z + (e - z))
+//   -> post_quant_conv 1x1x1 -> Decoder3D (vqvae_modules.py:377-409): conv_in, ResnetBlock, AttnBlock (one head over all
+//   4096 voxels), ResnetBlock, then per level ResnetBlock(s) + nearest x2 upsample + conv, GroupNorm, GELU, conv_out.
+// Same conventions as shape.cu: channels-last activations, one workspace sized by a dry run, every kernel on the
+// caller's stream.  Contractions reuse the implicit-GEMM kernels (tcgen05 in ECHO_PREC_BF16 where the shape allows, fp32
+// FMA otherwise and always in ECHO_PREC_FP32, the parity mode); attention over 4096 tokens x 256 channels uses the fp32
+// kernels in both modes (it is 2 % of the decoder's FLOPs).
+#include "unet.cuh"
+
+#include <math.h>
+
+using namespace echo;
+
+namespace {
+
+// one thread per voxel: squared distance to every code as the reference forms it, d = |z|^2 + |e|^2 - 2 z.e
+// (quantizer.py:79-82), first minimum wins (torch.argmin), value z + (e - z) (:96), then post_quant_conv (network.py:101).
+// Codebook and |e|^2 live in shared memory.  in: NCDHW (n, 3, vox); out: channels-last (n, vox, 3).
+__global__ void __launch_bounds__(256) vq_quantize_kernel(const float* __restrict__ z, long long vox, long long total,
+                                                          const float* __restrict__ codebook, int n_embed, const float* __restrict__ pw,
+                                                          const float* __restrict__ pb, float* __restrict__ out, int* __restrict__ indices) {
+  extern __shared__ float sm[];   // [n_embed][3] codes, [n_embed] squared norms
+  float* ee = sm + 3 * n_embed;
+  for (int i = threadIdx.x; i < n_embed; i += blockDim.x) {
+    const float a = codebook[3 * i], b = codebook[3 * i + 1], c = codebook[3 * i + 2];
+    sm[3 * i] = a; sm[3 * i + 1] = b; sm[3 * i + 2] = c;
+    ee[i] = a * a + b * b + c * c;
+  }
+  __syncthreads();
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long long)gridDim.x * blockDim.x) {
+    const long long obj = v / vox, r = v - obj * vox;
+    const float* zp = z + obj * 3 * vox + r;
+    const float z0 = zp[0], z1 = zp[vox], z2 = zp[2 * vox];
+    const float zz = z0 * z0 + z1 * z1 + z2 * z2;
+    float best = INFINITY;
+    int bi = 0;
+    for (int i = 0; i < n_embed; ++i) {
+      const float dot = fmaf(z2, sm[3 * i + 2], fmaf(z1, sm[3 * i + 1], z0 * sm[3 * i]));
+      const float d = (zz + ee[i]) - 2.f * dot;
+      if (d < best) { best = d; bi = i; }
+    }
+    const float q0 = z0 + (sm[3 * bi] - z0), q1 = z1 + (sm[3 * bi + 1] - z1), q2 = z2 + (sm[3 * bi + 2] - z2);
+    float* o = out + v * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = fmaf(pw[3 * c + 2], q2, fmaf(pw[3 * c + 1], q1, pw[3 * c] * q0)) + pb[c];
+    if (indices) indices[v] = bi;
+  }
+}
+
+// nearest x2 in d, h, w of a channels-last tensor (F.interpolate(scale_factor=2, mode="nearest"), vqvae_modules.py:36)
+template <class T>
+__global__ void upsample_dhw2_kernel(const T* __restrict__ x, int n, int d, int h, int w, int cv, long long nvec, T* __restrict__ out) {
+  constexpr int VE = 16 / (int)sizeof(T);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv); long long r = i / cv;
+    const int ow = (int)(r % (2 * w)); r /= 2 * w;
+    const int oh = (int)(r % (2 * h)); r /= 2 * h;
+    const int od = (int)(r % (2 * d)); const long long obj = r / (2 * d);
+    const long long src = (((obj * d + (od >> 1)) * h + (oh >> 1)) * w + (ow >> 1)) * (long long)cv + c;
+    reinterpret_cast<uint4*>(out)[i] = __ldg(reinterpret_cast<const uint4*>(x) + src);
+    (void)VE;
+  }
+}
+
+template <class T>
+__global__ void gelu_kernel(T* __restrict__ x, long long count) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    const float v = (float)x[i];
+    x[i] = (T)(0.5f * v * (1.f + erff(v * 0.70710678118654752440f)));   // nn.GELU(), exact erf form
+  }
+}
+
+struct ResnetW {
+  int cin = 0, cout = 0;
+  NormW n1, n2;
+  ConvW c1, c2, nin;
+  bool has_nin = false;
+};
+
+}  // namespace
+
+struct echo_vqvae {
+  echo_vqvae_desc_t d;
+  DevPool pool;
+  Arena arena;
+  bool dry = false;
+  int prec = ECHO_PREC_FP32;
+  DT adt = F32;
+  const float *codebook = nullptr, *pq_w = nullptr, *pq_b = nullptr;
+  ConvW conv_in, conv_out, qkv, attn_out;
+  NormW attn_norm, norm_out;
+  ResnetW mid1, mid2;
+  std::vector<std::vector<ResnetW>> up_blocks;   // [level][block]
+  std::vector<ConvW> up_conv;                    // [level] (level 0: unused)
+
+  Act new_act(int n, int dd, int h, int w, int c, DT dt) {
+    Act a;
+    a.n = n; a.d = dd; a.h = h; a.w = w; a.c = c; a.dt = dt;
+    a.p = arena.alloc(a.bytes());
+    return a;
+  }
+  void contract(const Act& x, const ConvW& w, int k, const Act* res, const Act& out, cudaStream_t s) {
+    if (dry) return;
+    GemmArgs g;
+    g.A = x.p; g.a_dt = x.dt; g.n = x.n; g.d = x.d; g.h = x.h; g.w = x.w; g.cin = x.c; g.lda = x.c;
+    g.od = out.d; g.oh = out.h; g.ow = out.w;
+    g.kd = g.kh = g.kw = k; g.pd = g.ph = g.pw = k / 2;
+    g.W = w.w; g.w_dt = F32; g.w_stride_n = (int64_t)w.taps * w.cin; g.cout = w.cout; g.bias = w.b;
+    if (res) { g.res = res->p; g.res_dt = res->dt; g.ld_res = res->c; }
+    g.out = out.p; g.out_dt = out.dt; g.ldo = out.c;
+    ECHO_CHECK(w.cin == x.c && w.cout == out.c && w.taps == k * k * k, "vqvae: weight/activation mismatch (cin %d vs %d, cout %d vs %d)", w.cin,
+               x.c, w.cout, out.c);
+    if (prec == ECHO_PREC_BF16 && w.wb && x.dt == BF16 && tc_available()) {
+      GemmArgs t = g;
+      t.W = w.wb; t.w_dt = BF16;
+      if (gemm_tc_supported(t)) { gemm_tc(t, s); return; }
+    }
+    gemm_simt(g, s);
+  }
+  Act gn(const Act& x, const NormW& nw, bool swish, cudaStream_t s) {
+    float* stats = arena.alloc_n<float>((size_t)x.n * 32 * 2);
+    float* partial = arena.alloc_n<float>(gn_partial_floats(x, 32));
+    Act o = new_act(x.n, x.d, x.h, x.w, x.c, x.dt);
+    if (!dry) {
+      gn_stats(x, 32, 1e-6f, stats, partial, s);            // Normalize(): GroupNorm(32, eps 1e-6), vqvae_modules.py:13-22
+      gn_apply(x, stats, nw.g, nw.b, 32, swish, o, s);
+    }
+    return o;
+  }
+  // ResnetBlock.forward, temb = None (vqvae_modules.py:107-127)
+  Act resnet(const Act& x, const ResnetW& r, cudaStream_t s) {
+    Act out = new_act(x.n, x.d, x.h, x.w, r.cout, x.dt);
+    const size_t m = arena.mark();
+    Act a1 = gn(x, r.n1, true, s);
+    Act h1 = new_act(x.n, x.d, x.h, x.w, r.cout, x.dt);
+    contract(a1, r.c1, 3, nullptr, h1, s);
+    Act a2 = gn(h1, r.n2, true, s);
+    if (r.has_nin) {
+      Act sk = new_act(x.n, x.d, x.h, x.w, r.cout, x.dt);
+      contract(x, r.nin, 1, nullptr, sk, s);
+      contract(a2, r.c2, 3, &sk, out, s);
+    } else {
+      contract(a2, r.c2, 3, &x, out, s);
+    }
+    arena.release(m);
+    return out;
+  }
+  // AttnBlock.forward (vqvae_modules.py:158-195): one head over all voxels, scale C^-0.5
+  Act attn(const Act& x, cudaStream_t s) {
+    Act out = new_act(x.n, x.d, x.h, x.w, x.c, x.dt);
+    const size_t m = arena.mark();
+    const int C = x.c, tokens = (int)x.voxels();
+    Act xn = gn(x, attn_norm, false, s);
+    Act qkvt = new_act(x.n, x.d, x.h, x.w, 3 * C, F32);
+    contract(xn, qkv, 1, nullptr, qkvt, s);
+    float* ws = arena.alloc_n<float>(attention_f32_ws_floats(x.n, tokens, 1));
+    Act o32 = new_act(x.n, x.d, x.h, x.w, C, F32);
+    if (!dry) attention_f32((const float*)qkvt.p, x.n, tokens, 1, C, ws, (float*)o32.p, s);
+    Act o = o32;
+    if (x.dt != F32) {
+      o = new_act(x.n, x.d, x.h, x.w, C, x.dt);
+      if (!dry) convert(o32.p, F32, o.p, o.dt, o.rows() * C, s);
+    }
+    contract(o, attn_out, 1, &x, out, s);
+    arena.release(m);
+    return out;
+  }
+  Act upsample(const Act& x, cudaStream_t s) {
+    Act o = new_act(x.n, 2 * x.d, 2 * x.h, 2 * x.w, x.c, x.dt);
+    if (!dry) {
+      const int cv = (int)(x.c * dt_size(x.dt) / 16);
+      ECHO_CHECK(x.c * dt_size(x.dt) % 16 == 0, "vqvae: upsample needs 16-byte channel vectors");
+      const long long nvec = (long long)o.rows() * cv;
+      long long blocks = (nvec + 255) / 256;
+      if (blocks > 148 * 32) blocks = 148 * 32;
+      if (x.dt == F32) upsample_dhw2_kernel<float><<<(int)blocks, 256, 0, s>>>((const float*)x.p, x.n, x.d, x.h, x.w, cv, nvec, (float*)o.p);
+      else upsample_dhw2_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, s>>>((const __nv_bfloat16*)x.p, x.n, x.d, x.h, x.w, cv, nvec, (__nv_bfloat16*)o.p);
+      ECHO_LAUNCH_CHECK();
+    }
+    return o;
+  }
+
+  void run(const float* latents, int n, float* sdf_out, int* indices_out, cudaStream_t s) {
+    ECHO_CHECK(n >= 0 && n <= d.max_objects, "vqvae_decode: %d objects exceed the handle's capacity %d", n, d.max_objects);
+    if (n == 0) return;
+    arena.release(0);
+    const int L = d.latent_size;
+    const long long vox = (long long)L * L * L;
+    Act zq = new_act(n, L, L, L, d.z_channels, F32);
+    if (!dry) {
+      const size_t smem = (size_t)d.n_embed * 4 * sizeof(float);
+      vq_quantize_kernel<<<148 * 2, 256, smem, s>>>(latents, vox, (long long)n * vox, codebook, d.n_embed, pq_w, pq_b, (float*)zq.p, indices_out);
+      ECHO_LAUNCH_CHECK();
+    }
+    Act h = new_act(n, L, L, L, conv_in.cout, adt);
+    contract(zq, conv_in, 3, nullptr, h, s);                 // 3 input channels: fp32 FMA kernel in both modes
+    h = resnet(h, mid1, s);
+    h = attn(h, s);
+    h = resnet(h, mid2, s);
+    for (int lvl = d.num_levels - 1; lvl >= 0; --lvl) {
+      for (auto& r : up_blocks[lvl]) h = resnet(h, r, s);
+      if (lvl != 0) {
+        Act u = upsample(h, s);
+        Act o = new_act(u.n, u.d, u.h, u.w, up_conv[lvl].cout, adt);
+        contract(u, up_conv[lvl], 3, nullptr, o, s);
+        h = o;
+      }
+    }
+    Act hn = gn(h, norm_out, false, s);
+    if (!dry) {
+      const long long cnt = (long long)hn.rows() * hn.c;
+      long long blocks = (cnt + 255) / 256;
+      if (blocks > 148 * 32) blocks = 148 * 32;
+      if (hn.dt == F32) gelu_kernel<float><<<(int)blocks, 256, 0, s>>>((float*)hn.p, cnt);
+      else gelu_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, s>>>((__nv_bfloat16*)hn.p, cnt);
+      ECHO_LAUNCH_CHECK();
+    }
+    // conv_out: out_ch = 1, so channels-last == the reference's NCDHW
+    Act e;
+    e.n = n; e.d = hn.d; e.h = hn.h; e.w = hn.w; e.c = d.out_ch; e.dt = F32; e.p = sdf_out;
+    contract(hn, conv_out, 3, nullptr, e, s);
+  }
+};
+
+namespace echo {
+
+echo_vqvae* vqvae_create(const echo_vqvae_desc_t* desc, const echo_weight_t* weights, int n_weights) {
+  ECHO_CHECK(desc, "vqvae: null desc");
+  echo_vqvae* h = new echo_vqvae();
+  try {
+    h->d = *desc;
+    const echo_vqvae_desc_t& d = h->d;
+    ECHO_CHECK(d.embed_dim == 3 && d.z_channels == 3, "vqvae: embed_dim / z_channels must be 3 (config/vqvae_snet.yaml)");
+    ECHO_CHECK(d.out_ch == 1, "vqvae: out_ch must be 1 (the output is written as NCDHW == channels-last)");
+    ECHO_CHECK(d.num_levels >= 1 && d.num_levels <= 8 && d.max_objects > 0 && d.n_embed > 0 && d.latent_size > 0, "vqvae: bad config");
+    ECHO_CHECK((size_t)d.n_embed * 16 <= 200 * 1024, "vqvae: codebook does not fit shared memory");
+    h->prec = d.precision;
+    ECHO_CHECK(h->prec == ECHO_PREC_FP32 || h->prec == ECHO_PREC_BF16, "vqvae: unknown precision %d", h->prec);
+    if (h->prec == ECHO_PREC_BF16 && !tc_available())
+      fail(ECHO_ERR_UNSUPPORTED, "vqvae: ECHO_PREC_BF16 needs the sm_100a tcgen05 kernels on a B200-class device");
+    h->adt = h->prec == ECHO_PREC_BF16 ? BF16 : F32;
+    WeightMap wm;
+    wm.load(weights, n_weights);
+    cudaStream_t s = 0;
+    DevPool& pool = h->pool;
+    const bool bf = h->prec == ECHO_PREC_BF16;
+    auto vec = [&](const std::string& name, int n) {
+      const WView& v = wm.get(name, {n});
+      float* o = pool.alloc_n<float>(n);
+      ECHO_CUDA(cudaMemcpyAsync(o, v.p, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+      return (const float*)o;
+    };
+    auto to_bf16 = [&](const float* w, size_t n) {
+      __nv_bfloat16* o = pool.alloc_n<__nv_bfloat16>(n);
+      convert(w, F32, o, BF16, (int64_t)n, s);
+      return (const __nv_bfloat16*)o;
+    };
+    auto conv = [&](const std::string& p, int cin, int cout, int k) {
+      ConvW c;
+      c.cin = cin; c.cout = cout; c.taps = k * k * k;
+      const WView& v = wm.get(p + ".weight", {cout, cin, k, k, k});
+      const size_t n_el = (size_t)cout * cin * c.taps;
+      float* o = pool.alloc_n<float>(n_el);
+      if (c.taps == 1) ECHO_CUDA(cudaMemcpyAsync(o, v.p, sizeof(float) * n_el, cudaMemcpyDeviceToDevice, s));
+      else repack_conv_weight(v.p, cout, cin, c.taps, o, s);
+      c.w = o;
+      if (bf) c.wb = to_bf16(o, n_el);
+      c.b = vec(p + ".bias", cout);
+      return c;
+    };
+    auto norm = [&](const std::string& p, int c) {
+      NormW n;
+      n.c = c;
+      n.g = vec(p + ".weight", c);
+      n.b = vec(p + ".bias", c);
+      return n;
+    };
+    auto resnet = [&](const std::string& p, int cin, int cout) {
+      ResnetW r;
+      r.cin = cin; r.cout = cout;
+      ECHO_CHECK(cin % 32 == 0 && cout % 32 == 0, "vqvae: Normalize() with 32 groups needs channels %% 32 == 0 (%d, %d)", cin, cout);
+      r.n1 = norm(p + ".norm1", cin);
+      r.c1 = conv(p + ".conv1", cin, cout, 3);
+      r.n2 = norm(p + ".norm2", cout);
+      r.c2 = conv(p + ".conv2", cout, cout, 3);
+      r.has_nin = cin != cout;
+      if (r.has_nin) r.nin = conv(p + ".nin_shortcut", cin, cout, 1);
+      return r;
+    };
+    {
+      const WView& cb = wm.get("quantize.embedding.weight", {d.n_embed, d.embed_dim});
+      float* o = pool.alloc_n<float>(cb.numel());
+      ECHO_CUDA(cudaMemcpyAsync(o, cb.p, sizeof(float) * cb.numel(), cudaMemcpyDeviceToDevice, s));
+      h->codebook = o;
+      const WView& pw = wm.get("post_quant_conv.weight", {d.z_channels, d.embed_dim, 1, 1, 1});
+      float* w = pool.alloc_n<float>(9);
+      ECHO_CUDA(cudaMemcpyAsync(w, pw.p, sizeof(float) * 9, cudaMemcpyDeviceToDevice, s));
+      h->pq_w = w;
+      h->pq_b = vec("post_quant_conv.bias", d.z_channels);
+    }
+    int block_in = d.ch * d.ch_mult[d.num_levels - 1];
+    h->conv_in = conv("decoder.conv_in", d.z_channels, block_in, 3);
+    h->conv_in.wb = nullptr;                                   // 3 input channels: fp32 kernel
+    h->mid1 = resnet("decoder.mid.block_1", block_in, block_in);
+    h->attn_norm = norm("decoder.mid.attn_1.norm", block_in);
+    {   // q, k, v 1x1 convs stacked [3C, C] (+ biases) for one projection launch
+      const int C = block_in;
+      float* w = pool.alloc_n<float>((size_t)3 * C * C);
+      float* b = pool.alloc_n<float>((size_t)3 * C);
+      const char* names[3] = {"q", "k", "v"};
+      for (int i = 0; i < 3; ++i) {
+        const WView& wv = wm.get(std::string("decoder.mid.attn_1.") + names[i] + ".weight", {C, C, 1, 1, 1});
+        const WView& bv = wm.get(std::string("decoder.mid.attn_1.") + names[i] + ".bias", {C});
+        ECHO_CUDA(cudaMemcpyAsync(w + (size_t)i * C * C, wv.p, sizeof(float) * C * C, cudaMemcpyDeviceToDevice, s));
+        ECHO_CUDA(cudaMemcpyAsync(b + (size_t)i * C, bv.p, sizeof(float) * C, cudaMemcpyDeviceToDevice, s));
+      }
+      h->qkv.cin = C; h->qkv.cout = 3 * C; h->qkv.taps = 1; h->qkv.w = w; h->qkv.b = b;   // fp32 output for the fp32 attention
+    }
+    h->attn_out = conv("decoder.mid.attn_1.proj_out", block_in, block_in, 1);
+    h->mid2 = resnet("decoder.mid.block_2", block_in, block_in);
+    h->up_blocks.resize(d.num_levels);
+    h->up_conv.resize(d.num_levels);
+    for (int lvl = d.num_levels - 1; lvl >= 0; --lvl) {
+      const int block_out = d.ch * d.ch_mult[lvl];
+      for (int i = 0; i < d.num_res_blocks; ++i) {
+        h->up_blocks[lvl].push_back(resnet("decoder.up." + std::to_string(lvl) + ".block." + std::to_string(i), block_in, block_out));
+        block_in = block_out;
+      }
+      if (lvl != 0) h->up_conv[lvl] = conv("decoder.up." + std::to_string(lvl) + ".upsample.conv", block_in, block_in, 3);
+    }
+    h->norm_out = norm("decoder.norm_out", block_in);
+    h->conv_out = conv("decoder.conv_out", block_in, d.out_ch, 3);
+    h->conv_out.wb = nullptr;                                  // one output channel: fp32 kernel
+    ECHO_CUDA(cudaFuncSetAttribute(vq_quantize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)d.n_embed * 16)));
+    ECHO_CUDA(cudaStreamSynchronize(s));
+    // size the workspace with a dry run at full capacity
+    h->dry = true;
+    h->arena.base = nullptr;
+    h->arena.cap = ~size_t(0) >> 1;
+    h->arena.off = h->arena.high = 0;
+    h->run(nullptr, d.max_objects, nullptr, nullptr, s);
+    h->dry = false;
+    h->arena.init(h->arena.high + (size_t(1) << 20));
+    return h;
+  } catch (...) {
+    h->arena.destroy();
+    h->pool.destroy();
+    delete h;
+    throw;
+  }
+}
+
+void vqvae_destroy(echo_vqvae* h) {
+  if (!h) return;
+  h->arena.destroy();
+  h->pool.destroy();
+  delete h;
+}
+
+void vqvae_decode(echo_vqvae* h, const float* latents, int n, float* sdf_out, int* indices_out, cudaStream_t s) {
+  h->run(latents, n, sdf_out, indices_out, s);
+}
+
+}  // namespace echo

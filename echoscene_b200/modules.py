@@ -475,3 +475,81 @@ class DiffusionUNet(nn.Module):
             raise EchoError("only conditioning_key='crossattn' is on the hot path")
         cc = torch.cat(c_crossattn, 1)
         return self.diffusion_net(x, obj_embed, triples, t, context=cc)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# VQ-VAE decode
+# ----------------------------------------------------------------------------------------------------------------------
+class VQVAE(_SpecModule):
+    """The decode half of model/networks/vqvae_networks/network.py:56-103 (same constructor): ``decode_no_quant(h)`` =
+    quantize -> post_quant_conv -> Decoder3D, what EchoToShape.rel2shape calls on the sampled latents
+    (echo2shape.py:522).  state_dict keys are the reference's (quantize.embedding.weight, post_quant_conv.*, decoder.*);
+    encoder / quant_conv entries of a reference checkpoint are accepted and ignored by ``load_state_dict`` (the encoder
+    is not on this path); ``encode*`` raise."""
+
+    def __init__(self, ddconfig, n_embed, embed_dim, remap=None, sane_index_shape=False, precision: str = "fp32"):
+        super().__init__()
+        if remap is not None:
+            raise EchoError("VQVAE: remap is outside the hot path")
+        dd = dict(ddconfig)
+        if dd.get("attn_resolutions"):
+            raise EchoError("VQVAE: attn_resolutions != [] is outside the hot path (config/vqvae_snet.yaml uses [])")
+        self.cfg = arch.VQVAEConfig(embed_dim=embed_dim, n_embed=n_embed, z_channels=dd["z_channels"], resolution=dd["resolution"],
+                                    out_ch=dd["out_ch"], ch=dd["ch"], ch_mult=tuple(dd["ch_mult"]), num_res_blocks=dd["num_res_blocks"])
+        self.ddconfig, self.n_embed, self.embed_dim = dd, n_embed, embed_dim
+        self.precision = precision
+        self._build_from_specs(arch.vqvae_decode_specs(self.cfg))
+        self.eval()
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        own = {k: v for k, v in state_dict.items() if not (k.startswith("encoder.") or k.startswith("quant_conv."))}
+        return super().load_state_dict(own, strict=strict, **kw)
+
+    def _ensure(self, n):
+        ver = self._weights_version()
+        if self._handle is not None and self._handle_key[0] == ver and n <= self._handle_key[1]:
+            return
+        self._destroy_handle()
+        cap = max(n, 1)
+        c = self.cfg
+        d = _lib.VqvaeDesc()
+        d.embed_dim, d.n_embed, d.z_channels, d.latent_size = c.embed_dim, c.n_embed, c.z_channels, c.latent_size
+        d.ch, d.num_levels, d.num_res_blocks, d.out_ch = c.ch, len(c.ch_mult), c.num_res_blocks, c.out_ch
+        for i, m in enumerate(c.ch_mult):
+            d.ch_mult[i] = m
+        d.max_objects = cap
+        d.precision = _lib.PREC_BF16 if self.precision == "bf16" else _lib.PREC_FP32
+        arr, nw, keep = _lib.weights_table(self.state_dict())
+        h = C.c_void_p()
+        _lib.check(_lib.lib().echo_vqvae_create(C.byref(h), C.byref(d), arr, nw))
+        self._handle, self._handle_key = h, (ver, cap)
+
+    def _destroy_handle(self):
+        if self._handle is not None:
+            _lib.lib().echo_vqvae_destroy(self._handle)
+            self._handle = None
+
+    @torch.no_grad()
+    def decode_no_quant(self, h, force_not_quantize=False, return_indices: bool = False):
+        """h (N, 3, 16, 16, 16) -> SDF (N, 1, 64, 64, 64), network.py:95-103."""
+        self._check_eval()
+        if force_not_quantize:
+            raise EchoError("VQVAE.decode_no_quant(force_not_quantize=True) is outside the hot path")
+        _lib.require_cuda(h)
+        c = self.cfg
+        n, L = h.shape[0], c.latent_size
+        assert h.shape == (n, c.z_channels, L, L, L), tuple(h.shape)
+        h = h.float().contiguous()
+        self._ensure(n)
+        out = torch.empty(n, c.out_ch, c.resolution, c.resolution, c.resolution, device=h.device)
+        idx = torch.empty(n * L * L * L, dtype=torch.int32, device=h.device) if return_indices else None
+        _lib.check(_lib.lib().echo_vqvae_decode(self._handle, _lib.ptr(h), n, _lib.ptr(out), _lib.ptr(idx), _lib.stream_ptr()))
+        return (out, idx) if return_indices else out
+
+    def forward(self, *a, **k):
+        raise EchoError("VQVAE.forward (encode + decode) is outside the hot path; use decode_no_quant")
+
+    def encode(self, *a, **k):
+        raise EchoError("VQVAE.encode is outside the hot path")
+
+    encode_no_quant = encode

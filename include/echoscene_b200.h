@@ -182,6 +182,23 @@ ECHO_API int echo_shape_trunk_async(echo_shape_t* h, const echo_graph_t* g, cons
 ECHO_API int echo_shape_latent(const echo_shape_t* h, int32_t n_nodes, float* out_dev, void* stream);
 ECHO_API void echo_shape_destroy(echo_shape_t* h);
 
+/* ---- VQ-VAE decode: VQVAE.decode_no_quant, model/networks/vqvae_networks/network.py:95-103 -- what
+ * EchoToShape.rel2shape calls on the latents the DDIM chain returns (echo2shape.py:522).
+ *   quantize (quantizer.py:68-99: nearest codebook entry per voxel) -> post_quant_conv -> Decoder3D
+ *   (vqvae_modules.py:292-409, config/vqvae_snet.yaml).  Weights by the reference's state_dict names:
+ *   quantize.embedding.weight, post_quant_conv.*, decoder.*.
+ * latents (n, 3, 16, 16, 16) f32 NCDHW -> sdf_out (n, 1, 64, 64, 64) f32; indices_out (n * 4096) int32 or NULL. */
+typedef struct echo_vqvae echo_vqvae_t;
+typedef struct {
+  int32_t embed_dim, n_embed, z_channels, latent_size;   /* 3, 8192, 3, 16 */
+  int32_t ch, num_levels, ch_mult[8], num_res_blocks, out_ch;   /* 64, 3, {1,2,4}, 1, 1 */
+  int32_t max_objects;
+  int32_t precision;                                     /* ECHO_PREC_* */
+} echo_vqvae_desc_t;
+ECHO_API int echo_vqvae_create(echo_vqvae_t** out, const echo_vqvae_desc_t* desc, const echo_weight_t* weights, int32_t n_weights);
+ECHO_API int echo_vqvae_decode(echo_vqvae_t* h, const float* latents, int32_t n, float* sdf_out, int32_t* indices_out, void* stream);
+ECHO_API void echo_vqvae_destroy(echo_vqvae_t* h);
+
 /* ---- schedule tables, for host-side checks against the reference's buffers.
  * layout: 5 x time_num f32 [sqrt_recip_ac, sqrt_recipm1_ac, post_mean_coef1, post_mean_coef2, post_log_var_clipped]
  * shape : ddim_steps x 4 f32 [sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev)] and the int32 DDIM timesteps. */
