@@ -9,6 +9,8 @@ The reference has no plugin/FFI boundary on the denoising path; its seam is the 
   model.networks.diffusion_shape.openai_model_3d.UNet3DModel                 (openai_model_3d.py:452)
   model.networks.diffusion_shape.network.UNet3DModel / DiffusionUNet         (network.py:9-17)
   model.networks.diffusion_shape.echo2shape.DDIMSampler                      (echo2shape.py:46, 122)
+  model.model_utils.VQVAE (looked up by load_vqvae, model_utils.py:7-32)      decode path only: rel2shape's
+                                                                             decode_no_quant (echo2shape.py:522)
 
 After that, ``scripts/eval_3dfront.py`` builds ``SGDiff`` as before (same YAML, same checkpoints: state_dict keys are
 identical), and ``Sg2ScDiffModel.sample`` runs both chains through libechoscene_b200.so.  Only the *denoiser-step*
@@ -24,8 +26,9 @@ import importlib
 from typing import Optional
 
 
-def patch_reference(precision: str = "fp32", ddim_steps: Optional[int] = None) -> dict:
-    """Call AFTER the reference checkout is importable (sys.path) and BEFORE SGDiff(...) is constructed."""
+def patch_reference(precision: str = "fp32", ddim_steps: Optional[int] = None, vqvae_decode: bool = True) -> dict:
+    """Call AFTER the reference checkout is importable (sys.path) and BEFORE SGDiff(...) is constructed.
+    ``vqvae_decode=False`` keeps the reference's VQVAE (needed for training, which encodes: echo2shape.py:349)."""
     from . import modules, samplers
 
     def _with_precision(cls):
@@ -43,6 +46,7 @@ def patch_reference(precision: str = "fp32", ddim_steps: Optional[int] = None) -
         def __init__(self, unet_params, vq_conf=None, conditioning_key=None):
             super().__init__(unet_params, vq_conf=vq_conf, conditioning_key=conditioning_key, precision=precision)
 
+    VQ = _with_precision(modules.VQVAE)
     done = {}
     targets = [
         ("model.graph", {"GraphTripleConv": modules.GraphTripleConv, "GraphTripleConvNet": modules.GraphTripleConvNet}),
@@ -54,6 +58,8 @@ def patch_reference(precision: str = "fp32", ddim_steps: Optional[int] = None) -
         ("model.EchoScene", {"GraphTripleConvNet": modules.GraphTripleConvNet}),
         ("model.EchoLayout", {"GraphTripleConvNet": modules.GraphTripleConvNet}),
     ]
+    if vqvae_decode:
+        targets.append(("model.model_utils", {"VQVAE": VQ}))
     for modname, names in targets:
         try:
             mod = importlib.import_module(modname)
