@@ -803,25 +803,43 @@ void ddim_update(const float* x, const void* e, DT edt, bool e_cl, int n, int c,
   ECHO_LAUNCH_CHECK();
 }
 
-void fold_upsample_weight(const float* w, int cout, int cin, float* out) {
+void fold_upsample_weight(const float* w, int cout, int cin, float* out, bool up_depth) {
   // phase p in {0,1} along one axis: folded tap 0 reads low-res offset p-1, tap 1 reads offset p;
   // p = 0: {k=0}, {k=1,2};  p = 1: {k=0,1}, {k=2}
   auto member = [](int p, int a, int k) { return p == 0 ? (a == 0 ? k == 0 : k >= 1) : (a == 0 ? k <= 1 : k == 2); };
+  if (!up_depth) {   // x(1,2,2): [cout][4 phases (py,px)][12 taps (kd,a,b)][cin]
+    for (int n = 0; n < cout; ++n)
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px)
+          for (int kd = 0; kd < 3; ++kd)
+            for (int a = 0; a < 2; ++a)
+              for (int b = 0; b < 2; ++b) {
+                float* dst = out + (((size_t)n * 4 + py * 2 + px) * 12 + (kd * 2 + a) * 2 + b) * cin;
+                for (int c = 0; c < cin; ++c) dst[c] = 0.f;
+                for (int kh = 0; kh < 3; ++kh)
+                  for (int kw = 0; kw < 3; ++kw) {
+                    if (!member(py, a, kh) || !member(px, b, kw)) continue;
+                    const float* src = w + ((size_t)n * 27 + kd * 9 + kh * 3 + kw) * cin;
+                    for (int c = 0; c < cin; ++c) dst[c] += src[c];
+                  }
+              }
+    return;
+  }
+  // x(2,2,2): [cout][8 phases (pz,py,px)][8 taps (a_d,a_h,a_w)][cin]
   for (int n = 0; n < cout; ++n)
-    for (int py = 0; py < 2; ++py)
-      for (int px = 0; px < 2; ++px)
+    for (int ph = 0; ph < 8; ++ph)
+      for (int t = 0; t < 8; ++t) {
+        const int pz = (ph >> 2) & 1, py = (ph >> 1) & 1, px = ph & 1, ad = (t >> 2) & 1, ah = (t >> 1) & 1, aw = t & 1;
+        float* dst = out + (((size_t)n * 8 + ph) * 8 + t) * cin;
+        for (int c = 0; c < cin; ++c) dst[c] = 0.f;
         for (int kd = 0; kd < 3; ++kd)
-          for (int a = 0; a < 2; ++a)
-            for (int b = 0; b < 2; ++b) {
-              float* dst = out + (((size_t)n * 4 + py * 2 + px) * 12 + (kd * 2 + a) * 2 + b) * cin;
-              for (int c = 0; c < cin; ++c) dst[c] = 0.f;
-              for (int kh = 0; kh < 3; ++kh)
-                for (int kw = 0; kw < 3; ++kw) {
-                  if (!member(py, a, kh) || !member(px, b, kw)) continue;
-                  const float* src = w + ((size_t)n * 27 + kd * 9 + kh * 3 + kw) * cin;
-                  for (int c = 0; c < cin; ++c) dst[c] += src[c];
-                }
+          for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) {
+              if (!member(pz, ad, kd) || !member(py, ah, kh) || !member(px, aw, kw)) continue;
+              const float* src = w + ((size_t)n * 27 + kd * 9 + kh * 3 + kw) * cin;
+              for (int c = 0; c < cin; ++c) dst[c] += src[c];
             }
+      }
 }
 
 void repack_conv_weight(const float* w, int cout, int cin, int taps, float* out, cudaStream_t s) {

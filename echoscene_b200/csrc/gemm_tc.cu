@@ -50,7 +50,7 @@ static inline int stages_for(int b_rows, int msub) {
   const int st = (SMEM_LIMIT - SMEM_FIXED) / (msub * A_STAGE_BYTES + b_rows * BLOCK_K * 2);
   return st > MAX_STAGES ? MAX_STAGES : st;
 }
-constexpr int MAX_TAPS = 48;   // 27 taps of a 3x3x3 kernel, or 4 phases x 12 folded taps of a conv after a nearest x(1,2,2) upsample
+constexpr int MAX_TAPS = 64;   // 27 taps of a 3x3x3 kernel, or phases x folded taps of a conv after a nearest upsample: 4 x 12 (x(1,2,2)), 8 x 8 (x2)
 
 struct TcParams {
   // problem
@@ -58,7 +58,8 @@ struct TcParams {
   int bd, bh, bw;               // tile box (bd*bh*bw == 128)
   int tiles_d, tiles_h, tiles_w;
   int num_m_tiles, num_n_tiles, block_n;
-  int up;                       // conv after nearest x(1,2,2) upsample, evaluated per output phase on the LOW-resolution input
+  int up;                       // conv after a nearest upsample, evaluated per output phase on the LOW-resolution input:
+                                // 0 none, 1 = x(1,2,2) (4 phases (py,px)), 2 = x(2,2,2) (8 phases (pz,py,px))
   int vm_tiles;                 // schedulable 128-row sub-blocks: num_m_tiles, or 4 x num_m_tiles (phase-major) when up
   int splitk;                   // > 1: the taps are cut into `splitk` equal groups, one CTA tile per group; raw fp32 partial
                                 // sums go to out + ks * rows * ldo (splitk_reduce_kernel finishes the epilogue)
@@ -348,9 +349,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int obj = stl.obj;
       const int ow_ = stl.w0 + ww, oh_ = stl.h0 + hh, od_ = stl.d0 + dd;
       const bool valid = ow_ < p.ow && oh_ < p.oh && od_ < p.od;
-      const long long orow = (p.up ? (((long long)obj * p.od + od_) * (2 * p.oh) + 2 * oh_ + (stl.phase >> 1)) * (2 * p.ow) + 2 * ow_ + (stl.phase & 1)
+      const int upd = p.up == 2 ? 1 : 0;   // depth doubled as well
+      const long long orow = (p.up ? ((((long long)obj * (p.od << upd) + ((od_ << upd) + (upd ? (stl.phase >> 2) : 0))) * (2 * p.oh) + 2 * oh_ +
+                                       ((stl.phase >> 1) & 1)) * (2 * p.ow) + 2 * ow_ + (stl.phase & 1))
                                    : (((long long)obj * p.od + od_) * p.oh + oh_) * p.ow + ow_) + ks * p.total_rows;
-      const long long cs_row = p.up ? (long long)stl.m_blk * 4 + stl.phase : stl.m_blk;
+      const long long cs_row = p.up ? (long long)stl.m_blk * (p.up == 2 ? 8 : 4) + stl.phase : stl.m_blk;
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (as + sub) * MAX_BLOCK_N;
       const int n_base = n_blk * p.block_n;
       if (p.geglu) {
@@ -639,14 +642,14 @@ struct TcGeom {
 TcGeom tc_geom(const GemmArgs& g) {
   TcGeom t;
   const bool up = g.up2 != 0;
-  const int gw = up ? g.w : g.ow, gh = up ? g.h : g.oh;
+  const int gw = up ? g.w : g.ow, gh = up ? g.h : g.oh, gd = g.up2 == 2 ? g.d : g.od;
   t.bw = pow2_floor(gw) > 128 ? 128 : pow2_floor(gw);
   t.bh = pow2_floor(gh) > 128 / t.bw ? 128 / t.bw : pow2_floor(gh);
   t.bd = 128 / (t.bw * t.bh);
-  t.tiles_w = cdiv(gw, t.bw); t.tiles_h = cdiv(gh, t.bh); t.tiles_d = cdiv(g.od, t.bd);
+  t.tiles_w = cdiv(gw, t.bw); t.tiles_h = cdiv(gh, t.bh); t.tiles_d = cdiv(gd, t.bd);
   t.num_m_tiles = g.n * t.tiles_d * t.tiles_h * t.tiles_w;
-  t.vm_tiles = t.num_m_tiles * (up ? 4 : 1);
-  t.taps = up ? 12 : g.kd * g.kh * g.kw;
+  t.vm_tiles = t.num_m_tiles * (g.up2 == 2 ? 8 : up ? 4 : 1);
+  t.taps = g.up2 == 2 ? 8 : up ? 12 : g.kd * g.kh * g.kw;
   t.kblocks_per_tap = cdiv(g.cin, BLOCK_K);
   return t;
 }
@@ -849,6 +852,7 @@ int gemm_tc_colsum_rows_per_obj(const GemmArgs& g) {
   GemmArgs t = g;
   t.n = 1;
   if (t.up2) { t.h = t.oh / 2; t.w = t.ow / 2; }
+  if (t.up2 == 2) t.d = t.od / 2;
   const TcGeom ge = tc_geom(t);
   return ge.vm_tiles;
 }
@@ -867,9 +871,11 @@ size_t gemm_tc_splitk_ws_bytes(const GemmArgs& g) {
 bool gemm_tc_supported(const GemmArgs& g) {
   if (g.a_dt != BF16 || g.w_dt != BF16) return false;
   if (g.nb0 * g.nb1 != 1 || g.alpha != 1.f || g.act > 1) return false;
-  if (g.up2) {   // W = [cout][4 phases][12 folded taps][cin] (fold_upsample_weight)
-    if (g.kd != 3 || g.kh != 3 || g.kw != 3 || g.sd != 1 || g.sh != 1 || g.sw != 1 || g.od != g.d || g.oh != 2 * g.h || g.ow != 2 * g.w) return false;
-    if (g.cin % 16 != 0 || g.lda != g.cin || g.w_stride_k != 1 || g.w_stride_n != (int64_t)48 * g.cin || g.epi || g.res) return false;
+  if (g.up2) {   // W = [cout][4 phases][12 folded taps][cin] or [cout][8][8][cin] (fold_upsample_weight)
+    if (g.up2 != 1 && g.up2 != 2) return false;
+    if (g.kd != 3 || g.kh != 3 || g.kw != 3 || g.sd != 1 || g.sh != 1 || g.sw != 1 || g.oh != 2 * g.h || g.ow != 2 * g.w) return false;
+    if (g.od != (g.up2 == 2 ? 2 * g.d : g.d)) return false;
+    if (g.cin % 16 != 0 || g.lda != g.cin || g.w_stride_k != 1 || g.w_stride_n != (int64_t)(g.up2 == 2 ? 64 : 48) * g.cin || g.epi || g.res) return false;
   } else
   if (g.cin % 16 != 0 || g.lda != g.cin || g.w_stride_k != 1 || g.w_stride_n != (int64_t)g.ktot()) return false;
   if (g.cout % 32 != 0) return false;
@@ -923,8 +929,8 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   if (dbg_trace())
     fprintf(stderr, "[echo-trace] gemm_tc rows=%lld cin=%d cout=%d k=%d stride=%d epi=%d up=%d bn=%d msub=%d splitk=%d cta2=%d\n",
             (long long)g.rows_out(), g.cin, g.cout, g.kd, g.sh, g.epi, g.up2, plan.block_n, plan.msub, plan.splitk, plan.cta2 ? 1 : 0);
-  p.up = up ? 1 : 0;
-  p.n_obj = g.n; p.od = g.od; p.oh = up ? g.h : g.oh; p.ow = up ? g.w : g.ow;   // the grid the 128-voxel boxes tile
+  p.up = g.up2;
+  p.n_obj = g.n; p.od = g.up2 == 2 ? g.d : g.od; p.oh = up ? g.h : g.oh; p.ow = up ? g.w : g.ow;   // the grid the 128-voxel boxes tile
   p.bw = ge.bw; p.bh = ge.bh; p.bd = ge.bd;
   p.tiles_w = ge.tiles_w; p.tiles_h = ge.tiles_h; p.tiles_d = ge.tiles_d;
   p.num_m_tiles = ge.num_m_tiles;
@@ -936,7 +942,16 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   p.splitk = plan.splitk;
   p.total_rows = g.rows_out();
   p.obj_mul = s2 ? 4 : 1;
-  if (up) {
+  if (g.up2 == 2) {
+    // output voxel (2z+pz, 2y+py, 2x+px) reads low-res {z+pz-1, z+pz} x {y+py-1, y+py} x {x+px-1, x+px}: tap (a_d, a_h, a_w)
+    for (int ph = 0; ph < 8; ++ph)
+      for (int t = 0; t < 8; ++t) {
+        p.tap_d[ph * 8 + t] = (int8_t)(((ph >> 2) & 1) - 1 + ((t >> 2) & 1));
+        p.tap_h[ph * 8 + t] = (int8_t)(((ph >> 1) & 1) - 1 + ((t >> 1) & 1));
+        p.tap_w[ph * 8 + t] = (int8_t)((ph & 1) - 1 + (t & 1));
+        p.tap_p[ph * 8 + t] = 0;
+      }
+  } else if (up) {
     // output voxel (d, 2y+py, 2x+px) reads low-res rows {y+py-1, y+py}: tap (kd, a, b) of phase (py, px)
     for (int ph = 0; ph < 4; ++ph)
       for (int t = 0; t < 12; ++t) {
@@ -987,7 +1002,7 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
     ECHO_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed: %d", (int)r);
   }
   {
-    const cuuint64_t ktot = up ? (cuuint64_t)48 * g.cin : (cuuint64_t)g.ktot();
+    const cuuint64_t ktot = g.up2 == 2 ? (cuuint64_t)64 * g.cin : up ? (cuuint64_t)48 * g.cin : (cuuint64_t)g.ktot();
     const cuuint64_t dims[2] = {ktot, (cuuint64_t)g.cout};
     const cuuint64_t strides[1] = {ktot * 2};
     const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(cta2 ? p.block_n / 2 : p.block_n)};

@@ -35,8 +35,9 @@ struct GemmArgs {
   int act = 0;                      // 0 none, 1 relu
   int epi = 0;                      // tcgen05 path only: 1 = GEGLU epilogue (W rows tiled [128 a | 128 g]; out width cout/2)
   int out_t = 0;                    // tcgen05 path only: bf16 output stored transposed per object, out[(obj*cout + n)*voxels + voxel]
-  int up2 = 0;                      // tcgen05 path only: the conv follows a nearest x(1,2,2) upsample of A (openai_model_3d.py:150-157);
-                                    // A is the LOW-resolution tensor (d,h,w), the output grid is (d,2h,2w), W = fold_upsample_weight()
+  int up2 = 0;                      // tcgen05 path only: the conv follows a nearest upsample of A; A is the LOW-resolution tensor
+                                    // (d,h,w), W = fold_upsample_weight(): 1 = x(1,2,2) (openai_model_3d.py:150-157), output grid
+                                    // (d,2h,2w); 2 = x(2,2,2) (vqvae_modules.py:35-39), output grid (2d,2h,2w)
   float alpha = 1.f;                // scales the accumulator before the epilogue adds
   // batching: problem b = b0*nb1 + b1
   int nb0 = 1, nb1 = 1;
@@ -176,7 +177,9 @@ void pad_qkv(const float* x, int64_t rows, int heads, int dh, int dhp, __nv_bflo
 // 3x3x3 conv after nearest x(1,2,2) upsample == 4 output-phase convs with 3x2x2 taps on the low-res input (the two
 // high-res rows that map to one low-res row share it, so their weights add): w [cout][27][cin] fp32 (tap-major) ->
 // out [cout][4 phases (py,px)][12 taps (kd,a,b)][cin] fp32, host-side (runs once at handle creation)
-void fold_upsample_weight(const float* w_host, int cout, int cin, float* out_host);
+// up_depth: the upsample also doubles the depth (F.interpolate(scale_factor=2), vqvae_modules.py:36): 8 phases (pz,py,px) x
+// 8 taps -> out [cout][8][8][cin]
+void fold_upsample_weight(const float* w_host, int cout, int cin, float* out_host, bool up_depth = false);
 // conv weight (cout, cin, taps) -> (cout, taps, cin); taps = kd*kh*kw
 void repack_conv_weight(const float* w, int cout, int cin, int taps, float* out, cudaStream_t s);
 // centre tap of a Conv1d(k=3) weight (cout, cin, 3) -> (cout, cin)

@@ -10,6 +10,7 @@
 #include "unet.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 using namespace echo;
 
@@ -90,10 +91,13 @@ struct echo_vqvae {
   DT adt = F32;
   const float *codebook = nullptr, *pq_w = nullptr, *pq_b = nullptr;
   ConvW conv_in, conv_out, qkv, attn_out;
+  ConvW conv_out_pad;          // bf16 mode: conv_out zero-padded to 32 output channels so it runs on the tcgen05 kernel
+  ConvW q_s, k_w, v_w;         // bf16 mode: q (pre-scaled by C^-0.5), k, v projections as separate dense matrices
   NormW attn_norm, norm_out;
   ResnetW mid1, mid2;
   std::vector<std::vector<ResnetW>> up_blocks;   // [level][block]
   std::vector<ConvW> up_conv;                    // [level] (level 0: unused)
+  std::vector<ConvW> up_fold;                    // bf16 mode: the same convs folded per output phase of the x2 upsample
 
   Act new_act(int n, int dd, int h, int w, int c, DT dt) {
     Act a;
@@ -147,8 +151,61 @@ struct echo_vqvae {
     arena.release(m);
     return out;
   }
+  // dense [rows, cin] x [cout, cin]^T on the tcgen05 kernel (rows presented as a 1 x 1 x rows "voxel" line)
+  void tc_matmul(const void* A, int64_t rows, int cin, const void* W, const float* bias, int cout, void* out, DT out_dt, int64_t ldo,
+                 int out_t, cudaStream_t s) {
+    GemmArgs g;
+    g.A = A; g.a_dt = BF16; g.n = 1; g.d = 1; g.h = 1; g.w = (int)rows; g.cin = cin; g.lda = cin;
+    g.od = 1; g.oh = 1; g.ow = (int)rows;
+    g.W = W; g.w_dt = BF16; g.w_stride_n = cin; g.cout = cout; g.bias = bias;
+    g.out = out; g.out_dt = out_dt; g.ldo = ldo; g.out_t = out_t;
+    ECHO_CHECK(gemm_tc_supported(g), "vqvae: %lld x %d x %d matmul not supported by the tcgen05 kernel", (long long)rows, cin, cout);
+    gemm_tc(g, s);
+  }
+  // AttnBlock on the tensor cores (bf16 mode): per object S = (Q C^-0.5) K^T (fp32, materialised: 64 MB), row softmax in
+  // fp32, P rounded to bf16, O = P V with V projected straight into V^T.  One head of 256 channels over 4096 tokens is
+  // GEMM-shaped work (8.6 GFLOP per product and object), not flash-attention-shaped: the tcgen05 GEMM takes it as is.
+  Act attn_tc(const Act& x, cudaStream_t s) {
+    Act out = new_act(x.n, x.d, x.h, x.w, x.c, x.dt);
+    const size_t m = arena.mark();
+    const int C = x.c, tokens = (int)x.voxels();
+    const int64_t rows = x.rows();
+    Act xn = gn(x, attn_norm, false, s);
+    __nv_bfloat16* q = arena.alloc_n<__nv_bfloat16>((size_t)rows * C);
+    __nv_bfloat16* k = arena.alloc_n<__nv_bfloat16>((size_t)rows * C);
+    __nv_bfloat16* vt = arena.alloc_n<__nv_bfloat16>((size_t)rows * C);          // [(obj, c), tokens]
+    float* sc = arena.alloc_n<float>((size_t)tokens * tokens);                   // one object's scores at a time
+    __nv_bfloat16* pb = arena.alloc_n<__nv_bfloat16>((size_t)tokens * tokens);
+    Act o = new_act(x.n, x.d, x.h, x.w, C, BF16);
+    if (!dry) {
+      GemmArgs g;   // projections over all objects at once (per-object transposed store for V)
+      g.A = xn.p; g.a_dt = BF16; g.n = x.n; g.d = x.d; g.h = x.h; g.w = x.w; g.cin = C; g.lda = C;
+      g.od = x.d; g.oh = x.h; g.ow = x.w; g.w_dt = BF16; g.w_stride_n = C; g.cout = C; g.out_dt = BF16; g.ldo = C;
+      GemmArgs gq = g; gq.W = q_s.wb; gq.bias = q_s.b; gq.out = q;
+      GemmArgs gk = g; gk.W = k_w.wb; gk.bias = k_w.b; gk.out = k;
+      GemmArgs gv = g; gv.W = v_w.wb; gv.bias = v_w.b; gv.out = vt; gv.out_t = 1;
+      ECHO_CHECK(gemm_tc_supported(gq) && gemm_tc_supported(gv), "vqvae: attention projections not supported by the tcgen05 kernel");
+      gemm_tc(gq, s);
+      gemm_tc(gk, s);
+      gemm_tc(gv, s);
+      for (int ob = 0; ob < x.n; ++ob) {
+        const __nv_bfloat16* qo = q + (size_t)ob * tokens * C;
+        const __nv_bfloat16* ko = k + (size_t)ob * tokens * C;
+        tc_matmul(qo, tokens, C, ko, nullptr, tokens, sc, F32, tokens, 0, s);                       // S = Q K^T (scale folded into Q)
+        softmax_rows(sc, tokens, tokens, s);                                                        // vqvae_modules.py:178
+        convert(sc, F32, pb, BF16, (int64_t)tokens * tokens, s);
+        tc_matmul(pb, tokens, tokens, vt + (size_t)ob * C * tokens, nullptr, C, (__nv_bfloat16*)o.p + (size_t)ob * tokens * C, BF16, C, 0, s);
+      }
+    }
+    contract(o, attn_out, 1, &x, out, s);
+    arena.release(m);
+    return out;
+  }
+
   // AttnBlock.forward (vqvae_modules.py:158-195): one head over all voxels, scale C^-0.5
   Act attn(const Act& x, cudaStream_t s) {
+    static const bool no_tc_attn = getenv("ECHO_VQ_NO_TC_ATTN") != nullptr;
+    if (prec == ECHO_PREC_BF16 && x.dt == BF16 && q_s.wb && !no_tc_attn && x.voxels() % 128 == 0) return attn_tc(x, s);
     Act out = new_act(x.n, x.d, x.h, x.w, x.c, x.dt);
     const size_t m = arena.mark();
     const int C = x.c, tokens = (int)x.voxels();
@@ -202,10 +259,27 @@ struct echo_vqvae {
     for (int lvl = d.num_levels - 1; lvl >= 0; --lvl) {
       for (auto& r : up_blocks[lvl]) h = resnet(h, r, s);
       if (lvl != 0) {
-        Act u = upsample(h, s);
-        Act o = new_act(u.n, u.d, u.h, u.w, up_conv[lvl].cout, adt);
-        contract(u, up_conv[lvl], 3, nullptr, o, s);
-        h = o;
+        static const bool no_fold = getenv("ECHO_VQ_NO_UPFOLD") != nullptr;   // A/B: explicit upsample + 27-tap conv
+        if (prec == ECHO_PREC_BF16 && h.dt == BF16 && up_fold[lvl].wb && !no_fold) {
+          // nearest x2 folded into the conv: eight output phases, 2x2x2 taps each, on the low-resolution tensor
+          Act o = new_act(h.n, 2 * h.d, 2 * h.h, 2 * h.w, up_conv[lvl].cout, adt);
+          if (!dry) {
+            GemmArgs g;
+            g.A = h.p; g.a_dt = BF16; g.n = h.n; g.d = h.d; g.h = h.h; g.w = h.w; g.cin = h.c; g.lda = h.c;
+            g.od = o.d; g.oh = o.h; g.ow = o.w; g.up2 = 2;
+            g.kd = g.kh = g.kw = 3; g.pd = g.ph = g.pw = 1;
+            g.W = up_fold[lvl].wb; g.w_dt = BF16; g.w_stride_n = (int64_t)64 * h.c; g.cout = o.c; g.bias = up_fold[lvl].b;
+            g.out = o.p; g.out_dt = BF16; g.ldo = o.c;
+            ECHO_CHECK(gemm_tc_supported(g), "vqvae: folded upsample conv not supported by the tcgen05 kernel");
+            gemm_tc(g, s);
+          }
+          h = o;
+        } else {
+          Act u = upsample(h, s);
+          Act o = new_act(u.n, u.d, u.h, u.w, up_conv[lvl].cout, adt);
+          contract(u, up_conv[lvl], 3, nullptr, o, s);
+          h = o;
+        }
       }
     }
     Act hn = gn(h, norm_out, false, s);
@@ -218,9 +292,17 @@ struct echo_vqvae {
       ECHO_LAUNCH_CHECK();
     }
     // conv_out: out_ch = 1, so channels-last == the reference's NCDHW
-    Act e;
-    e.n = n; e.d = hn.d; e.h = hn.h; e.w = hn.w; e.c = d.out_ch; e.dt = F32; e.p = sdf_out;
-    contract(hn, conv_out, 3, nullptr, e, s);
+    static const bool no_pad = getenv("ECHO_VQ_NO_OUTPAD") != nullptr;
+    if (prec == ECHO_PREC_BF16 && hn.dt == BF16 && conv_out_pad.wb && !no_pad) {
+      // a 1-column GEMM wastes the tensor core far less than a scalar reduction wastes the SM: 32 padded output channels
+      Act e32 = new_act(n, hn.d, hn.h, hn.w, 32, F32);
+      contract(hn, conv_out_pad, 3, nullptr, e32, s);
+      if (!dry) copy_cols((const float*)e32.p, 32, e32.rows(), 1, sdf_out, 1, s);
+    } else {
+      Act e;
+      e.n = n; e.d = hn.d; e.h = hn.h; e.w = hn.w; e.c = d.out_ch; e.dt = F32; e.p = sdf_out;
+      contract(hn, conv_out, 3, nullptr, e, s);
+    }
   }
 };
 
@@ -317,22 +399,69 @@ echo_vqvae* vqvae_create(const echo_vqvae_desc_t* desc, const echo_weight_t* wei
         ECHO_CUDA(cudaMemcpyAsync(b + (size_t)i * C, bv.p, sizeof(float) * C, cudaMemcpyDeviceToDevice, s));
       }
       h->qkv.cin = C; h->qkv.cout = 3 * C; h->qkv.taps = 1; h->qkv.w = w; h->qkv.b = b;   // fp32 output for the fp32 attention
+      if (bf) {   // tensor-core attention: separate dense projections, the softmax scale C^-0.5 folded into q (weights and bias)
+        h->q_s = conv("decoder.mid.attn_1.q", C, C, 1);
+        h->k_w = conv("decoder.mid.attn_1.k", C, C, 1);
+        h->v_w = conv("decoder.mid.attn_1.v", C, C, 1);
+        const float sc = 1.0f / sqrtf((float)C);
+        std::vector<float> hw((size_t)C * C), hb(C);
+        ECHO_CUDA(cudaStreamSynchronize(s));
+        ECHO_CUDA(cudaMemcpy(hw.data(), h->q_s.w, hw.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        ECHO_CUDA(cudaMemcpy(hb.data(), h->q_s.b, hb.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        for (auto& v : hw) v *= sc;
+        for (auto& v : hb) v *= sc;
+        float* ws = pool.alloc_n<float>(hw.size());
+        float* bs = pool.alloc_n<float>(hb.size());
+        ECHO_CUDA(cudaMemcpy(ws, hw.data(), hw.size() * sizeof(float), cudaMemcpyHostToDevice));
+        ECHO_CUDA(cudaMemcpy(bs, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice));
+        h->q_s.w = ws; h->q_s.b = bs; h->q_s.wb = to_bf16(ws, hw.size());
+      }
     }
     h->attn_out = conv("decoder.mid.attn_1.proj_out", block_in, block_in, 1);
     h->mid2 = resnet("decoder.mid.block_2", block_in, block_in);
     h->up_blocks.resize(d.num_levels);
     h->up_conv.resize(d.num_levels);
+    h->up_fold.resize(d.num_levels);
     for (int lvl = d.num_levels - 1; lvl >= 0; --lvl) {
       const int block_out = d.ch * d.ch_mult[lvl];
       for (int i = 0; i < d.num_res_blocks; ++i) {
         h->up_blocks[lvl].push_back(resnet("decoder.up." + std::to_string(lvl) + ".block." + std::to_string(i), block_in, block_out));
         block_in = block_out;
       }
-      if (lvl != 0) h->up_conv[lvl] = conv("decoder.up." + std::to_string(lvl) + ".upsample.conv", block_in, block_in, 3);
+      if (lvl != 0) {
+        h->up_conv[lvl] = conv("decoder.up." + std::to_string(lvl) + ".upsample.conv", block_in, block_in, 3);
+        if (bf) {
+          const size_t n_src = (size_t)block_in * 27 * block_in, n_dst = (size_t)block_in * 64 * block_in;
+          std::vector<float> hsrc(n_src), hdst(n_dst);
+          ECHO_CUDA(cudaStreamSynchronize(s));
+          ECHO_CUDA(cudaMemcpy(hsrc.data(), h->up_conv[lvl].w, n_src * sizeof(float), cudaMemcpyDeviceToHost));
+          fold_upsample_weight(hsrc.data(), block_in, block_in, hdst.data(), true);
+          float* o = pool.alloc_n<float>(n_dst);
+          ECHO_CUDA(cudaMemcpy(o, hdst.data(), n_dst * sizeof(float), cudaMemcpyHostToDevice));
+          h->up_fold[lvl] = h->up_conv[lvl];
+          h->up_fold[lvl].taps = 64;
+          h->up_fold[lvl].w = o;
+          h->up_fold[lvl].wb = to_bf16(o, n_dst);
+        }
+      }
     }
     h->norm_out = norm("decoder.norm_out", block_in);
     h->conv_out = conv("decoder.conv_out", block_in, d.out_ch, 3);
     h->conv_out.wb = nullptr;                                  // one output channel: fp32 kernel
+    if (bf) {   // ... or 32 zero-padded output channels on the tensor cores
+      const size_t row = (size_t)27 * block_in;
+      float* o = pool.alloc_n<float>(32 * row);
+      float* b = pool.alloc_n<float>(32);
+      ECHO_CUDA(cudaMemsetAsync(o, 0, 32 * row * sizeof(float), s));
+      ECHO_CUDA(cudaMemsetAsync(b, 0, 32 * sizeof(float), s));
+      ECHO_CUDA(cudaMemcpyAsync(o, h->conv_out.w, d.out_ch * row * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      ECHO_CUDA(cudaMemcpyAsync(b, h->conv_out.b, d.out_ch * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      h->conv_out_pad = h->conv_out;
+      h->conv_out_pad.cout = 32;
+      h->conv_out_pad.w = o;
+      h->conv_out_pad.b = b;
+      h->conv_out_pad.wb = to_bf16(o, 32 * row);
+    }
     ECHO_CUDA(cudaFuncSetAttribute(vq_quantize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)d.n_embed * 16)));
     ECHO_CUDA(cudaStreamSynchronize(s));
     // size the workspace with a dry run at full capacity
