@@ -123,6 +123,32 @@ def layout_rate(dev, pk, precision, steps=200):
             "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"]}}
 
 
+def vqvae_decode_rate(dev, precision):
+    """Secondary figure (the step right after the shape chain): VQVAE.decode_no_quant over the scene's 16 latents."""
+    from echoscene_b200 import arch, modules
+    from oracle import cases
+    cfg = cases.vqvae_cfg()
+    dd = dict(double_z=False, z_channels=cfg.z_channels, resolution=cfg.resolution, in_channels=1, out_ch=cfg.out_ch, ch=cfg.ch,
+              ch_mult=list(cfg.ch_mult), num_res_blocks=cfg.num_res_blocks, attn_resolutions=[], dropout=0.0)
+    m = modules.VQVAE(dd, cfg.n_embed, cfg.embed_dim, precision=precision)
+    m.load_state_dict(arch.make_state_dict(arch.vqvae_decode_specs(cfg), cases.WEIGHT_SEED_VQVAE))
+    m = m.to(dev)
+    z = cases.vqvae_inputs(N_NODES, seed=3).to(dev)
+    for _ in range(2):
+        m.decode_no_quant(z)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(3):
+        out = m.decode_no_quant(z)
+    e1.record()
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    ms = e0.elapsed_time(e1) / 3
+    return {"ms_per_scene": ms, "objects": N_NODES, "dtype": precision, "unit": "ms per 16-object decode",
+            "tflops_algorithmic": 723e9 * N_NODES / (ms * 1e-3) / 1e12}
+
+
 def conv_kernel_roofline(dev, pk):
     """The dominant kernel timed alone: tcgen05 implicit-GEMM conv 224@16^3 -> 224, N=16 objects (7 of these per step,
     SURVEY Appendix E).  CUDA events on the launching stream; L2 flushed between launches."""
@@ -377,6 +403,13 @@ def main():
                 "roofline": roof}
         if world == 1:
             line["layout_branch"] = layout_rate(dev, pk, "bf16" if precision == "bf16" else "fp32")
+            line["vqvae_decode"] = vqvae_decode_rate(dev, "bf16" if precision == "bf16" else "fp32")
+            # the reference runs the chains back to back (EchoScene.py:403-418): 1000 DDPM layout steps, 100 DDIM shape
+            # steps, one decode
+            line["full_chain_seconds_per_scene"] = {
+                "layout_1000_ddpm_steps": 1000.0 / line["layout_branch"]["value"], "shape_100_ddim_steps": DDIM_STEPS / value,
+                "vqvae_decode": line["vqvae_decode"]["ms_per_scene"] * 1e-3,
+                "total": 1000.0 / line["layout_branch"]["value"] + DDIM_STEPS / value + line["vqvae_decode"]["ms_per_scene"] * 1e-3}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             rate, tcpu = cpu_reference_rate(2, 2, 1)
