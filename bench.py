@@ -117,9 +117,9 @@ def layout_rate(dev, pk, precision, steps=200):
     torch.cuda.synchronize()
     m.frozen = False
     ms = e0.elapsed_time(e1) / steps
-    live_bytes = 115.30e6 * (2 if precision == "bf16" else 4)    # live parameters read once per step
+    live_bytes = 115.30e6 * 4    # live parameters read once per step; the layout branch streams fp32 weights in both modes
     ach = live_bytes / (ms * 1e-3) / 1e9
-    return {"value": 1e3 / ms, "unit": "layout-steps/s", "ms_per_step": ms, "n_nodes": N_NODES, "dtype": precision,
+    return {"value": 1e3 / ms, "unit": "layout-steps/s", "ms_per_step": ms, "n_nodes": N_NODES, "dtype": "f32",
             "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"]}}
 
 

@@ -27,7 +27,7 @@ struct echo_layout {
   std::vector<float> h_tab;
   float* d_tab = nullptr;
   float *temb = nullptr, *e1 = nullptr, *emb = nullptr, *emb_act = nullptr, *node = nullptr, *pred = nullptr, *latent = nullptr;
-  float *embout = nullptr, *v2 = nullptr, *a2vec = nullptr, *eps = nullptr;
+  float *embout = nullptr, *a2vec = nullptr, *eps = nullptr;
   int64_t* t_dev = nullptr;
   // CUDA-graph replay of one DDPM iteration (layout_step)
   float *sx = nullptr, *sobj = nullptr, *snoise = nullptr, *sout = nullptr;
@@ -39,6 +39,11 @@ struct echo_layout {
   bool graph_failed = false;
   std::vector<int> a2_off;
   int a2_total = 0;
+  // One token per object makes attention the identity on V (softmax over one key == 1), so each attention is two Linears
+  // with nothing in between: they are multiplied once at creation.  attn1: to_out . to_v  (C x C per block);
+  // attn2: [to_out_i . to_v_i] of all blocks stacked (a2_total x context_dim) -- one launch instead of 1 + 11.
+  std::vector<ConvW> attn1_fused;   // by attention index
+  ConvW attn2_fused;
   int N = 0;   // rows of the current call
 
   float* buf(int C) { return arena.alloc_n<float>((size_t)N * C); }
@@ -63,8 +68,10 @@ struct echo_layout {
     a.eps = in.eps; a.pro_act = in.silu ? 1 : 0;
     if (in.pro == PRO_GN) a.cpg = in.width() / 32;
     ECHO_CHECK((in.pro == PRO_GEGLU ? in.C : in.width()) == w.cin, "layout: linear input width %d != %d", in.width(), w.cin);
-    if (prec == ECHO_PREC_BF16 && w.wb && N <= 64) { a.W = w.wb; a.w_dt = BF16; }
-    else { a.W = w.w; a.w_dt = F32; }
+    // fp32 weights in every precision mode: a layout layer is a latency chain, not a bandwidth problem (461 MB per step
+    // against 1.6 ms), and the fp32 loader is the shorter instruction stream -- measured 1.60 ms/step against 1.70 with
+    // bf16 weights; it also keeps the layout branch on the 1e-3 parity contract in ECHO_PREC_BF16
+    a.W = w.w; a.w_dt = F32;
     linear_auto(a, s);
   }
   void lin(const float* X, int64_t ldx, const ConvW& w, float* Y, int64_t ldy, const float* res, int64_t ld_res, int in_act, int act,
@@ -104,11 +111,9 @@ struct echo_layout {
     In xn = plain(x, C); xn.pro = PRO_GN; xn.nw = &a.norm; xn.eps = 1e-6f;            // Normalize (eps 1e-6) -> proj_in
     float* t0 = buf(C);
     lin(xn, a.proj_in, t0, C, nullptr, 0, 0, s);
-    In l1 = plain(t0, C); l1.pro = PRO_LN; l1.nw = &a.ln1;                             // norm1 -> attn1.to_v (softmax over one key == 1)
-    float* v = buf(C);
-    lin(l1, a.v_only, v, C, nullptr, 0, 0, s);
-    float* t1 = buf(C);                                                                 // to_out + x + [attn2: to_out(to_v(context))]
-    lin(plain(v, C), a.attn1_out, t1, C, t0, C, 0, s, a2vec + a2_off[ai], a2_total);
+    In l1 = plain(t0, C); l1.pro = PRO_LN; l1.nw = &a.ln1;                             // norm1 -> attn1 = to_out(to_v(.)), one matrix
+    float* t1 = buf(C);                                                                 // ... + x + [attn2: to_out(to_v(context))]
+    lin(l1, attn1_fused[ai], t1, C, t0, C, 0, s, a2vec + a2_off[ai], a2_total);
     In l3 = plain(t1, C); l3.pro = PRO_LN; l3.nw = &a.ln3;                             // norm3 -> GEGLU proj
     float* f1 = buf(8 * C);
     lin(l3, a.ff1, f1, 8 * C, nullptr, 0, 0, s);
@@ -144,17 +149,7 @@ struct echo_layout {
     // all 22 emb_layers share SiLU(emb): activate once instead of in every warp of the stacked projection
     silu_f32(emb, emb_act, (int64_t)N * E, s);
     lin(emb_act, E, plan.emb_stack, embout, plan.emb_total, nullptr, 0, 0, 0, s);
-    lin(latent, d.context_dim, plan.v2_stack, v2, plan.v2_total, nullptr, 0, 0, 0, s);
-    {
-      int ai = 0;
-      auto a2 = [&](const AttnW& a) {
-        lin(v2 + a.v2_off, plan.v2_total, a.attn2_out, a2vec + a2_off[ai], a2_total, nullptr, 0, 0, 0, s);
-        ++ai;
-      };
-      for (auto& b : plan.in_blocks) if (b.attn) a2(b.at);
-      a2(plan.mid_at);
-      for (auto& b : plan.out_blocks) if (b.attn) a2(b.at);
-    }
+    lin(latent, d.context_dim, attn2_fused, a2vec, a2_total, nullptr, 0, 0, 0, s);   // all 11 attn2 vectors at once
     std::vector<std::pair<const float*, int>> hs;
     const float* h = nullptr;
     int hc = 0, ai = 0;
@@ -252,7 +247,7 @@ echo_layout* layout_create(const echo_layout_desc_t* desc, const echo_weight_t* 
     cfg.channel_mult.assign(d.channel_mult, d.channel_mult + d.num_levels);
     cfg.attention_resolutions.assign(d.attention_resolutions, d.attention_resolutions + d.num_attention_resolutions);
     cfg.num_res_blocks = d.num_res_blocks; cfg.num_heads = d.num_heads; cfg.context_dim = d.context_dim;
-    cfg.want_bf16 = h->prec == ECHO_PREC_BF16;
+    cfg.want_bf16 = false;   // see lin(): the layout branch streams fp32 weights in both modes
     build_unet_plan(wm, cfg, h->pool, h->plan, s);
     const int mc = d.model_channels, E = 4 * mc, gd = d.gconv_dim;
     auto linear = [&](const std::string& p, int cin, int cout) {
@@ -310,7 +305,6 @@ echo_layout* layout_create(const echo_layout_desc_t* desc, const echo_weight_t* 
     h->pred = h->pool.alloc_n<float>(T * 2 * gd);
     h->latent = h->pool.alloc_n<float>(N * d.context_dim);
     h->embout = h->pool.alloc_n<float>(N * h->plan.emb_total);
-    h->v2 = h->pool.alloc_n<float>(N * h->plan.v2_total);
     h->a2_total = h->plan.v2_total;
     h->a2vec = h->pool.alloc_n<float>(N * h->a2_total);
     h->eps = h->pool.alloc_n<float>(N * d.out_channels);
@@ -326,6 +320,45 @@ echo_layout* layout_create(const echo_layout_desc_t* desc, const echo_weight_t* 
       for (auto& b : h->plan.in_blocks) if (b.attn) add(b.at);
       add(h->plan.mid_at);
       for (auto& b : h->plan.out_blocks) if (b.attn) add(b.at);
+    }
+    {   // fused attention matrices (see the member comments): products in fp32 on the device, bf16 copies in bf16 mode
+      cudaStream_t s0 = 0;
+      auto matmul = [&](const float* A, int M, int J, const float* B, int K, float* Cout) {   // C[M,K] = A[M,J] B[J,K]
+        GemmArgs g;
+        g.A = A; g.n = 1; g.w = M; g.ow = M; g.cin = J; g.lda = J;
+        g.W = B; g.w_stride_n = 1; g.w_stride_k = K; g.cout = K;
+        g.out = Cout; g.ldo = K;
+        gemm_simt(g, s0);
+      };
+      auto to_bf16 = [&](const float* w, size_t n) {
+        __nv_bfloat16* o = h->pool.alloc_n<__nv_bfloat16>(n);
+        convert(w, F32, o, BF16, (int64_t)n, s0);
+        return (const __nv_bfloat16*)o;
+      };
+      const bool bf = false;   // fp32 weights in both modes, see lin()
+      const int ctx = d.context_dim;
+      float* w2 = h->pool.alloc_n<float>((size_t)h->a2_total * ctx);
+      float* b2 = h->pool.alloc_n<float>(h->a2_total);
+      int ai = 0;
+      auto fuse = [&](const AttnW& a) {
+        const int C = a.C;
+        ConvW f = a.attn1_out;                                              // bias of to_out; cin = cout = C
+        float* w1 = h->pool.alloc_n<float>((size_t)C * C);
+        matmul(a.attn1_out.w, C, C, a.v_only.w, C, w1);                     // to_v has no bias
+        f.w = w1;
+        f.wb = bf ? to_bf16(w1, (size_t)C * C) : nullptr;
+        h->attn1_fused.push_back(f);
+        const int off = h->a2_off[ai++];
+        matmul(a.attn2_out.w, C, C, h->plan.v2_stack.w + (size_t)a.v2_off * ctx, ctx, w2 + (size_t)off * ctx);
+        ECHO_CUDA(cudaMemcpyAsync(b2 + off, a.attn2_out.b, sizeof(float) * C, cudaMemcpyDeviceToDevice, s0));
+      };
+      for (auto& b : h->plan.in_blocks) if (b.attn) fuse(b.at);
+      fuse(h->plan.mid_at);
+      for (auto& b : h->plan.out_blocks) if (b.attn) fuse(b.at);
+      h->attn2_fused.cin = ctx; h->attn2_fused.cout = h->a2_total; h->attn2_fused.taps = 1;
+      h->attn2_fused.w = w2; h->attn2_fused.b = b2;
+      h->attn2_fused.wb = bf ? to_bf16(w2, (size_t)h->a2_total * ctx) : nullptr;
+      ECHO_CUDA(cudaStreamSynchronize(s0));
     }
     // workspace: every block output is (N, <= 2*mc*max_mult) fp32; ~60 live buffers is a generous bound
     int maxmult = 1;
