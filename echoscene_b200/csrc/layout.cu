@@ -44,6 +44,10 @@ struct echo_layout {
   // attn2: [to_out_i . to_v_i] of all blocks stacked (a2_total x context_dim) -- one launch instead of 1 + 11.
   std::vector<ConvW> attn1_fused;   // by attention index
   ConvW attn2_fused;
+  // the stacked emb_layers projection (46 M weights, the largest layer of the step) depends on the time embedding only,
+  // so it runs on a second stream beside the GCN chain and joins at the first ResBlock (a parallel branch of the graph)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int N = 0;   // rows of the current call
 
   float* buf(int C) { return arena.alloc_n<float>((size_t)N * C); }
@@ -144,11 +148,21 @@ struct echo_layout {
       if (d.enable_t_emb) lin(emb, E, time_emb_lin, node + od + gd, nd, nullptr, 0, 0, 0, s);
       prec = p;
     }
+    // all 22 emb_layers share SiLU(emb): activate once instead of in every warp of the stacked projection; fork it
+    static const bool no_side = getenv("ECHO_NO_LAYOUT_SIDE") != nullptr;
+    const bool fork = side && !no_side;
+    cudaStream_t q = s;
+    if (fork) {
+      ECHO_CUDA(cudaEventRecord(ev_fork, s));
+      ECHO_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+      q = side;
+    }
+    silu_f32(emb, emb_act, (int64_t)N * E, q);
+    lin(emb_act, E, plan.emb_stack, embout, plan.emb_total, nullptr, 0, 0, 0, q);
+    if (fork) ECHO_CUDA(cudaEventRecord(ev_join, side));
     if (T > 0) embedding_rows(pred_table, 2 * gd, g->triples, 3, 1, T, pred, 2 * gd, s);
     gcn.forward(g, node, pred, latent, nullptr, s);
-    // all 22 emb_layers share SiLU(emb): activate once instead of in every warp of the stacked projection
-    silu_f32(emb, emb_act, (int64_t)N * E, s);
-    lin(emb_act, E, plan.emb_stack, embout, plan.emb_total, nullptr, 0, 0, 0, s);
+    if (fork) ECHO_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
     lin(latent, d.context_dim, attn2_fused, a2vec, a2_total, nullptr, 0, 0, 0, s);   // all 11 attn2 vectors at once
     std::vector<std::pair<const float*, int>> hs;
     const float* h = nullptr;
@@ -321,6 +335,9 @@ echo_layout* layout_create(const echo_layout_desc_t* desc, const echo_weight_t* 
       add(h->plan.mid_at);
       for (auto& b : h->plan.out_blocks) if (b.attn) add(b.at);
     }
+    ECHO_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    ECHO_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    ECHO_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     {   // fused attention matrices (see the member comments): products in fp32 on the device, bf16 copies in bf16 mode
       cudaStream_t s0 = 0;
       auto matmul = [&](const float* A, int M, int J, const float* B, int K, float* Cout) {   // C[M,K] = A[M,J] B[J,K]
@@ -378,6 +395,9 @@ echo_layout* layout_create(const echo_layout_desc_t* desc, const echo_weight_t* 
 
 void layout_destroy(echo_layout* h) {
   if (!h) return;
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->gexec) cudaGraphExecDestroy(h->gexec);
   h->arena.destroy();
   h->pool.destroy();
