@@ -101,6 +101,7 @@ PROTOTYPES = {
     "echo_vqvae_destroy": (None, [_P]),
     "echo_op_conv3d": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "echo_op_upconv3d": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P]),
+    "echo_op_upconv3d_x2": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P]),
     "echo_op_linear": (C.c_int, [_P, _L, _I, _P, _P, _I, _P, _I, _P]),
     "echo_op_group_norm": (C.c_int, [_P, _I, _L, _I, _I, _P, _P, C.c_float, _I, _P, _P]),
     "echo_op_layer_norm": (C.c_int, [_P, _L, _I, _P, _P, C.c_float, _P, _P]),

@@ -329,23 +329,36 @@ int echo_op_conv3d(const float* x, int32_t n, int32_t d, int32_t h, int32_t w, i
   });
 }
 
+static void op_upconv3d_impl(const float* x, int32_t n, int32_t d, int32_t h, int32_t w, int32_t cin, const float* weight, const float* bias,
+                            int32_t cout, float* out, int32_t precision, void* stream, bool up_depth);
+
 int echo_op_upconv3d(const float* x, int32_t n, int32_t d, int32_t h, int32_t w, int32_t cin, const float* weight, const float* bias,
                      int32_t cout, float* out, int32_t precision, void* stream) {
-  return guard([&] {
+  return guard([&] { op_upconv3d_impl(x, n, d, h, w, cin, weight, bias, cout, out, precision, stream, false); });
+}
+
+int echo_op_upconv3d_x2(const float* x, int32_t n, int32_t d, int32_t h, int32_t w, int32_t cin, const float* weight, const float* bias,
+                        int32_t cout, float* out, int32_t precision, void* stream) {
+  return guard([&] { op_upconv3d_impl(x, n, d, h, w, cin, weight, bias, cout, out, precision, stream, true); });
+}
+
+static void op_upconv3d_impl(const float* x, int32_t n, int32_t d, int32_t h, int32_t w, int32_t cin, const float* weight, const float* bias,
+                            int32_t cout, float* out, int32_t precision, void* stream, bool up_depth) {
+  {
     ECHO_CHECK(x && weight && out, "op_upconv3d: bad arguments");
     ECHO_CHECK(precision == ECHO_PREC_BF16 && tc_available(), "op_upconv3d: the folded upsample conv is a tcgen05 (ECHO_PREC_BF16) kernel");
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t wn = (size_t)cout * cin * 27, fn = (size_t)cout * cin * 48;
+    const size_t wn = (size_t)cout * cin * 27, fn = (size_t)cout * cin * (up_depth ? 64 : 48);
     float* wr = (float*)g_scratch[0].get(wn * sizeof(float));
     repack_conv_weight(weight, cout, cin, 27, wr, s);
     std::vector<float> hsrc(wn), hdst(fn);
     ECHO_CUDA(cudaMemcpyAsync(hsrc.data(), wr, wn * sizeof(float), cudaMemcpyDeviceToHost, s));
     ECHO_CUDA(cudaStreamSynchronize(s));
-    fold_upsample_weight(hsrc.data(), cout, cin, hdst.data());
+    fold_upsample_weight(hsrc.data(), cout, cin, hdst.data(), up_depth);
     static Scratch fold32;
     float* wf = (float*)fold32.get(fn * sizeof(float));
     ECHO_CUDA(cudaMemcpyAsync(wf, hdst.data(), fn * sizeof(float), cudaMemcpyHostToDevice, s));
-    const int64_t rows_in = (int64_t)n * d * h * w, rows_out = rows_in * 4;
+    const int64_t rows_in = (int64_t)n * d * h * w, rows_out = rows_in * (up_depth ? 8 : 4);
     __nv_bfloat16* xb = (__nv_bfloat16*)g_scratch[1].get((size_t)rows_in * cin * 2);
     __nv_bfloat16* wb = (__nv_bfloat16*)g_scratch[2].get(fn * 2);
     __nv_bfloat16* ob = (__nv_bfloat16*)g_scratch[3].get((size_t)rows_out * cout * 2);
@@ -353,15 +366,15 @@ int echo_op_upconv3d(const float* x, int32_t n, int32_t d, int32_t h, int32_t w,
     convert(wf, F32, wb, BF16, (int64_t)fn, s);
     GemmArgs g;
     g.A = xb; g.a_dt = BF16; g.n = n; g.d = d; g.h = h; g.w = w; g.cin = cin; g.lda = cin;
-    g.od = d; g.oh = 2 * h; g.ow = 2 * w; g.up2 = 1;
+    g.od = up_depth ? 2 * d : d; g.oh = 2 * h; g.ow = 2 * w; g.up2 = up_depth ? 2 : 1;
     g.kd = g.kh = g.kw = 3; g.pd = g.ph = g.pw = 1;
-    g.W = wb; g.w_dt = BF16; g.w_stride_n = (int64_t)48 * cin; g.cout = cout; g.bias = bias;
+    g.W = wb; g.w_dt = BF16; g.w_stride_n = (int64_t)(up_depth ? 64 : 48) * cin; g.cout = cout; g.bias = bias;
     g.out = ob; g.out_dt = BF16; g.ldo = cout;
     ECHO_CHECK(gemm_tc_supported(g), "op_upconv3d: shape not supported by the tcgen05 kernel");
     gemm_tc(g, s);
     convert(ob, BF16, out, F32, rows_out * cout, s);
     ECHO_CUDA(cudaStreamSynchronize(s));   // hsrc / hdst are stack-scoped host staging
-  });
+  }
 }
 
 int echo_op_linear(const float* x, int64_t rows, int32_t cin, const float* weight, const float* bias, int32_t cout, float* out,

@@ -216,6 +216,10 @@ ECHO_API int echo_op_conv3d(const float* x, int32_t n, int32_t d, int32_t h, int
  * ECHO_PREC_BF16 only. */
 ECHO_API int echo_op_upconv3d(const float* x, int32_t n, int32_t d, int32_t h, int32_t w, int32_t cin,
                      const float* weight, const float* bias, int32_t cout, float* out, int32_t precision, void* stream);
+/* the same with the upsample doubling the depth as well (F.interpolate(scale_factor=2), vqvae_modules.py:35-39): eight output
+ * phases x 2x2x2 folded taps; x (n,d,h,w,cin) -> out (n,2d,2h,2w,cout) */
+ECHO_API int echo_op_upconv3d_x2(const float* x, int32_t n, int32_t d, int32_t h, int32_t w, int32_t cin,
+                        const float* weight, const float* bias, int32_t cout, float* out, int32_t precision, void* stream);
 ECHO_API int echo_op_linear(const float* x, int64_t rows, int32_t cin, const float* weight, const float* bias, int32_t cout,
                    float* out, int32_t precision, void* stream);
 ECHO_API int echo_op_group_norm(const float* x, int32_t n, int64_t voxels, int32_t c, int32_t groups, const float* gamma,

@@ -104,6 +104,23 @@ def _attention_ref(qkv, n, tokens, heads, dh):
     return out.permute(0, 2, 1, 3).reshape(n * tokens, C_)
 
 
+@pytest.mark.parametrize("n,c,cout,dhw", [(2, 256, 256, (16, 16, 16)), (1, 128, 128, (32, 32, 32)), (3, 64, 96, (4, 4, 8))])
+def test_upsample_x2_conv_folded(n, c, cout, dhw):
+    """Upsample(nearest x2 in d, h, w) + Conv3d k3 (vqvae_modules.py:24-39) as eight phase convolutions on the low-res input."""
+    _need_tc()
+    g = torch.Generator().manual_seed(c + cout + 1)
+    x = torch.randn(n, c, *dhw, generator=g).bfloat16().float()
+    w = (torch.randn(cout, c, 3, 3, 3, generator=g) / (c * 27) ** 0.5)
+    b = torch.randn(cout, generator=g)
+    want = F.conv3d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w, b, padding=1)
+    xc = _cl(x).cuda()
+    out = torch.empty(n, 2 * dhw[0], 2 * dhw[1], 2 * dhw[2], cout, device="cuda")
+    wd, bd = w.cuda().contiguous(), b.cuda()
+    _lib.check(_lib.lib().echo_op_upconv3d_x2(xc.data_ptr(), n, *dhw, c, wd.data_ptr(), bd.data_ptr(), cout, out.data_ptr(),
+                                              _lib.PREC_BF16, _lib.stream_ptr()))
+    assert_close(out.permute(0, 4, 1, 2, 3).cpu(), want, 1.5e-2, "folded x2 upsample conv")
+
+
 @pytest.mark.parametrize("n,tokens,heads,dh", [(2, 1024, 8, 56), (2, 256, 8, 84), (1, 50, 3, 20)])
 def test_attention_fp32(n, tokens, heads, dh):
     g = torch.Generator().manual_seed(tokens + dh)
