@@ -529,9 +529,12 @@ class VQVAE(_SpecModule):
             _lib.lib().echo_vqvae_destroy(self._handle)
             self._handle = None
 
+    max_chunk = 32   # objects decoded per library call: the decoder keeps ~0.5 GB of activations per object (bf16)
+
     @torch.no_grad()
     def decode_no_quant(self, h, force_not_quantize=False, return_indices: bool = False):
-        """h (N, 3, 16, 16, 16) -> SDF (N, 1, 64, 64, 64), network.py:95-103."""
+        """h (N, 3, 16, 16, 16) -> SDF (N, 1, 64, 64, 64), network.py:95-103.  Objects are independent (per-sample
+        GroupNorm and attention), so large batches are decoded in chunks of ``max_chunk`` with bit-identical results."""
         self._check_eval()
         if force_not_quantize:
             raise EchoError("VQVAE.decode_no_quant(force_not_quantize=True) is outside the hot path")
@@ -540,10 +543,15 @@ class VQVAE(_SpecModule):
         n, L = h.shape[0], c.latent_size
         assert h.shape == (n, c.z_channels, L, L, L), tuple(h.shape)
         h = h.float().contiguous()
-        self._ensure(n)
+        chunk = max(1, int(self.max_chunk))
+        self._ensure(min(n, chunk))
         out = torch.empty(n, c.out_ch, c.resolution, c.resolution, c.resolution, device=h.device)
         idx = torch.empty(n * L * L * L, dtype=torch.int32, device=h.device) if return_indices else None
-        _lib.check(_lib.lib().echo_vqvae_decode(self._handle, _lib.ptr(h), n, _lib.ptr(out), _lib.ptr(idx), _lib.stream_ptr()))
+        for b in range(0, n, chunk):
+            e = min(n, b + chunk)
+            _lib.check(_lib.lib().echo_vqvae_decode(self._handle, _lib.ptr(h[b:e]), e - b, _lib.ptr(out[b:e]),
+                                                    _lib.ptr(idx[b * L * L * L:e * L * L * L]) if idx is not None else None,
+                                                    _lib.stream_ptr()))
         return (out, idx) if return_indices else out
 
     def forward(self, *a, **k):

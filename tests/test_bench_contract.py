@@ -1,0 +1,52 @@
+"""CPU: the committed bench lines (profiles/r1_bench_*.json, written by bench.py on a B200) carry every key of the
+measurement contract, so a change to bench.py that drops one shows up here before a GPU run does."""
+import json
+import os
+
+import pytest
+
+PROF = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles")
+BASE = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+        "data", "config", "clocks", "gpu_launches", "e2e", "roofline"]
+
+
+def _line(name):
+    path = os.path.join(PROF, name)
+    if not os.path.exists(path):
+        pytest.skip(f"{name} not committed")
+    return json.load(open(path))
+
+
+def test_single_gpu_line():
+    d = _line("r1_bench_n1.json")
+    for k in BASE + ["cpu_baseline", "layout_branch"]:
+        assert k in d, k
+    assert d["metric"] == "denoiser-steps/sec" and d["unit"] == "steps/s" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert "workload" in d["config"] and "model" not in d["config"]
+    r = d["roofline"]
+    for k in ["bound", "achieved", "peak", "unit", "frac", "traffic"]:
+        assert k in r, k
+    assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= d["value"] * 1.02
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and "sample" in c
+    assert d["gpu_launches"] > 0
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+@pytest.mark.parametrize("name,n", [("r1_bench_n2.json", 2), ("r1_bench_n4.json", 4)])
+def test_multi_gpu_lines(name, n):
+    d = _line(name)
+    for k in BASE:
+        assert k in d, k
+    assert d["n_gpus"] == n and d["scaling"] == "weak" and d["config"]["scenes"] == n
+
+
+def test_reference_arm_line():
+    d = _line("r1_bench_reference_arm.json")
+    assert d["impl"] == "reference" and d["metric"] == "denoiser-steps/sec"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert d["cpu_baseline"]["value"] == d["value"]

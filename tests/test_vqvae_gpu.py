@@ -41,6 +41,9 @@ def test_vqvae_decode_objects_are_independent_and_deterministic():
     one = m.decode_no_quant(z[1:2])
     assert torch.equal(a[1:2], one)
     assert m.decode_no_quant(z[:0]).shape == (0, 1, 64, 64, 64)         # empty batch
+    m.max_chunk = 2                                                      # chunked decoding (3 = 2 + 1) is bit-identical
+    c, idx = m.decode_no_quant(z, return_indices=True)
+    assert torch.equal(c, a) and idx.shape == (3 * 4096,)
 
 
 def test_vqvae_decode_bf16_vs_reference_golden():
