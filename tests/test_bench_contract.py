@@ -37,7 +37,7 @@ def test_single_gpu_line():
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
 
 
-@pytest.mark.parametrize("name,n", [("r1_bench_n2.json", 2), ("r1_bench_n4.json", 4)])
+@pytest.mark.parametrize("name,n", [("r1_bench_n2.json", 2), ("r1_bench_n4.json", 4), ("r1_bench_n8.json", 8)])
 def test_multi_gpu_lines(name, n):
     d = _line(name)
     for k in BASE:
