@@ -81,6 +81,12 @@ int echo_has_tcgen05(void) {
 void echo_debug_set_tc_mode(int mode) { echo::set_tc_mode(mode); }
 void echo_debug_probe_begin(int64_t rows, int32_t cin, int32_t cout, int32_t ksize) { echo::tc_probe_begin(rows, cin, cout, ksize); }
 int32_t echo_debug_probe_end(double* avg_ms) { return echo::tc_probe_end(avg_ms); }
+int echo_debug_fold_upsample_weight(const float* w_host, int32_t cout, int32_t cin, int32_t up_depth, float* out_host) {
+  return guard([&] {
+    ECHO_CHECK(w_host && out_host && cout > 0 && cin > 0, "fold_upsample_weight: bad arguments");
+    fold_upsample_weight(w_host, cout, cin, out_host, up_depth != 0);
+  });
+}
 void echo_debug_probe_timeline(void* buf_dev) { echo::tc_probe_timeline((unsigned long long*)buf_dev); }
 int64_t echo_launch_count(void) { return g_launches; }
 void echo_launch_count_reset(void) { g_launches = 0; }

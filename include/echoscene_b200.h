@@ -126,6 +126,11 @@ ECHO_API int32_t echo_debug_probe_end(double* avg_ms);
 /* The next probed launch writes the timeline of its first CTA (tag << 32 | tile, globaltimer ns pairs after a count word)
  * into buf_dev (device memory, >= 8001 x 8 bytes, zeroed by the caller): where a tile's time goes (tools/gemm_timeline.py). */
 ECHO_API void echo_debug_probe_timeline(void* buf_dev);
+/* Host-only (no GPU needed): the weight fold behind the upsample-folded convolutions.  w_host [cout][27 taps (kd,kh,kw)][cin]
+ * -> out_host [cout][4 phases (py,px)][12 taps (kd,a,b)][cin] (up_depth = 0, nearest x(1,2,2)) or [cout][8 phases
+ * (pz,py,px)][8 taps (a_d,a_h,a_w)][cin] (up_depth = 1, nearest x2); tap a of phase p along an axis reads low-res offset
+ * p - 1 + a.  Exported so the fold can be checked against upsample + conv on the CPU (tests/test_fold_host.py). */
+ECHO_API int echo_debug_fold_upsample_weight(const float* w_host, int32_t cout, int32_t cin, int32_t up_depth, float* out_host);
 
 /* ---- graph: edges = stack([s, o]) of `triples` (T,3) int64 [s,p,o] — denoise_net.py:759-761, graph.py:142-143 */
 ECHO_API int echo_graph_create(echo_graph_t** out, const int64_t* triples_dev, int32_t n_triples, int32_t n_nodes, void* stream);
