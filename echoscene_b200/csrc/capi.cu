@@ -87,6 +87,10 @@ int echo_debug_fold_upsample_weight(const float* w_host, int32_t cout, int32_t c
     fold_upsample_weight(w_host, cout, cin, out_host, up_depth != 0);
   });
 }
+void echo_debug_tc_plan(int32_t n, int32_t d, int32_t h, int32_t w, int32_t cin, int32_t cout, int32_t ksize, int32_t epi, int32_t up2,
+                        int32_t allow_splitk, int32_t sms, int32_t* out4) {
+  echo::tc_plan_describe(n, d, h, w, cin, cout, ksize, epi, up2, allow_splitk, sms, out4);
+}
 void echo_debug_probe_timeline(void* buf_dev) { echo::tc_probe_timeline((unsigned long long*)buf_dev); }
 int64_t echo_launch_count(void) { return g_launches; }
 void echo_launch_count_reset(void) { g_launches = 0; }

@@ -857,6 +857,21 @@ int gemm_tc_colsum_rows_per_obj(const GemmArgs& g) {
   return ge.vm_tiles;
 }
 
+// host-only view of the launch plan for a (n, d, h, w, cin) -> cout contraction on `sms` SMs (tests/test_plan_host.py)
+void tc_plan_describe(int n, int d, int h, int w, int cin, int cout, int ksize, int epi, int up2, int allow_splitk, int sms, int* out4) {
+  GemmArgs g;
+  g.a_dt = BF16; g.w_dt = BF16; g.out_dt = BF16;
+  g.n = n; g.d = d; g.h = h; g.w = w; g.cin = cin; g.lda = cin; g.cout = cout;
+  g.kd = g.kh = g.kw = ksize; g.pd = g.ph = g.pw = ksize / 2;
+  g.up2 = up2; g.epi = epi;
+  g.od = up2 == 2 ? 2 * d : d; g.oh = up2 ? 2 * h : h; g.ow = up2 ? 2 * w : w;
+  static float dummy;
+  g.splitk_ws = allow_splitk ? (void*)&dummy : nullptr;
+  const TcGeom ge = tc_geom(g);
+  const TcPlan p = tc_plan(g, ge, sms);
+  out4[0] = p.block_n; out4[1] = p.msub; out4[2] = p.splitk; out4[3] = p.cta2 ? 1 : 0;
+}
+
 // floats of one partial row ([chunk][slot][2]) for `c` channels; 0 if c does not decompose into 7-channel blocks per group
 size_t gemm_tc_colsum_row_floats(int c) { return c % (32 * CS_SB) == 0 ? (size_t)(c / 32) * CS_SLOTS * 2 : 0; }
 

@@ -63,6 +63,8 @@ int gemm_tc_colsum_rows_per_obj(const GemmArgs& g);
 // floats of one partial row for a tensor with c channels: [c/32 chunks][8 slots][2] -- (sum, sumsq) of the 7-channel blocks
 // every 32-column chunk touches (slot s of chunk q <-> block 32q/7 + s); 0 when c is not a multiple of 224 (32 groups x 7)
 size_t gemm_tc_colsum_row_floats(int c);
+// the launch plan gemm_tc() would pick (host-only): out4 = {block_n, sub-blocks per CTA, split-K, CTA pairs}
+void tc_plan_describe(int n, int d, int h, int w, int cin, int cout, int ksize, int epi, int up2, int allow_splitk, int sms, int* out4);
 // bytes of fp32 workspace that let gemm_tc() split the reduction of this problem (0: never split)
 size_t gemm_tc_splitk_ws_bytes(const GemmArgs& g);
 // GroupNorm(+SiLU) with the statistics folded from the producer's column partials inside the apply kernel; `xb` != null:

@@ -126,6 +126,11 @@ ECHO_API int32_t echo_debug_probe_end(double* avg_ms);
 /* The next probed launch writes the timeline of its first CTA (tag << 32 | tile, globaltimer ns pairs after a count word)
  * into buf_dev (device memory, >= 8001 x 8 bytes, zeroed by the caller): where a tile's time goes (tools/gemm_timeline.py). */
 ECHO_API void echo_debug_probe_timeline(void* buf_dev);
+/* Host-only: the launch plan of the tcgen05 contraction kernel for an (n, d, h, w, cin) -> cout problem on `sms` SMs:
+ * out4 = {tile width, 128-row sub-blocks per CTA, split-K factor, CTA pairs}.  epi = 1: GEGLU epilogue; up2 = 1 / 2: conv after a
+ * nearest x(1,2,2) / x2 upsample; allow_splitk: a split-K workspace is offered. */
+ECHO_API void echo_debug_tc_plan(int32_t n, int32_t d, int32_t h, int32_t w, int32_t cin, int32_t cout, int32_t ksize, int32_t epi,
+                        int32_t up2, int32_t allow_splitk, int32_t sms, int32_t* out4);
 /* Host-only (no GPU needed): the weight fold behind the upsample-folded convolutions.  w_host [cout][27 taps (kd,kh,kw)][cin]
  * -> out_host [cout][4 phases (py,px)][12 taps (kd,a,b)][cin] (up_depth = 0, nearest x(1,2,2)) or [cout][8 phases
  * (pz,py,px)][8 taps (a_d,a_h,a_w)][cin] (up_depth = 1, nearest x2); tap a of phase p along an axis reads low-res offset
