@@ -50,3 +50,19 @@ def test_reference_arm_line():
     assert d["impl"] == "reference" and d["metric"] == "denoiser-steps/sec"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["cpu_baseline"]["value"] == d["value"]
+
+
+def test_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` (the driver's reference arm) runs without a GPU and prints one contract line."""
+    import subprocess
+    import sys
+    root = os.path.dirname(PROF)
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "denoiser-steps/sec" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
