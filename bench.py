@@ -372,8 +372,9 @@ def main():
         flop_launch = 2.0 * N_NODES * 4096 * 27 * 224 * 224
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel: Conv3d 3x3x3 224->224 @16^3 x 16 objects (7 launches per step, SURVEY App. E)",
                 "achieved": None, "peak": peak, "unit": "TFLOP/s", "frac": None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1_ncu_conv224.txt (ncu --set full)
-                "traffic": 32.29e6,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1_ncu_conv224.txt (ncu --set full):
+                # 32.18 MB + 0.16 MB -- the bf16 input and the weights once; the output (29 MB) stays in the 126 MB L2
+                "traffic": 32.34e6,
                 "algorithmic_bytes": 2.0 * (2 * N_NODES * 4096 * 224) + 2.0 * 27 * 224 * 224,
                 "flop_per_launch": flop_launch,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['source']}): kernel timed inside a long step",
