@@ -315,6 +315,45 @@ def unet3d_specs(cfg: UNet3DConfig) -> Specs:
 
 
 @dataclass
+class SceneEncoderConfig:
+    """The once-per-scene encoders of Sg2ScDiffModel (model/EchoScene.py:15-128, as built by SGDiff.py:21-22:
+    embedding_dim = 64, mlp_normalization = 'batch', gconv_num_layers = 5, CLIP features on)."""
+    gconv_dim: int = 64
+    add_dim: int = 512            # CLIP ViT-B/32 feature width (use_clip)
+    num_objs: int = 36            # len(vocab['object_idx_to_name']) incl. '_scene_'
+    num_preds: int = 16
+    num_layers: int = 5
+    residual: bool = True
+    rel_s_hidden: int = 960
+    context_dim: int = 1280
+
+    @property
+    def feat_dim(self) -> int:    # out_dim_ini_encoder == out_dim_manipulator
+        return 2 * self.gconv_dim + self.add_dim
+
+    def gcn_ec(self) -> GCNConfig:
+        return GCNConfig(self.feat_dim, self.feat_dim, self.num_layers, 4 * self.gconv_dim, self.feat_dim, self.residual)
+
+    def gcn_manipulation(self) -> GCNConfig:
+        din = self.feat_dim + self.gconv_dim + self.feat_dim   # latent_f | change flag | obj embedding + CLIP
+        return GCNConfig(din, self.feat_dim, min(self.num_layers, 5), 4 * self.gconv_dim, self.feat_dim, self.residual)
+
+
+def scene_encoder_specs(cfg: SceneEncoderConfig) -> Specs:
+    """The tensors Sg2ScDiffModel.sample touches before the two chains start (EchoScene.py:143-157, 181-195, 388-413):
+    embeddings, gconv_net_ec, gconv_net_manipulation, rel_s_mlp (make_mlp([640, 960, 1280], 'batch', norelu=True))."""
+    sp: Dict[str, ParamSpec] = OrderedDict()
+    sp["obj_embeddings_ec.weight"] = ParamSpec((cfg.num_objs + 1, 2 * cfg.gconv_dim), "normal")
+    sp["pred_embeddings_ec.weight"] = ParamSpec((cfg.num_preds, 2 * cfg.gconv_dim), "normal")
+    sp.update(gcn_specs(cfg.gcn_ec(), "gconv_net_ec."))
+    sp.update(gcn_specs(cfg.gcn_manipulation(), "gconv_net_manipulation."))
+    _lin(sp, "rel_s_mlp.0", cfg.feat_dim, cfg.rel_s_hidden, w_init="kaiming_normal")
+    _bn(sp, "rel_s_mlp.1", cfg.rel_s_hidden)
+    _lin(sp, "rel_s_mlp.3", cfg.rel_s_hidden, cfg.context_dim, w_init="kaiming_normal")
+    return sp
+
+
+@dataclass
 class VQVAEConfig:
     """model.params of config/vqvae_snet.yaml:5-19 (the decode half)."""
     embed_dim: int = 3

@@ -468,3 +468,31 @@ def vqvae_decode_no_quant(sd: SD, cfg, h: Tensor) -> Tensor:
     quant, _ = vq_quantize(sd, h)
     quant = _conv3(sd, "post_quant_conv", quant, 0)
     return vq_decoder(sd, cfg, quant)
+
+
+# --------------------------------------------------------------------------------------
+# once-per-scene encoders of Sg2ScDiffModel.sample, model/EchoScene.py:143-157, 181-195, 388-413
+# --------------------------------------------------------------------------------------
+
+
+def scene_encode(sd: SD, cfg, objs: Tensor, triples: Tensor, text_feat: Tensor, rel_feat: Tensor) -> Dict[str, Tensor]:
+    """What `sample` computes before the layout and shape chains: init_encoder (embeddings + CLIP -> gconv_net_ec), the zero
+    change vector, manipulate (gconv_net_manipulation) and the two rel_s_mlp conditionings.
+      obj_embed   (N, 640)    -> layout branch `obj_embed`                     (prepare_boxes(..., obj_embed_, ...))
+      latent      (N, 640)    -> layout branch relation condition
+      uc_s, c_s   (N, 1, 1280) -> shape branch unconditional / conditional context (EchoScene.py:405-410)"""
+    edges, p = edges_of(triples)
+    obj_embed = torch.cat([text_feat, F.embedding(objs, sd["obj_embeddings_ec.weight"])], dim=1)       # :149-153
+    pred_embed = torch.cat([rel_feat, F.embedding(p, sd["pred_embeddings_ec.weight"])], dim=1)
+    latent_obj, _ = graph_triple_conv_net(sd, "gconv_net_ec.", obj_embed, pred_embed, edges, cfg.num_layers)   # :155
+    change = torch.zeros(latent_obj.shape[0], cfg.gconv_dim, dtype=latent_obj.dtype, device=latent_obj.device)  # :393-397
+    latent_in = torch.cat([latent_obj, change], dim=1)
+    obj_vecs = torch.cat([latent_in, obj_embed], dim=1)                                                # manipulate, :186-193
+    latent, _ = graph_triple_conv_net(sd, "gconv_net_manipulation.", obj_vecs, pred_embed, edges, min(cfg.num_layers, 5))
+
+    def rel_s(x):   # make_mlp([640, 960, 1280], batch_norm='batch', norelu=True): Linear, BN, ReLU, Linear
+        h = F.relu(_bn_eval(sd, "rel_s_mlp.1", _linear(sd, "rel_s_mlp.0", x)))
+        return _linear(sd, "rel_s_mlp.3", h)
+
+    return {"obj_embed": obj_embed, "pred_embed": pred_embed, "latent": latent,
+            "uc_s": rel_s(obj_embed).unsqueeze(1), "c_s": rel_s(latent).unsqueeze(1)}

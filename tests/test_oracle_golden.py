@@ -92,3 +92,22 @@ def test_vqvae_decode_oracle_vs_reference():
         dec = orc.vqvae_decode_no_quant(sd, cfg, z)
     assert dec.shape == (1, 1, 64, 64, 64)
     assert max(rel_err(dec[:, :, ::2, ::2, ::2], G["dec_sub"][:1])) < TOL
+
+
+def test_scene_encoder_oracle_vs_reference():
+    """what Sg2ScDiffModel.sample computes before the chains (init_encoder, manipulate, rel_s_mlp) against the
+    outputs of the reference's own methods (oracle/gen_golden_scene.py)."""
+    pin = json.load(open(os.path.join(GOLD, "PINNING.json")))["cases"]["scene_encode"]
+    assert pin["rel_l2"] < 1e-6
+    cfg = cases.scene_cfg()
+    specs = arch.scene_encoder_specs(cfg)
+    assert arch.count_params(specs) == pin["detail"]["params"]
+    sd = arch.make_state_dict(specs, cases.WEIGHT_SEED_SCENE)
+    g, objs, text, rel = cases.scene_inputs()
+    G = gold("scene_encode.pt")
+    with torch.no_grad():
+        out = orc.scene_encode(sd, cfg, objs, g.triples, text, rel)
+    for k in ("obj_embed", "latent", "uc_s", "c_s"):
+        assert out[k].shape == G[k].shape, k
+        assert max(rel_err(out[k], G[k])) < TOL, k
+    assert out["uc_s"].shape == (8, 1, 1280) and out["obj_embed"].shape == (8, 640)
