@@ -406,6 +406,33 @@ def vqvae_decode_specs(cfg: VQVAEConfig) -> Specs:
     return sp
 
 
+def vqvae_encode_specs(cfg: VQVAEConfig, in_channels: int = 1) -> Specs:
+    """The part of the VQVAE state_dict that `VQVAE.encode_no_quant` touches (network.py:84-88): Encoder3D
+    (vqvae_modules.py:178-289; attn_resolutions = [] -> only mid.attn_1) and quant_conv."""
+    sp: Dict[str, ParamSpec] = OrderedDict()
+    nres = len(cfg.ch_mult)
+    in_mult = (1,) + tuple(cfg.ch_mult)
+    _conv(sp, "encoder.conv_in", in_channels, cfg.ch, 3, 3)
+    block_in = cfg.ch
+    for lvl in range(nres):
+        block_in = cfg.ch * in_mult[lvl]
+        block_out = cfg.ch * cfg.ch_mult[lvl]
+        for i in range(cfg.num_res_blocks):
+            _vq_resnet(sp, f"encoder.down.{lvl}.block.{i}", block_in, block_out)
+            block_in = block_out
+        if lvl != nres - 1:
+            _conv(sp, f"encoder.down.{lvl}.downsample.conv", block_in, block_in, 3, 3)
+    _vq_resnet(sp, "encoder.mid.block_1", block_in, block_in)
+    _norm(sp, "encoder.mid.attn_1.norm", block_in)
+    for n in ("q", "k", "v", "proj_out"):
+        _conv(sp, "encoder.mid.attn_1." + n, block_in, block_in, 1, 3)
+    _vq_resnet(sp, "encoder.mid.block_2", block_in, block_in)
+    _norm(sp, "encoder.norm_out", block_in)
+    _conv(sp, "encoder.conv_out", block_in, cfg.z_channels, 3, 3)
+    _conv(sp, "quant_conv", cfg.z_channels, cfg.embed_dim, 1, 3)
+    return sp
+
+
 def init_tensor(spec: ParamSpec, gen: torch.Generator, rerandomize_zero: bool = False,
                 randomize_bn: bool = False) -> torch.Tensor:
     """Draw one tensor following the reference's initialisers.

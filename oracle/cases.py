@@ -103,3 +103,9 @@ def scene_inputs(case: GraphCase = SCENE_CASE, cfg: "arch.SceneEncoderConfig" = 
     text = torch.nn.functional.normalize(torch.randn(case.n_nodes, cfg.add_dim, generator=gen), dim=1) * 10
     rel = torch.nn.functional.normalize(torch.randn(case.n_triples, cfg.add_dim, generator=gen), dim=1) * 10
     return g, objs, text, rel
+
+
+def vqvae_sdf_inputs(n: int = 1, seed: int = 8):
+    """truncated-SDF-like volumes (N, 1, 64, 64, 64), clamped to +-0.2 as the dataset does (threedfront_dataset.py)"""
+    gen = torch.Generator().manual_seed(seed + 700)
+    return (torch.randn(n, 1, 64, 64, 64, generator=gen) * 0.15).clamp(-0.2, 0.2)

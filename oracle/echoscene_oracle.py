@@ -496,3 +496,26 @@ def scene_encode(sd: SD, cfg, objs: Tensor, triples: Tensor, text_feat: Tensor, 
 
     return {"obj_embed": obj_embed, "pred_embed": pred_embed, "latent": latent,
             "uc_s": rel_s(obj_embed).unsqueeze(1), "c_s": rel_s(latent).unsqueeze(1)}
+
+
+def vq_encoder(sd: SD, cfg, x: Tensor, p: str = "encoder") -> Tensor:
+    """Encoder3D.forward.  vqvae_modules.py:256-289.  Downsample = zero-pad (0,1) on every spatial axis + Conv3d k3 stride 2
+    pad 0 (:42-58)."""
+    h = _conv3(sd, p + ".conv_in", x, 1)
+    nres = len(cfg.ch_mult)
+    for lvl in range(nres):
+        for i in range(cfg.num_res_blocks):
+            h = vq_resnet_block(sd, f"{p}.down.{lvl}.block.{i}", h)
+        if lvl != nres - 1:
+            h = F.pad(h, (0, 1, 0, 1, 0, 1), mode="constant", value=0)
+            h = F.conv3d(h, sd[f"{p}.down.{lvl}.downsample.conv.weight"], sd[f"{p}.down.{lvl}.downsample.conv.bias"], stride=2, padding=0)
+    h = vq_resnet_block(sd, p + ".mid.block_1", h)
+    h = vq_attn_block(sd, p + ".mid.attn_1", h)
+    h = vq_resnet_block(sd, p + ".mid.block_2", h)
+    h = F.gelu(_vq_norm(sd, p + ".norm_out", h))
+    return _conv3(sd, p + ".conv_out", h, 1)
+
+
+def vqvae_encode_no_quant(sd: SD, cfg, x: Tensor) -> Tensor:
+    """VQVAE.encode_no_quant(x): encoder -> quant_conv (no quantisation).  network.py:84-88; x (N, 1, 64, 64, 64) SDF."""
+    return _conv3(sd, "quant_conv", vq_encoder(sd, cfg, x), 0)

@@ -54,8 +54,24 @@ def main():
            "objects": int(z.shape[0]), "params": arch.count_params(arch.vqvae_decode_specs(cfg))}
     torch.save({"dec_sub": want[:, :, ::2, ::2, ::2].contiguous(), "dec_sum": want.double().sum(), "dec_abs_sum": want.double().abs().sum(),
                 "indices": info[2].to(torch.int32), "quant": quant_ref}, os.path.join(GOLD, "vqvae_decode.pt"))
+    # ---- encode_no_quant (oracle only): encoder + quant_conv, one object ----
+    esd = arch.make_state_dict(arch.vqvae_encode_specs(cfg), cases.WEIGHT_SEED_VQVAE + 1)
+    net2 = ref.VQVAE(vq["ddconfig"], vq["n_embed"], vq["embed_dim"]).eval()
+    res2 = net2.load_state_dict(esd, strict=False)
+    assert not res2.unexpected_keys, res2.unexpected_keys
+    assert all(k.startswith("decoder.") or k.startswith("post_quant_conv.") or k.startswith("quantize.") for k in res2.missing_keys)
+    xs = cases.vqvae_sdf_inputs()
+    with torch.no_grad():
+        ewant = net2.encode_no_quant(xs)
+        egot = orc.vqvae_encode_no_quant(esd, cfg, xs)
+    de = (egot.double() - ewant.double())
+    erec = {"max_abs": float(de.abs().max()), "rel_l2": float(de.norm() / ewant.double().norm()), "ref_abs_max": float(ewant.abs().max()),
+            "params": arch.count_params(arch.vqvae_encode_specs(cfg))}
+    torch.save({"z": ewant}, os.path.join(GOLD, "vqvae_encode.pt"))
     path = os.path.join(GOLD, "PINNING.json")
     pin = json.load(open(path))
+    pin["cases"]["vqvae_encode_no_quant"] = erec
+    print(json.dumps(erec, indent=1))
     pin["cases"]["vqvae_decode_no_quant"] = rec
     with open(path, "w") as f:
         json.dump(pin, f, indent=1)

@@ -111,3 +111,20 @@ def test_scene_encoder_oracle_vs_reference():
         assert out[k].shape == G[k].shape, k
         assert max(rel_err(out[k], G[k])) < TOL, k
     assert out["uc_s"].shape == (8, 1, 1280) and out["obj_embed"].shape == (8, 640)
+
+
+def test_vqvae_encode_oracle_vs_reference():
+    """SURVEY 8f-3 (oracle stage): VQVAE.encode_no_quant (Encoder3D -> quant_conv) against the reference's output for the
+    seeded SDF volume of oracle/gen_golden_vqvae.py."""
+    pin = json.load(open(os.path.join(GOLD, "PINNING.json")))["cases"]["vqvae_encode_no_quant"]
+    assert pin["rel_l2"] < 1e-6
+    cfg = cases.vqvae_cfg()
+    specs = arch.vqvae_encode_specs(cfg)
+    assert arch.count_params(specs) == pin["params"]
+    sd = arch.make_state_dict(specs, cases.WEIGHT_SEED_VQVAE + 1)
+    x = cases.vqvae_sdf_inputs()
+    with torch.no_grad():
+        z = orc.vqvae_encode_no_quant(sd, cfg, x)
+    G = gold("vqvae_encode.pt")
+    assert z.shape == (1, 3, 16, 16, 16) == G["z"].shape
+    assert max(rel_err(z, G["z"])) < TOL
