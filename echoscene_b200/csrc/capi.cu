@@ -130,11 +130,16 @@ int echo_graph_create(echo_graph_t** out, const int64_t* triples_dev, int32_t T,
       if (bytes) ECHO_CUDA(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
       return d;
     };
-    g->triples = (int64_t*)up(h.data(), sizeof(int64_t) * 3 * T);
-    g->s_idx = (int*)up(si.data(), sizeof(int) * T);
-    g->o_idx = (int*)up(oi.data(), sizeof(int) * T);
-    g->node_off = (int*)up(off.data(), sizeof(int) * (N + 1));
-    g->node_items = (int*)up(items.data(), sizeof(int) * 2 * T);
+    try {
+      g->triples = (int64_t*)up(h.data(), sizeof(int64_t) * 3 * T);
+      g->s_idx = (int*)up(si.data(), sizeof(int) * T);
+      g->o_idx = (int*)up(oi.data(), sizeof(int) * T);
+      g->node_off = (int*)up(off.data(), sizeof(int) * (N + 1));
+      g->node_items = (int*)up(items.data(), sizeof(int) * 2 * T);
+    } catch (...) {
+      echo_graph_destroy(g);  // frees whatever was uploaded (unset members are null)
+      throw;
+    }
     *out = g;
   });
 }
