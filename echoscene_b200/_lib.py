@@ -55,6 +55,12 @@ class ShapeDesc(C.Structure):
                 ("linear_end", C.c_float)]
 
 
+class SceneDesc(C.Structure):
+    _fields_ = [("gconv_dim", C.c_int32), ("add_dim", C.c_int32), ("num_objs", C.c_int32), ("num_preds", C.c_int32),
+                ("num_layers", C.c_int32), ("rel_s_hidden", C.c_int32), ("context_dim", C.c_int32),
+                ("max_nodes", C.c_int32), ("max_triples", C.c_int32), ("bn_eps", C.c_float)]
+
+
 class VqvaeDesc(C.Structure):
     _fields_ = [("embed_dim", C.c_int32), ("n_embed", C.c_int32), ("z_channels", C.c_int32), ("latent_size", C.c_int32),
                 ("ch", C.c_int32), ("num_levels", C.c_int32), ("ch_mult", C.c_int32 * 8), ("num_res_blocks", C.c_int32),
@@ -98,6 +104,12 @@ PROTOTYPES = {
     "echo_shape_latent": (C.c_int, [_P, _I, _P, _P]),
     "echo_shape_destroy": (None, [_P]),
     "echo_shape_schedule": (C.c_int, [_P, _P, _P]),
+    "echo_scene_create": (C.c_int, [C.POINTER(_P), C.POINTER(SceneDesc), C.POINTER(Weight), _I]),
+    "echo_scene_init_encoder": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "echo_scene_manipulate": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "echo_scene_rel_s": (C.c_int, [_P, _P, _I, _P, _P]),
+    "echo_scene_encode": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "echo_scene_destroy": (None, [_P]),
     "echo_vqvae_create": (C.c_int, [C.POINTER(_P), C.POINTER(VqvaeDesc), C.POINTER(Weight), _I]),
     "echo_vqvae_decode": (C.c_int, [_P, _P, _I, _P, _P, _P]),
     "echo_vqvae_destroy": (None, [_P]),

@@ -9,6 +9,7 @@
 
 struct echo_layout;
 struct echo_shape;
+struct echo_scene;
 
 namespace echo {
 void set_tc_mode(int);
@@ -30,6 +31,14 @@ echo_vqvae* vqvae_create(const echo_vqvae_desc_t*, const echo_weight_t*, int);
 void vqvae_destroy(echo_vqvae*);
 void vqvae_decode(echo_vqvae*, const float*, int, float*, int*, cudaStream_t);
 int shape_context_dim(const echo_shape*);
+echo_scene* scene_create(const echo_scene_desc_t*, const echo_weight_t*, int);
+void scene_destroy(echo_scene*);
+void scene_init_encoder(echo_scene*, const echo_graph*, const int64_t*, const float*, const float*, float*, float*, float*, cudaStream_t);
+void scene_manipulate(echo_scene*, const echo_graph*, const float*, const int64_t*, const float*, const float*, float*, float*, float*,
+                      cudaStream_t);
+void scene_rel_s(echo_scene*, const float*, int, float*, cudaStream_t);
+void scene_encode(echo_scene*, const echo_graph*, const int64_t*, const float*, const float*, const float*, float*, float*, float*,
+                  float*, cudaStream_t);
 void shape_tables(const echo_shape*, const std::vector<float>**, const std::vector<int32_t>**);
 bool conv3d_small_cout_supported(int cin, int cout, int taps);
 void conv3d_small_cout(const Act& x, const float* wt, const float* bias, int cout, float* out, cudaStream_t s);
@@ -105,12 +114,16 @@ int echo_graph_create(echo_graph_t** out, const int64_t* triples_dev, int32_t T,
       ECHO_CUDA(cudaStreamSynchronize(s));
     }
     std::vector<int> si(T), oi(T), off(N + 1, 0), items((size_t)2 * T);
+    int64_t p_lo = 0, p_hi = -1;
+    if (T) p_lo = p_hi = h[1];
     for (int t = 0; t < T; ++t) {
       const int64_t a = h[3 * t], b = h[3 * t + 2];
       // the reference would raise an index error (graph.py:146-147)
       ECHO_CHECK(a >= 0 && a < N && b >= 0 && b < N, "graph_create: triple %d has node index out of range [0, %d)", t, N);
       si[t] = (int)a;
       oi[t] = (int)b;
+      p_lo = std::min(p_lo, h[3 * t + 1]);
+      p_hi = std::max(p_hi, h[3 * t + 1]);
       off[a + 1]++;
       off[b + 1]++;
     }
@@ -123,6 +136,8 @@ int echo_graph_create(echo_graph_t** out, const int64_t* triples_dev, int32_t T,
     echo_graph* g = new echo_graph();
     g->id = next_id++;
     g->n_nodes = N;
+    g->p_min = p_lo;
+    g->p_max = p_hi;
     g->n_triples = T;
     auto up = [&](const void* src, size_t bytes) {
       void* d = nullptr;
@@ -193,6 +208,33 @@ void echo_gcn_destroy(echo_gcn_t* h) {
   h->pool.destroy();
   delete h;
 }
+
+int echo_scene_create(echo_scene_t** out, const echo_scene_desc_t* desc, const echo_weight_t* weights, int32_t n_weights) {
+  return guard([&] {
+    ECHO_CHECK(out, "scene_create: null out");
+    *out = scene_create(desc, weights, n_weights);
+  });
+}
+int echo_scene_init_encoder(echo_scene_t* h, const echo_graph_t* g, const int64_t* objs, const float* text_feat, const float* rel_feat,
+                            float* obj_embed_out, float* pred_embed_out, float* latent_obj_out, void* stream) {
+  return guard([&] { scene_init_encoder(h, g, objs, text_feat, rel_feat, obj_embed_out, pred_embed_out, latent_obj_out, (cudaStream_t)stream); });
+}
+int echo_scene_manipulate(echo_scene_t* h, const echo_graph_t* g, const float* latent_f, const int64_t* objs, const float* text_feat,
+                          const float* rel_feat, float* latent_out, float* obj_embed_out, float* pred_embed_out, void* stream) {
+  return guard([&] {
+    scene_manipulate(h, g, latent_f, objs, text_feat, rel_feat, latent_out, obj_embed_out, pred_embed_out, (cudaStream_t)stream);
+  });
+}
+int echo_scene_rel_s(echo_scene_t* h, const float* x, int32_t rows, float* out, void* stream) {
+  return guard([&] { scene_rel_s(h, x, rows, out, (cudaStream_t)stream); });
+}
+int echo_scene_encode(echo_scene_t* h, const echo_graph_t* g, const int64_t* objs, const float* text_feat, const float* rel_feat,
+                      const float* change, float* obj_embed_out, float* latent_out, float* uc_s_out, float* c_s_out, void* stream) {
+  return guard([&] {
+    scene_encode(h, g, objs, text_feat, rel_feat, change, obj_embed_out, latent_out, uc_s_out, c_s_out, (cudaStream_t)stream);
+  });
+}
+void echo_scene_destroy(echo_scene_t* h) { scene_destroy(h); }
 
 int echo_layout_create(echo_layout_t** out, const echo_layout_desc_t* desc, const echo_weight_t* weights, int32_t n_weights) {
   return guard([&] {

@@ -61,6 +61,8 @@ __global__ void node_pool_kernel(const float* __restrict__ t2, int ld, int H, in
   }
 }
 
+}  // namespace
+
 Mat folded_linear(const WeightMap& wm, const std::string& lin, const std::string& bn, int nout, int K, float eps, DevPool& pool,
                   cudaStream_t s) {
   const WView& w = wm.get(lin + ".weight", {nout, K});
@@ -96,8 +98,6 @@ Mat plain_linear(const WeightMap& wm, const std::string& lin, int nout, int K, D
   m.b = bo;
   return m;
 }
-
-}  // namespace
 
 // Few-row kernel up to 64 rows, tiled SIMT GEMM above (batched scene graphs: hundreds of nodes / thousands of edges).
 void linear_auto(const LinArgs& a, cudaStream_t s) {

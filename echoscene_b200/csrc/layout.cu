@@ -23,6 +23,7 @@ struct echo_layout {
   int prec = ECHO_PREC_FP32;
   ConvW box_emb, time_emb_lin;
   const float* pred_table = nullptr;
+  int pred_rows = 0;   // rows of pred_embeddings (16)
   const float* freqs = nullptr;
   std::vector<float> h_tab;
   float* d_tab = nullptr;
@@ -131,6 +132,9 @@ struct echo_layout {
 
   void forward(const echo_graph* g, const float* box_t, const float* obj_embed, const int64_t* t, float* eps_out, cudaStream_t s) {
     ECHO_CHECK(g && g->n_nodes <= d.max_nodes && g->n_triples <= d.max_triples, "layout: graph exceeds handle capacity");
+    // nn.Embedding would raise an index error (denoise_net.py:764 / openai_model_3d.py:807)
+    ECHO_CHECK(g->n_triples == 0 || (g->p_min >= 0 && g->p_max < pred_rows), "layout: predicate ids [%lld, %lld] outside pred_embeddings (%d rows)",
+               (long long)g->p_min, (long long)g->p_max, pred_rows);
     N = g->n_nodes;
     if (N == 0) return;
     const int T = g->n_triples, mc = d.model_channels, E = 4 * mc, gd = d.gconv_dim, od = d.obj_embed_dim;
@@ -285,6 +289,7 @@ echo_layout* layout_create(const echo_layout_desc_t* desc, const echo_weight_t* 
       float* o = h->pool.alloc_n<float>(pt.numel());
       ECHO_CUDA(cudaMemcpyAsync(o, pt.p, sizeof(float) * pt.numel(), cudaMemcpyDeviceToDevice, s));
       h->pred_table = o;
+      h->pred_rows = (int)pt.shape[0];
     }
     {
       const int half = mc / 2;

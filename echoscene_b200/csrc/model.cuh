@@ -58,6 +58,7 @@ struct echo_graph {
   int* o_idx = nullptr;         // (T)
   int* node_off = nullptr;      // (N+1) CSR offsets
   int* node_items = nullptr;    // (2T) item = t*2 + role(0 = subject, 1 = object), subjects first, ascending t
+  int64_t p_min = 0, p_max = -1;   // range of the predicate ids (host-side, from graph_create): embedding lookups check it
 };
 
 namespace echo {
@@ -86,6 +87,10 @@ struct Gcn {
 };
 
 void linear_auto(const LinArgs& a, cudaStream_t s);
+// Linear (+ eval BatchNorm1d folded in when `bn`.running_mean exists) / plain Linear copied into the handle's pool (gcn.cu)
+Mat folded_linear(const WeightMap& wm, const std::string& lin, const std::string& bn, int nout, int K, float eps, DevPool& pool,
+                  cudaStream_t s);
+Mat plain_linear(const WeightMap& wm, const std::string& lin, int nout, int K, DevPool& pool, cudaStream_t s);
 
 }  // namespace echo
 

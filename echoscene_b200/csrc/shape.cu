@@ -35,6 +35,7 @@ struct echo_shape {
   // prepared small weights
   ConvW se_conv0, se_conv2, se_lin, time_emb_lin;
   const float* pred_table = nullptr;
+  int pred_rows = 0;   // rows of pred_embeddings (16)
   const float* freqs = nullptr;
   // schedule
   std::vector<float> h_coef;
@@ -421,6 +422,9 @@ struct echo_shape {
   void run(const echo_graph* g, const float* x_local, int obj_begin, int n_local, const float* codes_all, const float* uc_all,
            const int64_t* t_all, int ddim_index, float* out_local, cudaStream_t s, cudaStream_t codes_stream = nullptr) {
     ECHO_CHECK(g && g->n_nodes <= d.max_nodes && g->n_triples <= d.max_triples, "shape: graph exceeds handle capacity");
+    // nn.Embedding would raise an index error (denoise_net.py:764 / openai_model_3d.py:807)
+    ECHO_CHECK(g->n_triples == 0 || (g->p_min >= 0 && g->p_max < pred_rows), "shape: predicate ids [%lld, %lld] outside pred_embeddings (%d rows)",
+               (long long)g->p_min, (long long)g->p_max, pred_rows);
     ECHO_CHECK(n_local >= 0 && n_local <= d.max_local_nodes && obj_begin >= 0 && obj_begin + n_local <= g->n_nodes,
                "shape: bad local range [%d, %d) of %d nodes (capacity %d)", obj_begin, obj_begin + n_local, g->n_nodes, d.max_local_nodes);
     ECHO_CHECK(ddim_index < (int)h_ts.size(), "shape: ddim_index %d out of range", ddim_index);
@@ -540,6 +544,7 @@ echo_shape* shape_create(const echo_shape_desc_t* desc, const echo_weight_t* wei
       float* o = h->pool.alloc_n<float>(pt.numel());
       ECHO_CUDA(cudaMemcpyAsync(o, pt.p, sizeof(float) * pt.numel(), cudaMemcpyDeviceToDevice, s));
       h->pred_table = o;
+      h->pred_rows = (int)pt.shape[0];
     }
     // frequency table of timestep_embedding: passed by the host (computed the way torch computes it) or rebuilt
     {

@@ -182,6 +182,164 @@ class GraphTripleConv(GraphTripleConvNet):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# once-per-scene encoders
+# ----------------------------------------------------------------------------------------------------------------------
+class SceneEncoder(_SpecModule):
+    """The encoder sub-modules of ``Sg2ScDiffModel`` and the methods of it that run before the two chains start
+    (model/EchoScene.py): ``obj_embeddings_ec``, ``pred_embeddings_ec``, ``gconv_net_ec``, ``gconv_net_manipulation``,
+    ``rel_s_mlp`` -- same state_dict keys, so the matching slice of a reference checkpoint loads with strict=True
+    (``load_reference_state_dict`` drops the keys of other sub-modules).
+
+      init_encoder(objs, triples, text_feat, rel_feat)            EchoScene.py:143-157
+      manipulate(latent_f, objs, triples, text_feat, rel_feat)    EchoScene.py:181-195
+      rel_s(x)   [the reference's self.rel_s_mlp(x)]              EchoScene.py:97-100
+      encode(objs, triples, text_feat, rel_feat)                  the encoder stage of sample(), EchoScene.py:388-410
+
+    Each method is ONE asynchronous C-ABI call (echo_scene_*); the reference's per-node host->device loop (:393-397)
+    does not exist here."""
+
+    PREFIXES = ("obj_embeddings_ec.", "pred_embeddings_ec.", "gconv_net_ec.", "gconv_net_manipulation.", "rel_s_mlp.")
+
+    def __init__(self, num_objs: int = 36, num_preds: int = 16, embedding_dim: int = 64, gconv_num_layers: int = 5,
+                 residual: bool = True, use_clip: bool = True, gconv_pooling: str = "avg",
+                 mlp_normalization: str = "batch", rel_s_hidden: int = 960, context_dim: int = 1280):
+        super().__init__()
+        if gconv_pooling != "avg":
+            raise EchoError(f"gconv_pooling='{gconv_pooling}' is not on the hot path (SGDiff.py:21-22 passes 'avg')")
+        if mlp_normalization != "batch":
+            raise EchoError("SceneEncoder mirrors the SGDiff construction (mlp_normalization='batch', SGDiff.py:21-22)")
+        self.cfg = arch.SceneEncoderConfig(gconv_dim=embedding_dim, add_dim=512 if use_clip else 0, num_objs=num_objs,
+                                           num_preds=num_preds, num_layers=gconv_num_layers, residual=residual,
+                                           rel_s_hidden=rel_s_hidden, context_dim=context_dim)
+        self.embedding_dim = embedding_dim
+        self.clip = use_clip
+        self.out_dim_ini_encoder = self.out_dim_manipulator = self.cfg.feat_dim
+        self._build_from_specs(arch.scene_encoder_specs(self.cfg))
+        self.eval()
+
+    @classmethod
+    def from_vocab(cls, vocab: dict, **kw) -> "SceneEncoder":
+        """num_objs / num_preds as Sg2ScDiffModel derives them (EchoScene.py:37-43)."""
+        return cls(num_objs=len(set(vocab["object_idx_to_name"])), num_preds=len(set(vocab["pred_idx_to_name"])), **kw)
+
+    def load_reference_state_dict(self, state_dict, strict: bool = True):
+        """Loads the encoder slice of a ``Sg2ScDiffModel`` state_dict (its other sub-modules -- the *_dc embeddings,
+        LayoutDiff, ShapeDiff -- are dropped)."""
+        sub = {k: v for k, v in state_dict.items() if k.startswith(self.PREFIXES)}
+        return self.load_state_dict(sub, strict=strict)
+
+    # ---- handle ----
+    def _ensure(self, n_nodes: int, n_triples: int):
+        ver = self._weights_version()
+        cap = self._handle_key[1] if self._handle_key else (0, 0)
+        if self._handle is not None and self._handle_key[0] == ver and n_nodes <= cap[0] and n_triples <= cap[1]:
+            return
+        self._destroy_handle()
+        cap = (_next_pow2(n_nodes, 32), _next_pow2(n_triples, 128))
+        c = self.cfg
+        d = _lib.SceneDesc(c.gconv_dim, c.add_dim, c.num_objs + 1, c.num_preds, c.num_layers, c.rel_s_hidden,
+                           c.context_dim, cap[0], cap[1], 1e-5)
+        arr, n, keep = _lib.weights_table(self.state_dict())
+        h = C.c_void_p()
+        _lib.check(_lib.lib().echo_scene_create(C.byref(h), C.byref(d), arr, n))
+        self._handle, self._handle_key = h, (ver, cap)
+
+    def _destroy_handle(self):
+        if self._handle is not None:
+            _lib.lib().echo_scene_destroy(self._handle)
+            self._handle = None
+
+    def _prep(self, objs, triples, text_feat, rel_feat):
+        self._check_eval()
+        _lib.require_cuda(objs, triples, text_feat, rel_feat)
+        n, t = int(objs.shape[0]), int(triples.shape[0])
+        if objs.dtype != torch.int64 or objs.dim() != 1:
+            raise EchoError(f"objs must be (N,) int64, got {tuple(objs.shape)} {objs.dtype}")
+        if n == 0:
+            raise EchoError("empty scene")
+        # nn.Embedding raises on these (EchoScene.py:149); one host read per scene (the reference does N + 44)
+        lo, hi = int(objs.min()), int(objs.max())
+        if lo < 0 or hi > self.cfg.num_objs:
+            raise IndexError(f"object class ids [{lo}, {hi}] outside obj_embeddings_ec ({self.cfg.num_objs + 1} rows)")
+        if self.clip:
+            if text_feat is None or rel_feat is None:
+                raise EchoError("use_clip=True needs text_feat (N,512) and rel_feat (T,512)")
+            if tuple(text_feat.shape) != (n, self.cfg.add_dim) or tuple(rel_feat.shape) != (t, self.cfg.add_dim):
+                raise EchoError(f"text_feat / rel_feat must be ({n},{self.cfg.add_dim}) / ({t},{self.cfg.add_dim}), got "
+                                f"{tuple(text_feat.shape)} / {tuple(rel_feat.shape)}")
+            text_feat, rel_feat = text_feat.float().contiguous(), rel_feat.float().contiguous()
+        else:
+            text_feat = rel_feat = None
+        self._ensure(n, t)
+        return objs.contiguous(), _lib.graph_for(triples, n), text_feat, rel_feat, n, t
+
+    @torch.no_grad()
+    def init_encoder(self, objs, triples, enc_text_feat=None, enc_rel_feat=None):
+        """-> obj_embed (N,feat), pred_embed (T,feat), latent_obj_f (N,feat), latent_pred_f (None: never read by the
+        sampling path, EchoScene.py:390-400)."""
+        objs, g, tf, rf, n, t = self._prep(objs, triples, enc_text_feat, enc_rel_feat)
+        f, dev = self.cfg.feat_dim, objs.device
+        obj_embed, pred_embed = torch.empty(n, f, device=dev), torch.empty(t, f, device=dev)
+        latent = torch.empty(n, f, device=dev)
+        _lib.check(_lib.lib().echo_scene_init_encoder(self._handle, g.h, _lib.ptr(objs), _lib.ptr(tf), _lib.ptr(rf),
+                                                      _lib.ptr(obj_embed), _lib.ptr(pred_embed), _lib.ptr(latent),
+                                                      _lib.stream_ptr()))
+        return obj_embed, pred_embed, latent, None
+
+    @torch.no_grad()
+    def manipulate(self, latent_f, objs, triples, dec_text_feat=None, dec_rel_feat=None):
+        """latent_f (N, feat + embedding_dim) = [latent | change flag] -> obj_vecs (N,feat), pred_vecs (None: unused by
+        the sampling path), obj_embed (N,feat), pred_embed (T,feat)."""
+        objs, g, tf, rf, n, t = self._prep(objs, triples, dec_text_feat, dec_rel_feat)
+        _lib.require_cuda(latent_f)
+        f, dev = self.cfg.feat_dim, objs.device
+        if tuple(latent_f.shape) != (n, f + self.cfg.gconv_dim):
+            raise EchoError(f"latent_f must be ({n},{f + self.cfg.gconv_dim}), got {tuple(latent_f.shape)}")
+        latent_f = latent_f.float().contiguous()
+        obj_embed, pred_embed = torch.empty(n, f, device=dev), torch.empty(t, f, device=dev)
+        latent = torch.empty(n, f, device=dev)
+        _lib.check(_lib.lib().echo_scene_manipulate(self._handle, g.h, _lib.ptr(latent_f), _lib.ptr(objs), _lib.ptr(tf),
+                                                    _lib.ptr(rf), _lib.ptr(latent), _lib.ptr(obj_embed),
+                                                    _lib.ptr(pred_embed), _lib.stream_ptr()))
+        return latent, None, obj_embed, pred_embed
+
+    @torch.no_grad()
+    def rel_s(self, x):
+        """self.rel_s_mlp(x): (M, feat) -> (M, context_dim)."""
+        self._check_eval()
+        _lib.require_cuda(x)
+        if x.dim() != 2 or x.shape[1] != self.cfg.feat_dim:
+            raise EchoError(f"rel_s input must be (M,{self.cfg.feat_dim}), got {tuple(x.shape)}")
+        x = x.float().contiguous()
+        m = int(x.shape[0])
+        self._ensure(max(m, 1), 0)
+        out = torch.empty(m, self.cfg.context_dim, device=x.device)
+        _lib.check(_lib.lib().echo_scene_rel_s(self._handle, _lib.ptr(x), m, _lib.ptr(out), _lib.stream_ptr()))
+        return out
+
+    @torch.no_grad()
+    def encode(self, objs, triples, text_feat=None, rel_feat=None, change=None, shape_cond: bool = True) -> Dict[str, torch.Tensor]:
+        """The encoder stage of ``Sg2ScDiffModel.sample`` (EchoScene.py:388-410) in one call.  ``change`` (N, embedding_dim)
+        defaults to the zero flag of ``sample``.  -> obj_embed, latent (N,feat); uc_s, c_s (N,1,context_dim) when
+        ``shape_cond`` (gen_shape=True)."""
+        objs, g, tf, rf, n, t = self._prep(objs, triples, text_feat, rel_feat)
+        c, dev = self.cfg, objs.device
+        if change is not None:
+            _lib.require_cuda(change)
+            if tuple(change.shape) != (n, c.gconv_dim):
+                raise EchoError(f"change must be ({n},{c.gconv_dim}), got {tuple(change.shape)}")
+            change = change.float().contiguous()
+        out = {"obj_embed": torch.empty(n, c.feat_dim, device=dev), "latent": torch.empty(n, c.feat_dim, device=dev)}
+        if shape_cond:
+            out["uc_s"] = torch.empty(n, 1, c.context_dim, device=dev)
+            out["c_s"] = torch.empty(n, 1, c.context_dim, device=dev)
+        _lib.check(_lib.lib().echo_scene_encode(self._handle, g.h, _lib.ptr(objs), _lib.ptr(tf), _lib.ptr(rf),
+                                                _lib.ptr(change), _lib.ptr(out["obj_embed"]), _lib.ptr(out["latent"]),
+                                                _lib.ptr(out.get("uc_s")), _lib.ptr(out.get("c_s")), _lib.stream_ptr()))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # layout denoiser
 # ----------------------------------------------------------------------------------------------------------------------
 def _fill_levels(desc, channel_mult, attention_resolutions):

@@ -1,0 +1,194 @@
+"""Scene-level sampling glue: the host side of ``Sg2ScDiffModel.sample`` / ``sample_with_changes`` /
+``sample_with_additions`` (model/EchoScene.py:388-532) and of the ``SGDiff`` facade over them (model/SGDiff.py:87-121).
+
+The arithmetic lives behind the C ABI (``SceneEncoder`` -> echo_scene_*, ``DiffusionPoint`` -> echo_layout_step,
+``DDIMSampler`` -> echo_shape_step, ``VQVAE`` -> echo_vqvae_decode); this file is the order of calls and the row
+bookkeeping the reference does around them (change flags, inserted nodes, which latent rows are replaced, ``keep``),
+restated without the per-node host->device copies of the reference (one upload of the change flags per scene instead of
+N, EchoScene.py:432-439).  It holds no parameters of its own: each component loads its slice of the reference's
+checkpoints (``SceneEncoder.load_reference_state_dict``, ``UNet1DModel`` / ``UNet3DModel`` / ``VQVAE`` state_dicts).
+
+Random draws follow the reference's streams: change flags from ``np.random.normal`` in ascending node order
+(EchoScene.py:437, 494), the layout chain from ``torch.randn`` (diffusion_ddpm.py:302, 336), ONE shape noise draw repeated
+for every object (echo2shape.py:507-510).  The reference also reseeds torch's global generator from the wall clock before
+that draw (echo2shape.py:502); that side effect is reproduced only with ``reference_rng=True``.
+"""
+from __future__ import annotations
+
+import time
+from typing import Callable, Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ._lib import EchoError
+
+
+def change_flags(n_nodes: int, marked: Sequence[int], dim: int, device) -> torch.Tensor:
+    """(N, dim) f32: zeros, and one ``np.random.normal(0, 1, dim)`` row per node of ``marked``, drawn in ascending node
+    order as the reference's loop does (EchoScene.py:432-439, 489-496).  One host->device copy."""
+    marked = set(int(i) for i in marked)
+    host = np.zeros((n_nodes, dim), dtype=np.float64)
+    for i in range(n_nodes):
+        if i in marked:
+            host[i] = np.random.normal(0, 1, dim)
+    return torch.from_numpy(host).float().to(device)
+
+
+def insert_zero_rows(latent: torch.Tensor, missing_nodes: Sequence[int]):
+    """The "append zero nodes" loop of sample_with_additions (EchoScene.py:478-486): for the i-th missing node a zero row is
+    inserted at ``missing_nodes[i] + i``, sequentially.  -> (latent with the rows inserted, nodes_added)."""
+    order = list(range(latent.shape[0]))
+    nodes_added = []
+    for i, m in enumerate(missing_nodes):
+        ad_id = int(m) + i
+        nodes_added.append(ad_id)
+        order.insert(ad_id, -1)          # same clamping as latent[:ad_id] ++ zeros ++ latent[ad_id:]
+    idx = torch.tensor(order, dtype=torch.int64, device=latent.device)
+    out = torch.zeros(len(order), latent.shape[1], dtype=latent.dtype, device=latent.device)
+    old = idx >= 0
+    out[old] = latent[idx[old]]
+    return out, nodes_added
+
+
+def replace_rows(base: torch.Tensor, new: torch.Tensor, touched: Sequence[int]) -> torch.Tensor:
+    """"take original nodes when untouched" (EchoScene.py:444-450, 501-507): rows ``touched`` of ``base`` come from ``new``."""
+    out = base.clone()
+    t = sorted(set(int(i) for i in touched))
+    if t:
+        if t[0] < 0 or t[-1] >= base.shape[0]:
+            # the reference's slice-and-cat would silently change the row count here; refuse instead of mis-shaping
+            raise IndexError(f"touched nodes {t} outside [0, {base.shape[0]})")
+        ti = torch.tensor(t, dtype=torch.int64, device=base.device)
+        out[ti] = new[ti]
+    return out
+
+
+def keep_mask(n: int, dropped: Sequence[int], device) -> torch.Tensor:
+    """(n, 1) f32: 1 for nodes kept from the input scene, 0 for manipulated / added ones (EchoScene.py:466-472)."""
+    dropped = set(int(i) for i in dropped)
+    k = np.asarray([0 if i in dropped else 1 for i in range(n)]).reshape(-1, 1)
+    return torch.from_numpy(k).float().to(device)
+
+
+class Sg2ScDiffModel:
+    """Sampling surface of the reference's scene model on the B200 components.
+
+    encoder : modules.SceneEncoder           (init_encoder / manipulate / rel_s)
+    layout  : samplers.DiffusionPoint        (gen_samples_sg)
+    shape   : modules.UNet3DModel or None    (iterated by samplers.DDIMSampler); None = layout only
+    vqvae   : modules.VQVAE or None          (decode_no_quant); None = ``shapes`` are the (N,3,16,16,16) latents
+    """
+
+    def __init__(self, encoder, layout, shape=None, vqvae=None, ddim_steps: int = 100, uc_scale: float = 3.0,
+                 z_shape=(3, 16, 16, 16), replace_latent: bool = False, box_dim: int = 8, size_dim: int = 3,
+                 translation_dim: int = 3, reference_rng: bool = False, ddim_sampler_cls: Optional[Callable] = None):
+        self.encoder, self.layout, self.shape, self.vqvae = encoder, layout, shape, vqvae
+        self.ddim_steps, self.uc_scale, self.z_shape = int(ddim_steps), uc_scale, tuple(z_shape)
+        self.replace_all_latent = replace_latent                      # EchoScene.py:27
+        self.box_dim, self.size_dim, self.translation_dim = box_dim, size_dim, translation_dim
+        self.embedding_dim = encoder.embedding_dim
+        self.out_dim_ini_encoder = encoder.out_dim_ini_encoder
+        self.reference_rng = reference_rng
+        self._ddim_cls = ddim_sampler_cls
+
+    # ---- the two chains -------------------------------------------------------------------------------------------
+    def generate_layout(self, triples, obj_embed, relation_cond) -> Dict[str, torch.Tensor]:
+        """prepare_boxes + EchoToLayout.generate_layout_sg (EchoScene.py:321-326, echo2layout.py:100-126)."""
+        n = obj_embed.shape[0]
+        samples = self.layout.gen_samples_sg((n, self.box_dim), obj_embed.device, obj_embed, triples,
+                                             condition=relation_cond, clip_denoised=False)
+        s, t = self.size_dim, self.size_dim + self.translation_dim
+        return {"sizes": samples[:, 0:s].contiguous(), "translations": samples[:, s:t].contiguous(),
+                "angles": samples[:, t:self.box_dim].contiguous()}
+
+    def rel2shape(self, triples, c_s, uc_s, x_T: Optional[torch.Tensor] = None):
+        """EchoToShape.rel2shape (echo2shape.py:484-525): one noise draw repeated per object, DDIM chain, VQ-VAE decode."""
+        if self.shape is None:
+            raise EchoError("gen_shape=True needs the shape branch (a UNet3DModel)")
+        B = c_s.shape[0]
+        if x_T is None:
+            if self.reference_rng:
+                torch.manual_seed(int(time.time()))                   # echo2shape.py:502
+            single = torch.randn((1,) + self.z_shape, device=c_s.device)
+            x_T = single.repeat(B, 1, 1, 1, 1)
+        cls = self._ddim_cls
+        if cls is None:
+            from .samplers import DDIMSampler as cls
+        samples, _ = cls(self.shape).sample(S=self.ddim_steps, batch_size=B, shape=self.z_shape, conditioning=c_s, x_T=x_T,
+                                            verbose=False, unconditional_guidance_scale=self.uc_scale,
+                                            unconditional_conditioning=uc_s, triplet=triples, eta=0.0)
+        return samples if self.vqvae is None else self.vqvae.decode_no_quant(samples)
+
+    def _chains(self, dec_triples, obj_embed_, latent, gen_shape, x_T):
+        layout_dict = self.generate_layout(dec_triples, obj_embed_, latent)
+        gen_sdf = None
+        if gen_shape:
+            uc_s = self.encoder.rel_s(obj_embed_).unsqueeze(1)        # embedding + CLIP, EchoScene.py:405-406
+            c_s = self.encoder.rel_s(latent).unsqueeze(1)
+            gen_sdf = self.rel2shape(dec_triples, c_s, uc_s, x_T)
+        return {"shapes": gen_sdf}, layout_dict
+
+    # ---- Sg2ScDiffModel ---------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def sample(self, dec_objs, dec_triplets, dec_text_feat, dec_rel_feat, gen_shape=False, x_T=None):
+        """EchoScene.py:388-420 -> ({'shapes': sdf or None}, {'sizes', 'translations', 'angles'})."""
+        enc = self.encoder.encode(dec_objs, dec_triplets, dec_text_feat, dec_rel_feat, shape_cond=gen_shape)
+        layout_dict = self.generate_layout(dec_triplets, enc["obj_embed"], enc["latent"])
+        gen_sdf = self.rel2shape(dec_triplets, enc["c_s"], enc["uc_s"], x_T) if gen_shape else None
+        return {"shapes": gen_sdf}, layout_dict
+
+    @torch.no_grad()
+    def sample_with_changes(self, enc_objs, enc_triples, enc_text_feat, enc_rel_feat, dec_objs, dec_triplets, dec_text_feat,
+                            dec_rel_feat, manipulated_nodes, gen_shape=False, x_T=None):
+        """EchoScene.py:422-472 -> (keep (N,1), {'shapes'}, layout_dict)."""
+        e = self.encoder
+        _, _, latent_obj, _ = e.init_encoder(enc_objs, enc_triples, enc_text_feat, enc_rel_feat)
+        change = change_flags(latent_obj.shape[0], manipulated_nodes, self.embedding_dim, latent_obj.device)
+        latent_, _, obj_embed_, _ = e.manipulate(torch.cat([latent_obj, change], dim=1), dec_objs, dec_triplets, dec_text_feat,
+                                                 dec_rel_feat)
+        latent = latent_ if self.replace_all_latent else replace_rows(latent_obj, latent_, manipulated_nodes)
+        shape_dict, layout_dict = self._chains(dec_triplets, obj_embed_, latent, gen_shape, x_T)
+        keep = keep_mask(len(layout_dict["translations"]), manipulated_nodes, latent.device)
+        return keep, shape_dict, layout_dict
+
+    @torch.no_grad()
+    def sample_with_additions(self, enc_objs, enc_triples, enc_text_feat, enc_rel_feat, dec_objs, dec_triplets, dec_text_feat,
+                              dec_rel_feat, missing_nodes, gen_shape=False, x_T=None):
+        """EchoScene.py:474-532 -> (keep (N,1), {'shapes'}, layout_dict).  As in the reference, the change flags are drawn
+        for the indices in ``missing_nodes`` (:492) while rows are replaced / dropped from ``keep`` at ``nodes_added`` =
+        missing_nodes[i] + i (:480, :503, :528)."""
+        e = self.encoder
+        _, _, latent_obj, _ = e.init_encoder(enc_objs, enc_triples, enc_text_feat, enc_rel_feat)
+        latent_obj, nodes_added = insert_zero_rows(latent_obj, missing_nodes)
+        change = change_flags(latent_obj.shape[0], missing_nodes, self.embedding_dim, latent_obj.device)
+        latent_, _, obj_embed_, _ = e.manipulate(torch.cat([latent_obj, change], dim=1), dec_objs, dec_triplets, dec_text_feat,
+                                                 dec_rel_feat)
+        latent = latent_ if self.replace_all_latent else replace_rows(latent_obj, latent_, nodes_added)
+        shape_dict, layout_dict = self._chains(dec_triplets, obj_embed_, latent, gen_shape, x_T)
+        keep = keep_mask(len(layout_dict["translations"]), nodes_added, latent.device)
+        return keep, shape_dict, layout_dict
+
+    # ---- SGDiff facade (model/SGDiff.py:87-121, type_ == 'echoscene') ----------------------------------------------
+    def sample_box_and_shape(self, dec_objs, dec_triplets, encoded_dec_text_feat, encoded_dec_rel_feat, gen_shape=False):
+        shape_dict, layout_dict = self.sample(dec_objs, dec_triplets, encoded_dec_text_feat, encoded_dec_rel_feat,
+                                              gen_shape=gen_shape)
+        return {**shape_dict, **layout_dict}
+
+    def sample_boxes_and_shape_with_changes(self, enc_objs, enc_triples, encoded_enc_text_feat, encoded_enc_rel_feat, dec_objs,
+                                            dec_triples, encoded_dec_text_feat, encoded_dec_rel_feat, manipulated_nodes,
+                                            gen_shape=False):
+        keep, shape_dict, layout_dict = self.sample_with_changes(enc_objs, enc_triples, encoded_enc_text_feat,
+                                                                 encoded_enc_rel_feat, dec_objs, dec_triples,
+                                                                 encoded_dec_text_feat, encoded_dec_rel_feat,
+                                                                 manipulated_nodes, gen_shape=gen_shape)
+        return keep, {**shape_dict, **layout_dict}
+
+    def sample_boxes_and_shape_with_additions(self, enc_objs, enc_triples, encoded_enc_text_feat, encoded_enc_rel_feat, dec_objs,
+                                              dec_triples, encoded_dec_text_feat, encoded_dec_rel_feat, missing_nodes,
+                                              gen_shape=False):
+        keep, shape_dict, layout_dict = self.sample_with_additions(enc_objs, enc_triples, encoded_enc_text_feat,
+                                                                   encoded_enc_rel_feat, dec_objs, dec_triples,
+                                                                   encoded_dec_text_feat, encoded_dec_rel_feat,
+                                                                   missing_nodes, gen_shape=gen_shape)
+        return keep, {**shape_dict, **layout_dict}

@@ -49,6 +49,7 @@ typedef struct echo_graph echo_graph_t;     /* CSR of one (batched) scene graph;
 typedef struct echo_gcn echo_gcn_t;         /* GraphTripleConvNet */
 typedef struct echo_layout echo_layout_t;   /* UNet1DModel + DDPM schedule */
 typedef struct echo_shape echo_shape_t;     /* UNet3DModel + DDIM schedule */
+typedef struct echo_scene echo_scene_t;     /* once-per-scene encoders of Sg2ScDiffModel */
 
 /* One named parameter / buffer of a reference state_dict (device pointer, fp32 or int64, reference layout). */
 typedef struct echo_weight {
@@ -208,6 +209,44 @@ typedef struct {
 ECHO_API int echo_vqvae_create(echo_vqvae_t** out, const echo_vqvae_desc_t* desc, const echo_weight_t* weights, int32_t n_weights);
 ECHO_API int echo_vqvae_decode(echo_vqvae_t* h, const float* latents, int32_t n, float* sdf_out, int32_t* indices_out, void* stream);
 ECHO_API void echo_vqvae_destroy(echo_vqvae_t* h);
+
+/* ---- once-per-scene encoders of Sg2ScDiffModel.sample (model/EchoScene.py:143-157, 181-195, 388-410): the stage between
+ * the dataset's tensors and the two chains.  state_dict keys: obj_embeddings_ec.weight (num_objs, 2*gconv_dim),
+ * pred_embeddings_ec.weight (num_preds, 2*gconv_dim), gconv_net_ec.*, gconv_net_manipulation.*, rel_s_mlp.{0,1,3}.*
+ * (rel_s_mlp optional: the layout-only model has none).  feat = 2*gconv_dim + add_dim (640). */
+typedef struct echo_scene_desc {
+  int32_t gconv_dim;            /* embedding_dim = 64 (SGDiff.py:21) */
+  int32_t add_dim;              /* 512 with CLIP features (use_clip), else 0 */
+  int32_t num_objs;             /* rows of obj_embeddings_ec = len(vocab['object_idx_to_name']) + 1 (EchoScene.py:47) */
+  int32_t num_preds;            /* rows of pred_embeddings_ec (EchoScene.py:48) */
+  int32_t num_layers;           /* gconv_num_layers = 5 */
+  int32_t rel_s_hidden;         /* 960 (EchoScene.py:97-100) */
+  int32_t context_dim;          /* 1280 */
+  int32_t max_nodes, max_triples;
+  float bn_eps;                 /* 1e-5 */
+} echo_scene_desc_t;
+ECHO_API int echo_scene_create(echo_scene_t** out, const echo_scene_desc_t* desc, const echo_weight_t* weights, int32_t n_weights);
+/* init_encoder(objs, triples, text_feat, rel_feat) (EchoScene.py:143-157): objs (N) i64 class ids -- the caller guarantees
+ * 0 <= objs[i] < num_objs (nn.Embedding would raise; predicate ids are checked against the graph) --, text_feat (N, add_dim),
+ * rel_feat (T, add_dim) -> obj_embed (N, feat), pred_embed (T, feat), latent_obj (N, feat).  Outputs may be NULL. */
+ECHO_API int echo_scene_init_encoder(echo_scene_t* h, const echo_graph_t* g, const int64_t* objs, const float* text_feat,
+                                     const float* rel_feat, float* obj_embed_out, float* pred_embed_out, float* latent_obj_out,
+                                     void* stream);
+/* manipulate(latent_f, objs, triples, text_feat, rel_feat) (EchoScene.py:181-195): latent_f (N, feat + gconv_dim) =
+ * [latent | change flag] -> latent (N, feat), obj_embed (N, feat), pred_embed (T, feat).  Outputs may be NULL. */
+ECHO_API int echo_scene_manipulate(echo_scene_t* h, const echo_graph_t* g, const float* latent_f, const int64_t* objs,
+                                   const float* text_feat, const float* rel_feat, float* latent_out, float* obj_embed_out,
+                                   float* pred_embed_out, void* stream);
+/* rel_s_mlp(x) (EchoScene.py:97-100, 405-410): x (rows, feat) -> out (rows, context_dim); rows <= max_nodes */
+ECHO_API int echo_scene_rel_s(echo_scene_t* h, const float* x, int32_t rows, float* out, void* stream);
+/* The whole encoder stage of Sg2ScDiffModel.sample (EchoScene.py:388-410) as one asynchronous call: init_encoder ->
+ * [latent_obj | change | obj_embed] -> manipulate -> rel_s_mlp twice.  change (N, gconv_dim) or NULL = zeros (sample, :393-397).
+ * -> obj_embed (N, feat) [layout branch obj_embed], latent (N, feat) [layout branch relation condition], uc_s / c_s
+ * (N, context_dim) [shape branch conditionings; either may be NULL when only the layout is sampled]. */
+ECHO_API int echo_scene_encode(echo_scene_t* h, const echo_graph_t* g, const int64_t* objs, const float* text_feat,
+                               const float* rel_feat, const float* change, float* obj_embed_out, float* latent_out,
+                               float* uc_s_out, float* c_s_out, void* stream);
+ECHO_API void echo_scene_destroy(echo_scene_t* h);
 
 /* ---- schedule tables, for host-side checks against the reference's buffers.
  * layout: 5 x time_num f32 [sqrt_recip_ac, sqrt_recipm1_ac, post_mean_coef1, post_mean_coef2, post_log_var_clipped]

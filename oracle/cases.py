@@ -105,6 +105,35 @@ def scene_inputs(case: GraphCase = SCENE_CASE, cfg: "arch.SceneEncoderConfig" = 
     return g, objs, text, rel
 
 
+# glue of sample / sample_with_changes / sample_with_additions (oracle/gen_golden_scene_glue.py)
+SCENE_GLUE_NP_SEED = 123                                       # np.random stream of the change flags (EchoScene.py:437, 494)
+SCENE_ENC_CASE_SAME = GraphCase("scene_enc_n8", 8, 28, 11)     # the scene before a relationship change: same nodes, other triples
+SCENE_ENC_CASE_SMALL = GraphCase("scene_enc_n6", 6, 18, 12)    # the scene before two objects are added
+# (case name, Sg2ScDiffModel method, replace_latent)
+SCENE_GLUE_CASES = (
+    ("sample", "sample", False),
+    ("changes", "sample_with_changes", False),
+    ("changes_replace_all", "sample_with_changes", True),
+    ("additions", "sample_with_additions", False),
+    ("additions_replace_all", "sample_with_additions", True),
+)
+
+
+def scene_glue_inputs(name: str):
+    """-> (positional tensor arguments of the method, marked nodes or None).  `changes`: nodes 1 and 5 manipulated;
+    `additions`: missing_nodes [2, 4] -> rows inserted at [2, 5] of the 6-node encoder scene (8 decoder nodes)."""
+    g, objs, text, rel = scene_inputs()
+    if name == "sample":
+        return (objs, g.triples, text, rel), None
+    if name.startswith("changes"):
+        ge, eobjs, etext, erel = scene_inputs(SCENE_ENC_CASE_SAME)
+        return (eobjs, ge.triples, etext, erel, objs, g.triples, text, rel), [5, 1]
+    if name.startswith("additions"):
+        ge, eobjs, etext, erel = scene_inputs(SCENE_ENC_CASE_SMALL)
+        return (eobjs, ge.triples, etext, erel, objs, g.triples, text, rel), [2, 4]
+    raise KeyError(name)
+
+
 def vqvae_sdf_inputs(n: int = 1, seed: int = 8):
     """truncated-SDF-like volumes (N, 1, 64, 64, 64), clamped to +-0.2 as the dataset does (threedfront_dataset.py)"""
     gen = torch.Generator().manual_seed(seed + 700)

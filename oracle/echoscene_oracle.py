@@ -475,27 +475,49 @@ def vqvae_decode_no_quant(sd: SD, cfg, h: Tensor) -> Tensor:
 # --------------------------------------------------------------------------------------
 
 
-def scene_encode(sd: SD, cfg, objs: Tensor, triples: Tensor, text_feat: Tensor, rel_feat: Tensor) -> Dict[str, Tensor]:
+def _scene_embed(sd: SD, objs: Tensor, triples: Tensor, text_feat: Tensor, rel_feat: Tensor):
+    edges, p = edges_of(triples)
+    obj_embed = torch.cat([text_feat, F.embedding(objs, sd["obj_embeddings_ec.weight"])], dim=1)       # :149-153
+    pred_embed = torch.cat([rel_feat, F.embedding(p, sd["pred_embeddings_ec.weight"])], dim=1)
+    return edges, obj_embed, pred_embed
+
+
+def scene_init_encoder(sd: SD, cfg, objs: Tensor, triples: Tensor, text_feat: Tensor, rel_feat: Tensor):
+    """Sg2ScDiffModel.init_encoder, EchoScene.py:143-157 (use_clip) -> obj_embed, pred_embed, latent_obj, latent_pred."""
+    edges, obj_embed, pred_embed = _scene_embed(sd, objs, triples, text_feat, rel_feat)
+    latent_obj, latent_pred = graph_triple_conv_net(sd, "gconv_net_ec.", obj_embed, pred_embed, edges, cfg.num_layers)   # :155
+    return obj_embed, pred_embed, latent_obj, latent_pred
+
+
+def scene_manipulate(sd: SD, cfg, latent_f: Tensor, objs: Tensor, triples: Tensor, text_feat: Tensor, rel_feat: Tensor):
+    """Sg2ScDiffModel.manipulate, EchoScene.py:181-195: latent_f (N, feat + gconv_dim) -> obj_vecs, pred_vecs, obj_embed,
+    pred_embed."""
+    edges, obj_embed, pred_embed = _scene_embed(sd, objs, triples, text_feat, rel_feat)
+    obj_vecs = torch.cat([latent_f, obj_embed], dim=1)                                                 # :192
+    latent, pred_vecs = graph_triple_conv_net(sd, "gconv_net_manipulation.", obj_vecs, pred_embed, edges, min(cfg.num_layers, 5))
+    return latent, pred_vecs, obj_embed, pred_embed
+
+
+def scene_rel_s(sd: SD, x: Tensor) -> Tensor:
+    """rel_s_mlp = make_mlp([640, 960, 1280], batch_norm='batch', norelu=True): Linear, BN, ReLU, Linear.  EchoScene.py:97-100"""
+    h = F.relu(_bn_eval(sd, "rel_s_mlp.1", _linear(sd, "rel_s_mlp.0", x)))
+    return _linear(sd, "rel_s_mlp.3", h)
+
+
+def scene_encode(sd: SD, cfg, objs: Tensor, triples: Tensor, text_feat: Tensor, rel_feat: Tensor,
+                 change: Optional[Tensor] = None) -> Dict[str, Tensor]:
     """What `sample` computes before the layout and shape chains: init_encoder (embeddings + CLIP -> gconv_net_ec), the zero
     change vector, manipulate (gconv_net_manipulation) and the two rel_s_mlp conditionings.
       obj_embed   (N, 640)    -> layout branch `obj_embed`                     (prepare_boxes(..., obj_embed_, ...))
       latent      (N, 640)    -> layout branch relation condition
       uc_s, c_s   (N, 1, 1280) -> shape branch unconditional / conditional context (EchoScene.py:405-410)"""
-    edges, p = edges_of(triples)
-    obj_embed = torch.cat([text_feat, F.embedding(objs, sd["obj_embeddings_ec.weight"])], dim=1)       # :149-153
-    pred_embed = torch.cat([rel_feat, F.embedding(p, sd["pred_embeddings_ec.weight"])], dim=1)
-    latent_obj, _ = graph_triple_conv_net(sd, "gconv_net_ec.", obj_embed, pred_embed, edges, cfg.num_layers)   # :155
-    change = torch.zeros(latent_obj.shape[0], cfg.gconv_dim, dtype=latent_obj.dtype, device=latent_obj.device)  # :393-397
-    latent_in = torch.cat([latent_obj, change], dim=1)
-    obj_vecs = torch.cat([latent_in, obj_embed], dim=1)                                                # manipulate, :186-193
-    latent, _ = graph_triple_conv_net(sd, "gconv_net_manipulation.", obj_vecs, pred_embed, edges, min(cfg.num_layers, 5))
-
-    def rel_s(x):   # make_mlp([640, 960, 1280], batch_norm='batch', norelu=True): Linear, BN, ReLU, Linear
-        h = F.relu(_bn_eval(sd, "rel_s_mlp.1", _linear(sd, "rel_s_mlp.0", x)))
-        return _linear(sd, "rel_s_mlp.3", h)
-
-    return {"obj_embed": obj_embed, "pred_embed": pred_embed, "latent": latent,
-            "uc_s": rel_s(obj_embed).unsqueeze(1), "c_s": rel_s(latent).unsqueeze(1)}
+    obj_embed, pred_embed, latent_obj, _ = scene_init_encoder(sd, cfg, objs, triples, text_feat, rel_feat)
+    if change is None:
+        change = torch.zeros(latent_obj.shape[0], cfg.gconv_dim, dtype=latent_obj.dtype, device=latent_obj.device)  # :393-397
+    latent, _, obj_embed, pred_embed = scene_manipulate(sd, cfg, torch.cat([latent_obj, change], dim=1), objs, triples, text_feat,
+                                                        rel_feat)
+    return {"obj_embed": obj_embed, "pred_embed": pred_embed, "latent": latent, "latent_obj": latent_obj,
+            "uc_s": scene_rel_s(sd, obj_embed).unsqueeze(1), "c_s": scene_rel_s(sd, latent).unsqueeze(1)}
 
 
 def vq_encoder(sd: SD, cfg, x: Tensor, p: str = "encoder") -> Tensor:

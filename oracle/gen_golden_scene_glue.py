@@ -1,0 +1,112 @@
+"""Golden vectors for the host glue of Sg2ScDiffModel.sample / sample_with_changes / sample_with_additions
+-- TEST INFRASTRUCTURE.  Run in the BUILD container only (needs /root/reference):  python oracle/gen_golden_scene_glue.py
+
+The reference's own methods (model/EchoScene.py:388-532) are run unbound on a holder module that owns the encoder
+sub-modules (built by the reference's constructors, as in oracle/gen_golden_scene.py) and two recording stubs in place of the
+diffusion branches: `LayoutDiff.set_input` records the conditioning the layout chain would receive, `ShapeDiff.rel2shape`
+records the shape conditioning.  What is pinned is therefore everything the glue decides: change flags (np.random stream),
+inserted zero rows, which latent rows are replaced, rel_s_mlp inputs, `keep`.  `.cuda()` is made the identity for the
+duration of the run (the methods hard-code it, :396, :438, :484) -- this container has no GPU.
+Writes tests/golden/scene_glue.pt (the recorded tensors); inputs are regenerated from seeds by oracle/cases.py.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from echoscene_b200 import arch              # noqa: E402
+from oracle import cases, ref_import         # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+class _Rec:
+    def __init__(self):
+        self.layout_in = None
+        self.shape_in = None
+
+
+def main():
+    torch.manual_seed(0)
+    ref = ref_import.load()
+    graph = importlib.import_module("model.graph")
+    es = importlib.import_module("model.EchoScene")
+    cfg = cases.scene_cfg()
+    gd, add = cfg.gconv_dim, cfg.add_dim
+    M = es.Sg2ScDiffModel
+    rec = _Rec()
+
+    class LayoutStub:
+        def set_input(self, d):
+            rec.layout_in = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in d.items()}
+
+        def generate_layout_sg(self, box_dim):
+            n = rec.layout_in["uc_b"].shape[0]
+            z = torch.zeros(n, box_dim)
+            return {"sizes": z[:, 0:3], "translations": z[:, 3:6], "angles": z[:, 6:8]}
+
+    class ShapeStub:
+        def rel2shape(self, d):
+            rec.shape_in = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in d.items()}
+            return torch.zeros(d["c_s"].shape[0], 1, 2, 2, 2)
+
+    class Holder(nn.Module):
+        def __init__(self, replace_latent):
+            super().__init__()
+            self.clip = True
+            self.embedding_dim = gd
+            self.out_dim_ini_encoder = gd * 2 + add
+            self.replace_all_latent = replace_latent
+            self.obj_embeddings_ec = nn.Embedding(cfg.num_objs + 1, gd * 2)
+            self.pred_embeddings_ec = nn.Embedding(cfg.num_preds, gd * 2)
+            kw = dict(hidden_dim=gd * 4, pooling="avg", mlp_normalization="batch", residual=cfg.residual)
+            self.gconv_net_ec = ref.GraphTripleConvNet(input_dim_obj=gd * 2 + add, input_dim_pred=gd * 2 + add, num_layers=cfg.num_layers,
+                                                       output_dim=gd * 2 + add, **kw)
+            self.gconv_net_manipulation = ref.GraphTripleConvNet(input_dim_obj=(gd * 2 + add) + gd + gd * 2 + add,
+                                                                 input_dim_pred=gd * 2 + add, num_layers=min(cfg.num_layers, 5),
+                                                                 output_dim=gd * 2 + add, **kw)
+            self.rel_s_mlp = graph.make_mlp([gd * 2 + add, 960, 1280], batch_norm="batch", norelu=True)
+            self.diff_cfg = types.SimpleNamespace(layout_branch=types.SimpleNamespace(denoiser_kwargs=types.SimpleNamespace(in_channels=8)))
+            self.LayoutDiff = LayoutStub()
+            self.ShapeDiff = ShapeStub()
+
+        init_encoder = M.init_encoder
+        manipulate = M.manipulate
+        prepare_boxes = M.prepare_boxes
+
+    sd = arch.make_state_dict(arch.scene_encoder_specs(cfg), cases.WEIGHT_SEED_SCENE)
+    out = {}
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        for name, fn, replace in cases.SCENE_GLUE_CASES:
+            h = Holder(replace).eval()
+            h.load_state_dict(sd, strict=True)
+            args, marked = cases.scene_glue_inputs(name)
+            np.random.seed(cases.SCENE_GLUE_NP_SEED)
+            rec.layout_in = rec.shape_in = None
+            if fn == "sample":
+                res = M.sample(h, *args, gen_shape=True)
+                keep = None
+            else:
+                res = getattr(M, fn)(h, *args, marked, gen_shape=True)
+                keep = res[0]
+            out[name] = {"uc_b": rec.layout_in["uc_b"], "c_b": rec.layout_in["c_b"], "preds": rec.layout_in["preds"],
+                         "uc_s": rec.shape_in["uc_s"], "c_s": rec.shape_in["c_s"], "keep": keep}
+            print(name, fn, {k: (tuple(v.shape) if torch.is_tensor(v) else v) for k, v in out[name].items()})
+    finally:
+        torch.Tensor.cuda = real_cuda
+    torch.save(out, os.path.join(GOLD, "scene_glue.pt"))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,181 @@
+"""CPU: host glue of the scene-level sampling surface (echoscene_b200/scene.py) against what the reference's
+own Sg2ScDiffModel.sample / sample_with_changes / sample_with_additions hand to the two diffusion branches
+(tests/golden/scene_glue.pt, recorded by oracle/gen_golden_scene_glue.py), and the SceneEncoder module surface.
+
+The encoder arithmetic is supplied here by the ORACLE (test infrastructure) behind the SceneEncoder method names, so that
+what is tested is the glue: change flags and their np.random stream, inserted zero rows, replaced latent rows, the
+rel_s_mlp inputs, `keep`.  The CUDA encoder itself is tested in tests/test_zz_scene_gpu.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from echoscene_b200 import _lib, arch, modules, scene
+from oracle import cases, echoscene_oracle as orc
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+class OracleEncoder:
+    """SceneEncoder's method surface on the CPU oracle."""
+
+    def __init__(self):
+        self.cfg = cases.scene_cfg()
+        self.sd = arch.make_state_dict(arch.scene_encoder_specs(self.cfg), cases.WEIGHT_SEED_SCENE)
+        self.embedding_dim = self.cfg.gconv_dim
+        self.out_dim_ini_encoder = self.cfg.feat_dim
+
+    def init_encoder(self, objs, triples, text, rel):
+        return orc.scene_init_encoder(self.sd, self.cfg, objs, triples, text, rel)
+
+    def manipulate(self, latent_f, objs, triples, text, rel):
+        return orc.scene_manipulate(self.sd, self.cfg, latent_f, objs, triples, text, rel)
+
+    def rel_s(self, x):
+        return orc.scene_rel_s(self.sd, x)
+
+    def encode(self, objs, triples, text, rel, change=None, shape_cond=True):
+        return orc.scene_encode(self.sd, self.cfg, objs, triples, text, rel, change)
+
+
+class RecLayout:
+    def gen_samples_sg(self, shape, device, obj_embed, triples=None, condition=None, clip_denoised=True, **kw):
+        assert clip_denoised is False
+        self.seen = {"uc_b": obj_embed, "c_b": condition, "preds": triples}
+        return torch.arange(shape[0] * shape[1], dtype=torch.float32).reshape(shape)
+
+
+class RecDDIM:
+    seen = None
+
+    def __init__(self, model):
+        self.model = model
+
+    def sample(self, S, batch_size, shape, conditioning=None, x_T=None, unconditional_conditioning=None, triplet=None, eta=0.,
+               **kw):
+        RecDDIM.seen = {"c_s": conditioning, "uc_s": unconditional_conditioning, "triples": triplet, "x_T": x_T, "S": S}
+        assert x_T.shape == (batch_size,) + tuple(shape) and eta == 0.0
+        return x_T * 0.5, {}
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return torch.load(os.path.join(GOLD, "scene_glue.pt"))
+
+
+@pytest.mark.parametrize("name,fn,replace", cases.SCENE_GLUE_CASES)
+def test_glue_matches_reference_methods(gold, name, fn, replace):
+    G = gold[name]
+    lay = RecLayout()
+    m = scene.Sg2ScDiffModel(OracleEncoder(), lay, shape=object(), vqvae=None, replace_latent=replace, ddim_sampler_cls=RecDDIM)
+    args, marked = cases.scene_glue_inputs(name)
+    np.random.seed(cases.SCENE_GLUE_NP_SEED)
+    torch.manual_seed(5)
+    if fn == "sample":
+        shape_dict, layout_dict = m.sample(*args, gen_shape=True)
+        keep = None
+    else:
+        keep, shape_dict, layout_dict = getattr(m, fn)(*args, marked, gen_shape=True)
+    # the oracle is pinned to the reference at max-abs 0, so the glue must reproduce the recorded tensors exactly
+    for k in ("uc_b", "c_b", "preds"):
+        assert torch.equal(lay.seen[k], G[k]), (name, k)
+    for k in ("uc_s", "c_s"):
+        assert torch.equal(RecDDIM.seen[k], G[k]), (name, k)
+    if keep is not None:
+        assert torch.equal(keep, G["keep"]) and keep.shape == (8, 1)
+    # one noise draw repeated for every object (echo2shape.py:507-510); S = ddim_steps
+    x_T = RecDDIM.seen["x_T"]
+    assert x_T.shape == (8, 3, 16, 16, 16) and torch.equal(x_T[0], x_T[7]) and RecDDIM.seen["S"] == 100
+    assert torch.equal(shape_dict["shapes"], x_T * 0.5)            # vqvae=None: the latents are returned
+    # generate_layout_sg's split (echo2layout.py:118-122)
+    s = torch.arange(64, dtype=torch.float32).reshape(8, 8)
+    assert torch.equal(layout_dict["sizes"], s[:, 0:3]) and torch.equal(layout_dict["translations"], s[:, 3:6])
+    assert torch.equal(layout_dict["angles"], s[:, 6:8])
+
+
+def test_facade_and_layout_only(gold):
+    lay = RecLayout()
+    m = scene.Sg2ScDiffModel(OracleEncoder(), lay)
+    args, _ = cases.scene_glue_inputs("sample")
+    out = m.sample_box_and_shape(*args, gen_shape=False)
+    assert out["shapes"] is None and set(out) == {"shapes", "sizes", "translations", "angles"}
+    assert torch.equal(lay.seen["c_b"], gold["sample"]["c_b"])
+    with pytest.raises(_lib.EchoError):
+        m.sample(*args, gen_shape=True)                           # no shape branch attached
+    args, marked = cases.scene_glue_inputs("changes")
+    np.random.seed(cases.SCENE_GLUE_NP_SEED)
+    keep, out = m.sample_boxes_and_shape_with_changes(*args, marked)
+    assert torch.equal(keep, gold["changes"]["keep"]) and torch.equal(lay.seen["c_b"], gold["changes"]["c_b"])
+
+
+def test_row_helpers():
+    x = torch.arange(12, dtype=torch.float32).reshape(4, 3)
+    ref = x.clone()
+    added = []
+    for i, mnode in enumerate([1, 3, 9]):                          # the reference's loop, EchoScene.py:478-486
+        ad = mnode + i
+        added.append(ad)
+        ref = torch.cat([ref[:ad], torch.zeros(1, 3), ref[ad:]], dim=0)
+    got, nodes = scene.insert_zero_rows(x, [1, 3, 9])
+    assert nodes == added and torch.equal(got, ref)
+    got, nodes = scene.insert_zero_rows(x, [])
+    assert nodes == [] and torch.equal(got, x)
+    new = -x
+    base = x.clone()
+    for t in sorted([2, 0]):                                       # EchoScene.py:446-448
+        base = torch.cat([base[:t], new[t:t + 1], base[t + 1:]], dim=0)
+    assert torch.equal(scene.replace_rows(x, new, [2, 0]), base)
+    with pytest.raises(IndexError):
+        scene.replace_rows(x, new, [4])
+    np.random.seed(3)
+    want = np.zeros((5, 4))
+    want[1] = np.random.normal(0, 1, 4)
+    want[3] = np.random.normal(0, 1, 4)
+    np.random.seed(3)
+    assert torch.equal(scene.change_flags(5, [3, 1, 3], 4, "cpu"), torch.from_numpy(want).float())
+    assert scene.keep_mask(4, [1], "cpu").flatten().tolist() == [1, 0, 1, 1]
+
+
+def test_scene_encoder_module_surface():
+    cfg = cases.scene_cfg()
+    specs = arch.scene_encoder_specs(cfg)
+    m = modules.SceneEncoder()
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(specs.keys())
+    for k, s in specs.items():
+        assert tuple(sd[k].shape) == tuple(s.shape), k
+    # a full Sg2ScDiffModel state_dict carries other sub-modules: only the encoder slice is loaded, strictly
+    full = dict(arch.make_state_dict(specs, cases.WEIGHT_SEED_SCENE))
+    full["obj_embeddings_dc.weight"] = torch.zeros(37, 128)
+    full["LayoutDiff.df.model.out.2.weight"] = torch.zeros(1)
+    m.load_reference_state_dict(full, strict=True)
+    assert torch.equal(m.state_dict()["rel_s_mlp.3.weight"], full["rel_s_mlp.3.weight"])
+    v = modules.SceneEncoder.from_vocab({"object_idx_to_name": ["a", "b", "b"], "pred_idx_to_name": ["in", "on"]})
+    assert v.state_dict()["obj_embeddings_ec.weight"].shape == (3, 128)
+    assert v.state_dict()["pred_embeddings_ec.weight"].shape == (2, 128)
+    # no CPU fallback, eval only
+    g, objs, text, rel = cases.scene_inputs()
+    with pytest.raises(_lib.EchoError):
+        m.encode(objs, g.triples, text, rel)
+    with pytest.raises(_lib.EchoError):
+        m.rel_s(torch.zeros(2, 640))
+    with pytest.raises(_lib.EchoError):
+        modules.SceneEncoder(gconv_pooling="wAvg")
+    m.train()
+    with pytest.raises(_lib.EchoError):
+        m.init_encoder(objs, g.triples, text, rel)
+
+
+def test_scene_entry_points_reject_bad_arguments():
+    import ctypes as C
+    L = _lib.lib()
+    h = C.c_void_p()
+    assert L.echo_scene_create(C.byref(h), None, None, 0) == -1
+    d = _lib.SceneDesc(64, 512, 37, 16, 5, 960, 1280, 32, 128, 1e-5)
+    assert L.echo_scene_create(None, C.byref(d), None, 0) == -1
+    bad = _lib.SceneDesc(63, 512, 37, 16, 5, 960, 1280, 32, 128, 1e-5)
+    assert L.echo_scene_create(C.byref(h), C.byref(bad), None, 0) == -1 and b"multiples of 4" in L.echo_last_error()
+    assert L.echo_scene_encode(None, None, None, None, None, None, None, None, None, None, None) == -1
+    assert L.echo_scene_rel_s(None, None, 1, None, None) == -1
+    L.echo_scene_destroy(None)
