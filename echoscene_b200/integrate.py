@@ -12,10 +12,15 @@ The reference has no plugin/FFI boundary on the denoising path; its seam is the 
   model.model_utils.VQVAE (looked up by load_vqvae, model_utils.py:7-32)      decode path only: rel2shape's
                                                                              decode_no_quant (echo2shape.py:522)
 
+  model.EchoScene.Sg2ScDiffModel.init_encoder / manipulate                   (EchoScene.py:143-157, 181-195) -> one
+                                                                             echo_scene_* call each (scene_encoders=True)
+
 After that, ``scripts/eval_3dfront.py`` builds ``SGDiff`` as before (same YAML, same checkpoints: state_dict keys are
-identical), and ``Sg2ScDiffModel.sample`` runs both chains through libechoscene_b200.so.  Only the *denoiser-step*
-classes are replaced; the one-time scene encoders keep using whatever ``model.graph`` provides — i.e. the CUDA
-GraphTripleConvNet too, since EchoScene.py imports it from model.graph (EchoScene.py:5).
+identical), and ``Sg2ScDiffModel.sample`` runs both chains through libechoscene_b200.so.  The one-time scene encoders
+ run through ``modules.SceneEncoder``: the model's ``init_encoder`` / ``manipulate`` methods are rebound to
+single C-ABI calls on a ``SceneEncoder`` that SHARES the model's own parameters (no copy; rebuilt when they are replaced),
+so ``sample`` / ``sample_with_changes`` / ``sample_with_additions`` run unchanged.  ``self.rel_s_mlp`` (two Linear layers on
+N rows) stays the reference's nn.Sequential on this route; ``echoscene_b200.scene.Sg2ScDiffModel`` is the fully native one.
 
 Training (`train_3dfront.py`) needs the backward pass, which is outside this round's scope: the patched classes raise
 in ``train()`` mode instead of silently computing something else.
@@ -26,9 +31,55 @@ import importlib
 from typing import Optional
 
 
-def patch_reference(precision: str = "fp32", ddim_steps: Optional[int] = None, vqvae_decode: bool = True) -> dict:
+def scene_encoder_of(model):
+    """The ``modules.SceneEncoder`` that runs ``model``'s (a reference Sg2ScDiffModel / Sg2BoxDiffModel instance) encoder
+    sub-modules.  Its parameters ARE the model's tensors (``load_state_dict(assign=True)``); it is rebuilt when the model's
+    parameters were replaced (``.cuda()``, ``load_networks``).  Kept outside the model's module tree, so the reference's
+    ``state_dict`` / checkpoints do not change."""
+    import torch.nn as nn
+    from . import modules
+
+    sd = {k: v for k, v in nn.Module.state_dict(model, keep_vars=True).items() if k.startswith(modules.SceneEncoder.PREFIXES)}
+    key = tuple(v.data_ptr() for v in sd.values())
+    cached = model.__dict__.get("_echo_scene_encoder")
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    enc = modules.SceneEncoder(num_objs=model.obj_embeddings_ec.weight.shape[0] - 1,
+                               num_preds=model.pred_embeddings_ec.weight.shape[0], embedding_dim=model.embedding_dim,
+                               gconv_num_layers=model.gconv_net_ec.num_layers,
+                               residual=any(k.endswith("linear_projection.weight") for k in sd), use_clip=bool(model.clip))
+    has_rel_s = any(k.startswith("rel_s_mlp.") for k in sd)          # the layout-only model has none
+    enc.load_state_dict(sd, strict=has_rel_s, assign=True)
+    enc.eval()
+    object.__setattr__(model, "_echo_scene_encoder", (key, enc))     # not a registered sub-module
+    return enc
+
+
+def _eval_only(model):
+    if model.training:   # the SceneEncoder is outside the module tree, so model.train() cannot reach its own eval check
+        from ._lib import EchoError
+        raise EchoError("init_encoder / manipulate on the B200 path are eval-mode only (BatchNorm running statistics, no "
+                        "autograd); patch_reference(scene_encoders=False) keeps the reference's methods for training")
+
+
+def _init_encoder(self, objs, triples, enc_text_feat, enc_rel_feat):
+    """Sg2ScDiffModel.init_encoder (EchoScene.py:143-157) as one echo_scene_init_encoder call."""
+    _eval_only(self)
+    return scene_encoder_of(self).init_encoder(objs, triples, enc_text_feat, enc_rel_feat)
+
+
+def _manipulate(self, latent_f, objs, triples, dec_text_feat, dec_rel_feat):
+    """Sg2ScDiffModel.manipulate (EchoScene.py:181-195) as one echo_scene_manipulate call."""
+    _eval_only(self)
+    return scene_encoder_of(self).manipulate(latent_f, objs, triples, dec_text_feat, dec_rel_feat)
+
+
+def patch_reference(precision: str = "fp32", ddim_steps: Optional[int] = None, vqvae_decode: bool = True,
+                    scene_encoders: bool = True) -> dict:
     """Call AFTER the reference checkout is importable (sys.path) and BEFORE SGDiff(...) is constructed.
-    ``vqvae_decode=False`` keeps the reference's VQVAE (needed for training, which encodes: echo2shape.py:349)."""
+    ``vqvae_decode=False`` keeps the reference's VQVAE (needed for training, which encodes: echo2shape.py:349);
+    ``scene_encoders=False`` keeps the reference's init_encoder / manipulate (they then run layer by layer on the patched
+    GraphTripleConvNet)."""
     from . import modules, samplers
 
     def _with_precision(cls):
@@ -70,4 +121,13 @@ def patch_reference(precision: str = "fp32", ddim_steps: Optional[int] = None, v
             if hasattr(mod, n):
                 setattr(mod, n, obj)
         done[modname] = sorted(names)
+    if scene_encoders:
+        for modname, cls in (("model.EchoScene", "Sg2ScDiffModel"), ("model.EchoLayout", "Sg2BoxDiffModel")):
+            try:
+                c = getattr(importlib.import_module(modname), cls)
+            except Exception as e:
+                done[modname + "." + cls] = f"not patched: {e!r}"
+                continue
+            c.init_encoder, c.manipulate = _init_encoder, _manipulate
+            done[modname + "." + cls] = ["init_encoder", "manipulate"]
     return done

@@ -179,3 +179,42 @@ def test_scene_entry_points_reject_bad_arguments():
     assert L.echo_scene_encode(None, None, None, None, None, None, None, None, None, None, None) == -1
     assert L.echo_scene_rel_s(None, None, 1, None, None) == -1
     L.echo_scene_destroy(None)
+
+
+def test_reference_side_binding_shares_parameters():
+    """integrate.scene_encoder_of(): the SceneEncoder behind the patched init_encoder / manipulate uses the model's own tensors,
+    stays out of its state_dict, is rebuilt when the parameters are replaced, and refuses train mode / CPU tensors."""
+    import torch.nn as nn
+    from echoscene_b200 import integrate
+
+    class Holder(nn.Module):                                     # the encoder sub-modules as EchoScene.py:46-100 builds them
+        def __init__(self):
+            super().__init__()
+            self.clip, self.embedding_dim = True, 64
+            self.obj_embeddings_ec = nn.Embedding(37, 128)
+            self.pred_embeddings_ec = nn.Embedding(16, 128)
+            kw = dict(hidden_dim=256, pooling="avg", mlp_normalization="batch", residual=True)
+            self.gconv_net_ec = modules.GraphTripleConvNet(640, 640, num_layers=5, output_dim=640, **kw)
+            self.gconv_net_manipulation = modules.GraphTripleConvNet(1344, 640, num_layers=5, output_dim=640, **kw)
+            self.rel_s_mlp = nn.Sequential(nn.Linear(640, 960), nn.BatchNorm1d(960), nn.ReLU(), nn.Linear(960, 1280))
+            self.obj_embeddings_dc = nn.Embedding(37, 128)       # present in the checkpoint, unused when sampling
+
+        init_encoder, manipulate = integrate._init_encoder, integrate._manipulate
+
+    h = Holder().eval()
+    keys = list(h.state_dict().keys())
+    enc = integrate.scene_encoder_of(h)
+    assert integrate.scene_encoder_of(h) is enc                                   # cached
+    assert list(h.state_dict().keys()) == keys                                    # not a registered sub-module
+    assert enc.state_dict()["gconv_net_ec.gconvs.0.net1.0.weight"].data_ptr() == h.gconv_net_ec.state_dict()["gconvs.0.net1.0.weight"].data_ptr()
+    assert enc.state_dict()["rel_s_mlp.3.bias"].data_ptr() == h.rel_s_mlp[3].bias.data_ptr()
+    assert [k for k in enc.state_dict()] == list(arch.scene_encoder_specs(cases.scene_cfg()).keys())
+    g, objs, text, rel = cases.scene_inputs()
+    with pytest.raises(_lib.EchoError, match="CUDA"):
+        h.init_encoder(objs, g.triples, text, rel)
+    h.train()
+    with pytest.raises(_lib.EchoError, match="eval"):
+        h.manipulate(torch.zeros(8, 704), objs, g.triples, text, rel)
+    h.eval()
+    h.obj_embeddings_ec.weight = nn.Parameter(h.obj_embeddings_ec.weight.detach().clone())   # what .cuda() / load does
+    assert integrate.scene_encoder_of(h) is not enc
