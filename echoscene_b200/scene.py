@@ -192,3 +192,56 @@ class Sg2ScDiffModel:
                                                                    encoded_dec_text_feat, encoded_dec_rel_feat,
                                                                    missing_nodes, gen_shape=gen_shape)
         return keep, {**shape_dict, **layout_dict}
+
+
+class Sg2BoxDiffModel(Sg2ScDiffModel):
+    """Sampling surface of the layout-only model (model/EchoLayout.py:291-401; SGDiff type_ == 'echolayout').  Same encoder
+    stage and layout chain; two behaviours of the reference differ from Sg2ScDiffModel and are kept: the additions draw
+    their change flags at ``nodes_added`` (EchoLayout.py:369-374, not at ``missing_nodes``), and ``sampleBoxes_with_additions``
+    returns ``keep`` as a plain Python list (:393-401)."""
+
+    def __init__(self, encoder, layout, **kw):
+        super().__init__(encoder, layout, shape=None, vqvae=None, **kw)
+
+    @torch.no_grad()
+    def sampleBoxes(self, dec_objs, dec_triplets, encoded_dec_text_feat, encoded_dec_rel_feat):
+        return self.sample(dec_objs, dec_triplets, encoded_dec_text_feat, encoded_dec_rel_feat, gen_shape=False)[1]
+
+    @torch.no_grad()
+    def sampleBoxes_with_changes(self, enc_objs, enc_triples, enc_text_feat, enc_rel_feat, dec_objs, dec_triples, dec_text_feat,
+                                 dec_rel_feat, manipulated_nodes):
+        keep, _, layout_dict = self.sample_with_changes(enc_objs, enc_triples, enc_text_feat, enc_rel_feat, dec_objs, dec_triples,
+                                                        dec_text_feat, dec_rel_feat, manipulated_nodes, gen_shape=False)
+        return keep, layout_dict
+
+    @torch.no_grad()
+    def sampleBoxes_with_additions(self, enc_objs, enc_triples, enc_text_feat, enc_rel_feat, dec_objs, dec_triples, dec_text_feat,
+                                   dec_rel_feat, missing_nodes):
+        e = self.encoder
+        _, _, latent_obj, _ = e.init_encoder(enc_objs, enc_triples, enc_text_feat, enc_rel_feat)
+        latent_obj, nodes_added = insert_zero_rows(latent_obj, missing_nodes)
+        change = change_flags(latent_obj.shape[0], nodes_added, self.embedding_dim, latent_obj.device)
+        latent_, _, obj_embed_, _ = e.manipulate(torch.cat([latent_obj, change], dim=1), dec_objs, dec_triples, dec_text_feat,
+                                                 dec_rel_feat)
+        latent = latent_ if self.replace_all_latent else replace_rows(latent_obj, latent_, nodes_added)
+        layout_dict = self.generate_layout(dec_triples, obj_embed_, latent)
+        added = set(nodes_added)
+        keep = [0 if i in added else 1 for i in range(len(layout_dict["translations"]))]
+        return keep, layout_dict
+
+    # ---- SGDiff facade, type_ == 'echolayout' (model/SGDiff.py:87-121) ------------------------------------------------
+    def sample_box_and_shape(self, dec_objs, dec_triplets, encoded_dec_text_feat, encoded_dec_rel_feat, gen_shape=False):
+        return self.sampleBoxes(dec_objs, dec_triplets, encoded_dec_text_feat, encoded_dec_rel_feat)
+
+    def sample_boxes_and_shape_with_changes(self, enc_objs, enc_triples, encoded_enc_text_feat, encoded_enc_rel_feat, dec_objs,
+                                            dec_triples, encoded_dec_text_feat, encoded_dec_rel_feat, manipulated_nodes,
+                                            gen_shape=False):
+        return self.sampleBoxes_with_changes(enc_objs, enc_triples, encoded_enc_text_feat, encoded_enc_rel_feat, dec_objs,
+                                             dec_triples, encoded_dec_text_feat, encoded_dec_rel_feat, manipulated_nodes)
+
+    def sample_boxes_and_shape_with_additions(self, enc_objs, enc_triples, encoded_enc_text_feat, encoded_enc_rel_feat, dec_objs,
+                                              dec_triples, encoded_dec_text_feat, encoded_dec_rel_feat, missing_nodes,
+                                              gen_shape=False):
+        # the reference's facade drops `keep` on this branch (SGDiff.py:114-116)
+        return self.sampleBoxes_with_additions(enc_objs, enc_triples, encoded_enc_text_feat, encoded_enc_rel_feat, dec_objs,
+                                               dec_triples, encoded_dec_text_feat, encoded_dec_rel_feat, missing_nodes)[1]

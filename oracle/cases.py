@@ -116,6 +116,10 @@ SCENE_GLUE_CASES = (
     ("changes_replace_all", "sample_with_changes", True),
     ("additions", "sample_with_additions", False),
     ("additions_replace_all", "sample_with_additions", True),
+    # the layout-only model (model/EchoLayout.py:291-400); its additions draw the change flags at nodes_added (:371)
+    ("box_sample", "sampleBoxes", False),
+    ("box_changes", "sampleBoxes_with_changes", False),
+    ("box_additions", "sampleBoxes_with_additions", False),
 )
 
 
@@ -123,8 +127,9 @@ def scene_glue_inputs(name: str):
     """-> (positional tensor arguments of the method, marked nodes or None).  `changes`: nodes 1 and 5 manipulated;
     `additions`: missing_nodes [2, 4] -> rows inserted at [2, 5] of the 6-node encoder scene (8 decoder nodes)."""
     g, objs, text, rel = scene_inputs()
-    if name == "sample":
+    if name in ("sample", "box_sample"):
         return (objs, g.triples, text, rel), None
+    name = name[4:] if name.startswith("box_") else name
     if name.startswith("changes"):
         ge, eobjs, etext, erel = scene_inputs(SCENE_ENC_CASE_SAME)
         return (eobjs, ge.triples, etext, erel, objs, g.triples, text, rel), [5, 1]

@@ -43,6 +43,7 @@ def main():
     cfg = cases.scene_cfg()
     gd, add = cfg.gconv_dim, cfg.add_dim
     M = es.Sg2ScDiffModel
+    MB = importlib.import_module("model.EchoLayout").Sg2BoxDiffModel
     rec = _Rec()
 
     class LayoutStub:
@@ -82,6 +83,7 @@ def main():
         init_encoder = M.init_encoder
         manipulate = M.manipulate
         prepare_boxes = M.prepare_boxes
+        prepare_input = MB.prepare_input        # the layout-only model's name for it (EchoLayout.py)
 
     sd = arch.make_state_dict(arch.scene_encoder_specs(cfg), cases.WEIGHT_SEED_SCENE)
     out = {}
@@ -97,11 +99,18 @@ def main():
             if fn == "sample":
                 res = M.sample(h, *args, gen_shape=True)
                 keep = None
+            elif fn == "sampleBoxes":
+                res = MB.sampleBoxes(h, *args)
+                keep = None
+            elif fn.startswith("sampleBoxes"):
+                res = getattr(MB, fn)(h, *args, marked)
+                keep = res[0]
             else:
                 res = getattr(M, fn)(h, *args, marked, gen_shape=True)
                 keep = res[0]
-            out[name] = {"uc_b": rec.layout_in["uc_b"], "c_b": rec.layout_in["c_b"], "preds": rec.layout_in["preds"],
-                         "uc_s": rec.shape_in["uc_s"], "c_s": rec.shape_in["c_s"], "keep": keep}
+            out[name] = {"uc_b": rec.layout_in["uc_b"], "c_b": rec.layout_in["c_b"], "preds": rec.layout_in["preds"], "keep": keep}
+            if rec.shape_in is not None:
+                out[name].update({"uc_s": rec.shape_in["uc_s"], "c_s": rec.shape_in["c_s"]})
             print(name, fn, {k: (tuple(v.shape) if torch.is_tensor(v) else v) for k, v in out[name].items()})
     finally:
         torch.Tensor.cuda = real_cuda

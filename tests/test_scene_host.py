@@ -64,7 +64,29 @@ def gold():
     return torch.load(os.path.join(GOLD, "scene_glue.pt"))
 
 
-@pytest.mark.parametrize("name,fn,replace", cases.SCENE_GLUE_CASES)
+@pytest.mark.parametrize("name,fn,replace", [c for c in cases.SCENE_GLUE_CASES if c[0].startswith("box_")])
+def test_layout_only_glue_matches_reference_methods(gold, name, fn, replace):
+    """Sg2BoxDiffModel.sampleBoxes* (model/EchoLayout.py:291-401)."""
+    G = gold[name]
+    lay = RecLayout()
+    m = scene.Sg2BoxDiffModel(OracleEncoder(), lay, replace_latent=replace)
+    args, marked = cases.scene_glue_inputs(name)
+    np.random.seed(cases.SCENE_GLUE_NP_SEED)
+    if fn == "sampleBoxes":
+        layout_dict = m.sampleBoxes(*args)
+        assert m.sample_box_and_shape(*args).keys() == layout_dict.keys() == {"sizes", "translations", "angles"}
+    else:
+        keep, layout_dict = getattr(m, fn)(*args, marked)
+        if torch.is_tensor(G["keep"]):
+            assert torch.equal(keep, G["keep"])
+        else:
+            assert keep == G["keep"] and isinstance(keep, list)
+    for k in ("uc_b", "c_b", "preds"):
+        assert torch.equal(lay.seen[k], G[k]), (name, k)
+    assert layout_dict["translations"].shape == (8, 3)
+
+
+@pytest.mark.parametrize("name,fn,replace", [c for c in cases.SCENE_GLUE_CASES if not c[0].startswith("box_")])
 def test_glue_matches_reference_methods(gold, name, fn, replace):
     G = gold[name]
     lay = RecLayout()

@@ -121,7 +121,7 @@ class RecDDIM:
         return x_T, {}
 
 
-@pytest.mark.parametrize("name,fn,replace", [c for c in cases.SCENE_GLUE_CASES if c[1] != "sample"])
+@pytest.mark.parametrize("name,fn,replace", [c for c in cases.SCENE_GLUE_CASES if c[1].startswith("sample_with")])
 def test_changes_and_additions_vs_reference_golden(enc, name, fn, replace):
     """sample_with_changes / sample_with_additions with the CUDA encoders: the conditioning tensors that reach the two branches
     against those recorded from the reference's own methods."""
