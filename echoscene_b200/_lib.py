@@ -112,6 +112,8 @@ PROTOTYPES = {
     "echo_scene_destroy": (None, [_P]),
     "echo_vqvae_create": (C.c_int, [C.POINTER(_P), C.POINTER(VqvaeDesc), C.POINTER(Weight), _I]),
     "echo_vqvae_decode": (C.c_int, [_P, _P, _I, _P, _P, _P]),
+    "echo_vqvae_encoder_create": (C.c_int, [C.POINTER(_P), C.POINTER(VqvaeDesc), C.POINTER(Weight), _I]),
+    "echo_vqvae_encode": (C.c_int, [_P, _P, _I, _P, _P]),
     "echo_vqvae_destroy": (None, [_P]),
     "echo_op_conv3d": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "echo_op_upconv3d": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P]),

@@ -30,6 +30,8 @@ const float* shape_latent(const echo_shape*);
 echo_vqvae* vqvae_create(const echo_vqvae_desc_t*, const echo_weight_t*, int);
 void vqvae_destroy(echo_vqvae*);
 void vqvae_decode(echo_vqvae*, const float*, int, float*, int*, cudaStream_t);
+echo_vqvae* vqvae_encoder_create(const echo_vqvae_desc_t*, const echo_weight_t*, int);
+void vqvae_encode(echo_vqvae*, const float*, int, float*, cudaStream_t);
 int shape_context_dim(const echo_shape*);
 echo_scene* scene_create(const echo_scene_desc_t*, const echo_weight_t*, int);
 void scene_destroy(echo_scene*);
@@ -327,6 +329,18 @@ int echo_vqvae_decode(echo_vqvae_t* h, const float* latents, int32_t n, float* s
   return guard([&] {
     ECHO_CHECK(h && (n == 0 || (latents && sdf_out)), "vqvae_decode: null argument");
     vqvae_decode(h, latents, n, sdf_out, indices_out, (cudaStream_t)stream);
+  });
+}
+int echo_vqvae_encoder_create(echo_vqvae_t** out, const echo_vqvae_desc_t* desc, const echo_weight_t* weights, int32_t n_weights) {
+  return guard([&] {
+    ECHO_CHECK(out && desc && (weights || n_weights == 0), "vqvae_encoder_create: null argument");
+    *out = vqvae_encoder_create(desc, weights, n_weights);
+  });
+}
+int echo_vqvae_encode(echo_vqvae_t* h, const float* sdf, int32_t n, float* latents_out, void* stream) {
+  return guard([&] {
+    ECHO_CHECK(h && (n == 0 || (sdf && latents_out)), "vqvae_encode: null argument");
+    vqvae_encode(h, sdf, n, latents_out, (cudaStream_t)stream);
   });
 }
 void echo_vqvae_destroy(echo_vqvae_t* h) { vqvae_destroy(h); }

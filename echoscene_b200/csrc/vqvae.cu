@@ -80,6 +80,72 @@ struct ResnetW {
   bool has_nin = false;
 };
 
+// state_dict entries -> prepared device copies in the handle's pool (conv kernels repacked tap-major, optional bf16 copy)
+struct VqLoader {
+  const WeightMap& wm;
+  DevPool& pool;
+  bool bf;
+  cudaStream_t s;
+  const float* vec(const std::string& name, int n) const {
+    const WView& v = wm.get(name, {n});
+    float* o = pool.alloc_n<float>(n);
+    ECHO_CUDA(cudaMemcpyAsync(o, v.p, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+    return o;
+  }
+  const __nv_bfloat16* to_bf16(const float* w, size_t n) const {
+    __nv_bfloat16* o = pool.alloc_n<__nv_bfloat16>(n);
+    convert(w, F32, o, BF16, (int64_t)n, s);
+    return o;
+  }
+  ConvW conv(const std::string& p, int cin, int cout, int k) const {
+    ConvW c;
+    c.cin = cin; c.cout = cout; c.taps = k * k * k;
+    const WView& v = wm.get(p + ".weight", {cout, cin, k, k, k});
+    const size_t n_el = (size_t)cout * cin * c.taps;
+    float* o = pool.alloc_n<float>(n_el);
+    if (c.taps == 1) ECHO_CUDA(cudaMemcpyAsync(o, v.p, sizeof(float) * n_el, cudaMemcpyDeviceToDevice, s));
+    else repack_conv_weight(v.p, cout, cin, c.taps, o, s);
+    c.w = o;
+    if (bf) c.wb = to_bf16(o, n_el);
+    c.b = vec(p + ".bias", cout);
+    return c;
+  }
+  NormW norm(const std::string& p, int c) const {
+    NormW n;
+    n.c = c;
+    n.g = vec(p + ".weight", c);
+    n.b = vec(p + ".bias", c);
+    return n;
+  }
+  ResnetW resnet(const std::string& p, int cin, int cout) const {
+    ResnetW r;
+    r.cin = cin; r.cout = cout;
+    ECHO_CHECK(cin % 32 == 0 && cout % 32 == 0, "vqvae: Normalize() with 32 groups needs channels %% 32 == 0 (%d, %d)", cin, cout);
+    r.n1 = norm(p + ".norm1", cin);
+    r.c1 = conv(p + ".conv1", cin, cout, 3);
+    r.n2 = norm(p + ".norm2", cout);
+    r.c2 = conv(p + ".conv2", cout, cout, 3);
+    r.has_nin = cin != cout;
+    if (r.has_nin) r.nin = conv(p + ".nin_shortcut", cin, cout, 1);
+    return r;
+  }
+  // q, k, v 1x1 convs of an AttnBlock stacked [3C, C] (+ biases) for one projection launch (fp32)
+  ConvW qkv_stack(const std::string& p, int C) const {
+    float* w = pool.alloc_n<float>((size_t)3 * C * C);
+    float* b = pool.alloc_n<float>((size_t)3 * C);
+    const char* names[3] = {"q", "k", "v"};
+    for (int i = 0; i < 3; ++i) {
+      const WView& wv = wm.get(p + names[i] + ".weight", {C, C, 1, 1, 1});
+      const WView& bv = wm.get(p + names[i] + ".bias", {C});
+      ECHO_CUDA(cudaMemcpyAsync(w + (size_t)i * C * C, wv.p, sizeof(float) * C * C, cudaMemcpyDeviceToDevice, s));
+      ECHO_CUDA(cudaMemcpyAsync(b + (size_t)i * C, bv.p, sizeof(float) * C, cudaMemcpyDeviceToDevice, s));
+    }
+    ConvW q;
+    q.cin = C; q.cout = 3 * C; q.taps = 1; q.w = w; q.b = b;
+    return q;
+  }
+};
+
 }  // namespace
 
 struct echo_vqvae {
@@ -98,6 +164,13 @@ struct echo_vqvae {
   std::vector<std::vector<ResnetW>> up_blocks;   // [level][block]
   std::vector<ConvW> up_conv;                    // [level] (level 0: unused)
   std::vector<ConvW> up_fold;                    // bf16 mode: the same convs folded per output phase of the x2 upsample
+  // encoder handles (vqvae_encoder_create): Encoder3D + quant_conv; conv_in / mid1 / attn_* / mid2 / norm_out / conv_out above
+  // hold the ENCODER's tensors then
+  bool is_encoder = false;
+  int in_ch = 1;
+  std::vector<std::vector<ResnetW>> down_blocks;   // [level][block]
+  std::vector<ConvW> down_conv;                    // [level] (last level: unused)
+  ConvW quant_conv;
 
   Act new_act(int n, int dd, int h, int w, int c, DT dt) {
     Act a;
@@ -105,18 +178,22 @@ struct echo_vqvae {
     a.p = arena.alloc(a.bytes());
     return a;
   }
-  void contract(const Act& x, const ConvW& w, int k, const Act* res, const Act& out, cudaStream_t s) {
+  // stride / pad: Conv3d(k, stride, padding = pad) with pad < 0 meaning k / 2; taps that fall outside the input read zeros, so
+  // Downsample's explicit (0, 1) zero pad + Conv3d(k3, stride 2, padding 0) (vqvae_modules.py:42-58) is stride 2, pad 0 with
+  // an output grid of half the input
+  void contract(const Act& x, const ConvW& w, int k, const Act* res, const Act& out, cudaStream_t s, int stride = 1, int pad = -1) {
     if (dry) return;
     GemmArgs g;
     g.A = x.p; g.a_dt = x.dt; g.n = x.n; g.d = x.d; g.h = x.h; g.w = x.w; g.cin = x.c; g.lda = x.c;
     g.od = out.d; g.oh = out.h; g.ow = out.w;
-    g.kd = g.kh = g.kw = k; g.pd = g.ph = g.pw = k / 2;
+    g.kd = g.kh = g.kw = k; g.pd = g.ph = g.pw = pad < 0 ? k / 2 : pad;
+    g.sd = g.sh = g.sw = stride;
     g.W = w.w; g.w_dt = F32; g.w_stride_n = (int64_t)w.taps * w.cin; g.cout = w.cout; g.bias = w.b;
     if (res) { g.res = res->p; g.res_dt = res->dt; g.ld_res = res->c; }
     g.out = out.p; g.out_dt = out.dt; g.ldo = out.c;
     ECHO_CHECK(w.cin == x.c && w.cout == out.c && w.taps == k * k * k, "vqvae: weight/activation mismatch (cin %d vs %d, cout %d vs %d)", w.cin,
                x.c, w.cout, out.c);
-    if (prec == ECHO_PREC_BF16 && w.wb && x.dt == BF16 && tc_available()) {
+    if (prec == ECHO_PREC_BF16 && w.wb && x.dt == BF16 && stride == 1 && tc_available()) {
       GemmArgs t = g;
       t.W = w.wb; t.w_dt = BF16;
       if (gemm_tc_supported(t)) { gemm_tc(t, s); return; }
@@ -239,7 +316,50 @@ struct echo_vqvae {
     return o;
   }
 
+  void gelu_inplace(const Act& x, cudaStream_t s) {
+    if (dry) return;
+    const long long cnt = (long long)x.rows() * x.c;
+    long long blocks = (cnt + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (x.dt == F32) gelu_kernel<float><<<(int)blocks, 256, 0, s>>>((float*)x.p, cnt);
+    else gelu_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, s>>>((__nv_bfloat16*)x.p, cnt);
+    ECHO_LAUNCH_CHECK();
+  }
+
+  // VQVAE.encode_no_quant (network.py:84-88): Encoder3D.forward (vqvae_modules.py:256-289) -> quant_conv.
+  // sdf (n, in_ch, R, R, R) NCDHW with in_ch == 1 (so it is channels-last as it stands) -> latents (n, embed_dim, L, L, L) NCDHW
+  void run_encode(const float* sdf, int n, float* latents_out, cudaStream_t s) {
+    ECHO_CHECK(is_encoder, "vqvae_encode: this handle was created by echo_vqvae_create (decoder); use echo_vqvae_encoder_create");
+    ECHO_CHECK(n >= 0 && n <= d.max_objects, "vqvae_encode: %d objects exceed the handle's capacity %d", n, d.max_objects);
+    if (n == 0) return;
+    arena.release(0);
+    const int R = d.latent_size << (d.num_levels - 1);
+    Act x;
+    x.n = n; x.d = x.h = x.w = R; x.c = in_ch; x.dt = F32; x.p = const_cast<float*>(sdf);
+    Act h = new_act(n, R, R, R, conv_in.cout, adt);
+    contract(x, conv_in, 3, nullptr, h, s);
+    for (int lvl = 0; lvl < d.num_levels; ++lvl) {
+      for (auto& r : down_blocks[lvl]) h = resnet(h, r, s);
+      if (lvl != d.num_levels - 1) {
+        Act o = new_act(n, h.d / 2, h.h / 2, h.w / 2, down_conv[lvl].cout, adt);
+        contract(h, down_conv[lvl], 3, nullptr, o, s, 2, 0);
+        h = o;
+      }
+    }
+    h = resnet(h, mid1, s);
+    h = attn(h, s);
+    h = resnet(h, mid2, s);
+    Act hn = gn(h, norm_out, false, s);
+    gelu_inplace(hn, s);                                            // activ = 'gelu', vqvae_modules.py:199-201, 288
+    Act z = new_act(n, hn.d, hn.h, hn.w, conv_out.cout, F32);
+    contract(hn, conv_out, 3, nullptr, z, s);
+    Act q = new_act(n, hn.d, hn.h, hn.w, quant_conv.cout, F32);
+    contract(z, quant_conv, 1, nullptr, q, s);
+    if (!dry) cl_to_ncdhw(q.p, F32, n, q.c, q.voxels(), q.c, latents_out, s);
+  }
+
   void run(const float* latents, int n, float* sdf_out, int* indices_out, cudaStream_t s) {
+    ECHO_CHECK(!is_encoder, "vqvae_decode: this handle was created by echo_vqvae_encoder_create (encoder)");
     ECHO_CHECK(n >= 0 && n <= d.max_objects, "vqvae_decode: %d objects exceed the handle's capacity %d", n, d.max_objects);
     if (n == 0) return;
     arena.release(0);
@@ -328,49 +448,12 @@ echo_vqvae* vqvae_create(const echo_vqvae_desc_t* desc, const echo_weight_t* wei
     cudaStream_t s = 0;
     DevPool& pool = h->pool;
     const bool bf = h->prec == ECHO_PREC_BF16;
-    auto vec = [&](const std::string& name, int n) {
-      const WView& v = wm.get(name, {n});
-      float* o = pool.alloc_n<float>(n);
-      ECHO_CUDA(cudaMemcpyAsync(o, v.p, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
-      return (const float*)o;
-    };
-    auto to_bf16 = [&](const float* w, size_t n) {
-      __nv_bfloat16* o = pool.alloc_n<__nv_bfloat16>(n);
-      convert(w, F32, o, BF16, (int64_t)n, s);
-      return (const __nv_bfloat16*)o;
-    };
-    auto conv = [&](const std::string& p, int cin, int cout, int k) {
-      ConvW c;
-      c.cin = cin; c.cout = cout; c.taps = k * k * k;
-      const WView& v = wm.get(p + ".weight", {cout, cin, k, k, k});
-      const size_t n_el = (size_t)cout * cin * c.taps;
-      float* o = pool.alloc_n<float>(n_el);
-      if (c.taps == 1) ECHO_CUDA(cudaMemcpyAsync(o, v.p, sizeof(float) * n_el, cudaMemcpyDeviceToDevice, s));
-      else repack_conv_weight(v.p, cout, cin, c.taps, o, s);
-      c.w = o;
-      if (bf) c.wb = to_bf16(o, n_el);
-      c.b = vec(p + ".bias", cout);
-      return c;
-    };
-    auto norm = [&](const std::string& p, int c) {
-      NormW n;
-      n.c = c;
-      n.g = vec(p + ".weight", c);
-      n.b = vec(p + ".bias", c);
-      return n;
-    };
-    auto resnet = [&](const std::string& p, int cin, int cout) {
-      ResnetW r;
-      r.cin = cin; r.cout = cout;
-      ECHO_CHECK(cin % 32 == 0 && cout % 32 == 0, "vqvae: Normalize() with 32 groups needs channels %% 32 == 0 (%d, %d)", cin, cout);
-      r.n1 = norm(p + ".norm1", cin);
-      r.c1 = conv(p + ".conv1", cin, cout, 3);
-      r.n2 = norm(p + ".norm2", cout);
-      r.c2 = conv(p + ".conv2", cout, cout, 3);
-      r.has_nin = cin != cout;
-      if (r.has_nin) r.nin = conv(p + ".nin_shortcut", cin, cout, 1);
-      return r;
-    };
+    const VqLoader ld{wm, pool, bf, s};
+    auto vec = [&](const std::string& name, int n) { return ld.vec(name, n); };
+    auto to_bf16 = [&](const float* w, size_t n) { return ld.to_bf16(w, n); };
+    auto conv = [&](const std::string& p, int cin, int cout, int k) { return ld.conv(p, cin, cout, k); };
+    auto norm = [&](const std::string& p, int c) { return ld.norm(p, c); };
+    auto resnet = [&](const std::string& p, int cin, int cout) { return ld.resnet(p, cin, cout); };
     {
       const WView& cb = wm.get("quantize.embedding.weight", {d.n_embed, d.embed_dim});
       float* o = pool.alloc_n<float>(cb.numel());
@@ -480,6 +563,67 @@ echo_vqvae* vqvae_create(const echo_vqvae_desc_t* desc, const echo_weight_t* wei
     throw;
   }
 }
+
+// Encoder3D + quant_conv.  fp32 only: the strided convs and the 1-channel stem have no tensor-core route yet,
+// and the training path that calls encode_no_quant (echo2shape.py:334-364) wants the reference's fp32 latents.
+echo_vqvae* vqvae_encoder_create(const echo_vqvae_desc_t* desc, const echo_weight_t* weights, int n_weights) {
+  ECHO_CHECK(desc, "vqvae_encoder: null desc");
+  echo_vqvae* h = new echo_vqvae();
+  try {
+    h->d = *desc;
+    h->is_encoder = true;
+    const echo_vqvae_desc_t& d = h->d;
+    ECHO_CHECK(d.num_levels >= 1 && d.num_levels <= 8 && d.max_objects > 0 && d.latent_size > 0 && d.ch > 0 && d.num_res_blocks >= 0 &&
+                   d.z_channels > 0 && d.embed_dim > 0,
+               "vqvae_encoder: bad config");
+    ECHO_CHECK(d.out_ch == 1, "vqvae_encoder: in_channels (== out_ch) must be 1 (the SDF volume is read as NCDHW == channels-last)");
+    if (d.precision != ECHO_PREC_FP32) fail(ECHO_ERR_UNSUPPORTED, "vqvae_encoder: only ECHO_PREC_FP32 is implemented for encode_no_quant");
+    h->prec = ECHO_PREC_FP32;
+    h->adt = F32;
+    h->in_ch = d.out_ch;
+    WeightMap wm;
+    wm.load(weights, n_weights);
+    cudaStream_t s = 0;
+    const VqLoader ld{wm, h->pool, false, s};
+    h->conv_in = ld.conv("encoder.conv_in", h->in_ch, d.ch, 3);
+    h->down_blocks.resize(d.num_levels);
+    h->down_conv.resize(d.num_levels);
+    int block_in = d.ch;
+    for (int lvl = 0; lvl < d.num_levels; ++lvl) {
+      block_in = d.ch * (lvl == 0 ? 1 : d.ch_mult[lvl - 1]);          // in_ch_mult = (1,) + ch_mult, vqvae_modules.py:213-218
+      const int block_out = d.ch * d.ch_mult[lvl];
+      for (int i = 0; i < d.num_res_blocks; ++i) {
+        h->down_blocks[lvl].push_back(ld.resnet("encoder.down." + std::to_string(lvl) + ".block." + std::to_string(i), block_in, block_out));
+        block_in = block_out;
+      }
+      if (lvl != d.num_levels - 1) h->down_conv[lvl] = ld.conv("encoder.down." + std::to_string(lvl) + ".downsample.conv", block_in, block_in, 3);
+    }
+    h->mid1 = ld.resnet("encoder.mid.block_1", block_in, block_in);
+    h->attn_norm = ld.norm("encoder.mid.attn_1.norm", block_in);
+    h->qkv = ld.qkv_stack("encoder.mid.attn_1.", block_in);
+    h->attn_out = ld.conv("encoder.mid.attn_1.proj_out", block_in, block_in, 1);
+    h->mid2 = ld.resnet("encoder.mid.block_2", block_in, block_in);
+    h->norm_out = ld.norm("encoder.norm_out", block_in);
+    h->conv_out = ld.conv("encoder.conv_out", block_in, d.z_channels, 3);   // double_z: False (config/vqvae_snet.yaml)
+    h->quant_conv = ld.conv("quant_conv", d.z_channels, d.embed_dim, 1);
+    ECHO_CUDA(cudaStreamSynchronize(s));
+    h->dry = true;
+    h->arena.base = nullptr;
+    h->arena.cap = ~size_t(0) >> 1;
+    h->arena.off = h->arena.high = 0;
+    h->run_encode(nullptr, d.max_objects, nullptr, s);
+    h->dry = false;
+    h->arena.init(h->arena.high + (size_t(1) << 20));
+    return h;
+  } catch (...) {
+    h->arena.destroy();
+    h->pool.destroy();
+    delete h;
+    throw;
+  }
+}
+
+void vqvae_encode(echo_vqvae* h, const float* sdf, int n, float* latents_out, cudaStream_t s) { h->run_encode(sdf, n, latents_out, s); }
 
 void vqvae_destroy(echo_vqvae* h) {
   if (!h) return;

@@ -639,13 +639,15 @@ class DiffusionUNet(nn.Module):
 # VQ-VAE decode
 # ----------------------------------------------------------------------------------------------------------------------
 class VQVAE(_SpecModule):
-    """The decode half of model/networks/vqvae_networks/network.py:56-103 (same constructor): ``decode_no_quant(h)`` =
-    quantize -> post_quant_conv -> Decoder3D, what EchoToShape.rel2shape calls on the sampled latents
-    (echo2shape.py:522).  state_dict keys are the reference's (quantize.embedding.weight, post_quant_conv.*, decoder.*);
-    encoder / quant_conv entries of a reference checkpoint are accepted and ignored by ``load_state_dict`` (the encoder
-    is not on this path); ``encode*`` raise."""
+    """model/networks/vqvae_networks/network.py:56-103 (same constructor).  ``decode_no_quant(h)`` = quantize ->
+    post_quant_conv -> Decoder3D, what EchoToShape.rel2shape calls on the sampled latents (echo2shape.py:522).  state_dict
+    keys are the reference's (quantize.embedding.weight, post_quant_conv.*, decoder.*).  With ``with_encoder=True`` the
+    module also owns encoder.* and quant_conv.* and ``encode_no_quant(x)`` (network.py:84-88, the call of the training
+    step on the ground-truth SDFs, echo2shape.py:334-364) runs through echo_vqvae_encode in fp32; without it those entries
+    of a reference checkpoint are accepted and ignored by ``load_state_dict`` and ``encode*`` raise."""
 
-    def __init__(self, ddconfig, n_embed, embed_dim, remap=None, sane_index_shape=False, precision: str = "fp32"):
+    def __init__(self, ddconfig, n_embed, embed_dim, remap=None, sane_index_shape=False, precision: str = "fp32",
+                 with_encoder: bool = False):
         super().__init__()
         if remap is not None:
             raise EchoError("VQVAE: remap is outside the hot path")
@@ -656,19 +658,27 @@ class VQVAE(_SpecModule):
                                     out_ch=dd["out_ch"], ch=dd["ch"], ch_mult=tuple(dd["ch_mult"]), num_res_blocks=dd["num_res_blocks"])
         self.ddconfig, self.n_embed, self.embed_dim = dd, n_embed, embed_dim
         self.precision = precision
-        self._build_from_specs(arch.vqvae_decode_specs(self.cfg))
+        self.with_encoder = bool(with_encoder)
+        specs = arch.vqvae_decode_specs(self.cfg)
+        if self.with_encoder:
+            if dd.get("double_z", False):
+                raise EchoError("VQVAE: double_z=True is outside the hot path (config/vqvae_snet.yaml uses False)")
+            if dd.get("in_channels", 1) != 1:
+                raise EchoError("VQVAE: the encoder takes 1-channel SDF volumes (config/vqvae_snet.yaml)")
+            enc = arch.vqvae_encode_specs(self.cfg, 1)
+            enc.update(specs)
+            specs = enc
+        self._build_from_specs(specs)
+        self._enc_handle, self._enc_key = None, None
         self.eval()
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
-        own = {k: v for k, v in state_dict.items() if not (k.startswith("encoder.") or k.startswith("quant_conv."))}
+        own = state_dict
+        if not self.with_encoder:
+            own = {k: v for k, v in state_dict.items() if not (k.startswith("encoder.") or k.startswith("quant_conv."))}
         return super().load_state_dict(own, strict=strict, **kw)
 
-    def _ensure(self, n):
-        ver = self._weights_version()
-        if self._handle is not None and self._handle_key[0] == ver and n <= self._handle_key[1]:
-            return
-        self._destroy_handle()
-        cap = max(n, 1)
+    def _desc(self, cap: int, precision: str):
         c = self.cfg
         d = _lib.VqvaeDesc()
         d.embed_dim, d.n_embed, d.z_channels, d.latent_size = c.embed_dim, c.n_embed, c.z_channels, c.latent_size
@@ -676,7 +686,33 @@ class VQVAE(_SpecModule):
         for i, m in enumerate(c.ch_mult):
             d.ch_mult[i] = m
         d.max_objects = cap
-        d.precision = _lib.PREC_BF16 if self.precision == "bf16" else _lib.PREC_FP32
+        d.precision = _lib.PREC_BF16 if precision == "bf16" else _lib.PREC_FP32
+        return d
+
+    def _ensure_encoder(self, n):
+        ver = self._weights_version()
+        if self._enc_handle is not None and self._enc_key[0] == ver and n <= self._enc_key[1]:
+            return
+        self._destroy_encoder()
+        cap = max(n, 1)
+        d = self._desc(cap, "fp32")                      # encode_no_quant is fp32 only (echo_vqvae_encoder_create)
+        arr, nw, keep = _lib.weights_table(self.state_dict())
+        h = C.c_void_p()
+        _lib.check(_lib.lib().echo_vqvae_encoder_create(C.byref(h), C.byref(d), arr, nw))
+        self._enc_handle, self._enc_key = h, (ver, cap)
+
+    def _destroy_encoder(self):
+        if getattr(self, "_enc_handle", None) is not None:
+            _lib.lib().echo_vqvae_destroy(self._enc_handle)
+            self._enc_handle = None
+
+    def _ensure(self, n):
+        ver = self._weights_version()
+        if self._handle is not None and self._handle_key[0] == ver and n <= self._handle_key[1]:
+            return
+        self._destroy_handle()
+        cap = max(n, 1)
+        d = self._desc(cap, self.precision)
         arr, nw, keep = _lib.weights_table(self.state_dict())
         h = C.c_void_p()
         _lib.check(_lib.lib().echo_vqvae_create(C.byref(h), C.byref(d), arr, nw))
@@ -686,6 +722,7 @@ class VQVAE(_SpecModule):
         if self._handle is not None:
             _lib.lib().echo_vqvae_destroy(self._handle)
             self._handle = None
+        self._destroy_encoder()
 
     max_chunk = 32   # objects decoded per library call: the decoder keeps ~0.5 GB of activations per object (bf16)
 
@@ -712,10 +749,34 @@ class VQVAE(_SpecModule):
                                                     _lib.stream_ptr()))
         return (out, idx) if return_indices else out
 
+    max_encode_chunk = 8   # objects encoded per library call: the fp32 encoder keeps ~0.6 GB of activations per object
+
+    @torch.no_grad()
+    def encode_no_quant(self, x):
+        """x (N, 1, 64, 64, 64) SDF -> latents (N, 3, 16, 16, 16): encoder -> quant_conv, no quantisation (network.py:84-88).
+        Objects are independent, so large batches run in chunks of ``max_encode_chunk`` with bit-identical results."""
+        if not self.with_encoder:
+            raise EchoError("VQVAE.encode_no_quant needs VQVAE(..., with_encoder=True) (the decode-only module owns no encoder "
+                            "weights)")
+        self._check_eval()
+        _lib.require_cuda(x)
+        c = self.cfg
+        n, R, L = x.shape[0], c.resolution, c.latent_size
+        if tuple(x.shape) != (n, 1, R, R, R):
+            raise EchoError(f"encode_no_quant input must be (N,1,{R},{R},{R}), got {tuple(x.shape)}")
+        x = x.float().contiguous()
+        chunk = max(1, int(self.max_encode_chunk))
+        self._ensure_encoder(min(n, chunk))
+        out = torch.empty(n, c.embed_dim, L, L, L, device=x.device)
+        for b in range(0, n, chunk):
+            e = min(n, b + chunk)
+            _lib.check(_lib.lib().echo_vqvae_encode(self._enc_handle, _lib.ptr(x[b:e]), e - b, _lib.ptr(out[b:e]),
+                                                    _lib.stream_ptr()))
+        return out
+
     def forward(self, *a, **k):
-        raise EchoError("VQVAE.forward (encode + decode) is outside the hot path; use decode_no_quant")
+        raise EchoError("VQVAE.forward (encode + quantise + decode, the VQ-VAE's own training step) is outside the hot path; "
+                        "use encode_no_quant / decode_no_quant")
 
     def encode(self, *a, **k):
-        raise EchoError("VQVAE.encode is outside the hot path")
-
-    encode_no_quant = encode
+        raise EchoError("VQVAE.encode (with quantisation losses) is outside the hot path; use encode_no_quant")

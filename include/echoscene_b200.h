@@ -208,6 +208,15 @@ typedef struct {
 } echo_vqvae_desc_t;
 ECHO_API int echo_vqvae_create(echo_vqvae_t** out, const echo_vqvae_desc_t* desc, const echo_weight_t* weights, int32_t n_weights);
 ECHO_API int echo_vqvae_decode(echo_vqvae_t* h, const float* latents, int32_t n, float* sdf_out, int32_t* indices_out, void* stream);
+/* ---- VQ-VAE encode: VQVAE.encode_no_quant, model/networks/vqvae_networks/network.py:84-88 -- what the
+ * training step calls on the ground-truth SDFs (echo2shape.py:334-364): Encoder3D (vqvae_modules.py:198-289: conv_in,
+ * per level ResnetBlock(s) + Downsample [zero pad (0,1) + Conv3d k3 stride 2], mid ResnetBlock / AttnBlock / ResnetBlock,
+ * GroupNorm, GELU, conv_out) -> quant_conv 1x1x1, no quantisation.  Same desc as the decoder (in_channels == out_ch == 1,
+ * double_z False); weights by the reference's names encoder.*, quant_conv.*.  ECHO_PREC_FP32 only (ECHO_ERR_UNSUPPORTED
+ * otherwise).  A handle is either a decoder or an encoder; both are freed by echo_vqvae_destroy.
+ * sdf (n, 1, R, R, R) f32, R = latent_size * 2^(num_levels-1) -> latents_out (n, embed_dim, L, L, L) f32 NCDHW. */
+ECHO_API int echo_vqvae_encoder_create(echo_vqvae_t** out, const echo_vqvae_desc_t* desc, const echo_weight_t* weights, int32_t n_weights);
+ECHO_API int echo_vqvae_encode(echo_vqvae_t* h, const float* sdf, int32_t n, float* latents_out, void* stream);
 ECHO_API void echo_vqvae_destroy(echo_vqvae_t* h);
 
 /* ---- once-per-scene encoders of Sg2ScDiffModel.sample (model/EchoScene.py:143-157, 181-195, 388-410): the stage between
