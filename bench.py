@@ -149,6 +149,36 @@ def vqvae_decode_rate(dev, precision):
             "tflops_algorithmic": 723e9 * N_NODES / (ms * 1e-3) / 1e12}
 
 
+def scene_encode_time(dev):
+    """Secondary figure (the stage right before the two chains): Sg2ScDiffModel.sample's encoders (init_encoder ->
+    manipulate -> rel_s_mlp x2) for the 16-node / 64-triple scene as ONE echo_scene_encode call, fp32.  HBM-bound weight
+    streaming like the layout step: 10 GraphTripleConv layers + rel_s_mlp = 28.9 M parameters read once per call."""
+    from echoscene_b200 import arch, modules
+    from oracle import cases
+    cfg = cases.scene_cfg()
+    m = modules.SceneEncoder()
+    m.load_state_dict(arch.make_state_dict(arch.scene_encoder_specs(cfg), cases.WEIGHT_SEED_SCENE))
+    m = m.to(dev)
+    g, objs, text, rel = cases.scene_inputs(cases.GraphCase("bench_scene", N_NODES, N_TRIPLES, 2))
+    a = [t.to(dev) for t in (objs, g.triples, text, rel)]
+    for _ in range(3):
+        out = m.encode(*a)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    reps = 20
+    e0.record()
+    for _ in range(reps):
+        out = m.encode(*a)
+    e1.record()
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(v).all() for v in out.values())
+    ms = e0.elapsed_time(e1) / reps
+    params = sum(v.numel() for k, v in m.state_dict().items() if v.dtype == torch.float32)
+    return {"ms_per_scene": ms, "n_nodes": N_NODES, "n_triples": N_TRIPLES, "dtype": "f32", "live_parameters": params,
+            "unit": "ms per scene encode (one C call; includes the object-id range check's host read)",
+            "hbm_gbs_algorithmic": params * 4 / (ms * 1e-3) / 1e9}
+
+
 def conv_kernel_roofline(dev, pk):
     """The dominant kernel timed alone: tcgen05 implicit-GEMM conv 224@16^3 -> 224, N=16 objects (7 of these per step,
     SURVEY Appendix E).  CUDA events on the launching stream; L2 flushed between launches."""
@@ -417,6 +447,12 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": "steps/s", "cores": cores, "kind": "port",
                                     "sample": f"2 timed shape steps over 2 objects ({tcpu:.2f} s each, torch fp32, {cores} threads), "
                                               "scaled by 2/16 to the N=16 step"}
+        if world == 1:
+            # last, and never fatal: a secondary figure must not cost the headline line
+            try:
+                line["scene_encode"] = scene_encode_time(dev)
+            except Exception as e:   # noqa: BLE001
+                line["scene_encode"] = {"error": repr(e)[:200]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
