@@ -71,6 +71,57 @@ def keep_mask(n: int, dropped: Sequence[int], device) -> torch.Tensor:
     return torch.from_numpy(k).float().to(device)
 
 
+def _strip(sd: dict, prefixes: Sequence[str]) -> dict:
+    """Entries of ``sd`` under the first prefix of ``prefixes`` that occurs, with that prefix removed."""
+    for p in prefixes:
+        sub = {k[len(p):]: v for k, v in sd.items() if isinstance(k, str) and k.startswith(p)}
+        if sub:
+            return sub
+    return {}
+
+
+def load_reference_checkpoint(ckpt, encoder=None, unet1d=None, unet3d=None, vqvae=None, strict: bool = True) -> dict:
+    """Distributes a checkpoint written by the reference (``SGDiff.save`` -> ``Sg2ScDiffModel.state_dict(epoch, counter)``,
+    model/SGDiff.py:123-129, model/EchoScene.py:534-544) over the B200 components, the way ``SGDiff.load_networks``
+    (model/SGDiff.py:49-84) distributes it over the reference's modules:
+
+      flat keys obj_embeddings_ec.* ... rel_s_mlp.*      -> encoder  (modules.SceneEncoder)
+      flat keys LayoutDiff.df.model.*                     -> unet1d   (modules.UNet1DModel; DiffusionPoint.model, diffusion_ddpm.py:562)
+      ckpt['shape_df']  keys diffusion_net.*              -> unet3d   (modules.UNet3DModel; DiffusionUNet.diffusion_net, network.py:17)
+      ckpt['vqvae']                                       -> vqvae    (modules.VQVAE)
+      ckpt['epoch'], ckpt['counter']                      -> returned; ckpt['opt'] (AdamW state) is not used when sampling
+
+    ``ckpt`` is a path or the loaded dict.  A ``module.`` prefix left by DistributedDataParallel (echo2shape.py:128-139) is
+    accepted.  Components passed as None are skipped; a component whose slice is absent raises (KeyError) unless it is the
+    shape branch of a layout-only checkpoint and ``strict`` is False (load_networks prints and carries on there, :66-67)."""
+    if isinstance(ckpt, (str, bytes)) or hasattr(ckpt, "__fspath__"):
+        ckpt = torch.load(ckpt, map_location="cpu", weights_only=False)
+    info = {"epoch": ckpt.get("epoch"), "counter": ckpt.get("counter"), "loaded": {}}
+    flat = {k: v for k, v in ckpt.items() if torch.is_tensor(v)}
+    if encoder is not None:
+        encoder.load_reference_state_dict(flat, strict=strict)
+        info["loaded"]["encoder"] = sum(1 for k in flat if k.startswith(encoder.PREFIXES))
+    if unet1d is not None:
+        sub = _strip(flat, ("LayoutDiff.df.model.", "LayoutDiff.df.module.model."))
+        if not sub:
+            raise KeyError("checkpoint has no LayoutDiff.df.model.* entries (not written by Sg2ScDiffModel / Sg2BoxDiffModel?)")
+        unet1d.load_state_dict(sub, strict=strict)
+        info["loaded"]["unet1d"] = len(sub)
+    for name, comp, key, prefixes in (("unet3d", unet3d, "shape_df", ("diffusion_net.", "module.diffusion_net.")),
+                                      ("vqvae", vqvae, "vqvae", ("module.",))):
+        if comp is None:
+            continue
+        if key not in ckpt:
+            if strict:
+                raise KeyError(f"checkpoint has no '{key}' entry (layout-only checkpoint?)")
+            continue
+        sd = ckpt[key]
+        sub = _strip(sd, prefixes) or dict(sd)
+        comp.load_state_dict(sub, strict=strict)
+        info["loaded"][name] = len(sub)
+    return info
+
+
 class Sg2ScDiffModel:
     """Sampling surface of the reference's scene model on the B200 components.
 

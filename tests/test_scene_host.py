@@ -240,3 +240,50 @@ def test_reference_side_binding_shares_parameters():
     h.eval()
     h.obj_embeddings_ec.weight = nn.Parameter(h.obj_embeddings_ec.weight.detach().clone())   # what .cuda() / load does
     assert integrate.scene_encoder_of(h) is not enc
+
+
+def test_load_reference_checkpoint(tmp_path):
+    """A file with the key structure SGDiff.save writes (EchoScene.py:534-544) is distributed over the components the way
+    SGDiff.load_networks does it (SGDiff.py:49-84)."""
+    ecfg, lcfg, vcfg = cases.scene_cfg(), cases.layout_cfg(), cases.vqvae_cfg()
+    esd = arch.make_state_dict(arch.scene_encoder_specs(ecfg), 1)
+    lsd = arch.make_state_dict(arch.unet1d_specs(lcfg), 2)
+    vsd = arch.make_state_dict(arch.vqvae_decode_specs(vcfg), 3)
+    ckpt = dict(esd)
+    ckpt["obj_embeddings_dc.weight"] = torch.zeros(37, 128)                       # unused sub-modules of the model
+    ckpt["pred_embeddings_man_dc.weight"] = torch.zeros(16, 128)
+    ckpt.update({"LayoutDiff.df.model." + k: v for k, v in lsd.items()})
+    ckpt.update({"epoch": 7, "counter": 1234, "opt": {"state": {}, "param_groups": []}})
+    ckpt["vqvae"] = {"module." + k: v for k, v in vsd.items()}                   # saved from a DDP wrapper
+    ckpt["vqvae"]["module.encoder.conv_in.weight"] = torch.zeros(64, 1, 3, 3, 3)
+    ckpt["shape_df"] = {"diffusion_net.out.2.bias": torch.ones(3)}
+    path = tmp_path / "model7.pth"
+    torch.save(ckpt, path)
+
+    class Rec:                                                                   # stands in for the 430 M-parameter UNet3DModel
+        def load_state_dict(self, sd, strict=True):
+            self.sd, self.strict = sd, strict
+
+    enc = modules.SceneEncoder()
+    u1 = modules.UNet1DModel(in_channels=8, model_channels=512, out_channels=8, num_res_blocks=2, attention_resolutions=[4, 2],
+                             channel_mult=[1, 1, 1, 1], num_heads=8, use_spatial_transformer=True, concat_dim=1280,
+                             crossattn_dim=1280, enable_t_emb=True)
+    dd = dict(double_z=False, z_channels=vcfg.z_channels, resolution=vcfg.resolution, in_channels=1, out_ch=vcfg.out_ch, ch=vcfg.ch,
+              ch_mult=list(vcfg.ch_mult), num_res_blocks=vcfg.num_res_blocks, attn_resolutions=[], dropout=0.0)
+    vq, u3 = modules.VQVAE(dd, vcfg.n_embed, vcfg.embed_dim), Rec()
+    info = scene.load_reference_checkpoint(str(path), encoder=enc, unet1d=u1, unet3d=u3, vqvae=vq)
+    assert info["epoch"] == 7 and info["counter"] == 1234
+    assert info["loaded"] == {"encoder": len(esd), "unet1d": len(lsd), "unet3d": 1, "vqvae": len(vsd) + 1}
+    for k, v in esd.items():
+        assert torch.equal(enc.state_dict()[k], v), k
+    for k in ("out.2.weight", "input_blocks.0.0.weight", "box_graph_cov.gconvs.4.net2.3.bias"):
+        assert torch.equal(u1.state_dict()[k], lsd[k]), k
+    assert torch.equal(vq.state_dict()["decoder.conv_out.bias"], vsd["decoder.conv_out.bias"])
+    assert list(u3.sd) == ["out.2.bias"] and u3.strict is True
+    # layout-only checkpoint: strict raises for the shape branch, strict=False carries on as load_networks does
+    lay = {k: v for k, v in ckpt.items() if k not in ("vqvae", "shape_df")}
+    with pytest.raises(KeyError):
+        scene.load_reference_checkpoint(lay, encoder=enc, unet1d=u1, unet3d=u3)
+    assert scene.load_reference_checkpoint(lay, unet1d=u1, unet3d=u3, strict=False)["loaded"] == {"unet1d": len(lsd)}
+    with pytest.raises(KeyError):
+        scene.load_reference_checkpoint({"epoch": 1}, unet1d=u1)
