@@ -197,3 +197,34 @@ def test_sample_surface_end_to_end_vs_oracle(enc):
     got = torch.cat([layout_dict["sizes"], layout_dict["translations"], layout_dict["angles"]], dim=1)
     assert_close(got, boxes, 5e-3, "sample(): layout chain")          # 10 chained steps: tolerance as test_model_gpu's chain test
     assert_close(shape_dict["shapes"], lat, 5e-3, "sample(): shape chain")
+
+
+def test_config1_echolayout_sampleBoxes_vs_oracle(enc):
+    """BASELINE config 1 through the native surface: echolayout, N = 8 nodes / 32 triples, layout only, 10 DDPM steps --
+    Sg2BoxDiffModel.sampleBoxes (EchoLayout.py:291-307) = scene encoders -> DiffusionPoint chain, against the oracle."""
+    m, sd, cfg = enc
+    lcfg = cases.layout_cfg()
+    lsd = arch.make_state_dict(arch.unet1d_specs(lcfg), cases.WEIGHT_SEED_LAYOUT)
+    u1 = modules.UNet1DModel(in_channels=8, model_channels=512, out_channels=8, num_res_blocks=2, attention_resolutions=[4, 2],
+                             channel_mult=[1, 1, 1, 1], num_heads=8, use_spatial_transformer=True, concat_dim=1280,
+                             crossattn_dim=1280, enable_t_emb=True)
+    u1.load_state_dict(lsd, strict=True)
+    steps = cases.LAYOUT_CHAIN_STEPS
+    dp = samplers.DiffusionPoint(u1.to(DEV), time_num=steps)
+    g, objs, text, rel = cases.scene_inputs()                                   # the 8-node / 32-triple scene
+    gen = torch.Generator().manual_seed(41)
+    noises = [torch.randn(8, 8, generator=gen) for _ in range(steps + 1)]
+    it = iter(noises)
+    real = dp.gen_samples_sg
+    dp.gen_samples_sg = lambda shape, device, obj_embed, triples=None, condition=None, clip_denoised=False, **kw: real(
+        shape, device, obj_embed, triples, condition, noise_fn=lambda size, dtype, device: next(it).to(device),
+        clip_denoised=clip_denoised)
+    model = scene.Sg2BoxDiffModel(m, dp)
+    out = model.sample_box_and_shape(*_cuda(objs, g.triples, text, rel))         # SGDiff.sample_box_and_shape, type_ 'echolayout'
+    assert set(out) == {"sizes", "translations", "angles"}
+    with torch.no_grad():
+        e = orc.scene_encode(sd, cfg, objs, g.triples, text, rel)
+        boxes = orc.layout_chain(lsd, lcfg, e["obj_embed"], g.triples, noises[0], noises[1:], steps)
+    got = torch.cat([out["sizes"], out["translations"], out["angles"]], dim=1)
+    assert got.shape == (8, 8)
+    assert_close(got, boxes, 5e-3, "config 1: sampleBoxes 10-step chain")
