@@ -440,6 +440,12 @@ class UNet1DModel(_SpecModule):
         self._check_eval()
         _lib.require_cuda(x_t, obj_embed, triples, noise)
         n = x_t.shape[0]
+        if (tuple(x_t.shape) != (n, self.cfg.in_channels) or tuple(obj_embed.shape) != (n, self.cfg.obj_embed_dim)
+                or tuple(noise.shape) != tuple(x_t.shape)):
+            raise EchoError(f"ddpm_step: x_t / noise must be ({n},{self.cfg.in_channels}) and obj_embed ({n},"
+                            f"{self.cfg.obj_embed_dim}); got {tuple(x_t.shape)}, {tuple(noise.shape)}, {tuple(obj_embed.shape)}")
+        if not 0 <= int(t) < self.time_num:
+            raise EchoError(f"ddpm_step: t = {t} outside the {self.time_num}-step schedule")
         self._ensure(n, triples.shape[0])
         g = _lib.graph_for(triples, n)
         x_t, obj_embed, noise = x_t.float().contiguous(), obj_embed.float().contiguous(), noise.float().contiguous()
@@ -535,6 +541,8 @@ class UNet3DModel(_SpecModule):
         assert x.shape == (n, c.in_channels, c.image_size, c.image_size, c.image_size), tuple(x.shape)
         obj_embed = obj_embed.reshape(obj_embed.shape[0], -1).float().contiguous()
         assert obj_embed.shape[1] == c.context_dim
+        if obj_embed.shape[0] != n:
+            raise EchoError(f"obj_embed has {obj_embed.shape[0]} rows for {n} objects")
         return n, x.float().contiguous(), obj_embed
 
     @torch.no_grad()
@@ -558,7 +566,11 @@ class UNet3DModel(_SpecModule):
         n, x_t, obj_embed = self._prep(x_t, obj_embed, triples)
         self._ensure(n, triples.shape[0])
         g = _lib.graph_for(triples, n)
-        out = torch.empty_like(x_t) if out is None else out
+        if out is None:
+            out = torch.empty_like(x_t)
+        elif (out.shape != x_t.shape or out.dtype != torch.float32 or out.device != x_t.device or not out.is_contiguous()
+              or out.data_ptr() == x_t.data_ptr()):
+            raise EchoError("ddim_step: `out` must be a distinct contiguous float32 tensor shaped and placed like x_t")
         _lib.check(_lib.lib().echo_shape_step(self._handle, g.h, _lib.ptr(x_t), _lib.ptr(obj_embed), int(index),
                                               _lib.ptr(out), _lib.stream_ptr()))
         return out
