@@ -84,6 +84,7 @@ PROTOTYPES = {
     "echo_debug_probe_timeline": (None, [_P]),
     "echo_debug_fold_upsample_weight": (C.c_int, [_P, _I, _I, _I, _P]),
     "echo_debug_tc_plan": (None, [_I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "echo_debug_graph_csr": (C.c_int, [_P, _I, _I, _P, _P, _P]),
     "echo_graph_create": (C.c_int, [C.POINTER(_P), _P, _I, _I, _P]),
     "echo_graph_destroy": (None, [_P]),
     "echo_gather_rows": (C.c_int, [_P, _P, _L, _L, _L, _P, _P]),

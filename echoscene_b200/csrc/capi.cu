@@ -76,6 +76,34 @@ struct Scratch {
 };
 static Scratch g_scratch[4];
 
+// Host side of echo_graph_create: subject / object indices, CSR of the incident (triple, role) items per node and the
+// predicate id range.  Item order per node = the order the reference's scatter_add visits them (graph.py:176-177): subject
+// roles by ascending triple index, then object roles.  Throws for node indices outside [0, N) (graph.py:146-147 would raise).
+static void build_csr(const int64_t* h, int T, int N, std::vector<int>& si, std::vector<int>& oi, std::vector<int>& off,
+                      std::vector<int>& items, int64_t& p_lo, int64_t& p_hi) {
+  si.assign(T, 0);
+  oi.assign(T, 0);
+  off.assign((size_t)N + 1, 0);
+  items.assign((size_t)2 * T, 0);
+  p_lo = 0;
+  p_hi = -1;
+  if (T) p_lo = p_hi = h[1];
+  for (int t = 0; t < T; ++t) {
+    const int64_t a = h[3 * t], b = h[3 * t + 2];
+    ECHO_CHECK(a >= 0 && a < N && b >= 0 && b < N, "graph_create: triple %d has node index out of range [0, %d)", t, N);
+    si[t] = (int)a;
+    oi[t] = (int)b;
+    p_lo = std::min(p_lo, h[3 * t + 1]);
+    p_hi = std::max(p_hi, h[3 * t + 1]);
+    off[a + 1]++;
+    off[b + 1]++;
+  }
+  for (int n = 0; n < N; ++n) off[n + 1] += off[n];
+  std::vector<int> fill(off.begin(), off.end() - 1);
+  for (int t = 0; t < T; ++t) items[fill[si[t]]++] = t * 2 + 0;
+  for (int t = 0; t < T; ++t) items[fill[oi[t]]++] = t * 2 + 1;
+}
+
 }  // namespace echo
 
 using namespace echo;
@@ -106,6 +134,19 @@ void echo_debug_probe_timeline(void* buf_dev) { echo::tc_probe_timeline((unsigne
 int64_t echo_launch_count(void) { return g_launches; }
 void echo_launch_count_reset(void) { g_launches = 0; }
 
+int echo_debug_graph_csr(const int64_t* triples_host, int32_t T, int32_t N, int32_t* node_off_out, int32_t* node_items_out,
+                         int64_t* pred_range_out) {
+  return guard([&] {
+    ECHO_CHECK(N >= 0 && T >= 0 && (triples_host || T == 0) && node_off_out && (node_items_out || T == 0), "debug_graph_csr: bad arguments");
+    std::vector<int> si, oi, off, items;
+    int64_t lo = 0, hi = -1;
+    build_csr(triples_host, T, N, si, oi, off, items, lo, hi);
+    for (int n = 0; n <= N; ++n) node_off_out[n] = off[n];
+    for (size_t i = 0; i < items.size(); ++i) node_items_out[i] = items[i];
+    if (pred_range_out) { pred_range_out[0] = lo; pred_range_out[1] = hi; }
+  });
+}
+
 int echo_graph_create(echo_graph_t** out, const int64_t* triples_dev, int32_t T, int32_t N, void* stream) {
   return guard([&] {
     ECHO_CHECK(out && N >= 0 && T >= 0 && (triples_dev || T == 0), "graph_create: bad arguments");
@@ -115,25 +156,9 @@ int echo_graph_create(echo_graph_t** out, const int64_t* triples_dev, int32_t T,
       ECHO_CUDA(cudaMemcpyAsync(h.data(), triples_dev, sizeof(int64_t) * 3 * T, cudaMemcpyDeviceToHost, s));
       ECHO_CUDA(cudaStreamSynchronize(s));
     }
-    std::vector<int> si(T), oi(T), off(N + 1, 0), items((size_t)2 * T);
+    std::vector<int> si, oi, off, items;
     int64_t p_lo = 0, p_hi = -1;
-    if (T) p_lo = p_hi = h[1];
-    for (int t = 0; t < T; ++t) {
-      const int64_t a = h[3 * t], b = h[3 * t + 2];
-      // the reference would raise an index error (graph.py:146-147)
-      ECHO_CHECK(a >= 0 && a < N && b >= 0 && b < N, "graph_create: triple %d has node index out of range [0, %d)", t, N);
-      si[t] = (int)a;
-      oi[t] = (int)b;
-      p_lo = std::min(p_lo, h[3 * t + 1]);
-      p_hi = std::max(p_hi, h[3 * t + 1]);
-      off[a + 1]++;
-      off[b + 1]++;
-    }
-    for (int n = 0; n < N; ++n) off[n + 1] += off[n];
-    std::vector<int> fill(off.begin(), off.end() - 1);
-    // subject roles first (ascending t), then object roles: the order scatter_add visits them (graph.py:176-177)
-    for (int t = 0; t < T; ++t) items[fill[si[t]]++] = t * 2 + 0;
-    for (int t = 0; t < T; ++t) items[fill[oi[t]]++] = t * 2 + 1;
+    build_csr(h.data(), T, N, si, oi, off, items, p_lo, p_hi);
     static std::atomic<uint64_t> next_id{1};
     echo_graph* g = new echo_graph();
     g->id = next_id++;

@@ -139,6 +139,11 @@ ECHO_API void echo_debug_tc_plan(int32_t n, int32_t d, int32_t h, int32_t w, int
 ECHO_API int echo_debug_fold_upsample_weight(const float* w_host, int32_t cout, int32_t cin, int32_t up_depth, float* out_host);
 
 /* ---- graph: edges = stack([s, o]) of `triples` (T,3) int64 [s,p,o] — denoise_net.py:759-761, graph.py:142-143 */
+/* host-only: the CSR echo_graph_create builds from host triples (T,3) [s,p,o] -- node_off_out (N+1), node_items_out (2T)
+ * with item = 2*t + role (0 subject, 1 object) in the order the reference's scatter_add visits them (graph.py:176-177),
+ * pred_range_out = {min p, max p} ({0,-1} when T == 0).  For CPU tests of the index work. */
+ECHO_API int echo_debug_graph_csr(const int64_t* triples_host, int32_t n_triples, int32_t n_nodes, int32_t* node_off_out,
+                                  int32_t* node_items_out, int64_t* pred_range_out);
 ECHO_API int echo_graph_create(echo_graph_t** out, const int64_t* triples_dev, int32_t n_triples, int32_t n_nodes, void* stream);
 ECHO_API void echo_graph_destroy(echo_graph_t* g);
 
