@@ -84,6 +84,8 @@ PROTOTYPES = {
     "echo_debug_probe_timeline": (None, [_P]),
     "echo_debug_fold_upsample_weight": (C.c_int, [_P, _I, _I, _I, _P]),
     "echo_debug_tc_plan": (None, [_I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "echo_debug_ddpm_tables": (C.c_int, [_I, C.c_float, C.c_float, _P]),
+    "echo_debug_ddim_schedule": (C.c_int, [_I, _I, C.c_float, C.c_float, _I, _P, _P, _P]),
     "echo_debug_graph_csr": (C.c_int, [_P, _I, _I, _P, _P, _P]),
     "echo_graph_create": (C.c_int, [C.POINTER(_P), _P, _I, _I, _P]),
     "echo_graph_destroy": (None, [_P]),

@@ -33,6 +33,8 @@ void vqvae_decode(echo_vqvae*, const float*, int, float*, int*, cudaStream_t);
 echo_vqvae* vqvae_encoder_create(const echo_vqvae_desc_t*, const echo_weight_t*, int);
 void vqvae_encode(echo_vqvae*, const float*, int, float*, cudaStream_t);
 int shape_context_dim(const echo_shape*);
+void ddpm_tables(int, float, float, std::vector<float>&);
+void ddim_schedule(int, int, float, float, std::vector<float>&, std::vector<int32_t>&);
 echo_scene* scene_create(const echo_scene_desc_t*, const echo_weight_t*, int);
 void scene_destroy(echo_scene*);
 void scene_init_encoder(echo_scene*, const echo_graph*, const int64_t*, const float*, const float*, float*, float*, float*, cudaStream_t);
@@ -133,6 +135,28 @@ void echo_debug_tc_plan(int32_t n, int32_t d, int32_t h, int32_t w, int32_t cin,
 void echo_debug_probe_timeline(void* buf_dev) { echo::tc_probe_timeline((unsigned long long*)buf_dev); }
 int64_t echo_launch_count(void) { return g_launches; }
 void echo_launch_count_reset(void) { g_launches = 0; }
+
+int echo_debug_ddpm_tables(int32_t time_num, float beta_start, float beta_end, float* host_out) {
+  return guard([&] {
+    ECHO_CHECK(host_out, "debug_ddpm_tables: null output");
+    std::vector<float> tab;
+    ddpm_tables(time_num, beta_start, beta_end, tab);
+    memcpy(host_out, tab.data(), tab.size() * sizeof(float));
+  });
+}
+int echo_debug_ddim_schedule(int32_t timesteps, int32_t ddim_steps, float linear_start, float linear_end, int32_t capacity,
+                             float* host_coef_out, int32_t* host_timesteps_out, int32_t* n_out) {
+  return guard([&] {
+    ECHO_CHECK(host_coef_out && host_timesteps_out && n_out, "debug_ddim_schedule: null output");
+    std::vector<float> coef;
+    std::vector<int32_t> ts;
+    ddim_schedule(timesteps, ddim_steps, linear_start, linear_end, coef, ts);
+    ECHO_CHECK((int)ts.size() <= capacity, "debug_ddim_schedule: %d steps exceed the caller's capacity %d", (int)ts.size(), capacity);
+    memcpy(host_coef_out, coef.data(), coef.size() * sizeof(float));
+    memcpy(host_timesteps_out, ts.data(), ts.size() * sizeof(int32_t));
+    *n_out = (int32_t)ts.size();
+  });
+}
 
 int echo_debug_graph_csr(const int64_t* triples_host, int32_t T, int32_t N, int32_t* node_off_out, int32_t* node_items_out,
                          int64_t* pred_range_out) {

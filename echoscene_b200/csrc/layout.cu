@@ -215,12 +215,13 @@ struct echo_layout {
 
 namespace echo {
 
-static void make_ddpm_tables(echo_layout* h) {
-  // get_betas('linear') = np.linspace(b0, b1, T) float64 (diffusion_ddpm.py:38-40); tables as fp32 torch ops (:133-162)
-  const int T = h->d.time_num;
+// get_betas('linear') = np.linspace(b0, b1, T) float64 (diffusion_ddpm.py:38-40); tables as fp32 torch ops (:133-162).
+// tab = 5 x T: sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, posterior_mean_coef1, posterior_mean_coef2,
+// posterior_log_variance_clipped.  Host-only (also exported as echo_debug_ddpm_tables for CPU tests).
+void ddpm_tables(int T, float beta_start, float beta_end, std::vector<float>& tab) {
   ECHO_CHECK(T >= 1, "layout: time_num must be >= 1");
   std::vector<double> betas(T);
-  const double b0 = (double)h->d.beta_start, b1 = (double)h->d.beta_end;
+  const double b0 = (double)beta_start, b1 = (double)beta_end;
   const double step = T > 1 ? (b1 - b0) / (double)(T - 1) : 0.0;
   for (int i = 0; i < T; ++i) betas[i] = (double)i * step + b0;
   if (T > 1) betas[T - 1] = b1;
@@ -233,16 +234,20 @@ static void make_ddpm_tables(echo_layout* h) {
     a32[i] = (float)(1.0 - betas[i]);
   }
   for (int i = 0; i < T; ++i) acp[i] = i == 0 ? 1.0f : ac[i - 1];
-  h->h_tab.assign((size_t)5 * T, 0.f);
+  tab.assign((size_t)5 * T, 0.f);
   for (int i = 0; i < T; ++i) {
     const float one_m = 1.0f - ac[i];
-    h->h_tab[0 * T + i] = sqrtf(1.0f / ac[i]);
-    h->h_tab[1 * T + i] = sqrtf(1.0f / ac[i] - 1.0f);
-    h->h_tab[2 * T + i] = b32[i] * sqrtf(acp[i]) / one_m;
-    h->h_tab[3 * T + i] = (1.0f - acp[i]) * sqrtf(a32[i]) / one_m;
+    tab[0 * T + i] = sqrtf(1.0f / ac[i]);
+    tab[1 * T + i] = sqrtf(1.0f / ac[i] - 1.0f);
+    tab[2 * T + i] = b32[i] * sqrtf(acp[i]) / one_m;
+    tab[3 * T + i] = (1.0f - acp[i]) * sqrtf(a32[i]) / one_m;
     const float pv = b32[i] * (1.0f - acp[i]) / one_m;
-    h->h_tab[4 * T + i] = logf(fmaxf(pv, 1e-20f));
+    tab[4 * T + i] = logf(fmaxf(pv, 1e-20f));
   }
+}
+
+static void make_ddpm_tables(echo_layout* h) {
+  ddpm_tables(h->d.time_num, h->d.beta_start, h->d.beta_end, h->h_tab);
   h->d_tab = h->pool.upload(h->h_tab);
 }
 

@@ -440,14 +440,15 @@ struct echo_shape {
 
 namespace echo {
 
-static void make_ddim_schedule(echo_shape* h) {
-  // make_beta_schedule('linear') = linspace(sqrt(ls), sqrt(le), T)^2 in float64 (ldm_diffusion_util.py:44-47);
-  // alphas_cumprod registered as fp32 (echo2shape.py:185-190); DDIM: c = T // S, timesteps range(0, T, c) + 1
-  // (ldm_diffusion_util.py:70-79); a_prev[0] = ac[0] (:88); sigma = 0 for eta = 0.
-  const int T = h->d.timesteps, S = h->d.ddim_steps;
+// make_beta_schedule('linear') = linspace(sqrt(ls), sqrt(le), T)^2 in float64 (ldm_diffusion_util.py:44-47);
+// alphas_cumprod registered as fp32 (echo2shape.py:185-190); DDIM: c = T // S, timesteps range(0, T, c) + 1
+// (ldm_diffusion_util.py:70-79); a_prev[0] = ac[0] (:88); sigma = 0 for eta = 0.
+// coef = n x 4 [sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev)], ts = the n DDIM timesteps.  Host-only (also exported
+// as echo_debug_ddim_schedule for CPU tests).
+void ddim_schedule(int T, int S, float linear_start, float linear_end, std::vector<float>& coef, std::vector<int32_t>& ts) {
   ECHO_CHECK(T > 0 && S > 0 && S <= T, "shape: bad schedule T=%d S=%d", T, S);
   std::vector<float> ac(T);
-  const double a = sqrt((double)h->d.linear_start), b = sqrt((double)h->d.linear_end);
+  const double a = sqrt((double)linear_start), b = sqrt((double)linear_end);
   double cp = 1.0;
   for (int i = 0; i < T; ++i) {
     // torch.linspace(a, b, T, float64): start + i*step for the first half, end - (T-1-i)*step for the second
@@ -458,22 +459,24 @@ static void make_ddim_schedule(echo_shape* h) {
     ac[i] = (float)cp;
   }
   const int c = T / S;
-  h->h_ts.clear();
-  for (int t = 0; t < T; t += c) h->h_ts.push_back(t + 1);
-  const int n = (int)h->h_ts.size();
-  h->h_coef.assign((size_t)n * 4, 0.f);
+  ts.clear();
+  for (int t = 0; t < T; t += c) ts.push_back(t + 1);
+  const int n = (int)ts.size();
+  coef.assign((size_t)n * 4, 0.f);
   for (int i = 0; i < n; ++i) {
-    ECHO_CHECK(h->h_ts[i] < T, "shape: DDIM timestep %d out of range for %d-step schedule (S must divide T)", h->h_ts[i], T);
-    const float a_t = ac[h->h_ts[i]];
-    const float a_prev = i == 0 ? ac[0] : ac[h->h_ts[i - 1]];
+    ECHO_CHECK(ts[i] < T, "shape: DDIM timestep %d out of range for %d-step schedule (S must divide T)", ts[i], T);
+    const float a_t = ac[ts[i]];
+    const float a_prev = i == 0 ? ac[0] : ac[ts[i - 1]];
     // samplers/ddim.py:246-249,252-261: torch.full(fp32) of numpy values, then fp32 tensor arithmetic
-    h->h_coef[4 * i + 0] = sqrtf(a_t);
-    h->h_coef[4 * i + 1] = (float)sqrt(1.0 - (double)a_t);   // np.sqrt(1 - alphas) on fp32 numpy -> fp32
-    h->h_coef[4 * i + 2] = sqrtf(a_prev);
-    h->h_coef[4 * i + 3] = sqrtf(1.0f - a_prev - 0.0f);
+    coef[4 * i + 0] = sqrtf(a_t);
+    coef[4 * i + 1] = sqrtf(1.0f - a_t);   // np.sqrt(1. - ddim_alphas): ddim_alphas is float32 numpy, 1. - x stays float32
+    coef[4 * i + 2] = sqrtf(a_prev);
+    coef[4 * i + 3] = sqrtf(1.0f - a_prev - 0.0f);
   }
-  // np.sqrt(1. - ddim_alphas): ddim_alphas is float32 numpy, 1. - x stays float32
-  for (int i = 0; i < n; ++i) h->h_coef[4 * i + 1] = sqrtf(1.0f - ac[h->h_ts[i]]);
+}
+
+static void make_ddim_schedule(echo_shape* h) {
+  ddim_schedule(h->d.timesteps, h->d.ddim_steps, h->d.linear_start, h->d.linear_end, h->h_coef, h->h_ts);
   h->d_coef = h->pool.upload(h->h_coef);
 }
 

@@ -139,6 +139,12 @@ ECHO_API void echo_debug_tc_plan(int32_t n, int32_t d, int32_t h, int32_t w, int
 ECHO_API int echo_debug_fold_upsample_weight(const float* w_host, int32_t cout, int32_t cin, int32_t up_depth, float* out_host);
 
 /* ---- graph: edges = stack([s, o]) of `triples` (T,3) int64 [s,p,o] — denoise_net.py:759-761, graph.py:142-143 */
+/* host-only: the sampler tables exactly as echo_layout_create / echo_shape_create compute them (same layouts as
+ * echo_layout_schedule / echo_shape_schedule below), for CPU tests against the reference's buffers.
+ * ddpm: host_out 5 x time_num f32.  ddim: host_coef_out n x 4 f32, host_timesteps_out n i32, *n_out = n <= capacity. */
+ECHO_API int echo_debug_ddpm_tables(int32_t time_num, float beta_start, float beta_end, float* host_out);
+ECHO_API int echo_debug_ddim_schedule(int32_t timesteps, int32_t ddim_steps, float linear_start, float linear_end, int32_t capacity,
+                                      float* host_coef_out, int32_t* host_timesteps_out, int32_t* n_out);
 /* host-only: the CSR echo_graph_create builds from host triples (T,3) [s,p,o] -- node_off_out (N+1), node_items_out (2T)
  * with item = 2*t + role (0 subject, 1 object) in the order the reference's scatter_add visits them (graph.py:176-177),
  * pred_range_out = {min p, max p} ({0,-1} when T == 0).  For CPU tests of the index work. */
