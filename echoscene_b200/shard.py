@@ -7,6 +7,11 @@ codes — the echo exchange, 256 B per object over NVLink, (3) runs the cheap GC
 UNet trunk + DDIM update on its own objects.  No other collective touches the data path; the final latents are gathered
 once after the chain.
 
+When a batch holds at least as many scenes as there are GPUs (BASELINE config 4: 64 scenes over 8 GPUs) the shard is by
+SCENE instead: the batched graph is block-diagonal per scene (collate_fn offsets, dataset/threedfront_dataset.py:698-701),
+so a rank that owns whole scenes needs no per-step collective at all -- `partition_scenes` / `scene_subgraph` cut the batch,
+`gather_latents` joins the results once after the chain.
+
 The host logic here is backend-agnostic (NCCL on the GPU box, gloo in the CPU tests): the compute callbacks are passed in.
 """
 from __future__ import annotations
@@ -57,3 +62,45 @@ def gather_latents(x_local: torch.Tensor, counts: Sequence[int], group=None) -> 
     """Final all-gather of the (n_local, 3, 16, 16, 16) latents before VQ-VAE decode (48 KB per object)."""
     flat = all_gather_rows(x_local.reshape(x_local.shape[0], -1), counts, group)
     return flat.reshape(-1, *x_local.shape[1:])
+
+
+def partition_scenes(obj_to_scene: torch.Tensor, world: int) -> List[Tuple[int, int, int, int]]:
+    """Contiguous scene ranges per rank for a collated batch (`obj_to_scene` (N,) int64, non-decreasing as collate_fn builds
+    it).  Scenes are split so that object counts are as even as contiguous ranges allow (greedy on the running total).
+    -> per rank (scene_begin, scene_end, node_begin, node_end); ranks beyond the number of scenes get empty ranges."""
+    o2s = obj_to_scene.detach().cpu().to(torch.int64)
+    n = int(o2s.numel())
+    if n and bool((o2s[1:] < o2s[:-1]).any()):
+        raise ValueError("obj_to_scene must be non-decreasing (nodes of a scene are contiguous in a collated batch)")
+    n_scenes = int(o2s[-1]) + 1 if n else 0
+    sizes = torch.bincount(o2s, minlength=n_scenes).tolist() if n else []
+    first = [0]
+    for c in sizes:
+        first.append(first[-1] + c)
+    out, sb = [], 0
+    for r in range(world):
+        # close this rank's range at the scene boundary nearest to its share of the objects, leaving >= 1 scene per later rank
+        target = n * (r + 1) / world
+        se = sb
+        last_allowed = n_scenes - min(world - 1 - r, max(n_scenes - sb - 1, 0)) if r < world - 1 else n_scenes
+        while se < last_allowed and (se == sb or abs(first[se + 1] - target) <= abs(first[se] - target)):
+            se += 1
+        if r == world - 1:
+            se = n_scenes
+        out.append((sb, se, first[sb], first[se]))
+        sb = se
+    return out
+
+
+def scene_subgraph(triples: torch.Tensor, node_begin: int, node_end: int) -> torch.Tensor:
+    """Triples of the scenes whose nodes are [node_begin, node_end) of the batched graph, re-based to local node indices.
+    Raises if a triple crosses the boundary (the batch would not be block-diagonal)."""
+    s, o = triples[:, 0], triples[:, 2]
+    s_in = (s >= node_begin) & (s < node_end)
+    o_in = (o >= node_begin) & (o < node_end)
+    if bool((s_in != o_in).any()):
+        raise ValueError("a triple connects nodes of different ranks' scenes: the batched graph is not block-diagonal")
+    local = triples[s_in].clone()
+    local[:, 0] -= node_begin
+    local[:, 2] -= node_begin
+    return local
