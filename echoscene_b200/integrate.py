@@ -44,12 +44,15 @@ def scene_encoder_of(model):
     cached = model.__dict__.get("_echo_scene_encoder")
     if cached is not None and cached[0] == key:
         return cached[1]
+    if "rel_s_mlp.3.weight" in sd and tuple(sd["rel_s_mlp.3.weight"].shape) != (1280, 960):
+        from ._lib import EchoError
+        raise EchoError("rel_s_mlp of the 'concat' conditioning variant ([640, 1280, 4096], EchoScene.py:98-99) is outside the hot path")
     enc = modules.SceneEncoder(num_objs=model.obj_embeddings_ec.weight.shape[0] - 1,
                                num_preds=model.pred_embeddings_ec.weight.shape[0], embedding_dim=model.embedding_dim,
                                gconv_num_layers=model.gconv_net_ec.num_layers,
-                               residual=any(k.endswith("linear_projection.weight") for k in sd), use_clip=bool(model.clip))
-    has_rel_s = any(k.startswith("rel_s_mlp.") for k in sd)          # the layout-only model has none
-    enc.load_state_dict(sd, strict=has_rel_s, assign=True)
+                               residual=any(k.endswith("linear_projection.weight") for k in sd), use_clip=bool(model.clip),
+                               with_rel_s=any(k.startswith("rel_s_mlp.") for k in sd))   # the layout-only model has none
+    enc.load_state_dict(sd, strict=True, assign=True)
     enc.eval()
     object.__setattr__(model, "_echo_scene_encoder", (key, enc))     # not a registered sub-module
     return enc

@@ -202,7 +202,8 @@ class SceneEncoder(_SpecModule):
 
     def __init__(self, num_objs: int = 36, num_preds: int = 16, embedding_dim: int = 64, gconv_num_layers: int = 5,
                  residual: bool = True, use_clip: bool = True, gconv_pooling: str = "avg",
-                 mlp_normalization: str = "batch", rel_s_hidden: int = 960, context_dim: int = 1280):
+                 mlp_normalization: str = "batch", rel_s_hidden: int = 960, context_dim: int = 1280,
+                 with_rel_s: bool = True):
         super().__init__()
         if gconv_pooling != "avg":
             raise EchoError(f"gconv_pooling='{gconv_pooling}' is not on the hot path (SGDiff.py:21-22 passes 'avg')")
@@ -214,7 +215,11 @@ class SceneEncoder(_SpecModule):
         self.embedding_dim = embedding_dim
         self.clip = use_clip
         self.out_dim_ini_encoder = self.out_dim_manipulator = self.cfg.feat_dim
-        self._build_from_specs(arch.scene_encoder_specs(self.cfg))
+        specs = arch.scene_encoder_specs(self.cfg)
+        self.with_rel_s = bool(with_rel_s)
+        if not self.with_rel_s:   # the layout-only model (model/EchoLayout.py) has no rel_s_mlp
+            specs = arch.OrderedDict((k, v) for k, v in specs.items() if not k.startswith("rel_s_mlp."))
+        self._build_from_specs(specs)
         self.eval()
 
     @classmethod
@@ -307,6 +312,8 @@ class SceneEncoder(_SpecModule):
     def rel_s(self, x):
         """self.rel_s_mlp(x): (M, feat) -> (M, context_dim)."""
         self._check_eval()
+        if not self.with_rel_s:
+            raise EchoError("this SceneEncoder was built without rel_s_mlp (layout-only model)")
         _lib.require_cuda(x)
         if x.dim() != 2 or x.shape[1] != self.cfg.feat_dim:
             raise EchoError(f"rel_s input must be (M,{self.cfg.feat_dim}), got {tuple(x.shape)}")
@@ -330,6 +337,8 @@ class SceneEncoder(_SpecModule):
                 raise EchoError(f"change must be ({n},{c.gconv_dim}), got {tuple(change.shape)}")
             change = change.float().contiguous()
         out = {"obj_embed": torch.empty(n, c.feat_dim, device=dev), "latent": torch.empty(n, c.feat_dim, device=dev)}
+        if shape_cond and not self.with_rel_s:
+            raise EchoError("shape_cond=True needs rel_s_mlp; this SceneEncoder was built without it (layout-only model)")
         if shape_cond:
             out["uc_s"] = torch.empty(n, 1, c.context_dim, device=dev)
             out["c_s"] = torch.empty(n, 1, c.context_dim, device=dev)

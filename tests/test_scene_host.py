@@ -240,6 +240,12 @@ def test_reference_side_binding_shares_parameters():
     h.eval()
     h.obj_embeddings_ec.weight = nn.Parameter(h.obj_embeddings_ec.weight.detach().clone())   # what .cuda() / load does
     assert integrate.scene_encoder_of(h) is not enc
+    # the layout-only model (model/EchoLayout.py) owns no rel_s_mlp: the encoder is built without it and says so
+    del h.rel_s_mlp
+    box = integrate.scene_encoder_of(h)
+    assert not box.with_rel_s and not any(k.startswith("rel_s_mlp.") for k in box.state_dict())
+    with pytest.raises(_lib.EchoError, match="rel_s_mlp"):
+        box.rel_s(torch.zeros(2, 640))
 
 
 def test_load_reference_checkpoint(tmp_path):
