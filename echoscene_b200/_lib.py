@@ -58,7 +58,8 @@ class ShapeDesc(C.Structure):
 class SceneDesc(C.Structure):
     _fields_ = [("gconv_dim", C.c_int32), ("add_dim", C.c_int32), ("num_objs", C.c_int32), ("num_preds", C.c_int32),
                 ("num_layers", C.c_int32), ("rel_s_hidden", C.c_int32), ("context_dim", C.c_int32),
-                ("max_nodes", C.c_int32), ("max_triples", C.c_int32), ("bn_eps", C.c_float)]
+                ("max_nodes", C.c_int32), ("max_triples", C.c_int32), ("bn_eps", C.c_float),
+                ("manipulate_pred_dc", C.c_int32)]
 
 
 class VqvaeDesc(C.Structure):

@@ -326,6 +326,9 @@ class SceneEncoderConfig:
     residual: bool = True
     rel_s_hidden: int = 960
     context_dim: int = 1280
+    # the layout-only model embeds the predicates of `manipulate` with pred_embeddings_man_dc (EchoLayout.py:154);
+    # Sg2ScDiffModel uses pred_embeddings_ec there too (EchoScene.py:187)
+    man_dc_preds: bool = False
 
     @property
     def feat_dim(self) -> int:    # out_dim_ini_encoder == out_dim_manipulator
@@ -345,6 +348,8 @@ def scene_encoder_specs(cfg: SceneEncoderConfig) -> Specs:
     sp: Dict[str, ParamSpec] = OrderedDict()
     sp["obj_embeddings_ec.weight"] = ParamSpec((cfg.num_objs + 1, 2 * cfg.gconv_dim), "normal")
     sp["pred_embeddings_ec.weight"] = ParamSpec((cfg.num_preds, 2 * cfg.gconv_dim), "normal")
+    if cfg.man_dc_preds:
+        sp["pred_embeddings_man_dc.weight"] = ParamSpec((cfg.num_preds, 2 * cfg.gconv_dim), "normal")
     sp.update(gcn_specs(cfg.gcn_ec(), "gconv_net_ec."))
     sp.update(gcn_specs(cfg.gcn_manipulation(), "gconv_net_manipulation."))
     _lin(sp, "rel_s_mlp.0", cfg.feat_dim, cfg.rel_s_hidden, w_init="kaiming_normal")

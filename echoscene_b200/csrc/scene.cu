@@ -23,10 +23,12 @@ struct echo_scene {
   echo::Gcn ec, mani;
   const float* obj_tab = nullptr;
   const float* pred_tab = nullptr;
+  const float* pred_tab_man = nullptr;   // pred_embeddings_man_dc when desc.manipulate_pred_dc (layout-only model), else null
   bool has_rel_s = false;
   echo::Mat rel0, rel3;          // rel_s_mlp.0 (+ BatchNorm rel_s_mlp.1 folded), rel_s_mlp.3
   // workspace (max_nodes / max_triples rows)
   float *obj_embed = nullptr, *pred_embed = nullptr, *latent_obj = nullptr, *mani_in = nullptr, *latent = nullptr, *rel_h = nullptr;
+  float* pred_embed_man = nullptr;       // predicate embeddings of the manipulate stage when they come from pred_tab_man
 };
 
 namespace echo {
@@ -79,6 +81,7 @@ echo_scene* scene_create(const echo_scene_desc_t* desc, const echo_weight_t* wei
     };
     h->obj_tab = table("obj_embeddings_ec.weight", d.num_objs);
     h->pred_tab = table("pred_embeddings_ec.weight", d.num_preds);
+    if (d.manipulate_pred_dc) h->pred_tab_man = table("pred_embeddings_man_dc.weight", d.num_preds);   // EchoLayout.py:154
     echo_gcn_desc_t g;
     g.input_dim_obj = h->feat; g.input_dim_pred = h->feat; g.num_layers = d.num_layers; g.hidden_dim = 4 * h->gd;
     g.output_dim = h->feat; g.max_nodes = h->d.max_nodes; g.max_triples = h->d.max_triples; g.bn_eps = eps;
@@ -99,6 +102,7 @@ echo_scene* scene_create(const echo_scene_desc_t* desc, const echo_weight_t* wei
     h->latent_obj = h->pool.alloc_n<float>(N * h->feat);
     h->mani_in = h->pool.alloc_n<float>(N * h->din_mani);
     h->latent = h->pool.alloc_n<float>(N * h->feat);
+    if (h->pred_tab_man) h->pred_embed_man = h->pool.alloc_n<float>(T * h->feat);
     ECHO_CUDA(cudaStreamSynchronize(s));
   } catch (...) {
     h->pool.destroy();
@@ -138,7 +142,7 @@ void scene_manipulate(echo_scene* h, const echo_graph* g, const float* latent_f,
   float* pe = pred_embed_out ? pred_embed_out : h->pred_embed;
   float* lt = latent_out ? latent_out : h->latent;
   embed_rows(h, h->obj_tab, objs, 1, 0, text_feat, N, oe, s);
-  embed_rows(h, h->pred_tab, g->triples, 3, 1, rel_feat, T, pe, s);
+  embed_rows(h, h->pred_tab_man ? h->pred_tab_man : h->pred_tab, g->triples, 3, 1, rel_feat, T, pe, s);
   const int lf = h->feat + h->gd;
   copy_cols(latent_f, lf, N, lf, h->mani_in, h->din_mani, s);                  // torch.cat([latent_f, obj_embed], dim=1), :192
   copy_cols(oe, h->feat, N, h->feat, h->mani_in + lf, h->din_mani, s);
@@ -170,7 +174,8 @@ void scene_encode(echo_scene* h, const echo_graph* g, const int64_t* objs, const
   ECHO_CHECK(objs && (h->add == 0 || (text_feat && (rel_feat || T == 0))), "scene_encode: null input");
   float* oe = obj_embed_out ? obj_embed_out : h->obj_embed;
   float* lt = latent_out ? latent_out : h->latent;
-  // dec and enc graph are the same scene here, so the embeddings of init_encoder and manipulate coincide
+  // dec and enc graph are the same scene here, so the embeddings of init_encoder and manipulate coincide (except the
+  // predicate table of the layout-only model, below)
   embed_rows(h, h->obj_tab, objs, 1, 0, text_feat, N, oe, s);
   embed_rows(h, h->pred_tab, g->triples, 3, 1, rel_feat, T, h->pred_embed, s);
   h->ec.forward(g, oe, h->pred_embed, h->latent_obj, nullptr, s);
@@ -178,7 +183,12 @@ void scene_encode(echo_scene* h, const echo_graph* g, const int64_t* objs, const
   else ECHO_CUDA(cudaMemsetAsync(h->mani_in, 0, sizeof(float) * (size_t)N * h->din_mani, s));   // the zero change flag, :393-397
   copy_cols(h->latent_obj, h->feat, N, h->feat, h->mani_in, h->din_mani, s);
   copy_cols(oe, h->feat, N, h->feat, h->mani_in + h->feat + h->gd, h->din_mani, s);
-  h->mani.forward(g, h->mani_in, h->pred_embed, lt, nullptr, s);
+  const float* pe_man = h->pred_embed;
+  if (h->pred_tab_man) {   // the layout-only model embeds the predicates of this stage with its own table
+    embed_rows(h, h->pred_tab_man, g->triples, 3, 1, rel_feat, T, h->pred_embed_man, s);
+    pe_man = h->pred_embed_man;
+  }
+  h->mani.forward(g, h->mani_in, pe_man, lt, nullptr, s);
   if (uc_s_out) scene_rel_s(h, oe, N, uc_s_out, s);
   if (c_s_out) scene_rel_s(h, lt, N, c_s_out, s);
 }

@@ -39,7 +39,10 @@ def scene_encoder_of(model):
     import torch.nn as nn
     from . import modules
 
-    sd = {k: v for k, v in nn.Module.state_dict(model, keep_vars=True).items() if k.startswith(modules.SceneEncoder.PREFIXES)}
+    # the layout-only model embeds the predicates of `manipulate` with its own table (EchoLayout.py:154)
+    man_dc = bool(getattr(type(model), "_echo_man_dc_preds", False))
+    pre = modules.SceneEncoder.PREFIXES + (("pred_embeddings_man_dc.",) if man_dc else ())
+    sd = {k: v for k, v in nn.Module.state_dict(model, keep_vars=True).items() if k.startswith(pre)}
     key = tuple(v.data_ptr() for v in sd.values())
     cached = model.__dict__.get("_echo_scene_encoder")
     if cached is not None and cached[0] == key:
@@ -51,7 +54,8 @@ def scene_encoder_of(model):
                                num_preds=model.pred_embeddings_ec.weight.shape[0], embedding_dim=model.embedding_dim,
                                gconv_num_layers=model.gconv_net_ec.num_layers,
                                residual=any(k.endswith("linear_projection.weight") for k in sd), use_clip=bool(model.clip),
-                               with_rel_s=any(k.startswith("rel_s_mlp.") for k in sd))   # the layout-only model has none
+                               with_rel_s=any(k.startswith("rel_s_mlp.") for k in sd),   # the layout-only model has none
+                               man_dc_preds=man_dc)
     enc.load_state_dict(sd, strict=True, assign=True)
     enc.eval()
     object.__setattr__(model, "_echo_scene_encoder", (key, enc))     # not a registered sub-module
@@ -132,5 +136,6 @@ def patch_reference(precision: str = "fp32", ddim_steps: Optional[int] = None, v
                 done[modname + "." + cls] = f"not patched: {e!r}"
                 continue
             c.init_encoder, c.manipulate = _init_encoder, _manipulate
+            c._echo_man_dc_preds = cls == "Sg2BoxDiffModel"
             done[modname + "." + cls] = ["init_encoder", "manipulate"]
     return done

@@ -190,6 +190,9 @@ class SceneEncoder(_SpecModule):
     ``rel_s_mlp`` -- same state_dict keys, so the matching slice of a reference checkpoint loads with strict=True
     (``load_reference_state_dict`` drops the keys of other sub-modules).
 
+    (``man_dc_preds=True``, ``with_rel_s=False``: the layout-only ``Sg2BoxDiffModel``, model/EchoLayout.py, whose ``manipulate``
+    embeds predicates with ``pred_embeddings_man_dc`` and which has no ``rel_s_mlp``.)
+
       init_encoder(objs, triples, text_feat, rel_feat)            EchoScene.py:143-157
       manipulate(latent_f, objs, triples, text_feat, rel_feat)    EchoScene.py:181-195
       rel_s(x)   [the reference's self.rel_s_mlp(x)]              EchoScene.py:97-100
@@ -199,11 +202,13 @@ class SceneEncoder(_SpecModule):
     does not exist here."""
 
     PREFIXES = ("obj_embeddings_ec.", "pred_embeddings_ec.", "gconv_net_ec.", "gconv_net_manipulation.", "rel_s_mlp.")
+    # + "pred_embeddings_man_dc." when man_dc_preds: the layout-only model's `manipulate` looks predicates up there
+    # (EchoLayout.py:154); Sg2ScDiffModel owns that table too but never reads it when sampling
 
     def __init__(self, num_objs: int = 36, num_preds: int = 16, embedding_dim: int = 64, gconv_num_layers: int = 5,
                  residual: bool = True, use_clip: bool = True, gconv_pooling: str = "avg",
                  mlp_normalization: str = "batch", rel_s_hidden: int = 960, context_dim: int = 1280,
-                 with_rel_s: bool = True):
+                 with_rel_s: bool = True, man_dc_preds: bool = False):
         super().__init__()
         if gconv_pooling != "avg":
             raise EchoError(f"gconv_pooling='{gconv_pooling}' is not on the hot path (SGDiff.py:21-22 passes 'avg')")
@@ -211,7 +216,7 @@ class SceneEncoder(_SpecModule):
             raise EchoError("SceneEncoder mirrors the SGDiff construction (mlp_normalization='batch', SGDiff.py:21-22)")
         self.cfg = arch.SceneEncoderConfig(gconv_dim=embedding_dim, add_dim=512 if use_clip else 0, num_objs=num_objs,
                                            num_preds=num_preds, num_layers=gconv_num_layers, residual=residual,
-                                           rel_s_hidden=rel_s_hidden, context_dim=context_dim)
+                                           rel_s_hidden=rel_s_hidden, context_dim=context_dim, man_dc_preds=bool(man_dc_preds))
         self.embedding_dim = embedding_dim
         self.clip = use_clip
         self.out_dim_ini_encoder = self.out_dim_manipulator = self.cfg.feat_dim
@@ -230,7 +235,10 @@ class SceneEncoder(_SpecModule):
     def load_reference_state_dict(self, state_dict, strict: bool = True):
         """Loads the encoder slice of a ``Sg2ScDiffModel`` state_dict (its other sub-modules -- the *_dc embeddings,
         LayoutDiff, ShapeDiff -- are dropped)."""
-        sub = {k: v for k, v in state_dict.items() if k.startswith(self.PREFIXES)}
+        pre = self.PREFIXES + (("pred_embeddings_man_dc.",) if self.cfg.man_dc_preds else ())
+        if not self.with_rel_s:
+            pre = tuple(p for p in pre if p != "rel_s_mlp.")
+        sub = {k: v for k, v in state_dict.items() if k.startswith(pre)}
         return self.load_state_dict(sub, strict=strict)
 
     # ---- handle ----
@@ -243,7 +251,7 @@ class SceneEncoder(_SpecModule):
         cap = (_next_pow2(n_nodes, 32), _next_pow2(n_triples, 128))
         c = self.cfg
         d = _lib.SceneDesc(c.gconv_dim, c.add_dim, c.num_objs + 1, c.num_preds, c.num_layers, c.rel_s_hidden,
-                           c.context_dim, cap[0], cap[1], 1e-5)
+                           c.context_dim, cap[0], cap[1], 1e-5, int(c.man_dc_preds))
         arr, n, keep = _lib.weights_table(self.state_dict())
         h = C.c_void_p()
         _lib.check(_lib.lib().echo_scene_create(C.byref(h), C.byref(d), arr, n))

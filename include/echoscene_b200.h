@@ -244,6 +244,8 @@ typedef struct echo_scene_desc {
   int32_t context_dim;          /* 1280 */
   int32_t max_nodes, max_triples;
   float bn_eps;                 /* 1e-5 */
+  int32_t manipulate_pred_dc;   /* 0: manipulate embeds predicates with pred_embeddings_ec (Sg2ScDiffModel, EchoScene.py:187);
+                                 * 1: with pred_embeddings_man_dc.weight (the layout-only Sg2BoxDiffModel, EchoLayout.py:154) */
 } echo_scene_desc_t;
 ECHO_API int echo_scene_create(echo_scene_t** out, const echo_scene_desc_t* desc, const echo_weight_t* weights, int32_t n_weights);
 /* init_encoder(objs, triples, text_feat, rel_feat) (EchoScene.py:143-157): objs (N) i64 class ids -- the caller guarantees

@@ -123,6 +123,18 @@ SCENE_GLUE_CASES = (
 )
 
 
+def scene_box_cfg() -> arch.SceneEncoderConfig:
+    """the layout-only model (model/EchoLayout.py): predicates of `manipulate` from pred_embeddings_man_dc"""
+    return arch.SceneEncoderConfig(man_dc_preds=True)
+
+
+def scene_box_state_dict():
+    """state_dict of the layout-only model's encoder slice: as scene_encoder_specs, plus the second predicate table, without
+    rel_s_mlp"""
+    sd = arch.make_state_dict(arch.scene_encoder_specs(scene_box_cfg()), WEIGHT_SEED_SCENE + 1)
+    return type(sd)((k, v) for k, v in sd.items() if not k.startswith("rel_s_mlp."))
+
+
 def scene_glue_inputs(name: str):
     """-> (positional tensor arguments of the method, marked nodes or None).  `changes`: nodes 1 and 5 manipulated;
     `additions`: missing_nodes [2, 4] -> rows inserted at [2, 5] of the 6-node encoder scene (8 decoder nodes)."""

@@ -475,10 +475,11 @@ def vqvae_decode_no_quant(sd: SD, cfg, h: Tensor) -> Tensor:
 # --------------------------------------------------------------------------------------
 
 
-def _scene_embed(sd: SD, objs: Tensor, triples: Tensor, text_feat: Tensor, rel_feat: Tensor):
+def _scene_embed(sd: SD, objs: Tensor, triples: Tensor, text_feat: Tensor, rel_feat: Tensor,
+                 pred_table: str = "pred_embeddings_ec.weight"):
     edges, p = edges_of(triples)
     obj_embed = torch.cat([text_feat, F.embedding(objs, sd["obj_embeddings_ec.weight"])], dim=1)       # :149-153
-    pred_embed = torch.cat([rel_feat, F.embedding(p, sd["pred_embeddings_ec.weight"])], dim=1)
+    pred_embed = torch.cat([rel_feat, F.embedding(p, sd[pred_table])], dim=1)
     return edges, obj_embed, pred_embed
 
 
@@ -492,7 +493,9 @@ def scene_init_encoder(sd: SD, cfg, objs: Tensor, triples: Tensor, text_feat: Te
 def scene_manipulate(sd: SD, cfg, latent_f: Tensor, objs: Tensor, triples: Tensor, text_feat: Tensor, rel_feat: Tensor):
     """Sg2ScDiffModel.manipulate, EchoScene.py:181-195: latent_f (N, feat + gconv_dim) -> obj_vecs, pred_vecs, obj_embed,
     pred_embed."""
-    edges, obj_embed, pred_embed = _scene_embed(sd, objs, triples, text_feat, rel_feat)
+    # the layout-only model looks the predicates up in pred_embeddings_man_dc here (EchoLayout.py:154)
+    table = "pred_embeddings_man_dc.weight" if getattr(cfg, "man_dc_preds", False) else "pred_embeddings_ec.weight"
+    edges, obj_embed, pred_embed = _scene_embed(sd, objs, triples, text_feat, rel_feat, table)
     obj_vecs = torch.cat([latent_f, obj_embed], dim=1)                                                 # :192
     latent, pred_vecs = graph_triple_conv_net(sd, "gconv_net_manipulation.", obj_vecs, pred_embed, edges, min(cfg.num_layers, 5))
     return latent, pred_vecs, obj_embed, pred_embed
@@ -516,8 +519,11 @@ def scene_encode(sd: SD, cfg, objs: Tensor, triples: Tensor, text_feat: Tensor, 
         change = torch.zeros(latent_obj.shape[0], cfg.gconv_dim, dtype=latent_obj.dtype, device=latent_obj.device)  # :393-397
     latent, _, obj_embed, pred_embed = scene_manipulate(sd, cfg, torch.cat([latent_obj, change], dim=1), objs, triples, text_feat,
                                                         rel_feat)
-    return {"obj_embed": obj_embed, "pred_embed": pred_embed, "latent": latent, "latent_obj": latent_obj,
-            "uc_s": scene_rel_s(sd, obj_embed).unsqueeze(1), "c_s": scene_rel_s(sd, latent).unsqueeze(1)}
+    out = {"obj_embed": obj_embed, "pred_embed": pred_embed, "latent": latent, "latent_obj": latent_obj}
+    if "rel_s_mlp.0.weight" in sd:   # the layout-only model has no rel_s_mlp (and never samples shapes)
+        out["uc_s"] = scene_rel_s(sd, obj_embed).unsqueeze(1)
+        out["c_s"] = scene_rel_s(sd, latent).unsqueeze(1)
+    return out
 
 
 def vq_encoder(sd: SD, cfg, x: Tensor, p: str = "encoder") -> Tensor:

@@ -83,16 +83,30 @@ def main():
         init_encoder = M.init_encoder
         manipulate = M.manipulate
         prepare_boxes = M.prepare_boxes
-        prepare_input = MB.prepare_input        # the layout-only model's name for it (EchoLayout.py)
+
+    class BoxHolder(Holder):                    # the layout-only model: its own methods and predicate table, no rel_s_mlp
+        def __init__(self, replace_latent):
+            super().__init__(replace_latent)
+            del self.rel_s_mlp
+            self.pred_embeddings_man_dc = nn.Embedding(cfg.num_preds, gd * 2)
+
+        init_encoder = MB.init_encoder
+        manipulate = MB.manipulate              # looks predicates up in pred_embeddings_man_dc (EchoLayout.py:154)
+        prepare_input = MB.prepare_input
 
     sd = arch.make_state_dict(arch.scene_encoder_specs(cfg), cases.WEIGHT_SEED_SCENE)
+    sd_box = cases.scene_box_state_dict()
     out = {}
     real_cuda = torch.Tensor.cuda
     torch.Tensor.cuda = lambda self, *a, **k: self
     try:
         for name, fn, replace in cases.SCENE_GLUE_CASES:
-            h = Holder(replace).eval()
-            h.load_state_dict(sd, strict=True)
+            if fn.startswith("sampleBoxes"):
+                h = BoxHolder(replace).eval()
+                h.load_state_dict(sd_box, strict=True)
+            else:
+                h = Holder(replace).eval()
+                h.load_state_dict(sd, strict=True)
             args, marked = cases.scene_glue_inputs(name)
             np.random.seed(cases.SCENE_GLUE_NP_SEED)
             rec.layout_in = rec.shape_in = None

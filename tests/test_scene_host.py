@@ -20,9 +20,12 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 class OracleEncoder:
     """SceneEncoder's method surface on the CPU oracle."""
 
-    def __init__(self):
-        self.cfg = cases.scene_cfg()
-        self.sd = arch.make_state_dict(arch.scene_encoder_specs(self.cfg), cases.WEIGHT_SEED_SCENE)
+    def __init__(self, box: bool = False):
+        if box:   # the layout-only model: second predicate table for manipulate, no rel_s_mlp (model/EchoLayout.py)
+            self.cfg, self.sd = cases.scene_box_cfg(), cases.scene_box_state_dict()
+        else:
+            self.cfg = cases.scene_cfg()
+            self.sd = arch.make_state_dict(arch.scene_encoder_specs(self.cfg), cases.WEIGHT_SEED_SCENE)
         self.embedding_dim = self.cfg.gconv_dim
         self.out_dim_ini_encoder = self.cfg.feat_dim
 
@@ -69,7 +72,7 @@ def test_layout_only_glue_matches_reference_methods(gold, name, fn, replace):
     """Sg2BoxDiffModel.sampleBoxes* (model/EchoLayout.py:291-401)."""
     G = gold[name]
     lay = RecLayout()
-    m = scene.Sg2BoxDiffModel(OracleEncoder(), lay, replace_latent=replace)
+    m = scene.Sg2BoxDiffModel(OracleEncoder(box=True), lay, replace_latent=replace)
     args, marked = cases.scene_glue_inputs(name)
     np.random.seed(cases.SCENE_GLUE_NP_SEED)
     if fn == "sampleBoxes":
@@ -189,6 +192,25 @@ def test_scene_encoder_module_surface():
         m.init_encoder(objs, g.triples, text, rel)
 
 
+def test_scene_encoder_layout_only_variant():
+    """SceneEncoder(man_dc_preds=True, with_rel_s=False) = the encoder slice of the layout-only Sg2BoxDiffModel."""
+    sd = cases.scene_box_state_dict()
+    m = modules.SceneEncoder(man_dc_preds=True, with_rel_s=False)
+    assert list(m.state_dict().keys()) == list(sd.keys()) and "pred_embeddings_man_dc.weight" in sd
+    full = dict(sd)
+    full["obj_embeddings_dc.weight"] = torch.zeros(37, 128)
+    full["rel_s_mlp.0.weight"] = torch.zeros(960, 640)             # a full-model checkpoint offered to the layout-only encoder
+    m.load_reference_state_dict(full, strict=True)
+    assert torch.equal(m.state_dict()["pred_embeddings_man_dc.weight"], sd["pred_embeddings_man_dc.weight"])
+    # the oracle follows the same switch: the two tables give different manipulate outputs
+    g, objs, text, rel = cases.scene_inputs()
+    cfg = cases.scene_box_cfg()
+    with torch.no_grad():
+        a = orc.scene_encode(sd, cfg, objs, g.triples, text, rel)
+        b = orc.scene_encode(sd, cases.scene_cfg(), objs, g.triples, text, rel)
+    assert "uc_s" not in a and torch.equal(a["obj_embed"], b["obj_embed"]) and not torch.equal(a["latent"], b["latent"])
+
+
 def test_scene_entry_points_reject_bad_arguments():
     import ctypes as C
     L = _lib.lib()
@@ -240,10 +262,15 @@ def test_reference_side_binding_shares_parameters():
     h.eval()
     h.obj_embeddings_ec.weight = nn.Parameter(h.obj_embeddings_ec.weight.detach().clone())   # what .cuda() / load does
     assert integrate.scene_encoder_of(h) is not enc
-    # the layout-only model (model/EchoLayout.py) owns no rel_s_mlp: the encoder is built without it and says so
+    # the layout-only model (model/EchoLayout.py) owns no rel_s_mlp and embeds the predicates of `manipulate` with
+    # pred_embeddings_man_dc (patch_reference marks its class): the encoder is built that way
     del h.rel_s_mlp
+    h.pred_embeddings_man_dc = nn.Embedding(16, 128)
+    Holder._echo_man_dc_preds = True
     box = integrate.scene_encoder_of(h)
     assert not box.with_rel_s and not any(k.startswith("rel_s_mlp.") for k in box.state_dict())
+    assert box.cfg.man_dc_preds
+    assert box.state_dict()["pred_embeddings_man_dc.weight"].data_ptr() == h.pred_embeddings_man_dc.weight.data_ptr()
     with pytest.raises(_lib.EchoError, match="rel_s_mlp"):
         box.rel_s(torch.zeros(2, 640))
 

@@ -228,3 +228,31 @@ def test_config1_echolayout_sampleBoxes_vs_oracle(enc):
     got = torch.cat([out["sizes"], out["translations"], out["angles"]], dim=1)
     assert got.shape == (8, 8)
     assert_close(got, boxes, 5e-3, "config 1: sampleBoxes 10-step chain")
+
+
+@pytest.mark.parametrize("name,fn,replace", [c for c in cases.SCENE_GLUE_CASES if c[0].startswith("box_")])
+def test_layout_only_model_vs_reference_golden(name, fn, replace):
+    """The layout-only Sg2BoxDiffModel (model/EchoLayout.py:291-401): SceneEncoder(man_dc_preds=True, with_rel_s=False) --
+    `manipulate` embeds predicates with pred_embeddings_man_dc (:154) -- under sampleBoxes / _with_changes / _with_additions,
+    against the conditioning recorded from the reference's own methods."""
+    sd = cases.scene_box_state_dict()
+    m = modules.SceneEncoder(man_dc_preds=True, with_rel_s=False)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV)
+    G = gold("scene_glue.pt")[name]
+    lay = RecLayout()
+    model = scene.Sg2BoxDiffModel(m, lay, replace_latent=replace)
+    args, marked = cases.scene_glue_inputs(name)
+    np.random.seed(cases.SCENE_GLUE_NP_SEED)
+    if fn == "sampleBoxes":
+        layout_dict = model.sampleBoxes(*_cuda(*args))
+    else:
+        keep, layout_dict = getattr(model, fn)(*_cuda(*args), marked)
+        assert (keep.cpu().flatten().tolist() if torch.is_tensor(keep) else keep) == (
+            G["keep"].flatten().tolist() if torch.is_tensor(G["keep"]) else G["keep"])
+    for k in ("uc_b", "c_b"):
+        assert_close(lay.seen[k], G[k], FP32_TOL, f"{name} {k}")
+    assert layout_dict["translations"].shape == (8, 3)
+    g, objs, text, rel = cases.scene_inputs()
+    with pytest.raises(_lib.EchoError, match="rel_s_mlp"):
+        m.encode(*_cuda(objs, g.triples, text, rel), shape_cond=True)
