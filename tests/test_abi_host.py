@@ -82,3 +82,32 @@ def test_synthetic_graph_contract():
     assert b.n_nodes == 32 and (b.triples[64:, 0] == t[:, 0] + 16).all()
     with pytest.raises(ValueError):
         synth.make_scene_graph(2, 4, 0)
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """Every descriptor struct of the header, compiled as C (the header must stay plain C), has the size and field offsets of
+    its ctypes mirror in _lib.py."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    pairs = {"echo_weight_t": _lib.Weight, "echo_gcn_desc_t": _lib.GcnDesc, "echo_layout_desc_t": _lib.LayoutDesc,
+             "echo_shape_desc_t": _lib.ShapeDesc, "echo_scene_desc_t": _lib.SceneDesc, "echo_vqvae_desc_t": _lib.VqvaeDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "echoscene_b200.h")}"',
+             'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    assert len(out) == len(pairs)
+    for line, (cname, cls) in zip(out, pairs.items()):
+        got = line.split()
+        want = [cname, str(C.sizeof(cls))] + [str(getattr(cls, f).offset) for f, _ in cls._fields_]
+        assert got == want, f"{cname}: header {got} vs ctypes {want}"
