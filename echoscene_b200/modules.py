@@ -9,6 +9,8 @@ lazily on the first call and whenever a parameter was modified or the graph outg
   GraphTripleConv / GraphTripleConvNet   model/graph.py:89-250
   UNet1DModel                            model/networks/diffusion_layout/denoise_net.py:451-806
   UNet3DModel, DiffusionUNet             model/networks/diffusion_shape/openai_model_3d.py:452-863, network.py:11-43
+  SceneEncoder                           the encoder sub-modules / methods of model/EchoScene.py:46-100, 143-195
+  VQVAE                                  model/networks/vqvae_networks/network.py:56-103 (decode 8f-1, encode_no_quant 8f-3)
 
 Inference only (eval-mode BatchNorm, no autograd): the training backward is outside this round's scope.
 """
