@@ -237,11 +237,14 @@ class SceneEncoder(_SpecModule):
     def load_reference_state_dict(self, state_dict, strict: bool = True):
         """Loads the encoder slice of a ``Sg2ScDiffModel`` state_dict (its other sub-modules -- the *_dc embeddings,
         LayoutDiff, ShapeDiff -- are dropped)."""
-        pre = self.PREFIXES + (("pred_embeddings_man_dc.",) if self.cfg.man_dc_preds else ())
-        if not self.with_rel_s:
-            pre = tuple(p for p in pre if p != "rel_s_mlp.")
+        pre = self.reference_prefixes()
         sub = {k: v for k, v in state_dict.items() if k.startswith(pre)}
         return self.load_state_dict(sub, strict=strict)
+
+    def reference_prefixes(self) -> tuple:
+        """key prefixes of the reference model's state_dict that belong to this encoder"""
+        pre = self.PREFIXES + (("pred_embeddings_man_dc.",) if self.cfg.man_dc_preds else ())
+        return pre if self.with_rel_s else tuple(p for p in pre if p != "rel_s_mlp.")
 
     # ---- handle ----
     def _ensure(self, n_nodes: int, n_triples: int):

@@ -100,7 +100,7 @@ def load_reference_checkpoint(ckpt, encoder=None, unet1d=None, unet3d=None, vqva
     flat = {k: v for k, v in ckpt.items() if torch.is_tensor(v)}
     if encoder is not None:
         encoder.load_reference_state_dict(flat, strict=strict)
-        info["loaded"]["encoder"] = sum(1 for k in flat if k.startswith(encoder.PREFIXES))
+        info["loaded"]["encoder"] = sum(1 for k in flat if k.startswith(encoder.reference_prefixes()))
     if unet1d is not None:
         sub = _strip(flat, ("LayoutDiff.df.model.", "LayoutDiff.df.module.model."))
         if not sub:
