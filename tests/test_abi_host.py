@@ -111,3 +111,40 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
         got = line.split()
         want = [cname, str(C.sizeof(cls))] + [str(getattr(cls, f).offset) for f, _ in cls._fields_]
         assert got == want, f"{cname}: header {got} vs ctypes {want}"
+
+
+def test_plain_c_client_links_and_calls(tmp_path):
+    """The boundary is a C ABI: a C99 translation unit that includes the header links against the library with no C++/torch in
+    sight, calls host-only entry points and gets codes + messages back (no GPU needed for these calls)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "client.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include <string.h>
+#include "echoscene_b200.h"
+int main(void) {
+  float tab[5 * 10];
+  int64_t tri[6] = {0, 3, 1, 1, 5, 0};
+  int32_t off[3], items[4];
+  int64_t range[2];
+  echo_gcn_t* h = NULL;
+  if (echo_version() != ECHO_ABI_VERSION) return 1;
+  if (echo_debug_ddpm_tables(10, 1e-4f, 0.02f, tab) != ECHO_OK) return 2;
+  if (echo_debug_graph_csr(tri, 2, 2, off, items, range) != ECHO_OK) return 3;
+  if (echo_gcn_create(&h, NULL, NULL, 0) != ECHO_ERR_INVALID || strlen(echo_last_error()) == 0) return 4;
+  printf("%d %.6f %d %d %d %d %lld %lld\n", echo_version(), tab[0], off[2], items[0], items[1], items[3], (long long)range[0],
+         (long long)range[1]);
+  return 0;
+}
+""")
+    exe = tmp_path / "client"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lechoscene_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    # node 0: subject of t0 (item 0), object of t1 (item 3); node 1: subject of t1 (item 2), object of t0 (item 1)
+    assert out[0] == "1" and out[2:] == ["4", "0", "3", "1", "3", "5"]
+    assert abs(float(out[1]) - 1.00005) < 1e-4                 # sqrt(1 / alphas_cumprod[0]) = sqrt(1 / (1 - 1e-4))
