@@ -9,6 +9,7 @@ python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 |
 python -m pytest tests/test_zzz_vqenc_gpu.py tests/test_zz_scene_gpu.py -m gpu -x -q > gpurun_out/new_gpu_tests.log 2>&1
 echo "new GPU tests rc=$?"; tail -5 gpurun_out/new_gpu_tests.log
 python tools/time_scene.py > gpurun_out/time_scene.log 2>&1; cat gpurun_out/time_scene.log
+python tools/sample_scene.py > gpurun_out/sample_scene.log 2>&1; tail -5 gpurun_out/sample_scene.log
 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 1500 gpurun_out/bench_n1.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_scene.csv \
     python tools/time_scene.py 16 64 1 > gpurun_out/ncu_scene.log 2>&1
