@@ -1,7 +1,6 @@
 """CPU: echoscene_b200.sgdiff.SGDiff -- the facade of model/SGDiff.py built from YAML files with the reference's key structure
 (config/full_mp.yaml, config/sdfusion-txt2shape_mp.yaml, config/vqvae_snet.yaml), its checkpoint loading, and that every
 sampling call ends in the CUDA library (no CPU fallback)."""
-import os
 
 import pytest
 import torch

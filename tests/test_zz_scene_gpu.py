@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from echoscene_b200 import _lib, arch, modules, samplers, scene, synth
+from echoscene_b200 import _lib, arch, modules, samplers, scene
 from oracle import cases, echoscene_oracle as orc
 from util import FP32_TOL, assert_close, gold
 
