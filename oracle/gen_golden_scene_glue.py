@@ -129,6 +129,61 @@ def main():
     finally:
         torch.Tensor.cuda = real_cuda
     torch.save(out, os.path.join(GOLD, "scene_glue.pt"))
+    pin_glue(out)
+
+
+def pin_glue(gold):
+    """Runs echoscene_b200/scene.py on the oracle encoders for every case and records its deviation from the reference's
+    recorded tensors in tests/golden/PINNING.json (expected: exactly 0)."""
+    import json
+    from echoscene_b200 import scene
+    from oracle.scene_encoder import OracleSceneEncoder
+
+    class Lay:
+        def gen_samples_sg(self, shape, device, obj_embed, triples=None, condition=None, **kw):
+            self.seen = {"uc_b": obj_embed, "c_b": condition}
+            return torch.zeros(shape)
+
+    class DDIM:
+        seen = None
+
+        def __init__(self, model):
+            pass
+
+        def sample(self, S, batch_size, shape, conditioning=None, x_T=None, unconditional_conditioning=None, **kw):
+            DDIM.seen = {"c_s": conditioning, "uc_s": unconditional_conditioning}
+            return x_T, {}
+
+    rec = {}
+    for name, fn, replace in cases.SCENE_GLUE_CASES:
+        box = fn.startswith("sampleBoxes")
+        lay = Lay()
+        cls = scene.Sg2BoxDiffModel if box else scene.Sg2ScDiffModel
+        kw = {} if box else dict(shape=object(), ddim_sampler_cls=DDIM)
+        m = cls(OracleSceneEncoder(box=box), lay, replace_latent=replace, **kw)
+        args, marked = cases.scene_glue_inputs(name)
+        np.random.seed(cases.SCENE_GLUE_NP_SEED)
+        if fn == "sample":
+            m.sample(*args, gen_shape=True)
+        elif fn == "sampleBoxes":
+            m.sampleBoxes(*args)
+        elif box:
+            getattr(m, fn)(*args, marked)
+        else:
+            getattr(m, fn)(*args, marked, gen_shape=True)
+        seen = dict(lay.seen)
+        if not box:
+            seen.update(DDIM.seen)
+        rec[name] = max(float((seen[k].double() - gold[name][k].double()).abs().max()) for k in seen)
+    path = os.path.join(GOLD, "PINNING.json")
+    pin = json.load(open(path))
+    pin["cases"]["scene_glue"] = {"max_abs": max(rec.values()), "detail": rec,
+                                  "what": "tensors handed to LayoutDiff.set_input / ShapeDiff.rel2shape by the reference's own "
+                                          "sample* / sampleBoxes* methods vs echoscene_b200/scene.py on the oracle encoders"}
+    with open(path, "w") as f:
+        json.dump(pin, f, indent=1)
+    print("scene_glue pinning:", rec)
+    assert pin["cases"]["scene_glue"]["max_abs"] == 0.0
 
 
 if __name__ == "__main__":
