@@ -148,3 +148,28 @@ int main(void) {
     # node 0: subject of t0 (item 0), object of t1 (item 3); node 1: subject of t1 (item 2), object of t0 (item 1)
     assert out[0] == "1" and out[2:] == ["4", "0", "3", "1", "3", "5"]
     assert abs(float(out[1]) - 1.00005) < 1e-4                 # sqrt(1 / alphas_cumprod[0]) = sqrt(1 / (1 - 1e-4))
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is the checker: only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import it."""
+    import ast
+    pkg = os.path.join(ROOT, "echoscene_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith(".py"):
+                continue
+            tree = ast.parse(open(os.path.join(dirpath, f)).read())
+            for node in ast.walk(tree):
+                mods = []
+                if isinstance(node, ast.Import):
+                    mods = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    mods = [node.module or ""]
+                assert not any(m == "oracle" or m.startswith("oracle.") for m in mods), f"{f} imports the oracle"
+    # importing the whole product surface must not pull it in either
+    import subprocess
+    import sys
+    code = ("import sys; import echoscene_b200.modules, echoscene_b200.samplers, echoscene_b200.scene, echoscene_b200.sgdiff, "
+            "echoscene_b200.integrate, echoscene_b200.shard, echoscene_b200.synth; "
+            "sys.exit(1 if any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules) else 0)")
+    assert subprocess.run([sys.executable, "-c", code], cwd=ROOT).returncode == 0
