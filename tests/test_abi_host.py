@@ -173,3 +173,14 @@ def test_product_never_imports_the_oracle():
             "echoscene_b200.integrate, echoscene_b200.shard, echoscene_b200.synth; "
             "sys.exit(1 if any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules) else 0)")
     assert subprocess.run([sys.executable, "-c", code], cwd=ROOT).returncode == 0
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    """No silent fallback: without the built shared library every entry into the product raises."""
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libechoscene_b200.so")
+    with pytest.raises(_lib.EchoError, match="not built"):
+        _lib.lib()
+    g = modules.GraphTripleConvNet(64, 16, num_layers=1, hidden_dim=32, residual=True, mlp_normalization="batch")
+    with pytest.raises(_lib.EchoError):
+        g(torch.randn(4, 64), torch.randn(3, 16), torch.zeros(3, 2, dtype=torch.int64))
