@@ -149,6 +149,14 @@ def vqvae_decode_rate(dev, precision):
             "tflops_algorithmic": 723e9 * N_NODES / (ms * 1e-3) / 1e12}
 
 
+def optional_figure(fn, *a):
+    """A secondary figure never costs the headline line: any failure becomes {"error": ...}."""
+    try:
+        return fn(*a)
+    except Exception as e:   # noqa: BLE001
+        return {"error": repr(e)[:200]}
+
+
 def scene_encode_time(dev):
     """Secondary figure (the stage right before the two chains): Sg2ScDiffModel.sample's encoders (init_encoder ->
     manipulate -> rel_s_mlp x2) for the 16-node / 64-triple scene as ONE echo_scene_encode call, fp32.  HBM-bound weight
@@ -449,10 +457,7 @@ def main():
                                               "scaled by 2/16 to the N=16 step"}
         if world == 1:
             # last, and never fatal: a secondary figure must not cost the headline line
-            try:
-                line["scene_encode"] = scene_encode_time(dev)
-            except Exception as e:   # noqa: BLE001
-                line["scene_encode"] = {"error": repr(e)[:200]}
+            line["scene_encode"] = optional_figure(scene_encode_time, dev)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

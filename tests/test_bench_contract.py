@@ -66,3 +66,11 @@ def test_reference_arm_runs_on_cpu():
     assert d["impl"] == "reference" and d["metric"] == "denoiser-steps/sec" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_secondary_figures_are_never_fatal():
+    """bench.py computes the scene-encode figure last and through optional_figure: without a GPU it degrades to an error entry."""
+    import bench
+    out = bench.optional_figure(bench.scene_encode_time, "cpu")
+    assert set(out) == {"error"} and "EchoError" in out["error"]
+    assert bench.optional_figure(lambda: {"ms": 1.0}) == {"ms": 1.0}
