@@ -19,8 +19,9 @@ After that, ``scripts/eval_3dfront.py`` builds ``SGDiff`` as before (same YAML, 
 identical), and ``Sg2ScDiffModel.sample`` runs both chains through libechoscene_b200.so.  The one-time scene encoders
  run through ``modules.SceneEncoder``: the model's ``init_encoder`` / ``manipulate`` methods are rebound to
 single C-ABI calls on a ``SceneEncoder`` that SHARES the model's own parameters (no copy; rebuilt when they are replaced),
-so ``sample`` / ``sample_with_changes`` / ``sample_with_additions`` run unchanged.  ``self.rel_s_mlp`` (two Linear layers on
-N rows) stays the reference's nn.Sequential on this route; ``echoscene_b200.scene.Sg2ScDiffModel`` is the fully native one.
+so ``sample`` / ``sample_with_changes`` / ``sample_with_additions`` run unchanged; ``self.rel_s_mlp(x)`` is routed to
+echo_scene_rel_s the first time the encoders run (its parameters stay where they are).  ``echoscene_b200.scene`` /
+``echoscene_b200.sgdiff`` are the same surface without any reference code.
 
 Training (`train_3dfront.py`) needs the backward pass, which is outside this round's scope: the patched classes raise
 in ``train()`` mode instead of silently computing something else.
@@ -59,7 +60,27 @@ def scene_encoder_of(model):
     enc.load_state_dict(sd, strict=True, assign=True)
     enc.eval()
     object.__setattr__(model, "_echo_scene_encoder", (key, enc))     # not a registered sub-module
+    if enc.with_rel_s:
+        _route_rel_s(model)
     return enc
+
+
+def _route_rel_s(model):
+    """``self.rel_s_mlp(x)`` in Sg2ScDiffModel.sample* (EchoScene.py:405-410) -> echo_scene_rel_s.  The nn.Sequential keeps its
+    parameters (state_dict unchanged); only its ``forward`` is rebound, and only for eval mode: under ``model.train()`` the
+    reference's own forward runs (autograd)."""
+    mlp = model.rel_s_mlp
+    if "_echo_forward" in mlp.__dict__:
+        return
+    original = mlp.forward
+
+    def forward(x, _model=model, _original=original):
+        if _model.training or mlp.training:
+            return _original(x)
+        return scene_encoder_of(_model).rel_s(x)
+
+    object.__setattr__(mlp, "_echo_forward", original)
+    object.__setattr__(mlp, "forward", forward)
 
 
 def _eval_only(model):

@@ -235,7 +235,12 @@ def test_reference_side_binding_shares_parameters():
     g, objs, text, rel = cases.scene_inputs()
     with pytest.raises(_lib.EchoError, match="CUDA"):
         h.init_encoder(objs, g.triples, text, rel)
+    # self.rel_s_mlp(x) is routed to the library in eval mode (parameters stay in the nn.Sequential) ...
+    with pytest.raises(_lib.EchoError, match="CUDA"):
+        h.rel_s_mlp(torch.zeros(2, 640))
+    assert list(h.state_dict().keys()) == keys
     h.train()
+    assert h.rel_s_mlp(torch.zeros(2, 640)).shape == (2, 1280)                     # ... and is the reference's own forward in training
     with pytest.raises(_lib.EchoError, match="eval"):
         h.manipulate(torch.zeros(8, 704), objs, g.triples, text, rel)
     h.eval()
