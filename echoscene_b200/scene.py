@@ -122,6 +122,15 @@ def load_reference_checkpoint(ckpt, encoder=None, unet1d=None, unet3d=None, vqva
     return info
 
 
+def split_by_scene(out: Dict[str, Optional[torch.Tensor]], obj_to_scene: torch.Tensor):
+    """Per-scene views of the row-wise results of ``sample_scenes``: a list (one dict per scene) of the rows of every tensor
+    whose first dimension is the node count."""
+    o2s = obj_to_scene.detach().cpu().to(torch.int64)
+    n_scenes = int(o2s.max()) + 1 if o2s.numel() else 0
+    idx = [torch.nonzero(o2s == k).flatten() for k in range(n_scenes)]
+    return [{k: (None if v is None else v[i.to(v.device)]) for k, v in out.items()} for i in idx]
+
+
 class Sg2ScDiffModel:
     """Sampling surface of the reference's scene model on the B200 components.
 
@@ -188,6 +197,31 @@ class Sg2ScDiffModel:
         layout_dict = self.generate_layout(dec_triplets, enc["obj_embed"], enc["latent"])
         gen_sdf = self.rel2shape(dec_triplets, enc["c_s"], enc["uc_s"], x_T) if gen_shape else None
         return {"shapes": gen_sdf}, layout_dict
+
+    @torch.no_grad()
+    def sample_scenes(self, objs, triples, text_feat, rel_feat, obj_to_scene, gen_shape=False, x_T_per_scene=None):
+        """Many scenes in one call (BASELINE config 4): the inputs are a collated batch as dataset collate_fn builds it
+        (threedfront_dataset.py:618-743: node / triple tensors concatenated, triple indices offset per scene, ``obj_to_scene``
+        (N,) int64).  The batched graph is block-diagonal, so encoders and both chains run over all nodes at once -- objects
+        are the batch dimension of both denoisers and the echo GCN never crosses a scene.  The reference samples scene by
+        scene with ONE shape-noise draw per call (echo2shape.py:507-510); here every scene gets its own draw
+        (``x_T_per_scene`` (S, 3, 16, 16, 16) or fresh ``randn``), repeated over that scene's objects.
+        -> ({'shapes'}, layout_dict, obj_to_scene): rows in node order; ``split_by_scene`` cuts them per scene."""
+        o2s = obj_to_scene.to(torch.int64)
+        n_scenes = int(o2s.max()) + 1 if o2s.numel() else 0
+        enc = self.encoder.encode(objs, triples, text_feat, rel_feat, shape_cond=gen_shape)
+        layout_dict = self.generate_layout(triples, enc["obj_embed"], enc["latent"])
+        gen_sdf = None
+        if gen_shape:
+            if x_T_per_scene is None:
+                if self.reference_rng:
+                    torch.manual_seed(int(time.time()))
+                x_T_per_scene = torch.randn((n_scenes,) + self.z_shape, device=enc["c_s"].device)
+            if tuple(x_T_per_scene.shape) != (n_scenes,) + self.z_shape:
+                raise EchoError(f"x_T_per_scene must be {(n_scenes,) + self.z_shape}, got {tuple(x_T_per_scene.shape)}")
+            x_T = x_T_per_scene.to(enc["c_s"].device)[o2s.to(enc["c_s"].device)].contiguous()
+            gen_sdf = self.rel2shape(triples, enc["c_s"], enc["uc_s"], x_T)
+        return {"shapes": gen_sdf}, layout_dict, o2s
 
     @torch.no_grad()
     def sample_with_changes(self, enc_objs, enc_triples, enc_text_feat, enc_rel_feat, dec_objs, dec_triplets, dec_text_feat,

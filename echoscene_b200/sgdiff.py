@@ -185,6 +185,13 @@ class SGDiff:
     def sample_boxes_and_shape_with_additions(self, *args, gen_shape=False):
         return self.diff.sample_boxes_and_shape_with_additions(*args, gen_shape=gen_shape)
 
+    def sample_scenes(self, objs, triples, text_feat, rel_feat, obj_to_scene, gen_shape=False, x_T_per_scene=None):
+        """A collated batch of scenes in one call (no counterpart in the reference, which samples scene by scene):
+        scene.Sg2ScDiffModel.sample_scenes."""
+        shape_dict, layout_dict, o2s = self.diff.sample_scenes(objs, triples, text_feat, rel_feat, obj_to_scene, gen_shape=gen_shape,
+                                                               x_T_per_scene=x_T_per_scene)
+        return {**shape_dict, **layout_dict, "obj_to_scene": o2s}
+
     def forward_mani(self, *args, **kwargs):
         raise EchoError("SGDiff.forward_mani is the training step (losses + backward): outside the B200 sampling path")
 

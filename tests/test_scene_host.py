@@ -304,3 +304,35 @@ def test_load_reference_checkpoint(tmp_path):
     assert scene.load_reference_checkpoint(lay, unet1d=u1, unet3d=u3, strict=False)["loaded"] == {"unet1d": len(lsd)}
     with pytest.raises(KeyError):
         scene.load_reference_checkpoint({"epoch": 1}, unet1d=u1)
+
+
+def test_sample_scenes_batches_block_diagonal_scenes():
+    """BASELINE config 4 through the public surface: a collated batch of scenes in one call.  On the oracle encoders the
+    batched conditioning equals the per-scene conditioning (the graph is block-diagonal), every scene gets its own shape noise
+    repeated over its objects, and split_by_scene cuts the rows back."""
+    from echoscene_b200 import synth
+    sizes = [5, 3, 8]
+    parts = [cases.scene_inputs(cases.GraphCase(f"s{i}", n, n + 2, 60 + i)) for i, n in enumerate(sizes)]
+    batch = synth.batch_scene_graphs([p[0] for p in parts])
+    objs, text, rel = (torch.cat([p[j] for p in parts]) for j in (1, 2, 3))
+    o2s = torch.cat([torch.full((n,), i, dtype=torch.int64) for i, n in enumerate(sizes)])
+    lay = RecLayout()
+    m = scene.Sg2ScDiffModel(OracleEncoder(), lay, shape=object(), ddim_sampler_cls=RecDDIM)
+    x_T = torch.randn(3, 3, 16, 16, 16, generator=torch.Generator().manual_seed(1))
+    shape_dict, layout_dict, got_o2s = m.sample_scenes(objs, batch.triples, text, rel, o2s, gen_shape=True, x_T_per_scene=x_T)
+    assert torch.equal(got_o2s, o2s) and layout_dict["sizes"].shape == (16, 3)
+    seen_x = RecDDIM.seen["x_T"]
+    assert seen_x.shape == (16, 3, 16, 16, 16)
+    assert torch.equal(seen_x[0], x_T[0]) and torch.equal(seen_x[4], x_T[0]) and torch.equal(seen_x[5], x_T[1]) and torch.equal(seen_x[15], x_T[2])
+    batched_uc, batched_c = RecDDIM.seen["uc_s"], lay.seen["c_b"]
+    off = 0
+    for (g, o, t, r), n in zip(parts, sizes):                                   # scene by scene, as the reference would run them
+        m.sample(o, g.triples, t, r, gen_shape=True, x_T=x_T[:1].repeat(n, 1, 1, 1, 1))
+        # same arithmetic on different matrix heights: equal up to fp32 summation order inside the CPU GEMMs
+        for a, b in ((batched_uc[off:off + n], RecDDIM.seen["uc_s"]), (batched_c[off:off + n], lay.seen["c_b"])):
+            assert float((a - b).abs().max() / b.abs().max()) < 1e-5
+        off += n
+    per = scene.split_by_scene({**shape_dict, **layout_dict}, o2s)
+    assert [p["sizes"].shape[0] for p in per] == sizes and per[2]["shapes"].shape == (8, 3, 16, 16, 16)
+    with pytest.raises(_lib.EchoError):
+        m.sample_scenes(objs, batch.triples, text, rel, o2s, gen_shape=True, x_T_per_scene=x_T[:2])
