@@ -61,3 +61,49 @@ def layout_inputs(n_nodes: int, seed: int, obj_dim: int = 640, box_dim: int = 8)
     obj_embed = torch.randn(n_nodes, obj_dim, generator=g)
     x_T = torch.randn(n_nodes, box_dim, generator=g)
     return obj_embed, x_T
+
+
+# ---- workload configuration of bench.py / smoke() (product side: nothing here touches oracle/) -----------------------
+WEIGHT_SEED_GCN = 10
+WEIGHT_SEED_LAYOUT = 11
+WEIGHT_SEED_SHAPE = 12
+WEIGHT_SEED_VQVAE = 13
+WEIGHT_SEED_SCENE = 14
+
+
+def layout_cfg():
+    from . import arch
+    return arch.UNet1DConfig()
+
+
+def shape_cfg():
+    from . import arch
+    return arch.UNet3DConfig()
+
+
+def vqvae_cfg():
+    from . import arch
+    return arch.VQVAEConfig()
+
+
+def scene_cfg():
+    from . import arch
+    return arch.SceneEncoderConfig()
+
+
+def vqvae_inputs(n: int = 2, seed: int = 6):
+    """latents as the DDIM chain leaves them: (n, 3, 16, 16, 16), O(1) values"""
+    gen = torch.Generator().manual_seed(seed + 500)
+    return torch.randn(n, 3, 16, 16, 16, generator=gen)
+
+
+def scene_inputs(n_nodes: int, n_triples: int, seed: int, cfg=None):
+    """dec_objs (N,) i64 class ids (last node = '_scene_' class 0), triples, CLIP-like text / relation features"""
+    cfg = cfg or scene_cfg()
+    g = make_scene_graph(n_nodes, n_triples, seed)
+    gen = torch.Generator().manual_seed(seed + 600)
+    objs = torch.randint(1, cfg.num_objs, (n_nodes,), generator=gen)
+    objs[-1] = 0
+    text = torch.nn.functional.normalize(torch.randn(n_nodes, cfg.add_dim, generator=gen), dim=1) * 10
+    rel = torch.nn.functional.normalize(torch.randn(n_triples, cfg.add_dim, generator=gen), dim=1) * 10
+    return g, objs, text, rel

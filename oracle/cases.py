@@ -12,11 +12,8 @@ import torch
 
 from echoscene_b200 import arch, synth
 
-WEIGHT_SEED_GCN = 10
-WEIGHT_SEED_LAYOUT = 11
-WEIGHT_SEED_SHAPE = 12
-WEIGHT_SEED_VQVAE = 13
-WEIGHT_SEED_SCENE = 14
+from echoscene_b200.synth import (WEIGHT_SEED_GCN, WEIGHT_SEED_LAYOUT, WEIGHT_SEED_SCENE, WEIGHT_SEED_SHAPE,  # noqa: E402,F401
+                                  WEIGHT_SEED_VQVAE)
 
 
 @dataclass
@@ -82,8 +79,7 @@ VQVAE_CASE_OBJECTS = 2
 
 def vqvae_inputs(n: int = VQVAE_CASE_OBJECTS, seed: int = 6):
     """latents as the DDIM chain leaves them: (n, 3, 16, 16, 16), O(1) values"""
-    gen = torch.Generator().manual_seed(seed + 500)
-    return torch.randn(n, 3, 16, 16, 16, generator=gen)
+    return synth.vqvae_inputs(n, seed)
 
 
 def scene_cfg() -> arch.SceneEncoderConfig:
@@ -95,14 +91,7 @@ SCENE_CASE = GraphCase("scene_encode_n8", 8, 32, 7)          # BASELINE config 1
 
 def scene_inputs(case: GraphCase = SCENE_CASE, cfg: "arch.SceneEncoderConfig" = None):
     """dec_objs (N,) i64 class ids (last node = '_scene_' class 0), triples, CLIP-like text / relation features"""
-    cfg = cfg or scene_cfg()
-    g = synth.make_scene_graph(case.n_nodes, case.n_triples, case.seed)
-    gen = torch.Generator().manual_seed(case.seed + 600)
-    objs = torch.randint(1, cfg.num_objs, (case.n_nodes,), generator=gen)
-    objs[-1] = 0
-    text = torch.nn.functional.normalize(torch.randn(case.n_nodes, cfg.add_dim, generator=gen), dim=1) * 10
-    rel = torch.nn.functional.normalize(torch.randn(case.n_triples, cfg.add_dim, generator=gen), dim=1) * 10
-    return g, objs, text, rel
+    return synth.scene_inputs(case.n_nodes, case.n_triples, case.seed, cfg)
 
 
 # glue of sample / sample_with_changes / sample_with_additions (oracle/gen_golden_scene_glue.py)

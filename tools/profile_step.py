@@ -12,7 +12,6 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from echoscene_b200 import arch, modules, synth  # noqa: E402
-from oracle import cases  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--branch", default="shape", choices=["shape", "layout"])
@@ -35,7 +34,7 @@ if args.branch == "shape":
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
 else:
-    sd = arch.make_state_dict(arch.unet1d_specs(cases.layout_cfg()), cases.WEIGHT_SEED_LAYOUT)
+    sd = arch.make_state_dict(arch.unet1d_specs(synth.layout_cfg()), synth.WEIGHT_SEED_LAYOUT)
     m = modules.UNet1DModel(in_channels=8, model_channels=512, out_channels=8, num_res_blocks=2, attention_resolutions=[4, 2],
                             channel_mult=[1, 1, 1, 1], num_heads=8, use_spatial_transformer=True, concat_dim=1280,
                             crossattn_dim=1280, enable_t_emb=True, precision=args.precision)
