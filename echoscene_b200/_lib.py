@@ -17,6 +17,14 @@ LIB_PATH = os.path.join(_HERE, "lib", "libechoscene_b200.so")
 
 PREC_FP32 = 0
 PREC_BF16 = 1
+PREC_X3 = 2
+
+
+def precision_code(name: str) -> int:
+    try:
+        return {"fp32": PREC_FP32, "bf16": PREC_BF16, "x3": PREC_X3}[name]
+    except KeyError:
+        raise EchoError(f"unknown precision {name!r} (fp32 | bf16 | x3)") from None
 
 
 class EchoError(RuntimeError):
@@ -80,6 +88,8 @@ PROTOTYPES = {
     "echo_launch_count": (C.c_int64, []),
     "echo_launch_count_reset": (None, []),
     "echo_debug_set_tc_mode": (None, [C.c_int]),
+    "echo_debug_set_layout_mode": (None, [C.c_int]),
+    "echo_debug_layout_info": (C.c_int, [_P, _P]),
     "echo_debug_probe_begin": (None, [C.c_int64, C.c_int, C.c_int, C.c_int]),
     "echo_debug_probe_end": (C.c_int, [C.POINTER(C.c_double)]),
     "echo_debug_probe_timeline": (None, [_P]),

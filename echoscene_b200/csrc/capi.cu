@@ -19,6 +19,8 @@ void layout_destroy(echo_layout*);
 void layout_forward(echo_layout*, const echo_graph*, const float*, const float*, const int64_t*, float*, cudaStream_t);
 void layout_step(echo_layout*, const echo_graph*, const float*, const float*, int, const float*, float*, cudaStream_t);
 const std::vector<float>& layout_table(const echo_layout*);
+void set_layout_mode(int);
+void layout_info(const echo_layout*, int64_t*);
 echo_shape* shape_create(const echo_shape_desc_t*, const echo_weight_t*, int);
 void shape_destroy(echo_shape*);
 void shape_forward(echo_shape*, const echo_graph*, const float*, const float*, const int64_t*, float*, cudaStream_t);
@@ -120,6 +122,13 @@ int echo_has_tcgen05(void) {
   return r;
 }
 void echo_debug_set_tc_mode(int mode) { echo::set_tc_mode(mode); }
+void echo_debug_set_layout_mode(int mode) { echo::set_layout_mode(mode); }
+int echo_debug_layout_info(const echo_layout_t* h, int64_t* out6) {
+  return guard([&] {
+    ECHO_CHECK(h && out6, "layout_info: null argument");
+    echo::layout_info(h, out6);
+  });
+}
 void echo_debug_probe_begin(int64_t rows, int32_t cin, int32_t cout, int32_t ksize) { echo::tc_probe_begin(rows, cin, cout, ksize); }
 int32_t echo_debug_probe_end(double* avg_ms) { return echo::tc_probe_end(avg_ms); }
 int echo_debug_fold_upsample_weight(const float* w_host, int32_t cout, int32_t cin, int32_t up_depth, float* out_host) {

@@ -748,6 +748,31 @@ void convert(const void* x, DT xdt, void* y, DT ydt, int64_t count, cudaStream_t
   ECHO_LAUNCH_CHECK();
 }
 
+namespace {
+__global__ void split_bf16_kernel(const float4* __restrict__ x, int64_t nvec, uint2* __restrict__ hi, uint2* __restrict__ lo) {
+  griddep_launch();
+  griddep_wait();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
+    const __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+    const __nv_bfloat162 c = __floats2bfloat162_rn(v.x - __bfloat162float(h0), v.y - __bfloat162float(h1));
+    const __nv_bfloat162 d = __floats2bfloat162_rn(v.z - __bfloat162float(h2), v.w - __bfloat162float(h3));
+    hi[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    lo[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&c), *reinterpret_cast<const uint32_t*>(&d));
+  }
+}
+}  // namespace
+
+void split_bf16(const float* x, int64_t count, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t s) {
+  ECHO_CHECK(count % 4 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)hi % 8) == 0 && ((uintptr_t)lo % 8) == 0, "split_bf16: count %% 4 and aligned operands");
+  if (count == 0) return;
+  int64_t blocks = (count / 4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  launch_pdl(split_bf16_kernel, dim3((int)blocks), dim3(256), 0, s, (const float4*)x, count / 4, (uint2*)hi, (uint2*)lo);
+  ECHO_LAUNCH_CHECK();
+}
+
 void add_rowvec(void* y, DT ydt, int64_t rows, int C, const float* v, int64_t ldv, int64_t rpo, cudaStream_t s) {
   const int grid = grid_for(rows * C, 256);
   if (ydt == F32) add_rowvec_kernel<float><<<grid, 256, 0, s>>>((float*)y, rows, C, v, ldv, rpo);

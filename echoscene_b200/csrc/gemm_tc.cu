@@ -46,8 +46,8 @@ constexpr int SMEM_CS_BYTES = 2 * 4 * (MAX_BLOCK_N / 32) * CS_SLOTS * 8;   // [s
 constexpr int SMEM_ADD_BYTES = 2 * 2 * MAX_BLOCK_N * 4;    // per-column epilogue addend (bias + rowvec): [tile parity][sub-block][column]
 constexpr int SMEM_FIXED = 1024 /*align*/ + 512 /*barriers + tmem ptr*/ + SMEM_CS_BYTES + SMEM_ADD_BYTES;
 // bytes in flight per SM is what hides the L2 latency of the TMA stream: use every stage that fits
-static inline int stages_for(int b_rows, int msub) {
-  const int st = (SMEM_LIMIT - SMEM_FIXED) / (msub * A_STAGE_BYTES + b_rows * BLOCK_K * 2);
+static inline int stages_for(int b_rows, int msub, bool split = false) {
+  const int st = (SMEM_LIMIT - SMEM_FIXED) / ((split ? 2 : 1) * (msub * A_STAGE_BYTES + b_rows * BLOCK_K * 2));
   return st > MAX_STAGES ? MAX_STAGES : st;
 }
 constexpr int MAX_TAPS = 64;   // 27 taps of a 3x3x3 kernel, or phases x folded taps of a conv after a nearest upsample: 4 x 12 (x(1,2,2)), 8 x 8 (x2)
@@ -159,17 +159,25 @@ __device__ __forceinline__ SubTile sub_tile(const TcParams& p, int vm) {
 //               columns fill TMEM, so the accumulator ring is one deep).  The main loop is bound by the ~56 B/clk an SM
 //               can pull from L2; sharing B between two A tiles cuts the bytes per MMA from (16 KiB + B/2) / 1 to
 //               (32 KiB + B/2) / 2, which is what makes the long-K convolutions MMA-bound.
-template <bool CTA2, int MSUB>
+// SPLIT = true: split-precision contraction (ECHO_PREC_X3).  Both operands arrive as TWO bf16 tensors, x = hi + lo with
+//               hi = bf16(x), lo = bf16(x - hi) (16 mantissa bits together); every k-step issues three MMAs into the SAME fp32
+//               TMEM accumulator, A_hi B_hi + A_lo B_hi + A_hi B_lo (the dropped lo x lo term is ~2^-16 relative), so the
+//               tensor cores reproduce an fp32 contraction to ~1e-5 -- north_star's 1e-3 parity contract on tcgen05.  A stage
+//               holds [A_hi | A_lo | B_hi | B_lo]; MSUB = 1 only.
+template <bool CTA2, int MSUB, bool SPLIT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_a2,
+               const __grid_constant__ CUtensorMap map_b2, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
-  constexpr int A_BYTES = MSUB * A_STAGE_BYTES;            // per stage: MSUB sub-block tiles back to back
+  static_assert(!SPLIT || MSUB == 1, "the split-precision mode runs one sub-block per CTA");
+  constexpr int A_BYTES = (SPLIT ? 2 : MSUB) * A_STAGE_BYTES;   // per stage: MSUB sub-block tiles back to back (SPLIT: hi tile, lo tile)
   constexpr int ACC_SLOTS = MSUB == 1 ? 2 : 1;
   const int STAGES = p.stages;
   const int B_ROWS = CTA2 ? (p.block_n >> 1) : p.block_n;   // rows of the B tile staged by THIS CTA
-  const int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
+  const int B_HALF_BYTES = B_ROWS * BLOCK_K * 2;
+  const int B_STAGE_BYTES = (SPLIT ? 2 : 1) * B_HALF_BYTES;   // SPLIT: hi tile, lo tile
   uint8_t* smem_b = smem + STAGES * A_BYTES;
   uint64_t* bars = (uint64_t*)(smem + STAGES * (A_BYTES + B_STAGE_BYTES));
   uint64_t* full_bar = bars;                   // [STAGES]  (CTA2: the leader's copy is the one in use)
@@ -253,6 +261,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             if (CTA2) tma_load_2d_2sm(&map_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, tap * p.cin + kb * BLOCK_K, n_row0);
             else tma_load_2d(&map_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, tap * p.cin + kb * BLOCK_K, n_row0);
+            if (SPLIT) {   // the low halves of both operands
+              uint8_t* dst = smem_a + stage * A_BYTES + A_STAGE_BYTES;
+              const int cw = st[0].w0 + p.tap_w[tap], chh = st[0].h0 + p.tap_h[tap], cd = st[0].d0 + p.tap_d[tap];
+              const int cn = st[0].obj * p.obj_mul + p.tap_p[tap];
+              if (CTA2) {
+                tma_load_5d_2sm(&map_a2, &full_bar[stage], dst, kb * BLOCK_K, cw, chh, cd, cn);
+                tma_load_2d_2sm(&map_b2, &full_bar[stage], smem_b + stage * B_STAGE_BYTES + B_HALF_BYTES, tap * p.cin + kb * BLOCK_K, n_row0);
+              } else {
+                tma_load_5d(&map_a2, &full_bar[stage], dst, kb * BLOCK_K, cw, chh, cd, cn);
+                tma_load_2d(&map_b2, &full_bar[stage], smem_b + stage * B_STAGE_BYTES + B_HALF_BYTES, tap * p.cin + kb * BLOCK_K, n_row0);
+              }
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -285,11 +305,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int k = 0; k < nk; ++k) {
               const uint64_t koff = (uint64_t)(k * UMMA_K * 2 / 16);
               const uint32_t acc = (kb_total | k) != 0 ? 1u : 0u;
+              if (SPLIT) {
+                const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * A_BYTES));
+                const uint64_t dal = make_smem_desc(smem_u32(smem_a + stage * A_BYTES + A_STAGE_BYTES));
+                const uint64_t dbl = make_smem_desc(smem_u32(smem_b + stage * B_STAGE_BYTES + B_HALF_BYTES));
+                if (CTA2) {
+                  umma_bf16_2sm(tmem_d, dal + koff, db + koff, idesc, acc);     // small terms first
+                  umma_bf16_2sm(tmem_d, da + koff, dbl + koff, idesc, 1u);
+                  umma_bf16_2sm(tmem_d, da + koff, db + koff, idesc, 1u);
+                } else {
+                  umma_bf16(tmem_d, dal + koff, db + koff, idesc, acc);
+                  umma_bf16(tmem_d, da + koff, dbl + koff, idesc, 1u);
+                  umma_bf16(tmem_d, da + koff, db + koff, idesc, 1u);
+                }
+              } else {
 #pragma unroll
               for (int j = 0; j < MSUB; ++j) {
                 const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * A_BYTES + j * A_STAGE_BYTES));
                 if (CTA2) umma_bf16_2sm(tmem_d + j * MAX_BLOCK_N, da + koff, db + koff, idesc, acc);
                 else umma_bf16(tmem_d + j * MAX_BLOCK_N, da + koff, db + koff, idesc, acc);
+              }
               }
             }
             if (CTA2) {
@@ -605,10 +640,12 @@ void tc_init() {
   }
   g_tc.encode = (EncodeTiledFn)fn;
   g_tc.sms = prop.multiProcessorCount;
-  if (cudaFuncSetAttribute(gemm_tc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
-      cudaFuncSetAttribute(gemm_tc_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
-      cudaFuncSetAttribute(gemm_tc_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
-      cudaFuncSetAttribute(gemm_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
+  if (cudaFuncSetAttribute(gemm_tc_kernel<false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_tc_kernel<true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_tc_kernel<false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_tc_kernel<true, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_tc_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_tc_kernel<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
     cudaGetLastError();
     return;
   }
@@ -662,7 +699,8 @@ TcPlan tc_plan(const GemmArgs& g, const TcGeom& t, int sms) {
   TcPlan best;
   double best_cost = 0;
   const bool geglu = g.epi == 1;
-  const bool can_split = g.splitk_ws && !geglu && !g.up2 && t.taps == 27 && g.sh == 1 && ((int64_t)g.od * g.oh * g.ow) % 128 == 0 &&
+  const bool x3 = g.A_lo != nullptr;
+  const bool can_split = !x3 && g.splitk_ws && !geglu && !g.up2 && t.taps == 27 && g.sh == 1 && ((int64_t)g.od * g.oh * g.ow) % 128 == 0 &&
                          g.out_dt == BF16 && split_env != 1;
   for (int bn = 256; bn >= 32; bn -= 32) {
     if (geglu && bn != 256) continue;
@@ -670,15 +708,15 @@ TcPlan tc_plan(const GemmArgs& g, const TcGeom& t, int sms) {
     const int n_tiles = cdiv(g.cout, bn);
     const bool cta2 = mode != 1 && t.num_m_tiles % 2 == 0 && bn % 32 == 0;
     for (int msub = 1; msub <= 2; ++msub) {
-      if (msub == 2 && (geglu || t.num_m_tiles % (cta2 ? 4 : 2) != 0)) continue;
-      if (msub_env && msub != msub_env && !(msub_env == 2 && (geglu || t.num_m_tiles % (cta2 ? 4 : 2) != 0))) continue;
+      if (msub == 2 && (x3 || geglu || t.num_m_tiles % (cta2 ? 4 : 2) != 0)) continue;
+      if (!x3 && msub_env && msub != msub_env && !(msub_env == 2 && (geglu || t.num_m_tiles % (cta2 ? 4 : 2) != 0))) continue;
       const int b_rows = cta2 ? bn / 2 : bn;
-      if (stages_for(b_rows, msub) < 3) continue;
+      if (stages_for(b_rows, msub, x3) < (x3 ? 2 : 3)) continue;
       for (int sk = 1; sk <= (can_split ? 3 : 1); sk += 2) {
         const long long tiles = (long long)(t.vm_tiles / msub) * n_tiles * sk;
         const long long waves = (tiles + sms - 1) / sms;
-        const double mma = msub * 4.0 * (bn / 2.0);
-        const double feed = (msub * 16384.0 + b_rows * 128.0) / 52.0;
+        const double mma = (x3 ? 3.0 : 1.0) * msub * 4.0 * (bn / 2.0);
+        const double feed = (x3 ? 2.0 : 1.0) * (msub * 16384.0 + b_rows * 128.0) / 52.0;
         const double stage = mma > feed ? mma : feed;
         const double mainloop = (double)t.taps * t.kblocks_per_tap / sk * stage;
         const double epi = msub * (1500.0 + 12.0 * bn);
@@ -885,6 +923,11 @@ size_t gemm_tc_splitk_ws_bytes(const GemmArgs& g) {
 
 bool gemm_tc_supported(const GemmArgs& g) {
   if (g.a_dt != BF16 || g.w_dt != BF16) return false;
+  if ((g.A_lo != nullptr) != (g.W_lo != nullptr)) return false;
+  if (g.A_lo) {   // split-precision mode: plain convolutions / linears with the standard epilogue
+    if (g.epi || g.out_t || g.up2 || g.colsum) return false;
+    if (((uintptr_t)g.A_lo % 16) || ((uintptr_t)g.W_lo % 16)) return false;
+  }
   if (g.nb0 * g.nb1 != 1 || g.alpha != 1.f || g.act > 1) return false;
   if (g.up2) {   // W = [cout][4 phases][12 folded taps][cin] or [cout][8][8][cin] (fold_upsample_weight)
     if (g.up2 != 1 && g.up2 != 2) return false;
@@ -922,7 +965,9 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   if (g.rows_out() == 0) return;
   if (dbg_skip("gemm_tc")) return;
   const bool s2 = g.sh == 2;
+  const bool x3 = g.A_lo != nullptr;
   const __nv_bfloat16* a_ptr = (const __nv_bfloat16*)g.A;
+  const __nv_bfloat16* a_lo_ptr = (const __nv_bfloat16*)g.A_lo;
   int in_h = g.h, in_w = g.w, in_objs = g.n;
   if (s2) {
     const long long nvec = (long long)g.n * g.d * g.h * g.w * (g.cin / 8);
@@ -931,6 +976,12 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
     launch_pdl(s2d_kernel, dim3((int)blocks), dim3(256), 0, s, a_ptr, g.n, g.d, g.h, g.w, g.cin, nvec, (__nv_bfloat16*)g.scratch);
     ECHO_LAUNCH_CHECK();
     a_ptr = (const __nv_bfloat16*)g.scratch;
+    if (x3) {   // the scratch holds both halves back to back (the caller sizes it for two copies)
+      __nv_bfloat16* lo_dst = (__nv_bfloat16*)g.scratch + nvec * 8;
+      launch_pdl(s2d_kernel, dim3((int)blocks), dim3(256), 0, s, a_lo_ptr, g.n, g.d, g.h, g.w, g.cin, nvec, lo_dst);
+      ECHO_LAUNCH_CHECK();
+      a_lo_ptr = lo_dst;
+    }
     in_h = g.h / 2;
     in_w = g.w / 2;
     in_objs = g.n * 4;
@@ -942,8 +993,8 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   const TcPlan plan = tc_plan(g, ge, g_tc.sms);
   ECHO_CHECK(plan.block_n > 0, "gemm_tc: no launch plan");
   if (dbg_trace())
-    fprintf(stderr, "[echo-trace] gemm_tc rows=%lld cin=%d cout=%d k=%d stride=%d epi=%d up=%d bn=%d msub=%d splitk=%d cta2=%d\n",
-            (long long)g.rows_out(), g.cin, g.cout, g.kd, g.sh, g.epi, g.up2, plan.block_n, plan.msub, plan.splitk, plan.cta2 ? 1 : 0);
+    fprintf(stderr, "[echo-trace] gemm_tc rows=%lld cin=%d cout=%d k=%d stride=%d epi=%d up=%d bn=%d msub=%d splitk=%d cta2=%d x3=%d\n",
+            (long long)g.rows_out(), g.cin, g.cout, g.kd, g.sh, g.epi, g.up2, plan.block_n, plan.msub, plan.splitk, plan.cta2 ? 1 : 0, x3 ? 1 : 0);
   p.up = g.up2;
   p.n_obj = g.n; p.od = g.up2 == 2 ? g.d : g.od; p.oh = up ? g.h : g.oh; p.ow = up ? g.w : g.ow;   // the grid the 128-voxel boxes tile
   p.bw = ge.bw; p.bh = ge.bh; p.bd = ge.bd;
@@ -1004,25 +1055,25 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   // CTA pairs (cta_group::2) whenever the 128-row tiles pair up: halves the B bytes each SM has to pull from L2
   const bool cta2 = plan.cta2;   // (a pair never straddles two phases: num_m_tiles is even)
 
-  CUtensorMap map_a, map_b;
-  {
+  CUtensorMap map_a, map_b, map_a2, map_b2;
+  for (int half = 0; half < (x3 ? 2 : 1); ++half) {
     const cuuint64_t dims[5] = {(cuuint64_t)g.cin, (cuuint64_t)in_w, (cuuint64_t)in_h, (cuuint64_t)g.d, (cuuint64_t)in_objs};
     const cuuint64_t strides[4] = {(cuuint64_t)g.cin * 2, (cuuint64_t)g.cin * 2 * in_w, (cuuint64_t)g.cin * 2 * in_w * in_h,
                                    (cuuint64_t)g.cin * 2 * in_w * in_h * g.d};
     const cuuint32_t box[5] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bd, 1};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = g_tc.encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)a_ptr, dims, strides, box, estr,
+    CUresult r = g_tc.encode(half ? &map_a2 : &map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)(half ? a_lo_ptr : a_ptr), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ECHO_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed: %d", (int)r);
   }
-  {
+  for (int half = 0; half < (x3 ? 2 : 1); ++half) {
     const cuuint64_t ktot = g.up2 == 2 ? (cuuint64_t)64 * g.cin : up ? (cuuint64_t)48 * g.cin : (cuuint64_t)g.ktot();
     const cuuint64_t dims[2] = {ktot, (cuuint64_t)g.cout};
     const cuuint64_t strides[1] = {ktot * 2};
     const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(cta2 ? p.block_n / 2 : p.block_n)};
     const cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_tc.encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)g.W, dims, strides, box, estr,
+    CUresult r = g_tc.encode(half ? &map_b2 : &map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)(half ? g.W_lo : g.W), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ECHO_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
@@ -1030,9 +1081,10 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
   const int msub = plan.msub;
   const int tiles = p.vm_tiles / msub * p.num_n_tiles * p.splitk;   // CTA tiles
   const int b_rows = cta2 ? p.block_n / 2 : p.block_n;
-  p.stages = stages_for(b_rows, msub);
-  ECHO_CHECK(p.stages >= 2, "gemm_tc: tile does not fit shared memory");
-  const int smem_bytes = p.stages * (msub * A_STAGE_BYTES + b_rows * BLOCK_K * 2) + SMEM_FIXED;
+  if (!x3) { map_a2 = map_a; map_b2 = map_b; }
+  p.stages = stages_for(b_rows, msub, x3);
+  ECHO_CHECK(p.stages >= 2 && (!x3 || msub == 1), "gemm_tc: tile does not fit shared memory");
+  const int smem_bytes = p.stages * (x3 ? 2 : 1) * (msub * A_STAGE_BYTES + b_rows * BLOCK_K * 2) + SMEM_FIXED;
   const bool probed = g_probe.on && g.rows_out() == g_probe.rows && g.cin == g_probe.cin && g.cout == g_probe.cout && g.kd == g_probe.k &&
                       !g.up2 && g.sh == 1;
   if (probed && g_probe.timeline) { p.dbg = g_probe.timeline; g_probe.timeline = nullptr; }
@@ -1062,12 +1114,14 @@ void gemm_tc(const GemmArgs& g, cudaStream_t s) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    if (msub == 2) ECHO_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, 2>, map_a, map_b, p));
-    else ECHO_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, 1>, map_a, map_b, p));
+    if (x3) ECHO_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, 1, true>, map_a, map_b, map_a2, map_b2, p));
+    else if (msub == 2) ECHO_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, 2, false>, map_a, map_b, map_a2, map_b2, p));
+    else ECHO_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, 1, false>, map_a, map_b, map_a2, map_b2, p));
   } else {
     const int grid = tiles < g_tc.sms ? tiles : g_tc.sms;
-    if (msub == 2) launch_pdl(gemm_tc_kernel<false, 2>, dim3(grid), dim3(NUM_THREADS), smem_bytes, s, map_a, map_b, p);
-    else launch_pdl(gemm_tc_kernel<false, 1>, dim3(grid), dim3(NUM_THREADS), smem_bytes, s, map_a, map_b, p);
+    if (x3) launch_pdl(gemm_tc_kernel<false, 1, true>, dim3(grid), dim3(NUM_THREADS), smem_bytes, s, map_a, map_b, map_a2, map_b2, p);
+    else if (msub == 2) launch_pdl(gemm_tc_kernel<false, 2, false>, dim3(grid), dim3(NUM_THREADS), smem_bytes, s, map_a, map_b, map_a2, map_b2, p);
+    else launch_pdl(gemm_tc_kernel<false, 1, false>, dim3(grid), dim3(NUM_THREADS), smem_bytes, s, map_a, map_b, map_a2, map_b2, p);
   }
   ECHO_LAUNCH_CHECK();
   if (probed) ECHO_CUDA(cudaEventRecord(g_probe.ev[g_probe.used++].second, s));

@@ -7,10 +7,13 @@
 // What remains is a chain of ~150 few-row contractions (rows = nodes) bound by streaming ~115 M live weights from
 // HBM once per step, plus GroupNorm/LayerNorm/GEGLU over (N, C) rows; the only cross-object coupling is the echo
 // GCN.  Activations are fp32 row-major (N, C) throughout; ECHO_PREC_BF16 streams bf16 copies of the weights.
+#include "layout_mk.cuh"
 #include "unet.cuh"
 
 #include <math.h>
 #include <stdlib.h>
+
+#include <deque>
 
 using namespace echo;
 
@@ -48,10 +51,35 @@ struct echo_layout {
   // the stacked emb_layers projection (46 M weights, the largest layer of the step) depends on the time embedding only,
   // so it runs on a second stream beside the GCN chain and joins at the first ResBlock (a parallel branch of the graph)
   cudaStream_t side = nullptr;
+  cudaStream_t cap = nullptr;   // capture origin of the replayed graph: independent of the caller's stream (legacy stream 0 cannot capture)
+  int64_t graph_replays = 0;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int N = 0;   // rows of the current call
 
+  // ---- persistent executor (layout_mk.cu): the step recorded as a program of stages, one cooperative kernel per iteration ----
+  bool mk_ok = false;
+  int mk_ctas = 0;
+  int mk_N = -1, mk_T = -1;
+  std::vector<MkOp> mk_ops;
+  std::vector<MkStage> mk_stages;
+  MkOp* d_mk_ops = nullptr;
+  MkStage* d_mk_stages = nullptr;
+  unsigned* d_mk_counters = nullptr;   // [MK_MAX_STAGES] stage counters, [MK_MAX_BG] background counters, [1] epoch
+  std::vector<float*> mk_bufs;         // activation buffers of the program, allocated once at capacity in program order
+  size_t mk_buf_i = 0;
+  int64_t mk_steps = 0;
+  static constexpr int MK_MAX_STAGES = 512, MK_MAX_BG = 64, MK_MAX_OPS = 1024;
+
   float* buf(int C) { return arena.alloc_n<float>((size_t)N * C); }
+  float* mkb(int C) {
+    if (mk_buf_i < mk_bufs.size()) return mk_bufs[mk_buf_i++];
+    float* b = pool.alloc_n<float>((size_t)d.max_nodes * C);
+    mk_bufs.push_back(b);
+    ++mk_buf_i;
+    return b;
+  }
+  void build_mk(int Nn, int T);
+  void step_mk(const echo_graph* g, const float* x_t, const float* obj_embed, int t, const float* noise, float* x_prev, cudaStream_t s);
 
   // input of a fused Linear: (possibly concatenated) rows + the elementwise op that precedes the Linear in the network
   struct In {
@@ -213,6 +241,298 @@ struct echo_layout {
   }
 };
 
+// ---- the step as a program for the persistent executor -------------------------------------------------------------------
+// Same network walk as forward() above (same fused weights, same prologue/epilogue assignment), with three differences that the
+// single kernel makes possible: every row of the time path is the same (one timestep per step), so time_embed / emb_layers /
+// box_time_emb are computed for ONE row; the GraphTripleConv gather-combine and mean pooling are prologues of the Linear that
+// consumes them; the posterior update is the epilogue of the out conv.
+void echo_layout::build_mk(int Nn, int T) {
+  mk_ops.clear();
+  mk_stages.clear();
+  mk_buf_i = 0;
+  const int mc = d.model_channels, E = 4 * mc, gd = d.gconv_dim, od = d.obj_embed_dim, ctx = d.context_dim;
+  const int nd = od + gd + (d.enable_t_emb ? gd : 0);
+  std::vector<MkOp> A, B;
+  int bg_wait = -1, bg_arrive = -1;
+  struct Chunk { MkOp op; int id; };
+  std::deque<Chunk> pending;   // emb_layers projections waiting for a stage to ride in the shadow of
+  auto flush = [&]() {
+    if (A.empty() && B.empty()) return;
+    if ((int)mk_stages.size() >= 2 && !pending.empty()) {   // emb exists after stage 1 (time_embed.2)
+      B.push_back(pending.front().op);
+      bg_arrive = pending.front().id;
+      pending.pop_front();
+    }
+    MkStage st;
+    memset(&st, 0, sizeof(st));
+    st.op_begin = (int)mk_ops.size(); st.n_a = (int)A.size(); st.n_b = (int)B.size();
+    st.bg_wait = bg_wait; st.bg_arrive = B.empty() ? -1 : bg_arrive;
+    ECHO_CHECK(st.n_a + st.n_b <= MK_MAX_STAGE_OPS, "layout program: too many ops in one stage");
+    int ub = 0;
+    for (auto* v : {&A, &B})
+      for (auto& o : *v) {
+        mk_plan_op(o, mk_ctas);
+        o.unit_begin = ub;
+        ub += o.units;
+        mk_ops.push_back(o);
+      }
+    mk_stages.push_back(st);
+    A.clear(); B.clear();
+    bg_wait = -1; bg_arrive = -1;
+  };
+  auto base_op = [&](int M, int K, int nout, const float* X, int64_t ldx, const float* W, const float* bias, float* Y, int64_t ldy) {
+    MkOp o;
+    memset(&o, 0, sizeof(o));
+    o.type = MK_T_LIN; o.M = M; o.K = K; o.nout = nout; o.X = X; o.ldx = ldx; o.W = W; o.bias = bias; o.Y = Y; o.ldy = ldy;
+    o.eps = 1e-5f;
+    return o;
+  };
+  auto lin_in = [&](const In& in, const ConvW& w, float* Y, int64_t ldy, const float* res, int64_t ld_res, int act) {
+    ECHO_CHECK((in.pro == PRO_GEGLU ? in.C : in.width()) == w.cin, "layout program: linear input width %d != %d", in.width(), w.cin);
+    MkOp o = base_op(Nn, w.cin, w.cout, in.X, in.ld ? in.ld : (in.pro == PRO_GEGLU ? 2 * in.C : in.C), w.w, w.b, Y, ldy);
+    if (in.X2) { o.X2 = in.X2; o.ldx2 = in.C2; o.K1 = in.C; }
+    o.pro = in.pro == PRO_GN ? MK_GN : in.pro == PRO_LN ? MK_LN : in.pro == PRO_GEGLU ? MK_GEGLU : in.pro == PRO_SILU ? MK_SILU : MK_NONE;
+    if (in.nw) { o.gamma = in.nw->g; o.beta = in.nw->b; }
+    o.eps = in.eps; o.pro_act = in.silu ? 1 : 0;
+    if (in.pro == PRO_GN) o.cpg = in.width() / 32;
+    o.res = res; o.ld_res = ld_res; o.act = act;
+    return o;
+  };
+
+  // ---- stage 0: time_embed.0 on the sinusoidal row, node features that do not need the time MLP, predicate rows, conv_in ----
+  {
+    MkOp o = base_op(1, mc, E, nullptr, mc, plan.time0.w, plan.time0.b, e1, E);
+    o.pro = MK_TEMB; o.act = 2;
+    A.push_back(o);
+    MkOp c;
+    memset(&c, 0, sizeof(c));
+    c.type = MK_T_COPY; c.M = Nn; c.K = od; c.x_ext = MK_EXT_OBJ; c.ldx = od; c.Y = node; c.ldy = nd;
+    A.push_back(c);
+    MkOp b = base_op(Nn, d.in_channels, gd, nullptr, d.in_channels, box_emb.w, box_emb.b, node + od, nd);
+    b.x_ext = MK_EXT_XT;
+    A.push_back(b);
+    if (T > 0) {
+      MkOp e;
+      memset(&e, 0, sizeof(e));
+      e.type = MK_T_EMBROWS; e.M = T; e.K = 2 * gd; e.aux0 = pred_table; e.Y = pred; e.ldy = 2 * gd;
+      A.push_back(e);
+    }
+  }
+  float* h0 = nullptr;
+  {
+    const BlockW& b0 = plan.in_blocks[0];
+    ECHO_CHECK(b0.kind == BlockW::CONV_IN, "layout program: first block must be the input conv");
+    h0 = mkb(b0.conv.cout);
+    MkOp o = base_op(Nn, d.in_channels, b0.conv.cout, nullptr, d.in_channels, b0.conv.w, b0.conv.b, h0, b0.conv.cout);
+    o.x_ext = MK_EXT_XT;
+    A.push_back(o);
+  }
+  flush();
+  // ---- stage 1: time_embed.2 ----
+  A.push_back(base_op(1, E, E, e1, E, plan.time2.w, plan.time2.b, emb, E));
+  flush();
+  // the emb_layers projections of all ResBlocks, one background op each, in consumption order (plan.emb_stack rows)
+  std::vector<std::pair<int, int>> res_chunks;   // (emb_off, cout) per ResBlock in forward order
+  {
+    auto add = [&](const ResW& r) { res_chunks.push_back({r.emb_off, r.cout}); };
+    for (auto& b : plan.in_blocks) if (b.kind == BlockW::RES) add(b.res);
+    add(plan.mid0); add(plan.mid2);
+    for (auto& b : plan.out_blocks) add(b.res);
+    ECHO_CHECK((int)res_chunks.size() <= MK_MAX_BG, "layout program: too many ResBlocks");
+    for (size_t j = 0; j < res_chunks.size(); ++j) {
+      const int off = res_chunks[j].first, co = res_chunks[j].second;
+      MkOp o = base_op(1, E, co, emb, E, plan.emb_stack.w + (size_t)off * E, plan.emb_stack.b + off, embout + off, plan.emb_total);
+      o.pro = MK_SILU;
+      pending.push_back({o, (int)j});
+    }
+  }
+  int res_counter = 0;   // index of the next ResBlock in forward order == its background counter
+  // ---- stage 2: box_time_emb -> every node row ----
+  if (d.enable_t_emb) {
+    MkOp o = base_op(1, E, gd, emb, E, time_emb_lin.w, time_emb_lin.b, node + od + gd, nd);
+    o.bcast_rows = Nn;
+    A.push_back(o);
+    flush();
+  }
+  // ---- echo GCN: 4 stages per layer ----
+  {
+    const int H = gcn.H, dp = gcn.dp;
+    const float* cur_obj = node;
+    const float* cur_pred = pred;
+    for (size_t li = 0; li < gcn.layers.size(); ++li) {
+      const GcnLayer& L = gcn.layers[li];
+      const bool lastl = li + 1 == gcn.layers.size();
+      float* nobj = lastl ? latent : gcn.obj_pp[li & 1];
+      float* npred = gcn.pred_pp[li & 1];
+      A.push_back(base_op(Nn, L.din, 2 * H, cur_obj, L.din, L.w_so.w, nullptr, gcn.pso, 2 * H));
+      if (T > 0) {
+        MkOp o = base_op(T, dp, H, cur_pred, dp, L.w_p.w, nullptr, gcn.pp, H);
+        A.push_back(o);
+      }
+      if (L.residual) A.push_back(base_op(Nn, L.din, L.dout, cur_obj, L.din, L.proj.w, L.proj.b, gcn.proj, L.dout));
+      flush();
+      if (T > 0) {
+        MkOp o = base_op(T, H, 2 * H + dp, gcn.pso, 2 * H, L.w2.w, L.w2.b, gcn.t2, 2 * H + dp);
+        o.pro = MK_EDGE; o.aux0 = gcn.pp; o.aux1 = L.b1; o.act = 1;
+        A.push_back(o);
+        flush();
+      }
+      {
+        MkOp o = base_op(Nn, H, H, gcn.t2, 2 * H + dp, L.w3.w, L.w3.b, gcn.n1, H);
+        o.pro = MK_POOL; o.aux_i = H + dp; o.act = 1;
+        A.push_back(o);
+      }
+      if (T > 0 && !lastl) {   // the last layer's predicate output is never read (denoise_net.py:766)
+        if (L.residual) {
+          MkOp o = base_op(T, dp, dp, cur_pred, dp, L.projp.w, L.projp.b, npred, dp);
+          o.res = gcn.t2 + H; o.ld_res = 2 * H + dp;
+          A.push_back(o);
+        } else {
+          MkOp c;
+          memset(&c, 0, sizeof(c));
+          c.type = MK_T_COPY; c.M = T; c.K = dp; c.X = gcn.t2 + H; c.ldx = 2 * H + dp; c.Y = npred; c.ldy = dp;
+          A.push_back(c);
+        }
+      }
+      flush();
+      {
+        MkOp o = base_op(Nn, H, L.dout, gcn.n1, H, L.w4.w, L.w4.b, nobj, L.dout);
+        o.act = 1;
+        if (L.residual) { o.res = gcn.proj; o.ld_res = L.dout; }
+        A.push_back(o);
+      }
+      flush();
+      cur_obj = nobj;
+      cur_pred = npred;
+    }
+  }
+  // ---- all 11 attn2 = to_out(to_v(latent)) vectors ----
+  A.push_back(base_op(Nn, ctx, a2_total, latent, ctx, attn2_fused.w, attn2_fused.b, a2vec, a2_total));
+  flush();
+  // ---- trunk ----
+  auto res_block = [&](const In& x, const ResW& r) -> float* {
+    float* out = mkb(r.cout);
+    float* h1 = mkb(r.cout);
+    In a1 = x; a1.pro = PRO_GN; a1.nw = &r.n1; a1.eps = 1e-5f; a1.silu = true;
+    bg_wait = res_counter++;
+    A.push_back(lin_in(a1, r.c1, h1, r.cout, embout + r.emb_off, 0 /* one row for all nodes */, 0));
+    const float* skip = x.X;
+    if (r.has_skip) {
+      float* sk = mkb(r.cout);
+      A.push_back(lin_in(x, r.skip, sk, r.cout, nullptr, 0, 0));
+      skip = sk;
+    } else {
+      ECHO_CHECK(!x.X2, "layout: identity skip over a concatenated input");
+    }
+    flush();
+    In a2 = plain(h1, r.cout); a2.pro = PRO_GN; a2.nw = &r.n2; a2.eps = 1e-5f; a2.silu = true;
+    A.push_back(lin_in(a2, r.c2, out, r.cout, skip, r.cout, 0));
+    flush();
+    return out;
+  };
+  auto transformer = [&](const float* x, const AttnW& at, int ai) -> float* {
+    const int C = at.C;
+    float* out = mkb(C);
+    float* t0 = mkb(C);
+    float* t1 = mkb(C);
+    float* f1 = mkb(8 * C);
+    float* t2 = mkb(C);
+    In xn = plain(x, C); xn.pro = PRO_GN; xn.nw = &at.norm; xn.eps = 1e-6f;
+    A.push_back(lin_in(xn, at.proj_in, t0, C, nullptr, 0, 0));
+    flush();
+    In l1 = plain(t0, C); l1.pro = PRO_LN; l1.nw = &at.ln1;
+    {
+      MkOp o = lin_in(l1, attn1_fused[ai], t1, C, t0, C, 0);
+      o.res2 = a2vec + a2_off[ai]; o.ld_res2 = a2_total;
+      A.push_back(o);
+    }
+    flush();
+    In l3 = plain(t1, C); l3.pro = PRO_LN; l3.nw = &at.ln3;
+    A.push_back(lin_in(l3, at.ff1, f1, 8 * C, nullptr, 0, 0));
+    flush();
+    In gg = plain(f1, 4 * C); gg.pro = PRO_GEGLU;
+    A.push_back(lin_in(gg, at.ff2, t2, C, t1, C, 0));
+    flush();
+    A.push_back(lin_in(plain(t2, C), at.proj_out, out, C, x, C, 0));
+    flush();
+    return out;
+  };
+  std::vector<std::pair<const float*, int>> hs;
+  const float* h = h0;
+  int hc = plan.in_blocks[0].conv.cout, ai = 0;
+  hs.push_back({h, hc});
+  for (size_t bi = 1; bi < plan.in_blocks.size(); ++bi) {
+    const BlockW& b = plan.in_blocks[bi];
+    if (b.kind == BlockW::RES) {
+      h = res_block(plain(h, hc), b.res); hc = b.res.cout;
+      if (b.attn) h = transformer(h, b.at, ai++);
+    } else {
+      float* o = mkb(b.conv.cout);
+      A.push_back(lin_in(plain(h, hc), b.conv, o, b.conv.cout, nullptr, 0, 0));
+      flush();
+      h = o; hc = b.conv.cout;
+    }
+    hs.push_back({h, hc});
+  }
+  h = res_block(plain(h, hc), plan.mid0);
+  h = transformer(h, plan.mid_at, ai++);
+  h = res_block(plain(h, plan.mid0.cout), plan.mid2);
+  hc = plan.mid2.cout;
+  for (auto& b : plan.out_blocks) {
+    auto sk = hs.back();
+    hs.pop_back();
+    In cat = plain(h, hc);
+    cat.X2 = sk.first; cat.C2 = sk.second;
+    h = res_block(cat, b.res); hc = b.res.cout;
+    if (b.attn) h = transformer(h, b.at, ai++);
+    if (b.up) {
+      float* o = mkb(b.conv.cout);
+      A.push_back(lin_in(plain(h, hc), b.conv, o, b.conv.cout, nullptr, 0, 0));
+      flush();
+      h = o; hc = b.conv.cout;
+    }
+  }
+  {
+    In hn = plain(h, hc); hn.pro = PRO_GN; hn.nw = &plan.out_norm; hn.eps = 1e-5f; hn.silu = true;
+    MkOp o = lin_in(hn, plan.out_conv, nullptr, d.out_channels, nullptr, 0, 0);
+    o.epi = MK_EPI_DDPM; o.y_ext = MK_EXT_XPREV;
+    A.push_back(o);
+    flush();
+  }
+  ECHO_CHECK(pending.empty(), "layout program: %d emb_layers projections were never scheduled", (int)pending.size());
+  ECHO_CHECK((int)mk_stages.size() <= MK_MAX_STAGES && (int)mk_ops.size() <= MK_MAX_OPS, "layout program too long (%d stages, %d ops)",
+             (int)mk_stages.size(), (int)mk_ops.size());
+  mk_N = Nn;
+  mk_T = T;
+}
+
+void echo_layout::step_mk(const echo_graph* g, const float* x_t, const float* obj_embed, int t, const float* noise, float* x_prev,
+                          cudaStream_t s) {
+  const int Nn = g->n_nodes, T = g->n_triples;
+  if (Nn != mk_N || T != mk_T) {
+    build_mk(Nn, T);
+    // a new program renumbers the stages: restart the counters (stream-ordered behind the previous program's last launch)
+    ECHO_CUDA(cudaMemsetAsync(d_mk_counters, 0, sizeof(unsigned) * (MK_MAX_STAGES + MK_MAX_BG + 2), s));
+    ECHO_CUDA(cudaMemcpyAsync(d_mk_ops, mk_ops.data(), sizeof(MkOp) * mk_ops.size(), cudaMemcpyHostToDevice, s));
+    ECHO_CUDA(cudaMemcpyAsync(d_mk_stages, mk_stages.data(), sizeof(MkStage) * mk_stages.size(), cudaMemcpyHostToDevice, s));
+    ECHO_CUDA(cudaStreamSynchronize(s));   // the host vectors may be rebuilt before an asynchronous copy would have read them
+  }
+  MkArgs a;
+  memset(&a, 0, sizeof(a));
+  a.ops = d_mk_ops; a.stages = d_mk_stages; a.n_stages = (int)mk_stages.size();
+  static const int max_stages = getenv("ECHO_MK_MAX_STAGES") ? atoi(getenv("ECHO_MK_MAX_STAGES")) : 0;   // debugging: run a prefix
+  if (max_stages > 0 && max_stages < a.n_stages) a.n_stages = max_stages;
+  a.bar = d_mk_counters; a.bg = d_mk_counters + MK_MAX_STAGES; a.epoch = d_mk_counters + MK_MAX_STAGES + MK_MAX_BG;
+  a.err = a.epoch + 1;
+  a.x_t = x_t; a.obj_embed = obj_embed; a.noise = noise; a.x_prev = x_prev;
+  a.t = t; a.tab = d_tab; a.T = d.time_num; a.freqs = freqs; a.temb_dim = d.model_channels;
+  a.s_idx = g->s_idx; a.o_idx = g->o_idx; a.node_off = g->node_off; a.node_items = g->node_items;
+  a.triples = (const long long*)g->triples;
+  a.H = gcn.H;
+  mk_launch(a, mk_ctas, s);
+  ++mk_steps;
+}
+
 namespace echo {
 
 // get_betas('linear') = np.linspace(b0, b1, T) float64 (diffusion_ddpm.py:38-40); tables as fp32 torch ops (:133-162).
@@ -346,6 +666,7 @@ echo_layout* layout_create(const echo_layout_desc_t* desc, const echo_weight_t* 
       for (auto& b : h->plan.out_blocks) if (b.attn) add(b.at);
     }
     ECHO_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    ECHO_CUDA(cudaStreamCreateWithFlags(&h->cap, cudaStreamNonBlocking));
     ECHO_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     ECHO_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     {   // fused attention matrices (see the member comments): products in fp32 on the device, bf16 copies in bf16 mode
@@ -387,6 +708,16 @@ echo_layout* layout_create(const echo_layout_desc_t* desc, const echo_weight_t* 
       h->attn2_fused.wb = bf ? to_bf16(w2, (size_t)h->a2_total * ctx) : nullptr;
       ECHO_CUDA(cudaStreamSynchronize(s0));
     }
+    {   // persistent executor (layout_mk.cu)
+      static const bool no_mk = getenv("ECHO_NO_MK") != nullptr;
+      h->mk_ok = !no_mk && mk_available(&h->mk_ctas) && d.in_channels == d.out_channels && d.model_channels % 2 == 0;
+      if (h->mk_ok) {
+        h->d_mk_ops = (MkOp*)h->pool.alloc(sizeof(MkOp) * echo_layout::MK_MAX_OPS);
+        h->d_mk_stages = (MkStage*)h->pool.alloc(sizeof(MkStage) * echo_layout::MK_MAX_STAGES);
+        h->d_mk_counters = (unsigned*)h->pool.alloc(sizeof(unsigned) * (echo_layout::MK_MAX_STAGES + echo_layout::MK_MAX_BG + 2));
+        ECHO_CUDA(cudaMemset(h->d_mk_counters, 0, sizeof(unsigned) * (echo_layout::MK_MAX_STAGES + echo_layout::MK_MAX_BG + 2)));
+      }
+    }
     // workspace: every block output is (N, <= 2*mc*max_mult) fp32; ~60 live buffers is a generous bound
     int maxmult = 1;
     for (int i = 0; i < d.num_levels; ++i) maxmult = d.channel_mult[i] > maxmult ? d.channel_mult[i] : maxmult;
@@ -406,6 +737,7 @@ echo_layout* layout_create(const echo_layout_desc_t* desc, const echo_weight_t* 
 void layout_destroy(echo_layout* h) {
   if (!h) return;
   if (h->side) cudaStreamDestroy(h->side);
+  if (h->cap) cudaStreamDestroy(h->cap);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->gexec) cudaGraphExecDestroy(h->gexec);
@@ -457,6 +789,17 @@ __global__ void layout_copy_out_kernel(const float* __restrict__ src, float* __r
 }
 }  // namespace
 
+int g_layout_mode = 0;   // echo_debug_set_layout_mode: 0 = automatic, 1 = never the persistent executor (per-layer kernels / graph replay)
+void set_layout_mode(int m) { g_layout_mode = m; }
+// {persistent-executor steps, graph replays, program stages, program ops, kernels inside the replayed graph, executor CTAs;
+//  negative CTA count: the executor's barrier watchdog fired (synchronises the device to read the flag)}
+void layout_info(const echo_layout* h, int64_t* out6) {
+  unsigned err = 0;
+  if (h->mk_ok) ECHO_CUDA(cudaMemcpy(&err, h->d_mk_counters + echo_layout::MK_MAX_STAGES + echo_layout::MK_MAX_BG + 1, sizeof(err), cudaMemcpyDeviceToHost));
+  out6[0] = h->mk_steps; out6[1] = h->graph_replays; out6[2] = (int64_t)h->mk_stages.size(); out6[3] = (int64_t)h->mk_ops.size();
+  out6[4] = h->graph_launches; out6[5] = h->mk_ok ? (err ? -h->mk_ctas : h->mk_ctas) : 0;
+}
+
 void layout_step(echo_layout* h, const echo_graph* g, const float* x_t, const float* obj_embed, int t, const float* noise, float* x_prev,
                  cudaStream_t s) {
   ECHO_CHECK(t >= 0 && t < h->d.time_num, "layout_step: t=%d outside [0, %d)", t, h->d.time_num);
@@ -464,6 +807,14 @@ void layout_step(echo_layout* h, const echo_graph* g, const float* x_t, const fl
   const int N = g->n_nodes, nx = N * h->d.out_channels, nobj = N * h->d.obj_embed_dim;
   if (N == 0) return;
   ECHO_CHECK(N <= h->d.max_nodes && h->d.in_channels == h->d.out_channels, "layout_step: graph exceeds handle capacity");
+  // the persistent executor: one cooperative kernel per iteration (few-row graphs; larger batches keep the per-layer kernels)
+  if (h->mk_ok && g_layout_mode != 1 && N <= 64 && g->n_triples <= 512) {
+    ECHO_CHECK(g->n_triples == 0 || (g->p_min >= 0 && g->p_max < h->pred_rows), "layout: predicate ids [%lld, %lld] outside pred_embeddings (%d rows)",
+               (long long)g->p_min, (long long)g->p_max, h->pred_rows);
+    ECHO_CHECK(g->n_triples <= h->d.max_triples, "layout_step: graph exceeds handle capacity");
+    h->step_mk(g, x_t, obj_embed, t, noise, x_prev, s);
+    return;
+  }
   static const bool no_graph = getenv("ECHO_NO_GRAPH") != nullptr;
   if (no_graph || h->graph_failed) {
     fill_i64(h->t_dev, N, t, s);
@@ -478,28 +829,28 @@ void layout_step(echo_layout* h, const echo_graph* g, const float* x_t, const fl
     if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
     cudaGraph_t graph = nullptr;
     const int64_t before = g_launches;
-    cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+    cudaError_t e = cudaStreamBeginCapture(h->cap, cudaStreamCaptureModeThreadLocal);
     if (e == cudaSuccess) {
       try {
-        layout_fill_t_kernel<<<cdiv(N, 128), 128, 0, s>>>(h->t_slot, h->t_dev, N);
+        layout_fill_t_kernel<<<cdiv(N, 128), 128, 0, h->cap>>>(h->t_slot, h->t_dev, N);
         ECHO_LAUNCH_CHECK();
-        h->forward(g, h->sx, h->sobj, h->t_dev, h->eps, s);
-        layout_ddpm_update_kernel<<<cdiv(nx, 128), 128, 0, s>>>(h->sx, h->eps, h->snoise, h->d_tab, h->d.time_num, h->t_slot, nx, h->sout);
+        h->forward(g, h->sx, h->sobj, h->t_dev, h->eps, h->cap);
+        layout_ddpm_update_kernel<<<cdiv(nx, 128), 128, 0, h->cap>>>(h->sx, h->eps, h->snoise, h->d_tab, h->d.time_num, h->t_slot, nx, h->sout);
         ECHO_LAUNCH_CHECK();
       } catch (...) {
-        cudaStreamEndCapture(s, &graph);
+        cudaStreamEndCapture(h->cap, &graph);
         if (graph) cudaGraphDestroy(graph);
         cudaGetLastError();
         throw;
       }
-      e = cudaStreamEndCapture(s, &graph);
+      e = cudaStreamEndCapture(h->cap, &graph);
     }
     if (e == cudaSuccess && graph) e = cudaGraphInstantiate(&h->gexec, graph, 0);
     if (graph) cudaGraphDestroy(graph);
-    if (e != cudaSuccess || !h->gexec) {   // capture unavailable on this stream: run the kernels directly from now on
+    if (e != cudaSuccess || !h->gexec) {   // capture / instantiation failed: run the kernels directly (retried on the next graph)
       cudaGetLastError();
       h->gexec = nullptr;
-      h->graph_failed = true;
+      h->gkey_id = 0;
       fill_i64(h->t_dev, N, t, s);
       h->forward(g, x_t, obj_embed, h->t_dev, h->eps, s);
       ddpm_update(x_t, h->eps, noise, h->d_tab, h->d.time_num, t, (int64_t)nx, x_prev, s);
@@ -511,6 +862,7 @@ void layout_step(echo_layout* h, const echo_graph* g, const float* x_t, const fl
     h->gkey_n = N;
   }
   ECHO_CUDA(cudaGraphLaunch(h->gexec, s));
+  ++h->graph_replays;
   count_launch((int)h->graph_launches);
   layout_copy_out_kernel<<<cdiv(nx, 128), 128, 0, s>>>(h->sout, x_prev, nx);
   ECHO_LAUNCH_CHECK();

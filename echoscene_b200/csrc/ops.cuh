@@ -45,6 +45,10 @@ struct GemmArgs {
   float* colsum = nullptr;          // tcgen05 path: per-column (sum, sumsq) partials, gemm_tc_colsum_rows() x cout x 2 floats
   void* scratch = nullptr;          // tcgen05 path, stride-2 convs: room for a space-to-depth copy of A (same bytes)
   void* splitk_ws = nullptr;        // tcgen05 path: gemm_tc_splitk_ws_bytes() of scratch lets the plan split K over tap groups
+  // tcgen05 path, split precision (ECHO_PREC_X3): A / W are the HIGH bf16 halves, these the LOW halves (x = hi + lo, split_bf16());
+  // three MMAs per k-step into one fp32 accumulator.  Stride-2 convs need `scratch` for a space-to-depth copy of BOTH halves.
+  const void* A_lo = nullptr;
+  const void* W_lo = nullptr;
   int64_t rows_out() const { return (int64_t)n * od * oh * ow; }
   int ktot() const { return kd * kh * kw * cin; }
 };
@@ -135,6 +139,8 @@ void ncdhw_to_cl_pad16(const float* x, int n, int c, int64_t voxels, __nv_bfloat
 // x channels-last with row stride ld (>= c) -> out (n, c, voxels)
 void cl_to_ncdhw(const void* x, DT xdt, int n, int c, int64_t voxels, int ld, float* out, cudaStream_t s);
 void convert(const void* x, DT xdt, void* y, DT ydt, int64_t count, cudaStream_t s);
+// x (fp32) -> hi = bf16(x), lo = bf16(x - hi): the operand format of the split-precision tcgen05 contraction; count % 4 == 0
+void split_bf16(const float* x, int64_t count, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t s);
 // y = x * sigmoid(x) (the SiLU in front of every ResBlock's emb_layers Linear, applied once to the shared time embedding)
 void silu_f32(const float* x, float* y, int64_t count, cudaStream_t s);
 // y[r, :] += v[r / rows_per_obj, :]

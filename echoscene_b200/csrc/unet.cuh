@@ -7,6 +7,7 @@ namespace echo {
 struct ConvW {   // repacked [cout][taps][cin] (K index = tap*cin + c); linear layers have taps == 1
   const float* w = nullptr;
   const __nv_bfloat16* wb = nullptr;
+  const __nv_bfloat16* wb_lo = nullptr;   // split-precision mode: wb = bf16(w), wb_lo = bf16(w - wb)
   const float* b = nullptr;
   int cout = 0, cin = 0, taps = 1;
 };
@@ -67,6 +68,7 @@ struct UNetCfg {
   std::vector<int> channel_mult, attention_resolutions;
   int num_res_blocks = 2, num_heads = 8, context_dim = 1280;
   bool want_bf16 = false;
+  bool want_x3 = false;   // hi/lo bf16 copies of the trunk's contraction weights (ECHO_PREC_X3), no layout-changing repacks
 };
 
 // Walks the reference constructor order (openai_model_3d.py:563-728 / denoise_net.py:553-713) and prepares

@@ -18,6 +18,15 @@ struct Prep {
     convert(w, F32, o, BF16, (int64_t)n, s);
     return o;
   }
+  // split-precision copies of a contraction weight
+  void to_x3(ConvW& c, size_t n) {
+    if (!cfg.want_x3 || n % 4) return;
+    __nv_bfloat16* hi = pool.alloc_n<__nv_bfloat16>(n);
+    __nv_bfloat16* lo = pool.alloc_n<__nv_bfloat16>(n);
+    split_bf16(c.w, (int64_t)n, hi, lo, s);
+    c.wb = hi;
+    c.wb_lo = lo;
+  }
   const float* copy_vec(const std::string& name, int n) {
     const WView& v = wm.get(name, {n});
     float* o = pool.alloc_n<float>(n);
@@ -53,6 +62,7 @@ struct Prep {
       c.w = o;
     }
     c.wb = to_bf16(c.w, n_el * c.taps);
+    to_x3(c, n_el * c.taps);
     c.b = copy_vec(p + ".bias", cout);
     return c;
   }
@@ -66,11 +76,12 @@ struct Prep {
     ECHO_CUDA(cudaMemcpyAsync(o, v.p, sizeof(float) * cout * cin, cudaMemcpyDeviceToDevice, s));
     c.w = o;
     c.wb = to_bf16(o, (size_t)cout * cin);
+    if (cfg.dims == 3) to_x3(c, (size_t)cout * cin);
     if (bias) c.b = copy_vec(p + ".bias", cout);
     return c;
   }
   // rows of several [cout_i, K] matrices stacked into one [sum, K]
-  ConvW stack(const std::vector<std::pair<std::string, int>>& items, int K, bool bias) {
+  ConvW stack(const std::vector<std::pair<std::string, int>>& items, int K, bool bias, bool x3 = false) {
     int total = 0;
     for (auto& it : items) total += it.second;
     ConvW c;
@@ -91,6 +102,7 @@ struct Prep {
     c.w = o;
     c.b = b;
     c.wb = to_bf16(o, (size_t)total * K);
+    if (x3) to_x3(c, (size_t)total * K);   // the stacked attn1 q/k/v (token-wise); emb / attn2.to_v stacks stay few-row fp32
     return c;
   }
 
@@ -127,7 +139,7 @@ struct Prep {
     a.ln1 = norm(b + "norm1", C);
     a.ln3 = norm(b + "norm3", C);
     if (cfg.dims == 3) {
-      a.qkv = stack({{b + "attn1.to_q", C}, {b + "attn1.to_k", C}, {b + "attn1.to_v", C}}, C, false);
+      a.qkv = stack({{b + "attn1.to_q", C}, {b + "attn1.to_k", C}, {b + "attn1.to_v", C}}, C, false, true);
       const int dhp = attention_pad_dh(a.dh);
       if (cfg.want_bf16 && dhp) {   // head-padded copy for the flash kernel: row (m*heads + h)*dhp + d <- row m*C + h*dh + d
         const size_t rows = (size_t)3 * a.heads * dhp;

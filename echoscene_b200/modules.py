@@ -423,7 +423,7 @@ class UNet1DModel(_SpecModule):
         d.num_res_blocks, d.num_heads, d.context_dim = c.num_res_blocks, c.num_heads, c.crossattn_dim
         d.obj_embed_dim, d.gconv_dim, d.enable_t_emb = c.obj_embed_dim, c.gconv_dim, int(c.enable_t_emb)
         d.max_nodes, d.max_triples = cap
-        d.precision = _lib.PREC_BF16 if self.precision == "bf16" else _lib.PREC_FP32
+        d.precision = _lib.precision_code(self.precision)
         d.time_num, d.beta_start, d.beta_end = self.time_num, self.beta_start, self.beta_end
         dev = next(self.parameters()).device
         arr, n, keep = _lib.weights_table(self.state_dict(),
@@ -541,7 +541,7 @@ class UNet3DModel(_SpecModule):
         d.num_res_blocks, d.num_heads, d.context_dim = c.num_res_blocks, c.num_heads, c.context_dim
         d.gconv_dim, d.enable_t_emb, d.latent_size = c.gconv_dim, int(c.enable_t_emb), c.image_size
         d.max_nodes, d.max_triples, d.max_local_nodes = cap
-        d.precision = _lib.PREC_BF16 if self.precision == "bf16" else _lib.PREC_FP32
+        d.precision = _lib.precision_code(self.precision)
         d.timesteps, d.ddim_steps = self.timesteps_total, self.ddim_steps
         d.linear_start, d.linear_end = self.linear_start, self.linear_end
         dev = next(self.parameters()).device
@@ -720,7 +720,7 @@ class VQVAE(_SpecModule):
         for i, m in enumerate(c.ch_mult):
             d.ch_mult[i] = m
         d.max_objects = cap
-        d.precision = _lib.PREC_BF16 if precision == "bf16" else _lib.PREC_FP32
+        d.precision = _lib.precision_code(precision)
         return d
 
     def _ensure_encoder(self, n):

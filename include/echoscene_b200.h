@@ -44,6 +44,9 @@ extern "C" {
 /* arithmetic of the dense contractions */
 #define ECHO_PREC_FP32 0        /* fp32 operands, fp32 FMA: the 1e-3 parity mode */
 #define ECHO_PREC_BF16 1        /* bf16 operands on tcgen05 tensor cores, fp32 accumulate, fp32 norms */
+#define ECHO_PREC_X3 2          /* shape branch: fp32 activations; every contraction on tcgen05 with both operands split into hi + lo bf16
+                                 * halves and three MMAs per k-step into one fp32 TMEM accumulator (hi.hi + lo.hi + hi.lo): fp32-grade
+                                 * results (~1e-5) -- the 1e-3 parity contract on the tensor cores */
 
 typedef struct echo_graph echo_graph_t;     /* CSR of one (batched) scene graph; edges are constant over a chain */
 typedef struct echo_gcn echo_gcn_t;         /* GraphTripleConvNet */
@@ -175,6 +178,13 @@ ECHO_API int echo_layout_forward(echo_layout_t* h, const echo_graph_t* g, const 
 ECHO_API int echo_layout_step(echo_layout_t* h, const echo_graph_t* g, const float* x_t, const float* obj_embed, int32_t t,
                      const float* noise, float* x_prev, void* stream);
 ECHO_API void echo_layout_destroy(echo_layout_t* h);
+/* How echo_layout_step executes (no reference counterpart; diagnostics for tests and bench.py).
+ * mode 0 (default): graphs of <= 64 nodes / <= 512 triples run as ONE persistent cooperative kernel (csrc/layout_mk.cu), larger
+ * batches as a replayed CUDA graph of the per-layer kernels; mode 1: never the persistent kernel.
+ * info out6 = {persistent-kernel steps so far, graph replays so far, stages and ops of the current program, kernels inside the
+ * replayed graph, CTAs of the persistent kernel (0: unavailable on this device)}. */
+ECHO_API void echo_debug_set_layout_mode(int mode);
+ECHO_API int echo_debug_layout_info(const echo_layout_t* h, int64_t* out6);
 
 /* ---- shape branch.
  * echo_shape_forward == UNet3DModel.forward(x, obj_embed, triples, timesteps, context) — openai_model_3d.py:816-863;

@@ -7,7 +7,7 @@ import torch
 import torch.nn.functional as F
 
 from echoscene_b200 import _lib
-from util import BF16_TOL, FP32_TOL, assert_close
+from util import BF16_OP_TOL, BF16_TOL, FP32_TOL, assert_close
 
 pytestmark = pytest.mark.gpu
 
@@ -196,4 +196,4 @@ def test_attention_bf16(n, tokens, heads, dh):
     qd = qkv.cuda()
     out = torch.empty(n * tokens, heads * dh, device="cuda")
     _lib.check(_lib.lib().echo_op_attention(qd.data_ptr(), n, tokens, heads, dh, out.data_ptr(), _lib.PREC_BF16, _lib.stream_ptr()))
-    assert_close(out.cpu(), want, BF16_TOL, "attention bf16")
+    assert_close(out.cpu(), want, BF16_OP_TOL, "attention bf16")

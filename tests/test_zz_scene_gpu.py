@@ -195,8 +195,8 @@ def test_sample_surface_end_to_end_vs_oracle(enc):
         boxes = orc.layout_chain(lsd, lcfg, e["obj_embed"], g.triples, noises[0], noises[1:], steps)
         lat = orc.shape_chain(ssd, scfg, e["uc_s"], g.triples, x_T, 100, k)
     got = torch.cat([layout_dict["sizes"], layout_dict["translations"], layout_dict["angles"]], dim=1)
-    assert_close(got, boxes, 5e-3, "sample(): layout chain")          # 10 chained steps: tolerance as test_model_gpu's chain test
-    assert_close(shape_dict["shapes"], lat, 5e-3, "sample(): shape chain")
+    assert_close(got, boxes, FP32_TOL, "sample(): layout chain")        # 10 chained steps, as test_model_gpu's chain test
+    assert_close(shape_dict["shapes"], lat, FP32_TOL, "sample(): shape chain")
 
 
 def test_config1_echolayout_sampleBoxes_vs_oracle(enc):
@@ -227,7 +227,7 @@ def test_config1_echolayout_sampleBoxes_vs_oracle(enc):
         boxes = orc.layout_chain(lsd, lcfg, e["obj_embed"], g.triples, noises[0], noises[1:], steps)
     got = torch.cat([out["sizes"], out["translations"], out["angles"]], dim=1)
     assert got.shape == (8, 8)
-    assert_close(got, boxes, 5e-3, "config 1: sampleBoxes 10-step chain")
+    assert_close(got, boxes, FP32_TOL, "config 1: sampleBoxes 10-step chain")
 
 
 @pytest.mark.parametrize("name,fn,replace", [c for c in cases.SCENE_GLUE_CASES if c[0].startswith("box_")])
