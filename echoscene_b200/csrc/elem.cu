@@ -926,41 +926,53 @@ __global__ void __launch_bounds__(256) gn_apply_cs_kernel(const __nv_bfloat16* _
                                                           int R, double count, float eps, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, int64_t V, int groups, int silu, int noct, int RY,
                                                           int rows_per_block, __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ ycat) {
-  extern __shared__ double gn_sm[];           // [C][2] channel sums, then [groups][2] floats
+  extern __shared__ double gn_sm[];           // [RS][C / 7][2] block sums, then [groups][2] floats
   griddep_launch();
   griddep_wait();
   const int C = CA + CB, obj = blockIdx.y, cpg = C / groups;
-  float* gst = reinterpret_cast<float*>(gn_sm + 2 * C);
   // phase 1: totals of every 7-channel block over the object's R tile partials.  A partial row is [chunk][8 slots][2]:
   // slot s of 32-column chunk q holds the part of block 32q/7 + s that lies inside the chunk (gemm_tc.cu epilogue).
+  // The R rows of a block are dealt to RS threads (all their loads in flight together: this prologue is a latency chain in
+  // front of the streaming pass of EVERY block of the grid); partial sums meet in shared memory in a fixed order.
   const int nblocks = C / 7;
-  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+  const int RS = max(1, min(8, (int)blockDim.x / nblocks));
+  double2* part = reinterpret_cast<double2*>(gn_sm);   // [RS][nblocks]
+  float* gst = reinterpret_cast<float*>(gn_sm + 2 * nblocks * RS);
+  for (int item = threadIdx.x; item < nblocks * RS; item += blockDim.x) {
+    const int b = item % nblocks, rs = item / nblocks;
     const bool in_a = b * 7 < CA;
     const int lb = in_a ? b : b - CA / 7;                 // block index inside its producer
     const int nch = (in_a ? CA : CB) >> 5;
     const float* src = (in_a ? csa : csb) + (int64_t)obj * R * nch * 16;
     const int q1 = (lb * 7) >> 5, q2 = (lb * 7 + 6) >> 5;
     const int i1 = (q1 * 8 + (lb - (q1 * 32) / 7)) * 2, i2 = (q2 * 8 + (lb - (q2 * 32) / 7)) * 2;
+    const bool two = q2 != q1;
     double a = 0.0, bsum = 0.0;
-    for (int r = 0; r < R; ++r) {
-      const float* row = src + (int64_t)r * nch * 16;
-      const float2 v = *reinterpret_cast<const float2*>(row + i1);
-      a += (double)v.x;
-      bsum += (double)v.y;
-      if (q2 != q1) {
-        const float2 w = *reinterpret_cast<const float2*>(row + i2);
-        a += (double)w.x;
-        bsum += (double)w.y;
+    for (int r = rs; r < R; r += 4 * RS) {
+      float2 v[4], w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int rr = r + k * RS;
+        const float* row = src + (int64_t)rr * nch * 16;
+        v[k] = rr < R ? *reinterpret_cast<const float2*>(row + i1) : make_float2(0.f, 0.f);
+        w[k] = (two && rr < R) ? *reinterpret_cast<const float2*>(row + i2) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        a += (double)v[k].x;
+        bsum += (double)v[k].y;
+        a += (double)w[k].x;
+        bsum += (double)w[k].y;
       }
     }
-    gn_sm[2 * b] = a;
-    gn_sm[2 * b + 1] = bsum;
+    part[rs * nblocks + b] = make_double2(a, bsum);
   }
   __syncthreads();
   if (threadIdx.x < groups) {
     const int bpg = cpg / 7;
     double a = 0.0, b = 0.0;
-    for (int k = threadIdx.x * bpg; k < (threadIdx.x + 1) * bpg; ++k) { a += gn_sm[2 * k]; b += gn_sm[2 * k + 1]; }
+    for (int k = threadIdx.x * bpg; k < (threadIdx.x + 1) * bpg; ++k)
+      for (int rs = 0; rs < RS; ++rs) { a += part[rs * nblocks + k].x; b += part[rs * nblocks + k].y; }
     const double mean = a / count;
     double var = b / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -1041,7 +1053,7 @@ void gn_apply_cs(const Act& xa, const Act* xb, const float* gamma, const float* 
   int rows_per_block = 16 * RY;
   while (rows_per_block > 2 * RY && (int64_t)cdiv(V, rows_per_block) * xa.n < 2 * 148) rows_per_block -= 2 * RY;
   dim3 grid(cdiv(V, rows_per_block), xa.n);
-  const size_t smem = (size_t)C * 2 * sizeof(double) + (size_t)groups * 2 * sizeof(float);
+  const size_t smem = (size_t)(C / 7 > threads ? C / 7 : threads) * 2 * sizeof(double) + (size_t)groups * 2 * sizeof(float);
   launch_pdl(gn_apply_cs_kernel, grid, dim3(threads), smem, s, (const __nv_bfloat16*)xa.p, xa.c, (const float*)xa.colsum,
              xb ? (const __nv_bfloat16*)xb->p : (const __nv_bfloat16*)nullptr, xb ? xb->c : 0, xb ? (const float*)xb->colsum : (const float*)nullptr,
              xa.colsum_rows, (double)V * (C / groups), eps, gamma, beta, V, groups, silu ? 1 : 0, noct, RY, rows_per_block,

@@ -291,7 +291,8 @@ void echo_layout::build_mk(int Nn, int T) {
     ECHO_CHECK((in.pro == PRO_GEGLU ? in.C : in.width()) == w.cin, "layout program: linear input width %d != %d", in.width(), w.cin);
     MkOp o = base_op(Nn, w.cin, w.cout, in.X, in.ld ? in.ld : (in.pro == PRO_GEGLU ? 2 * in.C : in.C), w.w, w.b, Y, ldy);
     if (in.X2) { o.X2 = in.X2; o.ldx2 = in.C2; o.K1 = in.C; }
-    o.pro = in.pro == PRO_GN ? MK_GN : in.pro == PRO_LN ? MK_LN : in.pro == PRO_GEGLU ? MK_GEGLU : in.pro == PRO_SILU ? MK_SILU : MK_NONE;
+    ECHO_CHECK(in.pro != PRO_GEGLU, "layout program: GEGLU is the epilogue of ff1, not a prologue");
+    o.pro = in.pro == PRO_GN ? MK_GN : in.pro == PRO_LN ? MK_LN : in.pro == PRO_SILU ? MK_SILU : MK_NONE;
     if (in.nw) { o.gamma = in.nw->g; o.beta = in.nw->b; }
     o.eps = in.eps; o.pro_act = in.silu ? 1 : 0;
     if (in.pro == PRO_GN) o.cpg = in.width() / 32;
@@ -435,7 +436,7 @@ void echo_layout::build_mk(int Nn, int T) {
     float* out = mkb(C);
     float* t0 = mkb(C);
     float* t1 = mkb(C);
-    float* f1 = mkb(8 * C);
+    float* f1 = mkb(4 * C);
     float* t2 = mkb(C);
     In xn = plain(x, C); xn.pro = PRO_GN; xn.nw = &at.norm; xn.eps = 1e-6f;
     A.push_back(lin_in(xn, at.proj_in, t0, C, nullptr, 0, 0));
@@ -448,10 +449,14 @@ void echo_layout::build_mk(int Nn, int T) {
     }
     flush();
     In l3 = plain(t1, C); l3.pro = PRO_LN; l3.nw = &at.ln3;
-    A.push_back(lin_in(l3, at.ff1, f1, 8 * C, nullptr, 0, 0));
+    {   // ff.net.0 (GEGLU): value rows [0, 4C) and gate rows [4C, 8C) of the projection meet in the epilogue; f1 is (N, 4C)
+      MkOp o = lin_in(l3, at.ff1, f1, 4 * C, nullptr, 0, 0);
+      o.nout = 4 * C;
+      o.epi = MK_EPI_GEGLU;
+      A.push_back(o);
+    }
     flush();
-    In gg = plain(f1, 4 * C); gg.pro = PRO_GEGLU;
-    A.push_back(lin_in(gg, at.ff2, t2, C, t1, C, 0));
+    A.push_back(lin_in(plain(f1, 4 * C), at.ff2, t2, C, t1, C, 0));
     flush();
     A.push_back(lin_in(plain(t2, C), at.proj_out, out, C, x, C, 0));
     flush();
@@ -529,8 +534,35 @@ void echo_layout::step_mk(const echo_graph* g, const float* x_t, const float* ob
   a.s_idx = g->s_idx; a.o_idx = g->o_idx; a.node_off = g->node_off; a.node_items = g->node_items;
   a.triples = (const long long*)g->triples;
   a.H = gcn.H;
+  static const char* timeline = getenv("ECHO_MK_TIMELINE");   // diagnostics: per-CTA per-stage SM clocks of every step -> file (last step wins)
+  long long* d_dbg = nullptr;
+  const size_t dbg_n = (size_t)mk_ctas * a.n_stages * 8;
+  if (timeline) {
+    ECHO_CUDA(cudaMalloc(&d_dbg, dbg_n * sizeof(long long)));
+    ECHO_CUDA(cudaMemsetAsync(d_dbg, 0, dbg_n * sizeof(long long), s));
+    a.dbg = d_dbg;
+  }
   mk_launch(a, mk_ctas, s);
   ++mk_steps;
+  if (timeline) {
+    std::vector<long long> hd(dbg_n);
+    ECHO_CUDA(cudaStreamSynchronize(s));
+    ECHO_CUDA(cudaMemcpy(hd.data(), d_dbg, dbg_n * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(d_dbg);
+    if (FILE* f = fopen(timeline, "wb")) {
+      const long long hdr[2] = {mk_ctas, a.n_stages};
+      fwrite(hdr, sizeof(long long), 2, f);
+      fwrite(hd.data(), sizeof(long long), dbg_n, f);
+      // per stage: foreground / background op counts and the shape of the first op
+      for (int i = 0; i < a.n_stages; ++i) {
+        const MkStage& st = mk_stages[i];
+        const MkOp& o = mk_ops[st.op_begin];
+        const long long rec[8] = {st.n_a, st.n_b, o.type, o.M, o.K, o.nout, o.pro, o.units};
+        fwrite(rec, sizeof(long long), 8, f);
+      }
+      fclose(f);
+    }
+  }
 }
 
 namespace echo {

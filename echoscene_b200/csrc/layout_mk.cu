@@ -1,28 +1,32 @@
 // Persistent executor of one layout DDPM iteration: UNet1DModel.forward (denoise_net.py:773-806, incl. box_messsage_passing
 // :758-771 and the GraphTripleConvNet of graph.py:124-250) + the posterior update (diffusion_ddpm.py:220-309) as ONE kernel.
 //
-// Why: the layout step is a chain of ~130 dependent few-row layers (rows = nodes / triples, 8..64 of them) whose cost as
+// Why: the layout step is a chain of ~120 dependent few-row layers (rows = nodes / triples, 8..64 of them) whose cost as
 // separate launches is the chain of launch + first-touch latencies (1.56 ms for 461 MB of weights = 4.5 % of the HBM
 // roofline, r1).  Here the step is a PROGRAM (layout.cu records it once per node/triple count): stages of independent ops,
 // each op cut into units (16 rows x FU output features); one cooperative grid of one CTA per SM walks the stages.
 //
-//   * weights never wait for a barrier: they are constants, so a producer warp per CTA streams the CTA's future weight
-//     slices HBM -> shared memory with cp.async.bulk (1-D TMA) through a 3-slot ring (120 KB in flight per SM), running
-//     ahead of the compute by up to three units = usually three stages;
+//   * weights never wait for a barrier: they are constants, so every CTA streams its future weight slices HBM -> shared
+//     memory with cp.async.bulk (1-D TMA, one copy per feature row into a bank-conflict-free padded layout) through a
+//     3-slot ring (108 KB in flight per SM), two to three stages ahead of the compute; the ring is refilled by one warp
+//     while the CTA waits at the stage barrier (the slot of a finished unit is free by program order: no empty-barriers);
 //   * a stage boundary is one arrival counter in L2 (release: bar.sync + fence + atomicAdd; acquire: one polling thread +
 //     bar.sync), ~1 us instead of a kernel boundary; activations are read with ld.global.cg (they are rewritten every step by
 //     other SMs, L1 must not serve them);
 //   * the elementwise op in front of a Linear is a prologue applied while its input rows are staged in shared memory (SiLU,
-//     GroupNorm via lane shuffles, LayerNorm per warp-row, GEGLU, the GraphTripleConv edge gather-combine with the node
-//     features staged per edge row, and the CSR mean pooling in the reference's summation order), so a stage is exactly one
-//     dependent contraction;
+//     GroupNorm via lane shuffles, LayerNorm per warp-row, the GraphTripleConv edge gather-combine with the node features
+//     staged per edge row, and the CSR mean pooling in the reference's summation order); GEGLU is the epilogue of ff1 (each
+//     unit carries the value row and the gate row of its features), so a stage is exactly one dependent contraction;
 //   * the time-embedding path (time MLP, the 22 stacked emb_layers projections = 40 % of the weight bytes) is computed for
 //     ONE row (all nodes of a step share t) and runs as background ops in the barrier shadow of the GCN stages.
 //
-// Contraction mapping inside a unit (8 consumer warps): the staged rows X_s [R][K] and the weight slice W_s [FU][K] are
-// both K-contiguous in shared memory; warp w owns K-chunks of 64 (one float2 per lane), keeps R x 4 accumulators per
-// feature group in registers, and a halving butterfly + a fixed-order sum over the warps finishes the dot products
-// (deterministic: no atomics on data).
+// Contraction of a unit (16 consumer warps): 16 staged rows X_s [16][K] x weight slice W_s [<= 24][K], both K-contiguous in
+// shared memory with a 16-float row pad.  The K range is dealt to the warps in steps of 16; a step is two
+// mma.sync.m16n8k8 per 8 features in split precision (3xTF32: x = hi + lo, hi.hi + lo.hi + hi.lo into an fp32 accumulator,
+// small terms first -- fp32-grade products, the tensor core does the k-reduction), fed by one LDS.128 per fragment (the k
+// index inside a step is permuted identically for A and B so that a thread's four k values are contiguous).  The warps'
+// partial tiles meet in shared memory and are summed in fixed order (deterministic: no atomics on data).  One-row ops (the
+// time path) are plain fp32 dot products, a warp group per feature.
 #include "layout_mk.cuh"
 
 #include "tc_ptx.cuh"
@@ -32,18 +36,22 @@ namespace {
 
 using namespace ptx;
 
-constexpr int MK_THREADS = 288;   // 8 consumer warps + 1 producer warp
+constexpr int MK_CW = 16;                  // warps (all of them compute; the last one also feeds the weight ring)
+constexpr int MK_CT = MK_CW * 32;
+constexpr int MK_THREADS = MK_CT;          // 512 threads: 128 registers each
 constexpr int MK_SLOTS = 3;
-constexpr int MK_MAXG = MK_MAX_FU / 4;
-constexpr int SM_W = MK_XCAP * 4;
-constexpr int SM_RED = SM_W + MK_SLOTS * MK_SLOT_BYTES;
-constexpr int SM_OPS = SM_RED + MK_MAXG * 8 * 64 * 4;
+constexpr int MK_XSTRIDE = MK_XROW + MK_PAD;             // floats between staged rows
+constexpr int SM_X = 16 * MK_XSTRIDE * 4;
+constexpr int SM_RED = SM_X + MK_SLOTS * MK_SLOT_BYTES;
+constexpr int SM_OPS = SM_RED + MK_CW * 16 * MK_MAX_FU * 4;
 constexpr int SM_BAR = SM_OPS + MK_MAX_STAGE_OPS * 256;
 constexpr int SM_TOTAL = SM_BAR + 64;
+static_assert(SM_TOTAL <= 232448, "shared memory budget of one CTA");
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
+// x * sigmoid(x) with the fast exponential / reciprocal (relative error ~1e-6; the prologue runs redundantly in every CTA)
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
-__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
@@ -67,385 +75,486 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-
-// Halving butterfly over the lanes: on return lane l holds the totals of elements [base, base + N/32) in v[0 .. N/32).
-template <int N>
-__device__ __forceinline__ int butterfly(float (&v)[N], int lane) {
-  int base = 0;
-#pragma unroll
-  for (int off = 16, n = N; off >= 1; off >>= 1, n >>= 1) {
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < n / 2; ++i) {
-      const float send = up ? v[i] : v[i + n / 2];
-      const float keep = up ? v[i + n / 2] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-    if (up) base += n / 2;
-  }
-  return base;
+// x = hi + lo with hi = x truncated to TF32 (exact subtraction, |lo| < 2^-10 |x|); the tensor core reads the upper 19 bits
+// of an operand register, i.e. truncates lo itself.  hi.hi + lo.hi + hi.lo then drops ~2^-20 |x w| per product.
+// (cvt.rna.tf32.f32 expands to four instructions on this target; truncation is one.)
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
 __device__ __forceinline__ const float* resolve_x(const MkOp& op, const MkArgs& a) {
   return op.x_ext == MK_EXT_XT ? a.x_t : op.x_ext == MK_EXT_OBJ ? a.obj_embed : op.X;
 }
 
-// rows m0 .. m0+R of the op's input, prologue applied, columns [seg0, seg0 + seg_len) -> Xs [R][KS]; one warp per row
-template <int R>
-__device__ void stage_input(const MkOp& op, const MkArgs& a, const float* X, float* Xs, int KS, int m0, int seg0, int seg_len, int warp,
-                            int lane) {
+__device__ __forceinline__ float4 load_in(const MkOp& op, const float* X, int m, int k) {
+  return (op.X2 && k >= op.K1) ? ld4(op.X2 + (long long)m * op.ldx2 + (k - op.K1)) : ld4(X + (long long)m * op.ldx + k);
+}
+
+// LayerNorm of one row by one warp, NJ float4 per lane (row length <= 128 * NJ)
+template <int NJ>
+__device__ __forceinline__ void ln_row(const MkOp& op, const float* X, int m, int nq, float4* xr, int lane) {
+  float4 v[NJ];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int q = lane + 32 * j;
+    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < nq) v[j] = ld4(X + (long long)m * op.ldx + 4 * q);
+  }
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)op.K;
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    if (lane + 32 * j < nq) {
+      const float d0 = v[j].x - mean, d1 = v[j].y - mean, d2 = v[j].z - mean, d3 = v[j].w - mean;
+      ss += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss / (float)op.K + op.eps);
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int q = lane + 32 * j;
+    if (q < nq) {
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(op.gamma + 4 * q)), bt = __ldg(reinterpret_cast<const float4*>(op.beta + 4 * q));
+      float4 o4;
+      o4.x = (v[j].x - mean) * rstd * gm.x + bt.x; o4.y = (v[j].y - mean) * rstd * gm.y + bt.y;
+      o4.z = (v[j].z - mean) * rstd * gm.z + bt.z; o4.w = (v[j].w - mean) * rstd * gm.w + bt.w;
+      xr[q] = o4;
+    }
+  }
+}
+
+// rows m0 .. m0+16 of the op's input, prologue applied, columns [seg0, seg0 + seg_len) -> Xs [16][MK_XSTRIDE]; one warp per
+// row, every global load of a row in flight before the first use
+__device__ void stage_rows(const MkOp& op, const MkArgs& a, const float* X, float* Xs, int m0, int seg0, int seg_len, int warp, int lane) {
   const int nq = seg_len >> 2;
-  for (int i = warp; i < R; i += 8) {
-    const int m = m0 + i;
-    float4* xr = reinterpret_cast<float4*>(Xs + i * KS);
-    if (m >= op.M) {
-      for (int q = lane; q < nq; q += 32) xr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-      continue;
-    }
-    switch (op.pro) {
-      case MK_GN: {   // K % 128 == 0: every lane is in range in every iteration, a group is cpg/4 adjacent lanes
-        const int gl = op.cpg >> 2;
-        const float inv = 1.f / (float)op.cpg;
-        for (int q = lane; q < nq; q += 32) {
-          const int k = seg0 + 4 * q;
-          float4 v = (op.X2 && k >= op.K1) ? ld4(op.X2 + (long long)m * op.ldx2 + (k - op.K1)) : ld4(X + (long long)m * op.ldx + k);
-          const float4 gm = __ldg(reinterpret_cast<const float4*>(op.gamma + k)), bt = __ldg(reinterpret_cast<const float4*>(op.beta + k));
-          float s = (v.x + v.y) + (v.z + v.w);
-          for (int o = 1; o < gl; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          const float mean = s * inv;
-          const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
-          float ss = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
-          for (int o = 1; o < gl; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-          const float rstd = rsqrtf(ss * inv + op.eps);
-          v.x = d0 * rstd * gm.x + bt.x; v.y = d1 * rstd * gm.y + bt.y; v.z = d2 * rstd * gm.z + bt.z; v.w = d3 * rstd * gm.w + bt.w;
-          if (op.pro_act) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
-          xr[q] = v;
-        }
-        break;
-      }
-      case MK_LN: {   // whole row by this warp (K <= 1280): two-pass statistics in registers
-        float4 v[10];
-        float s = 0.f;
+  const int m = m0 + warp;
+  float4* xr = reinterpret_cast<float4*>(Xs + warp * MK_XSTRIDE);
+  if (m >= op.M) {
+    for (int q = lane; q < nq; q += 32) xr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  switch (op.pro) {
+    case MK_GN: {   // K % 128 == 0: every lane is in range in every iteration, a group is cpg/4 adjacent lanes
+      const int gl = op.cpg >> 2;
+      const float inv = 1.f / (float)op.cpg;
+      for (int q0 = 0; q0 < nq; q0 += 128) {
+        float4 v[4];
 #pragma unroll
-        for (int j = 0; j < 10; ++j) {
-          const int q = lane + 32 * j;
+        for (int j = 0; j < 4; ++j) {
+          const int q = q0 + lane + 32 * j;
           v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (q < nq) { v[j] = ld4(X + (long long)m * op.ldx + 4 * q); s += (v[j].x + v[j].y) + (v[j].z + v[j].w); }
+          if (q < nq) v[j] = load_in(op, X, m, seg0 + 4 * q);
         }
 #pragma unroll
-        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        const float mean = s / (float)op.K;
-        float ss = 0.f;
-#pragma unroll
-        for (int j = 0; j < 10; ++j) {
-          if (lane + 32 * j < nq) {
+        for (int j = 0; j < 4; ++j) {
+          const int q = q0 + lane + 32 * j;
+          if (q < nq) {   // warp-uniform (nq % 32 == 0)
+            const int k = seg0 + 4 * q;
+            const float4 gm = __ldg(reinterpret_cast<const float4*>(op.gamma + k)), bt = __ldg(reinterpret_cast<const float4*>(op.beta + k));
+            float s = (v[j].x + v[j].y) + (v[j].z + v[j].w);
+            for (int o = 1; o < gl; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float mean = s * inv;
             const float d0 = v[j].x - mean, d1 = v[j].y - mean, d2 = v[j].z - mean, d3 = v[j].w - mean;
-            ss += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+            float ss = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+            for (int o = 1; o < gl; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            const float rstd = rsqrtf(ss * inv + op.eps);
+            float4 r;
+            r.x = d0 * rstd * gm.x + bt.x; r.y = d1 * rstd * gm.y + bt.y; r.z = d2 * rstd * gm.z + bt.z; r.w = d3 * rstd * gm.w + bt.w;
+            if (op.pro_act) { r.x = silu_f(r.x); r.y = silu_f(r.y); r.z = silu_f(r.z); r.w = silu_f(r.w); }
+            xr[q] = r;
           }
         }
+      }
+      break;
+    }
+    case MK_LN: {   // whole row by this warp: two-pass statistics in registers (K <= 512: four vectors per lane, else up to ten)
+      if (nq <= 128) ln_row<4>(op, X, m, nq, xr, lane);
+      else ln_row<10>(op, X, m, nq, xr, lane);
+      break;
+    }
+    case MK_EDGE: {   // X = [Ps | Po] (N, 2H), aux0 = Pp (T, H), aux1 = folded bias; same association as edge_combine_kernel
+      const int H = op.K;
+      const float* ps = X + (long long)a.s_idx[m] * 2 * H;
+      const float* po = X + (long long)a.o_idx[m] * 2 * H + H;
+      const float* pq = op.aux0 + (long long)m * H;
+      for (int q = lane; q < nq; q += 32) {
+        const int k = seg0 + 4 * q;
+        const float4 A = ld4(ps + k), B = ld4(pq + k), C = ld4(po + k), D = __ldg(reinterpret_cast<const float4*>(op.aux1 + k));
+        float4 r;
+        r.x = fmaxf(((A.x + B.x) + C.x) + D.x, 0.f);
+        r.y = fmaxf(((A.y + B.y) + C.y) + D.y, 0.f);
+        r.z = fmaxf(((A.z + B.z) + C.z) + D.z, 0.f);
+        r.w = fmaxf(((A.w + B.w) + C.w) + D.w, 0.f);
+        xr[q] = r;
+      }
+      break;
+    }
+    case MK_POOL: {   // CSR order = the reference's scatter_add order (subject roles by ascending t, then object roles)
+      const int beg = a.node_off[m], end = a.node_off[m + 1];
+      const float cnt = fmaxf((float)(end - beg), 1.f);
+      for (int q0 = 0; q0 < nq; q0 += 64) {   // two float4 columns per lane and pass (H = 256: one pass)
+        const int qa = q0 + lane, qb = q0 + lane + 32;
+        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+        for (int base = beg; base < end; base += 32) {
+          const int mine = base + lane < end ? a.node_items[base + lane] : 0;
+          const int nb = min(32, end - base);
+#pragma unroll 4
+          for (int e = 0; e < nb; ++e) {
+            const int item = __shfl_sync(0xffffffffu, mine, e), t = item >> 1, role = item & 1;
+            const float* src = X + (long long)t * op.ldx + (role ? op.aux_i : 0) + seg0;
+            if (qa < nq) { const float4 v = ld4(src + 4 * qa); acc0.x += v.x; acc0.y += v.y; acc0.z += v.z; acc0.w += v.w; }
+            if (qb < nq) { const float4 v = ld4(src + 4 * qb); acc1.x += v.x; acc1.y += v.y; acc1.z += v.z; acc1.w += v.w; }
+          }
+        }
+        if (qa < nq) xr[qa] = make_float4(acc0.x / cnt, acc0.y / cnt, acc0.z / cnt, acc0.w / cnt);
+        if (qb < nq) xr[qb] = make_float4(acc1.x / cnt, acc1.y / cnt, acc1.z / cnt, acc1.w / cnt);
+      }
+      break;
+    }
+    default: {   // MK_NONE / MK_SILU, optional channel concat [X | X2]
+      for (int q0 = 0; q0 < nq; q0 += 128) {
+        float4 v[4];
 #pragma unroll
-        for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        const float rstd = rsqrtf(ss / (float)op.K + op.eps);
+        for (int j = 0; j < 4; ++j) {
+          const int q = q0 + lane + 32 * j;
+          v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (q < nq) v[j] = load_in(op, X, m, seg0 + 4 * q);
+        }
 #pragma unroll
-        for (int j = 0; j < 10; ++j) {
-          const int q = lane + 32 * j;
+        for (int j = 0; j < 4; ++j) {
+          const int q = q0 + lane + 32 * j;
           if (q < nq) {
-            const float4 gm = __ldg(reinterpret_cast<const float4*>(op.gamma + 4 * q)), bt = __ldg(reinterpret_cast<const float4*>(op.beta + 4 * q));
-            float4 o4;
-            o4.x = (v[j].x - mean) * rstd * gm.x + bt.x; o4.y = (v[j].y - mean) * rstd * gm.y + bt.y;
-            o4.z = (v[j].z - mean) * rstd * gm.z + bt.z; o4.w = (v[j].w - mean) * rstd * gm.w + bt.w;
-            xr[q] = o4;
+            if (op.pro == MK_SILU) { v[j].x = silu_f(v[j].x); v[j].y = silu_f(v[j].y); v[j].z = silu_f(v[j].z); v[j].w = silu_f(v[j].w); }
+            xr[q] = v[j];
           }
         }
-        break;
       }
-      case MK_EDGE: {   // X = [Ps | Po] (N, 2H), aux0 = Pp (T, H), aux1 = folded bias; same association as edge_combine_kernel
-        const int H = op.K;
-        const float* ps = X + (long long)a.s_idx[m] * 2 * H;
-        const float* po = X + (long long)a.o_idx[m] * 2 * H + H;
-        const float* pq = op.aux0 + (long long)m * H;
-        for (int q = lane; q < nq; q += 32) {
-          const int k = seg0 + 4 * q;
-          const float4 A = ld4(ps + k), B = ld4(pq + k), C = ld4(po + k), D = __ldg(reinterpret_cast<const float4*>(op.aux1 + k));
-          float4 r;
-          r.x = fmaxf(((A.x + B.x) + C.x) + D.x, 0.f);
-          r.y = fmaxf(((A.y + B.y) + C.y) + D.y, 0.f);
-          r.z = fmaxf(((A.z + B.z) + C.z) + D.z, 0.f);
-          r.w = fmaxf(((A.w + B.w) + C.w) + D.w, 0.f);
-          xr[q] = r;
-        }
-        break;
-      }
-      case MK_POOL: {   // CSR order = the reference's scatter_add order (subject roles by ascending t, then object roles)
-        const int beg = a.node_off[m], end = a.node_off[m + 1];
-        const float cnt = fmaxf((float)(end - beg), 1.f);
-        for (int q = lane; q < nq; q += 32) {
-          const int k = seg0 + 4 * q;
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int it = beg; it < end; ++it) {
-            const int item = a.node_items[it], t = item >> 1, role = item & 1;
-            const float4 v = ld4(X + (long long)t * op.ldx + (role ? op.aux_i : 0) + k);
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-          }
-          acc.x /= cnt; acc.y /= cnt; acc.z /= cnt; acc.w /= cnt;
-          xr[q] = acc;
-        }
-        break;
-      }
-      case MK_TEMB: {   // [cos(t f) | sin(t f)], the arithmetic of timestep_embedding_kernel (elem.cu)
-        const int half = op.K >> 1;
-        float* xs = Xs + i * KS;
-        for (int k = lane; k < half; k += 32) {
-          const float arg = __fmul_rn((float)a.t, __ldg(a.freqs + k));
-          xs[k] = cosf(arg);
-          xs[half + k] = sinf(arg);
-        }
-        break;
-      }
-      default: {   // MK_NONE / MK_SILU / MK_GEGLU, optional channel concat [X | X2]
-        for (int q = lane; q < nq; q += 32) {
-          const int k = seg0 + 4 * q;
-          float4 v = (op.X2 && k >= op.K1) ? ld4(op.X2 + (long long)m * op.ldx2 + (k - op.K1)) : ld4(X + (long long)m * op.ldx + k);
-          if (op.pro == MK_SILU) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
-          if (op.pro == MK_GEGLU) {
-            const float4 g = ld4(X + (long long)m * op.ldx + op.K + k);
-            v.x *= gelu_erf(g.x); v.y *= gelu_erf(g.y); v.z *= gelu_erf(g.z); v.w *= gelu_erf(g.w);
-          }
-          xr[q] = v;
-        }
-        break;
-      }
+      break;
     }
   }
 }
 
-// acc[i*4 + j] += sum_k Xs[i][k] * Ws[(g*4 + j)][k] over this warp's K-chunks of the segment
-template <int R>
-__device__ __forceinline__ void fma_group(const float* Xs, int KS, const float* Ws, int K, int seg_len, int g, int feats, int warp, int lane,
-                                          float (&acc)[R * 4]) {
-  const int nch = (seg_len + 63) >> 6;
-  for (int c = warp; c < nch; c += 8) {
-    const int k = (c << 6) + 2 * lane;
-    if (k < seg_len) {
-      float2 xv[R];
-#pragma unroll
-      for (int i = 0; i < R; ++i) xv[i] = *reinterpret_cast<const float2*>(Xs + i * KS + k);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (g * 4 + j < feats) {
-          const float2 wv = *reinterpret_cast<const float2*>(Ws + (size_t)(g * 4 + j) * K + k);
-#pragma unroll
-          for (int i = 0; i < R; ++i) acc[i * 4 + j] = fmaf(xv[i].x, wv.x, fmaf(xv[i].y, wv.y, acc[i * 4 + j]));
-        }
-      }
+// the single input row of a one-row op (the time path) -> Xs[0 .. K), all consumer threads
+__device__ void stage_row1(const MkOp& op, const MkArgs& a, const float* X, float* Xs, int tid) {
+  if (op.pro == MK_TEMB) {   // [cos(t f) | sin(t f)], the arithmetic of timestep_embedding_kernel (elem.cu)
+    const int half = op.K >> 1;
+    for (int k = tid; k < half; k += MK_CT) {
+      const float arg = __fmul_rn((float)a.t, __ldg(a.freqs + k));
+      Xs[k] = cosf(arg);
+      Xs[half + k] = sinf(arg);
     }
+    return;
+  }
+  const int nq = op.K >> 2;
+  for (int q = tid; q < nq; q += MK_CT) {
+    float4 v = ld4(X + 4 * q);
+    if (op.pro == MK_SILU) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+    reinterpret_cast<float4*>(Xs)[q] = v;
   }
 }
 
-template <int R>
-__device__ __forceinline__ void reduce_store(float (&acc)[R * 4], float* red, int lane) {
-  if constexpr (R * 4 >= 32) {
-    constexpr int N = R * 4;
-    float v[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) v[i] = i < R * 4 ? acc[i] : 0.f;
-    const int base = butterfly<N>(v, lane);
-#pragma unroll
-    for (int e = 0; e < N / 32; ++e) red[base + e] = v[e];
+// what a thread needs for its output element, requested before the contraction so that the L2 latency hides under it
+struct EpiPre {
+  float b = 0.f, b2 = 0.f, r = 0.f;
+  int m = 0, n = 0;
+  bool valid = false;
+};
+
+__device__ __forceinline__ void epi_store(const MkOp& op, const MkArgs& a, const EpiPre& e, float v) {
+  v += e.b;
+  if (op.act == 1) v = fmaxf(v, 0.f);
+  else if (op.act == 2) v = v / (1.f + expf(-v));
+  v += e.r;
+  float* Y = op.y_ext == MK_EXT_XPREV ? a.x_prev : op.Y;
+  if (op.epi == MK_EPI_DDPM) {   // v = eps: x0 = a x - b eps; mean = c1 x0 + c2 x; + [t > 0] exp(0.5 logvar) noise (ddpm_update_kernel)
+    const int t = a.t, T = a.T;
+    const float ca = __ldg(a.tab + t), cb = __ldg(a.tab + T + t), c1 = __ldg(a.tab + 2 * T + t), c2 = __ldg(a.tab + 3 * T + t),
+                lv = __ldg(a.tab + 4 * T + t);
+    const float sig = (t == 0 ? 0.f : 1.f) * expf(0.5f * lv);
+    const long long idx = (long long)e.m * op.nout + e.n;
+    const float x = __ldcg(a.x_t + idx);
+    const float x0 = __fsub_rn(__fmul_rn(ca, x), __fmul_rn(cb, v));
+    const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, x));
+    Y[idx] = __fadd_rn(mean, __fmul_rn(sig, __ldcg(a.noise + idx)));
+  } else if (op.bcast_rows > 0) {
+    for (int rr = 0; rr < op.bcast_rows; ++rr) Y[(long long)rr * op.ldy + e.n] = v;
   } else {
-#pragma unroll
-    for (int i = 0; i < R * 4; ++i) {
-      float s = acc[i];
-#pragma unroll
-      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) red[i] = s;
-    }
+    Y[(long long)e.m * op.ldy + e.n] = v;
   }
 }
 
-// one unit of a LIN op: rows [m0, m0+R) x features [n0, n0+feats)
-template <int R>
-__device__ void lin_unit(const MkOp& op, const MkArgs& a, float* Xs, const float* Ws, float* red_s, int m0, int n0, int feats, bool restage,
-                         int tid) {
-  const int warp = tid >> 5, lane = tid & 31;
-  const int K = op.K, groups = (feats + 3) >> 2;
-  constexpr int NG = R * 4;
-  const int seg_max = ((MK_XCAP / R) >> 7) << 7;
-  const int nseg = (K + seg_max - 1) / seg_max;
+// one unit of a 16-row LIN op: rows [m0, m0+16) x features [n0, n0+feats)
+__device__ void lin_unit16(const MkOp& op, const MkArgs& a, float* Xs, const float* Ws, float* red_s, int m0, int n0, int feats, bool restage,
+                           int tid, long long* dbg) {
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int K = op.K, ws = K + MK_PAD;
+  const bool geglu = op.epi == MK_EPI_GEGLU;
+  const int srows = geglu ? 2 * feats : feats;     // weight rows in the slot
+  const int nt = (srows + 7) >> 3;                   // 8-feature MMA tiles (<= 3)
+  const int nseg = (K + MK_XROW - 1) / MK_XROW;
   const float* X = resolve_x(op, a);
-  const int rows = min(R, op.M - m0);
-  // epilogue operands requested before the contraction (their L2 latency hides under it)
-  const int total = groups * NG;
-  float pb[2] = {0.f, 0.f}, pr[2] = {0.f, 0.f};
-  bool pv[2] = {false, false};
-  int pm[2] = {0, 0}, pn[2] = {0, 0};
+  EpiPre e;
+  if (tid < 16 * feats) {
+    const int i = tid / feats, j = tid - i * feats;
+    e.m = m0 + i; e.n = n0 + j;
+    e.valid = e.m < op.M;
+    if (e.valid) {
+      if (op.bias) { e.b = __ldg(op.bias + e.n); if (geglu) e.b2 = __ldg(op.bias + op.nout + e.n); }
+      if (op.res) e.r = __ldcg(op.res + (long long)e.m * op.ld_res + e.n);
+      if (op.res2) e.r += __ldcg(op.res2 + (long long)e.m * op.ld_res2 + e.n);
+    }
+  }
+  float acc[3][4];
 #pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    const int o = tid + 256 * e;
-    if (o < total) {
-      const int g = o / NG, rem = o - g * NG, i = rem >> 2, j = rem & 3;
-      pv[e] = i < rows && g * 4 + j < feats;
-      pm[e] = m0 + i;
-      pn[e] = n0 + g * 4 + j;
-      if (pv[e]) {
-        if (op.bias) pb[e] = __ldg(op.bias + pn[e]);
-        if (op.res) pr[e] = __ldcg(op.res + (long long)pm[e] * op.ld_res + pn[e]);
-        if (op.res2) pr[e] += __ldcg(op.res2 + (long long)pm[e] * op.ld_res2 + pn[e]);
+  for (int i = 0; i < 3; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  for (int sg = 0; sg < nseg; ++sg) {
+    const int seg0 = sg * MK_XROW, seg_len = min(MK_XROW, K - seg0);
+    if (restage || nseg > 1) {
+      if (sg) cons_sync();   // everyone is done reading the previous segment
+      stage_rows(op, a, X, Xs, m0, seg0, seg_len, warp, lane);
+    }
+    cons_sync();   // rows staged; also: everyone left the previous unit's epilogue (red_s is about to be rewritten)
+    if (dbg && tid == 0) dbg[5] = clock64();
+    const int nks = (seg_len + 15) >> 4;
+    const float* xa_p = Xs + g * MK_XSTRIDE + 4 * t;
+    const float* xb_p = xa_p + 8 * MK_XSTRIDE;
+    const float* w_p = Ws + (size_t)g * ws + seg0 + 4 * t;
+    for (int ks = warp; ks < nks; ks += MK_CW) {
+      const int kk = ks << 4;
+      const bool kin = kk + 4 * t < seg_len;   // K % 16 != 0 tail: this thread's four k values are past the row and contribute zeros
+      float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;   // (the whole warp stays in the loop: mma.sync is warp-wide)
+      if (kin) { xa = *reinterpret_cast<const float4*>(xa_p + kk); xb = *reinterpret_cast<const float4*>(xb_p + kk); }
+      uint32_t ah[8], al[8];
+      split_tf32(xa.x, ah[0], al[0]); split_tf32(xb.x, ah[1], al[1]); split_tf32(xa.y, ah[2], al[2]); split_tf32(xb.y, ah[3], al[3]);
+      split_tf32(xa.z, ah[4], al[4]); split_tf32(xb.z, ah[5], al[5]); split_tf32(xa.w, ah[6], al[6]); split_tf32(xb.w, ah[7], al[7]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if (i < nt) {
+          float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kin && i * 8 + g < srows) w = *reinterpret_cast<const float4*>(w_p + (size_t)i * 8 * ws + kk);
+          uint32_t bh[4], bl[4];
+          split_tf32(w.x, bh[0], bl[0]); split_tf32(w.y, bh[1], bl[1]); split_tf32(w.z, bh[2], bl[2]); split_tf32(w.w, bh[3], bl[3]);
+          mma_tf32(acc[i], al[0], al[1], al[2], al[3], bh[0], bh[1]);
+          mma_tf32(acc[i], ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
+          mma_tf32(acc[i], ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
+          mma_tf32(acc[i], al[4], al[5], al[6], al[7], bh[2], bh[3]);
+          mma_tf32(acc[i], ah[4], ah[5], ah[6], ah[7], bl[2], bl[3]);
+          mma_tf32(acc[i], ah[4], ah[5], ah[6], ah[7], bh[2], bh[3]);
+        }
       }
     }
   }
-  float acc[NG];
-  if (nseg == 1) {
-    const int KS = K;
-    if (restage) stage_input<R>(op, a, X, Xs, KS, m0, 0, K, warp, lane);
-    cons_sync();   // rows staged; also: everyone left the previous unit's epilogue (red_s is about to be rewritten)
-    for (int g = 0; g < groups; ++g) {
+  // partial tiles -> red_s [warp][16 rows][8 * nt columns]
+  {
+    const int rw = 8 * nt;
+    float* r = red_s + warp * 16 * MK_MAX_FU;
 #pragma unroll
-      for (int i = 0; i < NG; ++i) acc[i] = 0.f;
-      fma_group<R>(Xs, KS, Ws, K, K, g, feats, warp, lane, acc);
-      reduce_store<R>(acc, red_s + (g * 8 + warp) * 64, lane);
+    for (int i = 0; i < 3; ++i) {
+      if (i < nt) {
+        *reinterpret_cast<float2*>(r + g * rw + i * 8 + 2 * t) = make_float2(acc[i][0], acc[i][1]);
+        *reinterpret_cast<float2*>(r + (g + 8) * rw + i * 8 + 2 * t) = make_float2(acc[i][2], acc[i][3]);
+      }
     }
-  } else {   // long rows (host guarantees one feature group): accumulators persist over the segments
-#pragma unroll
-    for (int i = 0; i < NG; ++i) acc[i] = 0.f;
-    for (int sg = 0; sg < nseg; ++sg) {
-      const int seg0 = sg * seg_max, seg_len = min(seg_max, K - seg0);
-      if (sg) cons_sync();   // everyone is done reading the previous segment
-      stage_input<R>(op, a, X, Xs, seg_max, m0, seg0, seg_len, warp, lane);
-      cons_sync();
-      fma_group<R>(Xs, seg_max, Ws + seg0, K, seg_len, 0, feats, warp, lane, acc);
-    }
-    reduce_store<R>(acc, red_s + warp * 64, lane);
   }
   cons_sync();
-  float* Y = op.y_ext == MK_EXT_XPREV ? a.x_prev : op.Y;
+  if (dbg && tid == 0) dbg[6] = clock64();
+  if (e.valid) {
+    const int rw = 8 * nt;
+    const int i = e.m - m0, j = e.n - n0;
+    const float* r = red_s + i * rw + j;
+    float v = 0.f, gt = 0.f;
 #pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    const int o = tid + 256 * e;
-    if (o < total && pv[e]) {
-      const int g = o / NG, rem = o - g * NG;
-      const float* r = red_s + g * 8 * 64 + rem;
-      float v = ((r[0] + r[64]) + (r[128] + r[192])) + ((r[256] + r[320]) + (r[384] + r[448]));
-      v += pb[e];
-      if (op.act == 1) v = fmaxf(v, 0.f);
-      else if (op.act == 2) v = silu_f(v);
-      v += pr[e];
-      const int m = pm[e], n = pn[e];
-      if (op.epi == MK_EPI_DDPM) {   // v = eps: x0 = a x - b eps; mean = c1 x0 + c2 x; + [t > 0] exp(0.5 logvar) noise (ddpm_update_kernel)
-        const int t = a.t, T = a.T;
-        const float ca = __ldg(a.tab + t), cb = __ldg(a.tab + T + t), c1 = __ldg(a.tab + 2 * T + t), c2 = __ldg(a.tab + 3 * T + t),
-                    lv = __ldg(a.tab + 4 * T + t);
-        const float sig = (t == 0 ? 0.f : 1.f) * expf(0.5f * lv);
-        const long long idx = (long long)m * op.nout + n;
-        const float x = __ldcg(a.x_t + idx);
-        const float x0 = __fsub_rn(__fmul_rn(ca, x), __fmul_rn(cb, v));
-        const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, x));
-        Y[idx] = __fadd_rn(mean, __fmul_rn(sig, __ldcg(a.noise + idx)));
-      } else if (op.bcast_rows > 0) {
-        for (int rr = 0; rr < op.bcast_rows; ++rr) Y[(long long)rr * op.ldy + n] = v;
-      } else {
-        Y[(long long)m * op.ldy + n] = v;
-      }
+    for (int w = 0; w < MK_CW; ++w) v += r[w * 16 * MK_MAX_FU];
+    if (geglu) {
+#pragma unroll
+      for (int w = 0; w < MK_CW; ++w) gt += r[w * 16 * MK_MAX_FU + feats];
+      v = (v + e.b) * gelu_erf(gt + e.b2);
+      e.b = 0.f;
     }
+    epi_store(op, a, e, v);
+  }
+  if (dbg && tid == 0) dbg[7] = clock64();
+}
+
+// one unit of a one-row LIN op: features [n0, n0+feats) of the row staged in Xs; feats <= 16, a group of 16 / feats warps per feature
+__device__ void lin_unit1(const MkOp& op, const MkArgs& a, float* Xs, const float* Ws, float* red_s, int n0, int feats, bool restage, int tid) {
+  const int warp = tid >> 5, lane = tid & 31;
+  const int K = op.K, ws = K + MK_PAD;
+  const float* X = resolve_x(op, a);
+  EpiPre e;
+  if (tid < feats) {
+    e.m = 0; e.n = n0 + tid; e.valid = true;
+    if (op.bias) e.b = __ldg(op.bias + e.n);
+    if (op.res) e.r = __ldcg(op.res + e.n);
+    if (op.res2) e.r += __ldcg(op.res2 + e.n);
+  }
+  if (restage) stage_row1(op, a, X, Xs, tid);
+  cons_sync();
+  const int parts = MK_CW / feats;       // warps per feature
+  const int j = warp % feats, part = warp / feats;
+  if (part < parts) {
+    const int nq = K >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(Xs);
+    const float4* w4 = reinterpret_cast<const float4*>(Ws + (size_t)j * ws);
+    float s0 = 0.f, s1 = 0.f;
+    int q = part * 32 + lane;
+    for (; q + parts * 32 < nq; q += 2 * parts * 32) {
+      const float4 xa = x4[q], wa = w4[q], xb = x4[q + parts * 32], wb = w4[q + parts * 32];
+      s0 = fmaf(xa.x, wa.x, fmaf(xa.y, wa.y, fmaf(xa.z, wa.z, fmaf(xa.w, wa.w, s0))));
+      s1 = fmaf(xb.x, wb.x, fmaf(xb.y, wb.y, fmaf(xb.z, wb.z, fmaf(xb.w, wb.w, s1))));
+    }
+    if (q < nq) {
+      const float4 xa = x4[q], wa = w4[q];
+      s0 = fmaf(xa.x, wa.x, fmaf(xa.y, wa.y, fmaf(xa.z, wa.z, fmaf(xa.w, wa.w, s0))));
+    }
+    float s = s0 + s1;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) red_s[part * 16 + j] = s;
+  }
+  cons_sync();
+  if (e.valid) {
+    float v = 0.f;
+    for (int p = 0; p < parts; ++p) v += red_s[p * 16 + tid];
+    epi_store(op, a, e, v);
   }
 }
 
-__device__ __forceinline__ int first_unit(const MkOp& op, int cta, int G) {
-  int f = (cta - op.unit_begin % G) % G;
+__device__ __forceinline__ int first_unit(int unit_begin, int cta, int G) {
+  int f = (cta - unit_begin % G) % G;
   return f < 0 ? f + G : f;
+}
+
+// Where the weight ring's feeder stands in the program (shared memory; only warp MK_CW - 1 touches it).
+struct Feeder {
+  int s, oi, u;      // next unit to issue: stage, op inside the stage, unit of the op (-1: op not entered yet)
+  unsigned issued;   // units issued so far == sequence number of the next one
+};
+
+// Issue this CTA's next weight slices until the ring is full: unit q goes to slot q % MK_SLOTS, which is free once unit
+// q - MK_SLOTS is complete (`completed` units are: the caller has passed their last shared-memory read in program order).
+// One bulk copy per feature row into the padded slot layout.  Called by the whole feeder warp; a call with a full ring costs a
+// few instructions, and the calls that do issue run in the shadow of the stage barrier.
+__device__ __noinline__ void feed(const MkArgs& a, Feeder* f, unsigned completed, uint8_t* Wslots, uint64_t* full_bar, int cta, int G, int lane) {
+  unsigned issued = f->issued;
+  if (issued >= completed + MK_SLOTS) return;
+  int s = f->s, oi = f->oi, u = f->u;
+  while (issued < completed + MK_SLOTS && s < a.n_stages) {
+    const int4 st = __ldg(reinterpret_cast<const int4*>(a.stages + s));   // op_begin, n_a, n_b, bg_wait
+    if (oi >= st.y + st.z) { ++s; oi = 0; u = -1; continue; }
+    const MkOp* op = a.ops + st.x + oi;
+    if (__ldg(&op->type) != MK_T_LIN) { ++oi; u = -1; continue; }
+    const int4 shp = __ldg(reinterpret_cast<const int4*>(&op->type));      // type, M, K, nout
+    const int4 pl = __ldg(reinterpret_cast<const int4*>(&op->x_ext));      // x_ext, y_ext, FU, n_slices
+    const int4 un = __ldg(reinterpret_cast<const int4*>(&op->row_tiles));  // row_tiles, units, unit_begin, rclass
+    if (u < 0) u = first_unit(un.z, cta, G);
+    if (u >= un.y) { ++oi; u = -1; continue; }
+    const int K = shp.z, nout = shp.w, FU = pl.z;
+    const bool geglu = __ldg(&op->epi) == MK_EPI_GEGLU;
+    const float* W = reinterpret_cast<const float*>(__ldg(reinterpret_cast<const unsigned long long*>(&op->W)));
+    const int n0 = (u % pl.w) * FU;
+    const int feats = min(FU, nout - n0);
+    const int srows = geglu ? 2 * feats : feats;
+    const unsigned slot = issued % MK_SLOTS;
+    if (lane == 0) mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)srows * (uint32_t)K * 4u);
+    __syncwarp();
+    if (lane < srows) {
+      const int row = lane < feats ? n0 + lane : nout + n0 + (lane - feats);
+      bulk_g2s(Wslots + slot * MK_SLOT_BYTES + (size_t)lane * (K + MK_PAD) * 4, W + (size_t)row * K, (uint32_t)K * 4u, &full_bar[slot]);
+    }
+    ++issued;
+    u += G;
+  }
+  __syncwarp();
+  if (lane == 0) { f->s = s; f->oi = oi; f->u = u; f->issued = issued; }
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(MK_THREADS, 1) layout_mk_kernel(const MkArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   float* Xs = reinterpret_cast<float*>(smem);
-  uint8_t* Wslots = smem + SM_W;
+  uint8_t* Wslots = smem + SM_X;
   float* red_s = reinterpret_cast<float*>(smem + SM_RED);
   MkOp* ops_s = reinterpret_cast<MkOp*>(smem + SM_OPS);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM_BAR);
-  uint64_t* empty_bar = full_bar + MK_SLOTS;
+  Feeder* feeder = reinterpret_cast<Feeder*>(full_bar + MK_SLOTS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x, cta = blockIdx.x;
   if (tid == 0) {
-    for (int i = 0; i < MK_SLOTS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 8); }
+    for (int i = 0; i < MK_SLOTS; ++i) mbar_init(&full_bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    feeder->s = 0; feeder->oi = 0; feeder->u = -1; feeder->issued = 0;
   }
   __syncthreads();
   const unsigned epoch = *a.epoch + 1u;
   const unsigned target = epoch * (unsigned)G;
+  const bool is_feeder = warp == MK_CW - 1;
 
-  if (warp == 8) {
-    // ================= producer: this CTA's weight slices, in program order, as far ahead as the ring allows =================
-    if (lane == 0) {
-      unsigned seq = 0;
-      for (int s = 0; s < a.n_stages; ++s) {
-        const MkStage st = a.stages[s];
-        for (int oi = 0; oi < st.n_a + st.n_b; ++oi) {
-          const MkOp* op = a.ops + st.op_begin + oi;
-          if (op->type != MK_T_LIN) continue;
-          const int units = op->units, FU = op->FU, n_slices = op->n_slices, K = op->K, nout = op->nout;
-          const float* W = op->W;
-          for (int u = first_unit(*op, cta, G); u < units; u += G) {
-            const int n0 = (u % n_slices) * FU;
-            const int feats = min(FU, nout - n0);
-            const unsigned slot = seq % MK_SLOTS, ph = (seq / MK_SLOTS) & 1u;
-            mbar_wait(&empty_bar[slot], ph ^ 1u);
-            const uint32_t bytes = (uint32_t)feats * (uint32_t)K * 4u;
-            mbar_arrive_expect_tx(&full_bar[slot], bytes);
-            bulk_g2s(Wslots + slot * MK_SLOT_BYTES, W + (size_t)n0 * K, bytes, &full_bar[slot]);
-            ++seq;
-          }
-        }
-      }
-    }
-    return;
-  }
-
-  // ================= consumers =================
-  unsigned seq = 0;
+  unsigned seq = 0;   // units this CTA has completed
   for (int s = 0; s < a.n_stages; ++s) {
     const MkStage st = a.stages[s];
     const int n_ops = st.n_a + st.n_b;
     {   // this stage's op records -> shared memory (constants: fetched while the barrier is still filling)
       const uint4* src = reinterpret_cast<const uint4*>(a.ops + st.op_begin);
       uint4* dst = reinterpret_cast<uint4*>(ops_s);
-      for (int i = tid; i < n_ops * 16; i += 256) dst[i] = __ldg(src + i);
+      for (int i = tid; i < n_ops * 16; i += MK_CT) dst[i] = __ldg(src + i);
     }
+    // weights are constants: the ring is topped up (two to three stages ahead) while the barrier fills
+    if (is_feeder) feed(a, feeder, seq, Wslots, full_bar, cta, G, lane);
+    long long* dbg = a.dbg ? a.dbg + ((long long)cta * a.n_stages + s) * 8 : nullptr;
     if (tid == 0) {
+      if (dbg) dbg[0] = clock64();
       if (s > 0) wait_counter(a.bar + s - 1, target, a.err);
       if (st.bg_wait >= 0) wait_counter(a.bg + st.bg_wait, target, a.err);
     }
     cons_sync();
+    if (dbg && tid == 0) dbg[1] = clock64();
     int staged = -1;
     for (int oi = 0; oi <= n_ops; ++oi) {
       if (oi == st.n_a) {   // the stage's foreground ops are done in this CTA
         cons_sync();
-        if (tid == 0) arrive_counter(a.bar + s);
+        if (tid == 0) {
+          if (dbg) dbg[2] = clock64();
+          arrive_counter(a.bar + s);
+        }
       }
       if (oi == n_ops) break;
       const MkOp& op = ops_s[oi];
       if (op.type == MK_T_LIN) {
-        for (int u = first_unit(op, cta, G); u < op.units; u += G) {
+        for (int u = first_unit(op.unit_begin, cta, G); u < op.units; u += G) {
           const int slice = u % op.n_slices, rt = u / op.n_slices;
           const int n0 = slice * op.FU, feats = min(op.FU, op.nout - n0);
           const unsigned slot = seq % MK_SLOTS, ph = (seq / MK_SLOTS) & 1u;
           const int key = oi * 64 + rt;
           const bool restage = staged != key;
+          if (is_feeder) feed(a, feeder, seq, Wslots, full_bar, cta, G, lane);   // several units per stage: keep the ring moving
           mbar_wait(&full_bar[slot], ph);
+          if (dbg && tid == 0) dbg[4] = clock64();
           const float* Ws = reinterpret_cast<const float*>(Wslots + slot * MK_SLOT_BYTES);
-          if (op.rclass == 16) lin_unit<16>(op, a, Xs, Ws, red_s, rt * 16, n0, feats, restage, tid);
-          else if (op.rclass == 8) lin_unit<8>(op, a, Xs, Ws, red_s, 0, n0, feats, restage, tid);
-          else lin_unit<1>(op, a, Xs, Ws, red_s, 0, n0, feats, restage, tid);
-          // every warp passed the barrier in front of the epilogue, i.e. finished reading the slot
-          if (lane == 0) mbar_arrive(&empty_bar[slot]);
-          const int seg_max = ((MK_XCAP / op.rclass) >> 7) << 7;
-          staged = op.K <= seg_max ? key : -1;
+          if (op.rclass == 16) lin_unit16(op, a, Xs, Ws, red_s, rt * 16, n0, feats, restage, tid, dbg);
+          else lin_unit1(op, a, Xs, Ws, red_s, n0, feats, restage, tid);
+          // every warp passed the barrier in front of the epilogue, i.e. finished reading the slot: unit `seq` is complete
+          staged = (op.rclass == 1 || op.K <= MK_XROW) ? key : -1;
           ++seq;
         }
       } else {
         const float* X = resolve_x(op, a);
-        for (int u = first_unit(op, cta, G); u < op.units; u += G) {
+        for (int u = first_unit(op.unit_begin, cta, G); u < op.units; u += G) {
           const int m0 = u * 16, rows = min(16, op.M - m0), kq = op.K >> 2;
-          for (int e = tid; e < rows * kq; e += 256) {
+          for (int e = tid; e < rows * kq; e += MK_CT) {
             const int i = e / kq, q = e - i * kq, m = m0 + i;
             float4 v;
             if (op.type == MK_T_COPY) v = ld4(X + (long long)m * op.ldx + 4 * q);
@@ -461,6 +570,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) layout_mk_kernel(const MkArgs a
       if (tid == 0) arrive_counter(a.bg + st.bg_arrive);
     }
     cons_sync();   // ops_s is rewritten by the next stage
+    if (dbg && tid == 0) dbg[3] = clock64();
   }
   if (cta == 0 && tid == 0) *a.epoch = epoch;
 }
@@ -498,21 +608,28 @@ void mk_plan_op(MkOp& op, int ctas) {
   }
   ECHO_CHECK(op.M >= 1 && op.K >= 4 && op.K % 4 == 0 && op.nout >= 1 && op.ldx % 4 == 0, "layout program: bad linear op (M=%d K=%d nout=%d)", op.M,
              op.K, op.nout);
-  op.rclass = op.M == 1 ? 1 : (op.M <= 8 ? 8 : 16);
+  const bool geglu = op.epi == MK_EPI_GEGLU;
+  // one-row ops without a row-wise prologue (the time path; also a one-node graph's plain layers) are fp32 dot products
+  const bool plain1 = op.M == 1 && (op.pro == MK_NONE || op.pro == MK_SILU || op.pro == MK_TEMB) && !op.X2 && !geglu && op.epi == MK_EPI_LIN &&
+                      op.K + MK_PAD <= 16 * MK_XSTRIDE;
+  op.rclass = plain1 ? 1 : 16;
   op.row_tiles = op.rclass == 16 ? cdiv(op.M, 16) : 1;
-  int cap = (MK_SLOT_BYTES / (op.K * 4)) / 4 * 4;
-  ECHO_CHECK(cap >= 4, "layout program: K=%d too long for a weight slot", op.K);
-  cap = cap > MK_MAX_FU ? MK_MAX_FU : cap;
-  const int seg_max = ((MK_XCAP / op.rclass) >> 7) << 7;
-  if (op.K > seg_max) {
-    ECHO_CHECK(op.pro == MK_NONE || op.pro == MK_SILU || op.pro == MK_GEGLU, "layout program: prologue %d needs the whole row staged (K=%d)", op.pro, op.K);
-    cap = 4;
+  const int per_feat = geglu ? 2 : 1;   // weight rows a feature brings into the slot
+  int cap = MK_SLOT_BYTES / ((op.K + MK_PAD) * 4) / per_feat;
+  const int hard = (op.rclass == 1 ? 16 : MK_MAX_FU) / per_feat;
+  cap = cap > hard ? hard : cap;
+  ECHO_CHECK(cap >= 1, "layout program: K=%d too long for a weight slot", op.K);
+  if (op.rclass == 16) {
+    ECHO_CHECK(op.pro != MK_TEMB, "layout program: the timestep embedding is a one-row prologue");
+    if (op.K > MK_XROW)
+      ECHO_CHECK(op.pro == MK_NONE || op.pro == MK_SILU, "layout program: prologue %d needs the whole row staged (K=%d)", op.pro, op.K);
+    ECHO_CHECK(op.bcast_rows == 0, "layout program: broadcast store needs a one-row op");
   }
   if (op.pro == MK_GN) ECHO_CHECK(op.K % 128 == 0 && op.cpg >= 4 && op.cpg <= 128 && (op.cpg & (op.cpg - 1)) == 0, "layout program: GroupNorm prologue K=%d cpg=%d", op.K, op.cpg);
   if (op.pro == MK_LN) ECHO_CHECK(op.K <= 1280, "layout program: LayerNorm prologue K=%d", op.K);
-  if (op.X2) ECHO_CHECK(op.K1 % 4 == 0 && op.K1 > 0 && op.K1 < op.K && op.ldx2 % 4 == 0 && op.pro != MK_GEGLU && op.pro != MK_LN, "layout program: bad concat input");
-  if (op.bcast_rows > 0) ECHO_CHECK(op.M == 1, "layout program: broadcast store needs a one-row op");
-  int want = 4 * cdiv((int64_t)op.nout * op.row_tiles, 4 * (int64_t)ctas);
+  if (op.X2) ECHO_CHECK(op.K1 % 4 == 0 && op.K1 > 0 && op.K1 < op.K && op.ldx2 % 4 == 0 && op.pro != MK_LN && op.pro != MK_EDGE && op.pro != MK_POOL, "layout program: bad concat input");
+  if (geglu) ECHO_CHECK(op.act == 0 && !op.res && !op.res2 && op.bias, "layout program: GEGLU epilogue takes bias only");
+  int want = cdiv((int64_t)op.nout * op.row_tiles, (int64_t)ctas);
   want = want < 4 ? 4 : want;
   op.FU = want > cap ? cap : want;
   op.n_slices = cdiv(op.nout, op.FU);

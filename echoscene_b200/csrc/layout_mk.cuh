@@ -14,12 +14,15 @@ enum MkPro : int {
   MK_SILU = 1,
   MK_GN = 2,      // GroupNorm(32 groups)(+SiLU) over the (concatenated) channels of a row
   MK_LN = 3,      // LayerNorm
-  MK_GEGLU = 4,   // x[k] = a[k] * gelu_erf(g[k]), [a | g] the two halves of a 2K-wide row
   MK_EDGE = 5,    // rows = triples: relu(Ps[s_t] + Pp[t] + Po[o_t] + b1)            (graph.py:146-156, re-associated)
   MK_POOL = 6,    // rows = nodes: mean over the node's CSR items of t2 rows          (graph.py:161-199)
   MK_TEMB = 7,    // row 0 = timestep_embedding(t)                                    (ldm_diffusion_util.py:174-194)
 };
-enum MkEpi : int { MK_EPI_LIN = 0, MK_EPI_DDPM = 1 };
+enum MkEpi : int {
+  MK_EPI_LIN = 0,
+  MK_EPI_DDPM = 1,
+  MK_EPI_GEGLU = 2,   // W = [2 nout][K]: y[n] = (w[n].x + b[n]) * gelu_erf(w[nout + n].x + b[nout + n])   (attention.py GEGLU)
+};
 enum MkExt : int { MK_EXT_NONE = 0, MK_EXT_XT = 1, MK_EXT_OBJ = 2, MK_EXT_XPREV = 3 };
 
 struct alignas(16) MkOp {
@@ -75,11 +78,14 @@ struct MkArgs {
   const int* node_items;
   const long long* triples;
   int H;
+  long long* dbg;    // diagnostics (ECHO_MK_TIMELINE): [cta][stage][8] SM clocks: stage entered, barrier passed, foreground ops done, stage left; of the stage's
+                     // last 16-row unit: weights landed, rows staged, contraction done, epilogue done
 };
 
-constexpr int MK_SLOT_BYTES = 40960;   // one staged weight slice: FU rows x K floats
-constexpr int MK_MAX_FU = 20;
-constexpr int MK_XCAP = 16 * 1280;     // floats of staged input: 16 rows x 1280 (or fewer rows x more columns)
+constexpr int MK_PAD = 16;             // floats of padding behind every staged row (activations and weights): conflict-free LDS.128
+constexpr int MK_SLOT_BYTES = 36864;   // one staged weight slice: up to MK_MAX_FU rows x (K + MK_PAD) floats
+constexpr int MK_MAX_FU = 24;          // weight rows of a unit (three 8-feature MMA tiles)
+constexpr int MK_XROW = 1280;          // staged columns of a 16-row tile per pass (longer rows go in segments)
 constexpr int MK_MAX_STAGE_OPS = 8;
 
 // host: fills FU / n_slices / row_tiles / units / rclass of a LIN op for a grid of `ctas`

@@ -80,6 +80,15 @@ struct echo_shape {
     void* scratch = nullptr;
     void* splitk_ws = nullptr;
     if (stride_hw == 2 && prec == ECHO_PREC_BF16 && x.dt == BF16) scratch = arena.alloc(x.bytes());
+    // split-precision mode: the fp32 input as hi + lo bf16 halves (every voxel-major contraction whose shape the tcgen05 kernel takes)
+    const bool x3 = prec == ECHO_PREC_X3 && w.wb_lo && x.dt == F32 && out.dt == F32 && x.c % 16 == 0 && w.cout % 32 == 0;
+    __nv_bfloat16 *a_hi = nullptr, *a_lo = nullptr;
+    if (x3) {
+      const size_t half = (size_t)x.rows() * x.c * sizeof(__nv_bfloat16);
+      a_hi = (__nv_bfloat16*)arena.alloc(half);
+      a_lo = (__nv_bfloat16*)arena.alloc(half);
+      if (stride_hw == 2) scratch = arena.alloc(2 * half);   // space-to-depth copies of both halves
+    }
     if (k == 3 && stride_hw == 1 && prec == ECHO_PREC_BF16 && x.dt == BF16 && out.dt == BF16 && (!res || res->dt == BF16)) {
       GemmArgs q;   // coarse levels: offer a workspace so the plan may split the taps over more CTAs
       q.n = x.n; q.od = out.d; q.oh = out.h; q.ow = out.w; q.kd = q.kh = q.kw = 3; q.sh = q.sw = 1; q.cout = w.cout;
@@ -104,6 +113,16 @@ struct echo_shape {
       t.colsum = out.colsum;
       t.splitk_ws = splitk_ws;
       if (gemm_tc_supported(t)) { gemm_tc(t, s); return; }
+    }
+    if (x3) {
+      GemmArgs t = g;
+      t.A = a_hi; t.A_lo = a_lo; t.a_dt = BF16;
+      t.W = w.wb; t.W_lo = w.wb_lo; t.w_dt = BF16;
+      ECHO_CHECK(gemm_tc_supported(t), "contract: split-precision contraction cin=%d cout=%d k=%d stride=%d not supported by the tcgen05 kernel",
+                 x.c, w.cout, k, stride_hw);
+      split_bf16((const float*)x.p, x.rows() * x.c, a_hi, a_lo, s);
+      gemm_tc(t, s);
+      return;
     }
     ECHO_CHECK(!out.colsum, "contract: column statistics were requested but the contraction left the tcgen05 path");
     gemm_simt(g, s);
@@ -489,9 +508,9 @@ echo_shape* shape_create(const echo_shape_desc_t* desc, const echo_weight_t* wei
     ECHO_CHECK(d.max_nodes > 0 && d.max_local_nodes > 0 && d.max_local_nodes <= d.max_nodes, "shape: bad capacities");
     ECHO_CHECK(d.model_channels % 32 == 0 && d.num_levels >= 1 && d.num_levels <= 8, "shape: bad config");
     h->prec = d.precision;
-    ECHO_CHECK(h->prec == ECHO_PREC_FP32 || h->prec == ECHO_PREC_BF16, "shape: unknown precision %d", h->prec);
-    if (h->prec == ECHO_PREC_BF16 && !tc_available())
-      fail(ECHO_ERR_UNSUPPORTED, "shape: ECHO_PREC_BF16 needs the sm_100a tcgen05 kernels on a B200-class device");
+    ECHO_CHECK(h->prec == ECHO_PREC_FP32 || h->prec == ECHO_PREC_BF16 || h->prec == ECHO_PREC_X3, "shape: unknown precision %d", h->prec);
+    if (h->prec != ECHO_PREC_FP32 && !tc_available())
+      fail(ECHO_ERR_UNSUPPORTED, "shape: ECHO_PREC_BF16 / ECHO_PREC_X3 need the sm_100a tcgen05 kernels on a B200-class device");
     h->adt = h->prec == ECHO_PREC_BF16 ? BF16 : F32;
     WeightMap wm;
     wm.load(weights, n_weights);
@@ -503,6 +522,7 @@ echo_shape* shape_create(const echo_shape_desc_t* desc, const echo_weight_t* wei
     cfg.attention_resolutions.assign(d.attention_resolutions, d.attention_resolutions + d.num_attention_resolutions);
     cfg.num_res_blocks = d.num_res_blocks; cfg.num_heads = d.num_heads; cfg.context_dim = d.context_dim;
     cfg.want_bf16 = h->prec == ECHO_PREC_BF16;
+    cfg.want_x3 = h->prec == ECHO_PREC_X3;
     build_unet_plan(wm, cfg, h->pool, h->plan, s);
 
     const int mc = d.model_channels, E = 4 * mc, gd = d.gconv_dim, ctx = d.context_dim;
