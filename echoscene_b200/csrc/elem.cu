@@ -1052,6 +1052,16 @@ void gn_apply_cs(const Act& xa, const Act* xb, const float* gamma, const float* 
   // coarse levels are latency-, not bandwidth-bound)
   int rows_per_block = 16 * RY;
   while (rows_per_block > 2 * RY && (int64_t)cdiv(V, rows_per_block) * xa.n < 2 * 148) rows_per_block -= 2 * RY;
+  {   // never a second, nearly empty wave (464 blocks on 444 resident slots cost 2x): grow the blocks until the grid is resident at once
+    static int resident = 0;
+    if (!resident) {
+      int per_sm = 0, sms = 148;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_apply_cs_kernel, 256, 4096 + 256);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+      resident = (per_sm > 0 ? per_sm : 2) * sms;
+    }
+    while ((int64_t)cdiv(V, rows_per_block) * xa.n > resident && rows_per_block < V) rows_per_block += 4 * RY;
+  }
   dim3 grid(cdiv(V, rows_per_block), xa.n);
   const size_t smem = (size_t)(C / 7 > threads ? C / 7 : threads) * 2 * sizeof(double) + (size_t)groups * 2 * sizeof(float);
   launch_pdl(gn_apply_cs_kernel, grid, dim3(threads), smem, s, (const __nv_bfloat16*)xa.p, xa.c, (const float*)xa.colsum,

@@ -64,6 +64,11 @@ struct echo_layout {
   std::vector<MkStage> mk_stages;
   MkOp* d_mk_ops = nullptr;
   MkStage* d_mk_stages = nullptr;
+  std::vector<MkFetch> mk_fetch;       // every CTA's weight fetches in consumption order (mk_build_fetch)
+  std::vector<int> mk_fetch_off;
+  MkFetch* d_mk_fetch = nullptr;
+  int* d_mk_fetch_off = nullptr;
+  static constexpr int MK_MAX_FETCH = 1 << 16;
   unsigned* d_mk_counters = nullptr;   // [MK_MAX_STAGES] stage counters, [MK_MAX_BG] background counters, [1] epoch
   std::vector<float*> mk_bufs;         // activation buffers of the program, allocated once at capacity in program order
   size_t mk_buf_i = 0;
@@ -272,7 +277,7 @@ void echo_layout::build_mk(int Nn, int T) {
     for (auto* v : {&A, &B})
       for (auto& o : *v) {
         mk_plan_op(o, mk_ctas);
-        o.unit_begin = ub;
+        o.unit_begin = ub % mk_ctas;   // the CTA that runs the op's first unit
         ub += o.units;
         mk_ops.push_back(o);
       }
@@ -507,6 +512,8 @@ void echo_layout::build_mk(int Nn, int T) {
   ECHO_CHECK(pending.empty(), "layout program: %d emb_layers projections were never scheduled", (int)pending.size());
   ECHO_CHECK((int)mk_stages.size() <= MK_MAX_STAGES && (int)mk_ops.size() <= MK_MAX_OPS, "layout program too long (%d stages, %d ops)",
              (int)mk_stages.size(), (int)mk_ops.size());
+  mk_build_fetch(mk_ops, mk_stages, mk_ctas, mk_fetch, mk_fetch_off);
+  ECHO_CHECK((int)mk_fetch.size() <= MK_MAX_FETCH, "layout program: %d weight fetches exceed the table", (int)mk_fetch.size());
   mk_N = Nn;
   mk_T = T;
 }
@@ -520,11 +527,14 @@ void echo_layout::step_mk(const echo_graph* g, const float* x_t, const float* ob
     ECHO_CUDA(cudaMemsetAsync(d_mk_counters, 0, sizeof(unsigned) * (MK_MAX_STAGES + MK_MAX_BG + 2), s));
     ECHO_CUDA(cudaMemcpyAsync(d_mk_ops, mk_ops.data(), sizeof(MkOp) * mk_ops.size(), cudaMemcpyHostToDevice, s));
     ECHO_CUDA(cudaMemcpyAsync(d_mk_stages, mk_stages.data(), sizeof(MkStage) * mk_stages.size(), cudaMemcpyHostToDevice, s));
+    ECHO_CUDA(cudaMemcpyAsync(d_mk_fetch, mk_fetch.data(), sizeof(MkFetch) * mk_fetch.size(), cudaMemcpyHostToDevice, s));
+    ECHO_CUDA(cudaMemcpyAsync(d_mk_fetch_off, mk_fetch_off.data(), sizeof(int) * mk_fetch_off.size(), cudaMemcpyHostToDevice, s));
     ECHO_CUDA(cudaStreamSynchronize(s));   // the host vectors may be rebuilt before an asynchronous copy would have read them
   }
   MkArgs a;
   memset(&a, 0, sizeof(a));
   a.ops = d_mk_ops; a.stages = d_mk_stages; a.n_stages = (int)mk_stages.size();
+  a.fetch = d_mk_fetch; a.fetch_off = d_mk_fetch_off;
   static const int max_stages = getenv("ECHO_MK_MAX_STAGES") ? atoi(getenv("ECHO_MK_MAX_STAGES")) : 0;   // debugging: run a prefix
   if (max_stages > 0 && max_stages < a.n_stages) a.n_stages = max_stages;
   a.bar = d_mk_counters; a.bg = d_mk_counters + MK_MAX_STAGES; a.epoch = d_mk_counters + MK_MAX_STAGES + MK_MAX_BG;
@@ -534,9 +544,12 @@ void echo_layout::step_mk(const echo_graph* g, const float* x_t, const float* ob
   a.s_idx = g->s_idx; a.o_idx = g->o_idx; a.node_off = g->node_off; a.node_items = g->node_items;
   a.triples = (const long long*)g->triples;
   a.H = gcn.H;
+  static const bool evict_first = !getenv("ECHO_MK_NO_EVICT_FIRST");
+  static const bool fenced = getenv("ECHO_MK_FENCE") != nullptr;   // A/B: __threadfence + atomicAdd instead of red.release
+  a.flags = (evict_first ? 1 : 0) | (fenced ? 2 : 0);
   static const char* timeline = getenv("ECHO_MK_TIMELINE");   // diagnostics: per-CTA per-stage SM clocks of every step -> file (last step wins)
   long long* d_dbg = nullptr;
-  const size_t dbg_n = (size_t)mk_ctas * a.n_stages * 8;
+  const size_t dbg_n = (size_t)mk_ctas * a.n_stages * 12;
   if (timeline) {
     ECHO_CUDA(cudaMalloc(&d_dbg, dbg_n * sizeof(long long)));
     ECHO_CUDA(cudaMemsetAsync(d_dbg, 0, dbg_n * sizeof(long long), s));
@@ -746,6 +759,8 @@ echo_layout* layout_create(const echo_layout_desc_t* desc, const echo_weight_t* 
       if (h->mk_ok) {
         h->d_mk_ops = (MkOp*)h->pool.alloc(sizeof(MkOp) * echo_layout::MK_MAX_OPS);
         h->d_mk_stages = (MkStage*)h->pool.alloc(sizeof(MkStage) * echo_layout::MK_MAX_STAGES);
+        h->d_mk_fetch = (MkFetch*)h->pool.alloc(sizeof(MkFetch) * echo_layout::MK_MAX_FETCH);
+        h->d_mk_fetch_off = (int*)h->pool.alloc(sizeof(int) * (h->mk_ctas + 1));
         h->d_mk_counters = (unsigned*)h->pool.alloc(sizeof(unsigned) * (echo_layout::MK_MAX_STAGES + echo_layout::MK_MAX_BG + 2));
         ECHO_CUDA(cudaMemset(h->d_mk_counters, 0, sizeof(unsigned) * (echo_layout::MK_MAX_STAGES + echo_layout::MK_MAX_BG + 2)));
       }

@@ -45,7 +45,8 @@ constexpr int SM_X = 16 * MK_XSTRIDE * 4;
 constexpr int SM_RED = SM_X + MK_SLOTS * MK_SLOT_BYTES;
 constexpr int SM_OPS = SM_RED + MK_CW * 16 * MK_MAX_FU * 4;
 constexpr int SM_BAR = SM_OPS + MK_MAX_STAGE_OPS * 256;
-constexpr int SM_TOTAL = SM_BAR + 64;
+constexpr int SM_FEED = SM_BAR + 64;
+constexpr int SM_TOTAL = SM_FEED + 320;
 static_assert(SM_TOTAL <= 232448, "shared memory budget of one CTA");
 
 // x * sigmoid(x) with the fast exponential / reciprocal (relative error ~1e-6; the prologue runs redundantly in every CTA)
@@ -66,14 +67,26 @@ __device__ __forceinline__ void wait_counter(const unsigned* p, unsigned target,
     if (++spins > (1u << 27)) { atomicExch(err, 1u); break; }
   }
 }
-__device__ __forceinline__ void arrive_counter(unsigned* p) {
-  __threadfence();
-  atomicAdd(p, 1u);
+// release: the CTA's stores (ordered before this thread by the preceding bar.sync) become visible before the count does
+__device__ __forceinline__ void arrive_counter(unsigned* p, bool fenced) {
+  if (fenced) {
+    __threadfence();
+    atomicAdd(p, 1u);
+  } else {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(1u) : "memory");
+  }
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
-               "r"(bytes), "r"(smem_u32(bar))
+// weights are read once per step: evict-first keeps the 439 MB stream from pushing the few MB of activations out of L2
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy(bool evict_first) {
+  uint64_t p;
+  if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
 }
 // x = hi + lo with hi = x truncated to TF32 (exact subtraction, |lo| < 2^-10 |x|); the tensor core reads the upper 19 bits
 // of an operand register, i.e. truncates lo itself.  hi.hi + lo.hi + hi.lo then drops ~2^-20 |x w| per product.
@@ -98,7 +111,7 @@ __device__ __forceinline__ float4 load_in(const MkOp& op, const float* X, int m,
 
 // LayerNorm of one row by one warp, NJ float4 per lane (row length <= 128 * NJ)
 template <int NJ>
-__device__ __forceinline__ void ln_row(const MkOp& op, const float* X, int m, int nq, float4* xr, int lane) {
+__device__ __forceinline__ void ln_row(const MkOp& op, const float* X, const float* gs, const float* bs, int m, int nq, float4* xr, int lane) {
   float4 v[NJ];
   float s = 0.f;
 #pragma unroll
@@ -127,7 +140,7 @@ __device__ __forceinline__ void ln_row(const MkOp& op, const float* X, int m, in
   for (int j = 0; j < NJ; ++j) {
     const int q = lane + 32 * j;
     if (q < nq) {
-      const float4 gm = __ldg(reinterpret_cast<const float4*>(op.gamma + 4 * q)), bt = __ldg(reinterpret_cast<const float4*>(op.beta + 4 * q));
+      const float4 gm = *reinterpret_cast<const float4*>(gs + 4 * q), bt = *reinterpret_cast<const float4*>(bs + 4 * q);
       float4 o4;
       o4.x = (v[j].x - mean) * rstd * gm.x + bt.x; o4.y = (v[j].y - mean) * rstd * gm.y + bt.y;
       o4.z = (v[j].z - mean) * rstd * gm.z + bt.z; o4.w = (v[j].w - mean) * rstd * gm.w + bt.w;
@@ -138,7 +151,9 @@ __device__ __forceinline__ void ln_row(const MkOp& op, const float* X, int m, in
 
 // rows m0 .. m0+16 of the op's input, prologue applied, columns [seg0, seg0 + seg_len) -> Xs [16][MK_XSTRIDE]; one warp per
 // row, every global load of a row in flight before the first use
-__device__ void stage_rows(const MkOp& op, const MkArgs& a, const float* X, float* Xs, int m0, int seg0, int seg_len, int warp, int lane) {
+// gs / bs: the prologue's scale and shift rows (they arrive with the unit's weight slice)
+__device__ void stage_rows(const MkOp& op, const MkArgs& a, const float* X, float* Xs, const float* gs, const float* bs, int m0, int seg0,
+                           int seg_len, int warp, int lane) {
   const int nq = seg_len >> 2;
   const int m = m0 + warp;
   float4* xr = reinterpret_cast<float4*>(Xs + warp * MK_XSTRIDE);
@@ -163,7 +178,7 @@ __device__ void stage_rows(const MkOp& op, const MkArgs& a, const float* X, floa
           const int q = q0 + lane + 32 * j;
           if (q < nq) {   // warp-uniform (nq % 32 == 0)
             const int k = seg0 + 4 * q;
-            const float4 gm = __ldg(reinterpret_cast<const float4*>(op.gamma + k)), bt = __ldg(reinterpret_cast<const float4*>(op.beta + k));
+            const float4 gm = *reinterpret_cast<const float4*>(gs + k), bt = *reinterpret_cast<const float4*>(bs + k);
             float s = (v[j].x + v[j].y) + (v[j].z + v[j].w);
             for (int o = 1; o < gl; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             const float mean = s * inv;
@@ -181,8 +196,8 @@ __device__ void stage_rows(const MkOp& op, const MkArgs& a, const float* X, floa
       break;
     }
     case MK_LN: {   // whole row by this warp: two-pass statistics in registers (K <= 512: four vectors per lane, else up to ten)
-      if (nq <= 128) ln_row<4>(op, X, m, nq, xr, lane);
-      else ln_row<10>(op, X, m, nq, xr, lane);
+      if (nq <= 128) ln_row<4>(op, X, gs, bs, m, nq, xr, lane);
+      else ln_row<10>(op, X, gs, bs, m, nq, xr, lane);
       break;
     }
     case MK_EDGE: {   // X = [Ps | Po] (N, 2H), aux0 = Pp (T, H), aux1 = folded bias; same association as edge_combine_kernel
@@ -266,33 +281,28 @@ __device__ void stage_row1(const MkOp& op, const MkArgs& a, const float* X, floa
   }
 }
 
-// what a thread needs for its output element, requested before the contraction so that the L2 latency hides under it
-struct EpiPre {
-  float b = 0.f, b2 = 0.f, r = 0.f;
-  int m = 0, n = 0;
-  bool valid = false;
-};
-
-__device__ __forceinline__ void epi_store(const MkOp& op, const MkArgs& a, const EpiPre& e, float v) {
-  v += e.b;
+// the epilogue of one output element (m, n): v = the dot product; eb = bias, er = residual(s), both requested before the
+// contraction so that their L2 latency hides under it
+__device__ __forceinline__ void epi_store(const MkOp& op, const MkArgs& a, int em, int en, float eb, float er, float v) {
+  v += eb;
   if (op.act == 1) v = fmaxf(v, 0.f);
   else if (op.act == 2) v = v / (1.f + expf(-v));
-  v += e.r;
+  v += er;
   float* Y = op.y_ext == MK_EXT_XPREV ? a.x_prev : op.Y;
   if (op.epi == MK_EPI_DDPM) {   // v = eps: x0 = a x - b eps; mean = c1 x0 + c2 x; + [t > 0] exp(0.5 logvar) noise (ddpm_update_kernel)
     const int t = a.t, T = a.T;
     const float ca = __ldg(a.tab + t), cb = __ldg(a.tab + T + t), c1 = __ldg(a.tab + 2 * T + t), c2 = __ldg(a.tab + 3 * T + t),
                 lv = __ldg(a.tab + 4 * T + t);
     const float sig = (t == 0 ? 0.f : 1.f) * expf(0.5f * lv);
-    const long long idx = (long long)e.m * op.nout + e.n;
+    const long long idx = (long long)em * op.nout + en;
     const float x = __ldcg(a.x_t + idx);
     const float x0 = __fsub_rn(__fmul_rn(ca, x), __fmul_rn(cb, v));
     const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, x));
     Y[idx] = __fadd_rn(mean, __fmul_rn(sig, __ldcg(a.noise + idx)));
   } else if (op.bcast_rows > 0) {
-    for (int rr = 0; rr < op.bcast_rows; ++rr) Y[(long long)rr * op.ldy + e.n] = v;
+    for (int rr = 0; rr < op.bcast_rows; ++rr) Y[(long long)rr * op.ldy + en] = v;
   } else {
-    Y[(long long)e.m * op.ldy + e.n] = v;
+    Y[(long long)em * op.ldy + en] = v;
   }
 }
 
@@ -306,16 +316,14 @@ __device__ void lin_unit16(const MkOp& op, const MkArgs& a, float* Xs, const flo
   const int nt = (srows + 7) >> 3;                   // 8-feature MMA tiles (<= 3)
   const int nseg = (K + MK_XROW - 1) / MK_XROW;
   const float* X = resolve_x(op, a);
-  EpiPre e;
-  if (tid < 16 * feats) {
-    const int i = tid / feats, j = tid - i * feats;
-    e.m = m0 + i; e.n = n0 + j;
-    e.valid = e.m < op.M;
-    if (e.valid) {
-      if (op.bias) { e.b = __ldg(op.bias + e.n); if (geglu) e.b2 = __ldg(op.bias + op.nout + e.n); }
-      if (op.res) e.r = __ldcg(op.res + (long long)e.m * op.ld_res + e.n);
-      if (op.res2) e.r += __ldcg(op.res2 + (long long)e.m * op.ld_res2 + e.n);
-    }
+  const int ei = tid / feats, ej = tid - ei * feats;   // this thread's output element
+  const int em = m0 + ei, en = n0 + ej;
+  const bool evalid = tid < 16 * feats && em < op.M;
+  float eb = 0.f, eb2 = 0.f, er = 0.f;
+  if (evalid) {
+    if (op.bias) { eb = __ldg(op.bias + en); if (geglu) eb2 = __ldg(op.bias + op.nout + en); }
+    if (op.res) er = __ldcg(op.res + (long long)em * op.ld_res + en);
+    if (op.res2) er += __ldcg(op.res2 + (long long)em * op.ld_res2 + en);
   }
   float acc[3][4];
 #pragma unroll
@@ -324,7 +332,7 @@ __device__ void lin_unit16(const MkOp& op, const MkArgs& a, float* Xs, const flo
     const int seg0 = sg * MK_XROW, seg_len = min(MK_XROW, K - seg0);
     if (restage || nseg > 1) {
       if (sg) cons_sync();   // everyone is done reading the previous segment
-      stage_rows(op, a, X, Xs, m0, seg0, seg_len, warp, lane);
+      stage_rows(op, a, X, Xs, Ws + (size_t)srows * ws, Ws + (size_t)(srows + 1) * ws, m0, seg0, seg_len, warp, lane);
     }
     cons_sync();   // rows staged; also: everyone left the previous unit's epilogue (red_s is about to be rewritten)
     if (dbg && tid == 0) dbg[5] = clock64();
@@ -371,20 +379,19 @@ __device__ void lin_unit16(const MkOp& op, const MkArgs& a, float* Xs, const flo
   }
   cons_sync();
   if (dbg && tid == 0) dbg[6] = clock64();
-  if (e.valid) {
+  if (evalid) {
     const int rw = 8 * nt;
-    const int i = e.m - m0, j = e.n - n0;
-    const float* r = red_s + i * rw + j;
+    const float* r = red_s + ei * rw + ej;
     float v = 0.f, gt = 0.f;
 #pragma unroll
     for (int w = 0; w < MK_CW; ++w) v += r[w * 16 * MK_MAX_FU];
     if (geglu) {
 #pragma unroll
       for (int w = 0; w < MK_CW; ++w) gt += r[w * 16 * MK_MAX_FU + feats];
-      v = (v + e.b) * gelu_erf(gt + e.b2);
-      e.b = 0.f;
+      v = (v + eb) * gelu_erf(gt + eb2);
+      eb = 0.f;
     }
-    epi_store(op, a, e, v);
+    epi_store(op, a, em, en, eb, er, v);
   }
   if (dbg && tid == 0) dbg[7] = clock64();
 }
@@ -394,12 +401,12 @@ __device__ void lin_unit1(const MkOp& op, const MkArgs& a, float* Xs, const floa
   const int warp = tid >> 5, lane = tid & 31;
   const int K = op.K, ws = K + MK_PAD;
   const float* X = resolve_x(op, a);
-  EpiPre e;
+  const int en = n0 + tid;
+  float eb = 0.f, er = 0.f;
   if (tid < feats) {
-    e.m = 0; e.n = n0 + tid; e.valid = true;
-    if (op.bias) e.b = __ldg(op.bias + e.n);
-    if (op.res) e.r = __ldcg(op.res + e.n);
-    if (op.res2) e.r += __ldcg(op.res2 + e.n);
+    if (op.bias) eb = __ldg(op.bias + en);
+    if (op.res) er = __ldcg(op.res + en);
+    if (op.res2) er += __ldcg(op.res2 + en);
   }
   if (restage) stage_row1(op, a, X, Xs, tid);
   cons_sync();
@@ -426,60 +433,70 @@ __device__ void lin_unit1(const MkOp& op, const MkArgs& a, float* Xs, const floa
     if (lane == 0) red_s[part * 16 + j] = s;
   }
   cons_sync();
-  if (e.valid) {
+  if (tid < feats) {
     float v = 0.f;
     for (int p = 0; p < parts; ++p) v += red_s[p * 16 + tid];
-    epi_store(op, a, e, v);
+    epi_store(op, a, 0, en, eb, er, v);
   }
 }
 
-__device__ __forceinline__ int first_unit(int unit_begin, int cta, int G) {
-  int f = (cta - unit_begin % G) % G;
+// first unit of an op that CTA `cta` runs: units are dealt round-robin starting where the previous op of the stage stopped
+// (ufirst = unit_begin % G, precomputed by the host: no integer division on the device)
+__device__ __forceinline__ int first_unit(int ufirst, int cta, int G) {
+  const int f = cta - ufirst;
   return f < 0 ? f + G : f;
 }
 
-// Where the weight ring's feeder stands in the program (shared memory; only warp MK_CW - 1 touches it).
+// The weight ring's feeder (shared memory; only warp MK_CW - 1 touches it).  The host lists every CTA's weight fetches in
+// consumption order (mk_build_fetch); the next MK_FETCH_AHEAD descriptors sit in shared memory, fetched with cp.async, so
+// that issuing a unit costs no global-memory round trip on the CTA's critical path.
+constexpr int MK_FETCH_AHEAD = 4;
 struct Feeder {
-  int s, oi, u;      // next unit to issue: stage, op inside the stage, unit of the op (-1: op not entered yet)
-  unsigned issued;   // units issued so far == sequence number of the next one
+  MkFetch desc[MK_FETCH_AHEAD];
+  const MkFetch* list;   // this CTA's descriptors
+  unsigned total;        // how many
+  unsigned issued;       // units issued so far == sequence number of the next one
+  long long issue_clk[8];   // diagnostics: SM clock at which unit q was issued, [q % 8]
 };
+static_assert(sizeof(MkFetch) == 48, "a fetch descriptor is three 16-byte cp.async transfers");
+
+__device__ __forceinline__ void feeder_prefetch(Feeder* f, unsigned q, int lane) {   // descriptor q -> desc[q % AHEAD]
+  if (q < f->total && lane < 3)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(reinterpret_cast<uint8_t*>(&f->desc[q % MK_FETCH_AHEAD]) + 16 * lane)),
+                 "l"(reinterpret_cast<const uint8_t*>(f->list + q) + 16 * lane)
+                 : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
 
 // Issue this CTA's next weight slices until the ring is full: unit q goes to slot q % MK_SLOTS, which is free once unit
 // q - MK_SLOTS is complete (`completed` units are: the caller has passed their last shared-memory read in program order).
-// One bulk copy per feature row into the padded slot layout.  Called by the whole feeder warp; a call with a full ring costs a
-// few instructions, and the calls that do issue run in the shadow of the stage barrier.
-__device__ __noinline__ void feed(const MkArgs& a, Feeder* f, unsigned completed, uint8_t* Wslots, uint64_t* full_bar, int cta, int G, int lane) {
+// One bulk copy per feature row into the padded slot layout; the GroupNorm / LayerNorm scale and shift of the op's prologue ride
+// along as two more rows.  Called by the whole feeder warp.
+__device__ __noinline__ void feed(Feeder* f, unsigned completed, uint8_t* Wslots, uint64_t* full_bar, int lane, uint64_t policy) {
   unsigned issued = f->issued;
-  if (issued >= completed + MK_SLOTS) return;
-  int s = f->s, oi = f->oi, u = f->u;
-  while (issued < completed + MK_SLOTS && s < a.n_stages) {
-    const int4 st = __ldg(reinterpret_cast<const int4*>(a.stages + s));   // op_begin, n_a, n_b, bg_wait
-    if (oi >= st.y + st.z) { ++s; oi = 0; u = -1; continue; }
-    const MkOp* op = a.ops + st.x + oi;
-    if (__ldg(&op->type) != MK_T_LIN) { ++oi; u = -1; continue; }
-    const int4 shp = __ldg(reinterpret_cast<const int4*>(&op->type));      // type, M, K, nout
-    const int4 pl = __ldg(reinterpret_cast<const int4*>(&op->x_ext));      // x_ext, y_ext, FU, n_slices
-    const int4 un = __ldg(reinterpret_cast<const int4*>(&op->row_tiles));  // row_tiles, units, unit_begin, rclass
-    if (u < 0) u = first_unit(un.z, cta, G);
-    if (u >= un.y) { ++oi; u = -1; continue; }
-    const int K = shp.z, nout = shp.w, FU = pl.z;
-    const bool geglu = __ldg(&op->epi) == MK_EPI_GEGLU;
-    const float* W = reinterpret_cast<const float*>(__ldg(reinterpret_cast<const unsigned long long*>(&op->W)));
-    const int n0 = (u % pl.w) * FU;
-    const int feats = min(FU, nout - n0);
-    const int srows = geglu ? 2 * feats : feats;
-    const unsigned slot = issued % MK_SLOTS;
-    if (lane == 0) mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)srows * (uint32_t)K * 4u);
+  const unsigned total = f->total;
+  if (issued >= completed + MK_SLOTS || issued >= total) return;
+  while (issued < completed + MK_SLOTS && issued < total) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
-    if (lane < srows) {
-      const int row = lane < feats ? n0 + lane : nout + n0 + (lane - feats);
-      bulk_g2s(Wslots + slot * MK_SLOT_BYTES + (size_t)lane * (K + MK_PAD) * 4, W + (size_t)row * K, (uint32_t)K * 4u, &full_bar[slot]);
+    const MkFetch d = f->desc[issued % MK_FETCH_AHEAD];
+    const unsigned slot = issued % MK_SLOTS;
+    const int srows = d.rows0 + d.rows1, all = srows + d.naux;
+    if (lane == 0) mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)all * (uint32_t)d.K * 4u);
+    __syncwarp();
+    if (lane < all) {
+      const float* src = lane < d.rows0 ? d.w + (size_t)lane * d.K
+                         : lane < srows ? d.g + (size_t)(lane - d.rows0) * d.K
+                         : lane == srows ? d.aux : d.aux2;
+      bulk_g2s(Wslots + slot * MK_SLOT_BYTES + (size_t)lane * (d.K + MK_PAD) * 4, src, (uint32_t)d.K * 4u, &full_bar[slot], policy);
     }
+    if (lane == 0) f->issue_clk[issued & 7] = clock64();
+    __syncwarp();   // every lane has read the descriptor: its place may be refilled
+    feeder_prefetch(f, issued + MK_FETCH_AHEAD, lane);
     ++issued;
-    u += G;
   }
   __syncwarp();
-  if (lane == 0) { f->s = s; f->oi = oi; f->u = u; f->issued = issued; }
+  if (lane == 0) f->issued = issued;
   __syncwarp();
 }
 
@@ -490,20 +507,26 @@ __global__ void __launch_bounds__(MK_THREADS, 1) layout_mk_kernel(const MkArgs a
   float* red_s = reinterpret_cast<float*>(smem + SM_RED);
   MkOp* ops_s = reinterpret_cast<MkOp*>(smem + SM_OPS);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM_BAR);
-  Feeder* feeder = reinterpret_cast<Feeder*>(full_bar + MK_SLOTS);
+  Feeder* feeder = reinterpret_cast<Feeder*>(smem + SM_FEED);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x, cta = blockIdx.x;
   if (tid == 0) {
     for (int i = 0; i < MK_SLOTS; ++i) mbar_init(&full_bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    feeder->s = 0; feeder->oi = 0; feeder->u = -1; feeder->issued = 0;
+    feeder->list = a.fetch + a.fetch_off[cta];
+    feeder->total = (unsigned)(a.fetch_off[cta + 1] - a.fetch_off[cta]);
+    feeder->issued = 0;
   }
   __syncthreads();
+  if (warp == MK_CW - 1)
+    for (int q = 0; q < MK_FETCH_AHEAD; ++q) feeder_prefetch(feeder, q, lane);
   const unsigned epoch = *a.epoch + 1u;
   const unsigned target = epoch * (unsigned)G;
   const bool is_feeder = warp == MK_CW - 1;
+  const uint64_t policy = l2_policy((a.flags & 1) != 0);
 
-  unsigned seq = 0;   // units this CTA has completed
+  unsigned seq = 0;          // units this CTA has completed
+  unsigned slot = 0, ph = 0;   // ring slot / mbarrier parity of unit `seq`
   for (int s = 0; s < a.n_stages; ++s) {
     const MkStage st = a.stages[s];
     const int n_ops = st.n_a + st.n_b;
@@ -513,8 +536,12 @@ __global__ void __launch_bounds__(MK_THREADS, 1) layout_mk_kernel(const MkArgs a
       for (int i = tid; i < n_ops * 16; i += MK_CT) dst[i] = __ldg(src + i);
     }
     // weights are constants: the ring is topped up (two to three stages ahead) while the barrier fills
-    if (is_feeder) feed(a, feeder, seq, Wslots, full_bar, cta, G, lane);
-    long long* dbg = a.dbg ? a.dbg + ((long long)cta * a.n_stages + s) * 8 : nullptr;
+    long long* dbg = a.dbg ? a.dbg + ((long long)cta * a.n_stages + s) * 12 : nullptr;
+    if (is_feeder) {
+      if (dbg && lane == 0) dbg[9] = clock64();
+      feed(feeder, seq, Wslots, full_bar, lane, policy);
+      if (dbg && lane == 0) dbg[10] = clock64();
+    }
     if (tid == 0) {
       if (dbg) dbg[0] = clock64();
       if (s > 0) wait_counter(a.bar + s - 1, target, a.err);
@@ -528,27 +555,27 @@ __global__ void __launch_bounds__(MK_THREADS, 1) layout_mk_kernel(const MkArgs a
         cons_sync();
         if (tid == 0) {
           if (dbg) dbg[2] = clock64();
-          arrive_counter(a.bar + s);
+          arrive_counter(a.bar + s, (a.flags & 2) != 0);
         }
       }
       if (oi == n_ops) break;
       const MkOp& op = ops_s[oi];
       if (op.type == MK_T_LIN) {
         for (int u = first_unit(op.unit_begin, cta, G); u < op.units; u += G) {
-          const int slice = u % op.n_slices, rt = u / op.n_slices;
+          const int rt = op.row_tiles == 1 ? 0 : u / op.n_slices, slice = u - rt * op.n_slices;
           const int n0 = slice * op.FU, feats = min(op.FU, op.nout - n0);
-          const unsigned slot = seq % MK_SLOTS, ph = (seq / MK_SLOTS) & 1u;
           const int key = oi * 64 + rt;
           const bool restage = staged != key;
-          if (is_feeder) feed(a, feeder, seq, Wslots, full_bar, cta, G, lane);   // several units per stage: keep the ring moving
+          if (is_feeder) feed(feeder, seq, Wslots, full_bar, lane, policy);   // several units per stage: keep the ring moving
           mbar_wait(&full_bar[slot], ph);
-          if (dbg && tid == 0) dbg[4] = clock64();
+          if (dbg && tid == 0) { dbg[4] = clock64(); dbg[8] = feeder->issue_clk[seq & 7]; }
           const float* Ws = reinterpret_cast<const float*>(Wslots + slot * MK_SLOT_BYTES);
           if (op.rclass == 16) lin_unit16(op, a, Xs, Ws, red_s, rt * 16, n0, feats, restage, tid, dbg);
           else lin_unit1(op, a, Xs, Ws, red_s, n0, feats, restage, tid);
           // every warp passed the barrier in front of the epilogue, i.e. finished reading the slot: unit `seq` is complete
           staged = (op.rclass == 1 || op.K <= MK_XROW) ? key : -1;
           ++seq;
+          if (++slot == MK_SLOTS) { slot = 0; ph ^= 1u; }
         }
       } else {
         const float* X = resolve_x(op, a);
@@ -567,7 +594,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) layout_mk_kernel(const MkArgs a
     }
     if (st.bg_arrive >= 0) {
       cons_sync();
-      if (tid == 0) arrive_counter(a.bg + st.bg_arrive);
+      if (tid == 0) arrive_counter(a.bg + st.bg_arrive, (a.flags & 2) != 0);
     }
     cons_sync();   // ops_s is rewritten by the next stage
     if (dbg && tid == 0) dbg[3] = clock64();
@@ -615,7 +642,8 @@ void mk_plan_op(MkOp& op, int ctas) {
   op.rclass = plain1 ? 1 : 16;
   op.row_tiles = op.rclass == 16 ? cdiv(op.M, 16) : 1;
   const int per_feat = geglu ? 2 : 1;   // weight rows a feature brings into the slot
-  int cap = MK_SLOT_BYTES / ((op.K + MK_PAD) * 4) / per_feat;
+  const int naux = (op.pro == MK_GN || op.pro == MK_LN) ? 2 : 0;   // scale / shift rows travel in the slot
+  int cap = (MK_SLOT_BYTES / ((op.K + MK_PAD) * 4) - naux) / per_feat;
   const int hard = (op.rclass == 1 ? 16 : MK_MAX_FU) / per_feat;
   cap = cap > hard ? hard : cap;
   ECHO_CHECK(cap >= 1, "layout program: K=%d too long for a weight slot", op.K);
@@ -630,10 +658,42 @@ void mk_plan_op(MkOp& op, int ctas) {
   if (op.X2) ECHO_CHECK(op.K1 % 4 == 0 && op.K1 > 0 && op.K1 < op.K && op.ldx2 % 4 == 0 && op.pro != MK_LN && op.pro != MK_EDGE && op.pro != MK_POOL, "layout program: bad concat input");
   if (geglu) ECHO_CHECK(op.act == 0 && !op.res && !op.res2 && op.bias, "layout program: GEGLU epilogue takes bias only");
   int want = cdiv((int64_t)op.nout * op.row_tiles, (int64_t)ctas);
-  want = want < 4 ? 4 : want;
+  static const int fu_min = getenv("ECHO_MK_FU_MIN") ? atoi(getenv("ECHO_MK_FU_MIN")) : 4;   // tuning knob: fatter units = fewer CTAs re-reading X
+  want = want < fu_min ? fu_min : want;
   op.FU = want > cap ? cap : want;
   op.n_slices = cdiv(op.nout, op.FU);
   op.units = op.n_slices * op.row_tiles;
+}
+
+// Every CTA's weight fetches in the order its consumer loop meets them (stages -> foreground then background ops -> the op's
+// units dealt round-robin from unit_begin): off[c] .. off[c + 1] index CTA c's descriptors in `out`.
+void mk_build_fetch(const std::vector<MkOp>& ops, const std::vector<MkStage>& stages, int ctas, std::vector<MkFetch>& out, std::vector<int>& off) {
+  out.clear();
+  off.assign(ctas + 1, 0);
+  for (int c = 0; c < ctas; ++c) {
+    off[c] = (int)out.size();
+    for (const MkStage& st : stages)
+      for (int oi = 0; oi < st.n_a + st.n_b; ++oi) {
+        const MkOp& op = ops[st.op_begin + oi];
+        if (op.type != MK_T_LIN) continue;
+        int first = c - op.unit_begin;
+        if (first < 0) first += ctas;
+        for (int u = first; u < op.units; u += ctas) {
+          const int slice = u % op.n_slices, n0 = slice * op.FU, feats = op.nout - n0 < op.FU ? op.nout - n0 : op.FU;
+          MkFetch d;
+          memset(&d, 0, sizeof(d));
+          d.w = op.W + (size_t)n0 * op.K;
+          d.K = op.K;
+          d.rows0 = feats;
+          if (op.epi == MK_EPI_GEGLU) { d.g = op.W + (size_t)(op.nout + n0) * op.K; d.rows1 = feats; }
+          if (op.pro == MK_GN || op.pro == MK_LN) { d.aux = op.gamma; d.aux2 = op.beta; d.naux = 2; }
+          ECHO_CHECK(d.rows0 + d.rows1 + d.naux <= 32 && (size_t)(d.rows0 + d.rows1 + d.naux) * (op.K + MK_PAD) * 4 <= (size_t)MK_SLOT_BYTES,
+                     "layout program: unit of %d rows x K=%d exceeds a weight slot", d.rows0 + d.rows1 + d.naux, op.K);
+          out.push_back(d);
+        }
+      }
+  }
+  off[ctas] = (int)out.size();
 }
 
 void mk_launch(const MkArgs& a, int ctas, cudaStream_t s) {

@@ -3,6 +3,8 @@
 #pragma once
 #include <stdint.h>
 
+#include <vector>
+
 #include "ops.cuh"
 
 namespace echo {
@@ -55,7 +57,18 @@ struct alignas(16) MkStage {
   int pad[3];
 };
 
+// one unit's weight fetch: rows0 value rows at w, rows1 GEGLU gate rows at g, naux (0 / 2) prologue rows (scale, shift), K floats each
+struct alignas(16) MkFetch {
+  const float* w;
+  const float* g;
+  const float* aux;
+  const float* aux2;
+  int K, rows0, rows1, naux;
+};
+
 struct MkArgs {
+  const MkFetch* fetch;    // all CTAs' fetch lists back to back
+  const int* fetch_off;    // [ctas + 1]
   const MkOp* ops;
   const MkStage* stages;
   int n_stages;
@@ -78,8 +91,9 @@ struct MkArgs {
   const int* node_items;
   const long long* triples;
   int H;
-  long long* dbg;    // diagnostics (ECHO_MK_TIMELINE): [cta][stage][8] SM clocks: stage entered, barrier passed, foreground ops done, stage left; of the stage's
-                     // last 16-row unit: weights landed, rows staged, contraction done, epilogue done
+  int flags;         // bit 0: stream the weights with the L2 evict-first policy; bit 1: barrier arrival as fence + atomic
+  long long* dbg;    // diagnostics (ECHO_MK_TIMELINE): [cta][stage][12] SM clocks: stage entered, barrier passed, foreground ops done, stage left; of the stage's
+                     // last 16-row unit: weights landed, rows staged, contraction done, epilogue done, weights issued; feeder call entered / left
 };
 
 constexpr int MK_PAD = 16;             // floats of padding behind every staged row (activations and weights): conflict-free LDS.128
@@ -91,6 +105,7 @@ constexpr int MK_MAX_STAGE_OPS = 8;
 // host: fills FU / n_slices / row_tiles / units / rclass of a LIN op for a grid of `ctas`
 void mk_plan_op(MkOp& op, int ctas);
 bool mk_available(int* ctas_out);
+void mk_build_fetch(const std::vector<MkOp>& ops, const std::vector<MkStage>& stages, int ctas, std::vector<MkFetch>& out, std::vector<int>& off);
 void mk_launch(const MkArgs& a, int ctas, cudaStream_t s);
 
 }  // namespace echo

@@ -39,6 +39,9 @@ class _SpecModule(nn.Module):
 
     def _build_from_specs(self, specs: "arch.Specs"):
         self._spec_keys = list(specs.keys())
+        # load_state_dict(assign=True) swaps Parameter objects without touching their versions: drop the cached list so
+        # that the next call sees the new storage (the hook also fires when a parent module loads a checkpoint)
+        self._register_load_state_dict_pre_hook(self._forget_weights)
         for key, spec in specs.items():
             parts = key.split(".")
             mod: nn.Module = self
@@ -67,6 +70,9 @@ class _SpecModule(nn.Module):
         if self._wlist is None or len(self._wlist) != len(self._spec_keys):
             self._wlist = list(self.state_dict(keep_vars=True).values())
         return tuple((t.data_ptr(), t._version) for t in self._wlist)
+
+    def _forget_weights(self, *a, **k):
+        self._wlist = None
 
     def _apply(self, fn, *a, **k):   # .cuda()/.to() replace parameter storage
         self._wlist = None
