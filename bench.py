@@ -299,6 +299,128 @@ def gpu_eager_baseline(dev, steps=3):
     return out
 
 
+def x3_parity_mode_rate(dev, steps=10):
+    """Secondary figure: the same chained shape step in ECHO_PREC_X3 -- fp32 activations, every contraction on tcgen05 with hi/lo
+    bf16 operands and three MMAs per k-step into one fp32 TMEM accumulator: north_star's 1e-3 parity contract ON the tensor
+    cores (measured 8e-5 against the oracle at N = 16 / 32, tests/test_parity_full_gpu.py).  Like-for-like with the
+    reference's own GPU default (TF32 convolutions)."""
+    from echoscene_b200 import synth
+    m, _ = build_model("x3", dev)
+    g = synth.make_scene_graph(N_NODES, N_TRIPLES, 2)
+    tri = g.triples.to(dev)
+    uc, x = synth.shape_inputs(N_NODES, 2, same_noise=True)
+    uc, x = uc.to(dev), x.to(dev)
+    y = torch.empty_like(x)
+    m._ensure(N_NODES, N_TRIPLES)
+    m.frozen = True
+    for i in range(3):
+        m.ddim_step(x, uc, tri, DDIM_STEPS - 1 - i, out=y)
+        x, y = y, x
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for i in range(steps):
+        m.ddim_step(x, uc, tri, DDIM_STEPS - 4 - i, out=y)
+        x, y = y, x
+    e1.record()
+    torch.cuda.synchronize()
+    assert torch.isfinite(x).all()
+    ms = e0.elapsed_time(e1) / steps
+    ach = FLOP_PER_OBJECT_STEP * N_NODES / (ms * 1e-3) / 1e12
+    return {"precision": "x3 (split bf16 hi/lo, 3 tcgen05 MMAs per k-step, fp32 activations)", "ms_per_step": ms, "steps_per_s": 1e3 / ms,
+            "timed_steps": steps, "tflops_algorithmic": ach, "parity_vs_oracle": "<= 1e-3 (measured 8e-5)"}
+
+
+def strong_scaling_line(m, dev, world, rank, steps):
+    """north_star's literal partition: ONE N = 16 scene over the G GPUs, 16 / G objects per rank, NCCL all-gather of the
+    (16 / G, 64) codes every step (the echo exchange).  value = steps/s of that one scene (strong scaling)."""
+    import torch.distributed as dist
+    from echoscene_b200 import synth
+    if N_NODES % world:
+        return {"skipped": f"{N_NODES} objects do not split over {world} ranks"}
+    k = N_NODES // world
+    g = synth.make_scene_graph(N_NODES, N_TRIPLES, 2)
+    tri = g.triples.to(dev)
+    uc, x_all = synth.shape_inputs(N_NODES, 2, same_noise=True)
+    uc = uc.to(dev)
+    x = x_all[rank * k:(rank + 1) * k].contiguous().to(dev)
+    y = torch.empty_like(x)
+    codes_all = torch.empty(N_NODES, 64, device=dev)
+    xs = torch.cuda.Stream(device=dev)
+
+    def step(xin, xout, i):
+        index = DDIM_STEPS - 1 - (i % DDIM_STEPS)
+        xs.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(xs):
+            codes = m.embed_local(xin, N_NODES, tri.shape[0])
+            dist.all_gather_into_tensor(codes_all, codes)
+        m.trunk_local(xin, rank * k, codes_all, uc, tri, index=index, out=xout, codes_stream=xs)
+
+    m.frozen = False
+    m._ensure(N_NODES, tri.shape[0], k)
+    m.frozen = True
+    for i in range(3):
+        step(x, y, i)
+        x, y = y, x
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for i in range(steps):
+        step(x, y, i)
+        x, y = y, x
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    m.frozen = False
+    ms = float(t.item()) / steps
+    return {"scaling": "strong", "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms, "scenes": 1, "objects_per_rank": k, "steps": steps,
+            "exchange": f"NCCL all-gather of ({k},64) fp32 codes per step"}
+
+
+def scene_sharded_line(m, dev, world, rank, steps, scenes_per_rank=8):
+    """BASELINE config 4 shape: a batch of 8 x G scenes of N = 16, whole scenes per rank (block-diagonal graph: the echo never
+    crosses scenes), NO data-path collective; every rank steps its 8 scenes (128 objects) as one batched call.  value =
+    scene-steps/s over the job (weak scaling; 64 scenes at G = 8)."""
+    import torch.distributed as dist
+    from echoscene_b200 import synth
+    graphs = [synth.make_scene_graph(N_NODES, N_TRIPLES, 100 + rank * scenes_per_rank + i) for i in range(scenes_per_rank)]
+    batch = synth.batch_scene_graphs(graphs)
+    ucs, xs_ = zip(*[synth.shape_inputs(N_NODES, 100 + rank * scenes_per_rank + i, same_noise=True) for i in range(scenes_per_rank)])
+    uc, x, tri = torch.cat(ucs).to(dev), torch.cat(xs_).to(dev), batch.triples.to(dev)
+    y = torch.empty_like(x)
+    m.frozen = False
+    m._ensure(batch.n_nodes, tri.shape[0])
+    m.frozen = True
+    for i in range(2):
+        m.ddim_step(x, uc, tri, DDIM_STEPS - 1 - i, out=y)
+        x, y = y, x
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for i in range(steps):
+        m.ddim_step(x, uc, tri, DDIM_STEPS - 3 - i, out=y)
+        x, y = y, x
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    m.frozen = False
+    assert torch.isfinite(x).all()
+    ms = float(t.item()) / steps
+    return {"scaling": "weak", "value": scenes_per_rank * world * 1e3 / ms, "unit": "scene-steps/s", "ms_per_batched_step": ms,
+            "scenes": scenes_per_rank * world, "scenes_per_rank": scenes_per_rank, "objects_per_rank": scenes_per_rank * N_NODES,
+            "steps": steps, "exchange": "none (scene-sharded: the collated graph is block-diagonal per scene)",
+            "tflops_algorithmic_per_gpu": FLOP_PER_OBJECT_STEP * N_NODES * scenes_per_rank / (ms * 1e-3) / 1e12}
+
+
 REFERENCE_BUDGET_S = 200.0   # the whole --impl reference run must end "within a few minutes"
 
 
@@ -332,7 +454,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -469,6 +591,7 @@ def main():
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1_ncu_conv224.txt (ncu --set full):
                 # 32.18 MB + 0.16 MB -- the bf16 input and the weights once; the output (29 MB) stays in the 126 MB L2
                 "traffic": 32.34e6,
+                "traffic_source": "static: one ncu --set full capture of this launch, profiles/r1_ncu_conv224.txt (not re-measured in this run)",
                 "algorithmic_bytes": 2.0 * (2 * N_NODES * 4096 * 224) + 2.0 * 27 * 224 * 224,
                 "flop_per_launch": flop_launch,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['source']}): kernel timed inside a long step",
@@ -516,6 +639,22 @@ def main():
         if world == 1:
             # last, and never fatal: a secondary figure must not cost the headline line
             line["scene_encode"] = optional_figure(scene_encode_time, dev)
+            if precision == "bf16":
+                line["parity_mode_x3"] = optional_figure(x3_parity_mode_rate, dev)
+    # ---- the other partitions of SURVEY 8(e), measured in the same run (every rank takes part; rank 0 reports) ----
+    extra = {}
+    if precision == "bf16":
+        try:
+            extra["config4_scene_sharded"] = scene_sharded_line(m, dev, world, rank, 10)
+        except Exception as e:   # noqa: BLE001
+            extra["config4_scene_sharded"] = {"error": repr(e)[:200]}
+        if world > 1:
+            try:
+                extra["strong_scaling_one_scene"] = strong_scaling_line(m, dev, world, rank, 30)
+            except Exception as e:   # noqa: BLE001
+                extra["strong_scaling_one_scene"] = {"error": repr(e)[:200]}
+    if rank == 0:
+        line.update(extra)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -66,6 +66,8 @@ struct echo_layout {
   MkStage* d_mk_stages = nullptr;
   std::vector<MkFetch> mk_fetch;       // every CTA's weight fetches in consumption order (mk_build_fetch)
   std::vector<int> mk_fetch_off;
+  std::vector<MkStageLite> mk_stages_lite;
+  MkStageLite* d_mk_stages_lite = nullptr;
   MkFetch* d_mk_fetch = nullptr;
   int* d_mk_fetch_off = nullptr;
   static constexpr int MK_MAX_FETCH = 1 << 16;
@@ -73,7 +75,7 @@ struct echo_layout {
   std::vector<float*> mk_bufs;         // activation buffers of the program, allocated once at capacity in program order
   size_t mk_buf_i = 0;
   int64_t mk_steps = 0;
-  static constexpr int MK_MAX_STAGES = 512, MK_MAX_BG = 64, MK_MAX_OPS = 1024;
+  static constexpr int MK_MAX_BG = 64, MK_MAX_OPS = 1024;
 
   float* buf(int C) { return arena.alloc_n<float>((size_t)N * C); }
   float* mkb(int C) {
@@ -512,6 +514,14 @@ void echo_layout::build_mk(int Nn, int T) {
   ECHO_CHECK(pending.empty(), "layout program: %d emb_layers projections were never scheduled", (int)pending.size());
   ECHO_CHECK((int)mk_stages.size() <= MK_MAX_STAGES && (int)mk_ops.size() <= MK_MAX_OPS, "layout program too long (%d stages, %d ops)",
              (int)mk_stages.size(), (int)mk_ops.size());
+  mk_stages_lite.clear();
+  for (const MkStage& st : mk_stages) {
+    ECHO_CHECK(st.op_begin < 65536 && st.bg_wait < 128 && st.bg_arrive < 128, "layout program: stage record out of range");
+    MkStageLite l;
+    l.op_begin = (unsigned short)st.op_begin; l.n_a = (unsigned char)st.n_a; l.n_b = (unsigned char)st.n_b;
+    l.bg_wait = (signed char)st.bg_wait; l.bg_arrive = (signed char)st.bg_arrive; l.pad = 0;
+    mk_stages_lite.push_back(l);
+  }
   mk_build_fetch(mk_ops, mk_stages, mk_ctas, mk_fetch, mk_fetch_off);
   ECHO_CHECK((int)mk_fetch.size() <= MK_MAX_FETCH, "layout program: %d weight fetches exceed the table", (int)mk_fetch.size());
   mk_N = Nn;
@@ -527,6 +537,7 @@ void echo_layout::step_mk(const echo_graph* g, const float* x_t, const float* ob
     ECHO_CUDA(cudaMemsetAsync(d_mk_counters, 0, sizeof(unsigned) * (MK_MAX_STAGES + MK_MAX_BG + 2), s));
     ECHO_CUDA(cudaMemcpyAsync(d_mk_ops, mk_ops.data(), sizeof(MkOp) * mk_ops.size(), cudaMemcpyHostToDevice, s));
     ECHO_CUDA(cudaMemcpyAsync(d_mk_stages, mk_stages.data(), sizeof(MkStage) * mk_stages.size(), cudaMemcpyHostToDevice, s));
+    ECHO_CUDA(cudaMemcpyAsync(d_mk_stages_lite, mk_stages_lite.data(), sizeof(MkStageLite) * mk_stages_lite.size(), cudaMemcpyHostToDevice, s));
     ECHO_CUDA(cudaMemcpyAsync(d_mk_fetch, mk_fetch.data(), sizeof(MkFetch) * mk_fetch.size(), cudaMemcpyHostToDevice, s));
     ECHO_CUDA(cudaMemcpyAsync(d_mk_fetch_off, mk_fetch_off.data(), sizeof(int) * mk_fetch_off.size(), cudaMemcpyHostToDevice, s));
     ECHO_CUDA(cudaStreamSynchronize(s));   // the host vectors may be rebuilt before an asynchronous copy would have read them
@@ -534,7 +545,7 @@ void echo_layout::step_mk(const echo_graph* g, const float* x_t, const float* ob
   MkArgs a;
   memset(&a, 0, sizeof(a));
   a.ops = d_mk_ops; a.stages = d_mk_stages; a.n_stages = (int)mk_stages.size();
-  a.fetch = d_mk_fetch; a.fetch_off = d_mk_fetch_off;
+  a.fetch = d_mk_fetch; a.fetch_off = d_mk_fetch_off; a.stages_lite = d_mk_stages_lite;
   static const int max_stages = getenv("ECHO_MK_MAX_STAGES") ? atoi(getenv("ECHO_MK_MAX_STAGES")) : 0;   // debugging: run a prefix
   if (max_stages > 0 && max_stages < a.n_stages) a.n_stages = max_stages;
   a.bar = d_mk_counters; a.bg = d_mk_counters + MK_MAX_STAGES; a.epoch = d_mk_counters + MK_MAX_STAGES + MK_MAX_BG;
@@ -758,11 +769,12 @@ echo_layout* layout_create(const echo_layout_desc_t* desc, const echo_weight_t* 
       h->mk_ok = !no_mk && mk_available(&h->mk_ctas) && d.in_channels == d.out_channels && d.model_channels % 2 == 0;
       if (h->mk_ok) {
         h->d_mk_ops = (MkOp*)h->pool.alloc(sizeof(MkOp) * echo_layout::MK_MAX_OPS);
-        h->d_mk_stages = (MkStage*)h->pool.alloc(sizeof(MkStage) * echo_layout::MK_MAX_STAGES);
+        h->d_mk_stages = (MkStage*)h->pool.alloc(sizeof(MkStage) * MK_MAX_STAGES);
+        h->d_mk_stages_lite = (MkStageLite*)h->pool.alloc(sizeof(MkStageLite) * MK_MAX_STAGES);
         h->d_mk_fetch = (MkFetch*)h->pool.alloc(sizeof(MkFetch) * echo_layout::MK_MAX_FETCH);
         h->d_mk_fetch_off = (int*)h->pool.alloc(sizeof(int) * (h->mk_ctas + 1));
-        h->d_mk_counters = (unsigned*)h->pool.alloc(sizeof(unsigned) * (echo_layout::MK_MAX_STAGES + echo_layout::MK_MAX_BG + 2));
-        ECHO_CUDA(cudaMemset(h->d_mk_counters, 0, sizeof(unsigned) * (echo_layout::MK_MAX_STAGES + echo_layout::MK_MAX_BG + 2)));
+        h->d_mk_counters = (unsigned*)h->pool.alloc(sizeof(unsigned) * (MK_MAX_STAGES + echo_layout::MK_MAX_BG + 2));
+        ECHO_CUDA(cudaMemset(h->d_mk_counters, 0, sizeof(unsigned) * (MK_MAX_STAGES + echo_layout::MK_MAX_BG + 2)));
       }
     }
     // workspace: every block output is (N, <= 2*mc*max_mult) fp32; ~60 live buffers is a generous bound
@@ -842,7 +854,7 @@ void set_layout_mode(int m) { g_layout_mode = m; }
 //  negative CTA count: the executor's barrier watchdog fired (synchronises the device to read the flag)}
 void layout_info(const echo_layout* h, int64_t* out6) {
   unsigned err = 0;
-  if (h->mk_ok) ECHO_CUDA(cudaMemcpy(&err, h->d_mk_counters + echo_layout::MK_MAX_STAGES + echo_layout::MK_MAX_BG + 1, sizeof(err), cudaMemcpyDeviceToHost));
+  if (h->mk_ok) ECHO_CUDA(cudaMemcpy(&err, h->d_mk_counters + MK_MAX_STAGES + echo_layout::MK_MAX_BG + 1, sizeof(err), cudaMemcpyDeviceToHost));
   out6[0] = h->mk_steps; out6[1] = h->graph_replays; out6[2] = (int64_t)h->mk_stages.size(); out6[3] = (int64_t)h->mk_ops.size();
   out6[4] = h->graph_launches; out6[5] = h->mk_ok ? (err ? -h->mk_ctas : h->mk_ctas) : 0;
 }

@@ -44,16 +44,22 @@ constexpr int MK_XSTRIDE = MK_XROW + MK_PAD;             // floats between stage
 constexpr int SM_X = 16 * MK_XSTRIDE * 4;
 constexpr int SM_RED = SM_X + MK_SLOTS * MK_SLOT_BYTES;
 constexpr int SM_OPS = SM_RED + MK_CW * 16 * MK_MAX_FU * 4;
-constexpr int SM_BAR = SM_OPS + MK_MAX_STAGE_OPS * 256;
+constexpr int SM_BAR = SM_OPS + 2 * MK_MAX_STAGE_OPS * 256;   // op records of the current and the next stage
 constexpr int SM_FEED = SM_BAR + 64;
-constexpr int SM_TOTAL = SM_FEED + 320;
+constexpr int SM_STG = SM_FEED + 320;                          // every stage record of the program (8 bytes each)
+constexpr int SM_TOTAL = SM_STG + MK_MAX_STAGES * 8;
 static_assert(SM_TOTAL <= 232448, "shared memory budget of one CTA");
 
 // x * sigmoid(x) with the fast exponential / reciprocal (relative error ~1e-6; the prologue runs redundantly in every CTA)
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
-__device__ __forceinline__ float4 ld4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+// Activations are plain (weak) loads.  They were written by other SMs in an earlier stage; the stage barrier's polling thread
+// acquires at gpu scope (LDG.STRONG.GPU + CCTL.IVALL: the SM's L1 is invalidated) and the CTA barrier behind it orders every
+// other thread after that acquire, so no stale line can be served -- the pattern of cooperative_groups' grid.sync().
+// (ld.global.cg compiles to LDG.STRONG.GPU, which measured ~4x slower for the 32 KB staging burst of a CTA.)
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float ld1(const float* p) { return *p; }
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -105,26 +111,40 @@ __device__ __forceinline__ const float* resolve_x(const MkOp& op, const MkArgs& 
   return op.x_ext == MK_EXT_XT ? a.x_t : op.x_ext == MK_EXT_OBJ ? a.obj_embed : op.X;
 }
 
-__device__ __forceinline__ float4 load_in(const MkOp& op, const float* X, int m, int k) {
-  return (op.X2 && k >= op.K1) ? ld4(op.X2 + (long long)m * op.ldx2 + (k - op.K1)) : ld4(X + (long long)m * op.ldx + k);
+// One input row of an op, resolved into registers once per unit (the op record itself lives in shared memory, and every
+// shared-memory store in between would make the compiler read its fields again)
+struct RowIn {
+  const float* x;    // row m of X
+  const float* x2;   // row m of X2, shifted so that x2[k] is column k of the concatenation (null: no concat)
+  int K1;
+};
+__device__ __forceinline__ RowIn row_in(const MkOp& op, const float* X, int m) {
+  RowIn r;
+  r.x = X + (long long)m * op.ldx;
+  r.x2 = op.X2 ? op.X2 + (long long)m * op.ldx2 - op.K1 : nullptr;
+  r.K1 = op.K1;
+  return r;
 }
+__device__ __forceinline__ float4 load_in(const RowIn& r, int k) { return (r.x2 && k >= r.K1) ? ld4(r.x2 + k) : ld4(r.x + k); }
 
 // LayerNorm of one row by one warp, NJ float4 per lane (row length <= 128 * NJ)
 template <int NJ>
 __device__ __forceinline__ void ln_row(const MkOp& op, const float* X, const float* gs, const float* bs, int m, int nq, float4* xr, int lane) {
   float4 v[NJ];
   float s = 0.f;
+  const float* xrow = X + (long long)m * op.ldx;
+  const float inv_k = 1.f / (float)op.K, eps = op.eps;
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
     const int q = lane + 32 * j;
     v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q < nq) v[j] = ld4(X + (long long)m * op.ldx + 4 * q);
+    if (q < nq) v[j] = ld4(xrow + 4 * q);
   }
 #pragma unroll
   for (int j = 0; j < NJ; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
 #pragma unroll
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / (float)op.K;
+  const float mean = s * inv_k;
   float ss = 0.f;
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
@@ -135,7 +155,7 @@ __device__ __forceinline__ void ln_row(const MkOp& op, const float* X, const flo
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  const float rstd = rsqrtf(ss / (float)op.K + op.eps);
+  const float rstd = rsqrtf(ss * inv_k + eps);
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
     const int q = lane + 32 * j;
@@ -151,6 +171,16 @@ __device__ __forceinline__ void ln_row(const MkOp& op, const float* X, const flo
 
 // rows m0 .. m0+16 of the op's input, prologue applied, columns [seg0, seg0 + seg_len) -> Xs [16][MK_XSTRIDE]; one warp per
 // row, every global load of a row in flight before the first use
+// sum over the gl (power of two <= 32) adjacent lanes of a group, same order as a doubling butterfly
+__device__ __forceinline__ float group_sum(float s, int gl) {
+  if (gl > 1) s += __shfl_xor_sync(0xffffffffu, s, 1);
+  if (gl > 2) s += __shfl_xor_sync(0xffffffffu, s, 2);
+  if (gl > 4) s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (gl > 8) s += __shfl_xor_sync(0xffffffffu, s, 8);
+  if (gl > 16) s += __shfl_xor_sync(0xffffffffu, s, 16);
+  return s;
+}
+
 // gs / bs: the prologue's scale and shift rows (they arrive with the unit's weight slice)
 __device__ void stage_rows(const MkOp& op, const MkArgs& a, const float* X, float* Xs, const float* gs, const float* bs, int m0, int seg0,
                            int seg_len, int warp, int lane) {
@@ -161,17 +191,20 @@ __device__ void stage_rows(const MkOp& op, const MkArgs& a, const float* X, floa
     for (int q = lane; q < nq; q += 32) xr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     return;
   }
-  switch (op.pro) {
+  const int pro = op.pro;
+  const RowIn in = row_in(op, X, m);
+  switch (pro) {
     case MK_GN: {   // K % 128 == 0: every lane is in range in every iteration, a group is cpg/4 adjacent lanes
       const int gl = op.cpg >> 2;
-      const float inv = 1.f / (float)op.cpg;
+      const float inv = 1.f / (float)op.cpg, eps = op.eps;
+      const bool act = op.pro_act != 0;
       for (int q0 = 0; q0 < nq; q0 += 128) {
         float4 v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int q = q0 + lane + 32 * j;
           v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (q < nq) v[j] = load_in(op, X, m, seg0 + 4 * q);
+          if (q < nq) v[j] = load_in(in, seg0 + 4 * q);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -180,15 +213,15 @@ __device__ void stage_rows(const MkOp& op, const MkArgs& a, const float* X, floa
             const int k = seg0 + 4 * q;
             const float4 gm = *reinterpret_cast<const float4*>(gs + k), bt = *reinterpret_cast<const float4*>(bs + k);
             float s = (v[j].x + v[j].y) + (v[j].z + v[j].w);
-            for (int o = 1; o < gl; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            s = group_sum(s, gl);
             const float mean = s * inv;
             const float d0 = v[j].x - mean, d1 = v[j].y - mean, d2 = v[j].z - mean, d3 = v[j].w - mean;
             float ss = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
-            for (int o = 1; o < gl; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-            const float rstd = rsqrtf(ss * inv + op.eps);
+            ss = group_sum(ss, gl);
+            const float rstd = rsqrtf(ss * inv + eps);
             float4 r;
             r.x = d0 * rstd * gm.x + bt.x; r.y = d1 * rstd * gm.y + bt.y; r.z = d2 * rstd * gm.z + bt.z; r.w = d3 * rstd * gm.w + bt.w;
-            if (op.pro_act) { r.x = silu_f(r.x); r.y = silu_f(r.y); r.z = silu_f(r.z); r.w = silu_f(r.w); }
+            if (act) { r.x = silu_f(r.x); r.y = silu_f(r.y); r.z = silu_f(r.z); r.w = silu_f(r.w); }
             xr[q] = r;
           }
         }
@@ -220,6 +253,8 @@ __device__ void stage_rows(const MkOp& op, const MkArgs& a, const float* X, floa
     case MK_POOL: {   // CSR order = the reference's scatter_add order (subject roles by ascending t, then object roles)
       const int beg = a.node_off[m], end = a.node_off[m + 1];
       const float cnt = fmaxf((float)(end - beg), 1.f);
+      const long long ldx = op.ldx;
+      const int aux_i = op.aux_i;
       for (int q0 = 0; q0 < nq; q0 += 64) {   // two float4 columns per lane and pass (H = 256: one pass)
         const int qa = q0 + lane, qb = q0 + lane + 32;
         float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
@@ -229,7 +264,7 @@ __device__ void stage_rows(const MkOp& op, const MkArgs& a, const float* X, floa
 #pragma unroll 4
           for (int e = 0; e < nb; ++e) {
             const int item = __shfl_sync(0xffffffffu, mine, e), t = item >> 1, role = item & 1;
-            const float* src = X + (long long)t * op.ldx + (role ? op.aux_i : 0) + seg0;
+            const float* src = X + (long long)t * ldx + (role ? aux_i : 0) + seg0;
             if (qa < nq) { const float4 v = ld4(src + 4 * qa); acc0.x += v.x; acc0.y += v.y; acc0.z += v.z; acc0.w += v.w; }
             if (qb < nq) { const float4 v = ld4(src + 4 * qb); acc1.x += v.x; acc1.y += v.y; acc1.z += v.z; acc1.w += v.w; }
           }
@@ -246,13 +281,13 @@ __device__ void stage_rows(const MkOp& op, const MkArgs& a, const float* X, floa
         for (int j = 0; j < 4; ++j) {
           const int q = q0 + lane + 32 * j;
           v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (q < nq) v[j] = load_in(op, X, m, seg0 + 4 * q);
+          if (q < nq) v[j] = load_in(in, seg0 + 4 * q);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int q = q0 + lane + 32 * j;
           if (q < nq) {
-            if (op.pro == MK_SILU) { v[j].x = silu_f(v[j].x); v[j].y = silu_f(v[j].y); v[j].z = silu_f(v[j].z); v[j].w = silu_f(v[j].w); }
+            if (pro == MK_SILU) { v[j].x = silu_f(v[j].x); v[j].y = silu_f(v[j].y); v[j].z = silu_f(v[j].z); v[j].w = silu_f(v[j].w); }
             xr[q] = v[j];
           }
         }
@@ -295,10 +330,10 @@ __device__ __forceinline__ void epi_store(const MkOp& op, const MkArgs& a, int e
                 lv = __ldg(a.tab + 4 * T + t);
     const float sig = (t == 0 ? 0.f : 1.f) * expf(0.5f * lv);
     const long long idx = (long long)em * op.nout + en;
-    const float x = __ldcg(a.x_t + idx);
+    const float x = ld1(a.x_t + idx);
     const float x0 = __fsub_rn(__fmul_rn(ca, x), __fmul_rn(cb, v));
     const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, x));
-    Y[idx] = __fadd_rn(mean, __fmul_rn(sig, __ldcg(a.noise + idx)));
+    Y[idx] = __fadd_rn(mean, __fmul_rn(sig, ld1(a.noise + idx)));
   } else if (op.bcast_rows > 0) {
     for (int rr = 0; rr < op.bcast_rows; ++rr) Y[(long long)rr * op.ldy + en] = v;
   } else {
@@ -316,23 +351,28 @@ __device__ void lin_unit16(const MkOp& op, const MkArgs& a, float* Xs, const flo
   const int nt = (srows + 7) >> 3;                   // 8-feature MMA tiles (<= 3)
   const int nseg = (K + MK_XROW - 1) / MK_XROW;
   const float* X = resolve_x(op, a);
-  const int ei = tid / feats, ej = tid - ei * feats;   // this thread's output element
+  const int ei = (int)(((float)tid + 0.5f) * __frcp_rn((float)feats)), ej = tid - ei * feats;   // this thread's output element (tid / feats)
   const int em = m0 + ei, en = n0 + ej;
   const bool evalid = tid < 16 * feats && em < op.M;
   float eb = 0.f, eb2 = 0.f, er = 0.f;
   if (evalid) {
     if (op.bias) { eb = __ldg(op.bias + en); if (geglu) eb2 = __ldg(op.bias + op.nout + en); }
-    if (op.res) er = __ldcg(op.res + (long long)em * op.ld_res + en);
-    if (op.res2) er += __ldcg(op.res2 + (long long)em * op.ld_res2 + en);
+    if (op.res) er = ld1(op.res + (long long)em * op.ld_res + en);
+    if (op.res2) er += ld1(op.res2 + (long long)em * op.ld_res2 + en);
   }
-  float acc[3][4];
+  // two accumulator chains per tile (hi.hi / the two cross terms): half the dependent-MMA depth, and the small terms meet first
+  float acc[3][4], acs[3][4];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  for (int i = 0; i < 3; ++i) {
+    acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    acs[i][0] = acs[i][1] = acs[i][2] = acs[i][3] = 0.f;
+  }
   for (int sg = 0; sg < nseg; ++sg) {
     const int seg0 = sg * MK_XROW, seg_len = min(MK_XROW, K - seg0);
     if (restage || nseg > 1) {
       if (sg) cons_sync();   // everyone is done reading the previous segment
       stage_rows(op, a, X, Xs, Ws + (size_t)srows * ws, Ws + (size_t)(srows + 1) * ws, m0, seg0, seg_len, warp, lane);
+      if (dbg && tid == 0) dbg[11] = clock64();
     }
     cons_sync();   // rows staged; also: everyone left the previous unit's epilogue (red_s is about to be rewritten)
     if (dbg && tid == 0) dbg[5] = clock64();
@@ -355,12 +395,12 @@ __device__ void lin_unit16(const MkOp& op, const MkArgs& a, float* Xs, const flo
           if (kin && i * 8 + g < srows) w = *reinterpret_cast<const float4*>(w_p + (size_t)i * 8 * ws + kk);
           uint32_t bh[4], bl[4];
           split_tf32(w.x, bh[0], bl[0]); split_tf32(w.y, bh[1], bl[1]); split_tf32(w.z, bh[2], bl[2]); split_tf32(w.w, bh[3], bl[3]);
-          mma_tf32(acc[i], al[0], al[1], al[2], al[3], bh[0], bh[1]);
-          mma_tf32(acc[i], ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
+          mma_tf32(acs[i], al[0], al[1], al[2], al[3], bh[0], bh[1]);
           mma_tf32(acc[i], ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
-          mma_tf32(acc[i], al[4], al[5], al[6], al[7], bh[2], bh[3]);
-          mma_tf32(acc[i], ah[4], ah[5], ah[6], ah[7], bl[2], bl[3]);
+          mma_tf32(acs[i], ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
           mma_tf32(acc[i], ah[4], ah[5], ah[6], ah[7], bh[2], bh[3]);
+          mma_tf32(acs[i], al[4], al[5], al[6], al[7], bh[2], bh[3]);
+          mma_tf32(acs[i], ah[4], ah[5], ah[6], ah[7], bl[2], bl[3]);
         }
       }
     }
@@ -372,8 +412,8 @@ __device__ void lin_unit16(const MkOp& op, const MkArgs& a, float* Xs, const flo
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       if (i < nt) {
-        *reinterpret_cast<float2*>(r + g * rw + i * 8 + 2 * t) = make_float2(acc[i][0], acc[i][1]);
-        *reinterpret_cast<float2*>(r + (g + 8) * rw + i * 8 + 2 * t) = make_float2(acc[i][2], acc[i][3]);
+        *reinterpret_cast<float2*>(r + g * rw + i * 8 + 2 * t) = make_float2(acc[i][0] + acs[i][0], acc[i][1] + acs[i][1]);
+        *reinterpret_cast<float2*>(r + (g + 8) * rw + i * 8 + 2 * t) = make_float2(acc[i][2] + acs[i][2], acc[i][3] + acs[i][3]);
       }
     }
   }
@@ -405,8 +445,8 @@ __device__ void lin_unit1(const MkOp& op, const MkArgs& a, float* Xs, const floa
   float eb = 0.f, er = 0.f;
   if (tid < feats) {
     if (op.bias) eb = __ldg(op.bias + en);
-    if (op.res) er = __ldcg(op.res + en);
-    if (op.res2) er += __ldcg(op.res2 + en);
+    if (op.res) er = ld1(op.res + en);
+    if (op.res2) er += ld1(op.res2 + en);
   }
   if (restage) stage_row1(op, a, X, Xs, tid);
   cons_sync();
@@ -525,18 +565,31 @@ __global__ void __launch_bounds__(MK_THREADS, 1) layout_mk_kernel(const MkArgs a
   const bool is_feeder = warp == MK_CW - 1;
   const uint64_t policy = l2_policy((a.flags & 1) != 0);
 
+  // the program's stage records -> shared memory once; op records of stage s + 1 are fetched (cp.async) while stage s runs
+  MkStageLite* stg = reinterpret_cast<MkStageLite*>(smem + SM_STG);
+  for (int i = tid; i < a.n_stages; i += MK_CT) stg[i] = a.stages_lite[i];
+  auto fetch_ops = [&](int s) {   // threads 0 .. 16 n_ops: one 16-byte piece of stage s's op records each
+    if (s < a.n_stages) {
+      const MkStageLite st = stg[s];
+      const int pieces = (st.n_a + st.n_b) * 16;
+      if (tid < pieces)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(reinterpret_cast<uint8_t*>(ops_s + (s & 1) * MK_MAX_STAGE_OPS) + 16 * tid)),
+                     "l"(reinterpret_cast<const uint8_t*>(a.ops + st.op_begin) + 16 * tid)
+                     : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  __syncthreads();
+  fetch_ops(0);
+
   unsigned seq = 0;          // units this CTA has completed
   unsigned slot = 0, ph = 0;   // ring slot / mbarrier parity of unit `seq`
   for (int s = 0; s < a.n_stages; ++s) {
-    const MkStage st = a.stages[s];
+    const MkStageLite st = stg[s];
     const int n_ops = st.n_a + st.n_b;
-    {   // this stage's op records -> shared memory (constants: fetched while the barrier is still filling)
-      const uint4* src = reinterpret_cast<const uint4*>(a.ops + st.op_begin);
-      uint4* dst = reinterpret_cast<uint4*>(ops_s);
-      for (int i = tid; i < n_ops * 16; i += MK_CT) dst[i] = __ldg(src + i);
-    }
-    // weights are constants: the ring is topped up (two to three stages ahead) while the barrier fills
+    const MkOp* ops_cur = ops_s + (s & 1) * MK_MAX_STAGE_OPS;
     long long* dbg = a.dbg ? a.dbg + ((long long)cta * a.n_stages + s) * 12 : nullptr;
+    // weights are constants: the ring is topped up (two to three stages ahead) while the barrier fills
     if (is_feeder) {
       if (dbg && lane == 0) dbg[9] = clock64();
       feed(feeder, seq, Wslots, full_bar, lane, policy);
@@ -547,8 +600,22 @@ __global__ void __launch_bounds__(MK_THREADS, 1) layout_mk_kernel(const MkArgs a
       if (s > 0) wait_counter(a.bar + s - 1, target, a.err);
       if (st.bg_wait >= 0) wait_counter(a.bg + st.bg_wait, target, a.err);
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");   // this stage's op records (requested a stage ago)
     cons_sync();
     if (dbg && tid == 0) dbg[1] = clock64();
+    if (dbg && tid == 32) {   // diagnostics: latency of two dependent L2 loads of freshly written activations, nothing else in flight yet
+      const MkOp& o0 = ops_cur[0];
+      if (o0.type == MK_T_LIN && o0.x_ext == MK_EXT_NONE && o0.X) {
+        long long t0, t1 = 0, t2 = 0;   // the clock reads are control-dependent on the loaded values: they cannot be issued early
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(t0)::"memory");
+        const float v = __ldcg(o0.X + (cta & 15) * 4);
+        if (__float_as_int(v) != 0x7fbadbad) asm volatile("mov.u64 %0, %%clock64;" : "=l"(t1)::"memory");
+        const float w = __ldcg(o0.X + (o0.M > 8 ? 8 * o0.ldx : 0) + 64 + (__float_as_int(v) & 4));
+        if (__float_as_int(w) != 0x7fbadbad) asm volatile("mov.u64 %0, %%clock64;" : "=l"(t2)::"memory");
+        dbg[3] = (t1 - t0) | ((t2 - t1) << 32);
+      }
+    }
+    fetch_ops(s + 1);   // into the other buffer: its last readers left it before this barrier
     int staged = -1;
     for (int oi = 0; oi <= n_ops; ++oi) {
       if (oi == st.n_a) {   // the stage's foreground ops are done in this CTA
@@ -559,7 +626,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) layout_mk_kernel(const MkArgs a
         }
       }
       if (oi == n_ops) break;
-      const MkOp& op = ops_s[oi];
+      const MkOp& op = ops_cur[oi];
       if (op.type == MK_T_LIN) {
         for (int u = first_unit(op.unit_begin, cta, G); u < op.units; u += G) {
           const int rt = op.row_tiles == 1 ? 0 : u / op.n_slices, slice = u - rt * op.n_slices;
@@ -596,8 +663,8 @@ __global__ void __launch_bounds__(MK_THREADS, 1) layout_mk_kernel(const MkArgs a
       cons_sync();
       if (tid == 0) arrive_counter(a.bg + st.bg_arrive, (a.flags & 2) != 0);
     }
-    cons_sync();   // ops_s is rewritten by the next stage
-    if (dbg && tid == 0) dbg[3] = clock64();
+    // no barrier here: the next stage's records live in the other buffer, and its first unit synchronises before it
+    // touches the shared staging areas
   }
   if (cta == 0 && tid == 0) *a.epoch = epoch;
 }

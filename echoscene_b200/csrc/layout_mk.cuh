@@ -66,7 +66,18 @@ struct alignas(16) MkFetch {
   int K, rows0, rows1, naux;
 };
 
+// what the kernel keeps of every stage in shared memory
+struct MkStageLite {
+  unsigned short op_begin;
+  unsigned char n_a, n_b;
+  signed char bg_wait, bg_arrive;
+  unsigned short pad;
+};
+static_assert(sizeof(MkStageLite) == 8, "stage records are copied as 8-byte words");
+constexpr int MK_MAX_STAGES = 192;
+
 struct MkArgs {
+  const MkStageLite* stages_lite;
   const MkFetch* fetch;    // all CTAs' fetch lists back to back
   const int* fetch_off;    // [ctas + 1]
   const MkOp* ops;
