@@ -66,6 +66,15 @@ struct echo_layout {
   MkStage* d_mk_stages = nullptr;
   std::vector<MkFetch> mk_fetch;       // every CTA's weight fetches in consumption order (mk_build_fetch)
   std::vector<int> mk_fetch_off;
+  // the time path is a pure function of t and the weights: emb = time_embed(timestep_embedding(t)), the 22 stacked emb_layers
+  // projections of SiLU(emb) and box_time_emb(emb) are tabulated once per handle for every t of the schedule (same kernels as
+  // forward()), which takes 3 stages, 22 background ops and 26 % of the weight bytes out of every step
+  float* ttab_emb = nullptr;    // [time_num][emb_total]
+  float* ttab_node = nullptr;   // [time_num][gconv_dim]
+  bool ttab_on = false;
+  void build_time_table(cudaStream_t s);
+  // proj_out(t1 + ff2(g) + b2) = [P | P F2] [t1 ; g] + (P b2 + bP): one contraction instead of two dependent ones
+  std::vector<ConvW> ffo_fused;
   std::vector<MkStageLite> mk_stages_lite;
   MkStageLite* d_mk_stages_lite = nullptr;
   MkFetch* d_mk_fetch = nullptr;
@@ -253,6 +262,44 @@ struct echo_layout {
 // single kernel makes possible: every row of the time path is the same (one timestep per step), so time_embed / emb_layers /
 // box_time_emb are computed for ONE row; the GraphTripleConv gather-combine and mean pooling are prologues of the Linear that
 // consumes them; the posterior update is the epilogue of the out conv.
+// Tabulate the time path for every t of the schedule with the launchers of forward() (rows = timesteps, in chunks of the
+// few-row kernel's 64 rows): the persistent executor reads row t instead of recomputing it in every step.
+void echo_layout::build_time_table(cudaStream_t s) {
+  const int TT = d.time_num, mc = d.model_channels, E = 4 * mc, gd = d.gconv_dim, et = plan.emb_total;
+  ttab_emb = pool.alloc_n<float>((size_t)TT * et);
+  ttab_node = pool.alloc_n<float>((size_t)TT * (d.enable_t_emb ? gd : 1));
+  float *tmp = nullptr;
+  const int CH = 64;
+  ECHO_CUDA(cudaMalloc(&tmp, sizeof(float) * CH * (size_t)(mc + 3 * E) + sizeof(int64_t) * CH));
+  float *tb = tmp, *x1 = tb + (size_t)CH * mc, *em = x1 + (size_t)CH * E, *ea = em + (size_t)CH * E;
+  int64_t* ti = reinterpret_cast<int64_t*>(ea + (size_t)CH * E);
+  const int saveN = N;
+  try {
+    for (int t0 = 0; t0 < TT; t0 += CH) {
+      const int n = TT - t0 < CH ? TT - t0 : CH;
+      std::vector<int64_t> hv(n);
+      for (int i = 0; i < n; ++i) hv[i] = t0 + i;
+      ECHO_CUDA(cudaMemcpyAsync(ti, hv.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, s));
+      ECHO_CUDA(cudaStreamSynchronize(s));   // hv dies with the iteration
+      N = n;
+      timestep_embedding_tab(ti, freqs, n, mc, tb, s);
+      lin(tb, mc, plan.time0, x1, E, nullptr, 0, 0, 2, s);
+      lin(x1, E, plan.time2, em, E, nullptr, 0, 0, 0, s);
+      if (d.enable_t_emb) lin(em, E, time_emb_lin, ttab_node + (size_t)t0 * gd, gd, nullptr, 0, 0, 0, s);
+      silu_f32(em, ea, (int64_t)n * E, s);
+      lin(ea, E, plan.emb_stack, ttab_emb + (size_t)t0 * et, et, nullptr, 0, 0, 0, s);
+    }
+    ECHO_CUDA(cudaStreamSynchronize(s));
+  } catch (...) {
+    N = saveN;
+    cudaFree(tmp);
+    throw;
+  }
+  N = saveN;
+  cudaFree(tmp);
+  ttab_on = true;
+}
+
 void echo_layout::build_mk(int Nn, int T) {
   mk_ops.clear();
   mk_stages.clear();
@@ -307,11 +354,19 @@ void echo_layout::build_mk(int Nn, int T) {
     return o;
   };
 
-  // ---- stage 0: time_embed.0 on the sinusoidal row, node features that do not need the time MLP, predicate rows, conv_in ----
+  // ---- stage 0: time_embed.0 on the sinusoidal row (without the time table), node features that do not need the time MLP,
+  //      predicate rows, conv_in ----
   {
-    MkOp o = base_op(1, mc, E, nullptr, mc, plan.time0.w, plan.time0.b, e1, E);
-    o.pro = MK_TEMB; o.act = 2;
-    A.push_back(o);
+    if (!ttab_on) {
+      MkOp o = base_op(1, mc, E, nullptr, mc, plan.time0.w, plan.time0.b, e1, E);
+      o.pro = MK_TEMB; o.act = 2;
+      A.push_back(o);
+    } else if (d.enable_t_emb) {   // box_time_emb(emb(t)) from the table -> every node row
+      MkOp c;
+      memset(&c, 0, sizeof(c));
+      c.type = MK_T_COPY; c.M = Nn; c.K = gd; c.x_ext = MK_EXT_TNODE; c.ldx = 0; c.Y = node + od + gd; c.ldy = nd;
+      A.push_back(c);
+    }
     MkOp c;
     memset(&c, 0, sizeof(c));
     c.type = MK_T_COPY; c.M = Nn; c.K = od; c.x_ext = MK_EXT_OBJ; c.ldx = od; c.Y = node; c.ldy = nd;
@@ -337,8 +392,10 @@ void echo_layout::build_mk(int Nn, int T) {
   }
   flush();
   // ---- stage 1: time_embed.2 ----
-  A.push_back(base_op(1, E, E, e1, E, plan.time2.w, plan.time2.b, emb, E));
-  flush();
+  if (!ttab_on) {
+    A.push_back(base_op(1, E, E, e1, E, plan.time2.w, plan.time2.b, emb, E));
+    flush();
+  }
   // the emb_layers projections of all ResBlocks, one background op each, in consumption order (plan.emb_stack rows)
   std::vector<std::pair<int, int>> res_chunks;   // (emb_off, cout) per ResBlock in forward order
   {
@@ -347,7 +404,7 @@ void echo_layout::build_mk(int Nn, int T) {
     add(plan.mid0); add(plan.mid2);
     for (auto& b : plan.out_blocks) add(b.res);
     ECHO_CHECK((int)res_chunks.size() <= MK_MAX_BG, "layout program: too many ResBlocks");
-    for (size_t j = 0; j < res_chunks.size(); ++j) {
+    for (size_t j = 0; j < res_chunks.size() && !ttab_on; ++j) {
       const int off = res_chunks[j].first, co = res_chunks[j].second;
       MkOp o = base_op(1, E, co, emb, E, plan.emb_stack.w + (size_t)off * E, plan.emb_stack.b + off, embout + off, plan.emb_total);
       o.pro = MK_SILU;
@@ -356,7 +413,7 @@ void echo_layout::build_mk(int Nn, int T) {
   }
   int res_counter = 0;   // index of the next ResBlock in forward order == its background counter
   // ---- stage 2: box_time_emb -> every node row ----
-  if (d.enable_t_emb) {
+  if (d.enable_t_emb && !ttab_on) {
     MkOp o = base_op(1, E, gd, emb, E, time_emb_lin.w, time_emb_lin.b, node + od + gd, nd);
     o.bcast_rows = Nn;
     A.push_back(o);
@@ -422,8 +479,14 @@ void echo_layout::build_mk(int Nn, int T) {
     float* out = mkb(r.cout);
     float* h1 = mkb(r.cout);
     In a1 = x; a1.pro = PRO_GN; a1.nw = &r.n1; a1.eps = 1e-5f; a1.silu = true;
-    bg_wait = res_counter++;
-    A.push_back(lin_in(a1, r.c1, h1, r.cout, embout + r.emb_off, 0 /* one row for all nodes */, 0));
+    if (ttab_on) {
+      MkOp o = lin_in(a1, r.c1, h1, r.cout, nullptr, 0, 0);
+      o.res_ext = 1; o.aux_i = r.emb_off;   // + emb_layers(SiLU(emb(t))): one table row for all nodes
+      A.push_back(o);
+    } else {
+      bg_wait = res_counter++;
+      A.push_back(lin_in(a1, r.c1, h1, r.cout, embout + r.emb_off, 0 /* one row for all nodes */, 0));
+    }
     const float* skip = x.X;
     if (r.has_skip) {
       float* sk = mkb(r.cout);
@@ -463,10 +526,18 @@ void echo_layout::build_mk(int Nn, int T) {
       A.push_back(o);
     }
     flush();
-    A.push_back(lin_in(plain(f1, 4 * C), at.ff2, t2, C, t1, C, 0));
-    flush();
-    A.push_back(lin_in(plain(t2, C), at.proj_out, out, C, x, C, 0));
-    flush();
+    if (!ffo_fused.empty()) {   // out = x + [P | P F2] [t1 ; g] + (P b2 + bP)
+      In cat = plain(t1, C);
+      cat.X2 = f1; cat.C2 = 4 * C;
+      A.push_back(lin_in(cat, ffo_fused[ai], out, C, x, C, 0));
+      flush();
+      (void)t2;
+    } else {
+      A.push_back(lin_in(plain(f1, 4 * C), at.ff2, t2, C, t1, C, 0));
+      flush();
+      A.push_back(lin_in(plain(t2, C), at.proj_out, out, C, x, C, 0));
+      flush();
+    }
     return out;
   };
   std::vector<std::pair<const float*, int>> hs;
@@ -531,6 +602,8 @@ void echo_layout::build_mk(int Nn, int T) {
 void echo_layout::step_mk(const echo_graph* g, const float* x_t, const float* obj_embed, int t, const float* noise, float* x_prev,
                           cudaStream_t s) {
   const int Nn = g->n_nodes, T = g->n_triples;
+  static const bool no_ttab = getenv("ECHO_MK_NO_TTAB") != nullptr;
+  if (!ttab_on && !no_ttab && !ttab_emb) build_time_table(s);
   if (Nn != mk_N || T != mk_T) {
     build_mk(Nn, T);
     // a new program renumbers the stages: restart the counters (stream-ordered behind the previous program's last launch)
@@ -551,6 +624,10 @@ void echo_layout::step_mk(const echo_graph* g, const float* x_t, const float* ob
   a.bar = d_mk_counters; a.bg = d_mk_counters + MK_MAX_STAGES; a.epoch = d_mk_counters + MK_MAX_STAGES + MK_MAX_BG;
   a.err = a.epoch + 1;
   a.x_t = x_t; a.obj_embed = obj_embed; a.noise = noise; a.x_prev = x_prev;
+  if (ttab_on) {
+    a.emb_row = ttab_emb + (size_t)t * plan.emb_total;
+    a.tnode_row = ttab_node + (size_t)t * d.gconv_dim;
+  }
   a.t = t; a.tab = d_tab; a.T = d.time_num; a.freqs = freqs; a.temb_dim = d.model_channels;
   a.s_idx = g->s_idx; a.o_idx = g->o_idx; a.node_off = g->node_off; a.node_items = g->node_items;
   a.triples = (const long long*)g->triples;
@@ -759,6 +836,34 @@ echo_layout* layout_create(const echo_layout_desc_t* desc, const echo_weight_t* 
       for (auto& b : h->plan.in_blocks) if (b.attn) fuse(b.at);
       fuse(h->plan.mid_at);
       for (auto& b : h->plan.out_blocks) if (b.attn) fuse(b.at);
+      {   // [P | P F2] and P b2 + bP per transformer block (persistent executor only)
+        static const bool no_ffo = getenv("ECHO_MK_NO_FFO") != nullptr;
+        auto fuse_ffo = [&](const AttnW& a) {
+          const int C = a.C, K = 5 * C;
+          float* w = h->pool.alloc_n<float>((size_t)C * K);
+          float* pf = h->pool.alloc_n<float>((size_t)C * 4 * C);
+          float* bb = h->pool.alloc_n<float>(C);
+          matmul(a.proj_out.w, C, C, a.ff2.w, 4 * C, pf);                                   // P F2: [C, 4C]
+          ECHO_CUDA(cudaMemcpy2DAsync(w, sizeof(float) * K, a.proj_out.w, sizeof(float) * C, sizeof(float) * C, C, cudaMemcpyDeviceToDevice, s0));
+          ECHO_CUDA(cudaMemcpy2DAsync(w + C, sizeof(float) * K, pf, sizeof(float) * 4 * C, sizeof(float) * 4 * C, C, cudaMemcpyDeviceToDevice, s0));
+          {   // bias: P b2 + bP  (b2 as a [C,1] matrix)
+            GemmArgs g;
+            g.A = a.proj_out.w; g.n = 1; g.w = C; g.ow = C; g.cin = C; g.lda = C;
+            g.W = a.ff2.b; g.w_stride_n = 1; g.w_stride_k = 1; g.cout = 1;
+            g.out = bb; g.ldo = 1;
+            gemm_simt(g, s0);
+            add_rowvec(bb, F32, 1, C, a.proj_out.b, C, 1, s0);
+          }
+          ConvW f;
+          f.w = w; f.b = bb; f.cin = K; f.cout = C; f.taps = 1;
+          h->ffo_fused.push_back(f);
+        };
+        if (!no_ffo) {
+          for (auto& b : h->plan.in_blocks) if (b.attn) fuse_ffo(b.at);
+          fuse_ffo(h->plan.mid_at);
+          for (auto& b : h->plan.out_blocks) if (b.attn) fuse_ffo(b.at);
+        }
+      }
       h->attn2_fused.cin = ctx; h->attn2_fused.cout = h->a2_total; h->attn2_fused.taps = 1;
       h->attn2_fused.w = w2; h->attn2_fused.b = b2;
       h->attn2_fused.wb = bf ? to_bf16(w2, (size_t)h->a2_total * ctx) : nullptr;

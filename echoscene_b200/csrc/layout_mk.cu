@@ -108,7 +108,7 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1
 }
 
 __device__ __forceinline__ const float* resolve_x(const MkOp& op, const MkArgs& a) {
-  return op.x_ext == MK_EXT_XT ? a.x_t : op.x_ext == MK_EXT_OBJ ? a.obj_embed : op.X;
+  return op.x_ext == MK_EXT_XT ? a.x_t : op.x_ext == MK_EXT_OBJ ? a.obj_embed : op.x_ext == MK_EXT_TNODE ? a.tnode_row : op.X;
 }
 
 // One input row of an op, resolved into registers once per unit (the op record itself lives in shared memory, and every
@@ -228,9 +228,9 @@ __device__ void stage_rows(const MkOp& op, const MkArgs& a, const float* X, floa
       }
       break;
     }
-    case MK_LN: {   // whole row by this warp: two-pass statistics in registers (K <= 512: four vectors per lane, else up to ten)
+    case MK_LN: {   // whole row by this warp: two-pass statistics in registers (K <= 512: four vectors per lane, else up to eight)
       if (nq <= 128) ln_row<4>(op, X, gs, bs, m, nq, xr, lane);
-      else ln_row<10>(op, X, gs, bs, m, nq, xr, lane);
+      else ln_row<8>(op, X, gs, bs, m, nq, xr, lane);
       break;
     }
     case MK_EDGE: {   // X = [Ps | Po] (N, 2H), aux0 = Pp (T, H), aux1 = folded bias; same association as edge_combine_kernel
@@ -357,7 +357,8 @@ __device__ void lin_unit16(const MkOp& op, const MkArgs& a, float* Xs, const flo
   float eb = 0.f, eb2 = 0.f, er = 0.f;
   if (evalid) {
     if (op.bias) { eb = __ldg(op.bias + en); if (geglu) eb2 = __ldg(op.bias + op.nout + en); }
-    if (op.res) er = ld1(op.res + (long long)em * op.ld_res + en);
+    if (op.res_ext) er = __ldg(a.emb_row + op.aux_i + en);
+    else if (op.res) er = ld1(op.res + (long long)em * op.ld_res + en);
     if (op.res2) er += ld1(op.res2 + (long long)em * op.ld_res2 + en);
   }
   // two accumulator chains per tile (hi.hi / the two cross terms): half the dependent-MMA depth, and the small terms meet first
@@ -721,7 +722,7 @@ void mk_plan_op(MkOp& op, int ctas) {
     ECHO_CHECK(op.bcast_rows == 0, "layout program: broadcast store needs a one-row op");
   }
   if (op.pro == MK_GN) ECHO_CHECK(op.K % 128 == 0 && op.cpg >= 4 && op.cpg <= 128 && (op.cpg & (op.cpg - 1)) == 0, "layout program: GroupNorm prologue K=%d cpg=%d", op.K, op.cpg);
-  if (op.pro == MK_LN) ECHO_CHECK(op.K <= 1280, "layout program: LayerNorm prologue K=%d", op.K);
+  if (op.pro == MK_LN) ECHO_CHECK(op.K <= MK_XROW, "layout program: LayerNorm prologue K=%d", op.K);
   if (op.X2) ECHO_CHECK(op.K1 % 4 == 0 && op.K1 > 0 && op.K1 < op.K && op.ldx2 % 4 == 0 && op.pro != MK_LN && op.pro != MK_EDGE && op.pro != MK_POOL, "layout program: bad concat input");
   if (geglu) ECHO_CHECK(op.act == 0 && !op.res && !op.res2 && op.bias, "layout program: GEGLU epilogue takes bias only");
   int want = cdiv((int64_t)op.nout * op.row_tiles, (int64_t)ctas);

@@ -25,7 +25,7 @@ enum MkEpi : int {
   MK_EPI_DDPM = 1,
   MK_EPI_GEGLU = 2,   // W = [2 nout][K]: y[n] = (w[n].x + b[n]) * gelu_erf(w[nout + n].x + b[nout + n])   (attention.py GEGLU)
 };
-enum MkExt : int { MK_EXT_NONE = 0, MK_EXT_XT = 1, MK_EXT_OBJ = 2, MK_EXT_XPREV = 3 };
+enum MkExt : int { MK_EXT_NONE = 0, MK_EXT_XT = 1, MK_EXT_OBJ = 2, MK_EXT_XPREV = 3, MK_EXT_TNODE = 4 };
 
 struct alignas(16) MkOp {
   const float* X;
@@ -47,7 +47,8 @@ struct alignas(16) MkOp {
   int x_ext, y_ext, FU, n_slices;
   int row_tiles, units, unit_begin, rclass;
   float eps;
-  int pad2[7];
+  int res_ext;          // 1: the residual is columns [aux_i, aux_i + nout) of the step's row of the time table (one row for all nodes)
+  int pad2[6];
 };
 static_assert(sizeof(MkOp) == 256, "MkOp is copied into shared memory as 16 uint4");
 
@@ -92,6 +93,8 @@ struct MkArgs {
   const float* noise;
   float* x_prev;
   int t;
+  const float* emb_row;     // time table: the stacked emb_layers projections of this step's t (see layout.cu), or null
+  const float* tnode_row;   // time table: box_time_emb(emb(t))
   const float* tab;   // DDPM tables 5 x T
   int T;
   const float* freqs;
@@ -108,9 +111,9 @@ struct MkArgs {
 };
 
 constexpr int MK_PAD = 16;             // floats of padding behind every staged row (activations and weights): conflict-free LDS.128
-constexpr int MK_SLOT_BYTES = 36864;   // one staged weight slice: up to MK_MAX_FU rows x (K + MK_PAD) floats
+constexpr int MK_SLOT_BYTES = 41216;   // one staged weight slice: up to MK_MAX_FU rows x (K + MK_PAD) floats (4 rows of K = 2560)
 constexpr int MK_MAX_FU = 24;          // weight rows of a unit (three 8-feature MMA tiles)
-constexpr int MK_XROW = 1280;          // staged columns of a 16-row tile per pass (longer rows go in segments)
+constexpr int MK_XROW = 1024;          // staged columns of a 16-row tile per pass (longer rows go in segments)
 constexpr int MK_MAX_STAGE_OPS = 8;
 
 // host: fills FU / n_slices / row_tiles / units / rclass of a LIN op for a grid of `ctas`
