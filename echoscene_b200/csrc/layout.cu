@@ -322,10 +322,32 @@ void echo_layout::build_mk(int Nn, int T) {
     st.op_begin = (int)mk_ops.size(); st.n_a = (int)A.size(); st.n_b = (int)B.size();
     st.bg_wait = bg_wait; st.bg_arrive = B.empty() ? -1 : bg_arrive;
     ECHO_CHECK(st.n_a + st.n_b <= MK_MAX_STAGE_OPS, "layout program: too many ops in one stage");
+    // Balance the stage: a stage whose ops add up to a little more than one unit per CTA makes a few CTAs run two units while the
+    // rest wait at the barrier.  Fatten the units (more features each) of the op with the most units until the stage fits one
+    // round, as long as its weight slot allows.
+    {
+      std::vector<MkOp*> all;
+      std::vector<int> mfu;
+      for (auto* v : {&A, &B}) for (auto& o : *v) { all.push_back(&o); mfu.push_back(4); }
+      auto total = [&]() { int t = 0; for (auto* o : all) t += o->units; return t; };
+      for (auto* o : all) mk_plan_op(*o, mk_ctas, 4);
+      static const bool no_balance = getenv("ECHO_MK_NO_BALANCE") != nullptr;
+      for (int it = 0; it < 16 && !no_balance && total() > mk_ctas && total() <= 3 * mk_ctas; ++it) {
+        int best = -1;
+        for (size_t i = 0; i < all.size(); ++i)
+          if (all[i]->type == MK_T_LIN && all[i]->rclass == 16 && (best < 0 || all[i]->units > all[best]->units)) {
+            MkOp trial = *all[i];
+            mk_plan_op(trial, mk_ctas, mfu[i] * 2);
+            if (trial.units < all[i]->units) best = (int)i;
+          }
+        if (best < 0) break;
+        mfu[best] *= 2;
+        mk_plan_op(*all[best], mk_ctas, mfu[best]);
+      }
+    }
     int ub = 0;
     for (auto* v : {&A, &B})
       for (auto& o : *v) {
-        mk_plan_op(o, mk_ctas);
         o.unit_begin = ub % mk_ctas;   // the CTA that runs the op's first unit
         ub += o.units;
         mk_ops.push_back(o);

@@ -695,7 +695,7 @@ bool mk_available(int* ctas_out) {
   return g_mk.ok;
 }
 
-void mk_plan_op(MkOp& op, int ctas) {
+void mk_plan_op(MkOp& op, int ctas, int min_fu) {
   if (op.type != MK_T_LIN) {
     ECHO_CHECK(op.K % 4 == 0 && op.ldx % 4 == 0 && op.ldy % 4 == 0, "layout program: copy op needs 16-byte rows");
     op.rclass = 16; op.row_tiles = cdiv(op.M, 16); op.FU = 0; op.n_slices = 1; op.units = op.row_tiles;
@@ -726,8 +726,7 @@ void mk_plan_op(MkOp& op, int ctas) {
   if (op.X2) ECHO_CHECK(op.K1 % 4 == 0 && op.K1 > 0 && op.K1 < op.K && op.ldx2 % 4 == 0 && op.pro != MK_LN && op.pro != MK_EDGE && op.pro != MK_POOL, "layout program: bad concat input");
   if (geglu) ECHO_CHECK(op.act == 0 && !op.res && !op.res2 && op.bias, "layout program: GEGLU epilogue takes bias only");
   int want = cdiv((int64_t)op.nout * op.row_tiles, (int64_t)ctas);
-  static const int fu_min = getenv("ECHO_MK_FU_MIN") ? atoi(getenv("ECHO_MK_FU_MIN")) : 4;   // tuning knob: fatter units = fewer CTAs re-reading X
-  want = want < fu_min ? fu_min : want;
+  want = want < min_fu ? min_fu : want;   // min_fu: the stage balancer asks for fatter units (layout.cu flush())
   op.FU = want > cap ? cap : want;
   op.n_slices = cdiv(op.nout, op.FU);
   op.units = op.n_slices * op.row_tiles;

@@ -117,7 +117,7 @@ constexpr int MK_XROW = 1024;          // staged columns of a 16-row tile per pa
 constexpr int MK_MAX_STAGE_OPS = 8;
 
 // host: fills FU / n_slices / row_tiles / units / rclass of a LIN op for a grid of `ctas`
-void mk_plan_op(MkOp& op, int ctas);
+void mk_plan_op(MkOp& op, int ctas, int min_fu = 4);
 bool mk_available(int* ctas_out);
 void mk_build_fetch(const std::vector<MkOp>& ops, const std::vector<MkStage>& stages, int ctas, std::vector<MkFetch>& out, std::vector<int>& off);
 void mk_launch(const MkArgs& a, int ctas, cudaStream_t s);
