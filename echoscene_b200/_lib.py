@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libechoscene_b200.so")
 PREC_FP32 = 0
 PREC_BF16 = 1
 PREC_X3 = 2
+INDEX_FROM_DEVICE = -2   # ECHO_INDEX_FROM_DEVICE: the step reads its DDIM index from the handle's device slot
 
 
 def precision_code(name: str) -> int:
@@ -112,6 +113,7 @@ PROTOTYPES = {
     "echo_shape_create": (C.c_int, [C.POINTER(_P), C.POINTER(ShapeDesc), C.POINTER(Weight), _I]),
     "echo_shape_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "echo_shape_step": (C.c_int, [_P, _P, _P, _P, _I, _P, _P]),
+    "echo_shape_set_index": (C.c_int, [_P, _I, _P]),
     "echo_shape_embed": (C.c_int, [_P, _P, _I, _P, _P]),
     "echo_shape_trunk": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _P, _I, _P, _P]),
     "echo_shape_trunk_async": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _P, _I, _P, _P, _P]),
@@ -222,7 +224,8 @@ class Graph:
         require_cuda(triples)
         if triples.dtype != torch.int64 or triples.dim() != 2 or triples.shape[1] != 3:
             raise EchoError(f"triples must be (T,3) int64, got {tuple(triples.shape)} {triples.dtype}")
-        self.triples = triples.contiguous()
+        self.source = triples                 # the cache key is the caller tensor's storage: keep it alive, its address
+        self.triples = triples.contiguous()   # cannot be recycled for another graph while this entry exists
         self.n_nodes = int(n_nodes)
         self.n_triples = int(triples.shape[0])
         h = _P()
@@ -250,6 +253,23 @@ def graph_for(triples: torch.Tensor, n_nodes: int) -> Graph:
             _graph_cache.clear()
         g = Graph(triples, n_nodes)
         _graph_cache[key] = g
+    return g
+
+
+_edge_cache: Dict[tuple, Graph] = {}
+
+
+def graph_for_edges(edges: torch.Tensor, n_nodes: int) -> Graph:
+    """Graph handle of an (T,2) [s,o] edge list, cached on the EDGE tensor (a GraphTripleConvNet sees the same `edges` in every
+    layer and every step; building a handle costs a device->host copy, a stream sync and five allocations)."""
+    key = (edges.data_ptr(), tuple(edges.shape), edges._version, int(n_nodes), edges.device.index)
+    g = _edge_cache.get(key)
+    if g is None:
+        if len(_edge_cache) > 64:
+            _edge_cache.clear()
+        g = Graph(edges_to_triples(edges), n_nodes)
+        g.source = edges   # the key is this tensor's storage
+        _edge_cache[key] = g
     return g
 
 

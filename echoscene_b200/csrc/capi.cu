@@ -24,6 +24,7 @@ void layout_info(const echo_layout*, int64_t*);
 echo_shape* shape_create(const echo_shape_desc_t*, const echo_weight_t*, int);
 void shape_destroy(echo_shape*);
 void shape_forward(echo_shape*, const echo_graph*, const float*, const float*, const int64_t*, float*, cudaStream_t);
+void shape_set_index(echo_shape*, int, cudaStream_t);
 void shape_step(echo_shape*, const echo_graph*, const float*, const float*, int, float*, cudaStream_t);
 void shape_embed(echo_shape*, const float*, int, float*, cudaStream_t);
 void shape_trunk(echo_shape*, const echo_graph*, const float*, int, int, const float*, const float*, const int64_t*, int, float*,
@@ -232,7 +233,7 @@ void echo_graph_destroy(echo_graph_t* g) {
 int echo_gather_rows(const float* obj, const int64_t* idx, int64_t n_idx, int64_t n_rows, int64_t dim, float* out, void* stream) {
   return guard([&] {
     ECHO_CHECK(obj && (out || n_idx == 0) && (idx || n_idx == 0) && dim > 0 && n_rows >= 0, "gather_rows: bad arguments");
-    gather_rows(obj, idx, n_idx, dim, out, (cudaStream_t)stream);
+    gather_rows(obj, idx, n_idx, n_rows, dim, out, (cudaStream_t)stream);
   });
 }
 
@@ -343,6 +344,12 @@ int echo_shape_step(echo_shape_t* h, const echo_graph_t* g, const float* x_t, co
   return guard([&] {
     ECHO_CHECK(h && g && x_t && obj_embed && x_prev, "shape_step: null argument");
     shape_step(h, g, x_t, obj_embed, ddim_index, x_prev, (cudaStream_t)stream);
+  });
+}
+int echo_shape_set_index(echo_shape_t* h, int32_t ddim_index, void* stream) {
+  return guard([&] {
+    ECHO_CHECK(h, "shape_set_index: null handle");
+    shape_set_index(h, ddim_index, (cudaStream_t)stream);
   });
 }
 int echo_shape_embed(echo_shape_t* h, const float* x_local, int32_t n_local, float* codes_out, void* stream) {

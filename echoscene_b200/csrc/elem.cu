@@ -500,7 +500,8 @@ __global__ void ddpm_update_kernel(const float* __restrict__ x, const float* __r
 // p_sample_ddim tail, sigma = 0 (samplers/ddim.py:252-261)
 template <class TE>
 __global__ void ddim_update_kernel(const float* __restrict__ x, const TE* __restrict__ e, int e_cl, int n, int c, int64_t V, int ld,
-                                   const float* __restrict__ coef, float* __restrict__ out) {
+                                   const float* __restrict__ coef, const int* __restrict__ slot, float* __restrict__ out) {
+  if (slot) coef += 4 * *slot;   // the step's DDIM index lives on the device (graph-replayed chains)
   const float sa = coef[0], s1m = coef[1], sap = coef[2], sdir = coef[3];
   const int64_t total = (int64_t)n * c * V;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -544,13 +545,18 @@ __global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restr
 }
 
 // one warp per gathered row; 16-byte copies when the row length allows
-__global__ void gather_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, int64_t n_idx, int64_t D,
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, int64_t n_idx, int64_t n_rows, int64_t D,
                                    float* __restrict__ out) {
   const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= n_idx) return;
-  const float* s = src + idx[r] * D;
   float* o = out + r * D;
+  const int64_t i = idx[r];
+  if (i < 0 || i >= n_rows) {   // torch's obj_vecs[idx] raises here; a kernel cannot: the row comes back as NaNs, never as foreign memory
+    for (int64_t c = lane; c < D; c += 32) o[c] = __int_as_float(0x7fc00000);
+    return;
+  }
+  const float* s = src + i * D;
   if ((D & 3) == 0) {
     for (int64_t q = lane; q < D / 4; q += 32) reinterpret_cast<float4*>(o)[q] = __ldg(reinterpret_cast<const float4*>(s) + q);
   } else {
@@ -821,10 +827,28 @@ void ddpm_update(const float* x, const float* eps, const float* noise, const flo
 }
 
 void ddim_update(const float* x, const void* e, DT edt, bool e_cl, int n, int c, int64_t V, int ld, const float* coef4, float* out,
-                 cudaStream_t s) {
+                 cudaStream_t s, const int* slot) {
   const int grid = grid_for((int64_t)n * c * V, 256);
-  if (edt == F32) ddim_update_kernel<float><<<grid, 256, 0, s>>>(x, (const float*)e, e_cl ? 1 : 0, n, c, V, ld, coef4, out);
-  else ddim_update_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(x, (const __nv_bfloat16*)e, e_cl ? 1 : 0, n, c, V, ld, coef4, out);
+  if (edt == F32) ddim_update_kernel<float><<<grid, 256, 0, s>>>(x, (const float*)e, e_cl ? 1 : 0, n, c, V, ld, coef4, slot, out);
+  else ddim_update_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(x, (const __nv_bfloat16*)e, e_cl ? 1 : 0, n, c, V, ld, coef4, slot, out);
+  ECHO_LAUNCH_CHECK();
+}
+
+namespace {
+__global__ void fill_i64_slot_kernel(int64_t* p, int n, const int32_t* __restrict__ table, const int* __restrict__ slot) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (int64_t)table[*slot];
+}
+__global__ void set_i32_kernel(int* p, int v) { *p = v; }
+}  // namespace
+
+void fill_i64_from_slot(int64_t* p, int n, const int32_t* table, const int* slot, cudaStream_t s) {
+  fill_i64_slot_kernel<<<cdiv(n, 128), 128, 0, s>>>(p, n, table, slot);
+  ECHO_LAUNCH_CHECK();
+}
+
+void set_i32(int* p, int v, cudaStream_t s) {
+  set_i32_kernel<<<1, 1, 0, s>>>(p, v);
   ECHO_LAUNCH_CHECK();
 }
 
@@ -883,9 +907,9 @@ void fold_bn(const float* w, const float* b, const float* gamma, const float* be
   ECHO_LAUNCH_CHECK();
 }
 
-void gather_rows(const float* src, const int64_t* idx, int64_t n_idx, int64_t D, float* out, cudaStream_t s) {
+void gather_rows(const float* src, const int64_t* idx, int64_t n_idx, int64_t n_rows, int64_t D, float* out, cudaStream_t s) {
   if (n_idx == 0) return;
-  gather_rows_kernel<<<cdiv(n_idx * 32, 256), 256, 0, s>>>(src, idx, n_idx, D, out);
+  gather_rows_kernel<<<cdiv(n_idx * 32, 256), 256, 0, s>>>(src, idx, n_idx, n_rows, D, out);
   ECHO_LAUNCH_CHECK();
 }
 

@@ -164,7 +164,10 @@ void ddpm_update(const float* x, const float* eps, const float* noise, const flo
                  float* out, cudaStream_t s);
 // DDIM eta=0 on an NCDHW latent, e_t given channels-last (or NCDHW when e_cl == false)
 void ddim_update(const float* x_ncdhw, const void* e, DT edt, bool e_cl, int n, int c, int64_t voxels, int e_ld,
-                 const float* coef4 /* device, 4 floats */, float* out_ncdhw, cudaStream_t s);
+                 const float* coef4 /* device, 4 floats */, float* out_ncdhw, cudaStream_t s, const int* slot = nullptr);
+// p[i] = table[*slot] (i < n) / *p = v: the DDIM index of a graph-replayed chain lives on the device
+void fill_i64_from_slot(int64_t* p, int n, const int32_t* table, const int* slot, cudaStream_t s);
+void set_i32(int* p, int v, cudaStream_t s);
 
 // attention (fp32, materialised scores): qkv [n*tokens, 3*heads*dh] -> out [n*tokens, heads*dh]
 void attention_f32(const float* qkv, int n, int tokens, int heads, int dh, float* scores_ws, float* out, cudaStream_t s);
@@ -197,6 +200,6 @@ void fold_bn(const float* w, const float* b, const float* gamma, const float* be
              float eps, int nout, int K, float* w_out, float* b_out, cudaStream_t s);
 
 // graph ops
-void gather_rows(const float* src, const int64_t* idx, int64_t n_idx, int64_t D, float* out, cudaStream_t s);
+void gather_rows(const float* src, const int64_t* idx, int64_t n_idx, int64_t n_rows, int64_t D, float* out, cudaStream_t s);   // idx outside [0, n_rows): NaN row
 
 }  // namespace echo

@@ -41,6 +41,8 @@ struct echo_shape {
   std::vector<float> h_coef;
   std::vector<int32_t> h_ts;
   float* d_coef = nullptr;
+  int32_t* d_ts = nullptr;     // the DDIM timesteps on the device
+  int* d_index = nullptr;      // the step's DDIM index for ECHO_INDEX_FROM_DEVICE calls (echo_shape_set_index)
   // persistent per-step buffers
   float *temb = nullptr, *e1 = nullptr, *emb = nullptr, *emb_act = nullptr, *node = nullptr, *pred = nullptr, *latent = nullptr, *codes = nullptr;
   float *embout = nullptr, *v2 = nullptr, *a2vec = nullptr;
@@ -422,7 +424,9 @@ struct echo_shape {
       contract(hn, plan.out_conv, 3, 1, nullptr, 0, nullptr, e, s);
     }
     if (!dry) {
-      if (ddim_index < 0) cl_to_ncdhw(e.p, F32, e.n, d.out_channels, e.voxels(), e.c, out_local, s);
+      if (ddim_index == -1) cl_to_ncdhw(e.p, F32, e.n, d.out_channels, e.voxels(), e.c, out_local, s);
+      else if (ddim_index == ECHO_INDEX_FROM_DEVICE)
+        ddim_update(x_local, e.p, F32, true, e.n, d.out_channels, e.voxels(), e.c, d_coef, out_local, s, d_index);
       else ddim_update(x_local, e.p, F32, true, e.n, d.out_channels, e.voxels(), e.c, d_coef + 4 * ddim_index, out_local, s);
     }
     arena.release(m0);
@@ -446,7 +450,7 @@ struct echo_shape {
                (long long)g->p_min, (long long)g->p_max, pred_rows);
     ECHO_CHECK(n_local >= 0 && n_local <= d.max_local_nodes && obj_begin >= 0 && obj_begin + n_local <= g->n_nodes,
                "shape: bad local range [%d, %d) of %d nodes (capacity %d)", obj_begin, obj_begin + n_local, g->n_nodes, d.max_local_nodes);
-    ECHO_CHECK(ddim_index < (int)h_ts.size(), "shape: ddim_index %d out of range", ddim_index);
+    ECHO_CHECK(ddim_index < (int)h_ts.size() && ddim_index >= ECHO_INDEX_FROM_DEVICE, "shape: ddim_index %d out of range", ddim_index);
     arena.release(0);
     const int L = d.latent_size;
     Act xcl = new_act(n_local, L, L, L, d.in_channels, F32);
@@ -497,6 +501,10 @@ void ddim_schedule(int T, int S, float linear_start, float linear_end, std::vect
 static void make_ddim_schedule(echo_shape* h) {
   ddim_schedule(h->d.timesteps, h->d.ddim_steps, h->d.linear_start, h->d.linear_end, h->h_coef, h->h_ts);
   h->d_coef = h->pool.upload(h->h_coef);
+  h->d_ts = h->pool.alloc_n<int32_t>(h->h_ts.size());
+  ECHO_CUDA(cudaMemcpy(h->d_ts, h->h_ts.data(), sizeof(int32_t) * h->h_ts.size(), cudaMemcpyHostToDevice));
+  h->d_index = h->pool.alloc_n<int>(4);
+  ECHO_CUDA(cudaMemset(h->d_index, 0, sizeof(int) * 4));
 }
 
 echo_shape* shape_create(const echo_shape_desc_t* desc, const echo_weight_t* weights, int n_weights) {
@@ -678,9 +686,21 @@ void shape_forward(echo_shape* h, const echo_graph* g, const float* x, const flo
   h->run(g, x, 0, g ? g->n_nodes : 0, nullptr, uc, t, -1, out, s);
 }
 
+// the timesteps of a sampler step: ddim_timesteps[index] for every node, index from the host or from the device slot
+static void fill_step_timesteps(echo_shape* h, int n_nodes, int ddim_index, cudaStream_t s) {
+  if (ddim_index == ECHO_INDEX_FROM_DEVICE) fill_i64_from_slot(h->t_dev, n_nodes, h->d_ts, h->d_index, s);
+  else fill_i64(h->t_dev, n_nodes, h->h_ts[ddim_index], s);
+}
+
+void shape_set_index(echo_shape* h, int ddim_index, cudaStream_t s) {
+  ECHO_CHECK(ddim_index >= 0 && ddim_index < (int)h->h_ts.size(), "shape_set_index: bad ddim_index %d", ddim_index);
+  set_i32(h->d_index, ddim_index, s);
+}
+
 void shape_step(echo_shape* h, const echo_graph* g, const float* x, const float* uc, int ddim_index, float* x_prev, cudaStream_t s) {
-  ECHO_CHECK(g && ddim_index >= 0 && ddim_index < (int)h->h_ts.size(), "shape_step: bad ddim_index %d", ddim_index);
-  fill_i64(h->t_dev, g->n_nodes, h->h_ts[ddim_index], s);
+  ECHO_CHECK(g && (ddim_index == ECHO_INDEX_FROM_DEVICE || (ddim_index >= 0 && ddim_index < (int)h->h_ts.size())), "shape_step: bad ddim_index %d",
+             ddim_index);
+  fill_step_timesteps(h, g->n_nodes, ddim_index, s);
   h->run(g, x, 0, g->n_nodes, nullptr, uc, h->t_dev, ddim_index, x_prev, s);
 }
 
@@ -695,8 +715,9 @@ void shape_trunk(echo_shape* h, const echo_graph* g, const float* x_local, int o
   ECHO_CHECK(codes_all, "shape_trunk: codes_all is required");
   const int64_t* t_use = t_all;
   if (!t_all) {
-    ECHO_CHECK(ddim_index >= 0, "shape_trunk: timesteps_all or ddim_index required");
-    fill_i64(h->t_dev, g->n_nodes, h->h_ts[ddim_index], s);
+    ECHO_CHECK(ddim_index >= 0 || ddim_index == ECHO_INDEX_FROM_DEVICE, "shape_trunk: timesteps_all or ddim_index required");
+    ECHO_CHECK(ddim_index < (int)h->h_ts.size(), "shape_trunk: bad ddim_index %d", ddim_index);
+    fill_step_timesteps(h, g->n_nodes, ddim_index, s);
     t_use = h->t_dev;
   }
   h->run(g, x_local, obj_begin, n_local, codes_all, uc_all, t_use, ddim_index, out_local, s, codes_stream);

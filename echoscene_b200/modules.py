@@ -142,7 +142,7 @@ class GraphTripleConvNet(_SpecModule):
         assert obj_vecs.shape[1] == self.cfg.input_dim_obj and pred_vecs.shape[1] == self.cfg.input_dim_pred
         assert edges.shape == (t, 2)
         self._ensure(n, t)
-        g = _lib.graph_for(_lib.edges_to_triples(edges), n) if not hasattr(edges, "_echo_graph") else edges._echo_graph
+        g = _lib.graph_for_edges(edges, n) if not hasattr(edges, "_echo_graph") else edges._echo_graph
         dout = self.cfg.output_dim or self.cfg.input_dim_obj
         obj_out = torch.empty(n, dout, device=obj_vecs.device)
         pred_out = torch.empty(t, self.cfg.input_dim_pred, device=obj_vecs.device)
@@ -602,6 +602,14 @@ class UNet3DModel(_SpecModule):
         _lib.check(_lib.lib().echo_shape_step(self._handle, g.h, _lib.ptr(x_t), _lib.ptr(obj_embed), int(index),
                                               _lib.ptr(out), _lib.stream_ptr()))
         return out
+
+    def set_step_index(self, index: int):
+        """Stream-ordered write of the DDIM index that ``ddim_step`` / ``trunk_local`` read when called with
+        ``index=_lib.INDEX_FROM_DEVICE``: such a step launches the same kernels for every index, so a chain can capture it once
+        in a CUDA graph (with the NCCL all-gather of a sharded step) and replay it -- set the index, replay."""
+        if self._handle is None:
+            raise EchoError("set_step_index: no handle yet (run a step, or _ensure(), first)")
+        _lib.check(_lib.lib().echo_shape_set_index(self._handle, int(index), _lib.stream_ptr()))
 
     # ---- per-object sharding (SURVEY §8e): embed local objects, all-gather the 64-d codes, run the trunk locally ----
     @torch.no_grad()

@@ -156,7 +156,8 @@ ECHO_API int echo_debug_graph_csr(const int64_t* triples_host, int32_t n_triples
 ECHO_API int echo_graph_create(echo_graph_t** out, const int64_t* triples_dev, int32_t n_triples, int32_t n_nodes, void* stream);
 ECHO_API void echo_graph_destroy(echo_graph_t* g);
 
-/* ---- obj_vecs[idx]: the bit-exact edge-index gather — model/graph.py:146-147 */
+/* ---- obj_vecs[idx]: the bit-exact edge-index gather — model/graph.py:146-147.  An index outside [0, n_rows) (torch raises an
+ * IndexError there) yields a row of NaNs; foreign memory is never read. */
 ECHO_API int echo_gather_rows(const float* obj_vecs, const int64_t* idx, int64_t n_idx, int64_t n_rows, int64_t dim,
                      float* out, void* stream);
 
@@ -210,6 +211,13 @@ ECHO_API int echo_shape_trunk(echo_shape_t* h, const echo_graph_t* g, const floa
 ECHO_API int echo_shape_trunk_async(echo_shape_t* h, const echo_graph_t* g, const float* x_local, int32_t obj_begin, int32_t n_local,
                            const float* codes_all, const float* obj_embed_all, const int64_t* timesteps_all,
                            int32_t ddim_index, float* out_local, void* codes_stream, void* stream);
+/* A chain whose launch sequence does not depend on the step: pass ECHO_INDEX_FROM_DEVICE as `ddim_index` to echo_shape_step /
+ * echo_shape_trunk / echo_shape_trunk_async and the step reads its DDIM index (timesteps, update coefficients) from a slot on
+ * the device, written by echo_shape_set_index (stream-ordered).  Such a step can be captured ONCE into a CUDA graph -- together
+ * with the NCCL all-gather of a sharded step -- and replayed for every iteration of DDIMSampler.ddim_sampling
+ * (samplers/ddim.py:156-181): set the index, replay. */
+#define ECHO_INDEX_FROM_DEVICE (-2)
+ECHO_API int echo_shape_set_index(echo_shape_t* h, int32_t ddim_index, void* stream);
 /* copies latent_shape_rel of the last forward/trunk call, (n_nodes, context_dim) f32, into out_dev. */
 ECHO_API int echo_shape_latent(const echo_shape_t* h, int32_t n_nodes, float* out_dev, void* stream);
 ECHO_API void echo_shape_destroy(echo_shape_t* h);
