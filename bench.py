@@ -716,7 +716,17 @@ def main():
     if rank == 0:
         line.update(extra)
         print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
+        if graphs:
+            # NCCL kernels captured in CUDA graphs keep the communicator busy at teardown (destroy_process_group never returned in
+            # a 2-GPU run): drop the graphs, drain the device, and leave without the collective shutdown
+            del graphs
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
