@@ -117,8 +117,18 @@ def layout_rate(dev, pk, precision, steps=200):
     ms = e0.elapsed_time(e1) / steps
     live_bytes = 115.30e6 * 4    # live parameters read once per step; the layout branch streams fp32 weights in both modes
     ach = live_bytes / (ms * 1e-3) / 1e9
+    import ctypes
+    info = (ctypes.c_int64 * 6)()
+    _lib_ = __import__("echoscene_b200._lib", fromlist=["_lib"])
+    _lib_.check(_lib_.lib().echo_debug_layout_info(m._handle, info))
     return {"value": 1e3 / ms, "unit": "layout-steps/s", "ms_per_step": ms, "n_nodes": N_NODES, "dtype": "f32",
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"]}}
+            "executor": {"persistent_kernel_steps": int(info[0]), "graph_replays": int(info[1]), "program_stages": int(info[2]),
+                         "program_ops": int(info[3]), "ctas": int(info[5])},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                         "algorithmic_bytes": live_bytes,
+                         "traffic": 330.3e6,
+                         "traffic_source": "static: dram__bytes_read + write of one persistent-kernel launch, profiles/r2_ncu_layout_mk_final.txt "
+                                           "(below the algorithmic bytes: the time path's weights are tabulated per handle, DESIGN section 4)"}}
 
 
 def vqvae_decode_rate(dev, precision):
@@ -329,6 +339,45 @@ def x3_parity_mode_rate(dev, steps=10):
     ach = FLOP_PER_OBJECT_STEP * N_NODES / (ms * 1e-3) / 1e12
     return {"precision": "x3 (split bf16 hi/lo, 3 tcgen05 MMAs per k-step, fp32 activations)", "ms_per_step": ms, "steps_per_s": 1e3 / ms,
             "timed_steps": steps, "tflops_algorithmic": ach, "parity_vs_oracle": "<= 1e-3 (measured 8e-5)"}
+
+
+def config3_rate(dev, steps=10):
+    """Secondary figure, BASELINE config 3: "echoscene N=32 nodes, 64^3 SDF latent, 250-step ... bf16, 1xB200" -- one 32-node scene
+    (T = 128 triples) on the 250-step schedule (timesteps range(0, 1000, 4) + 1), chained steps.  Parity of this size against the
+    oracle: tests/test_parity_full_gpu.py (N = 32 / T = 128)."""
+    from echoscene_b200 import arch, modules, synth
+    n, t, S = 32, 128, 250
+    sd = arch.make_state_dict(arch.unet3d_specs(synth.shape_cfg()), synth.WEIGHT_SEED_SHAPE)
+    m = modules.UNet3DModel(image_size=16, in_channels=3, out_channels=3, model_channels=224, num_res_blocks=2,
+                            attention_resolutions=[4, 2], channel_mult=[1, 2, 3], num_heads=8, dims=3, use_spatial_transformer=True,
+                            transformer_depth=1, context_dim=1280, legacy=False, messsage_passing=True, conditioning_key="crossattn",
+                            enable_t_emb=True, precision="bf16", ddim_steps=S)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev)
+    g = synth.make_scene_graph(n, t, 5)
+    tri = g.triples.to(dev)
+    uc, x = synth.shape_inputs(n, 5, same_noise=True)
+    uc, x = uc.to(dev), x.to(dev)
+    y = torch.empty_like(x)
+    m._ensure(n, t)
+    m.frozen = True
+    for i in range(3):
+        m.ddim_step(x, uc, tri, S - 1 - i, out=y)
+        x, y = y, x
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for i in range(steps):
+        m.ddim_step(x, uc, tri, S - 4 - i, out=y)
+        x, y = y, x
+    e1.record()
+    torch.cuda.synchronize()
+    m.frozen = False
+    assert torch.isfinite(x).all()
+    ms = e0.elapsed_time(e1) / steps
+    return {"workload": "echoscene N=32 nodes, T=128 triples, 250-step schedule, bf16", "ms_per_step": ms, "steps_per_s": 1e3 / ms,
+            "timed_steps": steps, "seconds_per_250_step_chain": 250 * ms * 1e-3,
+            "tflops_algorithmic": FLOP_PER_OBJECT_STEP * n / (ms * 1e-3) / 1e12}
 
 
 def strong_scaling_line(m, dev, world, rank, steps):
@@ -701,6 +750,7 @@ def main():
             line["scene_encode"] = optional_figure(scene_encode_time, dev)
             if precision == "bf16":
                 line["parity_mode_x3"] = optional_figure(x3_parity_mode_rate, dev)
+                line["config3_n32_s250"] = optional_figure(config3_rate, dev)
     # ---- the other partitions of SURVEY 8(e), measured in the same run (every rank takes part; rank 0 reports) ----
     extra = {}
     if precision == "bf16":
