@@ -37,6 +37,11 @@ class Weight(C.Structure):
                 ("shape", C.c_int64 * 6)]
 
 
+class OptTensor(C.Structure):   # echo_opt_tensor_t
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", C.c_int64), ("clip_group", C.c_int32), ("reserved", C.c_int32)]
+
+
 class GcnDesc(C.Structure):
     _fields_ = [("input_dim_obj", C.c_int32), ("input_dim_pred", C.c_int32), ("num_layers", C.c_int32),
                 ("hidden_dim", C.c_int32), ("output_dim", C.c_int32), ("max_nodes", C.c_int32),
@@ -114,6 +119,13 @@ PROTOTYPES = {
     "echo_shape_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "echo_shape_step": (C.c_int, [_P, _P, _P, _P, _I, _P, _P]),
     "echo_shape_set_index": (C.c_int, [_P, _I, _P]),
+    "echo_train_q_sample": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P]),
+    "echo_train_mse_rows": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _I, _P, _P]),
+    "echo_optimizer_create": (C.c_int, [_P, _P, _I]),
+    "echo_optimizer_set_tensors": (C.c_int, [_P, _P, _I, _P]),
+    "echo_optimizer_step": (C.c_int, [_P, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _P]),
+    "echo_optimizer_info": (C.c_int, [_P, _P, _P, _P]),
+    "echo_optimizer_destroy": (None, [_P]),
     "echo_shape_embed": (C.c_int, [_P, _P, _I, _P, _P]),
     "echo_shape_trunk": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _P, _I, _P, _P]),
     "echo_shape_trunk_async": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _P, _I, _P, _P, _P]),

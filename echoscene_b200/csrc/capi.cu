@@ -25,6 +25,11 @@ echo_shape* shape_create(const echo_shape_desc_t*, const echo_weight_t*, int);
 void shape_destroy(echo_shape*);
 void shape_forward(echo_shape*, const echo_graph*, const float*, const float*, const int64_t*, float*, cudaStream_t);
 void shape_set_index(echo_shape*, int, cudaStream_t);
+echo_optimizer* optimizer_create(const echo_opt_tensor_t*, int);
+void optimizer_destroy(echo_optimizer*);
+void optimizer_step(echo_optimizer*, int64_t, double, double, double, double, double, double, cudaStream_t);
+void optimizer_set_tensors(echo_optimizer*, const echo_opt_tensor_t*, int, cudaStream_t);
+void optimizer_info(const echo_optimizer*, int64_t*, float*, cudaStream_t);
 void shape_step(echo_shape*, const echo_graph*, const float*, const float*, int, float*, cudaStream_t);
 void shape_embed(echo_shape*, const float*, int, float*, cudaStream_t);
 void shape_trunk(echo_shape*, const echo_graph*, const float*, int, int, const float*, const float*, const int64_t*, int, float*,
@@ -346,6 +351,54 @@ int echo_shape_step(echo_shape_t* h, const echo_graph_t* g, const float* x_t, co
     shape_step(h, g, x_t, obj_embed, ddim_index, x_prev, (cudaStream_t)stream);
   });
 }
+int echo_train_q_sample(const float* x0, const float* noise, const int64_t* t, const float* sqrt_ac, const float* sqrt_1mac, int64_t rows,
+                        int64_t row_len, float* out, void* stream) {
+  return guard([&] {
+    ECHO_CHECK(rows >= 0 && row_len >= 0, "q_sample: negative size");
+    ECHO_CHECK(rows * row_len == 0 || (x0 && noise && t && sqrt_ac && sqrt_1mac && out), "q_sample: null argument");
+    q_sample(x0, noise, t, sqrt_ac, sqrt_1mac, rows, row_len, out, (cudaStream_t)stream);
+  });
+}
+int echo_train_mse_rows(const float* pred, const float* target, int64_t rows, int64_t row_len, const int32_t* ranges_host, int32_t n_ranges,
+                        float* out, void* stream) {
+  return guard([&] {
+    ECHO_CHECK(rows >= 0 && row_len > 0 && n_ranges > 0 && n_ranges <= 16 && ranges_host, "mse_rows: bad arguments");
+    ECHO_CHECK(rows == 0 || (pred && target && out), "mse_rows: null argument");
+    for (int k = 0; k < n_ranges; ++k)
+      ECHO_CHECK(ranges_host[2 * k] >= 0 && ranges_host[2 * k] < ranges_host[2 * k + 1] && ranges_host[2 * k + 1] <= row_len,
+                 "mse_rows: range %d = [%d, %d) outside a row of %lld", k, ranges_host[2 * k], ranges_host[2 * k + 1], (long long)row_len);
+    static thread_local int* d_ranges = nullptr;   // 32 ints, reused: the copy is stream-ordered in front of the kernel
+    if (!d_ranges) ECHO_CUDA(cudaMalloc(&d_ranges, sizeof(int) * 32));
+    ECHO_CUDA(cudaMemcpyAsync(d_ranges, ranges_host, sizeof(int) * 2 * n_ranges, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    mse_rows(pred, target, rows, row_len, d_ranges, n_ranges, out, (cudaStream_t)stream);
+  });
+}
+int echo_optimizer_create(echo_optimizer_t** out, const echo_opt_tensor_t* tensors, int32_t n_tensors) {
+  return guard([&] {
+    ECHO_CHECK(out, "optimizer_create: null argument");
+    *out = optimizer_create(tensors, n_tensors);
+  });
+}
+int echo_optimizer_set_tensors(echo_optimizer_t* h, const echo_opt_tensor_t* tensors, int32_t n_tensors, void* stream) {
+  return guard([&] {
+    ECHO_CHECK(h, "optimizer_set_tensors: null handle");
+    optimizer_set_tensors(h, tensors, n_tensors, (cudaStream_t)stream);
+  });
+}
+int echo_optimizer_step(echo_optimizer_t* h, int64_t step, double lr, double beta1, double beta2, double eps, double weight_decay,
+                        double clip_max_norm, void* stream) {
+  return guard([&] {
+    ECHO_CHECK(h, "optimizer_step: null handle");
+    optimizer_step(h, step, lr, beta1, beta2, eps, weight_decay, clip_max_norm, (cudaStream_t)stream);
+  });
+}
+int echo_optimizer_info(const echo_optimizer_t* h, int64_t* out4, float* clip2, void* stream) {
+  return guard([&] {
+    ECHO_CHECK(h && out4, "optimizer_info: null argument");
+    optimizer_info(h, out4, clip2, (cudaStream_t)stream);
+  });
+}
+void echo_optimizer_destroy(echo_optimizer_t* h) { optimizer_destroy(h); }
 int echo_shape_set_index(echo_shape_t* h, int32_t ddim_index, void* stream) {
   return guard([&] {
     ECHO_CHECK(h, "shape_set_index: null handle");

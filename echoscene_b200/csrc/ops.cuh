@@ -202,4 +202,11 @@ void fold_bn(const float* w, const float* b, const float* gamma, const float* be
 // graph ops
 void gather_rows(const float* src, const int64_t* idx, int64_t n_idx, int64_t n_rows, int64_t D, float* out, cudaStream_t s);   // idx outside [0, n_rows): NaN row
 
+// ---- training side (train.cu) ----
+// out = sqrt_ac[t_r] * x0 + sqrt_1mac[t_r] * noise, rows x row_len, one timestep per row
+void q_sample(const float* x0, const float* noise, const int64_t* t, const float* sqrt_ac, const float* sqrt_1mac, int64_t rows, int64_t row_len,
+              float* out, cudaStream_t s);
+// out[r][k] = mean((target - pred)^2 over columns ranges[2k] .. ranges[2k + 1]) -- ranges on the device
+void mse_rows(const float* pred, const float* target, int64_t rows, int64_t row_len, const int* ranges_dev, int n_ranges, float* out, cudaStream_t s);
+
 }  // namespace echo

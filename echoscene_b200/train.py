@@ -1,0 +1,151 @@
+"""Training-side pieces of the reference's train step that sit around the denoisers' forward / backward, on the CUDA
+path: ``q_sample``, the diffusion losses given a denoiser output, and the optimizer step of ``scripts/train_3dfront.py:247-259``
+(clip_grad_norm_ of the shape denoiser, the per-parameter NaN scrub loop, ``optimizerFULL.step()`` = AdamW) as one fused
+multi-tensor pass with no host synchronisation.  The backward pass of the denoisers is not part of this round; these are the
+HBM-bound stages a training iteration spends outside it, and they accept gradients from any producer (torch autograd today).
+No CPU fallback: CPU tensors raise ``EchoError``."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import EchoError
+
+
+def q_sample(x_start: torch.Tensor, t: torch.Tensor, noise: torch.Tensor, sqrt_alphas_cumprod: torch.Tensor,
+             sqrt_one_minus_alphas_cumprod: torch.Tensor) -> torch.Tensor:
+    """GaussianDiffusion.q_sample (diffusion_ddpm.py:191-201) / EchoToShape.q_sample (echo2shape.py:254-258): one timestep per
+    leading-dimension row, any trailing shape (boxes (B, 8), latents (B, 3, 16, 16, 16))."""
+    _lib.require_cuda(x_start, t, noise, sqrt_alphas_cumprod, sqrt_one_minus_alphas_cumprod)
+    if noise.shape != x_start.shape or t.shape != (x_start.shape[0],):
+        raise EchoError(f"q_sample: x_start {tuple(x_start.shape)}, noise {tuple(noise.shape)}, t {tuple(t.shape)}")
+    x0, nz = x_start.float().contiguous(), noise.float().contiguous()
+    t = t.to(torch.int64).contiguous()
+    a, b = sqrt_alphas_cumprod.float().contiguous(), sqrt_one_minus_alphas_cumprod.float().contiguous()
+    out = torch.empty_like(x0)
+    rows = x0.shape[0]
+    _lib.check(_lib.lib().echo_train_q_sample(_lib.ptr(x0), _lib.ptr(nz), _lib.ptr(t), _lib.ptr(a), _lib.ptr(b), rows,
+                                              x0.numel() // max(rows, 1), _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+def mse_rows(pred: torch.Tensor, target: torch.Tensor, ranges: Sequence[Sequence[int]]) -> torch.Tensor:
+    """out[r, k] = mean((target - pred)[r, ranges[k][0]:ranges[k][1]] ** 2) over the flattened trailing dimensions."""
+    _lib.require_cuda(pred, target)
+    if pred.shape != target.shape:
+        raise EchoError(f"mse_rows: {tuple(pred.shape)} vs {tuple(target.shape)}")
+    p, q = pred.float().contiguous(), target.float().contiguous()
+    rows = p.shape[0]
+    row_len = p.numel() // max(rows, 1)
+    flat = (C.c_int32 * (2 * len(ranges)))(*[int(v) for r in ranges for v in r])
+    out = torch.empty(rows, len(ranges), device=p.device)
+    _lib.check(_lib.lib().echo_train_mse_rows(_lib.ptr(p), _lib.ptr(q), rows, row_len, flat, len(ranges), _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+def layout_diffusion_loss(denoise_out: torch.Tensor, target: torch.Tensor, size_dim: int = 3, translation_dim: int = 3,
+                          angle_dim: int = 2):
+    """GaussianDiffusion.diffusion_loss with loss_iou = False (diffusion_ddpm.py:451-477): -> (loss, loss_dict with the reference's
+    keys).  Boxes are (B, size | translation | sin, cos)."""
+    bbox = size_dim + translation_dim + angle_dim
+    D = denoise_out.shape[1]
+    parts = mse_rows(denoise_out, target, [(0, size_dim), (size_dim, size_dim + translation_dim), (size_dim + translation_dim, bbox),
+                                            (0, bbox), (0, D)])
+    m = parts.mean(dim=0)
+    zero = torch.zeros((), device=parts.device)
+    return m[4] + zero, {"loss.bbox": m[3], "loss.trans": m[1], "loss.size": m[0], "loss.angle": m[2], "loss.liou": zero, "loss.bbox_iou": zero}
+
+
+def shape_diffusion_loss(model_output: torch.Tensor, target: torch.Tensor, t: torch.Tensor, logvar: torch.Tensor,
+                         lvlb_weights: torch.Tensor, l_simple_weight: float = 1.0, original_elbo_weight: float = 0.0):
+    """The loss terms of EchoToShape.p_losses (echo2shape.py:297-331) for the eps parameterisation."""
+    loss_simple = mse_rows(model_output, target, [(0, model_output[0].numel())])[:, 0]
+    logvar_t = logvar.to(loss_simple.device)[t]
+    loss = l_simple_weight * (loss_simple / torch.exp(logvar_t) + logvar_t).mean()
+    loss_vlb = (lvlb_weights.to(loss_simple.device)[t] * loss_simple).mean()
+    total = loss + original_elbo_weight * loss_vlb
+    return total, {"loss_simple": loss_simple.mean(), "loss_vlb": loss_vlb, "loss_total": total.detach().clone()}
+
+
+class FusedAdamW:
+    """``optimizerFULL`` of the reference (model/EchoScene.py:130-136: AdamW over the encoders, the layout denoiser and the shape
+    denoiser) with the step sequence of scripts/train_3dfront.py:247-259 fused into one pass:
+
+        clip_grad_norm_(clip_params, clip_max_norm)          # :251, the shape denoiser's parameters
+        for p in params: p.grad[isnan(p.grad)] = 0           # :252-256, ~700 `.any()` host synchronisations in the reference
+        optimizer.step()                                      # :258
+
+    ``params`` must have ``.grad`` set (fp32, CUDA, contiguous); the AdamW state lives in this object (``state_dict`` /
+    ``load_state_dict`` use torch.optim.AdamW's layout so the reference's checkpoints carry over)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-2, clip_params: Optional[Iterable[torch.nn.Parameter]] = None, clip_max_norm: float = 5.0):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise EchoError("FusedAdamW: no trainable parameters")
+        _lib.require_cuda(*self.params)
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
+        self.clip_ids = {id(p) for p in (clip_params or [])}
+        self.clip_max_norm = float(clip_max_norm) if self.clip_ids else 0.0
+        self.exp_avg = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params]
+        self.exp_avg_sq = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params]
+        self._handle, self._key = None, None
+        self.steps = 0
+
+    def _ensure(self):
+        for p in self.params:
+            if p.grad is None:
+                raise EchoError("FusedAdamW.step: a parameter has no gradient (the reference skips such parameters; allocate zeros)")
+            if p.dtype != torch.float32 or p.grad.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
+                raise EchoError("FusedAdamW: parameters and gradients must be contiguous fp32")
+        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in self.params)
+        if self._handle is not None and key == self._key:
+            return
+        arr = (_lib.OptTensor * len(self.params))()
+        for i, p in enumerate(self.params):
+            arr[i].param, arr[i].grad = p.data_ptr(), p.grad.data_ptr()
+            arr[i].exp_avg, arr[i].exp_avg_sq = self.exp_avg[i].data_ptr(), self.exp_avg_sq[i].data_ptr()
+            arr[i].numel, arr[i].clip_group = p.numel(), int(id(p) in self.clip_ids)
+        if self._handle is None:
+            h = C.c_void_p()
+            _lib.check(_lib.lib().echo_optimizer_create(C.byref(h), arr, len(self.params)))
+            self._handle = h
+        else:   # fresh gradient tensors (zero_grad(set_to_none=True)): same list, new addresses
+            _lib.check(_lib.lib().echo_optimizer_set_tensors(self._handle, arr, len(self.params), _lib.stream_ptr()))
+        self._key = key
+
+    def _destroy(self):
+        if self._handle is not None:
+            _lib.lib().echo_optimizer_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
+
+    @torch.no_grad()
+    def step(self, lr: Optional[float] = None):
+        """One fused step (three launches; no host synchronisation unless the gradient tensors moved).  ``lr``: this step's learning rate (the reference's LambdaLR
+        schedule, EchoScene.py:115-128, is evaluated by the caller)."""
+        self._ensure()
+        self.steps += 1
+        _lib.check(_lib.lib().echo_optimizer_step(self._handle, self.steps, float(self.lr if lr is None else lr), self.betas[0], self.betas[1],
+                                                  self.eps, self.weight_decay, self.clip_max_norm, _lib.stream_ptr()))
+
+    def info(self) -> Dict[str, float]:
+        """{steps, parameters, chunks, nan_gradients_scrubbed, last_grad_norm, last_clip_coef}; synchronises the stream."""
+        self._ensure()
+        out, clip = (C.c_int64 * 4)(), (C.c_float * 2)()
+        _lib.check(_lib.lib().echo_optimizer_info(self._handle, out, clip, _lib.stream_ptr()))
+        return {"steps": out[0], "parameters": out[1], "chunks": out[2], "nan_gradients_scrubbed": out[3], "last_grad_norm": clip[0],
+                "last_clip_coef": clip[1]}
+
+    def zero_grad(self):
+        for p in self.params:
+            if p.grad is not None:
+                p.grad.zero_()

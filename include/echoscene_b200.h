@@ -222,6 +222,42 @@ ECHO_API int echo_shape_set_index(echo_shape_t* h, int32_t ddim_index, void* str
 ECHO_API int echo_shape_latent(const echo_shape_t* h, int32_t n_nodes, float* out_dev, void* stream);
 ECHO_API void echo_shape_destroy(echo_shape_t* h);
 
+/* ---- training side: what a train_3dfront.py iteration does around the denoisers' forward / backward.
+ * echo_train_q_sample == GaussianDiffusion.q_sample (diffusion_ddpm.py:191-201) / EchoToShape.q_sample (echo2shape.py:254-258):
+ *   out[r, :] = sqrt_alphas_cumprod[t[r]] * x0[r, :] + sqrt_one_minus_alphas_cumprod[t[r]] * noise[r, :]   (rows x row_len f32, t int64).
+ * echo_train_mse_rows == the loss terms of diffusion_loss (diffusion_ddpm.py:451-462: ((target - out)**2).mean(dim=1) over the
+ *   size / translation / angle / whole-box column ranges) and of EchoToShape.p_losses (echo2shape.py:313: mse(reduction='none')
+ *   .mean([1,2,3,4])): out[r, k] = mean over columns [ranges[2k], ranges[2k+1]) of (target - pred)^2; `ranges` is a HOST array.
+ * echo_optimizer_* == the optimizer step of scripts/train_3dfront.py:247-259 in one pass over the parameters, no host
+ *   synchronisation: clip_grad_norm_(shape denoiser, max_norm) (:251) on the tensors flagged clip_group, then the
+ *   "isnan(grad).any() -> grad[isnan] = 0" loop over every parameter (:252-256), then optimizerFULL.step() = torch.optim.AdamW
+ *   (:258).  Gradients are left clipped and scrubbed in place, as the reference leaves them. */
+typedef struct echo_optimizer echo_optimizer_t;
+typedef struct {
+  float* param;        /* n f32, updated in place */
+  float* grad;         /* n f32 */
+  float* exp_avg;      /* n f32, AdamW state (zero before the first step) */
+  float* exp_avg_sq;   /* n f32 */
+  int64_t numel;
+  int32_t clip_group;  /* != 0: counted in, and scaled by, the gradient-norm clip */
+  int32_t reserved;
+} echo_opt_tensor_t;
+ECHO_API int echo_train_q_sample(const float* x0, const float* noise, const int64_t* t, const float* sqrt_alphas_cumprod,
+                        const float* sqrt_one_minus_alphas_cumprod, int64_t rows, int64_t row_len, float* out, void* stream);
+ECHO_API int echo_train_mse_rows(const float* pred, const float* target, int64_t rows, int64_t row_len, const int32_t* ranges_host,
+                        int32_t n_ranges, float* out, void* stream);
+ECHO_API int echo_optimizer_create(echo_optimizer_t** out, const echo_opt_tensor_t* tensors, int32_t n_tensors);
+/* the same tensor list at new addresses (torch's zero_grad(set_to_none=True) allocates fresh gradients every iteration) */
+ECHO_API int echo_optimizer_set_tensors(echo_optimizer_t* h, const echo_opt_tensor_t* tensors, int32_t n_tensors, void* stream);
+/* `step` = the number of this update, starting at 1 (torch.optim's state['step']): it sets the bias corrections.  Hyper-parameters
+ * are doubles: torch evaluates 1 - beta2, lr / (1 - beta1^step), ... on python floats and rounds the results to fp32. */
+ECHO_API int echo_optimizer_step(echo_optimizer_t* h, int64_t step, double lr, double beta1, double beta2, double eps, double weight_decay,
+                        double clip_max_norm /* <= 0: no clip */, void* stream);
+/* out4 = {steps taken, parameters, chunks, NaN gradients scrubbed so far}; clip2 (may be NULL) = {last total norm, last
+ * clip coefficient}.  Synchronises the stream (diagnostics; the step itself never does). */
+ECHO_API int echo_optimizer_info(const echo_optimizer_t* h, int64_t* out4, float* clip2, void* stream);
+ECHO_API void echo_optimizer_destroy(echo_optimizer_t* h);
+
 /* ---- VQ-VAE decode: VQVAE.decode_no_quant, model/networks/vqvae_networks/network.py:95-103 -- what
  * EchoToShape.rel2shape calls on the latents the DDIM chain returns (echo2shape.py:522).
  *   quantize (quantizer.py:68-99: nearest codebook entry per voxel) -> post_quant_conv -> Decoder3D
