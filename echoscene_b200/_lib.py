@@ -119,6 +119,7 @@ PROTOTYPES = {
     "echo_shape_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "echo_shape_step": (C.c_int, [_P, _P, _P, _P, _I, _P, _P]),
     "echo_shape_set_index": (C.c_int, [_P, _I, _P]),
+    "echo_metrics_validate_constraints": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _I, _P, _I, _P, _I, _I, C.c_float, _P, _P, _P]),
     "echo_train_q_sample": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P]),
     "echo_train_mse_rows": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _I, _P, _P]),
     "echo_optimizer_create": (C.c_int, [_P, _P, _I]),

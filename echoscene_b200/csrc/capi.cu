@@ -399,6 +399,23 @@ int echo_optimizer_info(const echo_optimizer_t* h, int64_t* out4, float* clip2, 
   });
 }
 void echo_optimizer_destroy(echo_optimizer_t* h) { optimizer_destroy(h); }
+int echo_metrics_validate_constraints(const int64_t* triples, int64_t n_triples, const float* boxes, int64_t n_nodes, int32_t box_dim,
+                                      const int32_t* keep, int32_t changes_mode, const int32_t* rel_of_pred_host, int32_t n_preds, int32_t strict,
+                                      float overlap_threshold, int8_t* out_rel, int8_t* out_ok, void* stream) {
+  return guard([&] {
+    ECHO_CHECK(n_triples >= 0 && n_nodes >= 0 && (box_dim == 6 || box_dim == 7) && n_preds > 0 && n_preds <= 64 && rel_of_pred_host,
+               "validate_constraints: bad arguments (box_dim %d, %d predicates)", box_dim, n_preds);
+    ECHO_CHECK(n_triples == 0 || (triples && boxes && out_rel && out_ok), "validate_constraints: null argument");
+    for (int i = 0; i < n_preds; ++i)
+      ECHO_CHECK(rel_of_pred_host[i] >= -1 && rel_of_pred_host[i] <= ECHO_REL_SYMMETRICAL_TO, "validate_constraints: relation code %d of predicate %d",
+                 rel_of_pred_host[i], i);
+    static thread_local int32_t* d_rel = nullptr;   // 64 ints, reused; the copy is stream-ordered in front of the kernel
+    if (!d_rel) ECHO_CUDA(cudaMalloc(&d_rel, sizeof(int32_t) * 64));
+    ECHO_CUDA(cudaMemcpyAsync(d_rel, rel_of_pred_host, sizeof(int32_t) * n_preds, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    validate_constraints(triples, n_triples, boxes, n_nodes, box_dim, keep, changes_mode != 0, d_rel, n_preds, strict != 0, overlap_threshold,
+                         out_rel, out_ok, (cudaStream_t)stream);
+  });
+}
 int echo_shape_set_index(echo_shape_t* h, int32_t ddim_index, void* stream) {
   return guard([&] {
     ECHO_CHECK(h, "shape_set_index: null handle");

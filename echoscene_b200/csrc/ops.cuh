@@ -209,4 +209,8 @@ void q_sample(const float* x0, const float* noise, const int64_t* t, const float
 // out[r][k] = mean((target - pred)^2 over columns ranges[2k] .. ranges[2k + 1]) -- ranges on the device
 void mse_rows(const float* pred, const float* target, int64_t rows, int64_t row_len, const int* ranges_dev, int n_ranges, float* out, cudaStream_t s);
 
+// ---- constraint metrics (metrics.cu): one thread per triple; out_rel = relation code (-1: not evaluated), out_ok = 0 / 1
+void validate_constraints(const int64_t* triples, int64_t T, const float* boxes, int64_t N, int D, const int32_t* keep, bool changes_mode,
+                          const int32_t* rel_of_pred_dev, int n_preds, bool strict, float overlap_threshold, int8_t* out_rel, int8_t* out_ok,
+                          cudaStream_t s);
 }  // namespace echo

@@ -258,6 +258,28 @@ ECHO_API int echo_optimizer_step(echo_optimizer_t* h, int64_t step, double lr, d
 ECHO_API int echo_optimizer_info(const echo_optimizer_t* h, int64_t* out4, float* clip2, void* stream);
 ECHO_API void echo_optimizer_destroy(echo_optimizer_t* h);
 
+/* ---- constraint metrics: validate_constrains / validate_constrains_changes, helpers/metrics_3dfront.py:57-306 -- the
+ * Python loop over the triples at the end of scripts/eval_3dfront.py (:209-210, :305) as one kernel.
+ *   triples (T,3) int64 [s,p,o]; boxes (N, D) f32, D = 6 or 7: [l, h, w, px, py, pz(, angle)] (denormalised, as the reference passes
+ *   them); keep (N) int32 or NULL; rel_of_pred_host[n_preds]: relation code of every predicate id (ECHO_REL_*, -1 = not a checked
+ *   relation) -- the caller resolves vocab["pred_idx_to_name"][p][:-1] once; changes_mode 0: a triple counts when keep is NULL or both
+ *   nodes are kept (validate_constrains), 1: when keep is NULL or either node changed (validate_constrains_changes).
+ *   out_rel (T) int8: ECHO_REL_* of the triple or -1 when it was skipped; out_ok (T) int8: 1 = the constraint holds. */
+#define ECHO_REL_LEFT 0
+#define ECHO_REL_RIGHT 1
+#define ECHO_REL_FRONT 2
+#define ECHO_REL_BEHIND 3
+#define ECHO_REL_BIGGER 4
+#define ECHO_REL_SMALLER 5
+#define ECHO_REL_TALLER 6
+#define ECHO_REL_SHORTER 7
+#define ECHO_REL_STANDING_ON 8
+#define ECHO_REL_CLOSE_BY 9
+#define ECHO_REL_SYMMETRICAL_TO 10
+ECHO_API int echo_metrics_validate_constraints(const int64_t* triples, int64_t n_triples, const float* boxes, int64_t n_nodes, int32_t box_dim,
+                                      const int32_t* keep, int32_t changes_mode, const int32_t* rel_of_pred_host, int32_t n_preds,
+                                      int32_t strict, float overlap_threshold, int8_t* out_rel, int8_t* out_ok, void* stream);
+
 /* ---- VQ-VAE decode: VQVAE.decode_no_quant, model/networks/vqvae_networks/network.py:95-103 -- what
  * EchoToShape.rel2shape calls on the latents the DDIM chain returns (echo2shape.py:522).
  *   quantize (quantizer.py:68-99: nearest codebook entry per voxel) -> post_quant_conv -> Decoder3D
