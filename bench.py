@@ -505,6 +505,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-graph-gcn", action="store_true",
+                    help="sharded step: run the echo GCN on the whole batched graph on every rank (round-1 behaviour) instead of on the "
+                         "connected components of the rank's own objects")
     ap.add_argument("--no-graph", action="store_true", help="launch every step's kernels directly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -555,7 +558,8 @@ def main():
             with torch.cuda.stream(xstream):
                 codes = m.embed_local(xin, n_total, tri.shape[0])
                 dist.all_gather_into_tensor(codes_all, codes)
-            m.trunk_local(xin, obj_begin, codes_all, uc_all, tri, index=index, out=xout, codes_stream=xstream)
+            m.trunk_local(xin, obj_begin, codes_all, uc_all, tri, index=index, out=xout, codes_stream=xstream,
+                          restrict_to_components=not args.full_graph_gcn)
 
     m._ensure(n_total, tri.shape[0], N_NODES if world > 1 else None)
     m.frozen = True
@@ -579,7 +583,8 @@ def main():
                 with torch.cuda.stream(xstream):
                     codes = m.embed_local(xin, n_total, tri.shape[0])
                     dist.all_gather_into_tensor(codes_all, codes)
-                m.trunk_local(xin, obj_begin, codes_all, uc_all, tri, index=INDEX_FROM_DEVICE, out=xout, codes_stream=xstream)
+                m.trunk_local(xin, obj_begin, codes_all, uc_all, tri, index=INDEX_FROM_DEVICE, out=xout, codes_stream=xstream,
+                              restrict_to_components=not args.full_graph_gcn)
         try:
             m.set_step_index(DDIM_STEPS - 1)
             cap = torch.cuda.Stream(device=dev)
@@ -722,7 +727,8 @@ def main():
                 "config": {"workload": "echoscene N=16 nodes, 64^3 SDF (3x16^3 latent), 100-step DDIM: shape denoiser step "
                                        "(UNet3DModel forward incl. echo message passing + DDIM update)",
                            "n_nodes": N_NODES, "n_triples": N_TRIPLES, "ddim_steps": DDIM_STEPS, "scenes": world,
-                           "sharding": "1 scene" if world == 1 else f"{world} scenes batched, 16 objects per rank, NCCL all-gather of (16,64) fp32 codes per step",
+                           "sharding": "1 scene" if world == 1 else f"{world} scenes batched, 16 objects per rank, NCCL all-gather of (16,64) fp32 codes per step; echo GCN on "
+                                       + ("the whole batched graph" if args.full_graph_gcn else "the connected components of the rank's objects"),
                            "l2": "not flushed: one step streams 0.84 GB of bf16 weights + >2 GB of activations (>> 126 MB L2)",
                            "weights": "random init (reference initialisers, zero-init tensors re-drawn), seed 12"},
                 "clocks": clocks, "gpu_launches": launches, "launch_mode": graph_note,

@@ -624,10 +624,38 @@ class UNet3DModel(_SpecModule):
 
     @torch.no_grad()
     def trunk_local(self, x_local, obj_begin, codes_all, obj_embed_all, triples, index: int = -1, timesteps_all=None,
-                    out: Optional[torch.Tensor] = None, codes_stream: Optional[torch.cuda.Stream] = None):
+                    out: Optional[torch.Tensor] = None, codes_stream: Optional[torch.cuda.Stream] = None,
+                    restrict_to_components: bool = False):
         """codes_stream: the stream the embed + all-gather of `codes_all` were queued on; when given, only the echo chain
-        waits for it and the first trunk blocks overlap the exchange."""
+        waits for it and the first trunk blocks overlap the exchange.
+        restrict_to_components: run the echo GCN only on the connected components of the scene graph that contain the local
+        objects (`shard.echo_components`; exact -- message passing never leaves a component).  In a collated batch of scenes that
+        is the rank's own scenes instead of the whole batch: the redundant part of the sharded step no longer grows with the
+        number of ranks."""
         _lib.require_cuda(x_local, codes_all, obj_embed_all, triples)
+        if restrict_to_components:
+            key = (triples.data_ptr(), tuple(triples.shape), triples._version, int(codes_all.shape[0]), int(obj_begin), int(x_local.shape[0]),
+                   obj_embed_all.data_ptr())
+            hit = self.__dict__.setdefault("_component_cache", {}).get(key)
+            if hit is None:
+                from . import shard
+                res = shard.echo_components(triples, codes_all.shape[0], int(obj_begin), int(x_local.shape[0]))
+                if res is not None:
+                    nodes, tri_sub, begin_sub = res
+                    res = (nodes, tri_sub, begin_sub, obj_embed_all.reshape(codes_all.shape[0], -1).index_select(0, nodes).contiguous())
+                if len(self._component_cache) > 16:
+                    self._component_cache.clear()
+                hit = self._component_cache[key] = (res, triples, obj_embed_all)    # the keyed tensors stay alive with the entry
+            if hit[0] is not None:
+                nodes, tri_sub, begin_sub, uc_sub = hit[0]
+                if codes_stream is not None:   # the gather of the exchanged codes belongs behind the all-gather, on its stream
+                    with torch.cuda.stream(codes_stream):
+                        codes_sub = codes_all.index_select(0, nodes)
+                else:
+                    codes_sub = codes_all.index_select(0, nodes)
+                t_sub = None if timesteps_all is None else timesteps_all.index_select(0, nodes)
+                return self.trunk_local(x_local, begin_sub, codes_sub, uc_sub, tri_sub, index=index, timesteps_all=t_sub, out=out,
+                                        codes_stream=codes_stream)
         n = codes_all.shape[0]
         nl = x_local.shape[0]
         self._ensure(n, triples.shape[0], nl)

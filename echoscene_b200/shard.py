@@ -104,3 +104,42 @@ def scene_subgraph(triples: torch.Tensor, node_begin: int, node_end: int) -> tor
     local[:, 0] -= node_begin
     local[:, 2] -= node_begin
     return local
+
+
+def echo_components(triples: torch.Tensor, n_nodes: int, obj_begin: int, n_local: int):
+    """The echo of a node depends only on its connected component of the scene graph (message passing never leaves it), so a rank
+    that owns objects [obj_begin, obj_begin + n_local) needs the GCN on the components those objects belong to and on nothing else
+    -- in a collated batch (block-diagonal graph) that is the rank's own scenes instead of the whole batch, for any graph it is
+    exact.  -> None when the components cover every node, else (nodes, triples_sub, begin_sub):
+      nodes        (n_sub,) int64, ascending: the nodes of those components (on the device of `triples`);
+      triples_sub  the triples among them, in their original order, re-indexed into `nodes`;
+      begin_sub    where the local range starts inside `nodes` (it stays contiguous: `nodes` is sorted and contains all of it).
+    One host round trip (union-find over the edges); callers cache the result per (graph, range)."""
+    tri = triples.detach().cpu()
+    parent = list(range(n_nodes))
+
+    def find(a):
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+
+    for s, _, o in tri.tolist():
+        ra, rb = find(s), find(o)
+        if ra != rb:
+            parent[max(ra, rb)] = min(ra, rb)
+    wanted = {find(i) for i in range(obj_begin, obj_begin + n_local)}
+    nodes = [i for i in range(n_nodes) if find(i) in wanted]
+    if len(nodes) == n_nodes:
+        return None
+    remap = torch.full((n_nodes,), -1, dtype=torch.int64)
+    remap[torch.tensor(nodes, dtype=torch.int64)] = torch.arange(len(nodes), dtype=torch.int64)
+    if tri.shape[0]:
+        keep = remap[tri[:, 0]] >= 0                      # an edge lies inside one component: its object node is kept with it
+        sub = tri[keep].clone()
+        sub[:, 0], sub[:, 2] = remap[sub[:, 0]], remap[sub[:, 2]]
+    else:
+        sub = tri.clone()
+    dev = triples.device
+    return torch.tensor(nodes, dtype=torch.int64, device=dev), sub.to(dev), int(remap[obj_begin])
+

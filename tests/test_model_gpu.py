@@ -308,3 +308,35 @@ def test_sharded_trunk_with_codes_on_their_own_stream(shape_sd):
         outs.append(ms.trunk_local(xd[lo:hi], lo, codes_all, ucd, tri, index=1, codes_stream=s2))
     torch.cuda.synchronize()
     assert torch.equal(torch.cat(outs), full)
+
+
+def test_sharded_trunk_restricted_to_the_components_of_its_objects(shape_sd):
+    """trunk_local(restrict_to_components=True): a rank that owns the second scene of a two-scene batch runs the echo GCN on that
+    scene only (shard.echo_components) and reproduces the batched step; with the exchange on its own stream too."""
+    m = shape_model(shape_sd, ddim_steps=2)
+    gs = [synth.make_scene_graph(3, 4, 1), synth.make_scene_graph(4, 6, 2)]
+    b = synth.batch_scene_graphs(gs)
+    uc, x_T = synth.shape_inputs(7, 50, same_noise=False)
+    tri, ucd, xd = b.triples.to(DEV), uc.to(DEV), x_T.to(DEV)
+    full = m.ddim_step(xd, ucd, tri, 1)
+    ms = shape_model(shape_sd, ddim_steps=2)
+    codes = torch.cat([ms.embed_local(xd[:3], 7, tri.shape[0]), ms.embed_local(xd[3:], 7, tri.shape[0])])
+    plain = ms.trunk_local(xd[3:], 3, codes, ucd, tri, index=1)
+    assert torch.equal(plain, full[3:])
+    got = ms.trunk_local(xd[3:], 3, codes, ucd, tri, index=1, restrict_to_components=True)
+    assert_close(got, full[3:], 1e-5, "component-restricted echo, rank 1")
+    got0 = ms.trunk_local(xd[:3], 0, codes, ucd, tri, index=1, restrict_to_components=True)
+    assert_close(got0, full[:3], 1e-5, "component-restricted echo, rank 0")
+    s2 = torch.cuda.Stream()
+    s2.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s2):
+        codes2 = codes.clone()
+    got2 = ms.trunk_local(xd[3:], 3, codes2, ucd, tri, index=1, codes_stream=s2, restrict_to_components=True)
+    torch.cuda.synchronize()
+    assert torch.equal(got2, got)
+    # one connected scene: nothing to restrict, the call is the plain one
+    g1 = synth.make_scene_graph(3, 4, 9)
+    uc1, x1 = synth.shape_inputs(3, 90, same_noise=True)
+    t1, u1, xx1 = g1.triples.to(DEV), uc1.to(DEV), x1.to(DEV)
+    c1 = torch.cat([ms.embed_local(xx1[:2], 3, 4), ms.embed_local(xx1[2:], 3, 4)])
+    assert torch.equal(ms.trunk_local(xx1[:2], 0, c1, u1, t1, index=1, restrict_to_components=True), ms.trunk_local(xx1[:2], 0, c1, u1, t1, index=1))

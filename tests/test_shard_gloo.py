@@ -146,3 +146,22 @@ def test_scene_shard_equals_batched_gloo():
     ret = mgr.dict()
     mp.spawn(_scene_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert len(ret) == world and all(v < 1e-5 for v in ret.values()), dict(ret)
+
+
+def test_echo_components_restrict_a_block_diagonal_batch():
+    """shard.echo_components: the nodes / re-indexed triples of the connected components that contain a rank's objects."""
+    from echoscene_b200 import shard, synth
+    gs = [synth.make_scene_graph(3, 4, 1), synth.make_scene_graph(4, 6, 2), synth.make_scene_graph(2, 1, 3)]
+    b = synth.batch_scene_graphs(gs)
+    nodes, tri, begin = shard.echo_components(b.triples, b.n_nodes, 3, 4)          # the rank owns scene 1 = nodes 3..6
+    assert nodes.tolist() == [3, 4, 5, 6] and begin == 0
+    assert torch.equal(tri, gs[1].triples)                                          # its own triples, re-based, original order
+    nodes, tri, begin = shard.echo_components(b.triples, b.n_nodes, 5, 3)          # a range across scenes 1 and 2
+    assert nodes.tolist() == [3, 4, 5, 6, 7, 8] and begin == 2
+    want = torch.cat([gs[1].triples, gs[2].triples + torch.tensor([4, 0, 4])])
+    assert torch.equal(tri, want)
+    assert shard.echo_components(b.triples, b.n_nodes, 0, b.n_nodes) is None        # everything is wanted: nothing to restrict
+    assert shard.echo_components(gs[1].triples, 4, 0, 2) is None or len(shard.echo_components(gs[1].triples, 4, 0, 2)[0]) <= 4
+    # an isolated node (no triples) is its own component
+    nodes, tri, begin = shard.echo_components(torch.zeros(0, 3, dtype=torch.int64), 5, 2, 1)
+    assert nodes.tolist() == [2] and tri.shape == (0, 3) and begin == 0
