@@ -531,12 +531,14 @@ class UNet3DModel(_SpecModule):
             self.ddim_steps, self.timesteps_total, self.linear_start, self.linear_end = new
             self._destroy_handle()
 
-    def _ensure(self, n_nodes, n_triples, n_local=None):
+    def _ensure(self, n_nodes, n_triples, n_local=None, sharded_call=False):
+        """sharded_call: the caller is embed_local / trunk_local (codes come from outside): a handle built for a shard also serves
+        a call whose local range happens to be the whole (sub)graph, so the handle is not rebuilt back and forth."""
         n_local = n_nodes if n_local is None else n_local
         ver = self._weights_version()
         cap = self._handle_key[1] if self._handle_key else (0, 0, 0)
         if (self._handle is not None and self._handle_key[0] == ver and n_nodes <= cap[0] and n_triples <= cap[1]
-                and n_local <= cap[2] and (cap[2] == cap[0]) == (n_local == n_nodes)):
+                and n_local <= cap[2] and ((cap[2] == cap[0]) == (n_local == n_nodes) or (sharded_call and cap[2] != cap[0]))):
             return
         self._destroy_handle()
         cap = (max(n_nodes, 1), _next_pow2(n_triples, 128), max(n_local, 1))
@@ -616,7 +618,7 @@ class UNet3DModel(_SpecModule):
     def embed_local(self, x_local, n_nodes, n_triples):
         _lib.require_cuda(x_local)
         nl = x_local.shape[0]
-        self._ensure(n_nodes, n_triples, nl)
+        self._ensure(n_nodes, n_triples, nl, sharded_call=True)
         codes = torch.empty(nl, self.cfg.gconv_dim, device=x_local.device)
         x_local = x_local.float().contiguous()
         _lib.check(_lib.lib().echo_shape_embed(self._handle, _lib.ptr(x_local), nl, _lib.ptr(codes), _lib.stream_ptr()))
@@ -658,7 +660,7 @@ class UNet3DModel(_SpecModule):
                                         codes_stream=codes_stream)
         n = codes_all.shape[0]
         nl = x_local.shape[0]
-        self._ensure(n, triples.shape[0], nl)
+        self._ensure(n, triples.shape[0], nl, sharded_call=True)
         g = _lib.graph_for(triples, n)
         x_local = x_local.float().contiguous()
         obj_embed_all = obj_embed_all.reshape(n, -1).float().contiguous()

@@ -92,7 +92,8 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
     if shutil.which("gcc") is None:
         pytest.skip("no C compiler")
     pairs = {"echo_weight_t": _lib.Weight, "echo_gcn_desc_t": _lib.GcnDesc, "echo_layout_desc_t": _lib.LayoutDesc,
-             "echo_shape_desc_t": _lib.ShapeDesc, "echo_scene_desc_t": _lib.SceneDesc, "echo_vqvae_desc_t": _lib.VqvaeDesc}
+             "echo_shape_desc_t": _lib.ShapeDesc, "echo_scene_desc_t": _lib.SceneDesc, "echo_vqvae_desc_t": _lib.VqvaeDesc,
+             "echo_opt_tensor_t": _lib.OptTensor}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "echoscene_b200.h")}"',
              'int main(void) {']
     for cname, cls in pairs.items():
