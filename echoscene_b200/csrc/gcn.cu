@@ -42,6 +42,35 @@ __global__ void edge_combine_kernel(const float* __restrict__ pso, const float* 
   }
 }
 
+// The same with the projected node table [N][2H] staged in shared memory first (scene-sized graphs: N * 2H floats fit): every node
+// row is read from HBM / L2 once per block, coalesced, instead of once per incident edge; a warp then combines one edge from
+// shared memory.  Identical arithmetic and association, so the two kernels are interchangeable bit for bit.
+__global__ void edge_combine_staged_kernel(const float* __restrict__ pso, const float* __restrict__ pp, const float* __restrict__ b1,
+                                           const int* __restrict__ s_idx, const int* __restrict__ o_idx, int T, int N, int H,
+                                           float* __restrict__ h1) {
+  extern __shared__ float4 node_s[];   // [N][2H / 4]
+  const int row4 = 2 * H / 4;
+  for (int i = threadIdx.x; i < N * row4; i += blockDim.x) node_s[i] = __ldg(reinterpret_cast<const float4*>(pso) + i);
+  __syncthreads();
+  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (int t = blockIdx.x * warps + (threadIdx.x >> 5); t < T; t += gridDim.x * warps) {
+    const float4* ps = node_s + (size_t)s_idx[t] * row4;
+    const float4* po = node_s + (size_t)o_idx[t] * row4 + H / 4;
+    const float4* pq = reinterpret_cast<const float4*>(pp + (int64_t)t * H);
+    const float4* bb = reinterpret_cast<const float4*>(b1);
+    float4* out = reinterpret_cast<float4*>(h1 + (int64_t)t * H);
+    for (int q = lane; q < H / 4; q += 32) {
+      const float4 a = ps[q], b = __ldg(pq + q), c = po[q], d = __ldg(bb + q);
+      float4 r;
+      r.x = fmaxf(((a.x + b.x) + c.x) + d.x, 0.f);
+      r.y = fmaxf(((a.y + b.y) + c.y) + d.y, 0.f);
+      r.z = fmaxf(((a.z + b.z) + c.z) + d.z, 0.f);
+      r.w = fmaxf(((a.w + b.w) + c.w) + d.w, 0.f);
+      out[q] = r;
+    }
+  }
+}
+
 // pooled[n, :] = (sum over items of t2[t, role ? H+Dp : 0 ...]) / max(count, 1)     (graph.py:161-199)
 __global__ void node_pool_kernel(const float* __restrict__ t2, int ld, int H, int off_o, const int* __restrict__ node_off,
                                  const int* __restrict__ node_items, int N, float* __restrict__ pooled) {
@@ -200,7 +229,12 @@ void Gcn::forward(const echo_graph* g, const float* obj, const float* pred, floa
       a.X = cur_pred; a.ldx = dp; a.M = T; a.K = dp; a.nout = H; a.W = L.w_p.w; a.Y = pp; a.ldy = H;
       linear_auto(a, s);
       // 2. warp-per-edge gather + combine
-      edge_combine_kernel<<<cdiv((int64_t)T * 32, 256), 256, 0, s>>>(pso, pp, L.b1, g->s_idx, g->o_idx, T, H, h1);
+      const size_t table = (size_t)N * 2 * H * sizeof(float);
+      if (table <= 48 * 1024) {   // a scene-sized graph: node features staged in shared memory, 16 edges per block
+        edge_combine_staged_kernel<<<cdiv(T, 16), 512, table, s>>>(pso, pp, L.b1, g->s_idx, g->o_idx, T, N, H, h1);
+      } else {
+        edge_combine_kernel<<<cdiv((int64_t)T * 32, 256), 256, 0, s>>>(pso, pp, L.b1, g->s_idx, g->o_idx, T, H, h1);
+      }
       ECHO_LAUNCH_CHECK();
       // 3. second Linear of net1
       a = LinArgs();

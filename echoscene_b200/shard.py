@@ -3,9 +3,10 @@
 Inside a shape step the only cross-object operation is the 5-layer echo GCN over the (N, 1408) node features, of which
 only the 64-d shape code depends on the (sharded) latents.  So objects are partitioned contiguously over ranks; per step
 each rank (1) runs `shape_embeddings` on its own latents, (2) takes part in ONE all-gather of the (n_local, 64) fp32
-codes — the echo exchange, 256 B per object over NVLink, (3) runs the cheap GCN redundantly on the whole graph and the
-UNet trunk + DDIM update on its own objects.  No other collective touches the data path; the final latents are gathered
-once after the chain.
+codes — the echo exchange, 256 B per object over NVLink, (3) runs the cheap GCN on the connected components of the scene graph
+that contain its objects (`echo_components`: message passing never leaves a component, so that is all the echo of its objects
+depends on -- one scene of a collated batch, the whole graph of a single scene) and the UNet trunk + DDIM update on its own
+objects.  No other collective touches the data path; the final latents are gathered once after the chain.
 
 When a batch holds at least as many scenes as there are GPUs (BASELINE config 4: 64 scenes over 8 GPUs) the shard is by
 SCENE instead: the batched graph is block-diagonal per scene (collate_fn offsets, dataset/threedfront_dataset.py:698-701),
