@@ -45,7 +45,7 @@ class OptTensor(C.Structure):   # echo_opt_tensor_t
 class GcnDesc(C.Structure):
     _fields_ = [("input_dim_obj", C.c_int32), ("input_dim_pred", C.c_int32), ("num_layers", C.c_int32),
                 ("hidden_dim", C.c_int32), ("output_dim", C.c_int32), ("max_nodes", C.c_int32),
-                ("max_triples", C.c_int32), ("bn_eps", C.c_float)]
+                ("max_triples", C.c_int32), ("bn_eps", C.c_float), ("keep_train_weights", C.c_int32)]
 
 
 class LayoutDesc(C.Structure):
@@ -109,6 +109,7 @@ PROTOTYPES = {
     "echo_gather_rows": (C.c_int, [_P, _P, _L, _L, _L, _P, _P]),
     "echo_gcn_create": (C.c_int, [C.POINTER(_P), C.POINTER(GcnDesc), C.POINTER(Weight), _I]),
     "echo_gcn_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "echo_gcn_forward_train": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "echo_gcn_destroy": (None, [_P]),
     "echo_layout_create": (C.c_int, [C.POINTER(_P), C.POINTER(LayoutDesc), C.POINTER(Weight), _I]),
     "echo_layout_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),

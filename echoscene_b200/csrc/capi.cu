@@ -268,6 +268,13 @@ int echo_gcn_forward(echo_gcn_t* h, const echo_graph_t* g, const float* obj, con
     h->net.forward(g, obj, pred, obj_out, pred_out, (cudaStream_t)stream);
   });
 }
+int echo_gcn_forward_train(echo_gcn_t* h, const echo_graph_t* g, const float* obj, const float* pred, float* obj_out, float* pred_out,
+                           void* stream) {
+  return guard([&] {
+    ECHO_CHECK(h && g && obj && (pred || g->n_triples == 0) && obj_out, "gcn_forward_train: null argument");
+    h->net.forward(g, obj, pred, obj_out, pred_out, (cudaStream_t)stream, true);
+  });
+}
 
 void echo_gcn_destroy(echo_gcn_t* h) {
   if (!h) return;

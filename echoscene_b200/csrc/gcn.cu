@@ -23,7 +23,7 @@ namespace {
 
 __global__ void edge_combine_kernel(const float* __restrict__ pso, const float* __restrict__ pp, const float* __restrict__ b1,
                                     const int* __restrict__ s_idx, const int* __restrict__ o_idx, int T, int H,
-                                    float* __restrict__ h1) {
+                                    float* __restrict__ h1, float floor_) {
   const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (t >= T) return;
   const float4* ps = reinterpret_cast<const float4*>(pso + (int64_t)s_idx[t] * 2 * H);
@@ -34,10 +34,10 @@ __global__ void edge_combine_kernel(const float* __restrict__ pso, const float* 
   for (int q = lane; q < H / 4; q += 32) {
     const float4 a = __ldg(ps + q), b = __ldg(pq + q), c = __ldg(po + q), d = __ldg(bb + q);
     float4 r;
-    r.x = fmaxf(((a.x + b.x) + c.x) + d.x, 0.f);
-    r.y = fmaxf(((a.y + b.y) + c.y) + d.y, 0.f);
-    r.z = fmaxf(((a.z + b.z) + c.z) + d.z, 0.f);
-    r.w = fmaxf(((a.w + b.w) + c.w) + d.w, 0.f);
+    r.x = fmaxf(((a.x + b.x) + c.x) + d.x, floor_);   // floor_ = 0: ReLU; -inf: the pre-activation (batch-statistics mode)
+    r.y = fmaxf(((a.y + b.y) + c.y) + d.y, floor_);
+    r.z = fmaxf(((a.z + b.z) + c.z) + d.z, floor_);
+    r.w = fmaxf(((a.w + b.w) + c.w) + d.w, floor_);
     out[q] = r;
   }
 }
@@ -47,7 +47,7 @@ __global__ void edge_combine_kernel(const float* __restrict__ pso, const float* 
 // shared memory.  Identical arithmetic and association, so the two kernels are interchangeable bit for bit.
 __global__ void edge_combine_staged_kernel(const float* __restrict__ pso, const float* __restrict__ pp, const float* __restrict__ b1,
                                            const int* __restrict__ s_idx, const int* __restrict__ o_idx, int T, int N, int H,
-                                           float* __restrict__ h1) {
+                                           float* __restrict__ h1, float floor_) {
   extern __shared__ float4 node_s[];   // [N][2H / 4]
   const int row4 = 2 * H / 4;
   for (int i = threadIdx.x; i < N * row4; i += blockDim.x) node_s[i] = __ldg(reinterpret_cast<const float4*>(pso) + i);
@@ -62,12 +62,43 @@ __global__ void edge_combine_staged_kernel(const float* __restrict__ pso, const 
     for (int q = lane; q < H / 4; q += 32) {
       const float4 a = ps[q], b = __ldg(pq + q), c = po[q], d = __ldg(bb + q);
       float4 r;
-      r.x = fmaxf(((a.x + b.x) + c.x) + d.x, 0.f);
-      r.y = fmaxf(((a.y + b.y) + c.y) + d.y, 0.f);
-      r.z = fmaxf(((a.z + b.z) + c.z) + d.z, 0.f);
-      r.w = fmaxf(((a.w + b.w) + c.w) + d.w, 0.f);
+      r.x = fmaxf(((a.x + b.x) + c.x) + d.x, floor_);
+      r.y = fmaxf(((a.y + b.y) + c.y) + d.y, floor_);
+      r.z = fmaxf(((a.z + b.z) + c.z) + d.z, floor_);
+      r.w = fmaxf(((a.w + b.w) + c.w) + d.w, floor_);
       out[q] = r;
     }
+  }
+}
+
+// BatchNorm1d on the statistics of the batch (the rows of the call), then ReLU, in place: y = (x - mean) rsqrt(var + eps) g + b with
+// the BIASED variance, as torch normalises in training mode (model/layers.py:29-30 under model.train()).  Block = 32 columns x 8
+// row lanes, two passes over the rows (mean, then centred squares), fixed summation order.
+__global__ void bn_rows_train_kernel(float* __restrict__ x, int64_t ld, int rows, int C, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, float eps) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, r0 = threadIdx.y;
+  const bool in = c < C;
+  float s = 0.f;
+  if (in) for (int r = r0; r < rows; r += 8) s += x[(int64_t)r * ld + c];
+  red[r0][threadIdx.x] = s;
+  __syncthreads();
+  float mean = 0.f;
+  for (int k = 0; k < 8; ++k) mean += red[k][threadIdx.x];
+  mean /= (float)rows;
+  __syncthreads();
+  float q = 0.f;
+  if (in) for (int r = r0; r < rows; r += 8) { const float d = x[(int64_t)r * ld + c] - mean; q = fmaf(d, d, q); }
+  red[r0][threadIdx.x] = q;
+  __syncthreads();
+  float var = 0.f;
+  for (int k = 0; k < 8; ++k) var += red[k][threadIdx.x];
+  var /= (float)rows;
+  if (!in) return;
+  const float sc = rsqrtf(var + eps) * gamma[c], sh = beta[c];
+  for (int r = r0; r < rows; r += 8) {
+    const int64_t i = (int64_t)r * ld + c;
+    x[i] = fmaxf((x[i] - mean) * sc + sh, 0.f);
   }
 }
 
@@ -158,6 +189,7 @@ void Gcn::create(const WeightMap& wm, const std::string& prefix, const echo_gcn_
   dp = d.input_dim_pred;
   H = d.hidden_dim;
   const float eps = d.bn_eps > 0 ? d.bn_eps : 1e-5f;
+  bn_eps = eps;
   max_d = d.input_dim_obj;
   layers.clear();
   for (int i = 0; i < d.num_layers; ++i) {
@@ -185,6 +217,33 @@ void Gcn::create(const WeightMap& wm, const std::string& prefix, const echo_gcn_
     L.w2 = folded_linear(wm, p + "net1." + std::to_string(st), p + "net1." + std::to_string(st + 1), 2 * H + dp, H, eps, pool, s);
     L.w3 = folded_linear(wm, p + "net2.0", p + "net2.1", H, H, eps, pool, s);
     L.w4 = folded_linear(wm, p + "net2." + std::to_string(st), p + "net2." + std::to_string(st + 1), L.dout, H, eps, pool, s);
+    if (bn && d.keep_train_weights) {   // batch-statistics mode: the unfolded Linears and the BatchNorm1d scale / shift
+      auto vec = [&](const std::string& name, int n) {
+        const WView& v = wm.get(name, {n});
+        float* o = pool.alloc_n<float>(n);
+        ECHO_CUDA(cudaMemcpyAsync(o, v.p, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+        return (const float*)o;
+      };
+      Mat r1 = plain_linear(wm, p + "net1.0", H, k1, pool, s);
+      float* rso = pool.alloc_n<float>((size_t)2 * H * L.din);
+      copy_cols(r1.w, k1, H, L.din, rso, L.din, s);
+      copy_cols(r1.w + L.din + dp, k1, H, L.din, rso + (size_t)H * L.din, L.din, s);
+      float* rp = pool.alloc_n<float>((size_t)H * dp);
+      copy_cols(r1.w + L.din, k1, H, dp, rp, dp, s);
+      L.t_so.w = rso; L.t_so.nout = 2 * H; L.t_so.K = L.din;
+      L.t_p.w = rp; L.t_p.nout = H; L.t_p.K = dp;
+      L.t_b1 = r1.b;
+      L.t2 = plain_linear(wm, p + "net1.3", 2 * H + dp, H, pool, s);
+      L.t3 = plain_linear(wm, p + "net2.0", H, H, pool, s);
+      L.t4 = plain_linear(wm, p + "net2.3", L.dout, H, pool, s);
+      const char* bns[4] = {"net1.1", "net1.4", "net2.1", "net2.4"};
+      const int widths[4] = {H, 2 * H + dp, H, L.dout};
+      for (int k = 0; k < 4; ++k) {
+        L.bn_g[k] = vec(p + bns[k] + ".weight", widths[k]);
+        L.bn_b[k] = vec(p + bns[k] + ".bias", widths[k]);
+      }
+      L.has_train = true;
+    }
     L.residual = wm.has(p + "linear_projection.weight");
     if (L.residual) {
       L.proj = plain_linear(wm, p + "linear_projection", L.dout, L.din, pool, s);
@@ -208,9 +267,19 @@ void Gcn::create(const WeightMap& wm, const std::string& prefix, const echo_gcn_
   ECHO_CUDA(cudaStreamSynchronize(s));
 }
 
-void Gcn::forward(const echo_graph* g, const float* obj, const float* pred, float* obj_out, float* pred_out, cudaStream_t s) {
+void Gcn::forward(const echo_graph* g, const float* obj, const float* pred, float* obj_out, float* pred_out, cudaStream_t s,
+                  bool batch_stats) {
   ECHO_CHECK(g, "gcn: null graph");
   const int N = g->n_nodes, T = g->n_triples;
+  if (batch_stats)
+    for (auto& L : layers)
+      ECHO_CHECK(L.has_train, "gcn: batch-statistics forward needs a handle created with keep_train_weights (and BatchNorm1d MLPs)");
+  // BatchNorm1d over the rows of the call + ReLU, in place (batch-statistics mode only)
+  auto bn_relu = [&](float* x, int64_t ld, int rows, int C, const float* gm, const float* bt) {
+    if (rows == 0) return;
+    bn_rows_train_kernel<<<cdiv(C, 32), dim3(32, 8), 0, s>>>(x, ld, rows, C, gm, bt, bn_eps);
+    ECHO_LAUNCH_CHECK();
+  };
   ECHO_CHECK(N <= max_nodes && T <= max_triples, "gcn: graph (%d nodes, %d triples) exceeds handle capacity (%d, %d)", N, T,
              max_nodes, max_triples);
   const float* cur_obj = obj;
@@ -222,25 +291,31 @@ void Gcn::forward(const echo_graph* g, const float* obj, const float* pred, floa
     float* npred = lastl && pred_out ? pred_out : pred_pp[li & 1];
     LinArgs a;
     // 1. node / predicate projections of net1.0
-    a.X = cur_obj; a.ldx = L.din; a.M = N; a.K = L.din; a.nout = 2 * H; a.W = L.w_so.w; a.Y = pso; a.ldy = 2 * H;
+    const bool bs = batch_stats;
+    a.X = cur_obj; a.ldx = L.din; a.M = N; a.K = L.din; a.nout = 2 * H; a.W = bs ? L.t_so.w : L.w_so.w; a.Y = pso; a.ldy = 2 * H;
     linear_auto(a, s);
     if (T > 0) {
       a = LinArgs();
-      a.X = cur_pred; a.ldx = dp; a.M = T; a.K = dp; a.nout = H; a.W = L.w_p.w; a.Y = pp; a.ldy = H;
+      a.X = cur_pred; a.ldx = dp; a.M = T; a.K = dp; a.nout = H; a.W = bs ? L.t_p.w : L.w_p.w; a.Y = pp; a.ldy = H;
       linear_auto(a, s);
-      // 2. warp-per-edge gather + combine
+      // 2. warp-per-edge gather + combine (+ ReLU; batch statistics: the pre-activation, BatchNorm1d over the T rows, then ReLU)
       const size_t table = (size_t)N * 2 * H * sizeof(float);
+      const float floor_ = bs ? -INFINITY : 0.f;
+      const float* b1 = bs ? L.t_b1 : L.b1;
       if (table <= 48 * 1024) {   // a scene-sized graph: node features staged in shared memory, 16 edges per block
-        edge_combine_staged_kernel<<<cdiv(T, 16), 512, table, s>>>(pso, pp, L.b1, g->s_idx, g->o_idx, T, N, H, h1);
+        edge_combine_staged_kernel<<<cdiv(T, 16), 512, table, s>>>(pso, pp, b1, g->s_idx, g->o_idx, T, N, H, h1, floor_);
       } else {
-        edge_combine_kernel<<<cdiv((int64_t)T * 32, 256), 256, 0, s>>>(pso, pp, L.b1, g->s_idx, g->o_idx, T, H, h1);
+        edge_combine_kernel<<<cdiv((int64_t)T * 32, 256), 256, 0, s>>>(pso, pp, b1, g->s_idx, g->o_idx, T, H, h1, floor_);
       }
       ECHO_LAUNCH_CHECK();
+      if (bs) bn_relu(h1, H, T, H, L.bn_g[0], L.bn_b[0]);
       // 3. second Linear of net1
       a = LinArgs();
-      a.X = h1; a.ldx = H; a.M = T; a.K = H; a.nout = 2 * H + dp; a.W = L.w2.w; a.bias = L.w2.b; a.act = 1; a.Y = t2;
+      a.X = h1; a.ldx = H; a.M = T; a.K = H; a.nout = 2 * H + dp; a.W = bs ? L.t2.w : L.w2.w; a.bias = bs ? L.t2.b : L.w2.b;
+      a.act = bs ? 0 : 1; a.Y = t2;
       a.ldy = 2 * H + dp;
       linear_auto(a, s);
+      if (bs) bn_relu(t2, 2 * H + dp, T, 2 * H + dp, L.bn_g[1], L.bn_b[1]);
     }
     // 4. deterministic segmented mean
     node_pool_kernel<<<N, 64, 0, s>>>(t2, 2 * H + dp, H, H + dp, g->node_off, g->node_items, N, pooled);
@@ -258,8 +333,10 @@ void Gcn::forward(const echo_graph* g, const float* obj, const float* pred, floa
     }
     // 5. net2 + residual
     a = LinArgs();
-    a.X = pooled; a.ldx = H; a.M = N; a.K = H; a.nout = H; a.W = L.w3.w; a.bias = L.w3.b; a.act = 1; a.Y = n1; a.ldy = H;
+    a.X = pooled; a.ldx = H; a.M = N; a.K = H; a.nout = H; a.W = bs ? L.t3.w : L.w3.w; a.bias = bs ? L.t3.b : L.w3.b; a.act = bs ? 0 : 1;
+    a.Y = n1; a.ldy = H;
     linear_auto(a, s);
+    if (bs) bn_relu(n1, H, N, H, L.bn_g[2], L.bn_b[2]);
     const float* resid = nullptr;
     if (L.residual) {
       a = LinArgs();
@@ -269,9 +346,16 @@ void Gcn::forward(const echo_graph* g, const float* obj, const float* pred, floa
       resid = proj;
     }
     a = LinArgs();
-    a.X = n1; a.ldx = H; a.M = N; a.K = H; a.nout = L.dout; a.W = L.w4.w; a.bias = L.w4.b; a.act = 1; a.res = resid;
-    a.ld_res = L.dout; a.Y = nobj; a.ldy = L.dout;
-    linear_auto(a, s);
+    if (bs) {   // Linear -> BatchNorm1d(batch) -> ReLU, then the residual projection on top (graph.py:203-206)
+      a.X = n1; a.ldx = H; a.M = N; a.K = H; a.nout = L.dout; a.W = L.t4.w; a.bias = L.t4.b; a.act = 0; a.Y = nobj; a.ldy = L.dout;
+      linear_auto(a, s);
+      bn_relu(nobj, L.dout, N, L.dout, L.bn_g[3], L.bn_b[3]);
+      if (resid) add_rowvec(nobj, F32, N, L.dout, resid, L.dout, 1, s);
+    } else {
+      a.X = n1; a.ldx = H; a.M = N; a.K = H; a.nout = L.dout; a.W = L.w4.w; a.bias = L.w4.b; a.act = 1; a.res = resid;
+      a.ld_res = L.dout; a.Y = nobj; a.ldy = L.dout;
+      linear_auto(a, s);
+    }
     cur_obj = nobj;
     cur_pred = npred;
   }

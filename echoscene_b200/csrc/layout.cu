@@ -784,7 +784,7 @@ echo_layout* layout_create(const echo_layout_desc_t* desc, const echo_weight_t* 
       }
       h->freqs = f;
     }
-    echo_gcn_desc_t gdsc;
+    echo_gcn_desc_t gdsc = {};
     gdsc.input_dim_obj = d.obj_embed_dim + gd + (d.enable_t_emb ? gd : 0);   // denoise_net.py:725-727
     gdsc.input_dim_pred = 2 * gd;
     gdsc.num_layers = 5;

@@ -74,6 +74,11 @@ struct GcnLayer {
   Mat proj;    // [dout, din] linear_projection
   Mat projp;   // [dp, dp]    linear_projection_pred
   bool residual = true;
+  // batch-statistics mode (echo_gcn_forward_train): the same four Linears UNFOLDED + their BatchNorm1d scale / shift
+  bool has_train = false;
+  Mat t_so, t_p, t2, t3, t4;          // raw weights, same row layout as the folded ones (t_so / t_p: no bias)
+  const float* t_b1 = nullptr;        // raw bias of net1.0
+  const float *bn_g[4] = {nullptr, nullptr, nullptr, nullptr}, *bn_b[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 struct Gcn {
@@ -83,7 +88,9 @@ struct Gcn {
   float *obj_pp[2] = {nullptr, nullptr}, *pred_pp[2] = {nullptr, nullptr};
   void create(const WeightMap& wm, const std::string& prefix, const echo_gcn_desc_t& d, DevPool& pool);
   // obj [N, din0], pred [T, dp] -> obj_out [N, dout_last], pred_out [T, dp] (either may alias internal buffers)
-  void forward(const echo_graph* g, const float* obj, const float* pred, float* obj_out, float* pred_out, cudaStream_t s);
+  void forward(const echo_graph* g, const float* obj, const float* pred, float* obj_out, float* pred_out, cudaStream_t s,
+               bool batch_stats = false);
+  float bn_eps = 1e-5f;
 };
 
 void linear_auto(const LinArgs& a, cudaStream_t s);

@@ -82,7 +82,7 @@ echo_scene* scene_create(const echo_scene_desc_t* desc, const echo_weight_t* wei
     h->obj_tab = table("obj_embeddings_ec.weight", d.num_objs);
     h->pred_tab = table("pred_embeddings_ec.weight", d.num_preds);
     if (d.manipulate_pred_dc) h->pred_tab_man = table("pred_embeddings_man_dc.weight", d.num_preds);   // EchoLayout.py:154
-    echo_gcn_desc_t g;
+    echo_gcn_desc_t g = {};
     g.input_dim_obj = h->feat; g.input_dim_pred = h->feat; g.num_layers = d.num_layers; g.hidden_dim = 4 * h->gd;
     g.output_dim = h->feat; g.max_nodes = h->d.max_nodes; g.max_triples = h->d.max_triples; g.bn_eps = eps;
     h->ec.create(wm, "gconv_net_ec.", g, h->pool);

@@ -592,7 +592,7 @@ echo_shape* shape_create(const echo_shape_desc_t* desc, const echo_weight_t* wei
       h->freqs = f;
     }
     // echo GCN (openai_model_3d.py:766-782)
-    echo_gcn_desc_t gdsc;
+    echo_gcn_desc_t gdsc = {};
     gdsc.input_dim_obj = ctx + gd + (d.enable_t_emb ? gd : 0);
     gdsc.input_dim_pred = 2 * gd;
     gdsc.num_layers = 5;

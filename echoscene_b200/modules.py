@@ -113,19 +113,24 @@ class GraphTripleConvNet(_SpecModule):
         self._build_from_specs(arch.gcn_specs(self.cfg))
         self.eval()
 
-    def _ensure(self, n_nodes: int, n_triples: int):
+    def _ensure(self, n_nodes: int, n_triples: int, train_weights: bool = False):
         ver = self._weights_version()
-        cap = self._handle_key[1] if self._handle_key else (0, 0)
-        if self._handle is not None and self._handle_key[0] == ver and n_nodes <= cap[0] and n_triples <= cap[1]:
+        cap = self._handle_key[1] if self._handle_key else (0, 0, False)
+        if (self._handle is not None and self._handle_key[0] == ver and n_nodes <= cap[0] and n_triples <= cap[1]
+                and (cap[2] or not train_weights)):
             return
         self._destroy_handle()
-        cap = (_next_pow2(n_nodes, 32), _next_pow2(n_triples, 128))
+        cap = (_next_pow2(n_nodes, 32), _next_pow2(n_triples, 128), bool(train_weights or cap[2]))
         d = _lib.GcnDesc(self.cfg.input_dim_obj, self.cfg.input_dim_pred, self.cfg.num_layers, self.cfg.hidden_dim,
-                         self.cfg.output_dim or 0, cap[0], cap[1], 1e-5)
-        arr, n, keep = _lib.weights_table(self.state_dict())
+                         self.cfg.output_dim or 0, cap[0], cap[1], 1e-5, int(cap[2]))
+        arr, n, keep = _lib.weights_table(self.state_dict_for_lib())
         h = C.c_void_p()
         _lib.check(_lib.lib().echo_gcn_create(C.byref(h), C.byref(d), arr, n))
         self._handle, self._handle_key = h, (ver, cap)
+
+    def state_dict_for_lib(self):
+        """the state_dict under the key names the library expects (gconvs.<i>.*); the single-layer subclass re-prefixes its keys"""
+        return self.state_dict()
 
     def _destroy_handle(self):
         if self._handle is not None:
@@ -135,19 +140,32 @@ class GraphTripleConvNet(_SpecModule):
     @torch.no_grad()
     def forward(self, obj_vecs, pred_vecs, edges):
         self._check_eval()
+        return self._run(obj_vecs, pred_vecs, edges, batch_stats=False)
+
+    @torch.no_grad()
+    def forward_batch_stats(self, obj_vecs, pred_vecs, edges):
+        """The forward the reference computes under ``model.train()`` (scripts/train_3dfront.py:237): every BatchNorm1d of the MLPs
+        normalises with the statistics of the batch (model/layers.py:29-30) -- triples for net1, nodes for net2.  Forward values only:
+        no autograd tape is recorded and the running statistics are not updated, which is why ``forward`` keeps refusing
+        ``train()`` mode instead of silently switching to this."""
+        if self.cfg.mlp_normalization != "batch":
+            return self._run(obj_vecs, pred_vecs, edges, batch_stats=False)
+        return self._run(obj_vecs, pred_vecs, edges, batch_stats=True)
+
+    def _run(self, obj_vecs, pred_vecs, edges, batch_stats: bool):
         _lib.require_cuda(obj_vecs, pred_vecs, edges)
         obj_vecs = obj_vecs.float().contiguous()
         pred_vecs = pred_vecs.float().contiguous()
         n, t = obj_vecs.shape[0], pred_vecs.shape[0]
         assert obj_vecs.shape[1] == self.cfg.input_dim_obj and pred_vecs.shape[1] == self.cfg.input_dim_pred
         assert edges.shape == (t, 2)
-        self._ensure(n, t)
+        self._ensure(n, t, train_weights=batch_stats)
         g = _lib.graph_for_edges(edges, n) if not hasattr(edges, "_echo_graph") else edges._echo_graph
         dout = self.cfg.output_dim or self.cfg.input_dim_obj
         obj_out = torch.empty(n, dout, device=obj_vecs.device)
         pred_out = torch.empty(t, self.cfg.input_dim_pred, device=obj_vecs.device)
-        _lib.check(_lib.lib().echo_gcn_forward(self._handle, g.h, _lib.ptr(obj_vecs), _lib.ptr(pred_vecs),
-                                               _lib.ptr(obj_out), _lib.ptr(pred_out), _lib.stream_ptr()))
+        fn = _lib.lib().echo_gcn_forward_train if batch_stats else _lib.lib().echo_gcn_forward
+        _lib.check(fn(self._handle, g.h, _lib.ptr(obj_vecs), _lib.ptr(pred_vecs), _lib.ptr(obj_out), _lib.ptr(pred_out), _lib.stream_ptr()))
         return obj_out, pred_out
 
 
@@ -174,19 +192,6 @@ class GraphTripleConv(GraphTripleConvNet):
     def state_dict_for_lib(self):
         return {"gconvs.0." + k: v for k, v in self.state_dict().items()}
 
-    def _ensure(self, n_nodes, n_triples):
-        ver = self._weights_version()
-        cap = self._handle_key[1] if self._handle_key else (0, 0)
-        if self._handle is not None and self._handle_key[0] == ver and n_nodes <= cap[0] and n_triples <= cap[1]:
-            return
-        self._destroy_handle()
-        cap = (_next_pow2(n_nodes, 32), _next_pow2(n_triples, 128))
-        d = _lib.GcnDesc(self.cfg.input_dim_obj, self.cfg.input_dim_pred, 1, self.cfg.hidden_dim, self.output_dim,
-                         cap[0], cap[1], 1e-5)
-        arr, n, keep = _lib.weights_table(self.state_dict_for_lib())
-        h = C.c_void_p()
-        _lib.check(_lib.lib().echo_gcn_create(C.byref(h), C.byref(d), arr, n))
-        self._handle, self._handle_key = h, (ver, cap)
 
 
 # ----------------------------------------------------------------------------------------------------------------------

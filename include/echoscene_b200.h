@@ -69,6 +69,7 @@ typedef struct echo_gcn_desc {
   int32_t output_dim;   /* <= 0: same as input_dim_obj for every layer */
   int32_t max_nodes, max_triples;
   float bn_eps;         /* 1e-5, model/layers.py:29-30 */
+  int32_t keep_train_weights;   /* != 0: also keep the unfolded Linear / BatchNorm1d tensors, for echo_gcn_forward_train */
 } echo_gcn_desc_t;
 
 /* UNet1DModel(**denoiser_kwargs) — config/full_mp.yaml:24-39, denoise_net.py:451-756 */
@@ -166,6 +167,12 @@ ECHO_API int echo_gather_rows(const float* obj_vecs, const int64_t* idx, int64_t
 ECHO_API int echo_gcn_create(echo_gcn_t** out, const echo_gcn_desc_t* desc, const echo_weight_t* weights, int32_t n_weights);
 ECHO_API int echo_gcn_forward(echo_gcn_t* h, const echo_graph_t* g, const float* obj_vecs, const float* pred_vecs,
                      float* obj_out, float* pred_out, void* stream);
+/* The same forward as the reference computes it under model.train() (scripts/train_3dfront.py:237): every BatchNorm1d of the
+ * build_mlp stacks (model/layers.py:21-38) normalises with the statistics of the batch -- the rows of the call: triples for
+ * net1, nodes for net2 -- (biased variance), not with its running statistics.  Forward only: no autograd tape, running
+ * statistics are not updated.  Needs echo_gcn_desc_t.keep_train_weights. */
+ECHO_API int echo_gcn_forward_train(echo_gcn_t* h, const echo_graph_t* g, const float* obj_vecs, const float* pred_vecs,
+                           float* obj_out, float* pred_out, void* stream);
 ECHO_API void echo_gcn_destroy(echo_gcn_t* h);
 
 /* ---- layout branch.

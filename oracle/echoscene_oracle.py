@@ -41,7 +41,13 @@ def _bn_eval(sd: SD, p: str, x: Tensor, eps: float = 1e-5) -> Tensor:
                         sd[p + ".bias"], False, 0.0, eps)
 
 
-def gcn_mlp(sd: SD, p: str, x: Tensor, n_layers: int = 2) -> Tensor:
+def _bn_batch(sd: SD, p: str, x: Tensor, eps: float = 1e-5) -> Tensor:
+    """BatchNorm1d under model.train(): the statistics of the batch (biased variance), model/layers.py:29-30.  The running
+    statistics' update is a side effect the forward value does not depend on."""
+    return F.batch_norm(x, None, None, sd[p + ".weight"], sd[p + ".bias"], True, 0.0, eps)
+
+
+def gcn_mlp(sd: SD, p: str, x: Tensor, n_layers: int = 2, batch_stats: bool = False) -> Tensor:
     """build_mlp(..., batch_norm='batch', final_nonlinearity=True): (Linear, BN, ReLU) x n.
     model/layers.py:21-38; index layout 0,1,2 / 3,4,5."""
     has_bn = (p + ".1.running_mean") in sd
@@ -49,12 +55,12 @@ def gcn_mlp(sd: SD, p: str, x: Tensor, n_layers: int = 2) -> Tensor:
     for i in range(n_layers):
         x = _linear(sd, f"{p}.{i * step}", x)
         if has_bn:
-            x = _bn_eval(sd, f"{p}.{i * step + 1}", x)
+            x = (_bn_batch if batch_stats else _bn_eval)(sd, f"{p}.{i * step + 1}", x)
         x = F.relu(x)
     return x
 
 
-def graph_triple_conv(sd: SD, p: str, obj_vecs: Tensor, pred_vecs: Tensor, edges: Tensor
+def graph_triple_conv(sd: SD, p: str, obj_vecs: Tensor, pred_vecs: Tensor, edges: Tensor, batch_stats: bool = False
                       ) -> Tuple[Tensor, Tensor]:
     """GraphTripleConv.forward with pooling='avg', residual=True.  model/graph.py:124-211."""
     n_obj, n_tri = obj_vecs.shape[0], pred_vecs.shape[0]
@@ -64,7 +70,7 @@ def graph_triple_conv(sd: SD, p: str, obj_vecs: Tensor, pred_vecs: Tensor, edges
     cur_s = obj_vecs[s_idx]                                     # graph.py:146
     cur_o = obj_vecs[o_idx]                                     # graph.py:147
     cur_t = torch.cat([cur_s, pred_vecs, cur_o], dim=1)         # graph.py:151
-    new_t = gcn_mlp(sd, p + "net1", cur_t)                      # graph.py:152
+    new_t = gcn_mlp(sd, p + "net1", cur_t, batch_stats=batch_stats)   # graph.py:152
     hid = (new_t.shape[1] - dp) // 2
     new_s, new_p, new_o = new_t[:, :hid], new_t[:, hid:hid + dp], new_t[:, hid + dp:]   # :156-158
     pooled = torch.zeros(n_obj, hid, dtype=obj_vecs.dtype, device=obj_vecs.device)
@@ -74,7 +80,7 @@ def graph_triple_conv(sd: SD, p: str, obj_vecs: Tensor, pred_vecs: Tensor, edges
     ones = torch.ones(n_tri, dtype=obj_vecs.dtype, device=obj_vecs.device)
     counts = counts.index_add(0, s_idx, ones).index_add(0, o_idx, ones)    # :191-192
     pooled = pooled / counts.clamp(min=1).view(-1, 1)           # :198-199
-    new_obj = gcn_mlp(sd, p + "net2", pooled)                   # :203
+    new_obj = gcn_mlp(sd, p + "net2", pooled, batch_stats=batch_stats)   # :203
     if (p + "linear_projection.weight") in sd:                  # residual, :205-209
         new_obj = new_obj + _linear(sd, p + "linear_projection", obj_vecs)
         new_p = new_p + _linear(sd, p + "linear_projection_pred", pred_vecs)
@@ -82,10 +88,10 @@ def graph_triple_conv(sd: SD, p: str, obj_vecs: Tensor, pred_vecs: Tensor, edges
 
 
 def graph_triple_conv_net(sd: SD, p: str, obj_vecs: Tensor, pred_vecs: Tensor, edges: Tensor,
-                          num_layers: int = 5) -> Tuple[Tensor, Tensor]:
-    """GraphTripleConvNet.forward.  model/graph.py:246-250."""
+                          num_layers: int = 5, batch_stats: bool = False) -> Tuple[Tensor, Tensor]:
+    """GraphTripleConvNet.forward.  model/graph.py:246-250.  batch_stats: as under model.train() (BatchNorm1d on batch statistics)."""
     for i in range(num_layers):
-        obj_vecs, pred_vecs = graph_triple_conv(sd, f"{p}gconvs.{i}.", obj_vecs, pred_vecs, edges)
+        obj_vecs, pred_vecs = graph_triple_conv(sd, f"{p}gconvs.{i}.", obj_vecs, pred_vecs, edges, batch_stats)
     return obj_vecs, pred_vecs
 
 

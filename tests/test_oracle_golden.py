@@ -128,3 +128,18 @@ def test_vqvae_encode_oracle_vs_reference():
     G = gold("vqvae_encode.pt")
     assert z.shape == (1, 3, 16, 16, 16) == G["z"].shape
     assert max(rel_err(z, G["z"])) < TOL
+
+
+def test_gcn_batch_statistics_oracle_matches_the_reference_in_train_mode():
+    """oracle.graph_triple_conv_net(batch_stats=True) against the reference's GraphTripleConvNet under .train()
+    (tests/golden/gcn_train.pt, oracle/gen_golden_train.py)."""
+    from oracle import gen_golden_train as gt
+    G = gold("gcn_train.pt")
+    gcfg = cases.layout_cfg().gcn()
+    sd = arch.make_state_dict(arch.gcn_specs(gcfg), cases.WEIGHT_SEED_GCN)
+    for name, n, t, seed in gt.TRAIN_CASES:
+        g, obj, pred = gt.inputs(n, t, seed, gcfg)
+        edges, _ = orc.edges_of(g.triples)
+        with torch.no_grad():
+            o_obj, o_pred = orc.graph_triple_conv_net(sd, "", obj, pred, edges, batch_stats=True)
+        assert torch.equal(o_obj, G[name]["obj"]) and torch.equal(o_pred, G[name]["pred"]), name

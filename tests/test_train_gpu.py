@@ -103,3 +103,30 @@ def test_fused_optimizer_refuses_cpu_and_missing_gradients():
     p = torch.nn.Parameter(torch.zeros(4, device=DEV))
     with pytest.raises(EchoError, match="gradient"):
         train.FusedAdamW([p]).step()
+
+
+def test_gcn_forward_on_batch_statistics_matches_the_reference_in_train_mode():
+    """echo_gcn_forward_train (BatchNorm1d on the statistics of the batch, model/layers.py:29-30 under model.train()) against the
+    reference's GraphTripleConvNet in .train() mode: a single scene (few-row kernels) and a collated batch (tiled GEMM path)."""
+    from echoscene_b200 import arch, modules
+    from echoscene_b200._lib import EchoError
+    from oracle import cases, echoscene_oracle as orc, gen_golden_train as gt
+    from util import FP32_TOL, gold
+    G = gold("gcn_train.pt")
+    gcfg = cases.layout_cfg().gcn()
+    sd = arch.make_state_dict(arch.gcn_specs(gcfg), cases.WEIGHT_SEED_GCN)
+    m = modules.GraphTripleConvNet(gcfg.input_dim_obj, gcfg.input_dim_pred, num_layers=gcfg.num_layers, hidden_dim=gcfg.hidden_dim,
+                                   residual=True, pooling="avg", mlp_normalization="batch", output_dim=gcfg.output_dim)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV)
+    for name, n, t, seed in gt.TRAIN_CASES:
+        g, obj, pred = gt.inputs(n, t, seed, gcfg)
+        edges, _ = orc.edges_of(g.triples)
+        o, p = m.forward_batch_stats(obj.to(DEV), pred.to(DEV), edges.to(DEV))
+        assert_close(o, G[name]["obj"], FP32_TOL, f"train-mode GCN {name}: nodes")
+        assert_close(p, G[name]["pred"], FP32_TOL, f"train-mode GCN {name}: predicates")
+        e, _ = m(obj.to(DEV), pred.to(DEV), edges.to(DEV))                       # the eval forward still works on the same handle
+        assert float((e.cpu() - G[name]["obj"]).abs().max()) > 1e-2
+    m.train()
+    with pytest.raises(EchoError):                                              # forward() keeps refusing train(): no autograd tape
+        m(obj.to(DEV), pred.to(DEV), edges.to(DEV))
