@@ -55,7 +55,7 @@ class LayoutDesc(C.Structure):
                 ("num_heads", C.c_int32), ("context_dim", C.c_int32), ("obj_embed_dim", C.c_int32),
                 ("gconv_dim", C.c_int32), ("enable_t_emb", C.c_int32), ("max_nodes", C.c_int32),
                 ("max_triples", C.c_int32), ("precision", C.c_int32), ("time_num", C.c_int32),
-                ("beta_start", C.c_float), ("beta_end", C.c_float)]
+                ("beta_start", C.c_float), ("beta_end", C.c_float), ("keep_train_weights", C.c_int32)]
 
 
 class ShapeDesc(C.Structure):
@@ -66,14 +66,14 @@ class ShapeDesc(C.Structure):
                 ("enable_t_emb", C.c_int32), ("latent_size", C.c_int32), ("max_nodes", C.c_int32),
                 ("max_triples", C.c_int32), ("max_local_nodes", C.c_int32), ("precision", C.c_int32),
                 ("timesteps", C.c_int32), ("ddim_steps", C.c_int32), ("linear_start", C.c_float),
-                ("linear_end", C.c_float)]
+                ("linear_end", C.c_float), ("keep_train_weights", C.c_int32)]
 
 
 class SceneDesc(C.Structure):
     _fields_ = [("gconv_dim", C.c_int32), ("add_dim", C.c_int32), ("num_objs", C.c_int32), ("num_preds", C.c_int32),
                 ("num_layers", C.c_int32), ("rel_s_hidden", C.c_int32), ("context_dim", C.c_int32),
                 ("max_nodes", C.c_int32), ("max_triples", C.c_int32), ("bn_eps", C.c_float),
-                ("manipulate_pred_dc", C.c_int32)]
+                ("manipulate_pred_dc", C.c_int32), ("keep_train_weights", C.c_int32)]
 
 
 class VqvaeDesc(C.Structure):
@@ -110,6 +110,9 @@ PROTOTYPES = {
     "echo_gcn_create": (C.c_int, [C.POINTER(_P), C.POINTER(GcnDesc), C.POINTER(Weight), _I]),
     "echo_gcn_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "echo_gcn_forward_train": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "echo_layout_set_batch_stats": (C.c_int, [_P, _I]),
+    "echo_shape_set_batch_stats": (C.c_int, [_P, _I]),
+    "echo_scene_set_batch_stats": (C.c_int, [_P, _I]),
     "echo_gcn_destroy": (None, [_P]),
     "echo_layout_create": (C.c_int, [C.POINTER(_P), C.POINTER(LayoutDesc), C.POINTER(Weight), _I]),
     "echo_layout_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),

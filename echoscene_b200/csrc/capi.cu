@@ -25,6 +25,9 @@ echo_shape* shape_create(const echo_shape_desc_t*, const echo_weight_t*, int);
 void shape_destroy(echo_shape*);
 void shape_forward(echo_shape*, const echo_graph*, const float*, const float*, const int64_t*, float*, cudaStream_t);
 void shape_set_index(echo_shape*, int, cudaStream_t);
+void shape_set_batch_stats(echo_shape*, bool);
+void layout_set_batch_stats(echo_layout*, bool);
+void scene_set_batch_stats(echo_scene*, bool);
 echo_optimizer* optimizer_create(const echo_opt_tensor_t*, int);
 void optimizer_destroy(echo_optimizer*);
 void optimizer_step(echo_optimizer*, int64_t, double, double, double, double, double, double, cudaStream_t);
@@ -422,6 +425,15 @@ int echo_metrics_validate_constraints(const int64_t* triples, int64_t n_triples,
     validate_constraints(triples, n_triples, boxes, n_nodes, box_dim, keep, changes_mode != 0, d_rel, n_preds, strict != 0, overlap_threshold,
                          out_rel, out_ok, (cudaStream_t)stream);
   });
+}
+int echo_layout_set_batch_stats(echo_layout_t* h, int32_t on) {
+  return guard([&] { layout_set_batch_stats(h, on != 0); });
+}
+int echo_shape_set_batch_stats(echo_shape_t* h, int32_t on) {
+  return guard([&] { shape_set_batch_stats(h, on != 0); });
+}
+int echo_scene_set_batch_stats(echo_scene_t* h, int32_t on) {
+  return guard([&] { scene_set_batch_stats(h, on != 0); });
 }
 int echo_shape_set_index(echo_shape_t* h, int32_t ddim_index, void* stream) {
   return guard([&] {

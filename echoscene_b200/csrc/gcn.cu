@@ -159,6 +159,12 @@ Mat plain_linear(const WeightMap& wm, const std::string& lin, int nout, int K, D
   return m;
 }
 
+void bn_rows_train(float* x, int64_t ld, int rows, int C, const float* gamma, const float* beta, float eps, cudaStream_t s) {
+  if (rows == 0 || C == 0) return;
+  bn_rows_train_kernel<<<cdiv(C, 32), dim3(32, 8), 0, s>>>(x, ld, rows, C, gamma, beta, eps);
+  ECHO_LAUNCH_CHECK();
+}
+
 // Few-row kernel up to 64 rows, tiled SIMT GEMM above (batched scene graphs: hundreds of nodes / thousands of edges).
 void linear_auto(const LinArgs& a, cudaStream_t s) {
   if (a.M <= 64 || a.in_act != 0 || a.act == 2 || a.pro != PRO_NONE || a.X2 || a.res2) {
@@ -275,11 +281,7 @@ void Gcn::forward(const echo_graph* g, const float* obj, const float* pred, floa
     for (auto& L : layers)
       ECHO_CHECK(L.has_train, "gcn: batch-statistics forward needs a handle created with keep_train_weights (and BatchNorm1d MLPs)");
   // BatchNorm1d over the rows of the call + ReLU, in place (batch-statistics mode only)
-  auto bn_relu = [&](float* x, int64_t ld, int rows, int C, const float* gm, const float* bt) {
-    if (rows == 0) return;
-    bn_rows_train_kernel<<<cdiv(C, 32), dim3(32, 8), 0, s>>>(x, ld, rows, C, gm, bt, bn_eps);
-    ECHO_LAUNCH_CHECK();
-  };
+  auto bn_relu = [&](float* x, int64_t ld, int rows, int C, const float* gm, const float* bt) { bn_rows_train(x, ld, rows, C, gm, bt, bn_eps, s); };
   ECHO_CHECK(N <= max_nodes && T <= max_triples, "gcn: graph (%d nodes, %d triples) exceeds handle capacity (%d, %d)", N, T,
              max_nodes, max_triples);
   const float* cur_obj = obj;

@@ -24,6 +24,7 @@ struct echo_layout {
   Gcn gcn;
   Arena arena;
   int prec = ECHO_PREC_FP32;
+  bool batch_stats = false;   // box_graph_cov normalises with the statistics of the batch (model.train() forward values)
   ConvW box_emb, time_emb_lin;
   const float* pred_table = nullptr;
   int pred_rows = 0;   // rows of pred_embeddings (16)
@@ -209,7 +210,7 @@ struct echo_layout {
     lin(emb_act, E, plan.emb_stack, embout, plan.emb_total, nullptr, 0, 0, 0, q);
     if (fork) ECHO_CUDA(cudaEventRecord(ev_join, side));
     if (T > 0) embedding_rows(pred_table, 2 * gd, g->triples, 3, 1, T, pred, 2 * gd, s);
-    gcn.forward(g, node, pred, latent, nullptr, s);
+    gcn.forward(g, node, pred, latent, nullptr, s, batch_stats);
     if (fork) ECHO_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
     lin(latent, d.context_dim, attn2_fused, a2vec, a2_total, nullptr, 0, 0, 0, s);   // all 11 attn2 vectors at once
     std::vector<std::pair<const float*, int>> hs;
@@ -793,6 +794,7 @@ echo_layout* layout_create(const echo_layout_desc_t* desc, const echo_weight_t* 
     gdsc.max_nodes = d.max_nodes;
     gdsc.max_triples = d.max_triples > 0 ? d.max_triples : 1;
     gdsc.bn_eps = 1e-5f;
+    gdsc.keep_train_weights = d.keep_train_weights;
     h->gcn.create(wm, "box_graph_cov.", gdsc, h->pool);
     make_ddpm_tables(h);
     const size_t N = d.max_nodes, T = gdsc.max_triples;
@@ -975,6 +977,12 @@ __global__ void layout_copy_out_kernel(const float* __restrict__ src, float* __r
 }
 }  // namespace
 
+void layout_set_batch_stats(echo_layout* h, bool on) {
+  ECHO_CHECK(h, "layout_set_batch_stats: null handle");
+  ECHO_CHECK(!on || h->d.keep_train_weights, "layout_set_batch_stats: the handle was created without keep_train_weights");
+  h->batch_stats = on;
+}
+
 int g_layout_mode = 0;   // echo_debug_set_layout_mode: 0 = automatic, 1 = never the persistent executor (per-layer kernels / graph replay)
 void set_layout_mode(int m) { g_layout_mode = m; }
 // {persistent-executor steps, graph replays, program stages, program ops, kernels inside the replayed graph, executor CTAs;
@@ -990,6 +998,7 @@ void layout_step(echo_layout* h, const echo_graph* g, const float* x_t, const fl
                  cudaStream_t s) {
   ECHO_CHECK(t >= 0 && t < h->d.time_num, "layout_step: t=%d outside [0, %d)", t, h->d.time_num);
   ECHO_CHECK(g, "layout_step: null graph");
+  ECHO_CHECK(!h->batch_stats, "layout_step: the sampler step runs on running statistics; switch echo_layout_set_batch_stats off first");
   const int N = g->n_nodes, nx = N * h->d.out_channels, nobj = N * h->d.obj_embed_dim;
   if (N == 0) return;
   ECHO_CHECK(N <= h->d.max_nodes && h->d.in_channels == h->d.out_channels, "layout_step: graph exceeds handle capacity");

@@ -94,6 +94,8 @@ struct Gcn {
 };
 
 void linear_auto(const LinArgs& a, cudaStream_t s);
+// BatchNorm1d on the statistics of the `rows` rows of x (biased variance) + ReLU, in place (gcn.cu)
+void bn_rows_train(float* x, int64_t ld, int rows, int C, const float* gamma, const float* beta, float eps, cudaStream_t s);
 // Linear (+ eval BatchNorm1d folded in when `bn`.running_mean exists) / plain Linear copied into the handle's pool (gcn.cu)
 Mat folded_linear(const WeightMap& wm, const std::string& lin, const std::string& bn, int nout, int K, float eps, DevPool& pool,
                   cudaStream_t s);

@@ -26,6 +26,10 @@ struct echo_scene {
   const float* pred_tab_man = nullptr;   // pred_embeddings_man_dc when desc.manipulate_pred_dc (layout-only model), else null
   bool has_rel_s = false;
   echo::Mat rel0, rel3;          // rel_s_mlp.0 (+ BatchNorm rel_s_mlp.1 folded), rel_s_mlp.3
+  echo::Mat rel0_raw;            // batch-statistics mode: rel_s_mlp.0 unfolded + BatchNorm1d scale / shift
+  const float *rel_bn_g = nullptr, *rel_bn_b = nullptr;
+  bool has_train = false, batch_stats = false;
+  float bn_eps = 1e-5f;
   // workspace (max_nodes / max_triples rows)
   float *obj_embed = nullptr, *pred_embed = nullptr, *latent_obj = nullptr, *mani_in = nullptr, *latent = nullptr, *rel_h = nullptr;
   float* pred_embed_man = nullptr;       // predicate embeddings of the manipulate stage when they come from pred_tab_man
@@ -85,6 +89,8 @@ echo_scene* scene_create(const echo_scene_desc_t* desc, const echo_weight_t* wei
     echo_gcn_desc_t g = {};
     g.input_dim_obj = h->feat; g.input_dim_pred = h->feat; g.num_layers = d.num_layers; g.hidden_dim = 4 * h->gd;
     g.output_dim = h->feat; g.max_nodes = h->d.max_nodes; g.max_triples = h->d.max_triples; g.bn_eps = eps;
+    g.keep_train_weights = d.keep_train_weights;
+    h->bn_eps = eps;
     h->ec.create(wm, "gconv_net_ec.", g, h->pool);
     g.input_dim_obj = h->din_mani;
     g.num_layers = std::min(d.num_layers, 5);        // EchoScene.py:84
@@ -95,7 +101,19 @@ echo_scene* scene_create(const echo_scene_desc_t* desc, const echo_weight_t* wei
       h->rel0 = folded_linear(wm, "rel_s_mlp.0", "rel_s_mlp.1", d.rel_s_hidden, h->feat, eps, h->pool, s);
       h->rel3 = plain_linear(wm, "rel_s_mlp.3", d.context_dim, d.rel_s_hidden, h->pool, s);
       h->rel_h = h->pool.alloc_n<float>((size_t)h->d.max_nodes * d.rel_s_hidden);
+      if (d.keep_train_weights && wm.has("rel_s_mlp.1.running_mean")) {
+        h->rel0_raw = plain_linear(wm, "rel_s_mlp.0", d.rel_s_hidden, h->feat, h->pool, s);
+        auto vec = [&](const char* name) {
+          const WView& v = wm.get(name, {d.rel_s_hidden});
+          float* o = h->pool.alloc_n<float>(d.rel_s_hidden);
+          ECHO_CUDA(cudaMemcpyAsync(o, v.p, sizeof(float) * d.rel_s_hidden, cudaMemcpyDeviceToDevice, s));
+          return (const float*)o;
+        };
+        h->rel_bn_g = vec("rel_s_mlp.1.weight");
+        h->rel_bn_b = vec("rel_s_mlp.1.bias");
+      }
     }
+    h->has_train = d.keep_train_weights != 0;
     const size_t N = h->d.max_nodes, T = h->d.max_triples;
     h->obj_embed = h->pool.alloc_n<float>(N * h->feat);
     h->pred_embed = h->pool.alloc_n<float>(T * h->feat);
@@ -129,7 +147,7 @@ void scene_init_encoder(echo_scene* h, const echo_graph* g, const int64_t* objs,
   float* lo = latent_obj_out ? latent_obj_out : h->latent_obj;
   embed_rows(h, h->obj_tab, objs, 1, 0, text_feat, N, oe, s);
   embed_rows(h, h->pred_tab, g->triples, 3, 1, rel_feat, T, pe, s);
-  h->ec.forward(g, oe, pe, lo, nullptr, s);
+  h->ec.forward(g, oe, pe, lo, nullptr, s, h->batch_stats);
 }
 
 // manipulate (EchoScene.py:181-195): latent_f (N, feat + gd) = [latent | change flag].
@@ -146,7 +164,7 @@ void scene_manipulate(echo_scene* h, const echo_graph* g, const float* latent_f,
   const int lf = h->feat + h->gd;
   copy_cols(latent_f, lf, N, lf, h->mani_in, h->din_mani, s);                  // torch.cat([latent_f, obj_embed], dim=1), :192
   copy_cols(oe, h->feat, N, h->feat, h->mani_in + lf, h->din_mani, s);
-  h->mani.forward(g, h->mani_in, pe, lt, nullptr, s);
+  h->mani.forward(g, h->mani_in, pe, lt, nullptr, s, h->batch_stats);
 }
 
 // rel_s_mlp (EchoScene.py:97-100): x (rows, feat) -> out (rows, context_dim)
@@ -157,9 +175,12 @@ void scene_rel_s(echo_scene* h, const float* x, int rows, float* out, cudaStream
   if (rows == 0) return;
   ECHO_CHECK(x && out, "scene_rel_s: null argument");
   LinArgs a;
-  a.X = x; a.ldx = h->feat; a.M = rows; a.K = h->feat; a.nout = h->rel0.nout; a.W = h->rel0.w; a.bias = h->rel0.b; a.act = 1;
+  const bool bs = h->batch_stats && h->rel_bn_g;   // Linear -> BatchNorm1d on the statistics of these rows -> ReLU
+  a.X = x; a.ldx = h->feat; a.M = rows; a.K = h->feat; a.nout = h->rel0.nout; a.W = bs ? h->rel0_raw.w : h->rel0.w;
+  a.bias = bs ? h->rel0_raw.b : h->rel0.b; a.act = bs ? 0 : 1;
   a.Y = h->rel_h; a.ldy = h->rel0.nout;
   linear_auto(a, s);
+  if (bs) bn_rows_train(h->rel_h, h->rel0.nout, rows, h->rel0.nout, h->rel_bn_g, h->rel_bn_b, h->bn_eps, s);
   a = LinArgs();
   a.X = h->rel_h; a.ldx = h->rel0.nout; a.M = rows; a.K = h->rel0.nout; a.nout = h->rel3.nout; a.W = h->rel3.w; a.bias = h->rel3.b;
   a.Y = out; a.ldy = h->rel3.nout;
@@ -178,7 +199,7 @@ void scene_encode(echo_scene* h, const echo_graph* g, const int64_t* objs, const
   // predicate table of the layout-only model, below)
   embed_rows(h, h->obj_tab, objs, 1, 0, text_feat, N, oe, s);
   embed_rows(h, h->pred_tab, g->triples, 3, 1, rel_feat, T, h->pred_embed, s);
-  h->ec.forward(g, oe, h->pred_embed, h->latent_obj, nullptr, s);
+  h->ec.forward(g, oe, h->pred_embed, h->latent_obj, nullptr, s, h->batch_stats);
   if (change) copy_cols(change, h->gd, N, h->gd, h->mani_in + h->feat, h->din_mani, s);
   else ECHO_CUDA(cudaMemsetAsync(h->mani_in, 0, sizeof(float) * (size_t)N * h->din_mani, s));   // the zero change flag, :393-397
   copy_cols(h->latent_obj, h->feat, N, h->feat, h->mani_in, h->din_mani, s);
@@ -188,9 +209,15 @@ void scene_encode(echo_scene* h, const echo_graph* g, const int64_t* objs, const
     embed_rows(h, h->pred_tab_man, g->triples, 3, 1, rel_feat, T, h->pred_embed_man, s);
     pe_man = h->pred_embed_man;
   }
-  h->mani.forward(g, h->mani_in, pe_man, lt, nullptr, s);
+  h->mani.forward(g, h->mani_in, pe_man, lt, nullptr, s, h->batch_stats);
   if (uc_s_out) scene_rel_s(h, oe, N, uc_s_out, s);
   if (c_s_out) scene_rel_s(h, lt, N, c_s_out, s);
+}
+
+void scene_set_batch_stats(echo_scene* h, bool on) {
+  ECHO_CHECK(h, "scene_set_batch_stats: null handle");
+  ECHO_CHECK(!on || h->has_train, "scene_set_batch_stats: the handle was created without keep_train_weights");
+  h->batch_stats = on;
 }
 
 }  // namespace echo

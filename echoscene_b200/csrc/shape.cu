@@ -31,6 +31,7 @@ struct echo_shape {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_codes = nullptr;
   bool dry = false;
   int prec = ECHO_PREC_FP32;
+  bool batch_stats = false;   // shape_code_graph_cov normalises with the statistics of the batch (model.train() forward values)
   DT adt = F32;   // trunk activation dtype
   // prepared small weights
   ConvW se_conv0, se_conv2, se_lin, time_emb_lin;
@@ -319,7 +320,7 @@ struct echo_shape {
     if (d.enable_t_emb) lin(emb, E, N, time_emb_lin, node + ctx + gd, nd, 0, 0, q);
     if (!dry) {
       if (T > 0) embedding_rows(pred_table, 2 * gd, g->triples, 3, 1, T, pred, 2 * gd, q);
-      gcn.forward(g, node, pred, latent, nullptr, q);
+      gcn.forward(g, node, pred, latent, nullptr, q, batch_stats);
     }
     const float* lat_loc = latent + (size_t)obj_begin * ctx;
     {
@@ -601,6 +602,7 @@ echo_shape* shape_create(const echo_shape_desc_t* desc, const echo_weight_t* wei
     gdsc.max_nodes = d.max_nodes;
     gdsc.max_triples = d.max_triples > 0 ? d.max_triples : 1;
     gdsc.bn_eps = 1e-5f;
+    gdsc.keep_train_weights = d.keep_train_weights;
     h->gcn.create(wm, "shape_code_graph_cov.", gdsc, h->pool);
     make_ddim_schedule(h);
 
@@ -700,8 +702,15 @@ void shape_set_index(echo_shape* h, int ddim_index, cudaStream_t s) {
 void shape_step(echo_shape* h, const echo_graph* g, const float* x, const float* uc, int ddim_index, float* x_prev, cudaStream_t s) {
   ECHO_CHECK(g && (ddim_index == ECHO_INDEX_FROM_DEVICE || (ddim_index >= 0 && ddim_index < (int)h->h_ts.size())), "shape_step: bad ddim_index %d",
              ddim_index);
+  ECHO_CHECK(!h->batch_stats, "shape_step: the sampler step runs on running statistics; switch echo_shape_set_batch_stats off first");
   fill_step_timesteps(h, g->n_nodes, ddim_index, s);
   h->run(g, x, 0, g->n_nodes, nullptr, uc, h->t_dev, ddim_index, x_prev, s);
+}
+
+void shape_set_batch_stats(echo_shape* h, bool on) {
+  ECHO_CHECK(h, "shape_set_batch_stats: null handle");
+  ECHO_CHECK(!on || h->d.keep_train_weights, "shape_set_batch_stats: the handle was created without keep_train_weights");
+  h->batch_stats = on;
 }
 
 void shape_embed(echo_shape* h, const float* x_local, int n_local, float* codes_out, cudaStream_t s) {

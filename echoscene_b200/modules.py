@@ -80,8 +80,17 @@ class _SpecModule(nn.Module):
 
     def _check_eval(self):
         if self.training:
-            raise EchoError(f"{type(self).__name__}: only eval() mode is implemented on the B200 path "
+            raise EchoError(f"{type(self).__name__}: this call is a sampler step and runs under eval() only "
                             "(the reference samples under model.eval(), scripts/eval_3dfront.py:395)")
+
+    _set_batch_stats_fn = None   # name of the library's echo_*_set_batch_stats for this handle type
+
+    def _apply_mode(self):
+        """model.train(): the BatchNorm1d layers of the GCN MLPs (and rel_s_mlp) normalise with the statistics of the batch
+        (model/layers.py:29-30) -- forward VALUES of the reference's training forward; nothing is recorded for a backward pass and
+        running statistics are not updated.  Called after _ensure()."""
+        fn = getattr(_lib.lib(), self._set_batch_stats_fn)
+        _lib.check(fn(self._handle, int(bool(self.training))))
 
     def _destroy_handle(self):
         raise NotImplementedError
@@ -139,15 +148,16 @@ class GraphTripleConvNet(_SpecModule):
 
     @torch.no_grad()
     def forward(self, obj_vecs, pred_vecs, edges):
-        self._check_eval()
+        """eval(): running statistics (folded into the Linears).  train(): ``forward_batch_stats``."""
+        if self.training:
+            return self.forward_batch_stats(obj_vecs, pred_vecs, edges)
         return self._run(obj_vecs, pred_vecs, edges, batch_stats=False)
 
     @torch.no_grad()
     def forward_batch_stats(self, obj_vecs, pred_vecs, edges):
         """The forward the reference computes under ``model.train()`` (scripts/train_3dfront.py:237): every BatchNorm1d of the MLPs
         normalises with the statistics of the batch (model/layers.py:29-30) -- triples for net1, nodes for net2.  Forward values only:
-        no autograd tape is recorded and the running statistics are not updated, which is why ``forward`` keeps refusing
-        ``train()`` mode instead of silently switching to this."""
+        no autograd tape is recorded and the running statistics are not updated."""
         if self.cfg.mlp_normalization != "batch":
             return self._run(obj_vecs, pred_vecs, edges, batch_stats=False)
         return self._run(obj_vecs, pred_vecs, edges, batch_stats=True)
@@ -258,20 +268,24 @@ class SceneEncoder(_SpecModule):
         return pre if self.with_rel_s else tuple(p for p in pre if p != "rel_s_mlp.")
 
     # ---- handle ----
+    _set_batch_stats_fn = "echo_scene_set_batch_stats"
+
     def _ensure(self, n_nodes: int, n_triples: int):
         ver = self._weights_version()
-        cap = self._handle_key[1] if self._handle_key else (0, 0)
-        if self._handle is not None and self._handle_key[0] == ver and n_nodes <= cap[0] and n_triples <= cap[1]:
-            return
+        cap = self._handle_key[1] if self._handle_key else (0, 0, False)
+        if (self._handle is not None and self._handle_key[0] == ver and n_nodes <= cap[0] and n_triples <= cap[1]
+                and (cap[2] or not self.training)):
+            return self._apply_mode()
         self._destroy_handle()
-        cap = (_next_pow2(n_nodes, 32), _next_pow2(n_triples, 128))
+        cap = (_next_pow2(n_nodes, 32), _next_pow2(n_triples, 128), bool(self.training or cap[2]))
         c = self.cfg
         d = _lib.SceneDesc(c.gconv_dim, c.add_dim, c.num_objs + 1, c.num_preds, c.num_layers, c.rel_s_hidden,
-                           c.context_dim, cap[0], cap[1], 1e-5, int(c.man_dc_preds))
+                           c.context_dim, cap[0], cap[1], 1e-5, int(c.man_dc_preds), int(cap[2]))
         arr, n, keep = _lib.weights_table(self.state_dict())
         h = C.c_void_p()
         _lib.check(_lib.lib().echo_scene_create(C.byref(h), C.byref(d), arr, n))
         self._handle, self._handle_key = h, (ver, cap)
+        self._apply_mode()
 
     def _destroy_handle(self):
         if self._handle is not None:
@@ -279,7 +293,6 @@ class SceneEncoder(_SpecModule):
             self._handle = None
 
     def _prep(self, objs, triples, text_feat, rel_feat):
-        self._check_eval()
         _lib.require_cuda(objs, triples, text_feat, rel_feat)
         n, t = int(objs.shape[0]), int(triples.shape[0])
         if objs.dtype != torch.int64 or objs.dim() != 1:
@@ -334,8 +347,7 @@ class SceneEncoder(_SpecModule):
 
     @torch.no_grad()
     def rel_s(self, x):
-        """self.rel_s_mlp(x): (M, feat) -> (M, context_dim)."""
-        self._check_eval()
+        """self.rel_s_mlp(x): (M, feat) -> (M, context_dim).  Under train() its BatchNorm1d uses the statistics of the M rows."""
         if not self.with_rel_s:
             raise EchoError("this SceneEncoder was built without rel_s_mlp (layout-only model)")
         _lib.require_cuda(x)
@@ -353,6 +365,7 @@ class SceneEncoder(_SpecModule):
         """The encoder stage of ``Sg2ScDiffModel.sample`` (EchoScene.py:388-410) in one call.  ``change`` (N, embedding_dim)
         defaults to the zero flag of ``sample``.  -> obj_embed, latent (N,feat); uc_s, c_s (N,1,context_dim) when
         ``shape_cond`` (gen_shape=True)."""
+        self._check_eval()
         objs, g, tf, rf, n, t = self._prep(objs, triples, text_feat, rel_feat)
         c, dev = self.cfg, objs.device
         if change is not None:
@@ -420,20 +433,24 @@ class UNet1DModel(_SpecModule):
             self.time_num, self.beta_start, self.beta_end = time_num, beta_start, beta_end
             self._destroy_handle()
 
+    _set_batch_stats_fn = "echo_layout_set_batch_stats"
+
     def _ensure(self, n_nodes, n_triples):
         ver = self._weights_version()
-        cap = self._handle_key[1] if self._handle_key else (0, 0)
-        if self._handle is not None and self._handle_key[0] == ver and n_nodes <= cap[0] and n_triples <= cap[1]:
-            return
+        cap = self._handle_key[1] if self._handle_key else (0, 0, False)
+        if (self._handle is not None and self._handle_key[0] == ver and n_nodes <= cap[0] and n_triples <= cap[1]
+                and (cap[2] or not self.training)):
+            return self._apply_mode()
         self._destroy_handle()
-        cap = (_next_pow2(n_nodes, 32), _next_pow2(n_triples, 128))
+        cap = (_next_pow2(n_nodes, 32), _next_pow2(n_triples, 128), bool(self.training or cap[2]))
         c = self.cfg
         d = _lib.LayoutDesc()
+        d.keep_train_weights = int(cap[2])
         d.in_channels, d.out_channels, d.model_channels = c.in_channels, c.out_channels, c.model_channels
         _fill_levels(d, c.channel_mult, c.attention_resolutions)
         d.num_res_blocks, d.num_heads, d.context_dim = c.num_res_blocks, c.num_heads, c.crossattn_dim
         d.obj_embed_dim, d.gconv_dim, d.enable_t_emb = c.obj_embed_dim, c.gconv_dim, int(c.enable_t_emb)
-        d.max_nodes, d.max_triples = cap
+        d.max_nodes, d.max_triples = cap[:2]
         d.precision = _lib.precision_code(self.precision)
         d.time_num, d.beta_start, d.beta_end = self.time_num, self.beta_start, self.beta_end
         dev = next(self.parameters()).device
@@ -442,6 +459,7 @@ class UNet1DModel(_SpecModule):
         h = C.c_void_p()
         _lib.check(_lib.lib().echo_layout_create(C.byref(h), C.byref(d), arr, n))
         self._handle, self._handle_key = h, (ver, cap)
+        self._apply_mode()
 
     def _destroy_handle(self):
         if self._handle is not None:
@@ -451,8 +469,8 @@ class UNet1DModel(_SpecModule):
     @torch.no_grad()
     def forward(self, box_t, obj_embed, triples, timesteps=None, context=None, y=None, **kwargs):
         """box_t (N,8), obj_embed (N,640), triples (T,3) i64, timesteps (N,) i64 -> (N,8,1).  ``context`` is accepted
-        and ignored exactly as the reference ignores it in crossattn mode (denoise_net.py:791-792)."""
-        self._check_eval()
+        and ignored exactly as the reference ignores it in crossattn mode (denoise_net.py:791-792).  Under train() box_graph_cov's
+        BatchNorm1d layers use the statistics of the batch (forward values of get_loss_iter's denoiser call)."""
         _lib.require_cuda(box_t, obj_embed, triples, timesteps)
         n = box_t.shape[0]
         box_t = box_t.float().contiguous()
@@ -536,24 +554,28 @@ class UNet3DModel(_SpecModule):
             self.ddim_steps, self.timesteps_total, self.linear_start, self.linear_end = new
             self._destroy_handle()
 
+    _set_batch_stats_fn = "echo_shape_set_batch_stats"
+
     def _ensure(self, n_nodes, n_triples, n_local=None, sharded_call=False):
         """sharded_call: the caller is embed_local / trunk_local (codes come from outside): a handle built for a shard also serves
         a call whose local range happens to be the whole (sub)graph, so the handle is not rebuilt back and forth."""
         n_local = n_nodes if n_local is None else n_local
         ver = self._weights_version()
-        cap = self._handle_key[1] if self._handle_key else (0, 0, 0)
+        cap = self._handle_key[1] if self._handle_key else (0, 0, 0, False)
         if (self._handle is not None and self._handle_key[0] == ver and n_nodes <= cap[0] and n_triples <= cap[1]
-                and n_local <= cap[2] and ((cap[2] == cap[0]) == (n_local == n_nodes) or (sharded_call and cap[2] != cap[0]))):
-            return
+                and n_local <= cap[2] and ((cap[2] == cap[0]) == (n_local == n_nodes) or (sharded_call and cap[2] != cap[0]))
+                and (cap[3] or not self.training)):
+            return self._apply_mode()
         self._destroy_handle()
-        cap = (max(n_nodes, 1), _next_pow2(n_triples, 128), max(n_local, 1))
+        cap = (max(n_nodes, 1), _next_pow2(n_triples, 128), max(n_local, 1), bool(self.training or cap[3]))
         c = self.cfg
         d = _lib.ShapeDesc()
+        d.keep_train_weights = int(cap[3])
         d.in_channels, d.out_channels, d.model_channels = c.in_channels, c.out_channels, c.model_channels
         _fill_levels(d, c.channel_mult, c.attention_resolutions)
         d.num_res_blocks, d.num_heads, d.context_dim = c.num_res_blocks, c.num_heads, c.context_dim
         d.gconv_dim, d.enable_t_emb, d.latent_size = c.gconv_dim, int(c.enable_t_emb), c.image_size
-        d.max_nodes, d.max_triples, d.max_local_nodes = cap
+        d.max_nodes, d.max_triples, d.max_local_nodes = cap[:3]
         d.precision = _lib.precision_code(self.precision)
         d.timesteps, d.ddim_steps = self.timesteps_total, self.ddim_steps
         d.linear_start, d.linear_end = self.linear_start, self.linear_end
@@ -563,6 +585,7 @@ class UNet3DModel(_SpecModule):
         h = C.c_void_p()
         _lib.check(_lib.lib().echo_shape_create(C.byref(h), C.byref(d), arr, n))
         self._handle, self._handle_key = h, (ver, cap)
+        self._apply_mode()
 
     def _destroy_handle(self):
         if self._handle is not None:
@@ -583,8 +606,8 @@ class UNet3DModel(_SpecModule):
     @torch.no_grad()
     def forward(self, x, obj_embed, triples, timesteps=None, context=None, y=None, **kwargs):
         """x (N,3,16,16,16), obj_embed (N,1,1280), triples (T,3) i64, timesteps (N,) i64 -> e_t like x.  ``context``
-        is accepted and ignored as in the reference ("we dont use the previous context", openai_model_3d.py:843-844)."""
-        self._check_eval()
+        is accepted and ignored as in the reference ("we dont use the previous context", openai_model_3d.py:843-844).  Under train()
+        shape_code_graph_cov's BatchNorm1d layers use the statistics of the batch (forward values of p_losses' denoiser call)."""
         n, x, obj_embed = self._prep(x, obj_embed, triples)
         timesteps = timesteps.to(torch.int64).contiguous()
         self._ensure(n, triples.shape[0])

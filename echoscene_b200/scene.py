@@ -142,7 +142,8 @@ class Sg2ScDiffModel:
 
     def __init__(self, encoder, layout, shape=None, vqvae=None, ddim_steps: int = 100, uc_scale: float = 3.0,
                  z_shape=(3, 16, 16, 16), replace_latent: bool = False, box_dim: int = 8, size_dim: int = 3,
-                 translation_dim: int = 3, reference_rng: bool = False, ddim_sampler_cls: Optional[Callable] = None):
+                 translation_dim: int = 3, reference_rng: bool = False, ddim_sampler_cls: Optional[Callable] = None,
+                 diffusion_bs: int = 16):
         self.encoder, self.layout, self.shape, self.vqvae = encoder, layout, shape, vqvae
         self.ddim_steps, self.uc_scale, self.z_shape = int(ddim_steps), uc_scale, tuple(z_shape)
         self.replace_all_latent = replace_latent                      # EchoScene.py:27
@@ -151,6 +152,8 @@ class Sg2ScDiffModel:
         self.out_dim_ini_encoder = encoder.out_dim_ini_encoder
         self.reference_rng = reference_rng
         self._ddim_cls = ddim_sampler_cls
+        self.diffusion_bs = int(diffusion_bs)                          # EchoScene.py:76 (SGDiff.py:21 passes 16)
+        self._shape_tables = self._layout_tables = None
 
     # ---- the two chains -------------------------------------------------------------------------------------------
     def generate_layout(self, triples, obj_embed, relation_cond) -> Dict[str, torch.Tensor]:
@@ -254,6 +257,124 @@ class Sg2ScDiffModel:
         keep = keep_mask(len(layout_dict["translations"]), nodes_added, latent.device)
         return keep, shape_dict, layout_dict
 
+    # ---- the training forward (forward VALUES) --------------------------------------------------------------
+    def train(self, mode: bool = True):
+        """model.train() / model.eval() of the reference (scripts/train_3dfront.py:237): BatchNorm1d of the GCN MLPs and rel_s_mlp
+        switch to batch statistics.  The VQ-VAE always stays in eval (echo2shape.py:334 switches only ``df``)."""
+        self.encoder.train(mode)
+        self.layout.train(mode)
+        if self.shape is not None:
+            self.shape.train(mode)
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def select_sdfs(self, dec_objs_to_scene, obj_cats, triples, sdfs, s_feat_ucon, s_feat_con, sample_type: str = "greedy"):
+        """Sg2ScDiffModel.select_sdfs, sample_type 'greedy' (EchoScene.py:289-319; the only option with message passing in the shape
+        branch, :104): whole scenes in order until the next one no longer fits ``diffusion_bs`` objects, and the triples among the
+        selected nodes.  -> (obj_cat_selected, {'sdf', 'uc_s', 'c_s', 'scene_ids', 'triples'})."""
+        if sample_type != "greedy":
+            raise EchoError(f"select_sdfs: sampling='{sample_type}' is outside the hot path (greedy is asserted with message passing, "
+                            "EchoScene.py:104)")
+        o2s = np.asarray(dec_objs_to_scene.detach().cpu() if torch.is_tensor(dec_objs_to_scene) else dec_objs_to_scene)
+        num = 0
+        for i in np.unique(o2s):
+            ids = np.where(o2s == i)[0]
+            if self.diffusion_bs - num < len(ids):
+                break
+            num += len(ids)
+        if num == 0:
+            raise EchoError(f"select_sdfs: the first scene has more than diffusion_bs = {self.diffusion_bs} objects (the reference "
+                            "fails in torch.cat of an empty list here)")
+        # scenes are contiguous node ranges in a collated batch (threedfront_dataset.py collate_fn), which the reference's
+        # `triples[:, 0] < num` mask relies on as well
+        sel = np.concatenate([np.where(o2s == i)[0] for i in np.unique(o2s)])[:num]
+        if not np.array_equal(sel, np.arange(num)):
+            raise EchoError("select_sdfs: obj_to_scene is not sorted by scene (not a collated batch)")
+        mask = (triples[:, 0] < num) & (triples[:, 2] < num)
+        triples_selected = triples[mask]
+        if len(triples_selected) == 0:
+            raise EchoError("select_sdfs: no triple among the selected objects (the reference passes triples=None to the denoiser here "
+                            "and fails inside it)")
+        bs = self.diffusion_bs
+        return obj_cats[:num][:bs], {"sdf": sdfs[:num][:bs], "uc_s": s_feat_ucon[:num][:bs], "c_s": s_feat_con[:num][:bs],
+                                      "scene_ids": o2s[:num][:bs], "triples": triples_selected}
+
+    @torch.no_grad()
+    def shape_loss(self, diff_dict):
+        """EchoToShape.set_input + forward (echo2shape.py:229-241, 334-366): VQ-VAE encode without quantisation, one timestep per
+        object, q_sample, the denoiser under train(), the eps losses.  Draw order: torch.randint (t), torch.randn_like (noise)."""
+        from . import train as T
+        if self.shape is None or self.vqvae is None:
+            raise EchoError("shape_loss needs the shape branch and a VQVAE built with with_encoder=True")
+        if self._shape_tables is None:
+            u = self.shape
+            self._shape_tables = {k: v.to(diff_dict["sdf"].device) for k, v in
+                                  T.shape_train_tables(u.timesteps_total, u.linear_start, u.linear_end).items()}
+        tb = self._shape_tables
+        self.shape.train(True)                                                        # switch_train, echo2shape.py:336
+        z = self.vqvae.encode_no_quant(diff_dict["sdf"])
+        t = torch.randint(0, self.shape.timesteps_total, (z.shape[0],), device=z.device).long()
+        noise = torch.randn_like(z)
+        x_noisy = T.q_sample(z, t, noise, tb["sqrt_alphas_cumprod"], tb["sqrt_one_minus_alphas_cumprod"])
+        out = self.shape(x_noisy, diff_dict["uc_s"], diff_dict["triples"], t, context=diff_dict["c_s"])
+        loss, loss_dict = T.shape_diffusion_loss(out, noise, t, tb["logvar"], tb["lvlb_weights"])
+        return loss, loss_dict
+
+    @torch.no_grad()
+    def layout_loss(self, diff_dict):
+        """EchoToLayout.set_input + forward -> DiffusionPoint.get_loss_iter -> GaussianDiffusion.p_losses (echo2layout.py:57-99,
+        diffusion_ddpm.py:597-608, 479-507): one timestep per SCENE, angle -> (sin, cos), q_sample, the denoiser under train(),
+        diffusion_loss with loss_iou = False.  Draw order: torch.randint (t per scene), torch.randn (noise)."""
+        from . import train as T
+        box, o2s = diff_dict["box"], diff_dict["obj_id_to_scene"]
+        if self._layout_tables is None:
+            m = self.layout.model
+            self._layout_tables = tuple(v.to(box.device) for v in T.layout_train_tables(m.time_num, m.beta_start, m.beta_end))
+        self.layout.train(True)                                                       # echo2layout.py:80
+        o2s = np.asarray(o2s.detach().cpu() if torch.is_tensor(o2s) else o2s)
+        unique_scenes, inv_idx = np.unique(o2s, return_inverse=True)
+        t = torch.randint(0, self.layout.time_num, size=unique_scenes.shape, device=box.device)
+        t = t[torch.from_numpy(inv_idx).to(box.device)]
+        D = box.shape[1]
+        data_start = torch.cat((box[:, :D - 1], torch.sin(box[:, D - 1:D]), torch.cos(box[:, D - 1:D])), dim=-1).float()
+        noise = torch.randn(data_start.shape, dtype=data_start.dtype, device=data_start.device)
+        data_t = T.q_sample(data_start, t, noise, *self._layout_tables)
+        out = self.layout._denoise(data_t, diff_dict["uc_b"], diff_dict["preds"], t, diff_dict["c_b"])
+        return T.layout_diffusion_loss(out, noise, self.size_dim, self.translation_dim, self.box_dim - self.size_dim - self.translation_dim)
+
+    @torch.no_grad()
+    def forward(self, enc_objs, enc_triples, enc_text_feat, enc_rel_feat, dec_objs, dec_objs_grained, dec_triples, dec_boxes,
+                dec_text_feat, dec_rel_feat, dec_objs_to_scene, missing_nodes, manipulated_nodes, dec_sdfs, dec_angles):
+        """Sg2ScDiffModel.forward (EchoScene.py:328-386), the forward of one training iteration (scripts/train_3dfront.py:239-241,
+        model.forward_mani) -> (obj_selected, Shape_loss, Layout_loss, loss_dict) as VALUES: no autograd tape (the backward pass is
+        not part of this round).  Same argument order, same random draws in the same order (np.random.normal change
+        flags, then the shape branch's randint / randn_like, then the layout branch's randint / randn), so a seeded run of the
+        reference produces the same losses."""
+        if not (self.encoder.training and self.layout.training and (self.shape is None or self.shape.training)):
+            raise EchoError("forward is the training forward: call .train() first (sampling entry points are sample*/eval())")
+        e = self.encoder
+        _, _, latent_obj, _ = e.init_encoder(enc_objs, enc_triples, enc_text_feat, enc_rel_feat)
+        latent_obj, nodes_added = insert_zero_rows(latent_obj, missing_nodes)
+        marked = list(nodes_added) + [int(i) for i in manipulated_nodes]
+        change = change_flags(latent_obj.shape[0], marked, self.embedding_dim, latent_obj.device)
+        latent_, _, obj_embed_, _ = e.manipulate(torch.cat([latent_obj, change], dim=1), dec_objs, dec_triples, dec_text_feat,
+                                                 dec_rel_feat)
+        latent = latent_ if self.replace_all_latent else replace_rows(latent_obj, latent_, marked)
+        obj_selected, shape_loss, loss_dict = None, None, {}
+        if self.shape is not None:
+            uc_s = e.rel_s(obj_embed_).unsqueeze(1)
+            c_s = e.rel_s(latent).unsqueeze(1)
+            obj_selected, shape_dict = self.select_sdfs(dec_objs_to_scene, dec_objs, dec_triples, dec_sdfs, uc_s, c_s)
+            shape_loss, d = self.shape_loss(shape_dict)
+            loss_dict.update(d)
+        boxes = torch.cat((dec_boxes, dec_angles.reshape(-1, 1)), dim=-1)           # prepare_boxes, EchoScene.py:321-326
+        layout_loss, d = self.layout_loss({"preds": dec_triples, "box": boxes, "uc_b": obj_embed_, "c_b": latent,
+                                           "obj_id_to_scene": dec_objs_to_scene})
+        loss_dict.update(d)
+        return obj_selected, shape_loss, layout_loss, loss_dict
+
     # ---- SGDiff facade (model/SGDiff.py:87-121, type_ == 'echoscene') ----------------------------------------------
     def sample_box_and_shape(self, dec_objs, dec_triplets, encoded_dec_text_feat, encoded_dec_rel_feat, gen_shape=False):
         shape_dict, layout_dict = self.sample(dec_objs, dec_triplets, encoded_dec_text_feat, encoded_dec_rel_feat,
@@ -287,6 +408,16 @@ class Sg2BoxDiffModel(Sg2ScDiffModel):
 
     def __init__(self, encoder, layout, **kw):
         super().__init__(encoder, layout, shape=None, vqvae=None, **kw)
+
+    @torch.no_grad()
+    def forward(self, enc_objs, enc_triples, enc_text_feat, enc_rel_feat, dec_objs, dec_triples, dec_boxes, dec_text_feat,
+                dec_rel_feat, dec_objs_to_scene, missing_nodes, manipulated_nodes, dec_angles):
+        """Sg2BoxDiffModel.forward (EchoLayout.py:247-289) -> (None, 0, Layout_loss, loss_dict): forward values, see
+        Sg2ScDiffModel.forward."""
+        _, _, layout_loss, loss_dict = super().forward(enc_objs, enc_triples, enc_text_feat, enc_rel_feat, dec_objs, None, dec_triples,
+                                                       dec_boxes, dec_text_feat, dec_rel_feat, dec_objs_to_scene, missing_nodes,
+                                                       manipulated_nodes, None, dec_angles)
+        return None, 0, layout_loss, loss_dict
 
     @torch.no_grad()
     def sampleBoxes(self, dec_objs, dec_triplets, encoded_dec_text_feat, encoded_dec_rel_feat):

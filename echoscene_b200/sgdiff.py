@@ -13,7 +13,8 @@ denoiser_kwargs)`` under ``DiffusionPoint(**layout_branch.diffusion_kwargs)`` (e
 ``DiffusionUNet(unet.params)`` with the DDPM schedule of ``model.params`` and the VQ-VAE of ``vq_cfg`` / ``vq_ckpt``
 (echo2shape.py:62-85, 174-190; model_utils.py:7-32), ``ddim_steps = 100`` (7 when ``misc.debug == 1``, echo2shape.py:116-120).
 
-Sampling only: ``forward_mani`` (the training step) raises -- the backward pass is outside this path.
+``train()`` + ``forward_mani`` compute the VALUES of the training forward (losses on batch statistics; ``with_vq_encoder=True``
+for the shape branch's VQ-VAE encode); the backward pass is outside this path.
 """
 from __future__ import annotations
 
@@ -63,7 +64,8 @@ class SGDiff:
     the working directory of its scripts)."""
 
     def __init__(self, type, diff_opt, vocab, replace_latent=False, with_changes=True, residual=False, gconv_pooling="avg",
-                 with_angles=False, clip=True, separated=False, precision: str = "fp32", config_dir: Optional[str] = None):
+                 with_angles=False, clip=True, separated=False, precision: str = "fp32", config_dir: Optional[str] = None,
+                 with_vq_encoder: bool = False):
         assert type in ["echoscene", "echolayout"], "{} is not included".format(type)
         assert replace_latent is not None and with_changes is not None
         if separated:
@@ -107,12 +109,14 @@ class SGDiff:
                                               precision=precision, ddim_steps=ddim_steps, timesteps=int(_get(mp, "timesteps", 1000)),
                                               linear_start=float(_get(mp, "linear_start")), linear_end=float(_get(mp, "linear_end")))
             self.vqvae = modules.VQVAE(dd, int(_get(vq, "model.params.n_embed")), int(_get(vq, "model.params.embed_dim")),
-                                       precision=precision)
+                                       precision=precision, with_encoder=with_vq_encoder)
             vq_ckpt = _get(diff_opt, "shape_branch.vq_ckpt")
             if isinstance(vq_ckpt, str) and os.path.isfile(self._resolve(vq_ckpt, must_exist=False)):
                 self.load_vqvae(self._resolve(vq_ckpt))                      # load_vqvae, model_utils.py:20-25
         cls = scene.Sg2BoxDiffModel if layout_only else scene.Sg2ScDiffModel
-        kw = dict(replace_latent=replace_latent, box_dim=box_dim, size_dim=s_dim, translation_dim=t_dim)
+        bs = _get(diff_opt, "hyper.batch_size")                                  # diffusion_bs, EchoScene.py:76 / SGDiff.py:21
+        kw = dict(replace_latent=replace_latent, box_dim=box_dim, size_dim=s_dim, translation_dim=t_dim,
+                  diffusion_bs=16 if bs is None else int(bs))
         if layout_only:
             self.diff = cls(self.encoder, self.layout, **kw)
         else:
@@ -171,9 +175,10 @@ class SGDiff:
         return self
 
     def train(self, mode: bool = True):
-        if mode:
-            raise EchoError("training mode is outside the B200 path (sampling only: eval-mode BatchNorm, no autograd)")
-        return self.eval()
+        """model.train() of scripts/train_3dfront.py:237: the BatchNorm1d layers switch to batch statistics (forward values only;
+        the VQ-VAE stays in eval as in the reference)."""
+        self.diff.train(mode)
+        return self
 
     # ---- sampling (SGDiff.py:87-121) ---------------------------------------------------------------------------------------
     def sample_box_and_shape(self, dec_objs, dec_triplets, encoded_dec_text_feat, encoded_dec_rel_feat, gen_shape=False):
@@ -192,8 +197,18 @@ class SGDiff:
                                                                x_T_per_scene=x_T_per_scene)
         return {**shape_dict, **layout_dict, "obj_to_scene": o2s}
 
-    def forward_mani(self, *args, **kwargs):
-        raise EchoError("SGDiff.forward_mani is the training step (losses + backward): outside the B200 sampling path")
+    def forward_mani(self, enc_objs, enc_triples, encoded_enc_text_feat, encoded_enc_rel_feat, dec_objs, dec_objs_grained,
+                     dec_triples, dec_boxes, dec_angles, dec_sdfs, encoded_dec_text_feat, encoded_dec_rel_feat, dec_objs_to_scene,
+                     missing_nodes, manipulated_nodes):
+        """SGDiff.forward_mani (SGDiff.py:32-47), same argument order -> (obj_selected, shape_loss, layout_loss, loss_dict) as
+        forward VALUES under train(): nothing is recorded for loss.backward()."""
+        if self.type_ == "echoscene":
+            return self.diff.forward(enc_objs, enc_triples, encoded_enc_text_feat, encoded_enc_rel_feat, dec_objs, dec_objs_grained,
+                                     dec_triples, dec_boxes, encoded_dec_text_feat, encoded_dec_rel_feat, dec_objs_to_scene,
+                                     missing_nodes, manipulated_nodes, dec_sdfs, dec_angles)
+        return self.diff.forward(enc_objs, enc_triples, encoded_enc_text_feat, encoded_enc_rel_feat, dec_objs, dec_triples, dec_boxes,
+                                 encoded_dec_text_feat, encoded_dec_rel_feat, dec_objs_to_scene, missing_nodes, manipulated_nodes,
+                                 dec_angles)
 
     def save(self, *args, **kwargs):
         raise EchoError("SGDiff.save writes optimizer state of the training loop: outside the B200 sampling path")

@@ -70,6 +70,33 @@ def shape_diffusion_loss(model_output: torch.Tensor, target: torch.Tensor, t: to
     return total, {"loss_simple": loss_simple.mean(), "loss_vlb": loss_vlb, "loss_total": total.detach().clone()}
 
 
+def layout_train_tables(time_num: int = 1000, beta_start: float = 1e-4, beta_end: float = 0.02):
+    """The q_sample tables of GaussianDiffusion.__init__ (diffusion_ddpm.py:133-148, linear get_betas :38-40): float64 betas and
+    cumulative product, rounded to fp32 BEFORE the square roots.  -> (sqrt_alphas_cumprod, sqrt_one_minus_alphas_cumprod) fp32."""
+    import numpy as np
+    betas = np.linspace(beta_start, beta_end, time_num).astype(np.float64)
+    ac = torch.from_numpy(np.cumprod(1.0 - betas, axis=0)).float()
+    return torch.sqrt(ac).float(), torch.sqrt(1.0 - ac).float()
+
+
+def shape_train_tables(timesteps: int = 1000, linear_start: float = 0.00085, linear_end: float = 0.012, v_posterior: float = 0.0):
+    """The tables EchoToShape.register_schedule builds for training (echo2shape.py:173-226; linear make_beta_schedule,
+    ldm_diffusion_util.py:44-47): float64 arithmetic, rounded to fp32 at the end; lvlb_weights for the eps parameterisation
+    (computed from the fp32 tables, as the reference does) with entry 0 overwritten by entry 1; logvar = 0 (:167-168).
+    -> dict(sqrt_alphas_cumprod, sqrt_one_minus_alphas_cumprod, lvlb_weights, logvar)."""
+    import numpy as np
+    betas = (torch.linspace(linear_start ** 0.5, linear_end ** 0.5, timesteps, dtype=torch.float64) ** 2).numpy()
+    alphas = 1.0 - betas
+    ac = np.cumprod(alphas, axis=0)
+    ac_prev = np.append(1.0, ac[:-1])
+    f32 = lambda a: torch.tensor(a, dtype=torch.float32)
+    post_var = (1 - v_posterior) * betas * (1.0 - ac_prev) / (1.0 - ac) + v_posterior * betas
+    lvlb = f32(betas) ** 2 / (2 * f32(post_var) * f32(alphas) * (1 - f32(ac)))
+    lvlb[0] = lvlb[1]
+    return {"sqrt_alphas_cumprod": f32(np.sqrt(ac)), "sqrt_one_minus_alphas_cumprod": f32(np.sqrt(1.0 - ac)),
+            "lvlb_weights": lvlb, "logvar": torch.full((timesteps,), 0.0)}
+
+
 class FusedAdamW:
     """``optimizerFULL`` of the reference (model/EchoScene.py:130-136: AdamW over the encoders, the layout denoiser and the shape
     denoiser) with the step sequence of scripts/train_3dfront.py:247-259 fused into one pass:

@@ -90,6 +90,8 @@ typedef struct echo_layout_desc {
   /* DDPM schedule — diffusion_ddpm.py:38-40,133-162 */
   int32_t time_num;
   float beta_start, beta_end;
+  int32_t keep_train_weights;   /* != 0: the GCN MLPs (and rel_s_mlp) also keep their unfolded tensors, for the batch-statistics forward
+                                  (echo_*_set_batch_stats) */
 } echo_layout_desc_t;
 
 /* UNet3DModel(**unet.params) — config/sdfusion-txt2shape_mp.yaml:16-41, openai_model_3d.py:452-782 */
@@ -112,6 +114,8 @@ typedef struct echo_shape_desc {
   int32_t timesteps;            /* 1000 */
   int32_t ddim_steps;           /* S */
   float linear_start, linear_end;
+  int32_t keep_train_weights;   /* != 0: the GCN MLPs (and rel_s_mlp) also keep their unfolded tensors, for the batch-statistics forward
+                                  (echo_*_set_batch_stats) */
 } echo_shape_desc_t;
 
 ECHO_API int echo_version(void);
@@ -218,6 +222,17 @@ ECHO_API int echo_shape_trunk(echo_shape_t* h, const echo_graph_t* g, const floa
 ECHO_API int echo_shape_trunk_async(echo_shape_t* h, const echo_graph_t* g, const float* x_local, int32_t obj_begin, int32_t n_local,
                            const float* codes_all, const float* obj_embed_all, const int64_t* timesteps_all,
                            int32_t ddim_index, float* out_local, void* codes_stream, void* stream);
+/* Training-mode forward values.  Under model.train() the reference's BatchNorm1d layers -- the MLPs of every
+ * GraphTripleConvNet (the two scene encoders, box_graph_cov, shape_code_graph_cov) and rel_s_mlp -- normalise with the statistics of
+ * the batch (model/layers.py:29-30).  With batch statistics switched on, echo_layout_forward / echo_shape_forward / echo_shape_trunk /
+ * echo_scene_init_encoder / _manipulate / _rel_s compute exactly that forward (GroupNorm / LayerNorm do not depend on the mode,
+ * dropout is 0 in the reference's configs).  Forward values only: nothing records an autograd tape, running statistics are not
+ * updated.  The handle must have been created with keep_train_weights; the sampler steps (echo_layout_step, echo_shape_step)
+ * refuse to run while the switch is on. */
+ECHO_API int echo_layout_set_batch_stats(echo_layout_t* h, int32_t on);
+ECHO_API int echo_shape_set_batch_stats(echo_shape_t* h, int32_t on);
+ECHO_API int echo_scene_set_batch_stats(echo_scene_t* h, int32_t on);
+
 /* A chain whose launch sequence does not depend on the step: pass ECHO_INDEX_FROM_DEVICE as `ddim_index` to echo_shape_step /
  * echo_shape_trunk / echo_shape_trunk_async and the step reads its DDIM index (timesteps, update coefficients) from a slot on
  * the device, written by echo_shape_set_index (stream-ordered).  Such a step can be captured ONCE into a CUDA graph -- together
@@ -329,6 +344,8 @@ typedef struct echo_scene_desc {
   float bn_eps;                 /* 1e-5 */
   int32_t manipulate_pred_dc;   /* 0: manipulate embeds predicates with pred_embeddings_ec (Sg2ScDiffModel, EchoScene.py:187);
                                  * 1: with pred_embeddings_man_dc.weight (the layout-only Sg2BoxDiffModel, EchoLayout.py:154) */
+  int32_t keep_train_weights;   /* != 0: the GCN MLPs (and rel_s_mlp) also keep their unfolded tensors, for the batch-statistics forward
+                                  (echo_*_set_batch_stats) */
 } echo_scene_desc_t;
 ECHO_API int echo_scene_create(echo_scene_t** out, const echo_scene_desc_t* desc, const echo_weight_t* weights, int32_t n_weights);
 /* init_encoder(objs, triples, text_feat, rel_feat) (EchoScene.py:143-157): objs (N) i64 class ids -- the caller guarantees

@@ -71,10 +71,15 @@ def test_echolayout_from_yaml_and_checkpoint(cfg_dir, tmp_path):
     m.eval()
     with pytest.raises(_lib.EchoError, match="CUDA"):
         m.sample_box_and_shape(objs, g.triples, text, rel)
-    with pytest.raises(_lib.EchoError):
-        m.train()
-    with pytest.raises(_lib.EchoError):
-        m.forward_mani()
+    # train(): batch-statistics forward values (the VQ-VAE stays in eval); the training forward ends in the CUDA library as well
+    assert m.train() is m and m.encoder.training and m.unet1d.training
+    boxes, angles = torch.zeros(len(objs), 6), torch.zeros(len(objs))
+    with pytest.raises(_lib.EchoError, match="CUDA"):
+        m.forward_mani(objs, g.triples, text, rel, objs, objs, g.triples, boxes, angles, None, text, rel,
+                       torch.zeros(len(objs), dtype=torch.int64), [], [])
+    with pytest.raises(_lib.EchoError, match="eval"):
+        m.sample_box_and_shape(objs, g.triples, text, rel)
+    assert not m.eval().encoder.training
 
 
 def test_echoscene_from_yaml(cfg_dir, tmp_path):

@@ -1,5 +1,6 @@
 #!/bin/bash
-set -u
+# training forward: two-arm loss parity
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_model_gpu.py tests/test_zz_scene_gpu.py tests/test_ops_gpu.py -m gpu -x -q 2>&1 | tail -4
-timeout 300 python tools/time_step.py --precision bf16 --steps 50 2>&1 | tail -1
+timeout 900 python tools/trainfwd_check.py --out gpurun_out/trainfwd.json > gpurun_out/trainfwd.log 2>&1
+echo "trainfwd rc=$?"
+tail -40 gpurun_out/trainfwd.log
