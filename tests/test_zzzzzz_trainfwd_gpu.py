@@ -2,7 +2,9 @@
 one SGDiff.forward_mani on a collated batch of three scenes (scripts/train_3dfront.py:237-241), eager fp32 on this GPU; the B200
 components, built from the same YAML files and loaded with the same weights, run train().forward_mani on the same batch under the
 same numpy / torch seeds.  Every stage that carries a BatchNorm1d (the two scene encoders, rel_s_mlp, both denoisers' GCNs) is
-compared on its own first, then every entry of the loss dictionary and both loss totals: all within north_star's 1e-3."""
+compared on its own first (the denoiser OUTPUTS: with random-initialised weights the losses themselves are dominated by the noise
+target), then every entry of the loss dictionary and both loss totals -- for a manipulation batch, for an addition (one node
+missing from the encoder-side scene, replace_latent = False) and for the layout-only model: all within north_star's 1e-3."""
 import json
 import os
 import subprocess
@@ -26,3 +28,5 @@ def test_forward_mani_losses_match_the_reference(tmp_path):
     assert res["selected_identical"] and res["worst_rel"] < 1e-3
     assert all(v < 1e-3 for v in res["stages"].values()), res["stages"]
     assert {"loss_simple", "loss_vlb", "loss.bbox", "loss.angle", "Shape_loss", "Layout_loss"} <= set(res["losses"])
+    # an addition with replace_latent = False (zero row inserted, touched rows only), and the layout-only model
+    assert {"loss_simple", "Layout_loss"} <= set(res["losses_addition"]) and "Layout_loss" in res["losses_layout_only"]

@@ -48,9 +48,19 @@ def wrap(x):
     return x
 
 
+class _Loader(yaml.SafeLoader):
+    """SafeLoader that reads `1e-4` as a float, as OmegaConf's loader does (plain PyYAML wants `1.0e-4` and returns a string)."""
+
+
+import re  # noqa: E402
+_Loader.add_implicit_resolver("tag:yaml.org,2002:float", re.compile(
+    r"^(?:[-+]?(?:[0-9][0-9_]*)\.[0-9_]*(?:[eE][-+]?[0-9]+)?|[-+]?(?:[0-9][0-9_]*)(?:[eE][-+]?[0-9]+)|\.[0-9_]+(?:[eE][-+][0-9]+)?"
+    r"|[-+]?\.(?:inf|Inf|INF)|\.(?:nan|NaN|NAN))$"), list("-+0123456789."))
+
+
 def load_yaml(path):
     with open(path) as f:
-        return wrap(yaml.safe_load(f))
+        return wrap(yaml.load(f, Loader=_Loader))
 
 
 def setup_reference():
@@ -63,7 +73,7 @@ def setup_reference():
         sys.path.insert(0, os.path.join(REF, "scripts"))
 
 
-def build(args, workdir):
+def build(args, workdir, model_type="echoscene"):
     """-> (SGDiff instance of the reference, config)."""
     import importlib
     cfg = load_yaml(os.path.join(REF, "config", "full_mp.yaml"))
@@ -95,7 +105,7 @@ def build(args, workdir):
     importlib.import_module("model.networks.diffusion_shape.echo2shape").time = types.SimpleNamespace(time=lambda: 1700000000)
     SGDiff = importlib.import_module("model.SGDiff").SGDiff
     torch.manual_seed(11)
-    model = SGDiff("echoscene", cfg, vocab, replace_latent=True, with_changes=True, residual=True, gconv_pooling="avg",
+    model = SGDiff(model_type, cfg, vocab, replace_latent=True, with_changes=True, residual=True, gconv_pooling="avg",
                    with_angles=True, clip=True, separated=False)
     return model, cfg
 
@@ -107,7 +117,8 @@ def redraw_zero_init(model):
     n = 0
     import itertools
     # EchoToShape is not an nn.Module: its denoiser's parameters are not among the model's
-    for name, p in itertools.chain(model.named_parameters(), model.diff.ShapeDiff.df.named_parameters()):
+    shape_df = model.diff.ShapeDiff.df.named_parameters() if hasattr(model.diff, "ShapeDiff") else []
+    for name, p in itertools.chain(model.named_parameters(), shape_df):
         if p.dim() >= 1 and float(p.detach().abs().max()) == 0.0:
             with torch.no_grad():
                 p.copy_((torch.randn(p.shape, generator=g) * 0.02).to(p.device))

@@ -8,6 +8,10 @@ totals must agree within north_star's 1e-3.  One process: nothing is patched, th
   python tools/trainfwd_check.py [--scenes 3 --nodes 7] [--out gpurun_out/trainfwd.json]
 
 TEST / MEASUREMENT INFRASTRUCTURE: imports baseline/_ref, never imported by the package.
+Three forward_mani calls are compared: a manipulation batch (replace_latent), an addition (one node missing from the encoder-side
+scene, replace_latent = False: zero row inserted, touched rows only) and the layout-only model SGDiff('echolayout').  With
+random-initialised weights the losses are dominated by the noise target, so the denoiser OUTPUTS (and every other stage that
+carries a BatchNorm1d) are compared on identical inputs first (`stages`).
 What this pins: BatchNorm1d on batch statistics in all four GCNs and rel_s_mlp, the greedy object selection, the VQ-VAE encode,
 q_sample of both branches (one timestep per object / per scene), both denoisers, the loss terms, and the order of the random
 draws.  What it does not: gradients (no backward pass on the B200 side).
@@ -50,15 +54,54 @@ def batch(n_scenes, nodes, dev):
                 o2s=torch.tensor(o2s, dtype=torch.int64), boxes=boxes.to(dev), angles=angles.to(dev), sdfs=sdfs.to(dev))
 
 
-def call(model, b, manipulated):
+def without_node(b, k):
+    """The encoder-side scene of an addition: node k and its triples removed, later node indices shifted down (what the dataset
+    hands over as enc_* next to missing_nodes = [k], threedfront_dataset.py)."""
+    keep_n = torch.ones(len(b["objs"]), dtype=torch.bool, device=b["objs"].device)
+    keep_n[k] = False
+    tr = b["triples"]
+    keep_t = (tr[:, 0] != k) & (tr[:, 2] != k)
+    tr = tr[keep_t].clone()
+    tr[:, 0] -= (tr[:, 0] > k).long()
+    tr[:, 2] -= (tr[:, 2] > k).long()
+    return dict(objs=b["objs"][keep_n], triples=tr, text=b["text"][keep_n], rel=b["rel"][keep_t])
+
+
+def call(model, b, manipulated, missing=(), layout_only=False):
     np.random.seed(5)
     torch.manual_seed(4321)
+    e = b
+    for k in sorted(missing, reverse=True):
+        e = without_node(e, k)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    out = model.forward_mani(b["objs"], b["triples"], b["text"], b["rel"], b["objs"], b["objs"], b["triples"], b["boxes"], b["angles"],
-                             b["sdfs"], b["text"], b["rel"], b["o2s"], [], list(manipulated))
+    if layout_only:   # SGDiff.forward_mani routes the same argument list to Sg2BoxDiffModel.forward (SGDiff.py:41-43)
+        out = model.forward_mani(e["objs"], e["triples"], e["text"], e["rel"], b["objs"], b["objs"], b["triples"], b["boxes"], b["angles"],
+                                 None, b["text"], b["rel"], b["o2s"], list(missing), list(manipulated))
+    else:
+        out = model.forward_mani(e["objs"], e["triples"], e["text"], e["rel"], b["objs"], b["objs"], b["triples"], b["boxes"], b["angles"],
+                                 b["sdfs"], b["text"], b["rel"], b["o2s"], list(missing), list(manipulated))
     torch.cuda.synchronize()
     return out, time.perf_counter() - t0
+
+
+def loss_table(tag, r, m):
+    """-> (rows, worst relative deviation) over the loss dictionary and the two totals of one forward_mani call on each side."""
+    (_, r_shape, r_layout, r_dict), (_, m_shape, m_layout, m_dict) = r, m
+    r_vals = {k: float(v.detach()) if torch.is_tensor(v) else float(v) for k, v in r_dict.items()}
+    m_vals = {k: float(v) for k, v in m_dict.items()}
+    for name, rv, mv in (("Shape_loss", r_shape, m_shape), ("Layout_loss", r_layout, m_layout)):
+        if torch.is_tensor(rv):
+            r_vals[name], m_vals[name] = float(rv.detach()), float(mv)
+    rows, worst = {}, 0.0
+    print(f"[{tag}]")
+    for k, rv in r_vals.items():
+        mv = m_vals[k]
+        rel = abs(rv - mv) / abs(rv) if rv != 0 else abs(mv)
+        rows[k] = {"reference": rv, "b200": mv, "rel": rel}
+        worst = max(worst, rel)
+        print(f"  {k:16s} reference {rv:.8f}   b200 {mv:.8f}   rel {rel:.2e}")
+    return rows, worst
 
 
 def stage_checks(ref, mine, b, dev):
@@ -117,41 +160,54 @@ def main(args):
     # echo2shape.py:317 indexes the CPU tensor `logvar` with CUDA timesteps, which the torch of this image (2.11) refuses; the
     # attribute is moved to the GPU on the instance -- the reference's files stay untouched and the values (all 0) are the same
     ref.diff.ShapeDiff.logvar = ref.diff.ShapeDiff.logvar.to(dev)
-    (r_sel, r_shape, r_layout, r_dict), _ = call(ref, b, manipulated)
-    (r_sel, r_shape, r_layout, r_dict), r_sec = call(ref, b, manipulated)
-    r_vals = {k: float(v) for k, v in r_dict.items()}
-    r_vals.update({"Shape_loss": float(r_shape), "Layout_loss": float(r_layout)})
+    call(ref, b, manipulated)
+    r1, r_sec = call(ref, b, manipulated)
+    # an addition (one node missing from the encoder-side scene) with replace_latent = False: only the touched rows are replaced
+    ref.diff.replace_all_latent = False
+    r2, _ = call(ref, b, [args.nodes + 3], missing=[2])
+    ref.diff.replace_all_latent = True
 
     # ---- the B200 arm: its own components from the same YAML files, the reference's weights as a checkpoint dict
     from echoscene_b200 import scene, sgdiff
     ckpt = {k: v.detach() for k, v in torch.nn.Module.state_dict(ref.diff).items() if torch.is_tensor(v)}
     ckpt["shape_df"] = ref.diff.ShapeDiff.df.state_dict()
     ckpt["vqvae"] = ref.diff.ShapeDiff.vqvae.state_dict()
-    vocab = ref.vocab
-    mine = sgdiff.SGDiff("echoscene", cfg, vocab, replace_latent=True, with_changes=True, residual=True, gconv_pooling="avg",
-                         with_angles=True, clip=True, separated=False, precision=args.precision,
-                         config_dir=os.path.join(rb.REF, "config"), with_vq_encoder=True)
+    kw = dict(replace_latent=True, with_changes=True, residual=True, gconv_pooling="avg", with_angles=True, clip=True, separated=False,
+              precision=args.precision, config_dir=os.path.join(rb.REF, "config"))
+    mine = sgdiff.SGDiff("echoscene", cfg, ref.vocab, with_vq_encoder=True, **kw)
     info = scene.load_reference_checkpoint(ckpt, encoder=mine.encoder, unet1d=mine.unet1d, unet3d=mine.unet3d, vqvae=mine.vqvae)
     print("loaded:", info["loaded"])
     mine = mine.cuda().train()
     stages = stage_checks(ref, mine, b, dev)
-    (m_sel, m_shape, m_layout, m_dict), _ = call(mine, b, manipulated)
-    (m_sel, m_shape, m_layout, m_dict), m_sec = call(mine, b, manipulated)
-    m_vals = {k: float(v) for k, v in m_dict.items()}
-    m_vals.update({"Shape_loss": float(m_shape), "Layout_loss": float(m_layout)})
+    call(mine, b, manipulated)
+    m1, m_sec = call(mine, b, manipulated)
+    mine.diff.replace_all_latent = False
+    m2, _ = call(mine, b, [args.nodes + 3], missing=[2])
 
-    worst = 0.0
-    rows = {}
-    for k, rv in r_vals.items():
-        mv = m_vals[k]
-        rel = abs(rv - mv) / max(abs(rv), 1e-30) if rv != 0 else abs(mv)
-        rows[k] = {"reference": rv, "b200": mv, "rel": rel}
-        worst = max(worst, rel)
-        print(f"  {k:16s} reference {rv:.8f}   b200 {mv:.8f}   rel {rel:.2e}")
-    same_sel = bool(torch.equal(r_sel.cpu(), m_sel.cpu()))
-    print(f"objects selected for the shape branch: {len(r_sel)} / {len(b['objs'])}, identical: {same_sel}")
-    print(f"forward_mani: reference (eager, autograd tape recorded) {r_sec * 1e3:.1f} ms, b200 (values only) {m_sec * 1e3:.1f} ms;  worst {worst:.3e}")
-    res = {"stages": stages, "losses": rows, "worst_rel": worst, "selected_identical": same_sel, "scenes": args.scenes, "nodes_per_scene": args.nodes,
+    rows1, w1 = loss_table("three scenes, two manipulated nodes, replace_latent", r1, m1)
+    rows2, w2 = loss_table("one missing node + one manipulated node, touched rows only", r2, m2)
+    same_sel = bool(torch.equal(r1[0].cpu(), m1[0].cpu()) and torch.equal(r2[0].cpu(), m2[0].cpu()))
+    print(f"objects selected for the shape branch: {len(r1[0])} / {len(b['objs'])}, identical: {same_sel}")
+    print(f"forward_mani: reference (eager, autograd tape recorded) {r_sec * 1e3:.1f} ms, b200 (values only) {m_sec * 1e3:.1f} ms")
+    del ref, mine
+    torch.cuda.empty_cache()
+
+    # ---- the layout-only model (SGDiff('echolayout'), model/EchoLayout.py:247-289)
+    refl, cfgl = rb.build(args, workdir, model_type="echolayout")
+    rb.redraw_zero_init(refl)
+    refl = refl.to(dev).train()
+    r3, _ = call(refl, b, manipulated, missing=[2], layout_only=True)
+    minel = sgdiff.SGDiff("echolayout", cfgl, refl.vocab, **kw)
+    ckl = {k: v.detach() for k, v in torch.nn.Module.state_dict(refl.diff).items() if torch.is_tensor(v)}
+    print("loaded:", scene.load_reference_checkpoint(ckl, encoder=minel.encoder, unet1d=minel.unet1d)["loaded"])
+    minel = minel.cuda().train()
+    m3, _ = call(minel, b, manipulated, missing=[2], layout_only=True)
+    rows3, w3 = loss_table("layout-only model (echolayout), one missing + two manipulated nodes", r3, m3)
+
+    worst = max(w1, w2, w3)
+    print(f"worst deviation {worst:.3e}")
+    res = {"stages": stages, "losses": rows1, "losses_addition": rows2, "losses_layout_only": rows3, "worst_rel": worst,
+           "selected_identical": same_sel, "scenes": args.scenes, "nodes_per_scene": args.nodes,
            "manipulated_nodes": manipulated, "precision": args.precision, "reference_ms": r_sec * 1e3, "b200_ms": m_sec * 1e3,
            "note": "reference = unmodified baseline/_ref under model.train(), eager fp32 (TF32 off) on the same GPU, building its autograd "
                    "tape; b200 = forward values only (no tape, no backward)"}
