@@ -110,6 +110,10 @@ PROTOTYPES = {
     "echo_gcn_create": (C.c_int, [C.POINTER(_P), C.POINTER(GcnDesc), C.POINTER(Weight), _I]),
     "echo_gcn_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "echo_gcn_forward_train": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "echo_gcn_train_create": (C.c_int, [C.POINTER(_P), C.POINTER(GcnDesc), C.POINTER(Weight), _I, C.POINTER(Weight), _I]),
+    "echo_gcn_train_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "echo_gcn_train_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "echo_gcn_train_destroy": (None, [_P]),
     "echo_layout_set_batch_stats": (C.c_int, [_P, _I]),
     "echo_shape_set_batch_stats": (C.c_int, [_P, _I]),
     "echo_scene_set_batch_stats": (C.c_int, [_P, _I]),

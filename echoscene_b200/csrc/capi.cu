@@ -10,6 +10,7 @@
 struct echo_layout;
 struct echo_shape;
 struct echo_scene;
+struct echo_gcn_train;
 
 namespace echo {
 void set_tc_mode(int);
@@ -26,6 +27,10 @@ void shape_destroy(echo_shape*);
 void shape_forward(echo_shape*, const echo_graph*, const float*, const float*, const int64_t*, float*, cudaStream_t);
 void shape_set_index(echo_shape*, int, cudaStream_t);
 void shape_set_batch_stats(echo_shape*, bool);
+echo_gcn_train* gcn_train_create(const echo_gcn_desc_t*, const echo_weight_t*, int, const echo_weight_t*, int);
+void gcn_train_forward(echo_gcn_train*, const echo_graph*, const float*, const float*, float*, float*, cudaStream_t);
+void gcn_train_backward(echo_gcn_train*, const echo_graph*, const float*, const float*, float*, float*, cudaStream_t);
+void gcn_train_destroy(echo_gcn_train*);
 void layout_set_batch_stats(echo_layout*, bool);
 void scene_set_batch_stats(echo_scene*, bool);
 echo_optimizer* optimizer_create(const echo_opt_tensor_t*, int);
@@ -426,6 +431,22 @@ int echo_metrics_validate_constraints(const int64_t* triples, int64_t n_triples,
                          out_rel, out_ok, (cudaStream_t)stream);
   });
 }
+int echo_gcn_train_create(echo_gcn_train_t** out, const echo_gcn_desc_t* desc, const echo_weight_t* params, int32_t n_params,
+                          const echo_weight_t* grads, int32_t n_grads) {
+  return guard([&] {
+    ECHO_CHECK(out, "gcn_train_create: null out");
+    *out = gcn_train_create(desc, params, n_params, grads, n_grads);
+  });
+}
+int echo_gcn_train_forward(echo_gcn_train_t* h, const echo_graph_t* g, const float* obj_vecs, const float* pred_vecs, float* obj_out,
+                           float* pred_out, void* stream) {
+  return guard([&] { gcn_train_forward(h, g, obj_vecs, pred_vecs, obj_out, pred_out, (cudaStream_t)stream); });
+}
+int echo_gcn_train_backward(echo_gcn_train_t* h, const echo_graph_t* g, const float* d_obj_out, const float* d_pred_out, float* d_obj_in,
+                            float* d_pred_in, void* stream) {
+  return guard([&] { gcn_train_backward(h, g, d_obj_out, d_pred_out, d_obj_in, d_pred_in, (cudaStream_t)stream); });
+}
+void echo_gcn_train_destroy(echo_gcn_train_t* h) { gcn_train_destroy(h); }
 int echo_layout_set_batch_stats(echo_layout_t* h, int32_t on) {
   return guard([&] { layout_set_batch_stats(h, on != 0); });
 }

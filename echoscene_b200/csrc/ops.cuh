@@ -113,6 +113,26 @@ struct LinArgs {
   int act = 0;                 // 0 none, 1 relu, 2 silu (before res)
 };
 void linear_rows(const LinArgs& a, cudaStream_t s);
+
+// fp32-grade GEMM on the tensor cores (3 x TF32 split, sgemm_x3.cu): C[m, n] = sum_k A(m, k) B(k, n) (+ bias[n]) (+ res[m, n]),
+// A(m, k) = A[m * sam + k * sak], B(k, n) = B[k * sbk + n * sbn]; one stride of each operand must be 1.
+struct SgemmX3Args {
+  const float* A = nullptr;
+  int64_t sam = 0, sak = 1;
+  const float* B = nullptr;
+  int64_t sbk = 0, sbn = 1;
+  float* C = nullptr;
+  int64_t ldc = 0;
+  int M = 0, N = 0, K = 0;
+  const float* bias = nullptr;
+  const float* res = nullptr;   // may alias C (accumulate in place)
+  int64_t ld_res = 0;
+  // split reduction: slice z of `splits` covers k in [z * chunk, min(K, (z + 1) * chunk)) and writes C + z * c_bs (no bias / res then)
+  int splits = 1, chunk = 0;
+  int64_t c_bs = 0;
+};
+bool sgemm_x3_supported(const SgemmX3Args& g);
+void sgemm_x3(const SgemmX3Args& g, cudaStream_t s);
 bool linear_rows_gn_supported(int K, int cpg);
 
 // ---------------------------------------------------------------------------------------------------------------

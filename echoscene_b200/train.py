@@ -97,6 +97,123 @@ def shape_train_tables(timesteps: int = 1000, linear_start: float = 0.00085, lin
             "lvlb_weights": lvlb, "logvar": torch.full((timesteps,), 0.0)}
 
 
+class GraphTripleConvNetTrainer:
+    """Training-mode forward AND backward of a ``modules.GraphTripleConvNet`` / ``GraphTripleConv`` on the CUDA path
+    (``echo_gcn_train_*``, csrc/gcn_train.cu): what the reference gets from autograd over model/graph.py:124-211 under
+    ``model.train()`` -- the first block of the backward pass.
+
+        tr = GraphTripleConvNetTrainer(net)                     # net: BatchNorm1d MLPs (mlp_normalization='batch')
+        obj_out, pred_out = tr.forward(obj_vecs, pred_vecs, edges)
+        d_obj, d_pred = tr.backward(d_obj_out, d_pred_out)     # every net parameter's .grad += its gradient
+        FusedAdamW(net.parameters()).step()                     # parameters are read in place: no rebuild after the step
+
+    The parameters' ``.grad`` tensors are views of ONE flat buffer owned by the trainer (``zero_grad`` is a single memset instead of
+    a launch per parameter) and are accumulated into, as autograd does; zero them between iterations.  The forward updates
+    running_mean / running_var / num_batches_tracked as torch does.  Deterministic: no float atomics anywhere."""
+
+    def __init__(self, net, max_nodes: int = 64, max_triples: int = 256):
+        if getattr(net.cfg, "mlp_normalization", None) != "batch":
+            raise EchoError("GraphTripleConvNetTrainer needs BatchNorm1d MLPs (mlp_normalization='batch', every construction on the hot path)")
+        self.net = net
+        self.cap = (int(max_nodes), int(max_triples))
+        self._handle, self._key, self._graph = None, None, None
+        params = list(net.parameters())
+        _lib.require_cuda(*params)
+        self._flat = torch.zeros(sum(p.numel() for p in params), device=params[0].device)
+        off = 0
+        for p in params:       # existing gradients are carried over into the flat buffer
+            view = self._flat[off:off + p.numel()].view_as(p)
+            if p.grad is not None:
+                view.copy_(p.grad)
+            p.grad = view
+            off += p.numel()
+
+    def _tables(self):
+        sd = self.net.state_dict_for_lib()
+        for k, v in sd.items():
+            if not v.is_contiguous():
+                raise EchoError(f"GraphTripleConvNetTrainer: parameter {k} must be contiguous (it is read in place)")
+        pre = "gconvs.0." if type(self.net).__name__ == "GraphTripleConv" else ""
+        grads = {}
+        for k, p in self.net.named_parameters():
+            if p.grad is None:
+                p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            if p.grad.dtype != torch.float32 or not p.grad.is_contiguous():
+                raise EchoError(f"GraphTripleConvNetTrainer: gradient of {k} must be contiguous fp32")
+            grads[pre + k] = p.grad
+        return sd, grads
+
+    def _ensure(self, n, t):
+        sd, grads = self._tables()
+        key = (tuple(v.data_ptr() for v in sd.values()), tuple(g.data_ptr() for g in grads.values()))
+        if self._handle is not None and key == self._key and n <= self.cap[0] and t <= self.cap[1]:
+            return
+        self._destroy()
+        self.cap = (max(self.cap[0], n), max(self.cap[1], t))
+        c = self.net.cfg
+        d = _lib.GcnDesc(c.input_dim_obj, c.input_dim_pred, c.num_layers, c.hidden_dim, c.output_dim or 0, self.cap[0], self.cap[1], 1e-5, 0)
+        pa, np_, keep1 = _lib.weights_table(sd)
+        ga, ng, keep2 = _lib.weights_table(grads)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().echo_gcn_train_create(C.byref(h), C.byref(d), pa, np_, ga, ng))
+        self._handle, self._key = h, key
+
+    def _destroy(self):
+        if self._handle is not None:
+            _lib.lib().echo_gcn_train_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
+
+    def zero_grad(self):
+        self._flat.zero_()
+
+    @torch.no_grad()
+    def forward(self, obj_vecs, pred_vecs, edges):
+        _lib.require_cuda(obj_vecs, pred_vecs, edges)
+        c = self.net.cfg
+        obj_vecs, pred_vecs = obj_vecs.float().contiguous(), pred_vecs.float().contiguous()
+        n, t = obj_vecs.shape[0], pred_vecs.shape[0]
+        if obj_vecs.shape[1] != c.input_dim_obj or pred_vecs.shape[1] != c.input_dim_pred or tuple(edges.shape) != (t, 2):
+            raise EchoError(f"GraphTripleConvNetTrainer.forward: obj {tuple(obj_vecs.shape)}, pred {tuple(pred_vecs.shape)}, edges {tuple(edges.shape)}")
+        self._ensure(n, t)
+        self._graph = _lib.graph_for_edges(edges, n)
+        obj_out = torch.empty(n, c.output_dim or c.input_dim_obj, device=obj_vecs.device)
+        pred_out = torch.empty(t, c.input_dim_pred, device=obj_vecs.device)
+        _lib.check(_lib.lib().echo_gcn_train_forward(self._handle, self._graph.h, _lib.ptr(obj_vecs), _lib.ptr(pred_vecs), _lib.ptr(obj_out),
+                                                     _lib.ptr(pred_out), _lib.stream_ptr()))
+        return obj_out, pred_out
+
+    @torch.no_grad()
+    def backward(self, d_obj_out, d_pred_out=None, need_input_grads: bool = True):
+        """cotangents of ``forward``'s two outputs (``d_pred_out`` None = zeros) -> (d_obj_vecs, d_pred_vecs) (None, None when
+        ``need_input_grads`` is False); the parameters' ``.grad`` are accumulated into."""
+        if self._graph is None:
+            raise EchoError("GraphTripleConvNetTrainer.backward: call forward first")
+        _lib.require_cuda(d_obj_out, d_pred_out)
+        c, g = self.net.cfg, self._graph
+        n, t = d_obj_out.shape[0], (d_pred_out.shape[0] if d_pred_out is not None else None)
+        d_obj_out = d_obj_out.float().contiguous()
+        if d_obj_out.shape[1] != (c.output_dim or c.input_dim_obj):
+            raise EchoError(f"backward: d_obj_out {tuple(d_obj_out.shape)}")
+        if d_pred_out is not None:
+            d_pred_out = d_pred_out.float().contiguous()
+            if d_pred_out.shape[1] != c.input_dim_pred:
+                raise EchoError(f"backward: d_pred_out {tuple(d_pred_out.shape)}")
+        self._ensure(n, t or 0)   # same tensors as in forward: no rebuild; a rebuilt handle refuses (nothing saved)
+        d_obj = d_pred = None
+        if need_input_grads:
+            d_obj = torch.empty(n, c.input_dim_obj, device=d_obj_out.device)
+            d_pred = torch.empty(g.n_triples, c.input_dim_pred, device=d_obj_out.device)
+        _lib.check(_lib.lib().echo_gcn_train_backward(self._handle, g.h, _lib.ptr(d_obj_out), _lib.ptr(d_pred_out), _lib.ptr(d_obj),
+                                                      _lib.ptr(d_pred), _lib.stream_ptr()))
+        return d_obj, d_pred
+
+
 class FusedAdamW:
     """``optimizerFULL`` of the reference (model/EchoScene.py:130-136: AdamW over the encoders, the layout denoiser and the shape
     denoiser) with the step sequence of scripts/train_3dfront.py:247-259 fused into one pass:

@@ -179,6 +179,26 @@ ECHO_API int echo_gcn_forward_train(echo_gcn_t* h, const echo_graph_t* g, const 
                            float* obj_out, float* pred_out, void* stream);
 ECHO_API void echo_gcn_destroy(echo_gcn_t* h);
 
+/* ---- GraphTripleConvNet, training executor: the forward under model.train() that keeps what the backward needs, and the backward
+ * the reference gets from autograd over model/graph.py:124-211 + model/layers.py:21-38 (loss.backward(), scripts/train_3dfront.py:247).
+ * `params` / `grads`: tables under the GraphTripleConvNet state_dict names ("gconvs.0.net1.0.weight", ...; BatchNorm1d buffers
+ * running_mean / running_var / num_batches_tracked optional in `params`).  The handle keeps the POINTERS: parameters are read in
+ * place on every call (an optimizer step between two iterations needs no rebuild), gradients are ACCUMULATED in place (+=, as
+ * autograd accumulates into .grad), the running statistics are updated by the forward as torch does (momentum 0.1, unbiased
+ * variance).  desc->keep_train_weights is ignored; BatchNorm1d MLPs (mlp_normalization = 'batch') are required.
+ *   forward : obj_vecs (N, din), pred_vecs (T, dp) -> obj_out (N, dout), pred_out (T, dp); T >= 2 and N >= 2 (torch refuses
+ *             BatchNorm1d on a single row in training mode)
+ *   backward: cotangents d_obj_out (N, dout), d_pred_out (T, dp) or NULL (= zeros) -> d_obj_in (N, din) / d_pred_in (T, dp), each
+ *             optional (NULL: not needed); must follow a forward on the same graph.  Deterministic (no float atomics). */
+typedef struct echo_gcn_train echo_gcn_train_t;
+ECHO_API int echo_gcn_train_create(echo_gcn_train_t** out, const echo_gcn_desc_t* desc, const echo_weight_t* params, int32_t n_params,
+                                   const echo_weight_t* grads, int32_t n_grads);
+ECHO_API int echo_gcn_train_forward(echo_gcn_train_t* h, const echo_graph_t* g, const float* obj_vecs, const float* pred_vecs,
+                                    float* obj_out, float* pred_out, void* stream);
+ECHO_API int echo_gcn_train_backward(echo_gcn_train_t* h, const echo_graph_t* g, const float* d_obj_out, const float* d_pred_out,
+                                     float* d_obj_in, float* d_pred_in, void* stream);
+ECHO_API void echo_gcn_train_destroy(echo_gcn_train_t* h);
+
 /* ---- layout branch.
  * echo_layout_forward == UNet1DModel.forward(box_t, obj_embed, triples, timesteps, context) — denoise_net.py:773-806;
  *   box_t (N,8) f32, obj_embed (N,640) f32, timesteps (N,) i64 -> eps (N,8) f32 (the reference returns (N,8,1)).

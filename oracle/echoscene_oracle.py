@@ -43,7 +43,17 @@ def _bn_eval(sd: SD, p: str, x: Tensor, eps: float = 1e-5) -> Tensor:
 
 def _bn_batch(sd: SD, p: str, x: Tensor, eps: float = 1e-5) -> Tensor:
     """BatchNorm1d under model.train(): the statistics of the batch (biased variance), model/layers.py:29-30.  The running
-    statistics' update is a side effect the forward value does not depend on."""
+    statistics' update is a side effect the forward value does not depend on; it is restated when the caller asks for it by
+    putting a dict under ``sd["__running_update__"]`` (torch/nn/modules/batchnorm.py: momentum 0.1, UNBIASED variance,
+    num_batches_tracked += 1)."""
+    track = sd.get("__running_update__")
+    if track is not None:
+        with torch.no_grad():
+            m = 0.1
+            track[p + ".running_mean"] = (1 - m) * sd[p + ".running_mean"] + m * x.detach().mean(0)
+            track[p + ".running_var"] = (1 - m) * sd[p + ".running_var"] + m * x.detach().var(0, unbiased=True)
+            if (p + ".num_batches_tracked") in sd:
+                track[p + ".num_batches_tracked"] = sd[p + ".num_batches_tracked"] + 1
     return F.batch_norm(x, None, None, sd[p + ".weight"], sd[p + ".bias"], True, 0.0, eps)
 
 

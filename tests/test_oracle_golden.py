@@ -143,3 +143,26 @@ def test_gcn_batch_statistics_oracle_matches_the_reference_in_train_mode():
         with torch.no_grad():
             o_obj, o_pred = orc.graph_triple_conv_net(sd, "", obj, pred, edges, batch_stats=True)
         assert torch.equal(o_obj, G[name]["obj"]) and torch.equal(o_pred, G[name]["pred"]), name
+
+
+def test_gcn_backward_oracle_matches_the_reference_autograd():
+    """oracle.gcn_backward (autograd over the oracle's forward restatement) against the reference's GraphTripleConvNet under .train()
+    differentiated by torch autograd (tests/golden/gcn_bwd.pt, oracle/gen_golden_gcn_bwd.py): input gradients, parameter gradients and
+    the BatchNorm1d buffers after the forward."""
+    from oracle import gcn_backward, gen_golden_gcn_bwd as gb
+    G = gold("gcn_bwd.pt")
+    sd = gb.state_dict()
+    for name, n, t, seed, with_pred in gb.CASES:
+        g, obj, pred, d_obj, d_pred = gb.inputs(n, t, seed, with_pred)
+        edges, _ = orc.edges_of(g.triples)
+        o, p, gi, gp, grads, track = gcn_backward.graph_triple_conv_net_backward(sd, obj, pred, edges, d_obj, d_pred, gb.CFG["num_layers"])
+        ref = G[name]
+        assert max(rel_err(o, ref["obj_out"])) < 1e-6 and max(rel_err(gi, ref["d_obj"])) < 1e-6 and max(rel_err(gp, ref["d_pred"])) < 1e-6
+        assert set(grads) == set(ref["grads"]) and set(track) == set(ref["buffers"])
+        for k, want in ref["grads"].items():
+            if float(want.abs().max()) == 0.0:
+                assert float(grads[k].abs().max()) == 0.0, k
+            else:
+                assert max(rel_err(grads[k], want)) < 1e-5, (name, k)
+        for k, want in ref["buffers"].items():
+            assert max(rel_err(track[k].float(), want.float())) < 1e-6, (name, k)
