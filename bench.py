@@ -164,6 +164,41 @@ def optional_figure(fn, *a):
         return {"error": repr(e)[:200]}
 
 
+def layout_batched_rate(dev, scenes=64, steps=20):
+    """Secondary figure (BASELINE config 4's shape on the layout branch): one DDPM step over a collated batch of `scenes` scenes of
+    16 nodes / 64 triples -- more than 64 rows, so every Linear runs as the fp32-grade 3 x TF32 tensor-core GEMM (csrc/sgemm_x3.cu)
+    behind its materialised prologue instead of the weight-streaming few-row kernel; the step is a replayed CUDA graph."""
+    from echoscene_b200 import arch, modules, synth
+    sd = arch.make_state_dict(arch.unet1d_specs(synth.layout_cfg()), synth.WEIGHT_SEED_LAYOUT)
+    m = modules.UNet1DModel(in_channels=8, model_channels=512, out_channels=8, num_res_blocks=2, attention_resolutions=[4, 2],
+                            channel_mult=[1, 1, 1, 1], num_heads=8, use_spatial_transformer=True, concat_dim=1280,
+                            crossattn_dim=1280, enable_t_emb=True, precision="fp32", time_num=1000)
+    m.load_state_dict(sd)
+    m = m.to(dev)
+    g = synth.batch_scene_graphs([synth.make_scene_graph(N_NODES, N_TRIPLES, 2 + i) for i in range(scenes)])
+    n, tri = g.n_nodes, g.triples.to(dev)
+    gen = torch.Generator().manual_seed(5)
+    obj_embed, x = torch.randn(n, 640, generator=gen).to(dev), torch.randn(n, 8, generator=gen).to(dev)
+    noise = torch.randn(steps + 5, n, 8, device=dev)
+    m._ensure(n, tri.shape[0])
+    m.frozen = True
+    for i in range(5):
+        x = m.ddpm_step(x, obj_embed, tri, 999 - i, noise[i])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for i in range(steps):
+        x = m.ddpm_step(x, obj_embed, tri, 994 - i, noise[5 + i])
+    e1.record()
+    torch.cuda.synchronize()
+    m.frozen = False
+    ms = e0.elapsed_time(e1) / steps
+    flops = 2.0 * 115.30e6 * n          # every live parameter is one multiply-add per row
+    return {"scenes": scenes, "nodes": n, "triples": int(tri.shape[0]), "ms_per_batched_step": ms, "value": scenes * 1e3 / ms,
+            "unit": "scene-steps/s", "dtype": "f32 (3 x TF32 split on the tensor cores)", "tflops_algorithmic": flops / (ms * 1e-3) / 1e12,
+            "seconds_per_scene_for_1000_steps": ms / scenes}
+
+
 def scene_encode_time(dev):
     """Secondary figure (the stage right before the two chains): Sg2ScDiffModel.sample's encoders (init_encoder ->
     manipulate -> rel_s_mlp x2) for the 16-node / 64-triple scene as ONE echo_scene_encode call, fp32.  HBM-bound weight
@@ -754,6 +789,7 @@ def main():
         if world == 1:
             # last, and never fatal: a secondary figure must not cost the headline line
             line["scene_encode"] = optional_figure(scene_encode_time, dev)
+            line["layout_branch_batched_64_scenes"] = optional_figure(layout_batched_rate, dev)
             if precision == "bf16":
                 line["parity_mode_x3"] = optional_figure(x3_parity_mode_rate, dev)
                 line["config3_n32_s250"] = optional_figure(config3_rate, dev)

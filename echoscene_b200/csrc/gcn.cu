@@ -17,6 +17,7 @@
 #include "model.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace echo {
 namespace {
@@ -165,9 +166,31 @@ void bn_rows_train(float* x, int64_t ld, int rows, int C, const float* gamma, co
   ECHO_LAUNCH_CHECK();
 }
 
-// Few-row kernel up to 64 rows, tiled SIMT GEMM above (batched scene graphs: hundreds of nodes / thousands of edges).
+// Few-row kernel (HBM-bound on the weights, linear.cu) up to 64 rows.  Above -- collated batches: hundreds of nodes, thousands of
+// edges -- the contraction is compute-bound and runs on the tensor cores at fp32 grade (3 x TF32, sgemm_x3.cu); a prologue
+// (GroupNorm / LayerNorm / GEGLU / SiLU / concat) is first materialised into the caller's scratch rows.  Without scratch, or with
+// bf16 weights, the previous routes remain: the few-row kernel at any M for prologue layers, the SIMT GEMM for plain ones.
 void linear_auto(const LinArgs& a, cudaStream_t s) {
-  if (a.M <= 64 || a.in_act != 0 || a.act == 2 || a.pro != PRO_NONE || a.X2 || a.res2) {
+  if (a.M <= 64) {
+    linear_rows(a, s);
+    return;
+  }
+  const bool plain = a.in_act == 0 && a.pro == PRO_NONE && !a.X2;
+  static const bool no_x3 = getenv("ECHO_NO_X3_LINEAR") != nullptr;
+  if (a.w_dt == F32 && !no_x3 && (plain || (a.scratch && a.scratch_floats >= (size_t)a.M * a.K))) {
+    SgemmX3Args g;
+    g.A = plain ? a.X : a.scratch; g.sam = plain ? a.ldx : a.K; g.sak = 1;
+    g.B = (const float*)a.W; g.sbk = 1; g.sbn = a.ldw ? a.ldw : a.K;
+    g.C = a.Y; g.ldc = a.ldy; g.M = a.M; g.N = a.nout; g.K = a.K;
+    g.bias = a.bias; g.act = a.act; g.res = a.res; g.ld_res = a.ld_res; g.res2 = a.res2; g.ld_res2 = a.ld_res2;
+    if (sgemm_x3_supported(g)) {
+      if (!plain) linear_prologue(a, a.scratch, s);
+      const size_t used = plain ? 0 : ((size_t)a.M * a.K + 3) / 4 * 4;
+      sgemm_x3_auto(g, a.scratch ? a.scratch + used : nullptr, a.scratch ? a.scratch_floats - used : 0, s);
+      return;
+    }
+  }
+  if (!plain || a.act == 2 || a.res2) {
     linear_rows(a, s);
     return;
   }

@@ -344,19 +344,6 @@ __global__ void __launch_bounds__(1024) colsum_acc_kernel(const float* __restric
   }
 }
 
-// out[m, n] = sum over the chunks of a split reduction (in chunk order) + bias[n] + res[m, n]
-__global__ void splitk_out_kernel(const float* __restrict__ ws, int M, int N, int splits, const float* __restrict__ bias,
-                                  const float* __restrict__ res, int64_t ld_res, float* __restrict__ out, int64_t ldo) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, mn = (int64_t)M * N;
-  if (i >= mn) return;
-  const int m = (int)(i / N), n = (int)(i % N);
-  float t = 0.f;
-  for (int b = 0; b < splits; ++b) t += ws[(int64_t)b * mn + i];
-  if (bias) t += bias[n];
-  if (res) t += res[(int64_t)m * ld_res + n];
-  out[(int64_t)m * ldo + n] = t;
-}
-
 // dW += sum over the row chunks of a split wgrad, in chunk order (deterministic)
 __global__ void splitk_acc_kernel(const float* __restrict__ ws, int64_t n, int splits, float* __restrict__ dW) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -586,29 +573,6 @@ void gcn_train_destroy(echo_gcn_train* h) {
 
 // Y = X W^T + b (+ res): up to 64 rows the few-row kernel of the sampling path (linear.cu, HBM-bound on W); beyond, the 3 x TF32
 // tensor-core GEMM (sgemm_x3.cu).
-// C = A B (+ bias) (+ res) on sgemm_x3; when the tile grid would leave most SMs idle (a few hundred rows against a wide reduction) the
-// reduction is split over blockIdx.z into a workspace and summed in chunk order.
-static void gemm_auto(SgemmX3Args g, float* ws, size_t ws_floats, cudaStream_t s) {
-  const int tiles = cdiv(g.M, 128) * cdiv(g.N, 64);
-  const size_t mn = (size_t)g.M * g.N;
-  int splits = std::min({cdiv(148, tiles), g.K / 64, ws ? (int)(ws_floats / mn) : 1, 16});
-  if (splits < 2) {
-    sgemm_x3(g, s);
-    return;
-  }
-  const int chunk = (cdiv(g.K, splits) + 15) & ~15;
-  splits = cdiv(g.K, chunk);
-  SgemmX3Args p = g;
-  p.C = ws; p.ldc = g.N; p.bias = nullptr; p.res = nullptr; p.splits = splits; p.chunk = chunk; p.c_bs = (int64_t)mn;
-  if (splits < 2 || !sgemm_x3_supported(p)) {
-    sgemm_x3(g, s);
-    return;
-  }
-  sgemm_x3(p, s);
-  splitk_out_kernel<<<cdiv((int64_t)mn, 256), 256, 0, s>>>(ws, g.M, g.N, splits, g.bias, g.res, g.ld_res, g.C, g.ldc);
-  ECHO_LAUNCH_CHECK();
-}
-
 static void lin_fwd(const float* X, int64_t ldx, int M, const TLin& l, float* Y, int64_t ldy, const float* res, int64_t ld_res, float* ws,
                     size_t ws_floats, cudaStream_t s) {
   if (M == 0) return;
@@ -617,7 +581,7 @@ static void lin_fwd(const float* X, int64_t ldx, int M, const TLin& l, float* Y,
     g.A = X; g.sam = ldx; g.sak = 1; g.B = l.w; g.sbk = 1; g.sbn = l.K; g.C = Y; g.ldc = ldy; g.M = M; g.N = l.nout; g.K = l.K;
     g.bias = l.b; g.res = res; g.ld_res = ld_res;
     if (sgemm_x3_supported(g)) {
-      gemm_auto(g, ws, ws_floats, s);
+      sgemm_x3_auto(g, ws, ws_floats, s);
       return;
     }
   }
@@ -726,7 +690,7 @@ static void lin_bwd(const float* dY, int64_t ldy, const float* X, int64_t ldx, i
     splitk_acc_kernel<<<cdiv(wn, 256), 256, 0, s>>>(ws, wn, splits, l.gw);
     ECHO_LAUNCH_CHECK();
   }
-  if (dX) gemm_auto(d, ws, ws_floats, s);   // (the workspace is reused in stream order: splitk_acc has consumed it by then)
+  if (dX) sgemm_x3_auto(d, ws, ws_floats, s);   // (the workspace is reused in stream order: splitk_acc has consumed it by then)
 }
 
 static void bn_bwd(const float* da, int64_t ldd, const float* z, int rows, const TBn& b, float* dz, float* part, cudaStream_t s) {

@@ -25,6 +25,8 @@ struct echo_layout {
   Arena arena;
   int prec = ECHO_PREC_FP32;
   bool batch_stats = false;   // box_graph_cov normalises with the statistics of the batch (model.train() forward values)
+  float* lin_scratch[2] = {nullptr, nullptr};   // handles for more than 64 nodes: rows of a Linear's prologue output (linear_auto)
+  size_t lin_scratch_floats = 0;
   ConvW box_emb, time_emb_lin;
   const float* pred_table = nullptr;
   int pred_rows = 0;   // rows of pred_embeddings (16)
@@ -122,6 +124,10 @@ struct echo_layout {
     // against 1.6 ms), and the fp32 loader is the shorter instruction stream -- measured 1.60 ms/step against 1.70 with
     // bf16 weights; it also keeps the layout branch on the 1e-3 parity contract in ECHO_PREC_BF16
     a.W = w.w; a.w_dt = F32;
+    if (lin_scratch[0]) {   // collated batches: the prologue's output rows, one buffer per stream the forward uses
+      a.scratch = lin_scratch[s == side ? 1 : 0];
+      a.scratch_floats = lin_scratch_floats;
+    }
     linear_auto(a, s);
   }
   void lin(const float* X, int64_t ldx, const ConvW& w, float* Y, int64_t ldy, const float* res, int64_t ld_res, int in_act, int act,
@@ -798,6 +804,10 @@ echo_layout* layout_create(const echo_layout_desc_t* desc, const echo_weight_t* 
     h->gcn.create(wm, "box_graph_cov.", gdsc, h->pool);
     make_ddpm_tables(h);
     const size_t N = d.max_nodes, T = gdsc.max_triples;
+    if (N > 64) {   // widest prologue input of this network: the GEGLU product / the skip concatenations / the stacked embeddings
+      h->lin_scratch_floats = N * (4096 + 8192);   // + partial tiles of a split reduction (sgemm_x3_auto)
+      for (int i = 0; i < 2; ++i) h->lin_scratch[i] = h->pool.alloc_n<float>(h->lin_scratch_floats);
+    }
     h->temb = h->pool.alloc_n<float>(N * mc);
     h->e1 = h->pool.alloc_n<float>(N * E);
     h->emb = h->pool.alloc_n<float>(N * E);

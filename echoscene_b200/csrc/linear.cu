@@ -204,6 +204,67 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(const LinArgs a, int k
   }
 }
 
+// The prologue alone, one warp per row: out[m, :] = what linear_rows_kernel feeds its dot products for row m (same expressions in
+// the same order), for the batched path where the contraction runs as a tiled GEMM over the materialised rows.
+template <int PRO>
+__global__ void __launch_bounds__(256) linear_prologue_kernel(const LinArgs a, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, m = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= a.M) return;
+  float ln_mean = 0.f, ln_rstd = 0.f;
+  if (PRO == PRO_LN) {
+    float s = 0.f;
+    for (int k = lane * 4; k < a.K; k += 128) { const float4 x = load_x(a, m, k); s += (x.x + x.y) + (x.z + x.w); }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    ln_mean = s / a.K;
+    float ss = 0.f;
+    for (int k = lane * 4; k < a.K; k += 128) {
+      const float4 x = load_x(a, m, k);
+      const float d0 = x.x - ln_mean, d1 = x.y - ln_mean, d2 = x.z - ln_mean, d3 = x.w - ln_mean;
+      ss += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    ln_rstd = rsqrtf(ss / a.K + a.eps);
+  }
+  for (int kb = 0; kb < a.K; kb += 128) {
+    const int k = kb + lane * 4;
+    const bool kin = k < a.K;
+    float4 gm = make_float4(1.f, 1.f, 1.f, 1.f), bt = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((PRO == PRO_GN || PRO == PRO_LN) && kin) {
+      gm = __ldg(reinterpret_cast<const float4*>(a.gamma + k));
+      bt = __ldg(reinterpret_cast<const float4*>(a.beta + k));
+    }
+    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kin) {
+      xv = load_x(a, m, k);
+      if (PRO == PRO_GEGLU) {
+        const float4 g = *reinterpret_cast<const float4*>(a.X + (int64_t)m * a.ldx + a.K + k);
+        xv.x *= gelu_erf(g.x); xv.y *= gelu_erf(g.y); xv.z *= gelu_erf(g.z); xv.w *= gelu_erf(g.w);
+      }
+    }
+    if (PRO == PRO_SILU) { xv.x = silu_f(xv.x); xv.y = silu_f(xv.y); xv.z = silu_f(xv.z); xv.w = silu_f(xv.w); }
+    if (PRO == PRO_GN) {   // K % 128 == 0: every lane is in range
+      const int gl = a.cpg >> 2;
+      float s = (xv.x + xv.y) + (xv.z + xv.w);
+      for (int o = 1; o < gl; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s / a.cpg;
+      const float d0 = xv.x - mean, d1 = xv.y - mean, d2 = xv.z - mean, d3 = xv.w - mean;
+      float ss = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+      for (int o = 1; o < gl; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float rstd = rsqrtf(ss / a.cpg + a.eps);
+      xv.x = d0 * rstd * gm.x + bt.x; xv.y = d1 * rstd * gm.y + bt.y;
+      xv.z = d2 * rstd * gm.z + bt.z; xv.w = d3 * rstd * gm.w + bt.w;
+      if (a.pro_act) { xv.x = silu_f(xv.x); xv.y = silu_f(xv.y); xv.z = silu_f(xv.z); xv.w = silu_f(xv.w); }
+    }
+    if (PRO == PRO_LN && kin) {
+      xv.x = (xv.x - ln_mean) * ln_rstd * gm.x + bt.x; xv.y = (xv.y - ln_mean) * ln_rstd * gm.y + bt.y;
+      xv.z = (xv.z - ln_mean) * ln_rstd * gm.z + bt.z; xv.w = (xv.w - ln_mean) * ln_rstd * gm.w + bt.w;
+    }
+    if (kin) *reinterpret_cast<float4*>(out + (int64_t)m * a.K + k) = xv;
+  }
+}
+
 template <class TW, int PRO>
 void launch_pro(const LinArgs& a, dim3 grid, int wk, int k_slice, size_t smem, cudaStream_t s) {
   launch_pdl(linear_rows_kernel<TW, PRO>, grid, dim3(32 * wk), smem, s, a, k_slice);
@@ -232,10 +293,7 @@ void launch(const LinArgs& a, cudaStream_t s) {
 
 bool linear_rows_gn_supported(int K, int cpg) { return K % 128 == 0 && (cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32 || cpg == 64 || cpg == 128); }
 
-void linear_rows(const LinArgs& a_in, cudaStream_t s) {
-  if (dbg_skip("linear_rows")) return;
-  LinArgs a = a_in;
-  if (a.in_act == 1 && a.pro == PRO_NONE) a.pro = PRO_SILU;   // legacy spelling
+static void check_lin_args(const LinArgs& a) {
   ECHO_CHECK(a.X && a.W && a.Y, "linear_rows: null operand");
   ECHO_CHECK(a.ldw % 4 == 0, "linear_rows: ldw %% 4");
   ECHO_CHECK(a.K % 4 == 0 && a.ldx % 4 == 0 && ((uintptr_t)a.X % 16) == 0 && ((uintptr_t)a.W % 16) == 0,
@@ -244,6 +302,31 @@ void linear_rows(const LinArgs& a_in, cudaStream_t s) {
                        "linear_rows: bad concat input");
   if (a.pro == PRO_GN) ECHO_CHECK(a.gamma && a.beta && linear_rows_gn_supported(a.K, a.cpg), "linear_rows: GroupNorm prologue needs K %% 128 == 0 and a power-of-two group of >= 4 channels (K=%d cpg=%d)", a.K, a.cpg);
   if (a.pro == PRO_LN) ECHO_CHECK(a.gamma && a.beta, "linear_rows: LayerNorm prologue needs gamma/beta");
+}
+
+void linear_prologue(const LinArgs& a_in, float* out, cudaStream_t s) {
+  LinArgs a = a_in;
+  if (a.in_act == 1 && a.pro == PRO_NONE) a.pro = PRO_SILU;
+  ECHO_CHECK(out && ((uintptr_t)out % 16) == 0, "linear_prologue: null / unaligned output");
+  check_lin_args(a);
+  if (a.M == 0) return;
+  const dim3 grid(cdiv(a.M, 8));
+  switch (a.pro) {
+    case PRO_NONE: linear_prologue_kernel<PRO_NONE><<<grid, 256, 0, s>>>(a, out); break;   // (a concat of X and X2)
+    case PRO_SILU: linear_prologue_kernel<PRO_SILU><<<grid, 256, 0, s>>>(a, out); break;
+    case PRO_GN: linear_prologue_kernel<PRO_GN><<<grid, 256, 0, s>>>(a, out); break;
+    case PRO_LN: linear_prologue_kernel<PRO_LN><<<grid, 256, 0, s>>>(a, out); break;
+    case PRO_GEGLU: linear_prologue_kernel<PRO_GEGLU><<<grid, 256, 0, s>>>(a, out); break;
+    default: fail(ECHO_ERR_INVALID, "linear_prologue: unknown prologue %d", a.pro);
+  }
+  ECHO_LAUNCH_CHECK();
+}
+
+void linear_rows(const LinArgs& a_in, cudaStream_t s) {
+  if (dbg_skip("linear_rows")) return;
+  LinArgs a = a_in;
+  if (a.in_act == 1 && a.pro == PRO_NONE) a.pro = PRO_SILU;   // legacy spelling
+  check_lin_args(a);
   if (a.M == 0) return;
   ECHO_CHECK(cdiv(a.M, 8) <= 65535, "linear_rows: too many rows");
   if (a.w_dt == F32) launch<float>(a, s);

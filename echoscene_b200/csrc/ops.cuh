@@ -111,8 +111,16 @@ struct LinArgs {
   int64_t ldy = 0;
   int in_act = 0;              // 0 none, 1 SiLU applied to X on load
   int act = 0;                 // 0 none, 1 relu, 2 silu (before res)
+  // linear_auto, more than 64 rows (collated batches): room for the prologue's output [M, K] (after which the contraction runs as a
+  // tensor-core GEMM; without it a layer with a prologue stays on the few-row kernel at any M) and, behind it, for the partial tiles
+  // of a split reduction
+  float* scratch = nullptr;
+  size_t scratch_floats = 0;
 };
 void linear_rows(const LinArgs& a, cudaStream_t s);
+// out[m, :] = the input row of the Linear after its prologue (SiLU / GroupNorm(+SiLU) / LayerNorm / GEGLU, concat of X and X2), the
+// arithmetic of linear_rows_kernel; out is dense [M, K]
+void linear_prologue(const LinArgs& a, float* out, cudaStream_t s);
 
 // fp32-grade GEMM on the tensor cores (3 x TF32 split, sgemm_x3.cu): C[m, n] = sum_k A(m, k) B(k, n) (+ bias[n]) (+ res[m, n]),
 // A(m, k) = A[m * sam + k * sak], B(k, n) = B[k * sbk + n * sbn]; one stride of each operand must be 1.
@@ -127,12 +135,16 @@ struct SgemmX3Args {
   const float* bias = nullptr;
   const float* res = nullptr;   // may alias C (accumulate in place)
   int64_t ld_res = 0;
+  int act = 0;                  // 0 none, 1 relu, 2 silu: applied after the bias, before res / res2 (LinArgs order)
+  const float* res2 = nullptr;
+  int64_t ld_res2 = 0;
   // split reduction: slice z of `splits` covers k in [z * chunk, min(K, (z + 1) * chunk)) and writes C + z * c_bs (no bias / res then)
   int splits = 1, chunk = 0;
   int64_t c_bs = 0;
 };
 bool sgemm_x3_supported(const SgemmX3Args& g);
 void sgemm_x3(const SgemmX3Args& g, cudaStream_t s);
+void sgemm_x3_auto(const SgemmX3Args& g, float* ws, size_t ws_floats, cudaStream_t s);   // splits the reduction when the grid is small
 bool linear_rows_gn_supported(int K, int cpg);
 
 // ---------------------------------------------------------------------------------------------------------------

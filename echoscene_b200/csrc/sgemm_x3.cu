@@ -13,6 +13,8 @@
 // whichever operand dimension is contiguous).
 #include "ops.cuh"
 
+#include <algorithm>
+
 namespace echo {
 namespace {
 
@@ -137,13 +139,36 @@ __global__ void __launch_bounds__(XT) sgemm_x3_kernel(const SgemmX3Args g) {
         if (n >= g.N) continue;
         float2 v = make_float2(acc[mt][nt][half * 2] + acs[mt][nt][half * 2], acc[mt][nt][half * 2 + 1] + acs[mt][nt][half * 2 + 1]);
         if (g.bias) { v.x += __ldg(g.bias + n); v.y += __ldg(g.bias + n + 1); }
+        if (g.act == 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+        else if (g.act == 2) { v.x = v.x / (1.f + expf(-v.x)); v.y = v.y / (1.f + expf(-v.y)); }
         if (g.res) {
           const float2 r = *reinterpret_cast<const float2*>(g.res + (int64_t)m * g.ld_res + n);
+          v.x += r.x; v.y += r.y;
+        }
+        if (g.res2) {
+          const float2 r = *reinterpret_cast<const float2*>(g.res2 + (int64_t)m * g.ld_res2 + n);
           v.x += r.x; v.y += r.y;
         }
         *reinterpret_cast<float2*>(C + (int64_t)m * g.ldc + n) = v;
       }
     }
+}
+
+// out[m, n] = epilogue(sum over the chunks of a split reduction, in chunk order)
+__global__ void sgemm_x3_splitk_out_kernel(const float* __restrict__ ws, int M, int N, int splits, const float* __restrict__ bias, int act,
+                                           const float* __restrict__ res, int64_t ld_res, const float* __restrict__ res2, int64_t ld_res2,
+                                           float* out, int64_t ldo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, mn = (int64_t)M * N;
+  if (i >= mn) return;
+  const int m = (int)(i / N), n = (int)(i % N);
+  float t = 0.f;
+  for (int b = 0; b < splits; ++b) t += ws[(int64_t)b * mn + i];
+  if (bias) t += __ldg(bias + n);
+  if (act == 1) t = fmaxf(t, 0.f);
+  else if (act == 2) t = t / (1.f + expf(-t));
+  if (res) t += res[(int64_t)m * ld_res + n];
+  if (res2) t += res2[(int64_t)m * ld_res2 + n];
+  out[(int64_t)m * ldo + n] = t;
 }
 
 }  // namespace
@@ -152,8 +177,10 @@ bool sgemm_x3_supported(const SgemmX3Args& g) {
   const bool a_kc = g.sak == 1, a_mc = g.sam == 1, b_nc = g.sbn == 1, b_kc = g.sbk == 1;
   if (!(a_kc || a_mc) || !(b_nc || b_kc)) return false;
   auto al16 = [](const void* p) { return ((uintptr_t)p % 16) == 0; };
-  if (!al16(g.A) || !al16(g.B) || ((uintptr_t)g.C % 8) || (g.res && ((uintptr_t)g.res % 8))) return false;
-  if ((a_kc ? g.sam : g.sak) % 4 || (b_nc ? g.sbk : g.sbn) % 4 || g.ldc % 2 || g.c_bs % 2 || (g.res && g.ld_res % 2)) return false;
+  if (!al16(g.A) || !al16(g.B) || ((uintptr_t)g.C % 8) || (g.res && ((uintptr_t)g.res % 8)) || (g.res2 && ((uintptr_t)g.res2 % 8))) return false;
+  if ((a_kc ? g.sam : g.sak) % 4 || (b_nc ? g.sbk : g.sbn) % 4 || g.ldc % 2 || g.c_bs % 2 || (g.res && g.ld_res % 2) ||
+      (g.res2 && g.ld_res2 % 2)) return false;
+  if (g.splits > 1 && (g.bias || g.res || g.res2 || g.act)) return false;
   // the contiguous extent must be a multiple of the float4 a thread moves; a split reduction needs chunks of whole k-tiles
   if (a_kc ? g.K % 4 : g.M % 4) return false;
   if (b_nc ? g.N % 4 : g.K % 4) return false;
@@ -176,6 +203,30 @@ void sgemm_x3(const SgemmX3Args& a, cudaStream_t s) {
   else if (b_nc) sgemm_x3_kernel<false, true><<<grid, XT, 0, s>>>(g);
   else sgemm_x3_kernel<false, false><<<grid, XT, 0, s>>>(g);
   ECHO_LAUNCH_CHECK();
+}
+
+// sgemm_x3 with the reduction split over blockIdx.z whenever the tile grid would leave most SMs idle (a few hundred rows against a
+// wide reduction) and `ws` has room for the partial tiles; the partials are summed in chunk order, then the epilogue is applied.
+void sgemm_x3_auto(const SgemmX3Args& g, float* ws, size_t ws_floats, cudaStream_t s) {
+  if (g.M == 0 || g.N == 0) return;
+  const int tiles = cdiv(g.M, XM) * cdiv(g.N, XN);
+  const size_t mn = (size_t)g.M * g.N;
+  int splits = std::min({cdiv(148, tiles), g.K / 64, ws ? (int)(ws_floats / mn) : 1, 16});
+  if (splits >= 2) {
+    const int chunk = (cdiv(g.K, splits) + XK - 1) / XK * XK;
+    splits = cdiv(g.K, chunk);
+    SgemmX3Args p = g;
+    p.C = ws; p.ldc = g.N; p.bias = nullptr; p.res = nullptr; p.res2 = nullptr; p.act = 0; p.splits = splits; p.chunk = chunk;
+    p.c_bs = (int64_t)mn;
+    if (splits >= 2 && sgemm_x3_supported(p)) {
+      sgemm_x3(p, s);
+      sgemm_x3_splitk_out_kernel<<<cdiv((int64_t)mn, 256), 256, 0, s>>>(ws, g.M, g.N, splits, g.bias, g.act, g.res, g.ld_res, g.res2, g.ld_res2,
+                                                                        g.C, g.ldc);
+      ECHO_LAUNCH_CHECK();
+      return;
+    }
+  }
+  sgemm_x3(g, s);
 }
 
 }  // namespace echo

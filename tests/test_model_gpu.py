@@ -148,6 +148,29 @@ def test_layout_batched_scenes_are_independent(layout_sd):
     assert_close(full[8:], c, 1e-5, "scene 1")
 
 
+def test_layout_large_batch_runs_on_the_tensor_core_path_and_equals_its_scenes(layout_sd):
+    """Six scenes collated (96 nodes, 384 triples: more than 64 rows, so every Linear's prologue is materialised and the contraction
+    runs as the 3 x TF32 tensor-core GEMM, csrc/sgemm_x3.cu) against the same scenes one by one on the few-row path, which is the
+    path pinned to the oracle: the forward, and a DDPM step through the replayed graph."""
+    m = layout_model(layout_sd)
+    gs = [synth.make_scene_graph(16, 64, 60 + i) for i in range(6)]
+    ins = [synth.layout_inputs(16, 70 + i) for i in range(6)]
+    b = synth.batch_scene_graphs(gs)
+    obj = torch.cat([i[0] for i in ins]).to(DEV)
+    x = torch.cat([i[1] for i in ins]).to(DEV)
+    ts = torch.cat([torch.full((16,), 100 + 150 * i) for i in range(6)]).to(DEV)
+    full = m(x, obj, b.triples.to(DEV), ts)
+    noise = torch.randn(96, 8, generator=torch.Generator().manual_seed(3)).to(DEV)
+    step = m.ddpm_step(x, obj, b.triples.to(DEV), 321, noise)
+    step2 = m.ddpm_step(x, obj, b.triples.to(DEV), 321, noise)               # second call: the replayed graph
+    assert torch.equal(step, step2)
+    for i, g in enumerate(gs):
+        r = slice(16 * i, 16 * i + 16)
+        one = m(x[r], obj[r], g.triples.to(DEV), ts[r])
+        assert_close(full[r], one, 1e-4, f"forward, scene {i}")
+        assert_close(step[r], m.ddpm_step(x[r], obj[r], g.triples.to(DEV), 321, noise[r]), 1e-4, f"DDPM step, scene {i}")
+
+
 # -------------------------------------------------------------------------------------------------------------- shape
 def test_shape_step_vs_reference_golden(shape_sd):
     cfg = cases.shape_cfg()
