@@ -33,7 +33,7 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 // A_KC: A's reduction index is the contiguous one (row-major [M, K]); else its row index is (A read transposed).
 // B_NC: B's column index is contiguous (row-major [K, N]); else its reduction index is (B = W^T of a row-major [N, K] weight).
 template <bool A_KC, bool B_NC>
-__global__ void __launch_bounds__(XT) sgemm_x3_kernel(const SgemmX3Args g) {
+__global__ void __launch_bounds__(XT, 2) sgemm_x3_kernel(const SgemmX3Args g) {
   __shared__ __align__(16) float As[XK][XA_LD];
   __shared__ __align__(16) float Bs[XK][XB_LD];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
