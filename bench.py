@@ -807,6 +807,18 @@ def main():
                 extra["strong_scaling_one_scene"] = {"error": repr(e)[:200]}
     if rank == 0:
         line.update(extra)
+        try:   # derived: the three chains of a scene when scenes are sampled as collated batches (sample_scenes), per GPU
+            lb, c4, dec = line["layout_branch_batched_64_scenes"], extra["config4_scene_sharded"], line["vqvae_decode"]
+            per_rank = c4["scenes_per_rank"]
+            line["full_chain_seconds_per_scene_batched"] = {
+                "layout_1000_ddpm_steps_64_scene_batches": lb["seconds_per_scene_for_1000_steps"],
+                "shape_100_ddim_steps_8_scene_batches": c4["ms_per_batched_step"] * 1e-3 * DDIM_STEPS / per_rank,
+                "vqvae_decode": dec["ms_per_scene"] * 1e-3,
+                "total": lb["seconds_per_scene_for_1000_steps"] + c4["ms_per_batched_step"] * 1e-3 * DDIM_STEPS / per_rank
+                         + dec["ms_per_scene"] * 1e-3,
+                "note": "derived from layout_branch_batched_64_scenes, config4_scene_sharded and vqvae_decode of this run"}
+        except (KeyError, TypeError):
+            pass
         print(json.dumps(line))
     sys.stdout.flush()
     if world > 1:
