@@ -1,6 +1,5 @@
 """Forward + backward of box_graph_cov (the layout denoiser's GraphTripleConvNet, 5 layers, config/full_mp.yaml widths) in training
-mode on a collated batch: the reference module under torch autograd (eager, TF32 off, baseline/_ref when present, else the oracle's
-restatement) against train.GraphTripleConvNetTrainer on the same GPU.  MEASUREMENT INFRASTRUCTURE.
+mode on a collated batch: the reference module under torch autograd (eager, TF32 off, baseline/_ref) against train.GraphTripleConvNetTrainer on the same GPU.  MEASUREMENT INFRASTRUCTURE.
 
   python tools/time_gcn_train.py [--scenes 64] [--out gpurun_out/gcn_train_timing.json]"""
 from __future__ import annotations
@@ -20,16 +19,15 @@ def main(a):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     from echoscene_b200 import arch, modules, synth, train
-    from oracle import cases, echoscene_oracle as orc
     dev = "cuda"
-    gcfg = cases.layout_cfg().gcn()
-    sd = arch.make_state_dict(arch.gcn_specs(gcfg), cases.WEIGHT_SEED_GCN)
+    gcfg = synth.layout_cfg().gcn()
+    sd = arch.make_state_dict(arch.gcn_specs(gcfg), synth.WEIGHT_SEED_GCN)
     g = synth.batch_scene_graphs([synth.make_scene_graph(8 + i % 9, 24 + 4 * (i % 9), 50 + i) for i in range(a.scenes)])
     gen = torch.Generator().manual_seed(8)
     n, t = g.n_nodes, g.triples.shape[0]
     obj, pred = torch.randn(n, gcfg.input_dim_obj, generator=gen).to(dev), torch.randn(t, gcfg.input_dim_pred, generator=gen).to(dev)
     d_obj, d_pred = torch.randn(n, gcfg.output_dim, generator=gen).to(dev), torch.randn(t, gcfg.input_dim_pred, generator=gen).to(dev)
-    edges = orc.edges_of(g.triples)[0].to(dev)
+    edges = torch.stack([g.triples[:, 0], g.triples[:, 2]], dim=1).to(dev)
 
     def timed(fn, reps):
         for _ in range(3):
@@ -44,30 +42,21 @@ def main(a):
         return e0.elapsed_time(e1) / reps
 
     # reference arm
-    kind = "oracle restatement (torch autograd)"
-    ref_net = None
-    if os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "model")):
-        from baseline import ref_runner
-        ref = ref_runner.load_reference()
-        Net = getattr(ref, "GraphTripleConvNet", None)
-        if Net is not None:
-            ref_net = Net(input_dim_obj=gcfg.input_dim_obj, input_dim_pred=gcfg.input_dim_pred, num_layers=gcfg.num_layers,
-                          hidden_dim=gcfg.hidden_dim, residual=True, pooling="avg", mlp_normalization="batch", output_dim=gcfg.output_dim)
-            ref_net.load_state_dict(sd, strict=True)
-            ref_net = ref_net.to(dev).train()
-            kind = "baseline/_ref GraphTripleConvNet under .train(), torch autograd, eager fp32"
-    if ref_net is None:
-        leaf = {k: (v.to(dev).requires_grad_(v.is_floating_point() and "running" not in k)) for k, v in sd.items()}
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "model")):
+        raise SystemExit("baseline/_ref is not installed (python baseline/install_ref.py in the build container): no reference arm")
+    from baseline import ref_runner
+    ref = ref_runner.load_reference()
+    ref_net = ref.GraphTripleConvNet(input_dim_obj=gcfg.input_dim_obj, input_dim_pred=gcfg.input_dim_pred, num_layers=gcfg.num_layers,
+                                     hidden_dim=gcfg.hidden_dim, residual=True, pooling="avg", mlp_normalization="batch",
+                                     output_dim=gcfg.output_dim)
+    ref_net.load_state_dict(sd, strict=True)
+    ref_net = ref_net.to(dev).train()
+    kind = "baseline/_ref GraphTripleConvNet under .train(), torch autograd, eager fp32"
 
     def ref_step():
         o, p = obj.clone().requires_grad_(True), pred.clone().requires_grad_(True)
-        if ref_net is not None:
-            ref_net.zero_grad(set_to_none=True)
-            ro, rp = ref_net(o, p, edges)
-        else:
-            for v in leaf.values():
-                v.grad = None
-            ro, rp = orc.graph_triple_conv_net(leaf, "", o, p, edges, num_layers=gcfg.num_layers, batch_stats=True)
+        ref_net.zero_grad(set_to_none=True)
+        ro, rp = ref_net(o, p, edges)
         ((ro * d_obj).sum() + (rp * d_pred).sum()).backward()
 
     m = modules.GraphTripleConvNet(gcfg.input_dim_obj, gcfg.input_dim_pred, num_layers=gcfg.num_layers, hidden_dim=gcfg.hidden_dim,
