@@ -24,6 +24,34 @@ def inputs(n, t, seed, cfg):
     return g, torch.randn(g.n_nodes, cfg.input_dim_obj, generator=gen), torch.randn(g.triples.shape[0], cfg.input_dim_pred, generator=gen)
 
 
+def tables_main():
+    """The q_sample / loss tables the two branches build for TRAINING, from the reference's own constructors: GaussianDiffusion.__init__
+    (diffusion_ddpm.py:119-166, through DiffusionPoint with a stub denoiser) and EchoToShape.register_schedule (echo2shape.py:173-226,
+    called unbound on a bare namespace: it only reads device / v_posterior / parameterization).  -> tests/golden/train_tables.pt, pins
+    echoscene_b200.train.layout_train_tables / shape_train_tables bit for bit."""
+    import importlib
+    import types
+    from echoscene_b200 import train
+    ref = ref_import.load()
+    dp = ref.DiffusionPoint(torch.nn.Identity(), config={}, schedule_type="linear", beta_start=1e-4, beta_end=0.02, time_num=1000,
+                            loss_type="mse", model_mean_type="eps", model_var_type="fixedsmall", loss_separate=True, loss_iou=False,
+                            iou_type="obb", train_stats_file=None)
+    g = dp.diffusion
+    e2s = importlib.import_module("model.networks.diffusion_shape.echo2shape")
+    ns = types.SimpleNamespace(device="cpu", v_posterior=0.0, parameterization="eps")
+    e2s.EchoToShape.register_schedule(ns, timesteps=1000, linear_start=0.00085, linear_end=0.012)
+    out = {"layout": {"sqrt_alphas_cumprod": g.sqrt_alphas_cumprod.clone(), "sqrt_one_minus_alphas_cumprod": g.sqrt_one_minus_alphas_cumprod.clone()},
+           "shape": {"sqrt_alphas_cumprod": ns.sqrt_alphas_cumprod.clone(), "sqrt_one_minus_alphas_cumprod": ns.sqrt_one_minus_alphas_cumprod.clone(),
+                     "lvlb_weights": ns.lvlb_weights.clone()}}
+    a, b = train.layout_train_tables(1000, 1e-4, 0.02)
+    t = train.shape_train_tables(1000, 0.00085, 0.012)
+    ok = (torch.equal(a, out["layout"]["sqrt_alphas_cumprod"]) and torch.equal(b, out["layout"]["sqrt_one_minus_alphas_cumprod"])
+          and all(torch.equal(t[k], v) for k, v in out["shape"].items()))
+    torch.save(out, os.path.join(ROOT, "tests", "golden", "train_tables.pt"))
+    print(f"training tables (layout q_sample, shape q_sample + lvlb_weights): bit-equal to the reference's constructors: {ok}")
+    assert ok
+
+
 def main():
     ref = ref_import.load()
     gcfg = cases.layout_cfg().gcn()
@@ -45,6 +73,7 @@ def main():
         assert float((r_obj - e_obj).abs().max()) > 1e-2, "batch statistics must change the result (else the case is vacuous)"
         out[name] = {"obj": r_obj, "pred": r_pred}
     torch.save(out, os.path.join(ROOT, "tests", "golden", "gcn_train.pt"))
+    tables_main()
     print(f"GraphTripleConvNet under .train(): oracle(batch_stats=True) vs reference max-abs {worst:.3e} over {len(TRAIN_CASES)} cases")
 
 

@@ -52,3 +52,19 @@ def test_schedule_entry_points_reject_bad_arguments():
                                       C.byref(n)) == -1 and b"capacity" in L.echo_last_error()
     assert L.echo_debug_ddim_schedule(10, 100, 0.00085, 0.012, 2, buf.ctypes.data_as(C.c_void_p), ts.ctypes.data_as(C.c_void_p),
                                       C.byref(n)) == -1
+
+
+def test_training_tables_are_bit_equal_to_the_reference_constructors():
+    """train.layout_train_tables / shape_train_tables (the q_sample factors of both branches and the shape branch's lvlb_weights)
+    against the tensors the reference's own constructors build -- GaussianDiffusion.__init__ and EchoToShape.register_schedule, run by
+    oracle/gen_golden_train.py in the build container (tests/golden/train_tables.pt).  Host arithmetic (float64 rounded to fp32 where
+    the reference rounds): bit for bit."""
+    import os
+    from echoscene_b200 import train
+    G = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_tables.pt"), map_location="cpu")
+    a, b = train.layout_train_tables(1000, 1e-4, 0.02)
+    assert torch.equal(a, G["layout"]["sqrt_alphas_cumprod"]) and torch.equal(b, G["layout"]["sqrt_one_minus_alphas_cumprod"])
+    t = train.shape_train_tables(1000, 0.00085, 0.012)
+    for k, v in G["shape"].items():
+        assert torch.equal(t[k], v), k
+    assert torch.equal(t["logvar"], torch.zeros(1000)) and float(t["lvlb_weights"][0]) == float(t["lvlb_weights"][1])
