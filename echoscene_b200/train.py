@@ -188,6 +188,44 @@ class GraphTripleConvNetTrainer:
                                                      _lib.ptr(pred_out), _lib.stream_ptr()))
         return obj_out, pred_out
 
+    def capture(self, obj_vecs, pred_vecs, edges, d_obj_out, d_pred_out=None):
+        """One training iteration -- forward + backward on fixed-size inputs -- as ONE replayed CUDA graph (the ~300 launches of an
+        iteration are launch-bound for a single scene).  The four tensors are copied into static buffers owned by the returned
+        object; ``replay(obj_vecs, pred_vecs, d_obj_out, d_pred_out)`` copies new values in and replays; its results
+        (``obj_out, pred_out, d_obj, d_pred``) are static tensors overwritten by the next replay.  Gradients accumulate into ``.grad``
+        exactly as with ``forward`` / ``backward``; the graph topology (``edges``) is fixed."""
+        _lib.require_cuda(obj_vecs, pred_vecs, edges, d_obj_out, d_pred_out)
+        trainer = self
+
+        class Iteration:
+            def __init__(it):
+                it.obj, it.pred = obj_vecs.float().contiguous().clone(), pred_vecs.float().contiguous().clone()
+                it.d_obj = d_obj_out.float().contiguous().clone()
+                it.d_pred = None if d_pred_out is None else d_pred_out.float().contiguous().clone()
+                it.edges = edges.contiguous().clone()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):            # warm-up outside the capture: handle, graph CSR, lazy module loads
+                    for _ in range(2):
+                        trainer.forward(it.obj, it.pred, it.edges)
+                        trainer.backward(it.d_obj, it.d_pred)
+                torch.cuda.current_stream().wait_stream(side)
+                trainer.zero_grad()
+                it.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(it.graph):
+                    it.obj_out, it.pred_out = trainer.forward(it.obj, it.pred, it.edges)
+                    it.d_obj_in, it.d_pred_in = trainer.backward(it.d_obj, it.d_pred)
+                trainer.zero_grad()                      # (capturing does not execute: nothing was accumulated, keep it explicit)
+
+            def replay(it, obj=None, pred=None, d_obj=None, d_pred=None):
+                for dst, src in ((it.obj, obj), (it.pred, pred), (it.d_obj, d_obj), (it.d_pred, d_pred)):
+                    if src is not None:
+                        dst.copy_(src)
+                it.graph.replay()
+                return it.obj_out, it.pred_out, it.d_obj_in, it.d_pred_in
+
+        return Iteration()
+
     @torch.no_grad()
     def backward(self, d_obj_out, d_pred_out=None, need_input_grads: bool = True):
         """cotangents of ``forward``'s two outputs (``d_pred_out`` None = zeros) -> (d_obj_vecs, d_pred_vecs) (None, None when

@@ -217,6 +217,39 @@ def test_gcn_backward_accumulates_is_deterministic_and_reads_parameters_in_place
         tr.forward(args[0][:1], args[1][:1], torch.zeros(1, 2, dtype=torch.int64, device=DEV))
 
 
+def test_gcn_training_iteration_as_one_cuda_graph():
+    """capture(): forward + backward replayed as one CUDA graph give bit-identical outputs and gradients to the launch-by-launch
+    calls, and follow new input values copied into the static buffers."""
+    from oracle import echoscene_oracle as orc
+    m, gb = _gcn_bwd_module()
+    name, n, t, seed, _ = gb.CASES[0]
+    tr = train.GraphTripleConvNetTrainer(m, max_nodes=n, max_triples=t)
+    g, obj, pred, d_obj, d_pred = gb.inputs(n, t, seed, True)
+    edges = orc.edges_of(g.triples)[0].to(DEV)
+    obj, pred, d_obj, d_pred = obj.to(DEV), pred.to(DEV), d_obj.to(DEV), d_pred.to(DEV)
+    bufs0 = {k: v.clone() for k, v in m.named_buffers()}
+    o, p = tr.forward(obj, pred, edges)
+    gi, gp = tr.backward(d_obj, d_pred)
+    want = {k: q.grad.clone() for k, q in m.named_parameters()}
+    bufs1 = {k: v.clone() for k, v in m.named_buffers()}
+    for k, v in m.named_buffers():
+        v.copy_(bufs0[k])
+    it = tr.capture(obj, pred, edges, d_obj, d_pred)
+    for k, v in m.named_buffers():            # the warm-up iterations of capture() advanced the running statistics
+        v.copy_(bufs0[k])
+    tr.zero_grad()
+    o2, p2, gi2, gp2 = it.replay()
+    assert torch.equal(o, o2) and torch.equal(p, p2) and torch.equal(gi, gi2) and torch.equal(gp, gp2)
+    for k, q in m.named_parameters():
+        assert torch.equal(q.grad, want[k]), k
+    for k, v in m.named_buffers():
+        assert torch.equal(v, bufs1[k]), k
+    tr.zero_grad()
+    o3, _, gi3, _ = it.replay(obj=2 * obj, d_obj=-d_obj)       # new values through the static buffers
+    o4, _ = tr.forward(2 * obj, pred, edges)
+    assert torch.equal(o3, o4) and not torch.equal(o3, o)
+
+
 def test_gcn_backward_many_rows_two_stage_kernels():
     """A collated batch of 70 scenes (560 nodes, 2240 triples) at the golden case's small widths: the row counts at which BatchNorm runs
     as two-stage kernels (partials per 256-row block, merged in block order) and the weight gradient's reduction is split into chunks,

@@ -82,9 +82,17 @@ def main(a):
         torch.cuda.profiler.stop()
         return
     r_ms, m_ms, f_ms = timed(ref_step, a.reps), timed(my_step, a.reps), timed(my_fwd, a.reps)
+    it = tr.capture(obj, pred, edges, d_obj, d_pred)
+
+    def graph_step():
+        tr.zero_grad()
+        it.replay()
+
+    g_ms = timed(graph_step, a.reps)
     params = sum(p.numel() for p in m.parameters())
     res = {"scenes": a.scenes, "nodes": n, "triples": t, "parameters": params, "reference": kind, "reference_ms_fwd_bwd": r_ms,
-           "b200_ms_fwd_bwd": m_ms, "b200_ms_fwd": f_ms, "speedup": r_ms / m_ms,
+           "b200_ms_fwd_bwd": m_ms, "b200_ms_fwd": f_ms, "speedup": r_ms / m_ms, "b200_ms_fwd_bwd_cuda_graph": g_ms,
+           "speedup_cuda_graph": r_ms / g_ms,
            "param_plus_grad_bytes_per_step": 3 * 4 * params,
            "hbm_gbs_on_params_and_grads": 3 * 4 * params / (m_ms * 1e-3) / 1e9}
     print(json.dumps(res, indent=1))
