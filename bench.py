@@ -199,6 +199,27 @@ def layout_batched_rate(dev, scenes=64, steps=20):
             "seconds_per_scene_for_1000_steps": ms / scenes}
 
 
+def sdf_to_mesh_time(dev, objects=16, R=64):
+    """Secondary figure (the stage after the decode): mesh.sdf_to_mesh over the scene's 16 decoded SDFs -- marching cubes
+    at level 0.02 on the GPU (the reference runs PyMCubes per object on the CPU; it is not available here, so there is no reference
+    time next to this one).  Synthetic SDFs: truncated spheres of growing radius."""
+    from echoscene_b200 import mesh
+    g = torch.stack(torch.meshgrid(*[torch.arange(R, dtype=torch.float32)] * 3, indexing="ij"), -1) / R - 0.5
+    sdf = torch.stack([(g - torch.tensor([0.01 * i, 0.0, 0.0])).norm(dim=-1) - 0.2 - 0.005 * i for i in range(objects)])
+    sdf = sdf.clamp(-0.2, 0.2)[:, None].to(dev)
+    for _ in range(2):
+        out = mesh.sdf_to_mesh(sdf)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(5):
+        out = mesh.sdf_to_mesh(sdf)
+    e1.record()
+    torch.cuda.synchronize()
+    return {"ms_per_scene": e0.elapsed_time(e1) / 5, "objects": objects, "resolution": R, "vertices": int(sum(len(v) for v in out[0])),
+            "triangles": int(sum(len(f) for f in out[1])), "unit": "ms per 16-object scene (two library calls and one 8-byte host read per object)"}
+
+
 def scene_encode_time(dev):
     """Secondary figure (the stage right before the two chains): Sg2ScDiffModel.sample's encoders (init_encoder ->
     manipulate -> rel_s_mlp x2) for the 16-node / 64-triple scene as ONE echo_scene_encode call, fp32.  HBM-bound weight
@@ -790,6 +811,7 @@ def main():
             # last, and never fatal: a secondary figure must not cost the headline line
             line["scene_encode"] = optional_figure(scene_encode_time, dev)
             line["layout_branch_batched_64_scenes"] = optional_figure(layout_batched_rate, dev)
+            line["sdf_to_mesh"] = optional_figure(sdf_to_mesh_time, dev)
             if precision == "bf16":
                 line["parity_mode_x3"] = optional_figure(x3_parity_mode_rate, dev)
                 line["config3_n32_s250"] = optional_figure(config3_rate, dev)

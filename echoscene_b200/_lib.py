@@ -114,6 +114,8 @@ PROTOTYPES = {
     "echo_gcn_train_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "echo_gcn_train_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "echo_gcn_train_destroy": (None, [_P]),
+    "echo_mesh_workspace_bytes": (C.c_int64, [_I]),
+    "echo_mesh_marching_cubes": (C.c_int, [_P, _I, C.c_float, _P, _L, _P, _L, _P, _P, _L, _P]),
     "echo_layout_set_batch_stats": (C.c_int, [_P, _I]),
     "echo_shape_set_batch_stats": (C.c_int, [_P, _I]),
     "echo_scene_set_batch_stats": (C.c_int, [_P, _I]),

@@ -27,6 +27,8 @@ void shape_destroy(echo_shape*);
 void shape_forward(echo_shape*, const echo_graph*, const float*, const float*, const int64_t*, float*, cudaStream_t);
 void shape_set_index(echo_shape*, int, cudaStream_t);
 void shape_set_batch_stats(echo_shape*, bool);
+size_t mesh_workspace_bytes(int R);
+void mesh_marching_cubes(const float*, int, float, float*, int64_t, int*, int64_t, int*, void*, size_t, cudaStream_t);
 echo_gcn_train* gcn_train_create(const echo_gcn_desc_t*, const echo_weight_t*, int, const echo_weight_t*, int);
 void gcn_train_forward(echo_gcn_train*, const echo_graph*, const float*, const float*, float*, float*, cudaStream_t);
 void gcn_train_backward(echo_gcn_train*, const echo_graph*, const float*, const float*, float*, float*, cudaStream_t);
@@ -447,6 +449,14 @@ int echo_gcn_train_backward(echo_gcn_train_t* h, const echo_graph_t* g, const fl
   return guard([&] { gcn_train_backward(h, g, d_obj_out, d_pred_out, d_obj_in, d_pred_in, (cudaStream_t)stream); });
 }
 void echo_gcn_train_destroy(echo_gcn_train_t* h) { gcn_train_destroy(h); }
+int64_t echo_mesh_workspace_bytes(int32_t resolution) { return resolution >= 2 && resolution <= 512 ? (int64_t)mesh_workspace_bytes(resolution) : -1; }
+int echo_mesh_marching_cubes(const float* sdf, int32_t resolution, float level, float* verts, int64_t max_verts, int32_t* faces,
+                             int64_t max_faces, int32_t* counts, void* workspace, int64_t workspace_bytes, void* stream) {
+  return guard([&] {
+    mesh_marching_cubes(sdf, resolution, level, verts, max_verts, faces, max_faces, counts, workspace,
+                        workspace_bytes > 0 ? (size_t)workspace_bytes : 0, (cudaStream_t)stream);
+  });
+}
 int echo_layout_set_batch_stats(echo_layout_t* h, int32_t on) {
   return guard([&] { layout_set_batch_stats(h, on != 0); });
 }

@@ -253,6 +253,20 @@ ECHO_API int echo_layout_set_batch_stats(echo_layout_t* h, int32_t on);
 ECHO_API int echo_shape_set_batch_stats(echo_shape_t* h, int32_t on);
 ECHO_API int echo_scene_set_batch_stats(echo_scene_t* h, int32_t on);
 
+/* ---- SDF -> triangle mesh: marching cubes over ONE (R, R, R) fp32 volume, the stage the reference runs per object on
+ * the CPU with PyMCubes -- mcubes.marching_cubes(sdf_i, level), model/diff_utils/util_3d.py:213-218 (level 0.02), followed by
+ * verts / n_cell - 0.5 (:219, left to the caller).  Vertices are shared per grid edge, in index coordinates (x = first array axis),
+ * linearly interpolated along the edge; "inside" is value < level; triangles are oriented with their normals pointing from inside
+ * to outside.  Case tables: derived from the method's definition (tools/gen_mc_tables.py); PyMCubes itself is not available here,
+ * so vertex / triangle ORDER and the diagonals chosen on ambiguous configurations are this library's, not PyMCubes' (DESIGN.md).
+ *   verts  (max_verts, 3) f32, faces (max_faces, 3) i32 vertex indices: written up to the capacities given (0 / NULL: count only);
+ *   counts (2,) i32 DEVICE: [number of vertices, number of triangles] of the whole mesh -- when they exceed the capacities the call
+ *          must be repeated with larger outputs (typical use: a counting call, one host read, then the emitting call);
+ *   workspace: echo_mesh_workspace_bytes(R) bytes of device scratch.  Deterministic: output order depends on the volume only. */
+ECHO_API int64_t echo_mesh_workspace_bytes(int32_t resolution);
+ECHO_API int echo_mesh_marching_cubes(const float* sdf, int32_t resolution, float level, float* verts, int64_t max_verts, int32_t* faces,
+                                      int64_t max_faces, int32_t* counts, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* A chain whose launch sequence does not depend on the step: pass ECHO_INDEX_FROM_DEVICE as `ddim_index` to echo_shape_step /
  * echo_shape_trunk / echo_shape_trunk_async and the step reads its DDIM index (timesteps, update coefficients) from a slot on
  * the device, written by echo_shape_set_index (stream-ordered).  Such a step can be captured ONCE into a CUDA graph -- together

@@ -1,0 +1,72 @@
+"""CPU: the marching-cubes oracle (oracle/mesh_oracle.py) and the derived case tables (tools/gen_mc_tables.py) against the METHOD --
+PyMCubes, which the reference calls (model/diff_utils/util_3d.py:217), is not available here, so the oracle is held to properties
+any correct marching cubes has: a closed, consistently oriented 2-manifold for a closed level set (also on white noise, where every
+ambiguous configuration occurs), boundary edges only on the volume's boundary, vertices on the level set of the edge-interpolated
+field, area / volume of an analytic sphere, and the classic edge table entry for entry."""
+import numpy as np
+
+from oracle import mesh_oracle as mo
+
+
+def grid(R):
+    return np.stack(np.meshgrid(*[np.arange(R, dtype=np.float32)] * 3, indexing="ij"), -1)
+
+
+def test_derived_edge_table_is_the_classic_one():
+    # the first two rows and a few landmarks of the published 256-entry edge table (Lorensen-Cline numbering, Bourke's listing)
+    classic = [0x0, 0x109, 0x203, 0x30a, 0x406, 0x50f, 0x605, 0x70c, 0x80c, 0x905, 0xa0f, 0xb06, 0xc0a, 0xd03, 0xe09, 0xf00,
+               0x190, 0x99, 0x393, 0x29a, 0x596, 0x49f, 0x795, 0x69c, 0x99c, 0x895, 0xb9f, 0xa96, 0xd9a, 0xc93, 0xf99, 0xe90]
+    assert [int(v) for v in mo.EDGE_TABLE[:32]] == classic
+    assert int(mo.EDGE_TABLE[255]) == 0 and int(mo.EDGE_TABLE[0x55]) == 0xff and int(mo.EDGE_TABLE[0xaa]) == 0xff   # bottom ring / top ring
+    assert all(int(mo.EDGE_TABLE[c]) == int(mo.EDGE_TABLE[255 - c]) for c in range(256))                             # complement symmetry
+    assert int(mo.NUM_TRI.max()) == 5 and int((mo.NUM_TRI > 0).sum()) == 254
+
+
+def test_sphere_is_a_closed_oriented_manifold_with_the_right_area_and_volume():
+    R, c, r = 32, np.array([15.3, 16.1, 14.7], dtype=np.float32), 9.5
+    vol = (np.linalg.norm(grid(R) - c, axis=-1) - r).astype(np.float32)
+    v, f = mo.marching_cubes(vol, 0.0)
+    counts, oriented = mo.edge_use_counts(f)
+    assert (counts == 2).all() and oriented
+    assert len(v) - len(counts) + len(f) == 2                                  # Euler characteristic of a sphere
+    area, volume = mo.area_and_volume(v, f)
+    assert abs(area / (4 * np.pi * r * r) - 1) < 0.01 and abs(volume / (4 / 3 * np.pi * r ** 3) - 1) < 0.01 and volume > 0   # outward normals
+    assert float(np.abs(np.linalg.norm(v - c, axis=1) - r).max()) < 0.03       # vertices on the level set (linear interpolation error)
+    assert f.dtype == np.int64 and v.dtype == np.float32 and int(f.max()) == len(v) - 1 and len(np.unique(f)) == len(v)
+
+
+def test_white_noise_gives_a_closed_manifold():
+    R = 20
+    rng = np.random.default_rng(3)
+    vol = rng.standard_normal((R, R, R)).astype(np.float32)
+    vol[0] = vol[-1] = vol[:, 0] = vol[:, -1] = vol[:, :, 0] = vol[:, :, -1] = 5.0          # outside shell: the level set is closed
+    v, f = mo.marching_cubes(vol, 0.0)
+    counts, oriented = mo.edge_use_counts(f)
+    assert len(f) > 10000 and (counts == 2).all() and oriented
+    _, volume = mo.area_and_volume(v, f)
+    assert volume > 0
+
+
+def test_open_surface_has_boundary_edges_only_on_the_volume_boundary():
+    R = 24
+    g = grid(R)
+    vol = (g[..., 0] * 0.3 + g[..., 1] * 0.5 + g[..., 2] - 14.2).astype(np.float32)
+    v, f = mo.marching_cubes(vol, 0.0)
+    e = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]])
+    und, counts = np.unique(np.sort(e, axis=1), axis=0, return_counts=True)
+    assert set(counts.tolist()) == {1, 2}
+    b = v[und[counts == 1]]                                                    # (n, 2, 3) end points of boundary edges
+    on_wall = ((b == 0) | (b == R - 1)).any(axis=2).all(axis=1)
+    assert on_wall.all()
+    assert float(np.abs(v[:, 0] * 0.3 + v[:, 1] * 0.5 + v[:, 2] - 14.2).max()) < 1e-4      # a linear field is met exactly
+
+
+def test_empty_and_full_volumes_and_the_scaling_of_sdf_to_mesh():
+    R = 8
+    for fill in (1.0, -1.0):
+        v, f = mo.marching_cubes(np.full((R, R, R), fill, dtype=np.float32), 0.02)
+        assert v.shape == (0, 3) and f.shape == (0, 3)
+    vol = (np.linalg.norm(grid(R) - 3.5, axis=-1) - 2.0).astype(np.float32)
+    vs, fs = mo.sdf_to_mesh(vol[None, None], level=0.02)
+    v, f = mo.marching_cubes(vol, 0.02)
+    assert np.array_equal(vs[0], v / np.float32(R) - np.float32(0.5)) and np.array_equal(fs[0], f)          # util_3d.py:218-219
