@@ -10,7 +10,6 @@ import json
 d=json.loads(open('gpurun_out/bench_n1.json').read().strip().splitlines()[-1])
 for k in ('value','ms_per_step','steps','launch_mode','gpu_launches','e2e','clocks','cpu_baseline'): print(k, d.get(k))
 print('roofline frac', d['roofline'].get('frac'), 'step', d['roofline']['step']['frac'])
-for k in ('layout_branch','layout_branch_batched_64_scenes','parity_mode_x3','config3_n32_s250','config4_scene_sharded','gpu_eager_baseline','scene_encode','vqvae_decode','full_chain_seconds_per_scene'): print(k, d.get(k))
+for k in ('layout_branch','layout_branch_batched_64_scenes','sdf_to_mesh','full_chain_seconds_per_scene_batched','parity_mode_x3','config3_n32_s250','config4_scene_sharded','gpu_eager_baseline','scene_encode','vqvae_decode','full_chain_seconds_per_scene'): print(k, d.get(k))
 PY
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -c 700
-timeout 300 python tools/time_gcn_train.py --scenes 64 --out gpurun_out/gcn_train_timing_s64.json 2>&1 | grep -E "ms|speedup"
