@@ -9,7 +9,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompil
 pids=()
 for f in runtime elem linear gemm_simt sgemm_x3 gemm_tc flash_tc conv_small gcn gcn_train scene unet_plan layout layout_mk train metrics mesh shape vqvae capi attention; do
   [ -f "$HERE/$f.cu" ] || continue
-  if [ ! -f "$HERE/obj/$f.o" ] || [ "$HERE/$f.cu" -nt "$HERE/obj/$f.o" ] || [ -n "$(find "$HERE" -maxdepth 1 -name '*.cuh' -newer "$HERE/obj/$f.o")" ] || [ "$HERE/../../include/echoscene_b200.h" -nt "$HERE/obj/$f.o" ]; then
+  if [ ! -f "$HERE/obj/$f.o" ] || [ "$HERE/$f.cu" -nt "$HERE/obj/$f.o" ] || [ -n "$(find "$HERE" -maxdepth 1 \( -name '*.cuh' -o -name '*.inc' \) -newer "$HERE/obj/$f.o")" ] || [ "$HERE/../../include/echoscene_b200.h" -nt "$HERE/obj/$f.o" ]; then
     $NVCC $FLAGS -c "$HERE/$f.cu" -o "$HERE/obj/$f.o" &
     pids+=($!)
   fi
