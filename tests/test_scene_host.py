@@ -336,3 +336,30 @@ def test_sample_scenes_batches_block_diagonal_scenes():
     assert [p["sizes"].shape[0] for p in per] == sizes and per[2]["shapes"].shape == (8, 3, 16, 16, 16)
     with pytest.raises(_lib.EchoError):
         m.sample_scenes(objs, batch.triples, text, rel, o2s, gen_shape=True, x_T_per_scene=x_T[:2])
+
+
+def test_select_sdfs_greedy_matches_the_reference():
+    """scene.Sg2ScDiffModel.select_sdfs against the reference's own Sg2ScDiffModel.select_sdfs(sample_type='greedy')
+    (model/EchoScene.py:246-319; tests/golden/select_sdfs.pt from oracle/gen_golden_select.py): whole scenes while they fit
+    diffusion_bs, the triples among the selected nodes; and the two inputs the reference fails on, refused with a message."""
+    import os
+    import types
+    from oracle import gen_golden_select as gs
+    G = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "select_sdfs.pt"), map_location="cpu")
+    enc = types.SimpleNamespace(embedding_dim=64, out_dim_ini_encoder=640)
+    for name, sizes, bs in gs.CASES:
+        o2s, objs, triples, sdfs, uc, c = gs.batch(sizes, 100 + len(sizes))
+        m = scene.Sg2ScDiffModel(enc, None, diffusion_bs=bs)
+        cats, d = m.select_sdfs(o2s, objs, triples, sdfs, uc, c)
+        ref = G[name]
+        assert torch.equal(cats, ref["obj_cat_selected"]), name
+        for k in ("sdf", "uc_s", "c_s", "triples"):
+            assert torch.equal(d[k], ref[k]), (name, k)
+        assert np.array_equal(np.asarray(d["scene_ids"]), ref["scene_ids"].numpy()), name
+    o2s, objs, triples, sdfs, uc, c = gs.batch([20, 4], 7)
+    with pytest.raises(_lib.EchoError, match="first scene"):                    # the reference: torch.cat of an empty list
+        scene.Sg2ScDiffModel(enc, None, diffusion_bs=16).select_sdfs(o2s, objs, triples, sdfs, uc, c)
+    with pytest.raises(_lib.EchoError, match="greedy"):
+        scene.Sg2ScDiffModel(enc, None, diffusion_bs=16).select_sdfs(o2s, objs, triples, sdfs, uc, c, sample_type="balance")
+    with pytest.raises(_lib.EchoError, match="sorted by scene"):
+        scene.Sg2ScDiffModel(enc, None, diffusion_bs=64).select_sdfs(torch.tensor([1, 0, 1, 0]), objs[:4], triples[:0], sdfs[:4], uc[:4], c[:4])
