@@ -6,7 +6,7 @@ appends them.  No CPU fallback."""
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Optional
+from typing import Dict, List
 
 import torch
 

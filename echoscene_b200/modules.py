@@ -17,7 +17,7 @@ Inference only (eval-mode BatchNorm, no autograd): the training backward is outs
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Optional, Sequence
+from typing import Dict, Optional
 
 import torch
 import torch.nn as nn

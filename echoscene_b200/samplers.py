@@ -9,13 +9,12 @@ no host synchronisation, no per-step tensor allocation except the reference-visi
 """
 from __future__ import annotations
 
-from typing import Callable, Optional
+from typing import Callable
 
 import numpy as np
 import torch
 import torch.nn as nn
 
-from . import _lib
 from ._lib import EchoError
 from .modules import UNet1DModel, UNet3DModel
 

@@ -8,7 +8,6 @@ numpy float32 scalars, so differences / products / quotients round to float32 be
 identity makes it in the reference."""
 from __future__ import annotations
 
-import math
 
 import numpy as np
 

@@ -1,7 +1,6 @@
 """Join an ECHO_TRACE=1 log of one profiled step with the ncu launch list of the same run: per-contraction time,
 TFLOP/s and tile-wave utilisation.  Usage: python tools/gemm_efficiency.py launches.csv trace.log"""
 import csv
-import re
 import sys
 from collections import defaultdict
 

@@ -1,5 +1,4 @@
 """Layout-steps/s (UNet1DModel forward + DDPM update, chained) at N nodes.  ECHO_NO_PDL=1 / ECHO_NO_GRAPH=1 for A/B."""
-import json
 import os
 import sys
 
