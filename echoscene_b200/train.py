@@ -97,6 +97,26 @@ def shape_train_tables(timesteps: int = 1000, linear_start: float = 0.00085, lin
             "lvlb_weights": lvlb, "logvar": torch.full((timesteps,), 0.0)}
 
 
+def lr_lambda(counter: int, lr_init: float = 1e-4, lr_step: Sequence[int] = (35000, 70000, 140000),
+              lr_evo: Sequence[float] = (5e-5, 1e-5, 5e-6)) -> float:
+    """Sg2ScDiffModel.lr_lambda (model/EchoScene.py:115-128; hyper.lr_init / lr_step / lr_evo of config/full_mp.yaml): the factor the
+    reference's LambdaLR applies to the optimizer's base rate at iteration ``counter``."""
+    if counter < lr_step[0]:
+        return 1.0
+    if counter < lr_step[1]:
+        return lr_evo[0] / lr_init
+    if counter < lr_step[2]:
+        return lr_evo[1] / lr_init
+    return lr_evo[2] / lr_init
+
+
+def learning_rate(counter: int, base_lr: float = 1e-4, **schedule) -> float:
+    """The rate ``optimizerFULL`` runs at after ``counter`` scheduler steps: AdamW's base rate (1e-4, EchoScene.py:134) times
+    ``lr_lambda(counter)`` -- what ``update_learning_rate`` (EchoScene.py:138-141) leaves in ``param_groups[0]['lr']``; pass it to
+    ``FusedAdamW.step(lr=...)``."""
+    return base_lr * lr_lambda(counter, **schedule)
+
+
 class GraphTripleConvNetTrainer:
     """Training-mode forward AND backward of a ``modules.GraphTripleConvNet`` / ``GraphTripleConv`` on the CUDA path
     (``echo_gcn_train_*``, csrc/gcn_train.cu): what the reference gets from autograd over model/graph.py:124-211 under

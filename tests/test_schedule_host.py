@@ -68,3 +68,33 @@ def test_training_tables_are_bit_equal_to_the_reference_constructors():
     for k, v in G["shape"].items():
         assert torch.equal(t[k], v), k
     assert torch.equal(t["logvar"], torch.zeros(1000)) and float(t["lvlb_weights"][0]) == float(t["lvlb_weights"][1])
+
+
+def test_learning_rate_schedule_is_the_reference_lambda():
+    """train.lr_lambda / learning_rate against torch's LambdaLR driven by the reference's own Sg2ScDiffModel.lr_lambda
+    (model/EchoScene.py:115-141), restated here from its four branches: the rate in param_groups after `counter` scheduler steps."""
+    from echoscene_b200 import train
+    lr_init, lr_step, lr_evo = 1e-4, [35000, 70000, 140000], [5e-5, 1e-5, 5e-6]
+
+    def reference_lambda(counter):                       # EchoScene.py:117-128
+        if counter < lr_step[0]:
+            return 1.0
+        elif counter < lr_step[1]:
+            return lr_evo[0] / lr_init
+        elif counter < lr_step[2]:
+            return lr_evo[1] / lr_init
+        else:
+            return lr_evo[2] / lr_init
+
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.AdamW([p], lr=1e-4)
+    probes = {0, 1, 34999, 35000, 35001, 69999, 70000, 139999, 140000, 200000}
+    for counter in sorted(probes):
+        sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_lambda=reference_lambda, last_epoch=-1)
+        for g in opt.param_groups:
+            g["lr"] = 1e-4
+        sched.last_epoch = counter - 1
+        opt.step()
+        sched.step()                                     # update_learning_rate, EchoScene.py:138-141
+        assert opt.param_groups[0]["lr"] == pytest.approx(train.learning_rate(counter), rel=1e-12), counter
+        assert train.lr_lambda(counter, lr_init, lr_step, lr_evo) == reference_lambda(counter)
