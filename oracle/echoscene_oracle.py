@@ -244,24 +244,26 @@ def _unet_trunk(sd: SD, cfg, dims: int, h: Tensor, emb: Tensor, context: Tensor)
 # --------------------------------------------------------------------------------------
 
 
-def box_message_passing(sd: SD, cfg, obj_embed: Tensor, triples: Tensor, box_t: Tensor, emb: Tensor) -> Tensor:
-    """UNet1DModel.box_messsage_passing.  denoise_net.py:758-771."""
+def box_message_passing(sd: SD, cfg, obj_embed: Tensor, triples: Tensor, box_t: Tensor, emb: Tensor, batch_stats: bool = False) -> Tensor:
+    """UNet1DModel.box_messsage_passing.  denoise_net.py:758-771.  batch_stats: as under model.train()."""
     edges, p = edges_of(triples)
     box_embed = _linear(sd, "box_embeddings", box_t)
     pred_embed = sd["pred_embeddings.weight"][p]
     node = torch.cat([obj_embed, box_embed], dim=1)
     if cfg.enable_t_emb:
         node = torch.cat([node, _linear(sd, "box_time_emb", emb)], dim=1)
-    out, _ = graph_triple_conv_net(sd, "box_graph_cov.", node, pred_embed, edges)
+    out, _ = graph_triple_conv_net(sd, "box_graph_cov.", node, pred_embed, edges, batch_stats=batch_stats)
     return out
 
 
 def unet1d_forward(sd: SD, cfg, box_t: Tensor, obj_embed: Tensor, triples: Tensor, timesteps: Tensor,
-                   context: Optional[Tensor] = None) -> Tensor:
-    """UNet1DModel.forward (conditioning_key='crossattn'): returns (N, 8, 1).  denoise_net.py:773-806."""
+                   context: Optional[Tensor] = None, batch_stats: bool = False) -> Tensor:
+    """UNet1DModel.forward (conditioning_key='crossattn'): returns (N, 8, 1).  denoise_net.py:773-806.
+    batch_stats: the forward under model.train() -- box_graph_cov's BatchNorm1d layers on the statistics of the batch (GroupNorm /
+    LayerNorm do not depend on the mode; dropout is 0; the checkpoint wrapper only changes what autograd stores)."""
     emb = _linear(sd, "time_embed.2", F.silu(_linear(sd, "time_embed.0",
                                                      timestep_embedding(timesteps, cfg.model_channels))))
-    latent = box_message_passing(sd, cfg, obj_embed, triples, box_t, emb)
+    latent = box_message_passing(sd, cfg, obj_embed, triples, box_t, emb, batch_stats)
     ctx = latent.unsqueeze(1)                      # overwrites `context`, denoise_net.py:791-792
     h = box_t.unsqueeze(1).permute(0, 2, 1)        # (N, 8, 1)
     return _unet_trunk(sd, cfg, 1, h, emb, ctx)
@@ -329,24 +331,25 @@ def shape_embeddings(sd: SD, x: Tensor) -> Tensor:
     return _linear(sd, "shape_embeddings.5", h.flatten(1))
 
 
-def shape_message_passing(sd: SD, cfg, obj_embed: Tensor, triples: Tensor, x: Tensor, emb: Tensor) -> Tensor:
-    """UNet3DModel.shape_messsage_passing.  openai_model_3d.py:800-814."""
+def shape_message_passing(sd: SD, cfg, obj_embed: Tensor, triples: Tensor, x: Tensor, emb: Tensor, batch_stats: bool = False) -> Tensor:
+    """UNet3DModel.shape_messsage_passing.  openai_model_3d.py:800-814.  batch_stats: as under model.train()."""
     edges, p = edges_of(triples)
     code = shape_embeddings(sd, x)
     pred_embed = sd["pred_embeddings.weight"][p]
     node = torch.cat([obj_embed.squeeze(1), code], dim=1)
     if cfg.enable_t_emb:
         node = torch.cat([node, _linear(sd, "shape_time_emb", emb)], dim=1)
-    out, _ = graph_triple_conv_net(sd, "shape_code_graph_cov.", node, pred_embed, edges)
+    out, _ = graph_triple_conv_net(sd, "shape_code_graph_cov.", node, pred_embed, edges, batch_stats=batch_stats)
     return out
 
 
 def unet3d_forward(sd: SD, cfg, x: Tensor, obj_embed: Tensor, triples: Tensor, timesteps: Tensor,
-                   context: Optional[Tensor] = None) -> Tensor:
-    """UNet3DModel.forward (crossattn, message passing): returns (N, 3, 16, 16, 16).  openai_model_3d.py:816-863."""
+                   context: Optional[Tensor] = None, batch_stats: bool = False) -> Tensor:
+    """UNet3DModel.forward (crossattn, message passing): returns (N, 3, 16, 16, 16).  openai_model_3d.py:816-863.
+    batch_stats: the forward under model.train() (shape_code_graph_cov's BatchNorm1d layers on the statistics of the batch)."""
     emb = _linear(sd, "time_embed.2", F.silu(_linear(sd, "time_embed.0",
                                                      timestep_embedding(timesteps, cfg.model_channels))))
-    latent = shape_message_passing(sd, cfg, obj_embed, triples, x, emb)
+    latent = shape_message_passing(sd, cfg, obj_embed, triples, x, emb, batch_stats)
     ctx = latent.unsqueeze(1)                      # "we dont use the previous context", :843-844
     return _unet_trunk(sd, cfg, 3, x, emb, ctx)
 

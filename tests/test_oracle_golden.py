@@ -166,3 +166,27 @@ def test_gcn_backward_oracle_matches_the_reference_autograd():
                 assert max(rel_err(grads[k], want)) < 1e-5, (name, k)
         for k, want in ref["buffers"].items():
             assert max(rel_err(track[k].float(), want.float())) < 1e-6, (name, k)
+
+
+def test_layout_denoiser_train_mode_oracle_forward_and_backward_match_the_reference():
+    """oracle.unet1d_forward(batch_stats=True) and autograd over it against the reference's UNet1DModel under .train() and ITS autograd
+    (tests/golden/layout_train.pt, oracle/gen_golden_layout_train.py): the forward output bit for bit, and for every parameter the
+    digest of its gradient (L2 norm, eight entries).  This is the parity contract the layout trunk's backward pass will be built
+    against; no CUDA code is involved yet."""
+    from oracle import gen_golden_layout_train as gt
+    G = gold("layout_train.pt")
+    lcfg = cases.layout_cfg()
+    sd = arch.make_state_dict(arch.unet1d_specs(lcfg), cases.WEIGHT_SEED_LAYOUT)
+    g, obj_embed, x, t, noise = gt.inputs(lcfg)
+    out, loss, grads = gt.oracle_grads(sd, lcfg, g, obj_embed, x, t, noise)
+    assert torch.equal(out, G["out"]) and abs(loss - G["loss"]) < 1e-6
+    assert set(G["no_grad"]) == {"box_graph_cov.gconvs.4.linear_projection_pred.weight", "box_graph_cov.gconvs.4.linear_projection_pred.bias"}
+    scale, noisy = G["grad_scale"], set(G["noise_level"])
+    assert len(noisy) == 90 and any(k.endswith("attn1.to_q.weight") for k in noisy)     # softmax over one token: q / k get no gradient
+    for k, d in G["grads"].items():
+        got = gt.digest(grads[k])
+        if k in noisy:
+            assert float(grads[k].abs().max()) < 1e-5 * scale, k
+            continue
+        assert abs(got["norm"] - d["norm"]) <= 1e-3 * d["norm"], k
+        assert float((got["samples"] - d["samples"]).abs().max()) <= 1e-3 * max(float(d["samples"].abs().max()), 1e-3 * d["norm"]), k
