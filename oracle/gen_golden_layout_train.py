@@ -33,7 +33,7 @@ def inputs(lcfg):
 
 def digest(grad: torch.Tensor):
     flat = grad.detach().reshape(-1)
-    idx = torch.linspace(0, flat.numel() - 1, 8).long()
+    idx = (torch.arange(8, dtype=torch.int64) * (flat.numel() - 1)) // 7
     return {"norm": float(flat.double().norm()), "samples": flat[idx].clone()}
 
 

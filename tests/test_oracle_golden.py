@@ -190,3 +190,28 @@ def test_layout_denoiser_train_mode_oracle_forward_and_backward_match_the_refere
             continue
         assert abs(got["norm"] - d["norm"]) <= 1e-3 * d["norm"], k
         assert float((got["samples"] - d["samples"]).abs().max()) <= 1e-3 * max(float(d["samples"].abs().max()), 1e-3 * d["norm"]), k
+
+
+def test_shape_denoiser_train_mode_oracle_forward_and_backward_match_the_reference():
+    """oracle.unet3d_forward(batch_stats=True) and autograd over it against the reference's UNet3DModel under .train() and ITS autograd
+    on three objects with one timestep each (tests/golden/shape_train.pt, oracle/gen_golden_shape_train.py): the forward output bit
+    for bit; per parameter the digest of its gradient, 1e-3 of its norm plus a rounding floor scaled by the largest gradient of the
+    model (most biases of this network carry gradients 1e-6 of the output convolution's).  The parity contract of the shape trunk's
+    backward kernels (conv dgrad / wgrad, GroupNorm, attention, GEGLU); no CUDA code is involved yet."""
+    from oracle import gen_golden_layout_train as gl, gen_golden_shape_train as gs
+    G = gold("shape_train.pt")
+    scfg = cases.shape_cfg()
+    sd = arch.make_state_dict(arch.unet3d_specs(scfg), cases.WEIGHT_SEED_SHAPE)
+    g, uc, x, t, noise = gs.inputs(scfg)
+    out, loss, grads = gs.oracle_grads(sd, scfg, g, uc, x, t, noise)
+    assert torch.equal(out, G["out"]) and abs(loss - G["loss"]) < 1e-6
+    assert set(G["no_grad"]) == {"shape_code_graph_cov.gconvs.4.linear_projection_pred.weight", "shape_code_graph_cov.gconvs.4.linear_projection_pred.bias"}
+    scale, noisy = G["grad_scale"], set(G["noise_level"])
+    for k, d in G["grads"].items():
+        if k in noisy:
+            assert float(grads[k].abs().max()) < 1e-5 * scale, k
+            continue
+        got = gl.digest(grads[k])
+        floor = 1e-7 * scale * grads[k].numel() ** 0.5
+        assert abs(got["norm"] - d["norm"]) <= 1e-3 * d["norm"] + floor, (k, got["norm"], d["norm"])
+        assert float((got["samples"] - d["samples"]).abs().max()) <= 1e-3 * float(d["samples"].abs().max()) + 1e-6 * scale, k
