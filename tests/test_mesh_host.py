@@ -70,3 +70,53 @@ def test_empty_and_full_volumes_and_the_scaling_of_sdf_to_mesh():
     vs, fs = mo.sdf_to_mesh(vol[None, None], level=0.02)
     v, f = mo.marching_cubes(vol, 0.02)
     assert np.array_equal(vs[0], v / np.float32(R) - np.float32(0.5)) and np.array_equal(fs[0], f)          # util_3d.py:218-219
+
+
+def test_case_tables_are_invariant_under_the_rotations_of_the_cube_and_under_complement():
+    """The derived tables treat the 24 rotations of the cube alike: rotating a corner configuration permutes its cut edges and keeps its
+    triangle count and its loop structure (sorted loop lengths); the complementary configuration has the same cut edges, the same
+    triangles up to orientation (reversed: the normal follows inside -> outside) and fan apex."""
+    import itertools
+    C = mo.CORNERS.astype(float) - 0.5
+    rots = []
+    for perm in itertools.permutations(range(3)):
+        for signs in itertools.product((1, -1), repeat=3):
+            M = np.zeros((3, 3))
+            for r, (p, s) in enumerate(zip(perm, signs)):
+                M[r, p] = s
+            if round(np.linalg.det(M)) == 1:
+                rots.append(M)
+    assert len(rots) == 24
+    edges = mo.gen.EDGES
+    edge_of = {frozenset(e): i for i, e in enumerate(edges)}
+
+    def loops_of(case):
+        tris = [tuple(int(v) for v in mo.TRI_TABLE[case, 3 * t:3 * t + 3]) for t in range(mo.NUM_TRI[case])]
+        # boundary edges of the triangle set = the loops' segments; group triangles into fans by shared apex chains (connected components)
+        comp = list(range(len(tris)))
+        for a in range(len(tris)):
+            for b in range(a + 1, len(tris)):
+                if len(set(tris[a]) & set(tris[b])) >= 2:
+                    ra, rb = comp[a], comp[b]
+                    comp = [ra if c == rb else c for c in comp]
+        sizes = {}
+        for c, t in zip(comp, tris):
+            sizes.setdefault(c, set()).update(t)
+        return sorted(len(v) for v in sizes.values())
+
+    for M in rots:
+        corner_map = [int(np.argmin(np.abs(C - (M @ C[i])).sum(1))) for i in range(8)]            # corner i moves to corner_map[i]
+        edge_map = [edge_of[frozenset((corner_map[a], corner_map[b]))] for a, b in edges]
+        for case in range(256):
+            rc = sum(((case >> i) & 1) << corner_map[i] for i in range(8))
+            assert mo.NUM_TRI[rc] == mo.NUM_TRI[case]
+            cut = {e for e in range(12) if (int(mo.EDGE_TABLE[case]) >> e) & 1}
+            assert {edge_map[e] for e in cut} == {e for e in range(12) if (int(mo.EDGE_TABLE[rc]) >> e) & 1}
+            assert loops_of(rc) == loops_of(case), (case, rc)
+    for case in range(256):
+        comp = 255 - case
+        assert mo.EDGE_TABLE[case] == mo.EDGE_TABLE[comp]
+        # same loops unless the configuration has an ambiguous face (there the inside-corner rule joins the other pair of edges)
+        amb = any(((case >> f[0]) & 1) == ((case >> f[2]) & 1) != ((case >> f[1]) & 1) == ((case >> f[3]) & 1) for f in mo.gen.FACES)
+        if not amb:
+            assert mo.NUM_TRI[case] == mo.NUM_TRI[comp] and loops_of(case) == loops_of(comp), case
