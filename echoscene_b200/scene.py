@@ -1,5 +1,6 @@
-"""Scene-level sampling glue: the host side of ``Sg2ScDiffModel.sample`` / ``sample_with_changes`` /
-``sample_with_additions`` (model/EchoScene.py:388-532) and of the ``SGDiff`` facade over them (model/SGDiff.py:87-121).
+"""Scene-level glue: the host side of ``Sg2ScDiffModel.sample`` / ``sample_with_changes`` / ``sample_with_additions``
+(model/EchoScene.py:388-532), of the training forward ``Sg2ScDiffModel.forward`` as loss values (:328-386, with ``select_sdfs``
+:289-319) and of the ``SGDiff`` facade over them (model/SGDiff.py:32-47, 87-121).
 
 The arithmetic lives behind the C ABI (``SceneEncoder`` -> echo_scene_*, ``DiffusionPoint`` -> echo_layout_step,
 ``DDIMSampler`` -> echo_shape_step, ``VQVAE`` -> echo_vqvae_decode); this file is the order of calls and the row

@@ -1,8 +1,15 @@
-"""Training-side pieces of the reference's train step that sit around the denoisers' forward / backward, on the CUDA
-path: ``q_sample``, the diffusion losses given a denoiser output, and the optimizer step of ``scripts/train_3dfront.py:247-259``
-(clip_grad_norm_ of the shape denoiser, the per-parameter NaN scrub loop, ``optimizerFULL.step()`` = AdamW) as one fused
-multi-tensor pass with no host synchronisation.  The backward pass of the denoisers is not part of this round; these are the
-HBM-bound stages a training iteration spends outside it, and they accept gradients from any producer (torch autograd today).
+"""Training-side pieces of the reference's train step, on the CUDA path:
+
+  * ``q_sample`` and the diffusion losses given a denoiser output (diffusion_ddpm.py:191-201, 451-477; echo2shape.py:254-258,
+    297-331), the training tables as the reference's constructors build them (``layout_train_tables`` / ``shape_train_tables``), the
+    LambdaLR schedule (``lr_lambda`` / ``learning_rate``) -- what ``scene.Sg2ScDiffModel.forward`` / ``SGDiff.forward_mani`` use to
+    compute the training forward's loss VALUES;
+  * ``GraphTripleConvNetTrainer``: forward AND backward of a GraphTripleConvNet in training mode (the first backward of this path;
+    the backward of the two denoiser trunks is not built), also as one replayed CUDA graph;
+  * ``FusedAdamW``: the optimizer step of ``scripts/train_3dfront.py:247-259`` (clip_grad_norm_ of the shape denoiser, the
+    per-parameter NaN scrub loop, ``optimizerFULL.step()`` = AdamW) as one fused multi-tensor pass with no host synchronisation; it
+    accepts gradients from any producer (torch autograd, or the trainer above).
+
 No CPU fallback: CPU tensors raise ``EchoError``."""
 from __future__ import annotations
 
