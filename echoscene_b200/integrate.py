@@ -23,8 +23,10 @@ so ``sample`` / ``sample_with_changes`` / ``sample_with_additions`` run unchange
 echo_scene_rel_s the first time the encoders run (its parameters stay where they are).  ``echoscene_b200.scene`` /
 ``echoscene_b200.sgdiff`` are the same surface without any reference code.
 
-Training (`train_3dfront.py`) needs the backward pass, which is outside this round's scope: the patched classes raise
-in ``train()`` mode instead of silently computing something else.
+Training (`train_3dfront.py`) needs an autograd tape through every module, and the denoiser trunks have no backward pass on
+this path yet: the classes handed to the reference raise in ``train()`` mode (``train_forward_values = False``) instead of
+returning tape-less values.  (The package's own facade, ``sgdiff.SGDiff``, does compute the training forward's loss VALUES in
+``train()`` mode: ``forward_mani``.)
 """
 from __future__ import annotations
 
@@ -112,12 +114,23 @@ def patch_reference(precision: str = "fp32", ddim_steps: Optional[int] = None, v
 
     def _with_precision(cls):
         class _P(cls):
+            train_forward_values = False   # the reference's training loop needs an autograd tape: refuse train() instead of returning values
+
             def __init__(self, *a, **k):
                 k.setdefault("precision", precision)
                 super().__init__(*a, **k)
         _P.__name__ = cls.__name__
         _P.__qualname__ = cls.__qualname__
         return _P
+
+    def _eval_only_class(cls):
+        class _E(cls):
+            train_forward_values = False
+        _E.__name__ = cls.__name__
+        _E.__qualname__ = cls.__qualname__
+        return _E
+
+    GTC, GTCN = _eval_only_class(modules.GraphTripleConv), _eval_only_class(modules.GraphTripleConvNet)
 
     U1, U3 = _with_precision(modules.UNet1DModel), _with_precision(modules.UNet3DModel)
 
@@ -128,14 +141,14 @@ def patch_reference(precision: str = "fp32", ddim_steps: Optional[int] = None, v
     VQ = _with_precision(modules.VQVAE)
     done = {}
     targets = [
-        ("model.graph", {"GraphTripleConv": modules.GraphTripleConv, "GraphTripleConvNet": modules.GraphTripleConvNet}),
+        ("model.graph", {"GraphTripleConv": GTC, "GraphTripleConvNet": GTCN}),
         ("model.networks.diffusion_layout.denoise_net", {"UNet1DModel": U1}),
         ("model.networks.diffusion_layout.echo2layout", {"UNet1DModel": U1, "DiffusionPoint": samplers.DiffusionPoint}),
         ("model.networks.diffusion_shape.openai_model_3d", {"UNet3DModel": U3}),
         ("model.networks.diffusion_shape.network", {"UNet3DModel": U3, "DiffusionUNet": DiffusionUNet}),
         ("model.networks.diffusion_shape.echo2shape", {"DDIMSampler": samplers.DDIMSampler, "DiffusionUNet": DiffusionUNet}),
-        ("model.EchoScene", {"GraphTripleConvNet": modules.GraphTripleConvNet}),
-        ("model.EchoLayout", {"GraphTripleConvNet": modules.GraphTripleConvNet}),
+        ("model.EchoScene", {"GraphTripleConvNet": GTCN}),
+        ("model.EchoLayout", {"GraphTripleConvNet": GTCN}),
     ]
     if vqvae_decode:
         targets.append(("model.model_utils", {"VQVAE": VQ}))

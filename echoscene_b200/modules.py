@@ -83,6 +83,16 @@ class _SpecModule(nn.Module):
             raise EchoError(f"{type(self).__name__}: this call is a sampler step and runs under eval() only "
                             "(the reference samples under model.eval(), scripts/eval_3dfront.py:395)")
 
+    # train(): forward computes VALUES on batch statistics, without an autograd tape.  integrate.patch_reference() turns this off on the
+    # classes it hands to the reference: inside the reference's own training loop a loss without a tape must not appear at all
+    train_forward_values = True
+
+    def _check_train_values(self):
+        if self.training and not self.train_forward_values:
+            raise EchoError(f"{type(self).__name__}: train() mode inside the patched reference -- the B200 path computes forward values "
+                            "only (no autograd tape, no backward pass for this module yet); keep the reference's own module for "
+                            "training, or call .eval() for sampling (scripts/eval_3dfront.py:395)")
+
     _set_batch_stats_fn = None   # name of the library's echo_*_set_batch_stats for this handle type
 
     def _apply_mode(self):
@@ -150,6 +160,7 @@ class GraphTripleConvNet(_SpecModule):
     def forward(self, obj_vecs, pred_vecs, edges):
         """eval(): running statistics (folded into the Linears).  train(): ``forward_batch_stats``."""
         if self.training:
+            self._check_train_values()
             return self.forward_batch_stats(obj_vecs, pred_vecs, edges)
         return self._run(obj_vecs, pred_vecs, edges, batch_stats=False)
 
@@ -471,6 +482,7 @@ class UNet1DModel(_SpecModule):
         """box_t (N,8), obj_embed (N,640), triples (T,3) i64, timesteps (N,) i64 -> (N,8,1).  ``context`` is accepted
         and ignored exactly as the reference ignores it in crossattn mode (denoise_net.py:791-792).  Under train() box_graph_cov's
         BatchNorm1d layers use the statistics of the batch (forward values of get_loss_iter's denoiser call)."""
+        self._check_train_values()
         _lib.require_cuda(box_t, obj_embed, triples, timesteps)
         n = box_t.shape[0]
         box_t = box_t.float().contiguous()
@@ -608,6 +620,7 @@ class UNet3DModel(_SpecModule):
         """x (N,3,16,16,16), obj_embed (N,1,1280), triples (T,3) i64, timesteps (N,) i64 -> e_t like x.  ``context``
         is accepted and ignored as in the reference ("we dont use the previous context", openai_model_3d.py:843-844).  Under train()
         shape_code_graph_cov's BatchNorm1d layers use the statistics of the batch (forward values of p_losses' denoiser call)."""
+        self._check_train_values()
         n, x, obj_embed = self._prep(x, obj_embed, triples)
         timesteps = timesteps.to(torch.int64).contiguous()
         self._ensure(n, triples.shape[0])

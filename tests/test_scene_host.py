@@ -363,3 +363,22 @@ def test_select_sdfs_greedy_matches_the_reference():
         scene.Sg2ScDiffModel(enc, None, diffusion_bs=16).select_sdfs(o2s, objs, triples, sdfs, uc, c, sample_type="balance")
     with pytest.raises(_lib.EchoError, match="sorted by scene"):
         scene.Sg2ScDiffModel(enc, None, diffusion_bs=64).select_sdfs(torch.tensor([1, 0, 1, 0]), objs[:4], triples[:0], sdfs[:4], uc[:4], c[:4])
+
+
+def test_classes_handed_to_the_reference_refuse_train_mode():
+    """integrate.patch_reference gives the reference subclasses with train_forward_values = False: in train() mode they raise before
+    anything is computed (the reference's training loop needs an autograd tape), while the package's own classes -- the SGDiff
+    facade's -- compute the training forward's values."""
+    class Patched(modules.GraphTripleConvNet):
+        train_forward_values = False
+    m = Patched(64, 16, num_layers=1, hidden_dim=32, residual=True, mlp_normalization="batch")
+    m.train()
+    with pytest.raises(_lib.EchoError, match="inside the patched reference"):
+        m(torch.zeros(4, 64), torch.zeros(3, 16), torch.zeros(3, 2, dtype=torch.int64))
+    m.eval()
+    with pytest.raises(_lib.EchoError, match="CUDA"):
+        m(torch.zeros(4, 64), torch.zeros(3, 16), torch.zeros(3, 2, dtype=torch.int64))
+    own = modules.GraphTripleConvNet(64, 16, num_layers=1, hidden_dim=32, residual=True, mlp_normalization="batch")
+    own.train()
+    with pytest.raises(_lib.EchoError, match="CUDA"):                           # goes on to the (CUDA-only) batch-statistics forward
+        own(torch.zeros(4, 64), torch.zeros(3, 16), torch.zeros(3, 2, dtype=torch.int64))
