@@ -13,7 +13,8 @@ denoiser_kwargs)`` under ``DiffusionPoint(**layout_branch.diffusion_kwargs)`` (e
 ``DiffusionUNet(unet.params)`` with the DDPM schedule of ``model.params`` and the VQ-VAE of ``vq_cfg`` / ``vq_ckpt``
 (echo2shape.py:62-85, 174-190; model_utils.py:7-32), ``ddim_steps = 100`` (7 when ``misc.debug == 1``, echo2shape.py:116-120).
 
-``train()`` + ``forward_mani`` compute the VALUES of the training forward (losses on batch statistics; ``with_vq_encoder=True``
+``save`` / ``state_dict(epoch, counter)`` write the reference's checkpoint format (a file the unmodified reference loads with
+strict=True after a ``load_networks`` round trip).  ``train()`` + ``forward_mani`` compute the VALUES of the training forward (losses on batch statistics; ``with_vq_encoder=True``
 for the shape branch's VQ-VAE encode); the backward pass is outside this path.
 """
 from __future__ import annotations
@@ -76,6 +77,7 @@ class SGDiff:
         self.type_, self.vocab, self.with_angles, self.diff_opt = type, vocab, with_angles, diff_opt
         self.epoch, self.counter = 0, 0
         self.precision, self._config_dir = precision, config_dir
+        self._foreign, self._foreign_opt, self._foreign_vqvae = {}, None, None
 
         layout_only = type == "echolayout"
         self.encoder = modules.SceneEncoder.from_vocab(vocab, embedding_dim=64, gconv_num_layers=5, residual=residual,
@@ -159,6 +161,13 @@ class SGDiff:
             self.epoch = info["epoch"]
         if info["counter"] is not None:
             self.counter = info["counter"]
+        # what the checkpoint holds besides this facade's components -- parameters of reference sub-modules that never run on this
+        # path (obj_embeddings_dc, pred_embeddings_dc, ...), the VQ-VAE encoder of a decode-only facade, the optimizer
+        # state: kept so that save() writes a checkpoint the reference loads with strict=True
+        owned = tuple(self.encoder.reference_prefixes()) + ("LayoutDiff.df.model.", "LayoutDiff.df.module.model.")
+        self._foreign = {k: v for k, v in ckpt.items() if torch.is_tensor(v) and not k.startswith(owned)}
+        self._foreign_opt = ckpt.get("opt")
+        self._foreign_vqvae = {k: v for k, v in ckpt.get("vqvae", {}).items()} if "vqvae" in ckpt else None
         return info
 
     def to(self, device):
@@ -210,5 +219,26 @@ class SGDiff:
                                  encoded_dec_text_feat, encoded_dec_rel_feat, dec_objs_to_scene, missing_nodes, manipulated_nodes,
                                  dec_angles)
 
-    def save(self, *args, **kwargs):
-        raise EchoError("SGDiff.save writes optimizer state of the training loop: outside the B200 sampling path")
+    def state_dict(self, epoch, counter, optimizer_state=None) -> dict:
+        """Sg2ScDiffModel.state_dict(epoch, counter) / Sg2BoxDiffModel's (model/EchoScene.py:534-544): the checkpoint dictionary the
+        reference's ``SGDiff.load_networks`` (SGDiff.py:49-84) reads -- flat keys of the scene model (this facade's encoder under its
+        reference names, the layout denoiser under ``LayoutDiff.df.model.``), ``epoch``, ``counter``, ``opt``, and for the full model
+        ``vqvae`` / ``shape_df`` (keys under ``diffusion_net.``, DiffusionUNet, network.py:17).  Tensors of reference sub-modules this
+        path never runs, and the optimizer state, are passed through from the checkpoint this facade was loaded from
+        (``load_networks``); without one they are absent and the reference needs ``strict=False`` / ``restart_optim=True``."""
+        out = {k: v.detach().cpu() for k, v in getattr(self, "_foreign", {}).items()}
+        out.update({k: v.detach().cpu() for k, v in self.encoder.state_dict().items()})
+        out.update({"LayoutDiff.df.model." + k: v.detach().cpu() for k, v in self.unet1d.state_dict().items()})
+        opt = optimizer_state if optimizer_state is not None else getattr(self, "_foreign_opt", None)
+        out.update({"epoch": epoch, "counter": counter, "opt": opt if opt is not None else {}})
+        if self.unet3d is not None:
+            vq = dict(getattr(self, "_foreign_vqvae", None) or {})
+            vq.update({k: v.detach().cpu() for k, v in self.vqvae.state_dict().items()})
+            out["vqvae"] = vq
+            out["shape_df"] = {"diffusion_net." + k: v.detach().cpu() for k, v in self.unet3d.state_dict().items()}
+        return out
+
+    def save(self, exp, outf, epoch, counter=None, optimizer_state=None):
+        """SGDiff.save (SGDiff.py:123-129): <exp>/<outf>/model<epoch>.pth in the reference's checkpoint format."""
+        os.makedirs(os.path.join(exp, outf), exist_ok=True)
+        torch.save(self.state_dict(epoch, counter, optimizer_state), os.path.join(exp, outf, "model{}.pth".format(epoch)))

@@ -111,3 +111,56 @@ def test_config_access_helpers():
     cfg = {"a": {"b": NS(c=[1, 2], d=None)}}
     assert sgdiff._get(cfg, "a.b.c") == [1, 2] and sgdiff._get(cfg, "a.b.d", 5) == 5 and sgdiff._get(cfg, "a.x.y", "z") == "z"
     assert sgdiff._plain({"k": (1, 2), "n": {"m": 3}}) == {"k": [1, 2], "n": {"m": 3}}
+
+
+import os  # noqa: E402
+
+_REF_INSTALLED = os.path.isdir(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "model"))
+
+
+@pytest.mark.skipif(not _REF_INSTALLED, reason="baseline/_ref (the reference copy) is not installed")
+def test_checkpoint_round_trip_through_the_unmodified_reference(tmp_path):
+    """SGDiff.save / load_networks against the reference's own: the UNMODIFIED reference SGDiff('echolayout') (reduced layout width,
+    CPU) writes a checkpoint with its own save(); the B200 facade loads it, saves it again; the two files hold the same dictionary
+    (keys, tensors, epoch, counter, optimizer state) and the reference restores itself from the facade's file with strict=True."""
+    import importlib
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import refbind_check as rb
+    rb.setup_reference()
+    cfg = rb.load_yaml(os.path.join(rb.REF, "config", "full_mp.yaml"))
+    cfg.hyper.device, cfg.hyper.batch_size = "cpu", 16
+    cfg.hyper.logs_dir = cfg.hyper.results_dir = str(tmp_path / "logs")
+    cfg.layout_branch.denoiser_kwargs.model_channels = 64                      # keeps the files small; the format does not depend on it
+    vocab = {"object_idx_to_name": ["_scene_"] + [f"c{i}" for i in range(35)], "pred_idx_to_name": ["in"] + [f"p{i}" for i in range(15)],
+             "object_idx_to_name_grained": ["x"]}
+    RefSGDiff = importlib.import_module("model.SGDiff").SGDiff
+    torch.manual_seed(3)
+    ref = RefSGDiff("echolayout", cfg, vocab, replace_latent=True, with_changes=True, residual=True, gconv_pooling="avg", with_angles=True,
+                    clip=True, separated=False)
+    ref.counter = 123
+    (tmp_path / "exp" / "checkpoint").mkdir(parents=True)
+    ref.save(str(tmp_path / "exp"), "checkpoint", 7, counter=123)              # the reference's own writer
+    mine = sgdiff.SGDiff("echolayout", cfg, vocab, replace_latent=True, residual=True, clip=True, config_dir=os.path.join(rb.REF, "config"))
+    info = mine.load_networks(str(tmp_path / "exp"), 7)
+    assert (mine.epoch, mine.counter) == (7, 123) and info["loaded"]["unet1d"] > 0
+    mine.save(str(tmp_path / "exp2"), "checkpoint", 7, counter=123)
+    a = torch.load(tmp_path / "exp" / "checkpoint" / "model7.pth", map_location="cpu", weights_only=False)
+    b = torch.load(tmp_path / "exp2" / "checkpoint" / "model7.pth", map_location="cpu", weights_only=False)
+    assert set(a) == set(b)
+    for k, v in a.items():
+        if torch.is_tensor(v):
+            assert torch.equal(v, b[k]), k
+    assert (b["epoch"], b["counter"]) == (7, 123) and b["opt"]["param_groups"] == a["opt"]["param_groups"]
+    want = {k: v.clone() for k, v in torch.nn.Module.state_dict(ref.diff).items()}
+    with torch.no_grad():
+        for p in ref.diff.parameters():
+            p.zero_()
+    ref.load_networks(str(tmp_path / "exp2"), 7, strict=True, restart_optim=False)     # the reference's own reader, strict
+    for k, v in torch.nn.Module.state_dict(ref.diff).items():
+        assert torch.equal(v, want[k]), k
+    # a facade that was never loaded writes its own components only (the reference then needs strict=False / restart_optim=True)
+    fresh = sgdiff.SGDiff("echolayout", cfg, vocab, replace_latent=True, residual=True, clip=True, config_dir=os.path.join(rb.REF, "config"))
+    sd = fresh.state_dict(1, 2)
+    assert sd["opt"] == {} and sd["epoch"] == 1 and "LayoutDiff.df.model.out.2.weight" in sd and "vqvae" not in sd
