@@ -37,6 +37,22 @@ def test_single_gpu_line():
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
 
 
+def test_round2_single_gpu_line_has_the_secondary_figures():
+    """The round's final default line (profiles/r2_bench_n1.json): contract keys, the reference on the same box as cpu_baseline, and
+    every secondary figure without an error entry."""
+    d = _line("r2_bench_n1.json")
+    for k in BASE + ["cpu_baseline", "layout_branch", "launch_mode"]:
+        assert k in d, k
+    assert d["steps"] >= 100 and d["cpu_baseline"]["kind"] == "reference" and "replayed CUDA graph" in d["launch_mode"]
+    for k in ("layout_branch_batched_64_scenes", "sdf_to_mesh", "parity_mode_x3", "config3_n32_s250", "config4_scene_sharded",
+              "gpu_eager_baseline", "scene_encode", "vqvae_decode", "full_chain_seconds_per_scene", "full_chain_seconds_per_scene_batched"):
+        assert k in d and "error" not in d[k], k
+    assert d["layout_branch"]["executor"]["persistent_kernel_steps"] > 0
+    assert d["layout_branch_batched_64_scenes"]["value"] > 3 * d["layout_branch"]["value"]          # batching pays on the layout branch
+    assert d["full_chain_seconds_per_scene_batched"]["total"] < d["full_chain_seconds_per_scene"]["total"]
+    assert d["roofline"]["traffic_source"].startswith("static")
+
+
 @pytest.mark.parametrize("name,n", [("r1_bench_n2.json", 2), ("r1_bench_n4.json", 4), ("r1_bench_n8.json", 8)])
 def test_multi_gpu_lines(name, n):
     d = _line(name)
