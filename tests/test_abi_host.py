@@ -40,6 +40,16 @@ def test_bad_arguments_return_codes():
     assert L.echo_op_conv3d(None, 1, 1, 1, 1, 16, None, None, 16, 5, 1, 1, None, 0, None) == -1
     with pytest.raises(_lib.EchoError):
         _lib.check(-1)
+    # the entry points added in round 2 validate before they touch the device
+    assert L.echo_gcn_train_create(C.byref(h), None, None, 0, None, 0) < 0 and b"gcn_train" in L.echo_last_error()
+    assert L.echo_gcn_train_forward(None, None, None, None, None, None, None) < 0
+    assert L.echo_gcn_train_backward(None, None, None, None, None, None, None) < 0
+    for fn in (L.echo_layout_set_batch_stats, L.echo_shape_set_batch_stats, L.echo_scene_set_batch_stats):
+        assert fn(None, 1) < 0 and b"set_batch_stats" in L.echo_last_error()
+    assert L.echo_mesh_workspace_bytes(1) == -1 and L.echo_mesh_workspace_bytes(1000) == -1 and L.echo_mesh_workspace_bytes(64) > 4 * 4 * 64 ** 3
+    assert L.echo_mesh_marching_cubes(None, 64, 0.02, None, 0, None, 0, None, None, 0, None) < 0 and b"marching_cubes" in L.echo_last_error()
+    assert L.echo_optimizer_create(None, None, 0) < 0
+    L.echo_gcn_train_destroy(None)                                              # destroying nothing is allowed
 
 
 def test_state_dict_keys_match_reference_specs():
